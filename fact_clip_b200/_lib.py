@@ -1,0 +1,91 @@
+"""ctypes binding of libfactk.so (include/factk.h).  No fallback: if the library is missing or a call
+fails, a RuntimeError is raised -- the product never routes through a CPU or library path."""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libfactk.so')
+
+F32, BF16 = 0, 1
+MAX_SRC = 4
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class Src(C.Structure):
+    _fields_ = [('A', vp), ('a_dtype', i32), ('lda', i32), ('a_slot', i32), ('K', i32), ('row_off', i32),
+                ('pos_ld', i32), ('pos_d', i32), ('ldw', i32), ('gather', vp), ('pos', vp), ('pos_idx', vp),
+                ('W', vp), ('w_bstride', i64)]
+
+
+class Gemm(C.Structure):
+    _fields_ = [('B', i32), ('slot', i32), ('N', i32), ('nsrc', i32), ('len', vp), ('src', Src * MAX_SRC),
+                ('bias', vp), ('bias_bstride', i64), ('alpha', f32), ('relu', i32), ('res', vp),
+                ('res_dtype', i32), ('ldres', i32), ('Y', vp), ('y_dtype', i32), ('ldy', i32)]
+
+
+_SIGS = {
+    'factk_version': (i32, []),
+    'factk_last_error': (C.c_char_p, []),
+    'factk_device_check': (i32, []),
+    'factk_gemm': (i32, [C.POINTER(Gemm), vp]),
+    'factk_softmax_splice': (i32, [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp]),
+    'factk_layernorm': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, f32, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
+    'factk_l2norm': (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, f32, vp]),
+    'factk_row_softmax': (i32, [vp, i32, vp, i32, i32, i32, vp, i32, f32, vp]),
+    'factk_mha_tokens': (i32, [vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    'factk_attn_rows_ws_floats': (C.c_size_t, [i32, i32, i32, i32, i32]),
+    'factk_attn_rows': (i32, [vp, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]),
+    'factk_col_softmax_ws_floats': (C.c_size_t, [i32, i32, i32, i32]),
+    'factk_col_softmax_apply': (i32, [vp, i32, vp, i32, i32, vp, i32, vp, i32, i32, i32, vp, i32, i32, vp, vp]),
+    'factk_tdu_segment': (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    'factk_segment_mean': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp]),
+    'factk_gru_bidir': (i32, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
+    'factk_gather_rows': (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp]),
+    'factk_fuse_eval': (i32, [vp, vp, i32, i32, vp, vp, i32, f32, vp, i32, i32, vp, i32, i32, vp]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def load():
+    """Load libfactk.so once; raise loudly if it is absent (build with ``python -m fact_clip_b200.build``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} not found: build it with `python -m fact_clip_b200.build` '
+                               '(there is no CPU / PyTorch fallback for the FACT forward)')
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise RuntimeError(f'factk {what} failed ({rc}): {load().factk_last_error().decode()}')
+
+
+def dt(t):
+    return _DT[t.dtype]
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

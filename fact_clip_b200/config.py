@@ -146,3 +146,20 @@ def tiny(f='m', block='iuU', fpos=False, F=32, A=32, H=64, M=12, layers=4, a_lay
 
 PRESETS = dict(gtea=gtea, breakfast=breakfast, havid_view0_lh_pt_holdout=havid_view0_lh_pt_holdout,
                epic_shape=epic_shape)
+
+
+_BLOCK_KEYS = ['hid_dim', 'dropout', 'a', 'a_nhead', 'a_ffdim', 'a_layers', 'a_dim', 'f', 'f_layers', 'f_ln', 'f_dim', 'f_ngp']
+
+
+def hparams(cfg, in_dim, n_classes):
+    """Flatten the cfg keys the forward reads (after the constructor's update_from) into plain dicts."""
+    blocks = []
+    for t in cfg.FACT.block:
+        node = {'i': cfg.Bi, 'u': cfg.Bu, 'U': cfg.BU}[t]
+        bc = {k: node[k] for k in _BLOCK_KEYS}
+        bc['type'] = t
+        blocks.append(bc)
+    clip = cfg.CLIP if 'CLIP' in cfg else None
+    return dict(in_dim=in_dim, n_classes=n_classes, blocks=blocks, ntoken=cfg.FACT.ntoken, fpos=bool(cfg.FACT.fpos),
+                mwt=float(cfg.FACT.mwt), trans=bool(cfg.FACT.trans),
+                temp=float(clip.temp) if clip is not None else 0.07)

@@ -1,0 +1,365 @@
+// Attention cores that are not plain GEMMs.
+//  * mha_tokens: token self-attention (M <= ~300 tokens), one CTA per (head, video).
+//  * attn_rows: tokens attend the T frames of their video (SCALayer cross attention), split over T
+//    with a deterministic log-sum-exp combine.
+//  * col_softmax_apply: softmax over the frame/segment axis of a logit matrix and the weighted row sum
+//    (the f2a direction of X2Y_map), again split over rows and combined in fixed order.
+// All softmax state lives in registers; fp32 throughout.
+#include "common.cuh"
+
+namespace factk {
+
+constexpr int SPLIT_ROWS = 512;   // rows of a video handled by one CTA in the split kernels
+
+// ------------------------------------------------------------------------------------------------
+// nn.MultiheadAttention core for self attention among tokens (models/basic.py:437,500).
+template <int DH>
+__global__ void __launch_bounds__(128) mha_tokens_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                                                         const float* __restrict__ V, int ld, float* __restrict__ O,
+                                                         int ldo, int M) {
+    extern __shared__ float sm[];
+    float* Ks = sm;
+    float* Vs = sm + (size_t)M * DH;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const size_t base = (size_t)b * M;
+    for (int i = threadIdx.x; i < M * DH; i += blockDim.x) {
+        const int m = i / DH, d = i % DH;
+        Ks[i] = K[(base + m) * ld + h * DH + d];
+        Vs[i] = V[(base + m) * ld + h * DH + d];
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)DH);
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        float q[DH], acc[DH];
+#pragma unroll
+        for (int d = 0; d < DH; ++d) { q[d] = Q[(base + m) * ld + h * DH + d] * scale; acc[d] = 0.f; }
+        float mx = -INFINITY, l = 0.f;
+        for (int j = 0; j < M; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) s = fmaf(q[d], Ks[j * DH + d], s);
+            const float nm = fmaxf(mx, s);
+            const float corr = __expf(mx - nm), p = __expf(s - nm);
+            l = l * corr + p;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, Vs[j * DH + d], acc[d] * corr);
+            mx = nm;
+        }
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) O[(base + m) * ldo + h * DH + d] = acc[d] * inv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SCALayer cross attention core (models/basic.py:507-514): partial over one split of rows.
+// partial layout: [B][nhead][nsplit][M][DH+2] = (running max, running sum, acc[DH]).
+template <int DH>
+__global__ void __launch_bounds__(320) attn_rows_partial_kernel(const float* __restrict__ Q, int ldq,
+                                                                const void* __restrict__ Kx, const void* __restrict__ Vx,
+                                                                int kv_dtype, int ldkv, float* __restrict__ part,
+                                                                int slot, const int32_t* __restrict__ len, int M,
+                                                                int nhead, int nsplit) {
+    constexpr int TR = 32;   // rows staged per iteration
+    __shared__ __align__(16) float Ks[TR][DH];
+    __shared__ __align__(16) float Vs[TR][DH];
+    const int sp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int len_b = len ? min(len[b], slot) : slot;
+    const int r0 = sp * SPLIT_ROWS;
+    if (r0 >= len_b) return;
+    const int r1 = min(r0 + SPLIT_ROWS, len_b);
+    const int m = threadIdx.x;
+    const bool active = m < M;
+    const float scale = rsqrtf((float)DH);
+    float q[DH], acc[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+        q[d] = active ? Q[((size_t)b * M + m) * ldq + h * DH + d] * scale : 0.f;
+        acc[d] = 0.f;
+    }
+    float mx = -INFINITY, l = 0.f;
+    for (int t0 = r0; t0 < r1; t0 += TR) {
+        const int nr = min(TR, r1 - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < TR * DH; i += blockDim.x) {
+            const int r = i / DH, d = i % DH;
+            float kv = 0.f, vv = 0.f;
+            if (r < nr) {
+                const size_t off = ((size_t)b * slot + t0 + r) * ldkv + h * DH + d;
+                kv = ld_elem(Kx, kv_dtype, off);
+                vv = ld_elem(Vx, kv_dtype, off);
+            }
+            Ks[r][d] = kv;
+            Vs[r][d] = vv;
+        }
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll 1
+        for (int r8 = 0; r8 < nr; r8 += 8) {
+            float s[8];
+            float bm = mx;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int d = 0; d < DH; d += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(&Ks[(r8 + j) & (TR - 1)][d]);
+                    a = fmaf(q[d], k4.x, a); a = fmaf(q[d + 1], k4.y, a);
+                    a = fmaf(q[d + 2], k4.z, a); a = fmaf(q[d + 3], k4.w, a);
+                }
+                s[j] = (r8 + j < nr) ? a : -INFINITY;
+                bm = fmaxf(bm, s[j]);
+            }
+            const float corr = __expf(mx - bm);
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[d] *= corr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p = __expf(s[j] - bm);   // exp(-inf) = 0 for padded rows
+                l += p;
+#pragma unroll
+                for (int d = 0; d < DH; d += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(&Vs[(r8 + j) & (TR - 1)][d]);
+                    acc[d] = fmaf(p, v4.x, acc[d]); acc[d + 1] = fmaf(p, v4.y, acc[d + 1]);
+                    acc[d + 2] = fmaf(p, v4.z, acc[d + 2]); acc[d + 3] = fmaf(p, v4.w, acc[d + 3]);
+                }
+            }
+            mx = bm;
+        }
+    }
+    if (active) {
+        float* o = part + ((((size_t)b * nhead + h) * nsplit + sp) * M + m) * (DH + 2);
+        o[0] = mx;
+        o[1] = l;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) o[2 + d] = acc[d];
+    }
+}
+
+template <int DH>
+__global__ void attn_rows_combine_kernel(const float* __restrict__ part, float* __restrict__ O, int ldo, int slot,
+                                         const int32_t* __restrict__ len, int M, int nhead, int nsplit) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int len_b = len ? min(len[b], slot) : slot;
+    const int ns = (len_b + SPLIT_ROWS - 1) / SPLIT_ROWS;
+    for (int i = threadIdx.x; i < M * DH; i += blockDim.x) {
+        const int m = i / DH, d = i % DH;
+        const float* p0 = part + (((size_t)b * nhead + h) * nsplit * M + m) * (DH + 2);
+        float gm = -INFINITY;
+        for (int s = 0; s < ns; ++s) gm = fmaxf(gm, p0[(size_t)s * M * (DH + 2)]);
+        float l = 0.f, a = 0.f;
+        for (int s = 0; s < ns; ++s) {
+            const float* p = p0 + (size_t)s * M * (DH + 2);
+            const float w = __expf(p[0] - gm);
+            l = fmaf(p[1], w, l);
+            a = fmaf(p[2 + d], w, a);
+        }
+        O[((size_t)b * M + m) * ldo + h * DH + d] = a / l;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// f2a direction of X2Y_map (models/basic.py:373-379): softmax over rows + weighted row sum.
+// stats partial: [B][nsplit][M][2]; stats: [B][M][2] = (max, 1/sum).
+__global__ void __launch_bounds__(256) col_stats_partial_kernel(const float* __restrict__ L, int ldl,
+                                                                float* __restrict__ sp_out, int slot,
+                                                                const int32_t* __restrict__ len, int M, int nsplit) {
+    const int sp = blockIdx.x, b = blockIdx.y;
+    const int len_b = len ? min(len[b], slot) : slot;
+    const int r0 = sp * SPLIT_ROWS;
+    if (r0 >= len_b) return;
+    const int r1 = min(r0 + SPLIT_ROWS, len_b);
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        float mx = -INFINITY, l = 0.f;
+        for (int t = r0; t < r1; ++t) {
+            const float v = L[((size_t)b * slot + t) * ldl + m];
+            const float nm = fmaxf(mx, v);
+            l = l * __expf(mx - nm) + __expf(v - nm);
+            mx = nm;
+        }
+        float* o = sp_out + (((size_t)b * nsplit + sp) * M + m) * 2;
+        o[0] = mx;
+        o[1] = l;
+    }
+}
+
+__global__ void col_stats_combine_kernel(const float* __restrict__ sp_in, float* __restrict__ stats, int slot,
+                                         const int32_t* __restrict__ len, int M, int nsplit) {
+    const int b = blockIdx.x;
+    const int len_b = len ? min(len[b], slot) : slot;
+    const int ns = (len_b + SPLIT_ROWS - 1) / SPLIT_ROWS;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        float gm = -INFINITY;
+        for (int s = 0; s < ns; ++s) gm = fmaxf(gm, sp_in[(((size_t)b * nsplit + s) * M + m) * 2]);
+        float l = 0.f;
+        for (int s = 0; s < ns; ++s) {
+            const float* p = sp_in + (((size_t)b * nsplit + s) * M + m) * 2;
+            l = fmaf(p[1], __expf(p[0] - gm), l);
+        }
+        stats[((size_t)b * M + m) * 2] = gm;
+        stats[((size_t)b * M + m) * 2 + 1] = 1.f / l;
+    }
+}
+
+// partial weighted sums: part[b][split][m][e] = sum_{t in split} p[t,m] X[t,e]; 32 tokens x 128 channels per CTA.
+__global__ void __launch_bounds__(256) col_apply_partial_kernel(const float* __restrict__ L, int ldl,
+                                                                const float* __restrict__ stats,
+                                                                const void* __restrict__ X, int x_dtype, int ldx,
+                                                                float* __restrict__ part, float* __restrict__ P, int ldp,
+                                                                int slot, const int32_t* __restrict__ len, int M, int E,
+                                                                int nsplit, int etiles) {
+    constexpr int TR = 32, TM = 32, TE = 128;
+    __shared__ float Ps[TR][TM + 1];
+    __shared__ __align__(16) float Xs[TR][TE];
+    const int sp = blockIdx.x, b = blockIdx.z;
+    const int mt = blockIdx.y / etiles, et = blockIdx.y % etiles;
+    const int len_b = len ? min(len[b], slot) : slot;
+    const int r0 = sp * SPLIT_ROWS;
+    if (r0 >= len_b) return;
+    const int r1 = min(r0 + SPLIT_ROWS, len_b);
+    const int tid = threadIdx.x;
+    const int tm = tid >> 5, te = tid & 31;   // 8 groups of 4 tokens, 32 groups of 4 channels
+    const int m0 = mt * TM, e0 = et * TE;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int t0 = r0; t0 < r1; t0 += TR) {
+        const int nr = min(TR, r1 - t0);
+        __syncthreads();
+        for (int i = tid; i < TR * TM; i += 256) {
+            const int r = i / TM, mm = i % TM;
+            float p = 0.f;
+            if (r < nr && m0 + mm < M) {
+                const size_t row = (size_t)b * slot + t0 + r;
+                const float* st = stats + ((size_t)b * M + m0 + mm) * 2;
+                p = __expf(L[row * ldl + m0 + mm] - st[0]) * st[1];
+                if (P != nullptr && et == 0) P[row * ldp + m0 + mm] = p;
+            }
+            Ps[r][mm] = p;
+        }
+        for (int i = tid; i < TR * TE; i += 256) {
+            const int r = i / TE, ee = i % TE;
+            Xs[r][ee] = (r < nr && e0 + ee < E) ? ld_elem(X, x_dtype, ((size_t)b * slot + t0 + r) * ldx + e0 + ee) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < TR; ++r) {
+            const float4 x4 = *reinterpret_cast<const float4*>(&Xs[r][te * 4]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float p = Ps[r][tm * 4 + i];
+                acc[i][0] = fmaf(p, x4.x, acc[i][0]); acc[i][1] = fmaf(p, x4.y, acc[i][1]);
+                acc[i][2] = fmaf(p, x4.z, acc[i][2]); acc[i][3] = fmaf(p, x4.w, acc[i][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + tm * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = e0 + te * 4 + j;
+            if (e < E) part[(((size_t)b * nsplit + sp) * M + m) * E + e] = acc[i][j];
+        }
+    }
+}
+
+__global__ void col_apply_combine_kernel(const float* __restrict__ part, float* __restrict__ out, int ldo, int slot,
+                                         const int32_t* __restrict__ len, int M, int E, int nsplit) {
+    const int b = blockIdx.y;
+    const int len_b = len ? min(len[b], slot) : slot;
+    const int ns = (len_b + SPLIT_ROWS - 1) / SPLIT_ROWS;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * E) return;
+    const int m = i / E, e = i % E;
+    float a = 0.f;
+    for (int s = 0; s < ns; ++s) a += part[(((size_t)b * nsplit + s) * M + m) * E + e];
+    out[((size_t)b * M + m) * ldo + e] = a;
+}
+
+static inline int nsplit_of(int slot) { return (slot + SPLIT_ROWS - 1) / SPLIT_ROWS; }
+
+}  // namespace factk
+
+using namespace factk;
+
+extern "C" int factk_mha_tokens(const float* Q, const float* K, const float* V, int ld, float* O, int ldo, int B, int M,
+                                int nhead, int dh, void* stream) {
+    FACTK_REQUIRE(Q && K && V && O && B > 0 && M > 0 && nhead > 0, "factk_mha_tokens: bad args");
+    const size_t smem = (size_t)2 * M * dh * sizeof(float);
+    FACTK_REQUIRE(smem <= 200 * 1024, "factk_mha_tokens: M*dh too large for shared memory (%zu B)", smem);
+    dim3 grid(nhead, B);
+#define LAUNCH(DH)                                                                                              \
+    do {                                                                                                        \
+        cudaFuncSetAttribute(mha_tokens_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   \
+        mha_tokens_kernel<DH><<<grid, 128, smem, (cudaStream_t)stream>>>(Q, K, V, ld, O, ldo, M);               \
+    } while (0)
+    switch (dh) {
+        case 4: LAUNCH(4); break;
+        case 8: LAUNCH(8); break;
+        case 16: LAUNCH(16); break;
+        case 32: LAUNCH(32); break;
+        case 64: LAUNCH(64); break;
+        default: FACTK_REQUIRE(false, "factk_mha_tokens: head dim %d unsupported (4/8/16/32/64)", dh);
+    }
+#undef LAUNCH
+    return check_launch("factk_mha_tokens");
+}
+
+extern "C" size_t factk_attn_rows_ws_floats(int B, int slot, int M, int nhead, int dh) {
+    return (size_t)B * nhead * nsplit_of(slot) * M * (dh + 2);
+}
+
+extern "C" int factk_attn_rows(const float* Q, int ldq, const void* Kx, const void* Vx, int kv_dtype, int ldkv, float* O,
+                               int ldo, int B, int slot, const int32_t* len, int M, int nhead, int dh, float* ws,
+                               void* stream) {
+    FACTK_REQUIRE(Q && Kx && Vx && O && ws && B > 0 && slot > 0 && M > 0, "factk_attn_rows: bad args");
+    FACTK_REQUIRE(M <= 320, "factk_attn_rows: at most 320 tokens (got %d)", M);
+    const int ns = nsplit_of(slot);
+    dim3 grid(ns, nhead, B), cgrid(nhead, B);
+    const int threads = ((M + 31) / 32) * 32;
+#define LAUNCH(DH)                                                                                                     \
+    do {                                                                                                               \
+        attn_rows_partial_kernel<DH><<<grid, threads, 0, (cudaStream_t)stream>>>(Q, ldq, Kx, Vx, kv_dtype, ldkv, ws,    \
+                                                                                 slot, len, M, nhead, ns);             \
+        attn_rows_combine_kernel<DH><<<cgrid, 256, 0, (cudaStream_t)stream>>>(ws, O, ldo, slot, len, M, nhead, ns);     \
+    } while (0)
+    switch (dh) {
+        case 4: LAUNCH(4); break;
+        case 8: LAUNCH(8); break;
+        case 16: LAUNCH(16); break;
+        case 32: LAUNCH(32); break;
+        case 64: LAUNCH(64); break;
+        default: FACTK_REQUIRE(false, "factk_attn_rows: head dim %d unsupported (4/8/16/32/64)", dh);
+    }
+#undef LAUNCH
+    return check_launch("factk_attn_rows");
+}
+
+extern "C" size_t factk_col_softmax_ws_floats(int B, int slot, int M, int E) {
+    const size_t ns = nsplit_of(slot);
+    return (size_t)B * ns * M * 2 + (size_t)B * M * 2 + (size_t)B * ns * M * E;
+}
+
+extern "C" int factk_col_softmax_apply(const float* L, int ldl, const void* X, int x_dtype, int ldx, float* out, int ldo,
+                                       float* P, int ldp, int B, int slot, const int32_t* len, int M, int E, float* ws,
+                                       void* stream) {
+    FACTK_REQUIRE(L && X && out && ws && B > 0 && slot > 0 && M > 0 && E > 0, "factk_col_softmax_apply: bad args");
+    const int ns = nsplit_of(slot);
+    float* sp = ws;
+    float* stats = sp + (size_t)B * ns * M * 2;
+    float* part = stats + (size_t)B * M * 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    col_stats_partial_kernel<<<dim3(ns, B), 256, 0, st>>>(L, ldl, sp, slot, len, M, ns);
+    col_stats_combine_kernel<<<B, 256, 0, st>>>(sp, stats, slot, len, M, ns);
+    const int etiles = (E + 127) / 128, mtiles = (M + 31) / 32;
+    col_apply_partial_kernel<<<dim3(ns, mtiles * etiles, B), 256, 0, st>>>(L, ldl, stats, X, x_dtype, ldx, part, P, ldp,
+                                                                           slot, len, M, E, ns, etiles);
+    col_apply_combine_kernel<<<dim3((M * E + 255) / 256, B), 256, 0, st>>>(part, out, ldo, slot, len, M, E, ns);
+    return check_launch("factk_col_softmax_apply");
+}

@@ -1,0 +1,121 @@
+// Prob fusion + argmax of the last block: Block._eval (models/blocks.py:242-261) and
+// FACT_CLIP.eval_with_clip (models/blocks.py:854-887).  One warp per frame; the per-video token mask
+// (argmax != null class) is rebuilt in shared memory by every CTA, so there is no host sync on
+// len(action_loc) (blocks.py:252,862).
+#include "common.cuh"
+
+namespace factk {
+
+constexpr int EV_WARPS = 8, EV_FRAMES = 64, EV_MAXM = 512;
+
+__global__ void __launch_bounds__(EV_WARPS * 32) fuse_eval_kernel(const float* __restrict__ aclogit,
+                                                                  const float* __restrict__ attn, int lda, int attn_slot,
+                                                                  const int32_t* __restrict__ seg_label,
+                                                                  const float* __restrict__ flogit, int ldf, float weight,
+                                                                  int64_t* __restrict__ pred, int slot,
+                                                                  const int32_t* __restrict__ len, int M, int C,
+                                                                  int chunks_per_video) {
+    __shared__ int valid[EV_MAXM];
+    __shared__ int any_valid;
+    const int b = blockIdx.x / chunks_per_video;
+    const int t0 = (blockIdx.x % chunks_per_video) * EV_FRAMES;
+    const int T = len ? min(len[b], slot) : slot;
+    if (t0 >= T) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) any_valid = 0;
+    __syncthreads();
+    // token-side: class argmax over C+1 logits (first index on ties); valid = not the null class
+    for (int m = w; m < M; m += EV_WARPS) {
+        const float* row = aclogit + ((size_t)b * M + m) * (C + 1);
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c <= C; c += 32) {
+            const float v = row[c];
+            if (v > best) { best = v; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) {
+            valid[m] = (bi != C);
+            if (bi != C) any_valid = 1;
+        }
+    }
+    __syncthreads();
+    const bool has_action = any_valid != 0;
+
+    for (int f = w; f < EV_FRAMES; f += EV_WARPS) {
+        const int t = t0 + f;
+        if (t >= T) break;
+        const size_t row = (size_t)b * slot + t;
+        const float* fl = flogit + row * (size_t)ldf;
+        // frame-branch softmax statistics
+        float fm = -INFINITY;
+        for (int c = lane; c < C; c += 32) fm = fmaxf(fm, fl[c]);
+        fm = warp_max(fm);
+        float fs = 0.f;
+        for (int c = lane; c < C; c += 32) fs += __expf(fl[c] - fm);
+        fs = 1.f / warp_sum(fs);
+
+        int mstar = -1;
+        float qm = 0.f, qs = 0.f;
+        const float* qrow = nullptr;
+        if (has_action) {
+            const size_t arow = (size_t)b * attn_slot + (seg_label ? seg_label[row] : t);
+            const float* ar = attn + arow * (size_t)lda;
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int m = lane; m < M; m += 32) {
+                if (!valid[m]) continue;
+                const float v = ar[m];
+                if (v > best) { best = v; bi = m; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            mstar = bi;
+            qrow = aclogit + ((size_t)b * M + mstar) * (C + 1);
+            qm = -INFINITY;
+            for (int c = lane; c < C; c += 32) qm = fmaxf(qm, qrow[c]);
+            qm = warp_max(qm);
+            for (int c = lane; c < C; c += 32) qs += __expf(qrow[c] - qm);
+            qs = 1.f / warp_sum(qs);
+        }
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            float p = __expf(fl[c] - fm) * fs;
+            if (has_action) p = (1.f - weight) * (__expf(qrow[c] - qm) * qs) + weight * p;
+            if (p > best) { best = p; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) pred[row] = (int64_t)bi;
+    }
+}
+
+}  // namespace factk
+
+using namespace factk;
+
+extern "C" int factk_fuse_eval(const float* action_clogit, const float* attn, int lda, int attn_slot,
+                               const int32_t* seg_label, const float* flogit, int ldf, float weight, int64_t* pred, int B,
+                               int slot, const int32_t* len, int M, int C, void* stream) {
+    FACTK_REQUIRE((M == 0 || action_clogit) && flogit && pred && B > 0 && slot > 0 && C > 0, "factk_fuse_eval: bad args");
+    FACTK_REQUIRE(M >= 0 && M <= EV_MAXM, "factk_fuse_eval: at most %d tokens", EV_MAXM);
+    FACTK_REQUIRE(M == 0 || attn != nullptr, "factk_fuse_eval: attention required when M > 0");
+    const int cpv = (slot + EV_FRAMES - 1) / EV_FRAMES;
+    fuse_eval_kernel<<<(unsigned)(cpv * B), EV_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        action_clogit, attn, lda, attn_slot, seg_label, flogit, ldf, weight, pred, slot, len, M, C, cpv);
+    return check_launch("factk_fuse_eval");
+}

@@ -1,0 +1,163 @@
+// Row-local operations: class-softmax splice, LayerNorm, L2 normalise, row softmax, row gather.
+// One warp per row; rows are [B][slot][ld] with len[b] valid rows per video.
+#include "common.cuh"
+
+namespace factk {
+
+constexpr int ROWS_PER_CTA = 8;   // 8 warps
+
+__device__ __forceinline__ bool row_of_warp(int B, int slot, const int32_t* len, int& b, int& t) {
+    const long row = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+    if (row >= (long)B * slot) return false;
+    b = (int)(row / slot);
+    t = (int)(row % slot);
+    return t < (len ? len[b] : slot);
+}
+
+// Block.process_feature (models/blocks.py:195-202) + the TDU argmax (blocks.py:420-421).
+__global__ void __launch_bounds__(256) softmax_splice_kernel(void* X, int dtype, int B, int slot, const int32_t* len,
+                                                             int ld, int H, int C, float* clogit, int32_t* pred) {
+    int b, t;
+    if (!row_of_warp(B, slot, len, b, t)) return;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)b * slot + t;
+    const size_t base = row * (size_t)ld + (H - C);
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, ld_elem(X, dtype, base + c));
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += __expf(ld_elem(X, dtype, base + c) - mx);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float best = -1.f;
+    int besti = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+        const float l = ld_elem(X, dtype, base + c);
+        const float p = __expf(l - mx) * inv;
+        clogit[row * (size_t)C + c] = l;
+        st_elem(X, dtype, base + c, p);
+        if (p > best) { best = p; besti = c; }   // strict > keeps the first index within a lane
+    }
+    if (pred) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) pred[row] = besti;
+    }
+}
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* X, int x_dtype, int ldx, const void* R, int r_dtype,
+                                                        int ldr, const float* w, const float* bb, float eps, int relu,
+                                                        void* Y, int y_dtype, int ldy, int B, int slot,
+                                                        const int32_t* len, int E) {
+    int b, t;
+    if (!row_of_warp(B, slot, len, b, t)) return;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)b * slot + t;
+    float s = 0.f;
+    for (int c = lane; c < E; c += 32) {
+        float v = ld_elem(X, x_dtype, row * ldx + c);
+        if (R) v += ld_elem(R, r_dtype, row * ldr + c);
+        s += v;
+    }
+    const float mu = warp_sum(s) / E;
+    float q = 0.f;
+    for (int c = lane; c < E; c += 32) {
+        float v = ld_elem(X, x_dtype, row * ldx + c);
+        if (R) v += ld_elem(R, r_dtype, row * ldr + c);
+        q += (v - mu) * (v - mu);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / E + eps);
+    for (int c = lane; c < E; c += 32) {
+        float v = ld_elem(X, x_dtype, row * ldx + c);
+        if (R) v += ld_elem(R, r_dtype, row * ldr + c);
+        v = (v - mu) * rstd * w[c] + bb[c];
+        if (relu) v = fmaxf(v, 0.f);
+        st_elem(Y, y_dtype, row * ldy + c, v);
+    }
+}
+
+__global__ void __launch_bounds__(256) l2norm_kernel(const void* X, int x_dtype, int ldx, void* Y, int y_dtype, int ldy,
+                                                     int B, int slot, const int32_t* len, int E, float eps) {
+    int b, t;
+    if (!row_of_warp(B, slot, len, b, t)) return;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)b * slot + t;
+    float q = 0.f;
+    for (int c = lane; c < E; c += 32) {
+        const float v = ld_elem(X, x_dtype, row * ldx + c);
+        q += v * v;
+    }
+    const float inv = 1.f / fmaxf(sqrtf(warp_sum(q)), eps);
+    for (int c = lane; c < E; c += 32) st_elem(Y, y_dtype, row * ldy + c, ld_elem(X, x_dtype, row * ldx + c) * inv);
+}
+
+__global__ void __launch_bounds__(256) row_softmax_kernel(const float* L, int ldl, float* P, int ldp, int B, int slot,
+                                                          const int32_t* len, int M, float scale) {
+    int b, t;
+    if (!row_of_warp(B, slot, len, b, t)) return;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)b * slot + t;
+    float mx = -INFINITY;
+    for (int c = lane; c < M; c += 32) mx = fmaxf(mx, L[row * ldl + c] * scale);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int c = lane; c < M; c += 32) sum += __expf(L[row * ldl + c] * scale - mx);
+    const float inv = 1.f / warp_sum(sum);
+    for (int c = lane; c < M; c += 32) P[row * ldp + c] = __expf(L[row * ldl + c] * scale - mx) * inv;
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* in, int ldi, int in_slot, const int32_t* idx,
+                                                          float* out, int ldo, int B, int slot, const int32_t* len, int E) {
+    int b, t;
+    if (!row_of_warp(B, slot, len, b, t)) return;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)b * slot + t;
+    const size_t src = (size_t)b * in_slot + idx[row];
+    for (int c = lane; c < E; c += 32) out[row * ldo + c] = in[src * ldi + c];
+}
+
+static inline unsigned row_grid(int B, int slot) { return (unsigned)(((long)B * slot + ROWS_PER_CTA - 1) / ROWS_PER_CTA); }
+
+}  // namespace factk
+
+using namespace factk;
+
+extern "C" int factk_softmax_splice(void* X, int dtype, int B, int slot, const int32_t* len, int ld, int H, int C,
+                                    float* clogit_out, int32_t* pred_out, void* stream) {
+    FACTK_REQUIRE(X && clogit_out && B > 0 && slot > 0 && C > 0 && C <= H && H <= ld, "factk_softmax_splice: bad args");
+    softmax_splice_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(X, dtype, B, slot, len, ld, H, C, clogit_out, pred_out);
+    return check_launch("factk_softmax_splice");
+}
+
+extern "C" int factk_layernorm(const void* X, int x_dtype, int ldx, const void* R, int r_dtype, int ldr, const float* w,
+                               const float* b, float eps, int relu, void* Y, int y_dtype, int ldy, int B, int slot,
+                               const int32_t* len, int E, void* stream) {
+    FACTK_REQUIRE(X && Y && w && b && B > 0 && slot > 0 && E > 0, "factk_layernorm: bad args");
+    layernorm_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(X, x_dtype, ldx, R, r_dtype, ldr, w, b, eps, relu, Y, y_dtype, ldy, B, slot, len, E);
+    return check_launch("factk_layernorm");
+}
+
+extern "C" int factk_l2norm(const void* X, int x_dtype, int ldx, void* Y, int y_dtype, int ldy, int B, int slot,
+                            const int32_t* len, int E, float eps, void* stream) {
+    FACTK_REQUIRE(X && Y && B > 0 && slot > 0 && E > 0, "factk_l2norm: bad args");
+    l2norm_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(X, x_dtype, ldx, Y, y_dtype, ldy, B, slot, len, E, eps);
+    return check_launch("factk_l2norm");
+}
+
+extern "C" int factk_row_softmax(const float* L, int ldl, float* P, int ldp, int B, int slot, const int32_t* len, int M,
+                                 float scale, void* stream) {
+    FACTK_REQUIRE(L && P && B > 0 && slot > 0 && M > 0, "factk_row_softmax: bad args");
+    row_softmax_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(L, ldl, P, ldp, B, slot, len, M, scale);
+    return check_launch("factk_row_softmax");
+}
+
+extern "C" int factk_gather_rows(const float* in, int ldi, int in_slot, const int32_t* idx, float* out, int ldo, int B,
+                                 int slot, const int32_t* len, int E, void* stream) {
+    FACTK_REQUIRE(in && idx && out && B > 0 && slot > 0 && E > 0, "factk_gather_rows: bad args");
+    gather_rows_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(in, ldi, in_slot, idx, out, ldo, B, slot, len, E);
+    return check_launch("factk_gather_rows");
+}

@@ -1,0 +1,380 @@
+"""Host-side orchestration of the FACT / FACT_CLIP forward over the factk kernels.
+
+One call runs a whole BATCH of videos: frames are packed as [B, slot, C] "rows" tensors (slot = the
+longest video rounded up to 128), tokens as [B, M, C], segments reuse the frame slots with a
+device-side count per video.  Nothing in here synchronises with the host: the data-dependent
+segment count S of the TDU blocks (models/blocks.py:420-426 does a D2H + Python parse) stays on the
+device, grids are sized for the worst case and exit early.
+
+Algebraic restructuring used (exact in real arithmetic, fp32 rounding-level differences only):
+  * X2Y_map in the f2a direction (models/basic.py:349-389): K/V projections of all T frames are never
+    formed.  logit = (Wk^T yq) . (x + pos) + yq.bk, and attn @ (X Wv^T + bv) = (attn @ X) Wv^T + bv.
+  * X2Y_map in the a2f direction: logit = (x + pos) . (Wq^T xk) + bq.xk, and
+    Y_W [y, attn @ xv] = y Wy^T + attn @ (xv Wa^T).
+"""
+import math
+
+import torch
+
+from . import ops
+from .ops import S
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class FactEngine:
+    def __init__(self, module, hp, clip, mode='bf16'):
+        assert mode in ('bf16', 'fp32')
+        self.m, self.hp, self.clip, self.mode = module, hp, clip, mode
+        self.act = torch.bfloat16 if mode == 'bf16' else torch.float32
+        self._bufs = {}
+        self._wcache, self._wsig = {}, None
+
+    # ------------------------------------------------------------------ memory / weights
+    def buf(self, name, shape, dtype=torch.float32):
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.dev)
+            self._bufs[key] = t
+        return t
+
+    def _refresh_weights(self):
+        params = dict(self.m.named_parameters())
+        params.update(dict(self.m.named_buffers()))
+        sig = tuple((k, v.data_ptr(), v._version) for k, v in params.items())
+        if sig != self._wsig:
+            self._wsig, self._wcache, self._p = sig, {}, params
+        self.dev = next(self.m.parameters()).device
+
+    def p(self, name):
+        t = self._p[name]
+        assert t.dtype == torch.float32 and t.is_cuda, f'{name}: fp32 CUDA master parameter expected'
+        return t.detach()
+
+    def derived(self, key, fn):
+        t = self._wcache.get(key)
+        if t is None:
+            with torch.no_grad():
+                t = fn().contiguous()
+            self._wcache[key] = t
+        return t
+
+    def taps(self, name):      # Conv1d weight (Cout, Cin, k) -> [k][Cout][Cin]
+        return self.derived(('taps', name), lambda: self.p(name).permute(2, 0, 1))
+
+    def tr(self, name):        # W^T
+        return self.derived(('tr', name), lambda: self.p(name).t())
+
+    def cat(self, *names):
+        return self.derived(('cat',) + names, lambda: torch.cat([self.p(n) for n in names], 0))
+
+    # ------------------------------------------------------------------ frame branch
+    def frame_branch(self, pfx, bc, x, in_map, tag):
+        """MSTCN / MSTCN2 (models/basic.py:200-220, 263-281) + process_feature (models/blocks.py:195-202).
+        x: [B, slot, Din].  Returns (frame_feature [B,slot,H] act dtype, frame_clogit fp32, pred int32)."""
+        B, slot, F, H, Lr, C = self.B, self.slot, bc['f_dim'], bc['hid_dim'], bc['f_layers'], self.hp['n_classes']
+        ln = self.len
+        fa, fb = self.buf('f_a', (B, slot, F), self.act), self.buf('f_b', (B, slot, F), self.act)
+        m2 = bc['f'] == 'm2'
+        other = lambda t: fb if t is fa else fa
+        if in_map:
+            w = pfx + ('conv_1x1_in' if m2 else 'conv_1x1')
+            ops.gemm([S(x, self.taps(w + '.weight')[0])], F, fa, len=ln, bias=self.p(w + '.bias'))
+            cur, nxt = fa, fb
+        else:
+            cur, nxt = x, fa
+        for i in range(Lr):
+            if not m2:
+                q = f'{pfx}layers.{i}.'
+                w3, d = self.taps(q + 'conv_dilated.weight'), 2 ** i
+                tmp = self.buf('f_tmp', (B, slot, F), self.act)
+                ops.gemm([S(cur, w3[k], off=(k - 1) * d) for k in range(3)], F, tmp, len=ln,
+                         bias=self.p(q + 'conv_dilated.bias'), relu=True)
+                ops.gemm([S(tmp, self.taps(q + 'conv_1x1.weight')[0])], F, nxt, len=ln,
+                         bias=self.p(q + 'conv_1x1.bias'), res=cur)
+            else:
+                tmp = self.buf('f_tmp2', (B, slot, 2 * F), self.act)
+                for j, (nm, d) in enumerate(((f'{pfx}conv_dilated_1.{i}', 2 ** (Lr - 1 - i)), (f'{pfx}conv_dilated_2.{i}', 2 ** i))):
+                    w3 = self.taps(nm + '.weight')
+                    ops.gemm([S(cur, w3[k], off=(k - 1) * d) for k in range(3)], F, tmp[:, :, j * F:(j + 1) * F],
+                             len=ln, bias=self.p(nm + '.bias'))
+                ops.gemm([S(tmp, self.taps(f'{pfx}conv_fusion.{i}.weight')[0])], F, nxt, len=ln,
+                         bias=self.p(f'{pfx}conv_fusion.{i}.bias'), relu=True, res=cur)
+            cur, nxt = nxt, other(nxt)
+        out = self.buf('frame_' + tag, (B, slot, H), self.act)
+        ops.gemm([S(cur, self.taps(pfx + 'conv_out.weight')[0])], H, out, len=ln, bias=self.p(pfx + 'conv_out.bias'))
+        clogit = self.buf('fclogit_' + tag, (B, slot, C))
+        pred = self.buf('fpred_' + tag, (B, slot), torch.int32)
+        ops.softmax_splice(out, C, clogit, pred, len=ln)
+        return out, clogit, pred
+
+    # ------------------------------------------------------------------ token side
+    def _mha_self(self, pfx, x, pos, nhead, tag):
+        """q = k = x + pos, v = x through a packed in_proj (basic.py:437,500); returns attn output before out_proj."""
+        B, M, A = x.shape
+        W, bias = self.p(pfx + 'in_proj_weight'), self.p(pfx + 'in_proj_bias')
+        qkv = self.buf('tok_qkv', (B, M, 3 * A))
+        ops.gemm([S(x, W[:2 * A], pos=pos)], 2 * A, qkv[:, :, :2 * A], bias=bias[:2 * A])
+        ops.gemm([S(x, W[2 * A:])], A, qkv[:, :, 2 * A:], bias=bias[2 * A:])
+        o = self.buf('tok_o', (B, M, A))
+        ops.mha_tokens(qkv[:, :, :A], qkv[:, :, A:2 * A], qkv[:, :, 2 * A:], o, nhead)
+        return o
+
+    def _ffn_ln(self, q, x, n_a, n_b, tag):
+        B, M, A = x.shape
+        ff = self.p(q + 'linear1.weight').shape[0]
+        h = self.buf('tok_ff', (B, M, ff))
+        ops.gemm([S(x, self.p(q + 'linear1.weight'))], ff, h, bias=self.p(q + 'linear1.bias'), relu=True)
+        t = self.buf('tok_t', (B, M, A))
+        ops.gemm([S(h, self.p(q + 'linear2.weight'))], A, t, bias=self.p(q + 'linear2.bias'), res=x)
+        ops.layernorm(t, self.p(q + n_a), self.p(q + n_b), x)
+
+    def sca_decoder(self, pfx, bc, frame, tag):
+        """SCADecoder over SCALayer (models/basic.py:542-557, 494-523): tokens attend frames. -> [B,M,H] fp32."""
+        B, slot, M, A, H, nh = self.B, self.slot, self.hp['ntoken'], bc['a_dim'], bc['hid_dim'], bc['a_nhead']
+        qpos = self.p('action_query')[:, 0]
+        tgt = self.buf('tok_x', (B, M, A))
+        tgt.zero_()
+        t = self.buf('tok_t', (B, M, A))
+        kv = self.buf('sca_kv', (B, slot, 2 * A), self.act)
+        ws = self.buf('attn_ws', (max(ops.attn_rows_ws(B, slot, M, nh, A // nh), 1),))
+        fpos = self.frame_pos
+        for i in range(bc['a_layers']):
+            q = f'{pfx}layers.{i}.'
+            o = self._mha_self(q + 'self_attn.', tgt, qpos, nh, tag)
+            ops.gemm([S(o, self.p(q + 'self_attn.out_proj.weight'))], A, t, bias=self.p(q + 'self_attn.out_proj.bias'), res=tgt)
+            ops.layernorm(t, self.p(q + 'norm1.weight'), self.p(q + 'norm1.bias'), tgt)
+            # cross attention: q from tokens, k from frames (+pos), v from frames
+            c = q + 'multihead_attn.'
+            cb = self.p(c + 'in_proj_bias')
+            if (c + 'in_proj_weight') in self._p:
+                W = self.p(c + 'in_proj_weight')
+                wq, wk, wv = W[:A], W[A:2 * A], W[2 * A:]
+            else:
+                wq, wk, wv = self.p(c + 'q_proj_weight'), self.p(c + 'k_proj_weight'), self.p(c + 'v_proj_weight')
+            cq = self.buf('tok_cq', (B, M, A))
+            ops.gemm([S(tgt, wq, pos=qpos)], A, cq, bias=cb[:A])
+            ops.gemm([S(frame, wk, pos=fpos)], A, kv[:, :, :A], len=self.len, bias=cb[A:2 * A])
+            ops.gemm([S(frame, wv)], A, kv[:, :, A:], len=self.len, bias=cb[2 * A:])
+            o = self.buf('tok_o', (B, M, A))
+            ops.attn_rows(cq, kv[:, :, :A], kv[:, :, A:], o, nh, ws, len=self.len)
+            ops.gemm([S(o, self.p(c + 'out_proj.weight'))], A, t, bias=self.p(c + 'out_proj.bias'), res=tgt)
+            ops.layernorm(t, self.p(q + 'norm2.weight'), self.p(q + 'norm2.bias'), tgt)
+            self._ffn_ln(q, tgt, 'norm3.weight', 'norm3.bias', tag)
+        ops.layernorm(tgt, self.p(pfx + 'norm.weight'), self.p(pfx + 'norm.bias'), t)
+        out = self.buf('action_' + tag, (B, M, H))
+        ops.gemm([S(t, self.p(pfx + 'out_linear.weight'))], H, out, bias=self.p(pfx + 'out_linear.bias'))
+        return out
+
+    def sa_decoder(self, pfx, bc, x, tag):
+        """SADecoder over SALayer (models/basic.py:578-593, 429-452). x: [B,M,A] fp32 -> [B,M,H] fp32."""
+        B, M, A, H, nh = self.B, self.hp['ntoken'], bc['a_dim'], bc['hid_dim'], bc['a_nhead']
+        qpos = self.p('action_query')[:, 0]
+        t = self.buf('tok_t', (B, M, A))
+        for i in range(bc['a_layers']):
+            q = f'{pfx}layers.{i}.'
+            o = self._mha_self(q + 'multihead_attn.', x, qpos, nh, tag)
+            ops.gemm([S(o, self.p(q + 'multihead_attn.out_proj.weight'))], A, t,
+                     bias=self.p(q + 'multihead_attn.out_proj.bias'), res=x)
+            ops.layernorm(t, self.p(q + 'norm1.weight'), self.p(q + 'norm1.bias'), x)
+            self._ffn_ln(q, x, 'norm2.weight', 'norm2.bias', tag)
+        out = self.buf('action_' + tag, (B, M, H))
+        ops.gemm([S(x, self.p(pfx + 'out_linear.weight'))], H, out, bias=self.p(pfx + 'out_linear.bias'))
+        return out
+
+    def token_splice(self, action, tag):
+        C = self.hp['n_classes']
+        clogit = self.buf('aclogit_' + tag, (self.B, self.hp['ntoken'], C + 1))
+        ops.softmax_splice(action, C + 1, clogit)
+        return clogit
+
+    # ------------------------------------------------------------------ cross attention
+    def f2a(self, pfx, bc, rows, rlen, pos_idx, action, tag, want_attn):
+        """X2Y_map with X = rows (frames or segments), Y = tokens (basic.py:349-389). -> tokens [B,M,A] fp32,
+        attn_logit [B,slot,Mp] (row = x, col = token), attn (or None)."""
+        B, slot, M, A, H = self.B, self.slot, self.hp['ntoken'], bc['a_dim'], bc['hid_dim']
+        Mp = _round_up(M, 4)
+        qpos = self.p('action_query')[:, 0]
+        alpha = 1.0 / math.sqrt(H)
+        yq = self.buf('x2y_tokH', (B, M, H))
+        ops.gemm([S(action, self.p(pfx + 'Y_Q.weight'), pos=qpos)], H, yq, bias=self.p(pfx + 'Y_Q.bias'))
+        qt = self.buf('x2y_qt', (B, M, H))                                  # alpha * Wk^T yq
+        ops.gemm([S(yq, self.tr(pfx + 'X_K.weight'))], H, qt, alpha=alpha)
+        cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * yq . bk
+        ops.gemm([S(yq, self.p(pfx + 'X_K.bias')[None, :])], 1, cb, alpha=alpha)
+        logit = self.buf('f2a_logit_' + tag, (B, slot, Mp))
+        ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0])
+        attn = self.buf('f2a_attn_' + tag, (B, slot, Mp)) if want_attn else None
+        xbar = self.buf('x2y_xbar', (B, M, H))
+        ws = self.buf('col_ws', (ops.col_softmax_ws(B, slot, M, H),))
+        ops.col_softmax_apply(logit, rows, xbar, M, ws, attn=attn, len=rlen, E=H)
+        feat = self.buf('x2y_tokH', (B, M, H))
+        ops.gemm([S(xbar, self.p(pfx + 'X_V.weight'))], H, feat, bias=self.p(pfx + 'X_V.bias'))
+        W = self.p(pfx + 'Y_W.weight')
+        out = self.buf('tok_x', (B, M, A))
+        ops.gemm([S(action, W[:, :H]), S(feat, W[:, H:])], A, out, bias=self.p(pfx + 'Y_W.bias'))
+        return out, logit, attn
+
+    def a2f(self, pfx, bc, action, rows, rlen, pos_idx, tag):
+        """X2Y_map with X = tokens, Y = rows (frames or segments). -> rows [B,slot,F] act dtype,
+        attn_logit [B,slot,Mp], attn [B,slot,Mp] (row = y, col = token)."""
+        B, slot, M, F, H = self.B, self.slot, self.hp['ntoken'], bc['f_dim'], bc['hid_dim']
+        Mp = _round_up(M, 4)
+        qpos = self.p('action_query')[:, 0]
+        alpha = 1.0 / math.sqrt(H)
+        xk = self.buf('x2y_tokH', (B, M, H))
+        ops.gemm([S(action, self.p(pfx + 'X_K.weight'), pos=qpos)], H, xk, bias=self.p(pfx + 'X_K.bias'))
+        kt = self.buf('x2y_qt', (B, M, H))                                  # alpha * Wq^T xk
+        ops.gemm([S(xk, self.tr(pfx + 'Y_Q.weight'))], H, kt, alpha=alpha)
+        cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * xk . bq
+        ops.gemm([S(xk, self.p(pfx + 'Y_Q.bias')[None, :])], 1, cb, alpha=alpha)
+        logit = self.buf('a2f_logit_' + tag, (B, slot, Mp))
+        ops.gemm([S(rows, kt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0])
+        attn = self.buf('a2f_attn_' + tag, (B, slot, Mp))
+        ops.row_softmax(logit, attn, M, len=rlen)
+        xv = self.buf('x2y_xv', (B, M, H))
+        ops.gemm([S(action, self.p(pfx + 'X_V.weight'))], H, xv, bias=self.p(pfx + 'X_V.bias'))
+        W = self.p(pfx + 'Y_W.weight')                                      # [F, 2H] = [Wy | Wa]
+        vt = self.buf('x2y_vt', (B, F, Mp))                                 # vt[b,f,m] = sum_h Wa[f,h] xv[b,m,h]
+        ops.gemm([S(W[None, :, H:], xv)], M, vt)
+        out = self.buf('a2f_out', (B, slot, F), self.act)
+        ops.gemm([S(rows, W[:, :H]), S(attn, vt, K=M)], F, out, len=rlen, bias=self.p(pfx + 'Y_W.bias'))
+        return out, logit, attn
+
+    # ------------------------------------------------------------------ blocks
+    def input_block(self, i, bc, x, st):
+        pfx = f'block_list.{i}.'
+        frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, x, True, f'b{i}')
+        action = self.sca_decoder(pfx + 'action_branch.', bc, frame, f'b{i}')
+        st['action_clogit'] = self.token_splice(action, f'b{i}')
+        return frame, action
+
+    def update_block(self, i, bc, frame, action, st):
+        pfx, tag = f'block_list.{i}.', f'b{i}'
+        tok, st['f2a_attn_logit'], st['f2a_attn'] = self.f2a(pfx + 'f2a_layer.', bc, frame, self.len, None, action, tag, self.keep)
+        action = self.sa_decoder(pfx + 'action_branch.', bc, tok, tag)
+        st['action_clogit'] = self.token_splice(action, tag)
+        fr, st['a2f_attn_logit'], st['a2f_attn'] = self.a2f(pfx + 'a2f_layer.', bc, action, frame, self.len, None, tag)
+        frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, fr, False, tag)
+        return frame, action
+
+    def update_block_tdu(self, i, bc, frame, action, pred, st):
+        """UpdateBlockTDU.forward (models/blocks.py:417-485) with the segmentation kept on device."""
+        pfx, tag = f'block_list.{i}.', f'b{i}'
+        B, slot, H, F, C = self.B, self.slot, bc['hid_dim'], bc['f_dim'], self.hp['n_classes']
+        Hh = H // 2
+        I32 = torch.int32
+        seg_label, seg_start = self.buf('seg_label_' + tag, (B, slot), I32), self.buf('seg_start_' + tag, (B, slot), I32)
+        seg_len, seg_center = self.buf('seg_len_' + tag, (B, slot), I32), self.buf('seg_center_' + tag, (B, slot), I32)
+        nseg = self.buf('nseg_' + tag, (B,), I32)
+        ops.tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=self.len)
+        st.update(seg_label=seg_label, seg_lens=seg_len, nseg=nseg, tdu_pred=pred)
+        seg0 = self.buf('seg0', (B, slot, H))
+        ops.segment_mean(frame, seg0, seg_start, seg_len, nseg)
+        g = pfx + 'seg_update.'
+        gi = self.buf('gru_gi', (B, slot, 6 * Hh))
+        ops.gemm([S(seg0, self.cat(g + 'weight_ih_l0', g + 'weight_ih_l0_reverse'))], 6 * Hh, gi, len=nseg,
+                 bias=self.cat(g + 'bias_ih_l0', g + 'bias_ih_l0_reverse'))
+        seg1 = self.buf('seg1', (B, slot, H))
+        ops.gru_bidir(gi, self.p(g + 'weight_hh_l0'), self.p(g + 'bias_hh_l0'), self.p(g + 'weight_hh_l0_reverse'),
+                      self.p(g + 'bias_hh_l0_reverse'), seg1, nseg, relu=True)
+        seg2 = self.buf('seg2', (B, slot, H), self.act)
+        ops.gemm([S(seg1, self.p(pfx + 'seg_combine.weight'))], H, seg2, len=nseg, bias=self.p(pfx + 'seg_combine.bias'))
+        st['seg_clogit'] = self.buf('seg_clogit_' + tag, (B, slot, C))
+        ops.softmax_splice(seg2, C, st['seg_clogit'], None, len=nseg)
+        pidx = seg_center if self.frame_pos is not None else None
+        tok, st['f2a_attn_logit'], st['f2a_attn_seg'] = self.f2a(pfx + 'f2a_layer.', bc, seg2, nseg, pidx, action, tag, self.keep)
+        action = self.sa_decoder(pfx + 'action_branch.', bc, tok, tag)
+        st['action_clogit'] = self.token_splice(action, tag)
+        seg3, st['a2f_attn_logit'], st['a2f_attn_seg'] = self.a2f(pfx + 'a2f_layer.', bc, action, seg2, nseg, pidx, tag)
+        W = self.p(pfx + 'sf_merge.0.weight')                               # [F, F+H], input = cat[s2f, frame]
+        fr = self.buf('sf_out', (B, slot, F), self.act)
+        ops.gemm([S(seg3, W[:, :F], gather=seg_label), S(frame, W[:, F:])], F, fr, len=self.len,
+                 bias=self.p(pfx + 'sf_merge.0.bias'), relu=True)
+        frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, fr, False, tag)
+        return frame, action
+
+    # ------------------------------------------------------------------ whole forward
+    @torch.no_grad()
+    def run(self, seqs, forced_preds=None, keep=False):
+        """seqs: list of (T_i, in_dim) fp32 CUDA tensors (or one packed [B,slot,D] + lengths via run_packed)."""
+        self._refresh_weights()
+        lengths = [int(s.shape[0]) for s in seqs]
+        B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
+        self.dev = seqs[0].device
+        x = self.buf('input', (B, slot, D))
+        for b, s in enumerate(seqs):
+            x[b, :lengths[b]].copy_(s, non_blocking=True)
+        ln = self.buf('len', (B,), torch.int32)
+        ln.copy_(torch.tensor(lengths, dtype=torch.int32), non_blocking=True)
+        return self.run_packed(x, ln, lengths, forced_preds, keep)
+
+    @torch.no_grad()
+    def run_packed(self, x, ln, lengths, forced_preds=None, keep=False):
+        self._refresh_weights()
+        hp = self.hp
+        self.B, self.slot, self.len, self.keep = x.shape[0], x.shape[1], ln, keep
+        B, slot, M, C, H = self.B, self.slot, hp['ntoken'], hp['n_classes'], hp['blocks'][0]['hid_dim']
+        self.frame_pos = None
+        if hp['fpos']:
+            self.frame_pos = self.derived(('pe', slot, H), lambda: _pos_table(H, slot, self.dev))
+        frame, action, stash, u = x, None, [], 0
+        pred = None
+        for i, bc in enumerate(hp['blocks']):
+            st = {}
+            if bc['type'] == 'i':
+                frame, action = self.input_block(i, bc, frame, st)
+            elif bc['type'] == 'u':
+                frame, action = self.update_block(i, bc, frame, action, st)
+            else:
+                if forced_preds is not None:
+                    fp = self.buf(f'forced_pred_{u}', (B, slot), torch.int32)
+                    for b in range(B):
+                        fp[b, :lengths[b]].copy_(forced_preds[u][b].to(torch.int32), non_blocking=True)
+                    pred = fp
+                frame, action = self.update_block_tdu(i, bc, frame, action, pred, st)
+                u += 1
+            pred = st['pred']
+            st['frame_feature'], st['action_feature'] = frame, action
+            stash.append(st)
+        last = stash[-1]
+        out = dict(blocks=stash, lengths=lengths)
+        if self.clip and 'text_embeddings' in self._p and self._p['text_embeddings'] is not None:
+            P = self.p('frame_projection.projection.0.weight').shape[0]
+            h1 = self.buf('clip_h1', (B, slot, P), self.act)
+            ops.gemm([S(frame, self.p('frame_projection.projection.0.weight'), K=H - C)], P, h1, len=ln,
+                     bias=self.p('frame_projection.projection.0.bias'))
+            ops.layernorm(h1, self.p('frame_projection.projection.1.weight'), self.p('frame_projection.projection.1.bias'),
+                          h1, relu=True, len=ln)
+            emb = self.buf('clip_emb', (B, slot, 512))
+            ops.gemm([S(h1, self.p('frame_projection.projection.4.weight'))], 512, emb, len=ln,
+                     bias=self.p('frame_projection.projection.4.bias'))
+            ops.l2norm(emb, emb, len=ln)
+            flogit = self.buf('clip_logit', (B, slot, C))
+            ops.gemm([S(emb, self.p('text_embeddings'))], C, flogit, len=ln, alpha=1.0 / hp['temp'])
+            out['projected_frame_embeddings'], out['clip_logit'] = emb, flogit
+        else:
+            flogit = last['frame_clogit']
+        pred64 = self.buf('pred64', (B, slot), torch.int64)
+        if 'a2f_attn' in last:
+            ops.fuse_eval(last['action_clogit'], last['a2f_attn'], flogit, hp['mwt'], pred64, M, C, len=ln)
+        elif 'a2f_attn_seg' in last:
+            ops.fuse_eval(last['action_clogit'], last['a2f_attn_seg'], flogit, hp['mwt'], pred64, M, C,
+                          seg_label=last['seg_label'], len=ln)
+        else:
+            ops.fuse_eval(None, None, flogit, hp['mwt'], pred64, 0, C, len=ln)
+        out['pred'] = pred64
+        return out
+
+
+def _pos_table(d_model, length, device):
+    """Sinusoid table of PositionalEncoding (models/basic.py:90-102), built on the host once per length."""
+    pe = torch.zeros(length, d_model)
+    position = torch.arange(0, length, dtype=torch.float).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.to(device)

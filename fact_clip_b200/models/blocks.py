@@ -1,0 +1,232 @@
+"""FACT / FACT_CLIP drop-in modules (counterpart of fact_clip/models/blocks.py in the reference).
+
+Same constructors, cfg keys, ``state_dict`` keys and ``forward(seq_list, label_list, compute_loss)``
+outputs as the reference (FACT: blocks.py:19-135, FACT_CLIP: blocks.py:504-920); the forward itself
+runs as hand-written sm_100a kernels through ``FactEngine`` -- batched over the whole ``seq_list``,
+with no host synchronisation until the predictions are copied back.
+
+Differences from the reference that a caller can observe:
+  * ``seq_list`` is processed as ONE batch instead of a Python loop over videos (blocks.py:113-116).
+  * the unused transcript (``torch_class_label_to_segment_label``, basic.py:38-54 -- a per-frame
+    Python loop) is not computed when ``FACT.trans`` is False.
+  * stashed attributes (``block.frame_clogit`` ...) are produced on request (``net.stash_video(i)``)
+    rather than on every call; they refer to the LAST video of the batch by default, like the
+    reference where each video overwrites the previous one.
+  * training (``compute_loss=True``) is not implemented yet: SURVEY.md section 8(f) rank 1.
+"""
+import torch
+import torch.nn as nn
+
+from .. import config as cfgmod
+from ..engine import FactEngine
+from . import basic
+
+try:  # the reference refuses to build FACT_CLIP without transformers (blocks.py:526-527); we do not need it
+    import transformers  # noqa: F401
+    CLIP_AVAILABLE = True
+except ImportError:  # pragma: no cover
+    CLIP_AVAILABLE = False
+
+
+class FeatureProjection(nn.Module):
+    """Linear -> LayerNorm -> ReLU -> Dropout -> Linear, then L2-normalise (blocks.py:141-175).
+    Parameter holder; the math runs fused in the engine's CLIP head."""
+
+    def __init__(self, feature_dim, clip_dim=512, hidden_dim=512, dropout=0.1):
+        super().__init__()
+        self.feature_dim, self.clip_dim = feature_dim, clip_dim
+        self.projection = nn.Sequential(nn.Linear(feature_dim, hidden_dim), nn.LayerNorm(hidden_dim), nn.ReLU(),
+                                        nn.Dropout(dropout), nn.Linear(hidden_dim, clip_dim))
+
+
+class Block(nn.Module):
+    """Shared factories (blocks.py:204-240) and the attribute stash the loss / viz code reads."""
+
+    def __str__(self):
+        a2f = self.a2f_layer if hasattr(self, 'a2f_layer') else None
+        f2a = self.f2a_layer if hasattr(self, 'f2a_layer') else None
+        return (f'{type(self).__name__}(\n  f:{self.frame_branch},\n  a:{self.action_branch},\n'
+                f'  a2f:{a2f},\n  f2a:{f2a}\n)')
+
+    __repr__ = __str__
+
+    @staticmethod
+    def create_fbranch(cfg, in_dim=None, f_inmap=False):
+        in_dim = cfg.f_dim if in_dim is None else in_dim
+        if cfg.f == 'm':
+            return basic.MSTCN(in_dim, cfg.f_dim, cfg.hid_dim, cfg.f_layers, dropout=cfg.dropout, ln=cfg.f_ln,
+                               ngroup=cfg.f_ngp, in_map=f_inmap)
+        if cfg.f == 'm2':
+            return basic.MSTCN2(in_dim, cfg.f_dim, cfg.hid_dim, cfg.f_layers, dropout=cfg.dropout, ln=cfg.f_ln,
+                                ngroup=cfg.f_ngp, in_map=f_inmap)
+        raise ValueError(f"frame branch {cfg.f!r}: only 'm' (MSTCN) and 'm2' (MSTCN++) exist (blocks.py:208-213)")
+
+    @staticmethod
+    def create_abranch(cfg):
+        if cfg.a == 'sa':
+            layer = basic.SALayer(cfg.a_dim, cfg.a_nhead, dim_feedforward=cfg.a_ffdim, dropout=cfg.dropout, attn_dropout=cfg.dropout)
+            return basic.SADecoder(cfg.a_dim, cfg.a_dim, cfg.hid_dim, layer, cfg.a_layers, in_map=False)
+        if cfg.a == 'sca':
+            layer = basic.SCALayer(cfg.a_dim, cfg.hid_dim, cfg.a_nhead, cfg.a_ffdim, dropout=cfg.dropout, attn_dropout=cfg.dropout)
+            norm = nn.LayerNorm(cfg.a_dim)
+            return basic.SCADecoder(cfg.a_dim, cfg.a_dim, cfg.hid_dim, layer, cfg.a_layers, norm=norm, in_map=False)
+        if cfg.a in ('gru', 'gru_om'):
+            raise NotImplementedError("action branch 'gru' needs FACT.trans=True: SURVEY 8(f) rank 4")
+        raise ValueError(cfg.a)
+
+    @staticmethod
+    def create_cross_attention(cfg, outdim, kq_pos=True):
+        return basic.X2Y_map(cfg.hid_dim, cfg.hid_dim, outdim, head_dim=cfg.hid_dim, dropout=cfg.dropout, kq_pos=kq_pos)
+
+
+class InputBlock(Block):
+    def __init__(self, cfg, in_dim, nclass):
+        super().__init__()
+        self.cfg, self.nclass = cfg, nclass
+        self.frame_branch = self.create_fbranch(cfg.Bi, in_dim, f_inmap=True)
+        self.action_branch = self.create_abranch(cfg.Bi)
+
+
+class UpdateBlock(Block):
+    def __init__(self, cfg, nclass):
+        super().__init__()
+        self.cfg, self.nclass = cfg, nclass
+        c = cfg.Bu
+        self.frame_branch = self.create_fbranch(c)
+        self.f2a_layer = self.create_cross_attention(c, c.a_dim)
+        self.action_branch = self.create_abranch(c)
+        self.a2f_layer = self.create_cross_attention(c, c.f_dim)
+
+
+class UpdateBlockTDU(Block):
+    def __init__(self, cfg, nclass):
+        super().__init__()
+        self.cfg, self.nclass = cfg, nclass
+        c = cfg.BU
+        self.frame_branch = self.create_fbranch(c)
+        self.seg_update = nn.GRU(c.hid_dim, c.hid_dim // 2, c.s_layers, bidirectional=True)
+        self.seg_combine = nn.Linear(c.hid_dim, c.hid_dim)
+        self.f2a_layer = self.create_cross_attention(c, c.a_dim)
+        self.action_branch = self.create_abranch(c)
+        self.a2f_layer = self.create_cross_attention(c, c.f_dim)
+        self.sf_merge = nn.Sequential(nn.Linear(c.hid_dim + c.f_dim, c.f_dim), nn.ReLU())
+        if c.s_layers != 1:
+            raise NotImplementedError('BU.s_layers != 1 is used by no shipped config')
+
+
+class TDU:
+    """Stand-in for basic.TemporalDownsampleUpsample holding what the loss reads (seg_label, seg_lens)."""
+
+    def __init__(self, seg_label, seg_lens):
+        self.seg_label, self.seg_lens, self.num_seg = seg_label, seg_lens, int(seg_lens.numel())
+
+
+class _FactBase(nn.Module):
+    """Everything FACT and FACT_CLIP share: constructor body, batched forward, stash, save_model."""
+
+    def _build(self, cfg, in_dim, n_classes):
+        self.cfg, self.num_classes, self.in_dim = cfg, n_classes, in_dim
+        base = cfg.Bi
+        self.frame_pe = basic.PositionalEncoding(base.hid_dim, max_len=10000, empty=(not cfg.FACT.fpos))
+        self.channel_masking_dropout = nn.Dropout2d(p=cfg.FACT.cmr)
+        if cfg.FACT.trans:
+            raise NotImplementedError('FACT.trans=True (transcript-conditioned model) is SURVEY 8(f) rank 4')
+        self.action_query = nn.Parameter(torch.randn([cfg.FACT.ntoken, 1, base.a_dim]))
+        return base
+
+    def _build_blocks(self, cfg, in_dim, n_classes, base):
+        blocks = []
+        for t in cfg.FACT.block:
+            if t == 'i':
+                blocks.append(InputBlock(cfg, in_dim, n_classes))
+            elif t == 'u':
+                cfgmod.update_from(cfg.Bu, base, inplace=True)
+                base = cfg.Bu
+                blocks.append(UpdateBlock(cfg, n_classes))
+            elif t == 'U':
+                cfgmod.update_from(cfg.BU, base, inplace=True)
+                base = cfg.BU
+                blocks.append(UpdateBlockTDU(cfg, n_classes))
+            else:
+                raise ValueError(f'FACT.block type {t!r} (the reference handles i/u/U only, blocks.py:38-48)')
+        self.block_list = nn.ModuleList(blocks)
+        self.mcriterion = None
+        self.compute_mode = 'bf16'      # 'bf16' (default) or 'fp32'; see DESIGN.md
+        self._engine = None
+
+    # -------------------------------------------------------------- engine plumbing
+    def engine(self):
+        if self._engine is None or self._engine.mode != self.compute_mode:
+            hp = cfgmod.hparams(self.cfg, self.in_dim, self.num_classes)
+            self._engine = FactEngine(self, hp, clip=isinstance(self, FACT_CLIP), mode=self.compute_mode)
+        return self._engine
+
+    def forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
+        if compute_loss or (self.training and torch.is_grad_enabled() and compute_loss):
+            raise NotImplementedError('compute_loss=True (training step) is not built yet: SURVEY.md 8(f) rank 1')
+        dev = self.action_query.device
+        if dev.type != 'cuda':
+            raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
+        seqs = [s if s.is_cuda else s.to(dev, non_blocking=True) for s in seq_list]
+        out = self.engine().run(seqs, forced_preds=forced_preds, keep=getattr(self, 'keep_attn', False))
+        self._last = out
+        pred = out['pred'].cpu().numpy()            # the one D2H sync of the call (blocks.py:900)
+        self.stash_video(len(seqs) - 1)
+        return [{'pred': pred[b, :T].copy()} for b, T in enumerate(out['lengths'])]
+
+    def stash_video(self, b):
+        """Expose video ``b`` of the last batch through the reference's per-block attributes
+        (blocks.py:305-309, 359-366, 473-483) as views -- shapes (T,1,C), (M,1,C+1), (1,T,M)..."""
+        out = self._last
+        T, M = out['lengths'][b], self.cfg.FACT.ntoken
+        for blk, st in zip(self.block_list, out['blocks']):
+            C = self.num_classes
+            blk.frame_clogit = st['frame_clogit'][b, :T].unsqueeze(1)
+            blk.action_clogit = st['action_clogit'][b].unsqueeze(1)
+            blk.action_feature = st['action_feature'][b, :, :-(C + 1)].unsqueeze(1)
+            if 'nseg' in st:
+                S = int(st['nseg'][b])
+                lab = st['seg_label'][b, :T].long()
+                blk.tdu = TDU(lab, st['seg_lens'][b, :S].long())
+                blk.seg_clogit = st['seg_clogit'][b, :S].unsqueeze(1)
+                blk.a2f_attn_logit = st['a2f_attn_logit'][b, :S, :M].unsqueeze(0)
+                blk.a2f_attn = st['a2f_attn_seg'][b, :S, :M][lab].unsqueeze(0)
+                blk.f2a_attn_logit = st['f2a_attn_logit'][b, :S, :M].t().unsqueeze(0)
+                if st.get('f2a_attn_seg') is not None:
+                    blk.f2a_attn = st['f2a_attn_seg'][b, :S, :M][lab].t().unsqueeze(0)
+            elif 'a2f_attn' in st:
+                blk.a2f_attn_logit = st['a2f_attn_logit'][b, :T, :M].unsqueeze(0)
+                blk.a2f_attn = st['a2f_attn'][b, :T, :M].unsqueeze(0)
+                blk.f2a_attn_logit = st['f2a_attn_logit'][b, :T, :M].t().unsqueeze(0)
+                if st.get('f2a_attn') is not None:
+                    blk.f2a_attn = st['f2a_attn'][b, :T, :M].t().unsqueeze(0)
+        if 'projected_frame_embeddings' in out:
+            self.projected_frame_embeddings = out['projected_frame_embeddings'][b, :T].unsqueeze(1)
+
+    def save_model(self, fname):
+        torch.save(self.state_dict(), fname)
+
+
+class FACT(_FactBase):
+    def __init__(self, cfg, in_dim, n_classes):
+        super().__init__()
+        base = self._build(cfg, in_dim, n_classes)
+        self._build_blocks(cfg, in_dim, n_classes, base)
+
+
+class FACT_CLIP(_FactBase):
+    """FACT + projection of frame features into CLIP text space + zero-shot logit head."""
+
+    def __init__(self, cfg, in_dim, n_classes, text_embeddings=None):
+        super().__init__()
+        base = self._build(cfg, in_dim, n_classes)
+        # blocks.py:568 computes this from Bi.hid_dim BEFORE the block loop; keep the order so
+        # the RNG stream (and hence the random init) matches the reference constructor.
+        self.frame_projection = FeatureProjection(feature_dim=base.hid_dim - n_classes, clip_dim=512,
+                                                  hidden_dim=cfg.CLIP.projection_hidden_dim,
+                                                  dropout=cfg.CLIP.projection_dropout)
+        if text_embeddings is not None:
+            self.register_buffer('text_embeddings', text_embeddings)
+        else:
+            self.text_embeddings = None
+        self._build_blocks(cfg, in_dim, n_classes, base)

@@ -1,0 +1,145 @@
+"""Tensor-level wrappers over the factk C ABI (include/factk.h).
+
+Every function takes CUDA torch tensors (torch is only the allocator / stream provider), launches the
+hand-written kernels on the current stream and returns nothing (outputs are written in place).
+Layout: "rows" tensors are [B, slot, ld] with ``len`` (int32 [B], device) valid rows per video.
+"""
+import torch
+
+from . import _lib as L
+
+
+def S(A, W, K=None, off=0, gather=None, pos=None, pos_d=None, pos_idx=None):
+    """One GEMM operand: rows of ``A`` ([B|1, a_slot, lda]) times ``W^T`` (W: [N,K] shared or [B,N,K] per video)."""
+    return dict(A=A, W=W, K=K, off=off, gather=gather, pos=pos, pos_d=pos_d, pos_idx=pos_idx)
+
+
+def _row_ld(t):
+    assert t.stride(-1) == 1, 'rows tensors must be contiguous in the last dimension'
+    return t.stride(-2)
+
+
+def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None):
+    g = L.Gemm()
+    B, slot = out.shape[0], out.shape[1]
+    g.B, g.slot, g.N, g.nsrc = B, slot, N, len_(srcs)
+    g.len = L.ptr(len)
+    for i, s in enumerate(srcs):
+        A, W = s['A'], s['W']
+        x = g.src[i]
+        x.A, x.a_dtype, x.lda = A.data_ptr(), L.dt(A), _row_ld(A)
+        x.a_slot = 0 if (A.shape[0] == 1 and B > 1) else A.stride(0) // _row_ld(A)
+        x.K = s['K'] if s['K'] is not None else W.shape[-1]
+        x.row_off = s['off']
+        x.gather = L.ptr(s['gather'])
+        if s['pos'] is not None:
+            x.pos, x.pos_ld = s['pos'].data_ptr(), s['pos'].stride(0)
+            x.pos_d = s['pos_d'] if s['pos_d'] is not None else s['pos'].shape[-1]
+            x.pos_idx = L.ptr(s['pos_idx'])
+        assert W.dtype == torch.float32 and W.stride(-1) == 1
+        x.W, x.ldw = W.data_ptr(), W.stride(-2)
+        x.w_bstride = W.stride(0) if W.dim() == 3 else 0
+    if bias is not None:
+        g.bias = bias.data_ptr()
+        g.bias_bstride = bias.stride(0) if bias.dim() == 2 else 0
+    g.alpha, g.relu = float(alpha), int(relu)
+    if res is not None:
+        g.res, g.res_dtype, g.ldres = res.data_ptr(), L.dt(res), _row_ld(res)
+    g.Y, g.y_dtype, g.ldy = out.data_ptr(), L.dt(out), _row_ld(out)
+    L.call('factk_gemm', g, L.stream())
+
+
+len_ = len   # the builtin (``len`` is also a keyword argument name in this module)
+
+
+def softmax_splice(x, C, clogit, pred=None, len=None, H=None):
+    B, slot = x.shape[0], x.shape[1]
+    H = x.shape[-1] if H is None else H
+    L.call('factk_softmax_splice', x.data_ptr(), L.dt(x), B, slot, L.ptr(len), _row_ld(x), H, C,
+           clogit.data_ptr(), L.ptr(pred), L.stream())
+
+
+def layernorm(x, w, b, out, res=None, eps=1e-5, relu=False, len=None, E=None):
+    B, slot = x.shape[0], x.shape[1]
+    E = x.shape[-1] if E is None else E
+    L.call('factk_layernorm', x.data_ptr(), L.dt(x), _row_ld(x),
+           L.ptr(res), L.dt(res) if res is not None else 0, _row_ld(res) if res is not None else 0,
+           w.data_ptr(), b.data_ptr(), float(eps), int(relu), out.data_ptr(), L.dt(out), _row_ld(out),
+           B, slot, L.ptr(len), E, L.stream())
+
+
+def l2norm(x, out, eps=1e-12, len=None):
+    B, slot, E = x.shape
+    L.call('factk_l2norm', x.data_ptr(), L.dt(x), _row_ld(x), out.data_ptr(), L.dt(out), _row_ld(out),
+           B, slot, L.ptr(len), E, float(eps), L.stream())
+
+
+def row_softmax(logit, out, M, scale=1.0, len=None):
+    B, slot = logit.shape[0], logit.shape[1]
+    L.call('factk_row_softmax', logit.data_ptr(), _row_ld(logit), out.data_ptr(), _row_ld(out), B, slot,
+           L.ptr(len), M, float(scale), L.stream())
+
+
+def mha_tokens(q, k, v, out, nhead):
+    B, M = q.shape[0], q.shape[1]
+    E = out.shape[-1]
+    assert _row_ld(q) == _row_ld(k) == _row_ld(v)
+    L.call('factk_mha_tokens', q.data_ptr(), k.data_ptr(), v.data_ptr(), _row_ld(q), out.data_ptr(), _row_ld(out),
+           B, M, nhead, E // nhead, L.stream())
+
+
+def attn_rows_ws(B, slot, M, nhead, dh):
+    return int(L.load().factk_attn_rows_ws_floats(B, slot, M, nhead, dh))
+
+
+def attn_rows(q, kx, vx, out, nhead, ws, len=None):
+    B, M, E = q.shape[0], q.shape[1], out.shape[-1]
+    slot = kx.shape[1]
+    assert _row_ld(kx) == _row_ld(vx) and kx.dtype == vx.dtype
+    L.call('factk_attn_rows', q.data_ptr(), _row_ld(q), kx.data_ptr(), vx.data_ptr(), L.dt(kx), _row_ld(kx),
+           out.data_ptr(), _row_ld(out), B, slot, L.ptr(len), M, nhead, E // nhead, ws.data_ptr(), L.stream())
+
+
+def col_softmax_ws(B, slot, M, E):
+    return int(L.load().factk_col_softmax_ws_floats(B, slot, M, E))
+
+
+def col_softmax_apply(logit, x, out, M, ws, attn=None, len=None, E=None):
+    B, slot = logit.shape[0], logit.shape[1]
+    E = x.shape[-1] if E is None else E
+    L.call('factk_col_softmax_apply', logit.data_ptr(), _row_ld(logit), x.data_ptr(), L.dt(x), _row_ld(x),
+           out.data_ptr(), _row_ld(out), L.ptr(attn), _row_ld(attn) if attn is not None else 0,
+           B, slot, L.ptr(len), M, E, ws.data_ptr(), L.stream())
+
+
+def tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=None):
+    B, slot = pred.shape
+    L.call('factk_tdu_segment', pred.data_ptr(), B, slot, L.ptr(len), seg_label.data_ptr(), seg_start.data_ptr(),
+           seg_len.data_ptr(), seg_center.data_ptr(), nseg.data_ptr(), L.stream())
+
+
+def segment_mean(x, seg, seg_start, seg_len, nseg, E=None):
+    B, slot = x.shape[0], x.shape[1]
+    E = x.shape[-1] if E is None else E
+    L.call('factk_segment_mean', x.data_ptr(), L.dt(x), _row_ld(x), seg.data_ptr(), L.dt(seg), _row_ld(seg),
+           seg_start.data_ptr(), seg_len.data_ptr(), nseg.data_ptr(), B, slot, E, L.stream())
+
+
+def gru_bidir(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, nseg, relu=True):
+    B, slot = gi.shape[0], gi.shape[1]
+    Hh = w_hh_f.shape[1]
+    L.call('factk_gru_bidir', gi.data_ptr(), w_hh_f.data_ptr(), b_hh_f.data_ptr(), w_hh_b.data_ptr(), b_hh_b.data_ptr(),
+           Hh, out.data_ptr(), L.dt(out), _row_ld(out), int(relu), B, slot, nseg.data_ptr(), L.stream())
+
+
+def gather_rows(src, idx, out, E, len=None):
+    B, slot = out.shape[0], out.shape[1]
+    L.call('factk_gather_rows', src.data_ptr(), _row_ld(src), src.shape[1], idx.data_ptr(), out.data_ptr(),
+           _row_ld(out), B, slot, L.ptr(len), E, L.stream())
+
+
+def fuse_eval(action_clogit, attn, flogit, weight, pred, M, C, seg_label=None, len=None):
+    B, slot = flogit.shape[0], flogit.shape[1]
+    L.call('factk_fuse_eval', L.ptr(action_clogit), L.ptr(attn), _row_ld(attn) if attn is not None else 0,
+           attn.shape[1] if attn is not None else 0, L.ptr(seg_label), flogit.data_ptr(), _row_ld(flogit),
+           float(weight), pred.data_ptr(), B, slot, L.ptr(len), M, C, L.stream())

@@ -1,0 +1,166 @@
+/*
+ * factk -- C ABI of the B200 (sm_100a) kernel library behind the FACT / FACT_CLIP forward.
+ *
+ * The reference (lucas-t-t/FACT-CLIP) has no FFI / plugin layer: its boundary is the Python
+ * nn.Module API of fact_clip/models/blocks.py (FACT :19-135, FACT_CLIP :504-920).  The host side in
+ * fact_clip_b200/ mirrors that API and binds THIS header through ctypes (INTEGRATION.md shows the
+ * stub).  Every entry point below names the reference code it replaces (path:line under
+ * /root/reference/fact_clip/).
+ *
+ * Conventions
+ *  - all pointers are BORROWED device pointers (except factk_last_error); the library never
+ *    allocates or frees caller memory and never synchronises; every launch goes to `stream`
+ *    (a cudaStream_t passed as void*).
+ *  - return value: 0 on success, negative on error; factk_last_error() gives a thread-local text.
+ *  - "rows" layout: an activation is a row-major matrix [B][slot][ld] -- B videos, `slot` row
+ *    slots per video of which the first len[b] are valid (len == NULL: all slot rows valid), `ld`
+ *    elements per row.  Frames, segments and action tokens all use it.  Rows >= len[b] are never
+ *    read as data (they read as zero for convolution taps) and never written.
+ *  - dtype codes: FACTK_F32 = 0, FACTK_BF16 = 1.
+ */
+#ifndef FACTK_H_
+#define FACTK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FACTK_F32 0
+#define FACTK_BF16 1
+#define FACTK_MAX_SRC 4
+
+#define FACTK_OK 0
+#define FACTK_ERR_ARG (-1)
+#define FACTK_ERR_CUDA (-2)
+#define FACTK_ERR_DEVICE (-3)
+#define FACTK_ERR_UNSUPPORTED (-4)
+
+int factk_version(void);
+const char* factk_last_error(void);
+/* 0 when the current device is sm_100 (B200); FACTK_ERR_DEVICE otherwise. */
+int factk_device_check(void);
+
+/* One operand of the generalised GEMM: rows of A (optionally shifted / gathered / with a positional
+ * term on the first pos_d channels) times W^T.  Replaces, depending on use: nn.Conv1d taps
+ * (models/basic.py:138-139,158,177,182), nn.Linear (basic.py:343-347, blocks.py:402,414,153-159) and
+ * add_positional_encoding (basic.py:313-320). */
+typedef struct {
+    const void* A;        /* [B][a_slot][lda] */
+    int32_t a_dtype;
+    int32_t lda;
+    int32_t a_slot;
+    int32_t K;
+    int32_t row_off;      /* tap offset in rows; source rows outside [0,len[b]) read as zero */
+    int32_t pos_ld;
+    int32_t pos_d;
+    int32_t ldw;
+    const int32_t* gather;  /* optional [B][slot] source-row index (seg->frame upsample, blocks.py:442) */
+    const float* pos;       /* optional table [n][pos_ld]; added to channels < pos_d */
+    const int32_t* pos_idx; /* optional [B][slot] row index into pos (seg_center, blocks.py:454-455); default: row */
+    const float* W;         /* [N][ldw] fp32, y = A W^T */
+    int64_t w_bstride;      /* elements between per-video weights; 0 = shared */
+} factk_src_t;
+
+typedef struct {
+    int32_t B, slot, N, nsrc;
+    const int32_t* len;     /* [B] valid rows, or NULL */
+    factk_src_t src[FACTK_MAX_SRC];
+    const float* bias;      /* [N] or NULL */
+    int64_t bias_bstride;
+    float alpha;            /* y = relu?(alpha * sum + bias) + res */
+    int32_t relu;
+    const void* res;        /* optional residual [B][slot][ldres], added after the activation */
+    int32_t res_dtype, ldres;
+    void* Y;                /* [B][slot][ldy] */
+    int32_t y_dtype, ldy;
+} factk_gemm_t;
+
+/* y[b,t,:N] = act(alpha * sum_s A_s[b, idx_s(t)] W_s[b]^T + bias) + res.  fp32 accumulate (CUDA cores). */
+int factk_gemm(const factk_gemm_t* g, void* stream);
+
+/* Block.process_feature (blocks.py:195-202) in place on rows [B][slot][ld] of width H: the last C
+ * channels are logits -> clogit_out fp32 [B][slot][C]; they are overwritten by softmax(logits).
+ * pred_out (optional, int32 [B][slot]) = argmax of the probabilities, first index on ties
+ * (blocks.py:420-421). */
+int factk_softmax_splice(void* X, int dtype, int B, int slot, const int32_t* len, int ld, int H, int C,
+                         float* clogit_out, int32_t* pred_out, void* stream);
+
+/* y = LayerNorm(x (+ r)) * w + b, optional ReLU (nn.LayerNorm in basic.py:407-408,472-474,
+ * blocks.py:155,223).  x, r: [B][slot][ld*] of dtype; y may alias x. */
+int factk_layernorm(const void* X, int x_dtype, int ldx, const void* R, int r_dtype, int ldr,
+                    const float* w, const float* b, float eps, int relu,
+                    void* Y, int y_dtype, int ldy, int B, int slot, const int32_t* len, int E, void* stream);
+
+/* F.normalize(x, dim=-1, eps) (blocks.py:174). */
+int factk_l2norm(const void* X, int x_dtype, int ldx, void* Y, int y_dtype, int ldy,
+                 int B, int slot, const int32_t* len, int E, float eps, void* stream);
+
+/* softmax over the first M columns of each row: P = softmax(scale * L) (basic.py:376, a2f direction;
+ * blocks.py:826 with scale = 1).  L fp32 [B][slot][ldl]; P fp32 [B][slot][ldp] (may alias L). */
+int factk_row_softmax(const float* L, int ldl, float* P, int ldp, int B, int slot, const int32_t* len, int M,
+                      float scale, void* stream);
+
+/* Token self-attention core of nn.MultiheadAttention (basic.py:500, 437): Q,K,V fp32 [B][M][ld]
+ * already projected; O[b,m,h*dh:(h+1)*dh] = softmax(q k^T / sqrt(dh)) v per head. */
+int factk_mha_tokens(const float* Q, const float* K, const float* V, int ld, float* O, int ldo,
+                     int B, int M, int nhead, int dh, void* stream);
+
+/* Tokens-attend-rows core of the SCALayer cross attention (basic.py:507-514): Q fp32 [B][M][ldq]
+ * (projected), Kx/Vx rows [B][slot][ldkv] of dtype (projected keys / values, column offsets applied
+ * by the caller), softmax over the len[b] valid rows per head.  ws: fp32 scratch of
+ * factk_attn_rows_ws_floats(...) floats. */
+size_t factk_attn_rows_ws_floats(int B, int slot, int M, int nhead, int dh);
+int factk_attn_rows(const float* Q, int ldq, const void* Kx, const void* Vx, int kv_dtype, int ldkv,
+                    float* O, int ldo, int B, int slot, const int32_t* len, int M, int nhead, int dh,
+                    float* ws, void* stream);
+
+/* Softmax over ROWS (the X axis of X2Y_map in the f2a direction, basic.py:373-379):
+ *   L fp32 [B][slot][ldl] holds logits (row = frame/segment, column = token m < M);
+ *   stats[b][m] = (max, sum exp) over valid rows;
+ *   out[b][m][:E] = sum_t softmax_t(L[b,t,m]) * X[b,t,:E]   (X of dtype, row-major [B][slot][ldx]);
+ *   P (optional, fp32 [B][slot][ldp]) receives the normalised attention. */
+size_t factk_col_softmax_ws_floats(int B, int slot, int M, int E);
+int factk_col_softmax_apply(const float* L, int ldl, const void* X, int x_dtype, int ldx,
+                            float* out, int ldo, float* P, int ldp,
+                            int B, int slot, const int32_t* len, int M, int E, float* ws, void* stream);
+
+/* Run-length segmentation on device (utils/utils.py:25-48, basic.py:597-607, blocks.py:454):
+ * pred int32 [B][slot] -> seg_label[B][slot], seg_start[B][slot], seg_len[B][slot],
+ * seg_center[B][slot] (= (start+end)/2 floor), nseg[B]. */
+int factk_tdu_segment(const int32_t* pred, int B, int slot, const int32_t* len,
+                      int32_t* seg_label, int32_t* seg_start, int32_t* seg_len, int32_t* seg_center,
+                      int32_t* nseg, void* stream);
+
+/* TemporalDownsampleUpsample.feature_frame2seg (basic.py:615-625): deterministic segment mean.
+ * X rows of dtype [B][slot][ldx] -> seg fp32/bf16 [B][slot][lds], first nseg[b] rows. */
+int factk_segment_mean(const void* X, int x_dtype, int ldx, void* seg, int s_dtype, int lds,
+                       const int32_t* seg_start, const int32_t* seg_len, const int32_t* nseg,
+                       int B, int slot, int E, void* stream);
+
+/* Bidirectional GRU recurrence (nn.GRU(H, H/2, 1, bidirectional=True), blocks.py:401,432) over the
+ * nseg[b] segments of each video.  gi fp32 [B][slot][6*Hh] = x W_ih^T + b_ih for (fwd r,z,n | bwd r,z,n);
+ * w_hh_{f,b} fp32 [3*Hh][Hh]; b_hh_{f,b} [3*Hh].  out [B][slot][2*Hh] of dtype = relu?(cat[fwd,bwd]). */
+int factk_gru_bidir(const float* gi, const float* w_hh_f, const float* b_hh_f,
+                    const float* w_hh_b, const float* b_hh_b, int Hh,
+                    void* out, int o_dtype, int ldo, int relu,
+                    int B, int slot, const int32_t* nseg, void* stream);
+
+/* out[b,t,:E] = in[b, idx[b,t], :E] fp32 (attn_seg2frame, basic.py:645-651). */
+int factk_gather_rows(const float* in, int ldi, int in_slot, const int32_t* idx, float* out, int ldo,
+                      int B, int slot, const int32_t* len, int E, void* stream);
+
+/* Prob fusion + argmax: Block._eval (blocks.py:242-261) / FACT_CLIP.eval_with_clip (blocks.py:854-887).
+ * action_clogit fp32 [B][M][C+1]; attn fp32 [B][attn_slot][lda] (a2f attention, row = frame, or row =
+ * segment when seg_label != NULL); flogit fp32 [B][slot][ldf] frame-branch logits (frame_clogit, or
+ * CLIP similarity / temp) -> pred int64 [B][slot]. */
+int factk_fuse_eval(const float* action_clogit, const float* attn, int lda, int attn_slot,
+                    const int32_t* seg_label, const float* flogit, int ldf, float weight,
+                    int64_t* pred, int B, int slot, const int32_t* len, int M, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACTK_H_ */

@@ -1,0 +1,85 @@
+"""CPU checks of the drop-in boundary: constructor / state_dict contract vs the reference-generated
+fixtures, the C-ABI library's exported symbols, and the loud failure without a CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, golden_names, load_golden
+from fact_clip_b200 import _lib, config as C
+from fact_clip_b200.models.blocks import FACT, FACT_CLIP
+from fact_clip_b200.utils.synth import make_text_embeddings
+
+
+def build_ours(g, seed=5):
+    cfg = C.tiny(**g['tiny_kwargs'])
+    torch.manual_seed(seed)
+    if g['clip']:
+        return FACT_CLIP(cfg, g['in_dim'], g['n_classes'], make_text_embeddings(g['n_classes']))
+    return FACT(cfg, g['in_dim'], g['n_classes'])
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_state_dict_contract(name):
+    g = load_golden(name)
+    net = build_ours(g)
+    ours = {k: v for k, v in net.state_dict().items() if not k.endswith('.pe')}
+    ref = g['state_dict']
+    assert list(ours.keys()) == list(ref.keys())           # same names, same registration order
+    for k in ref:
+        assert ours[k].shape == ref[k].shape, k
+    net.load_state_dict(ref, strict=False)
+    missing = set(net.state_dict()) - set(ref)
+    assert all(k.endswith('.pe') for k in missing)
+
+
+def test_same_seed_same_init():
+    """Same torch layer constructors in the same order => identical random init as the reference
+    (the fixture generator scaled the class-logit layers by SHARPEN=3 afterwards)."""
+    g = load_golden('tiny_m_iuU_clip')
+    net = build_ours(g, seed=5)
+    sd = net.state_dict()
+    for k, v in g['state_dict'].items():
+        scale = 3.0 if k.endswith(('out_linear.weight', 'conv_out.weight', 'seg_combine.weight')) else 1.0
+        torch.testing.assert_close(sd[k] * scale, v, rtol=1e-6, atol=1e-7, msg=k)
+
+
+def test_update_from_mutates_cfg_like_reference():
+    cfg = C.havid_view0_lh_pt_holdout()
+    assert cfg.Bu.hid_dim is None
+    FACT(cfg, 64, 75)
+    assert cfg.Bu.hid_dim == 512 and cfg.BU.f_dim == 256 and cfg.BU.f == 'm'
+
+
+def test_metric_config_parameter_count():
+    net = FACT_CLIP(C.havid_view0_lh_pt_holdout(), 2048, 75, make_text_embeddings(75))
+    assert sum(p.numel() for p in net.parameters()) == 29290240
+    assert len(net.state_dict()) == 417
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'factk.h')).read()
+    declared = set(re.findall(r'\b(factk_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.exported_symbols())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.factk_version() >= 100
+    assert isinstance(lib.factk_last_error(), bytes)
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    net = FACT(C.tiny(), 24, 7).eval()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        net([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)])
+
+
+def test_unsupported_variants_raise():
+    cfg = C.tiny()
+    cfg.FACT.trans = True
+    with pytest.raises(NotImplementedError):
+        FACT(cfg, 24, 7)

@@ -1,0 +1,259 @@
+"""Per-kernel parity (GPU, through the C ABI) against plain torch-CPU fp32 restatements / the oracle."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, GOLDEN
+
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import fact_oracle as O  # noqa: E402
+from fact_clip_b200 import ops  # noqa: E402
+from fact_clip_b200.ops import S  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def close(a, b, rtol=1e-4, atol=1e-5):
+    torch.testing.assert_close(a.float().cpu(), b.float().cpu(), rtol=rtol, atol=atol)
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+# ------------------------------------------------------------------------------------------ gemm
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('B,slot,K,N,lens', [(1, 128, 64, 128, [128]), (3, 256, 437, 75, [256, 130, 1]),
+                                              (2, 384, 2048, 256, [300, 384]), (2, 130, 20, 9, [7, 130]), (1, 64, 30, 17, [64])])
+def test_gemm_plain(dtype, B, slot, K, N, lens):
+    x = rnd(B, slot, K + (3 if K == 30 else 4 if K % 2 == 0 else 3), seed=1).to(dtype)   # vector and scalar load paths
+    w, bias = rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    ln = torch.tensor(lens, dtype=torch.int32)
+    out = torch.full((B, slot, N), 7.0, dtype=dtype, device=DEV)
+    ops.gemm([S(x.to(DEV), w.to(DEV), K=K)], N, out, len=ln.to(DEV), bias=bias.to(DEV), relu=True)
+    ref = torch.relu(x[..., :K].float() @ w.t() + bias)
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    for b, T in enumerate(lens):
+        close(out[b, :T], ref[b, :T], **tol)
+        assert bool((out[b, T:].float() == 7.0).all())          # rows >= len are never written
+
+
+def test_gemm_conv_taps_and_residual():
+    """Three shifted taps == nn.Conv1d(k=3, dilation=d, padding=d); then 1x1 + residual (basic.py:158-164)."""
+    B, slot, F, lens = 2, 256, 32, [256, 100]
+    x = rnd(B, slot, F, seed=4)
+    conv = torch.nn.Conv1d(F, F, 3, padding=8, dilation=8)
+    w3 = conv.weight.detach().permute(2, 0, 1).contiguous()
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    xd = x.to(DEV)
+    h = torch.zeros(B, slot, F, device=DEV)
+    ops.gemm([S(xd, w3[k].to(DEV), off=(k - 1) * 8) for k in range(3)], F, h, len=ln, bias=conv.bias.detach().to(DEV), relu=True)
+    w1 = rnd(F, F, seed=5, scale=F ** -0.5)
+    y = torch.zeros(B, slot, F, device=DEV)
+    ops.gemm([S(h, w1.to(DEV))], F, y, len=ln, res=xd)
+    for b, T in enumerate(lens):
+        hr = torch.relu(conv(x[b, :T].t()[None])[0].t()).detach()
+        close(h[b, :T], hr)
+        close(y[b, :T], hr @ w1.t() + x[b, :T])
+
+
+def test_gemm_gather_pos_pervideo_weights():
+    B, slot, K1, K2, N, M = 2, 128, 16, 24, 20, 10
+    lens = [128, 50]
+    seg = rnd(B, slot, K1, seed=6)
+    fr = rnd(B, slot, K2, seed=7)
+    idx = torch.randint(0, 40, (B, slot), generator=torch.Generator().manual_seed(8), dtype=torch.int32)
+    pos = rnd(slot, K2, seed=9)
+    pidx = torch.randint(0, slot, (B, slot), generator=torch.Generator().manual_seed(10), dtype=torch.int32)
+    w1 = rnd(N, K1, seed=11)
+    w2 = rnd(B, N, K2, seed=12)             # per-video weights
+    bias = rnd(B, N, seed=13)
+    out = torch.zeros(B, slot, N, device=DEV)
+    ops.gemm([S(seg.to(DEV), w1.to(DEV), gather=idx.to(DEV)),
+              S(fr.to(DEV), w2.to(DEV), pos=pos.to(DEV), pos_d=12, pos_idx=pidx.to(DEV))], N, out,
+             len=torch.tensor(lens, dtype=torch.int32, device=DEV), bias=bias.to(DEV), alpha=0.5)
+    for b, T in enumerate(lens):
+        a2 = fr[b, :T].clone()
+        a2[:, :12] += pos[pidx[b, :T].long()][:, :12]
+        ref = 0.5 * (seg[b][idx[b, :T].long()] @ w1.t() + a2 @ w2[b].t()) + bias[b]
+        close(out[b, :T], ref)
+
+
+def test_gemm_shared_A_rows():
+    """A with a single 'video' broadcast against per-video weights (used for vt = Wa xv^T)."""
+    B, Fd, H, M = 3, 40, 32, 11
+    Wa, xv = rnd(1, Fd, H, seed=14), rnd(B, M, H, seed=15)
+    out = torch.zeros(B, Fd, 12, device=DEV)
+    ops.gemm([S(Wa.to(DEV), xv.to(DEV))], M, out)
+    close(out[:, :, :M], torch.einsum('fh,bmh->bfm', Wa[0], xv))
+
+
+# ------------------------------------------------------------------------------------------ row ops
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_softmax_splice(dtype):
+    B, slot, H, C, lens = 2, 64, 48, 11, [64, 9]
+    x = rnd(B, slot, H, seed=16, scale=2.0).to(dtype)
+    xd = x.to(DEV).clone()
+    clogit = torch.zeros(B, slot, C, device=DEV)
+    pred = torch.full((B, slot), -1, dtype=torch.int32, device=DEV)
+    ops.softmax_splice(xd, C, clogit, pred, len=torch.tensor(lens, dtype=torch.int32, device=DEV))
+    for b, T in enumerate(lens):
+        feat, cl = O.process_feature(x[b, :T].float(), C)
+        close(clogit[b, :T], cl, rtol=0, atol=0)
+        close(xd[b, :T], feat, rtol=1e-2 if dtype == torch.bfloat16 else 1e-5, atol=1e-2 if dtype == torch.bfloat16 else 1e-6)
+        assert torch.equal(pred[b, :T].cpu().long(), cl.argmax(-1))
+        close(xd[b, T:], x[b, T:], rtol=0, atol=0)
+
+
+def test_layernorm_l2norm_rowsoftmax_gather():
+    B, slot, E = 2, 40, 96
+    x, r = rnd(B, slot, E, seed=17), rnd(B, slot, E, seed=18)
+    w, bb = rnd(E, seed=19), rnd(E, seed=20)
+    y = torch.zeros(B, slot, E, device=DEV)
+    ops.layernorm(x.to(DEV), w.to(DEV), bb.to(DEV), y, res=r.to(DEV), relu=True)
+    close(y, torch.relu(torch.nn.functional.layer_norm(x + r, (E,), w, bb)), rtol=1e-4, atol=1e-5)
+    ops.l2norm(x.to(DEV), y)
+    close(y, torch.nn.functional.normalize(x, dim=-1))
+    p = torch.zeros(B, slot, E, device=DEV)
+    ops.row_softmax(x.to(DEV), p, 75, scale=0.5)
+    close(p[..., :75], torch.softmax(0.5 * x[..., :75], -1))
+    idx = torch.randint(0, slot, (B, slot), generator=torch.Generator().manual_seed(21), dtype=torch.int32)
+    g = torch.zeros(B, slot, E, device=DEV)
+    ops.gather_rows(x.to(DEV), idx.to(DEV), g, E)
+    close(g, torch.stack([x[b][idx[b].long()] for b in range(B)]), rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize('M,nh,dh', [(75, 8, 32), (12, 4, 8), (300, 8, 32), (60, 8, 64)])
+def test_mha_tokens(M, nh, dh):
+    B, E = 2, nh * dh
+    qkv = rnd(B, M, 3 * E, seed=22)
+    d = qkv.to(DEV)
+    o = torch.zeros(B, M, E, device=DEV)
+    ops.mha_tokens(d[..., :E], d[..., E:2 * E], d[..., 2 * E:], o, nh)
+    q, k, v = [t.view(B, M, nh, dh).transpose(1, 2) for t in (qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:])]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), -1) @ v).transpose(1, 2).reshape(B, M, E)
+    close(o, ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('M,nh,dh,slot,lens', [(75, 8, 32, 1280, [1280, 700, 3]), (12, 4, 8, 128, [37, 128]), (300, 8, 32, 640, [640])])
+def test_attn_rows(dtype, M, nh, dh, slot, lens):
+    B, E = len(lens), nh * dh
+    q = rnd(B, M, E, seed=23)
+    kv = rnd(B, slot, 2 * E, seed=24).to(dtype)
+    o = torch.zeros(B, M, E, device=DEV)
+    kvd = kv.to(DEV)
+    ws = torch.empty(ops.attn_rows_ws(B, slot, M, nh, dh), device=DEV)
+    ops.attn_rows(q.to(DEV), kvd[..., :E], kvd[..., E:], o, nh, ws, len=torch.tensor(lens, dtype=torch.int32, device=DEV))
+    for b, T in enumerate(lens):
+        qq = q[b].view(M, nh, dh).transpose(0, 1)
+        kk = kv[b, :T, :E].float().view(T, nh, dh).transpose(0, 1)
+        vv = kv[b, :T, E:].float().view(T, nh, dh).transpose(0, 1)
+        ref = (torch.softmax(qq @ kk.transpose(1, 2) / math.sqrt(dh), -1) @ vv).transpose(0, 1).reshape(M, E)
+        close(o[b], ref, rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('M,E,slot,lens', [(75, 512, 1280, [1280, 600, 1]), (12, 64, 128, [100, 128])])
+def test_col_softmax_apply(M, E, slot, lens):
+    B, Mp = len(lens), (M + 3) // 4 * 4
+    logit = rnd(B, slot, Mp, seed=25, scale=3.0)
+    x = rnd(B, slot, E, seed=26)
+    out = torch.zeros(B, M, E, device=DEV)
+    attn = torch.zeros(B, slot, Mp, device=DEV)
+    ws = torch.empty(ops.col_softmax_ws(B, slot, M, E), device=DEV)
+    ops.col_softmax_apply(logit.to(DEV), x.to(DEV), out, M, ws, attn=attn, len=torch.tensor(lens, dtype=torch.int32, device=DEV))
+    for b, T in enumerate(lens):
+        p = torch.softmax(logit[b, :T, :M], dim=0)
+        close(attn[b, :T, :M], p, rtol=1e-4, atol=1e-6)
+        close(out[b], p.t() @ x[b, :T], rtol=2e-4, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ TDU
+def test_tdu_segment_and_mean():
+    g = torch.Generator().manual_seed(27)
+    B, slot, E = 4, 2304, 64
+    lens = [2304, 1500, 1, 1025]
+    pred = torch.zeros(B, slot, dtype=torch.int32)
+    for b in range(B):
+        # run lengths 1..7 -> many segments; video 2 has a single frame; video 3 one long run
+        runs = torch.randint(1, 8, (slot,), generator=g)
+        cls = torch.randint(0, 5, (slot,), generator=g)
+        p = torch.repeat_interleave(cls, runs)[:slot]
+        pred[b] = p.int() if b != 3 else 2
+    x = rnd(B, slot, E, seed=28)
+    names = ['seg_label', 'seg_start', 'seg_len', 'seg_center']
+    o = {n: torch.full((B, slot), -1, dtype=torch.int32, device=DEV) for n in names}
+    nseg = torch.zeros(B, dtype=torch.int32, device=DEV)
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    ops.tdu_segment(pred.to(DEV), o['seg_label'], o['seg_start'], o['seg_len'], o['seg_center'], nseg, len=ln)
+    seg = torch.zeros(B, slot, E, device=DEV)
+    ops.segment_mean(x.to(DEV), seg, o['seg_start'], o['seg_len'], nseg)
+    for b, T in enumerate(lens):
+        lab, start, slen = O.run_length(pred[b, :T].numpy())
+        S = len(slen)
+        assert int(nseg[b]) == S
+        assert np.array_equal(o['seg_label'][b, :T].cpu().numpy(), lab)
+        assert np.array_equal(o['seg_start'][b, :S].cpu().numpy(), start)
+        assert np.array_equal(o['seg_len'][b, :S].cpu().numpy(), slen)
+        assert np.array_equal(o['seg_center'][b, :S].cpu().numpy(), (start + start + slen - 1) // 2)
+        ref = torch.zeros(S, E).index_add_(0, torch.from_numpy(lab), x[b, :T]) / torch.from_numpy(slen)[:, None]
+        close(seg[b, :S], ref, rtol=1e-4, atol=1e-5)
+    # determinism: bit-identical on a second run
+    seg2 = torch.zeros(B, slot, E, device=DEV)
+    ops.segment_mean(x.to(DEV), seg2, o['seg_start'], o['seg_len'], nseg)
+    assert torch.equal(seg, seg2)
+
+
+@pytest.mark.parametrize('Hh,nsegs', [(32, [19, 1, 7, 40, 3]), (256, [300, 17])])
+def test_gru_bidir(Hh, nsegs):
+    B, slot, H = len(nsegs), 384, 2 * Hh
+    gru = torch.nn.GRU(H, Hh, 1, bidirectional=True)
+    sd = {'g.' + k: v.detach() for k, v in gru.state_dict().items()}
+    x = rnd(B, slot, H, seed=29)
+    wih = torch.cat([sd['g.weight_ih_l0'], sd['g.weight_ih_l0_reverse']])
+    bih = torch.cat([sd['g.bias_ih_l0'], sd['g.bias_ih_l0_reverse']])
+    gi = (x @ wih.t() + bih).to(DEV)
+    out = torch.zeros(B, slot, H, device=DEV)
+    ops.gru_bidir(gi, sd['g.weight_hh_l0'].to(DEV), sd['g.bias_hh_l0'].to(DEV), sd['g.weight_hh_l0_reverse'].to(DEV),
+                  sd['g.bias_hh_l0_reverse'].to(DEV), out, torch.tensor(nsegs, dtype=torch.int32, device=DEV), relu=False)
+    for b, Sg in enumerate(nsegs):
+        ref = O.gru_bidir_fast(sd, 'g.', x[b, :Sg])
+        close(out[b, :Sg], ref, rtol=2e-4, atol=2e-5)
+        assert bool((out[b, Sg:] == 0).all())
+
+
+# ------------------------------------------------------------------------------------------ eval
+def test_fuse_eval_known_answers():
+    cases = torch.load(os.path.join(GOLDEN, 'eval_cases.pt'), weights_only=False)
+    for c in cases:
+        ac, attn, fc = c['action_clogit'][:, 0], c['a2f_attn'][0], c['frame_clogit'][:, 0]
+        T, M, Cc = fc.shape[0], ac.shape[0], fc.shape[1]
+        pred = torch.full((1, T), -1, dtype=torch.int64, device=DEV)
+        ops.fuse_eval(ac[None].contiguous().to(DEV), attn[None].contiguous().to(DEV), fc[None].contiguous().to(DEV),
+                      c['weight'], pred, M, Cc)
+        assert torch.equal(pred[0].cpu(), c['pred'])
+
+
+def test_fuse_eval_segment_gather():
+    g = torch.Generator().manual_seed(30)
+    T, Sg, M, Cc = 50, 9, 7, 5
+    ac = torch.randn(M, Cc + 1, generator=g) * 3
+    attn_seg = torch.softmax(torch.randn(Sg, M, generator=g) * 2, -1)
+    lab = torch.sort(torch.randint(0, Sg, (T,), generator=g)).values
+    fl = torch.randn(T, Cc, generator=g)
+    pred = torch.zeros(1, T, dtype=torch.int64, device=DEV)
+    ops.fuse_eval(ac[None].to(DEV), attn_seg[None].contiguous().to(DEV), fl[None].to(DEV), 0.1, pred, M, Cc,
+                  seg_label=lab.int()[None].to(DEV))
+    ref = O.fuse_eval(ac, attn_seg[lab], torch.softmax(fl, -1), 0.1)
+    assert torch.equal(pred[0].cpu(), ref)
