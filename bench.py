@@ -1,0 +1,240 @@
+"""Benchmark of the FACT_CLIP forward hot path (BASELINE.json metric: frames/sec, T=4096, 2048-d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--videos B] [--mode bf16|fp32]
+
+One "step" = one batched forward of B synthetic videos of T=4096 frames per GPU through the
+havid_view0_lh_pt_holdout FACT_CLIP configuration (random-init weights, segment-structured synthetic
+features).  Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_FRAMES, IN_DIM, N_CLASSES = 4096, 2048, 75
+PRESET = 'havid_view0_lh_pt_holdout'
+METRIC, UNIT = 'frames/sec FACT_CLIP fwd (T=4096,2048-d)', 'frames/s'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        mx = max((float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()), default=None)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=reasons, samples=len(sm))
+
+
+def build_model(mode):
+    from fact_clip_b200 import config as C
+    from fact_clip_b200.models.blocks import FACT_CLIP
+    from fact_clip_b200.utils.synth import make_text_embeddings
+    cfg = C.PRESETS[PRESET]()
+    torch.manual_seed(0)
+    net = FACT_CLIP(cfg, IN_DIM, N_CLASSES, make_text_embeddings(N_CLASSES)).eval()
+    net.compute_mode = mode
+    return net, cfg
+
+
+def alg_flops_tcn_layer(F):
+    """Dilated residual layer: conv3 (3 taps) + 1x1 = 8 F^2 FLOP per frame."""
+    return 8.0 * F * F
+
+
+def cpu_baseline(n_videos, threads):
+    """The oracle port (oracle/fact_oracle.py, 'kind: port') timed on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import fact_oracle as O
+    from fact_clip_b200.utils.synth import make_batch
+    torch.set_num_threads(threads)
+    net, cfg = build_model('fp32')
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    hp = O.hparams_from_cfg(cfg, IN_DIM, N_CLASSES)
+    xs, _ = make_batch([T_FRAMES] * n_videos, IN_DIM, N_CLASSES, base_seed=1000)
+    O.forward(sd, hp, xs[:1], clip=True)                       # warm-up
+    t0 = time.perf_counter()
+    O.forward(sd, hp, xs, clip=True)
+    dt = time.perf_counter() - t0
+    return n_videos * T_FRAMES / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = 2
+    vals = []
+    for _ in range(args.warmup + args.steps):
+        v, dt = cpu_baseline(n, threads)
+        vals.append((v, dt))
+    vals = vals[args.warmup:]
+    fps = sum(n * T_FRAMES for _ in vals) / sum(dt for _, dt in vals)
+    sample = f'{n} videos x T={T_FRAMES} per step, oracle port (torch CPU fp32), {threads} threads'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * sum(dt for _, dt in vals) / len(vals), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'FACT_CLIP {PRESET} forward, T={T_FRAMES}, D={IN_DIM}, C={N_CLASSES}, {n} videos/step (CPU)'},
+        'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--videos', type=int, default=16, help='videos per GPU per step')
+    ap.add_argument('--mode', default='bf16')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from fact_clip_b200 import _lib, ops
+    from fact_clip_b200.utils.synth import make_video
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.check(_lib.load().factk_device_check(), 'device_check')
+
+    net, cfg = build_model(args.mode)
+    net = net.to(dev)
+    eng = net.engine()
+    B, T = args.videos, T_FRAMES
+    # rank r owns videos {r*B .. r*B+B-1} of the sweep (videos shard, no data-path collective)
+    host = torch.empty(B, T, IN_DIM, pin_memory=True)
+    for b in range(B):
+        host[b].copy_(make_video(T, IN_DIM, N_CLASSES, seed=5000 + rank * B + b)[0])
+    x = host.to(dev)
+    lengths = [T] * B
+    ln = torch.tensor(lengths, dtype=torch.int32, device=dev)
+    seq_host = [host[b] for b in range(B)]
+    labels = [torch.zeros(T, dtype=torch.long) for _ in range(B)]
+
+    def step_resident():
+        return eng.run_packed(x, ln, lengths)
+
+    def step_e2e():
+        return net(seq_host, labels)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    sampler = ClockSampler(local)
+    ops.COUNTERS['launches'] = 0
+    ops.TIMER = ops.KernelTimer(('tcn_conv3', 'tcn_1x1'))
+    sampler.start()
+    ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    clocks = sampler.summary()
+    launches = ops.COUNTERS['launches'] // (args.steps + max(args.warmup, 3))
+    ktimes = ops.TIMER.collect(skip_steps=max(args.warmup, 3), steps=args.steps)
+    ops.TIMER = None
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+
+    frames_step = B * T * world
+    value = frames_step * args.steps / (ms * 1e-3)
+    e2e = frames_step * args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel family: the dilated residual layer of the frame branch
+    pk = peaks()
+    F = cfg.Bi.f_dim
+    n_layers = sum(b_.f_layers for b_ in (cfg.Bi, cfg.Bu, cfg.BU, cfg.BU))
+    t_layer_ms = (ktimes['tcn_conv3']['ms'] + ktimes['tcn_1x1']['ms']) / max(ktimes['tcn_conv3']['n'], 1)
+    ach_tf = alg_flops_tcn_layer(F) * B * T / (t_layer_ms * 1e-3) / 1e12 if t_layer_ms > 0 else 0.0
+    stash = step_resident()
+    nseg = [st['nseg'].tolist() for st in stash['blocks'] if 'nseg' in st]
+
+    res = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': args.mode if args.mode == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': {'workload': f'FACT_CLIP {PRESET} forward, T={T}, D={IN_DIM}, C={N_CLASSES}, F=A=256, M=75, block iuUU; '
+                               f'{B} videos/GPU/step, random-init weights, segment-structured synthetic features',
+                   'videos_per_gpu': B, 'frames_per_step': frames_step,
+                   'l2_policy': f'inputs larger than L2 ({B * T * IN_DIM * 4 / 2**20:.0f} MiB of fp32 features per step)',
+                   'segments_per_U_block_rank0': [[min(s), max(s)] for s in nseg]},
+        'clocks': clocks, 'gpu_launches': launches,
+        'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': B * T * IN_DIM * 4 * world,
+                'd2h_bytes_per_step': B * T * 8 * world, 'ms_per_step': ms_e2e / args.steps},
+        'roofline': {'bound': 'tensor', 'kernel': 'dilated residual layer (conv3+ReLU+1x1+residual), 40 per forward',
+                     'achieved': ach_tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': ach_tf / pk['tf_sust'],
+                     'traffic': None, 'peak_source': pk['src'] + ' (sustained bf16, kernel timed inside a long step)',
+                     'ms_per_layer': t_layer_ms, 'share_of_step': (ktimes['tcn_conv3']['ms'] + ktimes['tcn_1x1']['ms']) / args.steps / (ms / args.steps)},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            fps, dt = cpu_baseline(2, threads)
+            res['cpu_baseline'] = {'value': fps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                   'sample': f'2 videos x T={T} of the same workload, oracle port (torch CPU fp32), {dt:.1f} s'}
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -92,9 +92,9 @@ class FactEngine:
                 w3, d = self.taps(q + 'conv_dilated.weight'), 2 ** i
                 tmp = self.buf('f_tmp', (B, slot, F), self.act)
                 ops.gemm([S(cur, w3[k], off=(k - 1) * d) for k in range(3)], F, tmp, len=ln,
-                         bias=self.p(q + 'conv_dilated.bias'), relu=True)
+                         bias=self.p(q + 'conv_dilated.bias'), relu=True, tag='tcn_conv3')
                 ops.gemm([S(tmp, self.taps(q + 'conv_1x1.weight')[0])], F, nxt, len=ln,
-                         bias=self.p(q + 'conv_1x1.bias'), res=cur)
+                         bias=self.p(q + 'conv_1x1.bias'), res=cur, tag='tcn_1x1')
             else:
                 tmp = self.buf('f_tmp2', (B, slot, 2 * F), self.act)
                 for j, (nm, d) in enumerate(((f'{pfx}conv_dilated_1.{i}', 2 ** (Lr - 1 - i)), (f'{pfx}conv_dilated_2.{i}', 2 ** i))):

@@ -167,7 +167,7 @@ class _FactBase(nn.Module):
         dev = self.action_query.device
         if dev.type != 'cuda':
             raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
-        seqs = [s if s.is_cuda else s.to(dev, non_blocking=True) for s in seq_list]
+        seqs = list(seq_list)        # CUDA tensors, or (pinned) host tensors copied straight into the packed batch
         out = self.engine().run(seqs, forced_preds=forced_preds, keep=getattr(self, 'keep_attn', False))
         self._last = out
         pred = out['pred'].cpu().numpy()            # the one D2H sync of the call (blocks.py:900)

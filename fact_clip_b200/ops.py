@@ -9,6 +9,26 @@ import torch
 from . import _lib as L
 
 
+COUNTERS = {'launches': 0}
+TIMER = None
+
+
+class KernelTimer:
+    """CUDA-event timing of tagged launches on the launching stream (used by bench.py for the roofline line)."""
+
+    def __init__(self, tags):
+        self.tags, self.pairs = set(tags), {t: [] for t in tags}
+
+    def collect(self, skip_steps, steps):
+        torch.cuda.synchronize()
+        out = {}
+        for t, pairs in self.pairs.items():
+            per_step = len(pairs) // max(skip_steps + steps, 1)
+            use = pairs[skip_steps * per_step:]
+            out[t] = dict(ms=sum(a.elapsed_time(b) for a, b in use), n=len(use))
+        return out
+
+
 def S(A, W, K=None, off=0, gather=None, pos=None, pos_d=None, pos_idx=None):
     """One GEMM operand: rows of ``A`` ([B|1, a_slot, lda]) times ``W^T`` (W: [N,K] shared or [B,N,K] per video)."""
     return dict(A=A, W=W, K=K, off=off, gather=gather, pos=pos, pos_d=pos_d, pos_idx=pos_idx)
@@ -19,7 +39,7 @@ def _row_ld(t):
     return t.stride(-2)
 
 
-def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None):
+def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None, tag=None):
     g = L.Gemm()
     B, slot = out.shape[0], out.shape[1]
     g.B, g.slot, g.N, g.nsrc = B, slot, N, len_(srcs)
@@ -46,7 +66,15 @@ def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None):
     if res is not None:
         g.res, g.res_dtype, g.ldres = res.data_ptr(), L.dt(res), _row_ld(res)
     g.Y, g.y_dtype, g.ldy = out.data_ptr(), L.dt(out), _row_ld(out)
+    timed = TIMER is not None and tag in TIMER.tags
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.call('factk_gemm', g, L.stream())
+    if timed:
+        e1.record()
+        TIMER.pairs[tag].append((e0, e1))
+    COUNTERS['launches'] += 1
 
 
 len_ = len   # the builtin (``len`` is also a keyword argument name in this module)
@@ -55,6 +83,7 @@ len_ = len   # the builtin (``len`` is also a keyword argument name in this modu
 def softmax_splice(x, C, clogit, pred=None, len=None, H=None):
     B, slot = x.shape[0], x.shape[1]
     H = x.shape[-1] if H is None else H
+    COUNTERS['launches'] += 1
     L.call('factk_softmax_splice', x.data_ptr(), L.dt(x), B, slot, L.ptr(len), _row_ld(x), H, C,
            clogit.data_ptr(), L.ptr(pred), L.stream())
 
@@ -62,6 +91,7 @@ def softmax_splice(x, C, clogit, pred=None, len=None, H=None):
 def layernorm(x, w, b, out, res=None, eps=1e-5, relu=False, len=None, E=None):
     B, slot = x.shape[0], x.shape[1]
     E = x.shape[-1] if E is None else E
+    COUNTERS['launches'] += 1
     L.call('factk_layernorm', x.data_ptr(), L.dt(x), _row_ld(x),
            L.ptr(res), L.dt(res) if res is not None else 0, _row_ld(res) if res is not None else 0,
            w.data_ptr(), b.data_ptr(), float(eps), int(relu), out.data_ptr(), L.dt(out), _row_ld(out),
@@ -70,12 +100,14 @@ def layernorm(x, w, b, out, res=None, eps=1e-5, relu=False, len=None, E=None):
 
 def l2norm(x, out, eps=1e-12, len=None):
     B, slot, E = x.shape
+    COUNTERS['launches'] += 1
     L.call('factk_l2norm', x.data_ptr(), L.dt(x), _row_ld(x), out.data_ptr(), L.dt(out), _row_ld(out),
            B, slot, L.ptr(len), E, float(eps), L.stream())
 
 
 def row_softmax(logit, out, M, scale=1.0, len=None):
     B, slot = logit.shape[0], logit.shape[1]
+    COUNTERS['launches'] += 1
     L.call('factk_row_softmax', logit.data_ptr(), _row_ld(logit), out.data_ptr(), _row_ld(out), B, slot,
            L.ptr(len), M, float(scale), L.stream())
 
@@ -84,6 +116,7 @@ def mha_tokens(q, k, v, out, nhead):
     B, M = q.shape[0], q.shape[1]
     E = out.shape[-1]
     assert _row_ld(q) == _row_ld(k) == _row_ld(v)
+    COUNTERS['launches'] += 1
     L.call('factk_mha_tokens', q.data_ptr(), k.data_ptr(), v.data_ptr(), _row_ld(q), out.data_ptr(), _row_ld(out),
            B, M, nhead, E // nhead, L.stream())
 
@@ -96,6 +129,7 @@ def attn_rows(q, kx, vx, out, nhead, ws, len=None):
     B, M, E = q.shape[0], q.shape[1], out.shape[-1]
     slot = kx.shape[1]
     assert _row_ld(kx) == _row_ld(vx) and kx.dtype == vx.dtype
+    COUNTERS['launches'] += 2
     L.call('factk_attn_rows', q.data_ptr(), _row_ld(q), kx.data_ptr(), vx.data_ptr(), L.dt(kx), _row_ld(kx),
            out.data_ptr(), _row_ld(out), B, slot, L.ptr(len), M, nhead, E // nhead, ws.data_ptr(), L.stream())
 
@@ -107,6 +141,7 @@ def col_softmax_ws(B, slot, M, E):
 def col_softmax_apply(logit, x, out, M, ws, attn=None, len=None, E=None):
     B, slot = logit.shape[0], logit.shape[1]
     E = x.shape[-1] if E is None else E
+    COUNTERS['launches'] += 4
     L.call('factk_col_softmax_apply', logit.data_ptr(), _row_ld(logit), x.data_ptr(), L.dt(x), _row_ld(x),
            out.data_ptr(), _row_ld(out), L.ptr(attn), _row_ld(attn) if attn is not None else 0,
            B, slot, L.ptr(len), M, E, ws.data_ptr(), L.stream())
@@ -114,6 +149,7 @@ def col_softmax_apply(logit, x, out, M, ws, attn=None, len=None, E=None):
 
 def tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=None):
     B, slot = pred.shape
+    COUNTERS['launches'] += 1
     L.call('factk_tdu_segment', pred.data_ptr(), B, slot, L.ptr(len), seg_label.data_ptr(), seg_start.data_ptr(),
            seg_len.data_ptr(), seg_center.data_ptr(), nseg.data_ptr(), L.stream())
 
@@ -121,6 +157,7 @@ def tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=None)
 def segment_mean(x, seg, seg_start, seg_len, nseg, E=None):
     B, slot = x.shape[0], x.shape[1]
     E = x.shape[-1] if E is None else E
+    COUNTERS['launches'] += 1
     L.call('factk_segment_mean', x.data_ptr(), L.dt(x), _row_ld(x), seg.data_ptr(), L.dt(seg), _row_ld(seg),
            seg_start.data_ptr(), seg_len.data_ptr(), nseg.data_ptr(), B, slot, E, L.stream())
 
@@ -128,18 +165,21 @@ def segment_mean(x, seg, seg_start, seg_len, nseg, E=None):
 def gru_bidir(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, nseg, relu=True):
     B, slot = gi.shape[0], gi.shape[1]
     Hh = w_hh_f.shape[1]
+    COUNTERS['launches'] += 1
     L.call('factk_gru_bidir', gi.data_ptr(), w_hh_f.data_ptr(), b_hh_f.data_ptr(), w_hh_b.data_ptr(), b_hh_b.data_ptr(),
            Hh, out.data_ptr(), L.dt(out), _row_ld(out), int(relu), B, slot, nseg.data_ptr(), L.stream())
 
 
 def gather_rows(src, idx, out, E, len=None):
     B, slot = out.shape[0], out.shape[1]
+    COUNTERS['launches'] += 1
     L.call('factk_gather_rows', src.data_ptr(), _row_ld(src), src.shape[1], idx.data_ptr(), out.data_ptr(),
            _row_ld(out), B, slot, L.ptr(len), E, L.stream())
 
 
 def fuse_eval(action_clogit, attn, flogit, weight, pred, M, C, seg_label=None, len=None):
     B, slot = flogit.shape[0], flogit.shape[1]
+    COUNTERS['launches'] += 1
     L.call('factk_fuse_eval', L.ptr(action_clogit), L.ptr(attn), _row_ld(attn) if attn is not None else 0,
            attn.shape[1] if attn is not None else 0, L.ptr(seg_label), flogit.data_ptr(), _row_ld(flogit),
            float(weight), pred.data_ptr(), B, slot, L.ptr(len), M, C, L.stream())
