@@ -17,13 +17,14 @@ vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 class Src(C.Structure):
     _fields_ = [('A', vp), ('a_dtype', i32), ('lda', i32), ('a_slot', i32), ('K', i32), ('row_off', i32),
-                ('pos_ld', i32), ('pos_d', i32), ('ldw', i32), ('gather', vp), ('pos', vp), ('pos_idx', vp),
+                ('pos_ld', i32), ('pos_d', i32), ('ldw', i32), ('w_dtype', i32), ('reserved_', i32), ('gather', vp), ('pos', vp), ('pos_idx', vp),
                 ('W', vp), ('w_bstride', i64)]
 
 
 class Gemm(C.Structure):
     _fields_ = [('B', i32), ('slot', i32), ('N', i32), ('nsrc', i32), ('len', vp), ('src', Src * MAX_SRC),
-                ('bias', vp), ('bias_bstride', i64), ('alpha', f32), ('relu', i32), ('res', vp),
+                ('bias', vp), ('bias_bstride', i64), ('alpha', f32), ('relu', i32), ('pre', vp), ('pre_idx', vp),
+                ('pre_bstride', i64), ('pre_dtype', i32), ('ldpre', i32), ('res', vp),
                 ('res_dtype', i32), ('ldres', i32), ('Y', vp), ('y_dtype', i32), ('ldy', i32)]
 
 
@@ -32,6 +33,8 @@ _SIGS = {
     'factk_last_error': (C.c_char_p, []),
     'factk_device_check': (i32, []),
     'factk_gemm': (i32, [C.POINTER(Gemm), vp]),
+    'factk_gemm_tc': (i32, [C.POINTER(Gemm), vp]),
+    'factk_gemm_tc_supported': (i32, [C.POINTER(Gemm)]),
     'factk_softmax_splice': (i32, [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp]),
     'factk_layernorm': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, f32, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
     'factk_l2norm': (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, f32, vp]),

@@ -46,7 +46,7 @@ __device__ __forceinline__ void load_w8(const factk_gemm_t& g, const factk_src_t
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[j] = 0.f;
     if (n >= g.N) return;
-    const float* wr = s.W + (size_t)b * (size_t)s.w_bstride + (size_t)n * (size_t)s.ldw;
+    const float* wr = reinterpret_cast<const float*>(s.W) + (size_t)b * (size_t)s.w_bstride + (size_t)n * (size_t)s.ldw;
     const bool vec = ((reinterpret_cast<uintptr_t>(s.W) & 15u) == 0) && ((s.ldw & 3) == 0) && ((s.w_bstride & 3) == 0);
     if (vec && k + 8 <= s.K) {
         float4 v0 = *reinterpret_cast<const float4*>(wr + k), v1 = *reinterpret_cast<const float4*>(wr + k + 4);
@@ -127,12 +127,14 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ f
     const bool yvec = ((reinterpret_cast<uintptr_t>(g.Y) & 15u) == 0) && ((g.ldy & 3) == 0);
     const bool rvec = g.res && ((reinterpret_cast<uintptr_t>(g.res) & 15u) == 0) && ((g.ldres & 3) == 0);
     const float* bias = g.bias ? g.bias + (size_t)b * (size_t)g.bias_bstride : nullptr;
+    const size_t pre_base = (size_t)b * (size_t)g.pre_bstride;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = t0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (r >= len_b) continue;
         const size_t yrow = ((size_t)b * g.slot + r) * (size_t)g.ldy;
         const size_t rrow = ((size_t)b * g.slot + r) * (size_t)g.ldres;
+        const size_t prow = g.pre ? pre_base + (size_t)(g.pre_idx ? g.pre_idx[(size_t)b * g.slot + r] : r) * (size_t)g.ldpre : 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int c = n0 + h * 64 + tx * 4;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ f
             for (int j = 0; j < 4; ++j) {
                 float x = acc[i][h * 4 + j] * g.alpha;
                 if (bias && c + j < g.N) x += bias[c + j];
+                if (g.pre && c + j < g.N) x += ld_elem(g.pre, g.pre_dtype, prow + c + j);
                 if (g.relu) x = fmaxf(x, 0.f);
                 v[j] = x;
             }
@@ -184,6 +187,7 @@ extern "C" int factk_gemm(const factk_gemm_t* g, void* stream) {
         const factk_src_t& x = g->src[s];
         FACTK_REQUIRE(x.A && x.W && x.K > 0 && x.lda >= x.K && x.ldw >= x.K, "factk_gemm: bad source %d", s);
         FACTK_REQUIRE(x.a_dtype == FACTK_F32 || x.a_dtype == FACTK_BF16, "factk_gemm: bad a_dtype");
+        FACTK_REQUIRE(x.w_dtype == FACTK_F32, "factk_gemm: weights must be fp32 (source %d)", s);
     }
     const int tpv = (g->slot + BM - 1) / BM;
     dim3 grid((unsigned)(tpv * g->B), (unsigned)((g->N + BN - 1) / BN));

@@ -304,7 +304,6 @@ class FactEngine:
         self._refresh_weights()
         lengths = [int(s.shape[0]) for s in seqs]
         B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
-        self.dev = seqs[0].device
         x = self.buf('input', (B, slot, D))
         for b, s in enumerate(seqs):
             x[b, :lengths[b]].copy_(s, non_blocking=True)

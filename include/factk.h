@@ -57,10 +57,12 @@ typedef struct {
     int32_t pos_ld;
     int32_t pos_d;
     int32_t ldw;
+    int32_t w_dtype;      /* FACTK_F32 for factk_gemm; FACTK_BF16 (or FACTK_F32 = tf32 math) for factk_gemm_tc */
+    int32_t reserved_;
     const int32_t* gather;  /* optional [B][slot] source-row index (seg->frame upsample, blocks.py:442) */
     const float* pos;       /* optional table [n][pos_ld]; added to channels < pos_d */
     const int32_t* pos_idx; /* optional [B][slot] row index into pos (seg_center, blocks.py:454-455); default: row */
-    const float* W;         /* [N][ldw] fp32, y = A W^T */
+    const void* W;          /* [N][ldw] of w_dtype, y = A W^T */
     int64_t w_bstride;      /* elements between per-video weights; 0 = shared */
 } factk_src_t;
 
@@ -70,16 +72,30 @@ typedef struct {
     factk_src_t src[FACTK_MAX_SRC];
     const float* bias;      /* [N] or NULL */
     int64_t bias_bstride;
-    float alpha;            /* y = relu?(alpha * sum + bias) + res */
+    float alpha;            /* y = relu?(alpha * sum + bias + pre) + res */
     int32_t relu;
+    const void* pre;        /* optional pre-activation addend rows: pre[b*pre_bstride + idx(t)*ldpre + n] */
+    const int32_t* pre_idx; /* optional [B][slot] row index into pre (default: t) */
+    int64_t pre_bstride;    /* elements between per-video blocks of pre; 0 = shared table */
+    int32_t pre_dtype, ldpre;
     const void* res;        /* optional residual [B][slot][ldres], added after the activation */
     int32_t res_dtype, ldres;
     void* Y;                /* [B][slot][ldy] */
     int32_t y_dtype, ldy;
 } factk_gemm_t;
 
-/* y[b,t,:N] = act(alpha * sum_s A_s[b, idx_s(t)] W_s[b]^T + bias) + res.  fp32 accumulate (CUDA cores). */
+/* y[b,t,:N] = act(alpha * sum_s A_s[b, idx_s(t)] W_s[b]^T + bias + pre) + res.  fp32 accumulate (CUDA cores). */
 int factk_gemm(const factk_gemm_t* g, void* stream);
+
+/* Same contract on the 5th-generation tensor cores: TMA-staged operands (128B-swizzled shared memory),
+ * tcgen05.mma with fp32 accumulators in tensor memory, epilogue from TMEM.  Restrictions (else
+ * FACTK_ERR_UNSUPPORTED): every source has the same dtype -- bf16 A with bf16 W (kind::f16), or fp32 A
+ * with fp32 W (kind::tf32, operands truncated to tf32 by the tensor core); K a multiple of 64 (bf16) /
+ * 32 (fp32); no gather / pos on sources (use `pre`); 16-byte aligned rows; slot a multiple of 128.
+ * Rows of A in [len[b], slot) must be zero where convolution taps (row_off != 0) can reach them. */
+int factk_gemm_tc(const factk_gemm_t* g, void* stream);
+/* 1 if factk_gemm_tc accepts this descriptor, 0 otherwise (no launch). */
+int factk_gemm_tc_supported(const factk_gemm_t* g);
 
 /* Block.process_feature (blocks.py:195-202) in place on rows [B][slot][ld] of width H: the last C
  * channels are logits -> clogit_out fp32 [B][slot][C]; they are overwritten by softmax(logits).
