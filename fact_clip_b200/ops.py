@@ -39,7 +39,7 @@ def _row_ld(t):
     return t.stride(-2)
 
 
-def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None, tag=None):
+def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None, tag=None, tc=False, pre=None, pre_idx=None):
     g = L.Gemm()
     B, slot = out.shape[0], out.shape[1]
     g.B, g.slot, g.N, g.nsrc = B, slot, N, len_(srcs)
@@ -56,13 +56,17 @@ def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None, tag
             x.pos, x.pos_ld = s['pos'].data_ptr(), s['pos'].stride(0)
             x.pos_d = s['pos_d'] if s['pos_d'] is not None else s['pos'].shape[-1]
             x.pos_idx = L.ptr(s['pos_idx'])
-        assert W.dtype == torch.float32 and W.stride(-1) == 1
-        x.W, x.ldw = W.data_ptr(), W.stride(-2)
+        assert W.stride(-1) == 1
+        x.W, x.ldw, x.w_dtype = W.data_ptr(), W.stride(-2), L.dt(W)
         x.w_bstride = W.stride(0) if W.dim() == 3 else 0
     if bias is not None:
         g.bias = bias.data_ptr()
         g.bias_bstride = bias.stride(0) if bias.dim() == 2 else 0
     g.alpha, g.relu = float(alpha), int(relu)
+    if pre is not None:
+        g.pre, g.pre_dtype, g.ldpre = pre.data_ptr(), L.dt(pre), _row_ld(pre)
+        g.pre_bstride = pre.stride(0) if pre.dim() == 3 else 0
+        g.pre_idx = L.ptr(pre_idx)
     if res is not None:
         g.res, g.res_dtype, g.ldres = res.data_ptr(), L.dt(res), _row_ld(res)
     g.Y, g.y_dtype, g.ldy = out.data_ptr(), L.dt(out), _row_ld(out)
@@ -70,7 +74,7 @@ def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None, tag
     if timed:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    L.call('factk_gemm', g, L.stream())
+    L.call('factk_gemm_tc' if tc else 'factk_gemm', g, L.stream())
     if timed:
         e1.record()
         TIMER.pairs[tag].append((e0, e1))
