@@ -29,7 +29,8 @@ class FactEngine:
         assert mode in ('bf16', 'fp32')
         self.m, self.hp, self.clip, self.mode = module, hp, clip, mode
         self.act = torch.bfloat16 if mode == 'bf16' else torch.float32
-        self._bufs = {}
+        self._bufs, self._zbufs, self._len_sig = {}, {}, None
+        self.use_tc = True
         self._wcache, self._wsig = {}, None
 
     # ------------------------------------------------------------------ memory / weights
@@ -40,6 +41,35 @@ class FactEngine:
             t = torch.empty(shape, dtype=dtype, device=self.dev)
             self._bufs[key] = t
         return t
+
+    def zbuf(self, name, shape, dtype):
+        """Buffer that feeds convolution taps: rows in [len, slot) must read as zero for the TMA path, so it is
+        zero-initialised and re-zeroed whenever the batch's lengths change (no kernel ever writes those rows)."""
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self.dev)
+            self._bufs[key] = t
+            self._zbufs[key] = t
+        return t
+
+    def wbf(self, W):
+        """bf16 copy of an fp32 weight view (cached until the master parameters change)."""
+        key = ('bf16', W.data_ptr(), tuple(W.shape), tuple(W.stride()))
+        return self.derived(key, lambda: W.to(torch.bfloat16))
+
+    def mm(self, srcs, N, out, tf32=False, **kw):
+        """GEMM dispatch: tcgen05 kernel when the operands qualify (bf16 mode), CUDA-core kernel otherwise."""
+        if self.mode == 'bf16' and self.use_tc:
+            dts = {s['A'].dtype for s in srcs}
+            plain = all(s['gather'] is None and s['pos'] is None and s['W'].dim() == 2 for s in srcs)
+            if plain and dts == {torch.bfloat16} and all((s['K'] or s['W'].shape[-1]) % 64 == 0 for s in srcs):
+                for s in srcs:
+                    s['W'] = self.wbf(s['W'])
+                return ops.gemm(srcs, N, out, tc=True, **kw)
+            if plain and tf32 and dts == {torch.float32} and all((s['K'] or s['W'].shape[-1]) % 32 == 0 for s in srcs):
+                return ops.gemm(srcs, N, out, tc=True, **kw)
+        return ops.gemm(srcs, N, out, **kw)
 
     def _refresh_weights(self):
         params = dict(self.m.named_parameters())
@@ -77,12 +107,12 @@ class FactEngine:
         x: [B, slot, Din].  Returns (frame_feature [B,slot,H] act dtype, frame_clogit fp32, pred int32)."""
         B, slot, F, H, Lr, C = self.B, self.slot, bc['f_dim'], bc['hid_dim'], bc['f_layers'], self.hp['n_classes']
         ln = self.len
-        fa, fb = self.buf('f_a', (B, slot, F), self.act), self.buf('f_b', (B, slot, F), self.act)
+        fa, fb = self.zbuf('f_a', (B, slot, F), self.act), self.zbuf('f_b', (B, slot, F), self.act)
         m2 = bc['f'] == 'm2'
         other = lambda t: fb if t is fa else fa
         if in_map:
             w = pfx + ('conv_1x1_in' if m2 else 'conv_1x1')
-            ops.gemm([S(x, self.taps(w + '.weight')[0])], F, fa, len=ln, bias=self.p(w + '.bias'))
+            self.mm([S(x, self.taps(w + '.weight')[0])], F, fa, tf32=True, len=ln, bias=self.p(w + '.bias'))
             cur, nxt = fa, fb
         else:
             cur, nxt = x, fa
@@ -91,21 +121,21 @@ class FactEngine:
                 q = f'{pfx}layers.{i}.'
                 w3, d = self.taps(q + 'conv_dilated.weight'), 2 ** i
                 tmp = self.buf('f_tmp', (B, slot, F), self.act)
-                ops.gemm([S(cur, w3[k], off=(k - 1) * d) for k in range(3)], F, tmp, len=ln,
-                         bias=self.p(q + 'conv_dilated.bias'), relu=True, tag='tcn_conv3')
-                ops.gemm([S(tmp, self.taps(q + 'conv_1x1.weight')[0])], F, nxt, len=ln,
-                         bias=self.p(q + 'conv_1x1.bias'), res=cur, tag='tcn_1x1')
+                self.mm([S(cur, w3[k], off=(k - 1) * d) for k in range(3)], F, tmp, len=ln,
+                        bias=self.p(q + 'conv_dilated.bias'), relu=True, tag='tcn_conv3')
+                self.mm([S(tmp, self.taps(q + 'conv_1x1.weight')[0])], F, nxt, len=ln,
+                        bias=self.p(q + 'conv_1x1.bias'), res=cur, tag='tcn_1x1')
             else:
                 tmp = self.buf('f_tmp2', (B, slot, 2 * F), self.act)
                 for j, (nm, d) in enumerate(((f'{pfx}conv_dilated_1.{i}', 2 ** (Lr - 1 - i)), (f'{pfx}conv_dilated_2.{i}', 2 ** i))):
                     w3 = self.taps(nm + '.weight')
-                    ops.gemm([S(cur, w3[k], off=(k - 1) * d) for k in range(3)], F, tmp[:, :, j * F:(j + 1) * F],
-                             len=ln, bias=self.p(nm + '.bias'))
-                ops.gemm([S(tmp, self.taps(f'{pfx}conv_fusion.{i}.weight')[0])], F, nxt, len=ln,
-                         bias=self.p(f'{pfx}conv_fusion.{i}.bias'), relu=True, res=cur)
+                    self.mm([S(cur, w3[k], off=(k - 1) * d) for k in range(3)], F, tmp[:, :, j * F:(j + 1) * F],
+                            len=ln, bias=self.p(nm + '.bias'))
+                self.mm([S(tmp, self.taps(f'{pfx}conv_fusion.{i}.weight')[0])], F, nxt, len=ln,
+                        bias=self.p(f'{pfx}conv_fusion.{i}.bias'), relu=True, res=cur)
             cur, nxt = nxt, other(nxt)
         out = self.buf('frame_' + tag, (B, slot, H), self.act)
-        ops.gemm([S(cur, self.taps(pfx + 'conv_out.weight')[0])], H, out, len=ln, bias=self.p(pfx + 'conv_out.bias'))
+        self.mm([S(cur, self.taps(pfx + 'conv_out.weight')[0])], H, out, len=ln, bias=self.p(pfx + 'conv_out.bias'))
         clogit = self.buf('fclogit_' + tag, (B, slot, C))
         pred = self.buf('fpred_' + tag, (B, slot), torch.int32)
         ops.softmax_splice(out, C, clogit, pred, len=ln)
@@ -157,8 +187,12 @@ class FactEngine:
                 wq, wk, wv = self.p(c + 'q_proj_weight'), self.p(c + 'k_proj_weight'), self.p(c + 'v_proj_weight')
             cq = self.buf('tok_cq', (B, M, A))
             ops.gemm([S(tgt, wq, pos=qpos)], A, cq, bias=cb[:A])
-            ops.gemm([S(frame, wk, pos=fpos)], A, kv[:, :, :A], len=self.len, bias=cb[A:2 * A])
-            ops.gemm([S(frame, wv)], A, kv[:, :, A:], len=self.len, bias=cb[2 * A:])
+            if fpos is None:
+                wkv = self.derived(('wkv', c), lambda: torch.cat([wk, wv], 0))
+                self.mm([S(frame, wkv)], 2 * A, kv, len=self.len, bias=cb[A:])
+            else:
+                ops.gemm([S(frame, wk, pos=fpos)], A, kv[:, :, :A], len=self.len, bias=cb[A:2 * A])
+                self.mm([S(frame, wv)], A, kv[:, :, A:], len=self.len, bias=cb[2 * A:])
             o = self.buf('tok_o', (B, M, A))
             ops.attn_rows(cq, kv[:, :, :A], kv[:, :, A:], o, nh, ws, len=self.len)
             ops.gemm([S(o, self.p(c + 'out_proj.weight'))], A, t, bias=self.p(c + 'out_proj.bias'), res=tgt)
@@ -240,7 +274,7 @@ class FactEngine:
         W = self.p(pfx + 'Y_W.weight')                                      # [F, 2H] = [Wy | Wa]
         vt = self.buf('x2y_vt', (B, F, Mp))                                 # vt[b,f,m] = sum_h Wa[f,h] xv[b,m,h]
         ops.gemm([S(W[None, :, H:], xv)], M, vt)
-        out = self.buf('a2f_out', (B, slot, F), self.act)
+        out = self.zbuf('a2f_out', (B, slot, F), self.act)
         ops.gemm([S(rows, W[:, :H]), S(attn, vt, K=M)], F, out, len=rlen, bias=self.p(pfx + 'Y_W.bias'))
         return out, logit, attn
 
@@ -272,17 +306,17 @@ class FactEngine:
         nseg = self.buf('nseg_' + tag, (B,), I32)
         ops.tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=self.len)
         st.update(seg_label=seg_label, seg_lens=seg_len, nseg=nseg, tdu_pred=pred)
-        seg0 = self.buf('seg0', (B, slot, H))
+        seg0 = self.buf('seg0', (B, slot, H), self.act)
         ops.segment_mean(frame, seg0, seg_start, seg_len, nseg)
         g = pfx + 'seg_update.'
         gi = self.buf('gru_gi', (B, slot, 6 * Hh))
-        ops.gemm([S(seg0, self.cat(g + 'weight_ih_l0', g + 'weight_ih_l0_reverse'))], 6 * Hh, gi, len=nseg,
-                 bias=self.cat(g + 'bias_ih_l0', g + 'bias_ih_l0_reverse'))
-        seg1 = self.buf('seg1', (B, slot, H))
+        self.mm([S(seg0, self.cat(g + 'weight_ih_l0', g + 'weight_ih_l0_reverse'))], 6 * Hh, gi, len=nseg,
+                bias=self.cat(g + 'bias_ih_l0', g + 'bias_ih_l0_reverse'))
+        seg1 = self.buf('seg1', (B, slot, H), self.act)
         ops.gru_bidir(gi, self.p(g + 'weight_hh_l0'), self.p(g + 'bias_hh_l0'), self.p(g + 'weight_hh_l0_reverse'),
                       self.p(g + 'bias_hh_l0_reverse'), seg1, nseg, relu=True)
         seg2 = self.buf('seg2', (B, slot, H), self.act)
-        ops.gemm([S(seg1, self.p(pfx + 'seg_combine.weight'))], H, seg2, len=nseg, bias=self.p(pfx + 'seg_combine.bias'))
+        self.mm([S(seg1, self.p(pfx + 'seg_combine.weight'))], H, seg2, len=nseg, bias=self.p(pfx + 'seg_combine.bias'))
         st['seg_clogit'] = self.buf('seg_clogit_' + tag, (B, slot, C))
         ops.softmax_splice(seg2, C, st['seg_clogit'], None, len=nseg)
         pidx = seg_center if self.frame_pos is not None else None
@@ -291,9 +325,12 @@ class FactEngine:
         st['action_clogit'] = self.token_splice(action, tag)
         seg3, st['a2f_attn_logit'], st['a2f_attn_seg'] = self.a2f(pfx + 'a2f_layer.', bc, action, seg2, nseg, pidx, tag)
         W = self.p(pfx + 'sf_merge.0.weight')                               # [F, F+H], input = cat[s2f, frame]
-        fr = self.buf('sf_out', (B, slot, F), self.act)
-        ops.gemm([S(seg3, W[:, :F], gather=seg_label), S(frame, W[:, F:])], F, fr, len=self.len,
-                 bias=self.p(pfx + 'sf_merge.0.bias'), relu=True)
+        fr = self.zbuf('sf_out', (B, slot, F), self.act)
+        # cat[s2f, frame] W^T = (seg3 W1^T)[seg_label] + frame W2^T: the gather moves to a segment-level product
+        s2f = self.buf('sf_pre', (B, slot, F))
+        self.mm([S(seg3, W[:, :F])], F, s2f, len=nseg)
+        self.mm([S(frame, W[:, F:])], F, fr, len=self.len, bias=self.p(pfx + 'sf_merge.0.bias'), relu=True,
+                pre=s2f, pre_idx=seg_label)
         frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, fr, False, tag)
         return frame, action
 
@@ -316,6 +353,10 @@ class FactEngine:
         self._refresh_weights()
         hp = self.hp
         self.B, self.slot, self.len, self.keep = x.shape[0], x.shape[1], ln, keep
+        if self._len_sig != tuple(lengths):
+            for t in self._zbufs.values():
+                t.zero_()
+            self._len_sig = tuple(lengths)
         B, slot, M, C, H = self.B, self.slot, hp['ntoken'], hp['n_classes'], hp['blocks'][0]['hid_dim']
         self.frame_pos = None
         if hp['fpos']:
@@ -344,13 +385,14 @@ class FactEngine:
         if self.clip and 'text_embeddings' in self._p and self._p['text_embeddings'] is not None:
             P = self.p('frame_projection.projection.0.weight').shape[0]
             h1 = self.buf('clip_h1', (B, slot, P), self.act)
-            ops.gemm([S(frame, self.p('frame_projection.projection.0.weight'), K=H - C)], P, h1, len=ln,
-                     bias=self.p('frame_projection.projection.0.bias'))
+            w0 = self.derived(('clip_w0pad',), lambda: torch.nn.functional.pad(self.p('frame_projection.projection.0.weight'), (0, C)))
+            self.mm([S(frame, w0)], P, h1, len=ln,
+                    bias=self.p('frame_projection.projection.0.bias'))
             ops.layernorm(h1, self.p('frame_projection.projection.1.weight'), self.p('frame_projection.projection.1.bias'),
                           h1, relu=True, len=ln)
             emb = self.buf('clip_emb', (B, slot, 512))
-            ops.gemm([S(h1, self.p('frame_projection.projection.4.weight'))], 512, emb, len=ln,
-                     bias=self.p('frame_projection.projection.4.bias'))
+            self.mm([S(h1, self.p('frame_projection.projection.4.weight'))], 512, emb, len=ln,
+                    bias=self.p('frame_projection.projection.4.bias'))
             ops.l2norm(emb, emb, len=ln)
             flogit = self.buf('clip_logit', (B, slot, C))
             ops.gemm([S(emb, self.p('text_embeddings'))], C, flogit, len=ln, alpha=1.0 / hp['temp'])

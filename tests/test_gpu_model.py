@@ -151,3 +151,46 @@ def test_shipped_configs_vs_oracle_fp32(preset, ncls, lens):
         if seg_ok:
             assert (saves[b]['pred'] == o['pred'].numpy()).mean() >= 0.999
     print(preset, rows)
+
+
+@pytest.mark.parametrize('preset,ncls,lens', CFGS)
+def test_shipped_configs_bf16_tensor_core_path(preset, ncls, lens):
+    """bf16 mode (tcgen05 GEMMs) vs the fp32 oracle with the oracle's segmentation forced:
+    per-block logits within 2e-2 relative (north_star), final argmax >= 99.9 % identical."""
+    cfg = C.PRESETS[preset]()
+    clip = bool(cfg.use_clip)
+    torch.manual_seed(0)
+    net = (FACT_CLIP(cfg, 2048, ncls, make_text_embeddings(ncls)) if clip else FACT(cfg, 2048, ncls)).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    hp = O.hparams_from_cfg(cfg, 2048, ncls)
+    xs, ys = make_batch(lens, 2048, ncls, base_seed=40, nseg=8)
+    outs = []
+    for x in xs:
+        with torch.no_grad():
+            outs.append(O.forward_video(sd, hp, x, clip=clip, fast_gru=True))
+    nU = sum(1 for b in hp['blocks'] if b['type'] == 'U')
+    forced = [[[b_['tdu_pred'] for b_ in o['blocks'] if 'tdu_pred' in b_][u].to(DEV) for o in outs] for u in range(nU)]
+    net.compute_mode, net.keep_attn = 'bf16', True
+    net = net.to(DEV)
+    saves = net([x.to(DEV) for x in xs], [y.to(DEV) for y in ys], forced_preds=forced)
+    rows, agree, tot = [], 0, 0
+    for b, o in enumerate(outs):
+        net.stash_video(b)
+        for i, (blk, st) in enumerate(zip(net.block_list, o['blocks'])):
+            for k in ('frame_clogit', 'action_clogit', 'seg_clogit'):
+                if k in st:
+                    r = rel(getattr(blk, k)[:, 0], st[k])
+                    rows.append((b, i, k, round(r, 5)))
+                    assert r < 2e-2, (preset, b, i, k, r)
+            if 'a2f_attn' in st:
+                r = rel(blk.a2f_attn[0], st['a2f_attn'])
+                rows.append((b, i, 'a2f_attn', round(r, 5)))
+                assert r < 2e-2, (preset, b, i, 'a2f_attn', r)
+        if clip:
+            r = rel(net._last['clip_logit'][b, :lens[b]], o['clip_logit'])
+            rows.append((b, 'clip_logit', round(r, 5)))
+            assert r < 2e-2
+        agree += int((saves[b]['pred'] == o['pred'].numpy()).sum())
+        tot += lens[b]
+    print(preset, rows)
+    assert agree / tot >= 0.999
