@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const void* X, int x_dtype,
 }
 
 __global__ void __launch_bounds__(256) row_softmax_kernel(const float* L, int ldl, float* P, int ldp, int B, int slot,
-                                                          const int32_t* len, int M, float scale) {
+                                                          const int32_t* len, int M, float scale, __nv_bfloat16* P16,
+                                                          int ldp16, int pad16) {
     int b, t;
     if (!row_of_warp(B, slot, len, b, t)) return;
     const int lane = threadIdx.x & 31;
@@ -107,7 +108,13 @@ __global__ void __launch_bounds__(256) row_softmax_kernel(const float* L, int ld
     float sum = 0.f;
     for (int c = lane; c < M; c += 32) sum += __expf(L[row * ldl + c] * scale - mx);
     const float inv = 1.f / warp_sum(sum);
-    for (int c = lane; c < M; c += 32) P[row * ldp + c] = __expf(L[row * ldl + c] * scale - mx) * inv;
+    for (int c = lane; c < M; c += 32) {
+        const float pv = __expf(L[row * ldl + c] * scale - mx) * inv;
+        P[row * ldp + c] = pv;
+        if (P16) P16[row * ldp16 + c] = __float2bfloat16_rn(pv);
+    }
+    if (P16)
+        for (int c = M + lane; c < pad16; c += 32) P16[row * ldp16 + c] = __float2bfloat16_rn(0.f);
 }
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* in, int ldi, int in_slot, const int32_t* idx,
@@ -149,9 +156,11 @@ extern "C" int factk_l2norm(const void* X, int x_dtype, int ldx, void* Y, int y_
 }
 
 extern "C" int factk_row_softmax(const float* L, int ldl, float* P, int ldp, int B, int slot, const int32_t* len, int M,
-                                 float scale, void* stream) {
+                                 float scale, void* P16, int ldp16, int pad16, void* stream) {
     FACTK_REQUIRE(L && P && B > 0 && slot > 0 && M > 0, "factk_row_softmax: bad args");
-    row_softmax_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(L, ldl, P, ldp, B, slot, len, M, scale);
+    FACTK_REQUIRE(P16 == nullptr || (pad16 >= M && pad16 <= ldp16), "factk_row_softmax: bad bf16 copy shape");
+    row_softmax_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(L, ldl, P, ldp, B, slot, len, M, scale,
+                                                                              reinterpret_cast<__nv_bfloat16*>(P16), ldp16, pad16);
     return check_launch("factk_row_softmax");
 }
 

@@ -98,11 +98,19 @@ __global__ void __launch_bounds__(128) segment_mean_kernel(const void* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bidirectional GRU recurrence.  One 4-CTA cluster advances NB chains (videos) of one direction; CTA `rank`
+// owns hidden units [rank*U, rank*U+U) with all three gate rows of W_hh for them resident in shared memory
+// (transposed, fp32).  Per step: (1) every thread accumulates a quarter-K slice of one gate row for the NB
+// chains, (2) one thread per (chain, unit) sums the partials, applies the gates and writes the new hidden
+// value into the next-step buffer of all four CTAs through distributed shared memory, (3) a split cluster
+// barrier (arrive.release ... wait.acquire) with the global store of the output and the prefetch of the
+// next step's input gates placed between arrive and wait so their latency is off the critical path.
 constexpr int GRU_CS = 4;   // CTAs per cluster
-constexpr int GRU_NB = 4;   // chains (videos) advanced together by one cluster
+constexpr int GRU_KQ = 4;   // K split of the mat-vec inside a CTA
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
+template <int NB>
 __global__ void __cluster_dims__(GRU_CS, 1, 1)
 gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, const float* __restrict__ bhh_f,
                    const float* __restrict__ whh_b, const float* __restrict__ bhh_b, int Hh, void* out, int o_dtype,
@@ -111,11 +119,11 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / GRU_CS;
     const int dir = cid & 1, grp = cid >> 1;
-    const int U = Hh / GRU_CS, R = 3 * U;
+    const int U = Hh / GRU_CS, R = 3 * U, KS = Hh / GRU_KQ;
     extern __shared__ __align__(16) float sm[];
-    float* Wt = sm;                                  // [Hh][R]   transposed slice of W_hh
-    float* hb = Wt + (size_t)Hh * R;                 // [2][NB][Hh] double-buffered hidden state
-    float* gx = hb + 2 * GRU_NB * Hh;                // [NB][2][U]  sigmoid(r), sigmoid(z)
+    float* Wt = sm;                                  // [Hh][R]        transposed slice of W_hh
+    float* hb = Wt + (size_t)Hh * R;                 // [2][NB][Hh]    double-buffered hidden state
+    float* part = hb + 2 * NB * Hh;                  // [NB][KQ][R]    partial dot products
     const float* whh = dir ? whh_b : whh_f;
     const float* bhh = dir ? bhh_b : bhh_f;
     const int tid = threadIdx.x;
@@ -124,81 +132,91 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
         const int k = i / R, j = i % R, g = j / U, u = j % U;
         Wt[i] = whh[((size_t)g * Hh + rank * U + u) * Hh + k];
     }
-    for (int i = tid; i < 2 * GRU_NB * Hh; i += blockDim.x) hb[i] = 0.f;
+    for (int i = tid; i < 2 * NB * Hh; i += blockDim.x) hb[i] = 0.f;
 
-    int S[GRU_NB], vb[GRU_NB], maxS = 0;
+    int S[NB], vb[NB], maxS = 0;
 #pragma unroll
-    for (int nb = 0; nb < GRU_NB; ++nb) {
-        vb[nb] = grp * GRU_NB + nb;
+    for (int nb = 0; nb < NB; ++nb) {
+        vb[nb] = grp * NB + nb;
         S[nb] = (vb[nb] < B) ? min(nseg[vb[nb]], slot) : 0;
         maxS = max(maxS, S[nb]);
     }
-    const bool active = tid < R;
-    const int g = active ? tid / U : 0, u = active ? tid % U : 0, unit = rank * U + u;
-    const float bias = active ? bhh[g * Hh + unit] : 0.f;
-    const size_t gstride = (size_t)6 * Hh;
-
-    float gin[GRU_NB];
-    auto load_gi = [&](int t) {
+    // mat-vec role
+    const bool mv = tid < GRU_KQ * R;
+    const int kq = mv ? tid / R : 0, j = mv ? tid % R : 0;
+    // gate role: one thread per (chain, owned unit)
+    const bool gate = tid < NB * U;
+    const int gnb = gate ? tid / U : 0, gu = gate ? tid % U : 0, unit = rank * U + gu;
+    int myS = 0, myv = 0;
 #pragma unroll
-        for (int nb = 0; nb < GRU_NB; ++nb) {
-            gin[nb] = 0.f;
-            if (active && t < S[nb]) {
-                const int s = dir ? S[nb] - 1 - t : t;
-                gin[nb] = gi[((size_t)vb[nb] * slot + s) * gstride + (size_t)dir * 3 * Hh + (size_t)g * Hh + unit];
-            }
+    for (int nb = 0; nb < NB; ++nb)
+        if (nb == gnb) { myS = S[nb]; myv = vb[nb]; }
+    if (!gate) myS = 0;
+    float b_r = 0.f, b_z = 0.f, b_n = 0.f;
+    if (gate) { b_r = bhh[unit]; b_z = bhh[Hh + unit]; b_n = bhh[2 * Hh + unit]; }
+    const size_t gstride = (size_t)6 * Hh;
+    float g_r = 0.f, g_z = 0.f, g_n = 0.f;
+    auto load_gi = [&](int t) {
+        if (t < myS) {
+            const int s = dir ? myS - 1 - t : t;
+            const float* p = gi + ((size_t)myv * slot + s) * gstride + (size_t)dir * 3 * Hh + unit;
+            g_r = __ldg(p); g_z = __ldg(p + Hh); g_n = __ldg(p + 2 * Hh);
         }
     };
     load_gi(0);
+    float* hb_remote[GRU_CS];
+#pragma unroll
+    for (int rr = 0; rr < GRU_CS; ++rr) hb_remote[rr] = cluster.map_shared_rank(hb, rr);
     __syncthreads();
     cluster.sync();
 
     for (int t = 0; t < maxS; ++t) {
         const int cur = t & 1;
-        const float* h = hb + cur * GRU_NB * Hh;
-        float acc[GRU_NB];
+        const float* h = hb + cur * NB * Hh;
+        if (mv) {
+            float acc[NB];
 #pragma unroll
-        for (int nb = 0; nb < GRU_NB; ++nb) acc[nb] = bias;
-        if (active) {
-            for (int k = 0; k < Hh; k += 4) {
-                const float w0 = Wt[(size_t)(k + 0) * R + tid], w1 = Wt[(size_t)(k + 1) * R + tid];
-                const float w2 = Wt[(size_t)(k + 2) * R + tid], w3 = Wt[(size_t)(k + 3) * R + tid];
+            for (int nb = 0; nb < NB; ++nb) acc[nb] = 0.f;
+            const float* wcol = Wt + (size_t)(kq * KS) * R + j;
+            const float* hk = h + kq * KS;
+#pragma unroll 4
+            for (int k = 0; k < KS; k += 4) {
+                const float w0 = wcol[(size_t)(k + 0) * R], w1 = wcol[(size_t)(k + 1) * R];
+                const float w2 = wcol[(size_t)(k + 2) * R], w3 = wcol[(size_t)(k + 3) * R];
 #pragma unroll
-                for (int nb = 0; nb < GRU_NB; ++nb) {
-                    const float4 h4 = *reinterpret_cast<const float4*>(&h[nb * Hh + k]);
+                for (int nb = 0; nb < NB; ++nb) {
+                    const float4 h4 = *reinterpret_cast<const float4*>(&hk[nb * Hh + k]);
                     acc[nb] = fmaf(w0, h4.x, acc[nb]); acc[nb] = fmaf(w1, h4.y, acc[nb]);
                     acc[nb] = fmaf(w2, h4.z, acc[nb]); acc[nb] = fmaf(w3, h4.w, acc[nb]);
                 }
             }
-        }
-        float gcur[GRU_NB];
 #pragma unroll
-        for (int nb = 0; nb < GRU_NB; ++nb) gcur[nb] = gin[nb];
-        if (t + 1 < maxS) load_gi(t + 1);
-        if (active && g < 2) {
-#pragma unroll
-            for (int nb = 0; nb < GRU_NB; ++nb) gx[(nb * 2 + g) * U + u] = sigmoidf_(gcur[nb] + acc[nb]);
+            for (int nb = 0; nb < NB; ++nb) part[(nb * GRU_KQ + kq) * R + j] = acc[nb];
         }
         __syncthreads();
-        if (active && g == 2) {
+        float hn = 0.f;
+        const bool live = gate && t < myS;
+        if (live) {
+            const float* pp = part + (size_t)gnb * GRU_KQ * R;
+            float a_r = b_r, a_z = b_z, a_n = b_n;
 #pragma unroll
-            for (int nb = 0; nb < GRU_NB; ++nb) {
-                if (t < S[nb]) {
-                    const float r = gx[(nb * 2 + 0) * U + u], z = gx[(nb * 2 + 1) * U + u];
-                    const float n = tanhf(gcur[nb] + r * acc[nb]);
-                    const float hn = (1.f - z) * n + z * h[nb * Hh + unit];
-#pragma unroll
-                    for (int rr = 0; rr < GRU_CS; ++rr) {
-                        float* dst = cluster.map_shared_rank(hb, rr);
-                        dst[(cur ^ 1) * GRU_NB * Hh + nb * Hh + unit] = hn;
-                    }
-                    const int s = dir ? S[nb] - 1 - t : t;
-                    st_elem(out, o_dtype, ((size_t)vb[nb] * slot + s) * (size_t)ldo + (size_t)dir * Hh + unit,
-                            relu ? fmaxf(hn, 0.f) : hn);
-                }
+            for (int q = 0; q < GRU_KQ; ++q) {
+                a_r += pp[q * R + gu]; a_z += pp[q * R + U + gu]; a_n += pp[q * R + 2 * U + gu];
             }
+            const float r = sigmoidf_(g_r + a_r), z = sigmoidf_(g_z + a_z);
+            const float n = tanhf(g_n + r * a_n);
+            hn = (1.f - z) * n + z * h[gnb * Hh + unit];
+            const int o = (cur ^ 1) * NB * Hh + gnb * Hh + unit;
+#pragma unroll
+            for (int rr = 0; rr < GRU_CS; ++rr) hb_remote[rr][o] = hn;
         }
-        cluster.sync();
+        cluster.barrier_arrive();
+        if (live) {
+            const int s = dir ? myS - 1 - t : t;
+            st_elem(out, o_dtype, ((size_t)myv * slot + s) * (size_t)ldo + (size_t)dir * Hh + unit, relu ? fmaxf(hn, 0.f) : hn);
+        }
+        load_gi(t + 1);
+        cluster.barrier_wait();
     }
 }
 
@@ -230,13 +248,26 @@ extern "C" int factk_gru_bidir(const float* gi, const float* w_hh_f, const float
     FACTK_REQUIRE(gi && w_hh_f && b_hh_f && w_hh_b && b_hh_b && out && nseg && B > 0 && slot > 0, "factk_gru_bidir: bad args");
     FACTK_REQUIRE(Hh > 0 && Hh % (4 * GRU_CS) == 0, "factk_gru_bidir: hidden size %d must be a multiple of %d", Hh, 4 * GRU_CS);
     const int U = Hh / GRU_CS, R = 3 * U;
-    const size_t smem = ((size_t)Hh * R + 2 * GRU_NB * Hh + GRU_NB * 2 * U) * sizeof(float);
-    FACTK_REQUIRE(smem <= 227 * 1024 && R <= 1024, "factk_gru_bidir: hidden size %d does not fit one cluster (%zu B smem)", Hh, smem);
-    cudaError_t e = cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("factk_gru_bidir: smem attr: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; }
-    const int groups = (B + GRU_NB - 1) / GRU_NB;
-    const int threads = ((R + 31) / 32) * 32;
-    gru_cluster_kernel<<<groups * 2 * GRU_CS, threads, smem, (cudaStream_t)stream>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, Hh,
-                                                                                      out, o_dtype, ldo, relu, B, slot, nseg);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // chains advanced per cluster: as few as possible while all clusters are co-resident (one CTA per SM)
+    int NB = 1;
+    while (NB < 4 && ((B + NB - 1) / NB) * 2 * GRU_CS > sms - 16) NB *= 2;
+    const size_t smem = ((size_t)Hh * R + 2 * NB * Hh + (size_t)NB * GRU_KQ * R) * sizeof(float);
+    FACTK_REQUIRE(smem <= 227 * 1024 && GRU_KQ * R <= 1024, "factk_gru_bidir: hidden size %d does not fit one cluster (%zu B smem)", Hh, smem);
+    const int groups = (B + NB - 1) / NB;
+    int threads = GRU_KQ * R > NB * U ? GRU_KQ * R : NB * U;
+    threads = ((threads + 31) / 32) * 32;
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(N_)                                                                                                          \
+    do {                                                                                                                    \
+        cudaError_t e = cudaFuncSetAttribute(gru_cluster_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) { set_error("factk_gru_bidir: smem attr: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; } \
+        gru_cluster_kernel<N_><<<groups * 2 * GRU_CS, threads, smem, st>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, Hh, out,    \
+                                                                          o_dtype, ldo, relu, B, slot, nseg);              \
+    } while (0)
+    if (NB == 1) LAUNCH(1); else if (NB == 2) LAUNCH(2); else LAUNCH(4);
+#undef LAUNCH
     return check_launch("factk_gru_bidir");
 }

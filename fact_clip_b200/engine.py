@@ -58,6 +58,10 @@ class FactEngine:
         key = ('bf16', W.data_ptr(), tuple(W.shape), tuple(W.stride()))
         return self.derived(key, lambda: W.to(torch.bfloat16))
 
+    def x2y_tc(self, rows, H):
+        return (self.mode == 'bf16' and self.use_tc and rows.dtype == torch.bfloat16 and self.frame_pos is None
+                and H % 64 == 0)
+
     def mm(self, srcs, N, out, tf32=False, **kw):
         """GEMM dispatch: tcgen05 kernel when the operands qualify (bf16 mode), CUDA-core kernel otherwise."""
         if self.mode == 'bf16' and self.use_tc:
@@ -235,12 +239,13 @@ class FactEngine:
         alpha = 1.0 / math.sqrt(H)
         yq = self.buf('x2y_tokH', (B, M, H))
         ops.gemm([S(action, self.p(pfx + 'Y_Q.weight'), pos=qpos)], H, yq, bias=self.p(pfx + 'Y_Q.bias'))
-        qt = self.buf('x2y_qt', (B, M, H))                                  # alpha * Wk^T yq
+        tc = self.x2y_tc(rows, H)
+        qt = self.buf('x2y_qt16' if tc else 'x2y_qt', (B, M, H), torch.bfloat16 if tc else torch.float32)   # alpha * Wk^T yq
         ops.gemm([S(yq, self.tr(pfx + 'X_K.weight'))], H, qt, alpha=alpha)
         cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * yq . bk
         ops.gemm([S(yq, self.p(pfx + 'X_K.bias')[None, :])], 1, cb, alpha=alpha)
         logit = self.buf('f2a_logit_' + tag, (B, slot, Mp))
-        ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0])
+        ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc)
         attn = self.buf('f2a_attn_' + tag, (B, slot, Mp)) if want_attn else None
         xbar = self.buf('x2y_xbar', (B, M, H))
         ws = self.buf('col_ws', (ops.col_softmax_ws(B, slot, M, H),))
@@ -261,21 +266,29 @@ class FactEngine:
         alpha = 1.0 / math.sqrt(H)
         xk = self.buf('x2y_tokH', (B, M, H))
         ops.gemm([S(action, self.p(pfx + 'X_K.weight'), pos=qpos)], H, xk, bias=self.p(pfx + 'X_K.bias'))
-        kt = self.buf('x2y_qt', (B, M, H))                                  # alpha * Wq^T xk
+        tc = self.x2y_tc(rows, H)
+        kt = self.buf('x2y_qt16' if tc else 'x2y_qt', (B, M, H), torch.bfloat16 if tc else torch.float32)   # alpha * Wq^T xk
         ops.gemm([S(xk, self.tr(pfx + 'Y_Q.weight'))], H, kt, alpha=alpha)
         cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * xk . bq
         ops.gemm([S(xk, self.p(pfx + 'Y_Q.bias')[None, :])], 1, cb, alpha=alpha)
         logit = self.buf('a2f_logit_' + tag, (B, slot, Mp))
-        ops.gemm([S(rows, kt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0])
+        ops.gemm([S(rows, kt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc)
         attn = self.buf('a2f_attn_' + tag, (B, slot, Mp))
-        ops.row_softmax(logit, attn, M, len=rlen)
+        Kp = _round_up(M, 64)
+        attn16 = self.buf('a2f_attn16', (B, slot, Kp), torch.bfloat16) if tc else None
+        ops.row_softmax(logit, attn, M, len=rlen, out16=attn16)
         xv = self.buf('x2y_xv', (B, M, H))
         ops.gemm([S(action, self.p(pfx + 'X_V.weight'))], H, xv, bias=self.p(pfx + 'X_V.bias'))
         W = self.p(pfx + 'Y_W.weight')                                      # [F, 2H] = [Wy | Wa]
-        vt = self.buf('x2y_vt', (B, F, Mp))                                 # vt[b,f,m] = sum_h Wa[f,h] xv[b,m,h]
-        ops.gemm([S(W[None, :, H:], xv)], M, vt)
         out = self.zbuf('a2f_out', (B, slot, F), self.act)
-        ops.gemm([S(rows, W[:, :H]), S(attn, vt, K=M)], F, out, len=rlen, bias=self.p(pfx + 'Y_W.bias'))
+        if tc:
+            vt = self.zbuf('x2y_vt16', (B, F, Kp), torch.bfloat16)          # vt[b,f,m] = sum_h Wa[f,h] xv[b,m,h]; pad cols stay 0
+            ops.gemm([S(W[None, :, H:], xv)], M, vt)
+            ops.gemm([S(rows, self.wbf(W[:, :H])), S(attn16, vt)], F, out, len=rlen, bias=self.p(pfx + 'Y_W.bias'), tc=True)
+        else:
+            vt = self.buf('x2y_vt', (B, F, Mp))
+            ops.gemm([S(W[None, :, H:], xv)], M, vt)
+            ops.gemm([S(rows, W[:, :H]), S(attn, vt, K=M)], F, out, len=rlen, bias=self.p(pfx + 'Y_W.bias'))
         return out, logit, attn
 
     # ------------------------------------------------------------------ blocks
@@ -395,7 +408,7 @@ class FactEngine:
                     bias=self.p('frame_projection.projection.4.bias'))
             ops.l2norm(emb, emb, len=ln)
             flogit = self.buf('clip_logit', (B, slot, C))
-            ops.gemm([S(emb, self.p('text_embeddings'))], C, flogit, len=ln, alpha=1.0 / hp['temp'])
+            self.mm([S(emb, self.p('text_embeddings'))], C, flogit, tf32=True, len=ln, alpha=1.0 / hp['temp'])
             out['projected_frame_embeddings'], out['clip_logit'] = emb, flogit
         else:
             flogit = last['frame_clogit']

@@ -109,11 +109,12 @@ def l2norm(x, out, eps=1e-12, len=None):
            B, slot, L.ptr(len), E, float(eps), L.stream())
 
 
-def row_softmax(logit, out, M, scale=1.0, len=None):
+def row_softmax(logit, out, M, scale=1.0, len=None, out16=None):
     B, slot = logit.shape[0], logit.shape[1]
     COUNTERS['launches'] += 1
     L.call('factk_row_softmax', logit.data_ptr(), _row_ld(logit), out.data_ptr(), _row_ld(out), B, slot,
-           L.ptr(len), M, float(scale), L.stream())
+           L.ptr(len), M, float(scale), L.ptr(out16), _row_ld(out16) if out16 is not None else 0,
+           out16.shape[-1] if out16 is not None else 0, L.stream())
 
 
 def mha_tokens(q, k, v, out, nhead):

@@ -115,9 +115,10 @@ int factk_l2norm(const void* X, int x_dtype, int ldx, void* Y, int y_dtype, int 
                  int B, int slot, const int32_t* len, int E, float eps, void* stream);
 
 /* softmax over the first M columns of each row: P = softmax(scale * L) (basic.py:376, a2f direction;
- * blocks.py:826 with scale = 1).  L fp32 [B][slot][ldl]; P fp32 [B][slot][ldp] (may alias L). */
+ * blocks.py:826 with scale = 1).  L fp32 [B][slot][ldl]; P fp32 [B][slot][ldp] (may alias L).
+ * P16 (optional): bf16 copy [B][slot][ldp16] with columns M..pad16-1 zeroed -- the tensor-core operand. */
 int factk_row_softmax(const float* L, int ldl, float* P, int ldp, int B, int slot, const int32_t* len, int M,
-                      float scale, void* stream);
+                      float scale, void* P16, int ldp16, int pad16, void* stream);
 
 /* Token self-attention core of nn.MultiheadAttention (basic.py:500, 437): Q,K,V fp32 [B][M][ld]
  * already projected; O[b,m,h*dh:(h+1)*dh] = softmax(q k^T / sqrt(dh)) v per head. */
