@@ -126,6 +126,7 @@ def main():
     ap.add_argument('--videos', type=int, default=16, help='videos per GPU per step')
     ap.add_argument('--mode', default='bf16')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='print a CUDA-event breakdown per kernel family to stderr')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -193,6 +194,16 @@ def main():
     launches = ops.COUNTERS['launches'] // (args.steps + max(args.warmup, 3))
     ktimes = ops.TIMER.collect(skip_steps=max(args.warmup, 3), steps=args.steps)
     ops.TIMER = None
+    if args.profile:
+        ops.TIMER = ops.KernelTimer(None)
+        for _ in range(3):
+            step_resident()
+        prof = ops.TIMER.collect(skip_steps=1, steps=2)
+        ops.TIMER = None
+        tot = sum(v['ms'] for v in prof.values())
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+            sys.stderr.write(f"  {k:28s} n/step={v['n'] // 2:4d} {v['ms'] / 2:8.3f} ms/step {100 * v['ms'] / tot:5.1f}%\n")
+        sys.stderr.write(f"  total {tot / 2:.3f} ms/step (sum of kernel times)\n")
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
 
     frames_step = B * T * world

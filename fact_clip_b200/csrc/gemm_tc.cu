@@ -53,7 +53,8 @@ struct TcCfg {
     static constexpr int STAGE_B = BN * 128;
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+    static constexpr int STG = 4 * 32 * 36 * 4;   // per-epilogue-warp staging tile [32][36] fp32
+    static constexpr int SMEM = NSTAGE * STAGE + 256 + STG + 1024;
 };
 
 __device__ __forceinline__ void ld_row32(const void* base, int dtype, size_t off, bool vec, float o[32]) {
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         }
     } else {
         const int q = warp & 3;             // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
+        float* stg = reinterpret_cast<float*>(smem + Cfg::NSTAGE * Cfg::STAGE + 256) + (warp - 2) * (32 * 36);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int b, t0, nt, len_b;
@@ -185,13 +186,9 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             ++it;
             tc::mbar_wait(&tfull[acc], aphase);
             tc::tc_fence_after();
-            const int t = t0 + row;
-            const bool valid = t < len_b;
-            const size_t grow = (size_t)b * p.slot + t;
             const float* bias = p.bias ? p.bias + (size_t)b * (size_t)p.bias_bstride : nullptr;
-            size_t prow = 0;
-            if (p.pre && valid)
-                prow = (size_t)b * (size_t)p.pre_bstride + (size_t)(p.pre_idx ? p.pre_idx[grow] : t) * (size_t)p.ldpre;
+            // lane -> (row within a 4-row pass, 4 consecutive columns) for the coalesced second phase
+            const int pr = lane >> 3, cg = (lane & 7) * 4;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 const int n0 = nt * BN + c * 32;
@@ -200,45 +197,57 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                 __syncwarp();
                 tc::tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
                 tc::tmem_ld_wait();
-                if (!valid) continue;
-                const bool fullc = n0 + 32 <= p.N;
+                // phase 1: thread = accumulator row -> staging tile [32 rows][36] (conflict-free float4 stores)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = v[j] * p.alpha;
-                    if (bias && (fullc || n0 + j < p.N)) x += __ldg(bias + n0 + j);
-                    v[j] = x;
-                }
-                if (p.pre) {
-                    if (fullc) {
-                        float a[32];
-                        ld_row32(p.pre, p.pre_dtype, prow + n0, p.vec_io, a);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += a[j];
-                    } else {
-                        for (int j = 0; j < 32 && n0 + j < p.N; ++j) v[j] += ld_elem(p.pre, p.pre_dtype, prow + n0 + j);
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(&stg[lane * 36 + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                // phase 2: 8 lanes cover the 32 columns of one row, 4 rows per pass -> contiguous 64/128-byte row segments
+                const int n = n0 + cg;
+                const bool colv = n + 4 <= p.N;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias) {
+                    if (colv) b4 = make_float4(__ldg(bias + n), __ldg(bias + n + 1), __ldg(bias + n + 2), __ldg(bias + n + 3));
+                    else {
+                        float tb[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int j = 0; j < 4 && n + j < p.N; ++j) tb[j] = __ldg(bias + n + j);
+                        b4 = make_float4(tb[0], tb[1], tb[2], tb[3]);
                     }
                 }
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (p.res) {
-                    const size_t rrow = grow * (size_t)p.ldres + n0;
-                    if (fullc) {
-                        float a[32];
-                        ld_row32(p.res, p.res_dtype, rrow, p.vec_io, a);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += a[j];
-                    } else {
-                        for (int j = 0; j < 32 && n0 + j < p.N; ++j) v[j] += ld_elem(p.res, p.res_dtype, rrow + j);
+#pragma unroll 2
+                for (int pass = 0; pass < 8; ++pass) {
+                    const int r = pass * 4 + pr;
+                    const int t = t0 + q * 32 + r;
+                    if (t >= len_b || n >= p.N) continue;
+                    const size_t grow = (size_t)b * p.slot + t;
+                    const float4 a4 = *reinterpret_cast<const float4*>(&stg[r * 36 + cg]);
+                    float x[4] = {a4.x * p.alpha + b4.x, a4.y * p.alpha + b4.y, a4.z * p.alpha + b4.z, a4.w * p.alpha + b4.w};
+                    if (p.pre) {
+                        const size_t prow = (size_t)b * (size_t)p.pre_bstride + (size_t)(p.pre_idx ? p.pre_idx[grow] : t) * (size_t)p.ldpre + n;
+                        if (colv && p.vec_io) {
+                            const float4 e = ld_vec4(p.pre, p.pre_dtype, prow);
+                            x[0] += e.x; x[1] += e.y; x[2] += e.z; x[3] += e.w;
+                        } else {
+                            for (int j = 0; j < 4 && n + j < p.N; ++j) x[j] += ld_elem(p.pre, p.pre_dtype, prow + j);
+                        }
                     }
-                }
-                const size_t yrow = grow * (size_t)p.ldy + n0;
-                if (fullc && p.vec_io) {
+                    if (p.relu) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) st_vec4(p.Y, p.y_dtype, yrow + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                } else {
-                    for (int j = 0; j < 32 && n0 + j < p.N; ++j) st_elem(p.Y, p.y_dtype, yrow + j, v[j]);
+                        for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
+                    }
+                    if (p.res) {
+                        const size_t rrow = grow * (size_t)p.ldres + n;
+                        if (colv && p.vec_io) {
+                            const float4 e = ld_vec4(p.res, p.res_dtype, rrow);
+                            x[0] += e.x; x[1] += e.y; x[2] += e.z; x[3] += e.w;
+                        } else {
+                            for (int j = 0; j < 4 && n + j < p.N; ++j) x[j] += ld_elem(p.res, p.res_dtype, rrow + j);
+                        }
+                    }
+                    const size_t yrow = grow * (size_t)p.ldy + n;
+                    if (colv && p.vec_io) st_vec4(p.Y, p.y_dtype, yrow, make_float4(x[0], x[1], x[2], x[3]));
+                    else
+                        for (int j = 0; j < 4 && n + j < p.N; ++j) st_elem(p.Y, p.y_dtype, yrow + j, x[j]);
                 }
             }
             tc::tc_fence_before();

@@ -99,40 +99,75 @@ __global__ void __launch_bounds__(128) segment_mean_kernel(const void* __restric
 
 // ------------------------------------------------------------------------------------------------
 // Bidirectional GRU recurrence.  One 4-CTA cluster advances NB chains (videos) of one direction; CTA `rank`
-// owns hidden units [rank*U, rank*U+U) with all three gate rows of W_hh for them resident in shared memory
-// (transposed, fp32).  Per step: (1) every thread accumulates a quarter-K slice of one gate row for the NB
-// chains, (2) one thread per (chain, unit) sums the partials, applies the gates and writes the new hidden
-// value into the next-step buffer of all four CTAs through distributed shared memory, (3) a split cluster
-// barrier (arrive.release ... wait.acquire) with the global store of the output and the prefetch of the
-// next step's input gates placed between arrive and wait so their latency is off the critical path.
+// owns hidden units [rank*U, rank*U+U).  The W_hh rows of those units live in REGISTERS (thread (kq, j) keeps
+// the KS = Hh/4 weights of gate row j for K slice kq), so a step reads only the hidden state from shared memory.
+// Per step: (1) every thread accumulates its K slice for the NB chains -> partials in shared memory,
+// (2) one thread per (chain, unit) sums the partials, applies the gates and stores the new hidden value into
+// the next-step buffer of all four CTAs through distributed shared memory, (3) one lane per gate warp does a
+// release-arrive on each CTA's "hidden state ready" mbarrier; consumers acquire-wait on their local barrier.
+// No cluster-wide barrier inside the loop; the global store of the output and the prefetch of the next input
+// gates come after the arrive, off the critical path.
 constexpr int GRU_CS = 4;   // CTAs per cluster
 constexpr int GRU_KQ = 4;   // K split of the mat-vec inside a CTA
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
-template <int NB>
-__global__ void __cluster_dims__(GRU_CS, 1, 1)
+__device__ __forceinline__ uint32_t cluster_map_u32(const void* local_smem, int rank) {
+    uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local_smem), raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+    return raddr;
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t raddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 24)) __trap();     // protocol bug: fail loudly instead of hanging the GPU
+    }
+}
+
+template <int NB, int KS>
+__global__ void __cluster_dims__(GRU_CS, 1, 1) __launch_bounds__(GRU_KQ * 3 * KS, 1)
 gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, const float* __restrict__ bhh_f,
-                   const float* __restrict__ whh_b, const float* __restrict__ bhh_b, int Hh, void* out, int o_dtype,
+                   const float* __restrict__ whh_b, const float* __restrict__ bhh_b, void* out, int o_dtype,
                    int ldo, int relu, int B, int slot, const int32_t* __restrict__ nseg) {
+    constexpr int Hh = GRU_KQ * KS, U = KS, R = 3 * U;
+    constexpr int GATE_T = NB * U, GATE_W = (GATE_T + 31) / 32;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / GRU_CS;
     const int dir = cid & 1, grp = cid >> 1;
-    const int U = Hh / GRU_CS, R = 3 * U, KS = Hh / GRU_KQ;
-    extern __shared__ __align__(16) float sm[];
-    float* Wt = sm;                                  // [Hh][R]        transposed slice of W_hh
-    float* hb = Wt + (size_t)Hh * R;                 // [2][NB][Hh]    double-buffered hidden state
-    float* part = hb + 2 * NB * Hh;                  // [NB][KQ][R]    partial dot products
+    __shared__ __align__(16) float hb[2 * NB * Hh];          // double-buffered hidden state
+    __shared__ float part[NB * GRU_KQ * R];                  // partial dot products
+    __shared__ __align__(8) uint64_t hready[2];
     const float* whh = dir ? whh_b : whh_f;
     const float* bhh = dir ? bhh_b : bhh_f;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int kq = tid / R, j = tid % R;                     // blockDim.x == KQ * R exactly
 
-    for (int i = tid; i < Hh * R; i += blockDim.x) {
-        const int k = i / R, j = i % R, g = j / U, u = j % U;
-        Wt[i] = whh[((size_t)g * Hh + rank * U + u) * Hh + k];
+    float w[KS];
+    {
+        const int g = j / U, u = j % U;
+        const float* wr = whh + ((size_t)g * Hh + rank * U + u) * Hh + kq * KS;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) w[k] = wr[k];
     }
     for (int i = tid; i < 2 * NB * Hh; i += blockDim.x) hb[i] = 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&hready[i]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(GRU_CS * GATE_W) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     int S[NB], vb[NB], maxS = 0;
 #pragma unroll
@@ -141,11 +176,8 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
         S[nb] = (vb[nb] < B) ? min(nseg[vb[nb]], slot) : 0;
         maxS = max(maxS, S[nb]);
     }
-    // mat-vec role
-    const bool mv = tid < GRU_KQ * R;
-    const int kq = mv ? tid / R : 0, j = mv ? tid % R : 0;
-    // gate role: one thread per (chain, owned unit)
-    const bool gate = tid < NB * U;
+    const bool gate_warp = (tid >> 5) < GATE_W;
+    const bool gate = tid < GATE_T;
     const int gnb = gate ? tid / U : 0, gu = gate ? tid % U : 0, unit = rank * U + gu;
     int myS = 0, myv = 0;
 #pragma unroll
@@ -164,60 +196,71 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
         }
     };
     load_gi(0);
-    float* hb_remote[GRU_CS];
-#pragma unroll
-    for (int rr = 0; rr < GRU_CS; ++rr) hb_remote[rr] = cluster.map_shared_rank(hb, rr);
+    const uint32_t hb_u32 = (uint32_t)__cvta_generic_to_shared(hb);
+    const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(&hready[0]);
     __syncthreads();
     cluster.sync();
 
     for (int t = 0; t < maxS; ++t) {
         const int cur = t & 1;
+        if (t > 0) mbar_wait_acquire_cluster(&hready[cur], ((t - 1) >> 1) & 1);
         const float* h = hb + cur * NB * Hh;
-        if (mv) {
+        {
             float acc[NB];
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) acc[nb] = 0.f;
-            const float* wcol = Wt + (size_t)(kq * KS) * R + j;
             const float* hk = h + kq * KS;
-#pragma unroll 4
+#pragma unroll
             for (int k = 0; k < KS; k += 4) {
-                const float w0 = wcol[(size_t)(k + 0) * R], w1 = wcol[(size_t)(k + 1) * R];
-                const float w2 = wcol[(size_t)(k + 2) * R], w3 = wcol[(size_t)(k + 3) * R];
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
                     const float4 h4 = *reinterpret_cast<const float4*>(&hk[nb * Hh + k]);
-                    acc[nb] = fmaf(w0, h4.x, acc[nb]); acc[nb] = fmaf(w1, h4.y, acc[nb]);
-                    acc[nb] = fmaf(w2, h4.z, acc[nb]); acc[nb] = fmaf(w3, h4.w, acc[nb]);
+                    acc[nb] = fmaf(w[k], h4.x, acc[nb]); acc[nb] = fmaf(w[k + 1], h4.y, acc[nb]);
+                    acc[nb] = fmaf(w[k + 2], h4.z, acc[nb]); acc[nb] = fmaf(w[k + 3], h4.w, acc[nb]);
                 }
             }
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) part[(nb * GRU_KQ + kq) * R + j] = acc[nb];
         }
         __syncthreads();
-        float hn = 0.f;
-        const bool live = gate && t < myS;
-        if (live) {
-            const float* pp = part + (size_t)gnb * GRU_KQ * R;
-            float a_r = b_r, a_z = b_z, a_n = b_n;
+        if (gate_warp) {
+            float hn = 0.f;
+            const bool live = gate && t < myS;
+            if (live) {
+                const float* pp = part + gnb * GRU_KQ * R;
+                float a_r = b_r, a_z = b_z, a_n = b_n;
 #pragma unroll
-            for (int q = 0; q < GRU_KQ; ++q) {
-                a_r += pp[q * R + gu]; a_z += pp[q * R + U + gu]; a_n += pp[q * R + 2 * U + gu];
+                for (int q = 0; q < GRU_KQ; ++q) {
+                    a_r += pp[q * R + gu]; a_z += pp[q * R + U + gu]; a_n += pp[q * R + 2 * U + gu];
+                }
+                const float r = sigmoidf_(g_r + a_r), z = sigmoidf_(g_z + a_z);
+                const float n = tanhf(g_n + r * a_n);
+                hn = (1.f - z) * n + z * h[gnb * Hh + unit];
+                const int o = (cur ^ 1) * NB * Hh + gnb * Hh + unit;
+#pragma unroll
+                for (int rr = 0; rr < GRU_CS; ++rr) {
+                    uint32_t ra;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(hb_u32 + (uint32_t)o * 4u), "r"(rr));
+                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(hn) : "memory");
+                }
             }
-            const float r = sigmoidf_(g_r + a_r), z = sigmoidf_(g_z + a_z);
-            const float n = tanhf(g_n + r * a_n);
-            hn = (1.f - z) * n + z * h[gnb * Hh + unit];
-            const int o = (cur ^ 1) * NB * Hh + gnb * Hh + unit;
+            __syncwarp();
+            if (lane == 0) {
 #pragma unroll
-            for (int rr = 0; rr < GRU_CS; ++rr) hb_remote[rr][o] = hn;
+                for (int rr = 0; rr < GRU_CS; ++rr) {
+                    uint32_t ra;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar_u32 + (uint32_t)(cur ^ 1) * 8u), "r"(rr));
+                    mbar_arrive_remote_release(ra);
+                }
+            }
+            if (live) {
+                const int s = dir ? myS - 1 - t : t;
+                st_elem(out, o_dtype, ((size_t)myv * slot + s) * (size_t)ldo + (size_t)dir * Hh + unit, relu ? fmaxf(hn, 0.f) : hn);
+            }
+            load_gi(t + 1);
         }
-        cluster.barrier_arrive();
-        if (live) {
-            const int s = dir ? myS - 1 - t : t;
-            st_elem(out, o_dtype, ((size_t)myv * slot + s) * (size_t)ldo + (size_t)dir * Hh + unit, relu ? fmaxf(hn, 0.f) : hn);
-        }
-        load_gi(t + 1);
-        cluster.barrier_wait();
     }
+    cluster.sync();     // nobody may exit while peers can still write into its shared memory
 }
 
 }  // namespace factk
@@ -246,28 +289,30 @@ extern "C" int factk_gru_bidir(const float* gi, const float* w_hh_f, const float
                                const float* b_hh_b, int Hh, void* out, int o_dtype, int ldo, int relu, int B, int slot,
                                const int32_t* nseg, void* stream) {
     FACTK_REQUIRE(gi && w_hh_f && b_hh_f && w_hh_b && b_hh_b && out && nseg && B > 0 && slot > 0, "factk_gru_bidir: bad args");
-    FACTK_REQUIRE(Hh > 0 && Hh % (4 * GRU_CS) == 0, "factk_gru_bidir: hidden size %d must be a multiple of %d", Hh, 4 * GRU_CS);
-    const int U = Hh / GRU_CS, R = 3 * U;
+    FACTK_REQUIRE(Hh == 32 || Hh == 64 || Hh == 128 || Hh == 256,
+                  "factk_gru_bidir: hidden size per direction %d unsupported (32/64/128/256, i.e. hid_dim 64..512)", Hh);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // chains advanced per cluster: as few as possible while all clusters are co-resident (one CTA per SM)
     int NB = 1;
     while (NB < 4 && ((B + NB - 1) / NB) * 2 * GRU_CS > sms - 16) NB *= 2;
-    const size_t smem = ((size_t)Hh * R + 2 * NB * Hh + (size_t)NB * GRU_KQ * R) * sizeof(float);
-    FACTK_REQUIRE(smem <= 227 * 1024 && GRU_KQ * R <= 1024, "factk_gru_bidir: hidden size %d does not fit one cluster (%zu B smem)", Hh, smem);
     const int groups = (B + NB - 1) / NB;
-    int threads = GRU_KQ * R > NB * U ? GRU_KQ * R : NB * U;
-    threads = ((threads + 31) / 32) * 32;
+    const int KS = Hh / GRU_KQ;
+    const int threads = GRU_KQ * 3 * KS;
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(N_)                                                                                                          \
-    do {                                                                                                                    \
-        cudaError_t e = cudaFuncSetAttribute(gru_cluster_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) { set_error("factk_gru_bidir: smem attr: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; } \
-        gru_cluster_kernel<N_><<<groups * 2 * GRU_CS, threads, smem, st>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, Hh, out,    \
-                                                                          o_dtype, ldo, relu, B, slot, nseg);              \
+#define LAUNCH(N_, K_)                                                                                                  \
+    gru_cluster_kernel<N_, K_><<<groups * 2 * GRU_CS, threads, 0, st>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, \
+                                                                        ldo, relu, B, slot, nseg)
+#define LAUNCH_K(N_)                                                \
+    do {                                                            \
+        if (KS == 8) LAUNCH(N_, 8);                                 \
+        else if (KS == 16) LAUNCH(N_, 16);                          \
+        else if (KS == 32) LAUNCH(N_, 32);                          \
+        else LAUNCH(N_, 64);                                        \
     } while (0)
-    if (NB == 1) LAUNCH(1); else if (NB == 2) LAUNCH(2); else LAUNCH(4);
+    if (NB == 1) LAUNCH_K(1); else if (NB == 2) LAUNCH_K(2); else LAUNCH_K(4);
+#undef LAUNCH_K
 #undef LAUNCH
     return check_launch("factk_gru_bidir");
 }

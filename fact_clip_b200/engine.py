@@ -62,6 +62,20 @@ class FactEngine:
         return (self.mode == 'bf16' and self.use_tc and rows.dtype == torch.bfloat16 and self.frame_pos is None
                 and H % 64 == 0)
 
+    def lin(self, x, W, N, out, pos=None, **kw):
+        """Token-side Linear with an optional query-position on the input.  On the tensor-core path (tf32) the
+        position term moves to a cached table: (x + pos) W^T = x W^T + (pos W[:, :d]^T)."""
+        K = W.shape[-1]
+        if (self.mode == 'bf16' and self.use_tc and x.dtype == torch.float32 and W.dim() == 2 and K % 32 == 0
+                and x.shape[0] == out.shape[0]):
+            pre = None
+            if pos is not None:
+                assert kw.get('alpha', 1.0) == 1.0
+                d = pos.shape[-1]
+                pre = self.derived(('posW', W.data_ptr(), tuple(W.shape), tuple(W.stride())), lambda: pos @ W[:, :d].t())
+            return ops.gemm([S(x, W)], N, out, tc=True, pre=pre, **kw)
+        return ops.gemm([S(x, W, pos=pos)], N, out, **kw)
+
     def mm(self, srcs, N, out, tf32=False, **kw):
         """GEMM dispatch: tcgen05 kernel when the operands qualify (bf16 mode), CUDA-core kernel otherwise."""
         if self.mode == 'bf16' and self.use_tc:
@@ -151,8 +165,8 @@ class FactEngine:
         B, M, A = x.shape
         W, bias = self.p(pfx + 'in_proj_weight'), self.p(pfx + 'in_proj_bias')
         qkv = self.buf('tok_qkv', (B, M, 3 * A))
-        ops.gemm([S(x, W[:2 * A], pos=pos)], 2 * A, qkv[:, :, :2 * A], bias=bias[:2 * A])
-        ops.gemm([S(x, W[2 * A:])], A, qkv[:, :, 2 * A:], bias=bias[2 * A:])
+        self.lin(x, W[:2 * A], 2 * A, qkv[:, :, :2 * A], pos=pos, bias=bias[:2 * A])
+        self.lin(x, W[2 * A:], A, qkv[:, :, 2 * A:], bias=bias[2 * A:])
         o = self.buf('tok_o', (B, M, A))
         ops.mha_tokens(qkv[:, :, :A], qkv[:, :, A:2 * A], qkv[:, :, 2 * A:], o, nhead)
         return o
@@ -161,9 +175,9 @@ class FactEngine:
         B, M, A = x.shape
         ff = self.p(q + 'linear1.weight').shape[0]
         h = self.buf('tok_ff', (B, M, ff))
-        ops.gemm([S(x, self.p(q + 'linear1.weight'))], ff, h, bias=self.p(q + 'linear1.bias'), relu=True)
+        self.lin(x, self.p(q + 'linear1.weight'), ff, h, bias=self.p(q + 'linear1.bias'), relu=True)
         t = self.buf('tok_t', (B, M, A))
-        ops.gemm([S(h, self.p(q + 'linear2.weight'))], A, t, bias=self.p(q + 'linear2.bias'), res=x)
+        self.lin(h, self.p(q + 'linear2.weight'), A, t, bias=self.p(q + 'linear2.bias'), res=x)
         ops.layernorm(t, self.p(q + n_a), self.p(q + n_b), x)
 
     def sca_decoder(self, pfx, bc, frame, tag):
@@ -179,7 +193,7 @@ class FactEngine:
         for i in range(bc['a_layers']):
             q = f'{pfx}layers.{i}.'
             o = self._mha_self(q + 'self_attn.', tgt, qpos, nh, tag)
-            ops.gemm([S(o, self.p(q + 'self_attn.out_proj.weight'))], A, t, bias=self.p(q + 'self_attn.out_proj.bias'), res=tgt)
+            self.lin(o, self.p(q + 'self_attn.out_proj.weight'), A, t, bias=self.p(q + 'self_attn.out_proj.bias'), res=tgt)
             ops.layernorm(t, self.p(q + 'norm1.weight'), self.p(q + 'norm1.bias'), tgt)
             # cross attention: q from tokens, k from frames (+pos), v from frames
             c = q + 'multihead_attn.'
@@ -190,7 +204,7 @@ class FactEngine:
             else:
                 wq, wk, wv = self.p(c + 'q_proj_weight'), self.p(c + 'k_proj_weight'), self.p(c + 'v_proj_weight')
             cq = self.buf('tok_cq', (B, M, A))
-            ops.gemm([S(tgt, wq, pos=qpos)], A, cq, bias=cb[:A])
+            self.lin(tgt, wq, A, cq, pos=qpos, bias=cb[:A])
             if fpos is None:
                 wkv = self.derived(('wkv', c), lambda: torch.cat([wk, wv], 0))
                 self.mm([S(frame, wkv)], 2 * A, kv, len=self.len, bias=cb[A:])
@@ -199,12 +213,12 @@ class FactEngine:
                 self.mm([S(frame, wv)], A, kv[:, :, A:], len=self.len, bias=cb[2 * A:])
             o = self.buf('tok_o', (B, M, A))
             ops.attn_rows(cq, kv[:, :, :A], kv[:, :, A:], o, nh, ws, len=self.len)
-            ops.gemm([S(o, self.p(c + 'out_proj.weight'))], A, t, bias=self.p(c + 'out_proj.bias'), res=tgt)
+            self.lin(o, self.p(c + 'out_proj.weight'), A, t, bias=self.p(c + 'out_proj.bias'), res=tgt)
             ops.layernorm(t, self.p(q + 'norm2.weight'), self.p(q + 'norm2.bias'), tgt)
             self._ffn_ln(q, tgt, 'norm3.weight', 'norm3.bias', tag)
         ops.layernorm(tgt, self.p(pfx + 'norm.weight'), self.p(pfx + 'norm.bias'), t)
         out = self.buf('action_' + tag, (B, M, H))
-        ops.gemm([S(t, self.p(pfx + 'out_linear.weight'))], H, out, bias=self.p(pfx + 'out_linear.bias'))
+        self.lin(t, self.p(pfx + 'out_linear.weight'), H, out, bias=self.p(pfx + 'out_linear.bias'))
         return out
 
     def sa_decoder(self, pfx, bc, x, tag):
@@ -215,12 +229,12 @@ class FactEngine:
         for i in range(bc['a_layers']):
             q = f'{pfx}layers.{i}.'
             o = self._mha_self(q + 'multihead_attn.', x, qpos, nh, tag)
-            ops.gemm([S(o, self.p(q + 'multihead_attn.out_proj.weight'))], A, t,
+            self.lin(o, self.p(q + 'multihead_attn.out_proj.weight'), A, t,
                      bias=self.p(q + 'multihead_attn.out_proj.bias'), res=x)
             ops.layernorm(t, self.p(q + 'norm1.weight'), self.p(q + 'norm1.bias'), x)
             self._ffn_ln(q, x, 'norm2.weight', 'norm2.bias', tag)
         out = self.buf('action_' + tag, (B, M, H))
-        ops.gemm([S(x, self.p(pfx + 'out_linear.weight'))], H, out, bias=self.p(pfx + 'out_linear.bias'))
+        self.lin(x, self.p(pfx + 'out_linear.weight'), H, out, bias=self.p(pfx + 'out_linear.bias'))
         return out
 
     def token_splice(self, action, tag):
@@ -238,12 +252,12 @@ class FactEngine:
         qpos = self.p('action_query')[:, 0]
         alpha = 1.0 / math.sqrt(H)
         yq = self.buf('x2y_tokH', (B, M, H))
-        ops.gemm([S(action, self.p(pfx + 'Y_Q.weight'), pos=qpos)], H, yq, bias=self.p(pfx + 'Y_Q.bias'))
+        self.lin(action, self.p(pfx + 'Y_Q.weight'), H, yq, pos=qpos, bias=self.p(pfx + 'Y_Q.bias'))
         tc = self.x2y_tc(rows, H)
         qt = self.buf('x2y_qt16' if tc else 'x2y_qt', (B, M, H), torch.bfloat16 if tc else torch.float32)   # alpha * Wk^T yq
-        ops.gemm([S(yq, self.tr(pfx + 'X_K.weight'))], H, qt, alpha=alpha)
+        self.lin(yq, self.tr(pfx + 'X_K.weight'), H, qt, alpha=alpha)
         cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * yq . bk
-        ops.gemm([S(yq, self.p(pfx + 'X_K.bias')[None, :])], 1, cb, alpha=alpha)
+        self.lin(yq, self.p(pfx + 'X_K.bias')[None, :], 1, cb, alpha=alpha)
         logit = self.buf('f2a_logit_' + tag, (B, slot, Mp))
         ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc)
         attn = self.buf('f2a_attn_' + tag, (B, slot, Mp)) if want_attn else None
@@ -251,10 +265,10 @@ class FactEngine:
         ws = self.buf('col_ws', (ops.col_softmax_ws(B, slot, M, H),))
         ops.col_softmax_apply(logit, rows, xbar, M, ws, attn=attn, len=rlen, E=H)
         feat = self.buf('x2y_tokH', (B, M, H))
-        ops.gemm([S(xbar, self.p(pfx + 'X_V.weight'))], H, feat, bias=self.p(pfx + 'X_V.bias'))
+        self.lin(xbar, self.p(pfx + 'X_V.weight'), H, feat, bias=self.p(pfx + 'X_V.bias'))
         W = self.p(pfx + 'Y_W.weight')
         out = self.buf('tok_x', (B, M, A))
-        ops.gemm([S(action, W[:, :H]), S(feat, W[:, H:])], A, out, bias=self.p(pfx + 'Y_W.bias'))
+        self.mm([S(action, W[:, :H]), S(feat, W[:, H:])], A, out, tf32=True, bias=self.p(pfx + 'Y_W.bias'))
         return out, logit, attn
 
     def a2f(self, pfx, bc, action, rows, rlen, pos_idx, tag):
@@ -265,12 +279,12 @@ class FactEngine:
         qpos = self.p('action_query')[:, 0]
         alpha = 1.0 / math.sqrt(H)
         xk = self.buf('x2y_tokH', (B, M, H))
-        ops.gemm([S(action, self.p(pfx + 'X_K.weight'), pos=qpos)], H, xk, bias=self.p(pfx + 'X_K.bias'))
+        self.lin(action, self.p(pfx + 'X_K.weight'), H, xk, pos=qpos, bias=self.p(pfx + 'X_K.bias'))
         tc = self.x2y_tc(rows, H)
         kt = self.buf('x2y_qt16' if tc else 'x2y_qt', (B, M, H), torch.bfloat16 if tc else torch.float32)   # alpha * Wq^T xk
-        ops.gemm([S(xk, self.tr(pfx + 'Y_Q.weight'))], H, kt, alpha=alpha)
+        self.lin(xk, self.tr(pfx + 'Y_Q.weight'), H, kt, alpha=alpha)
         cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * xk . bq
-        ops.gemm([S(xk, self.p(pfx + 'Y_Q.bias')[None, :])], 1, cb, alpha=alpha)
+        self.lin(xk, self.p(pfx + 'Y_Q.bias')[None, :], 1, cb, alpha=alpha)
         logit = self.buf('a2f_logit_' + tag, (B, slot, Mp))
         ops.gemm([S(rows, kt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc)
         attn = self.buf('a2f_attn_' + tag, (B, slot, Mp))
@@ -278,7 +292,7 @@ class FactEngine:
         attn16 = self.buf('a2f_attn16', (B, slot, Kp), torch.bfloat16) if tc else None
         ops.row_softmax(logit, attn, M, len=rlen, out16=attn16)
         xv = self.buf('x2y_xv', (B, M, H))
-        ops.gemm([S(action, self.p(pfx + 'X_V.weight'))], H, xv, bias=self.p(pfx + 'X_V.bias'))
+        self.lin(action, self.p(pfx + 'X_V.weight'), H, xv, bias=self.p(pfx + 'X_V.bias'))
         W = self.p(pfx + 'Y_W.weight')                                      # [F, 2H] = [Wy | Wa]
         out = self.zbuf('a2f_out', (B, slot, F), self.act)
         if tc:

@@ -17,7 +17,8 @@ class KernelTimer:
     """CUDA-event timing of tagged launches on the launching stream (used by bench.py for the roofline line)."""
 
     def __init__(self, tags):
-        self.tags, self.pairs = set(tags), {t: [] for t in tags}
+        self.tags = None if tags is None else set(tags)
+        self.pairs = {} if tags is None else {t: [] for t in tags}
 
     def collect(self, skip_steps, steps):
         torch.cuda.synchronize()
@@ -27,6 +28,20 @@ class KernelTimer:
             use = pairs[skip_steps * per_step:]
             out[t] = dict(ms=sum(a.elapsed_time(b) for a, b in use), n=len(use))
         return out
+
+
+def _call(name, tag, *args):
+    """Launch through the C ABI; when a KernelTimer is active, bracket the launch with CUDA events."""
+    t = TIMER
+    key = tag or name
+    if t is not None and (t.tags is None or key in t.tags):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.call(name, *args)
+        e1.record()
+        t.pairs.setdefault(key, []).append((e0, e1))
+    else:
+        L.call(name, *args)
 
 
 def S(A, W, K=None, off=0, gather=None, pos=None, pos_d=None, pos_idx=None):
@@ -70,14 +85,7 @@ def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None, tag
     if res is not None:
         g.res, g.res_dtype, g.ldres = res.data_ptr(), L.dt(res), _row_ld(res)
     g.Y, g.y_dtype, g.ldy = out.data_ptr(), L.dt(out), _row_ld(out)
-    timed = TIMER is not None and tag in TIMER.tags
-    if timed:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    L.call('factk_gemm_tc' if tc else 'factk_gemm', g, L.stream())
-    if timed:
-        e1.record()
-        TIMER.pairs[tag].append((e0, e1))
+    _call('factk_gemm_tc' if tc else 'factk_gemm', tag or ('gemm_tc' if tc else 'gemm_simt'), g, L.stream())
     COUNTERS['launches'] += 1
 
 
@@ -88,7 +96,7 @@ def softmax_splice(x, C, clogit, pred=None, len=None, H=None):
     B, slot = x.shape[0], x.shape[1]
     H = x.shape[-1] if H is None else H
     COUNTERS['launches'] += 1
-    L.call('factk_softmax_splice', x.data_ptr(), L.dt(x), B, slot, L.ptr(len), _row_ld(x), H, C,
+    _call('factk_softmax_splice', None, x.data_ptr(), L.dt(x), B, slot, L.ptr(len), _row_ld(x), H, C,
            clogit.data_ptr(), L.ptr(pred), L.stream())
 
 
@@ -96,7 +104,7 @@ def layernorm(x, w, b, out, res=None, eps=1e-5, relu=False, len=None, E=None):
     B, slot = x.shape[0], x.shape[1]
     E = x.shape[-1] if E is None else E
     COUNTERS['launches'] += 1
-    L.call('factk_layernorm', x.data_ptr(), L.dt(x), _row_ld(x),
+    _call('factk_layernorm', None, x.data_ptr(), L.dt(x), _row_ld(x),
            L.ptr(res), L.dt(res) if res is not None else 0, _row_ld(res) if res is not None else 0,
            w.data_ptr(), b.data_ptr(), float(eps), int(relu), out.data_ptr(), L.dt(out), _row_ld(out),
            B, slot, L.ptr(len), E, L.stream())
@@ -105,14 +113,14 @@ def layernorm(x, w, b, out, res=None, eps=1e-5, relu=False, len=None, E=None):
 def l2norm(x, out, eps=1e-12, len=None):
     B, slot, E = x.shape
     COUNTERS['launches'] += 1
-    L.call('factk_l2norm', x.data_ptr(), L.dt(x), _row_ld(x), out.data_ptr(), L.dt(out), _row_ld(out),
+    _call('factk_l2norm', None, x.data_ptr(), L.dt(x), _row_ld(x), out.data_ptr(), L.dt(out), _row_ld(out),
            B, slot, L.ptr(len), E, float(eps), L.stream())
 
 
 def row_softmax(logit, out, M, scale=1.0, len=None, out16=None):
     B, slot = logit.shape[0], logit.shape[1]
     COUNTERS['launches'] += 1
-    L.call('factk_row_softmax', logit.data_ptr(), _row_ld(logit), out.data_ptr(), _row_ld(out), B, slot,
+    _call('factk_row_softmax', None, logit.data_ptr(), _row_ld(logit), out.data_ptr(), _row_ld(out), B, slot,
            L.ptr(len), M, float(scale), L.ptr(out16), _row_ld(out16) if out16 is not None else 0,
            out16.shape[-1] if out16 is not None else 0, L.stream())
 
@@ -122,7 +130,7 @@ def mha_tokens(q, k, v, out, nhead):
     E = out.shape[-1]
     assert _row_ld(q) == _row_ld(k) == _row_ld(v)
     COUNTERS['launches'] += 1
-    L.call('factk_mha_tokens', q.data_ptr(), k.data_ptr(), v.data_ptr(), _row_ld(q), out.data_ptr(), _row_ld(out),
+    _call('factk_mha_tokens', None, q.data_ptr(), k.data_ptr(), v.data_ptr(), _row_ld(q), out.data_ptr(), _row_ld(out),
            B, M, nhead, E // nhead, L.stream())
 
 
@@ -135,7 +143,7 @@ def attn_rows(q, kx, vx, out, nhead, ws, len=None):
     slot = kx.shape[1]
     assert _row_ld(kx) == _row_ld(vx) and kx.dtype == vx.dtype
     COUNTERS['launches'] += 2
-    L.call('factk_attn_rows', q.data_ptr(), _row_ld(q), kx.data_ptr(), vx.data_ptr(), L.dt(kx), _row_ld(kx),
+    _call('factk_attn_rows', None, q.data_ptr(), _row_ld(q), kx.data_ptr(), vx.data_ptr(), L.dt(kx), _row_ld(kx),
            out.data_ptr(), _row_ld(out), B, slot, L.ptr(len), M, nhead, E // nhead, ws.data_ptr(), L.stream())
 
 
@@ -147,7 +155,7 @@ def col_softmax_apply(logit, x, out, M, ws, attn=None, len=None, E=None):
     B, slot = logit.shape[0], logit.shape[1]
     E = x.shape[-1] if E is None else E
     COUNTERS['launches'] += 4
-    L.call('factk_col_softmax_apply', logit.data_ptr(), _row_ld(logit), x.data_ptr(), L.dt(x), _row_ld(x),
+    _call('factk_col_softmax_apply', None, logit.data_ptr(), _row_ld(logit), x.data_ptr(), L.dt(x), _row_ld(x),
            out.data_ptr(), _row_ld(out), L.ptr(attn), _row_ld(attn) if attn is not None else 0,
            B, slot, L.ptr(len), M, E, ws.data_ptr(), L.stream())
 
@@ -155,7 +163,7 @@ def col_softmax_apply(logit, x, out, M, ws, attn=None, len=None, E=None):
 def tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=None):
     B, slot = pred.shape
     COUNTERS['launches'] += 1
-    L.call('factk_tdu_segment', pred.data_ptr(), B, slot, L.ptr(len), seg_label.data_ptr(), seg_start.data_ptr(),
+    _call('factk_tdu_segment', None, pred.data_ptr(), B, slot, L.ptr(len), seg_label.data_ptr(), seg_start.data_ptr(),
            seg_len.data_ptr(), seg_center.data_ptr(), nseg.data_ptr(), L.stream())
 
 
@@ -163,7 +171,7 @@ def segment_mean(x, seg, seg_start, seg_len, nseg, E=None):
     B, slot = x.shape[0], x.shape[1]
     E = x.shape[-1] if E is None else E
     COUNTERS['launches'] += 1
-    L.call('factk_segment_mean', x.data_ptr(), L.dt(x), _row_ld(x), seg.data_ptr(), L.dt(seg), _row_ld(seg),
+    _call('factk_segment_mean', None, x.data_ptr(), L.dt(x), _row_ld(x), seg.data_ptr(), L.dt(seg), _row_ld(seg),
            seg_start.data_ptr(), seg_len.data_ptr(), nseg.data_ptr(), B, slot, E, L.stream())
 
 
@@ -171,20 +179,20 @@ def gru_bidir(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, nseg, relu=True):
     B, slot = gi.shape[0], gi.shape[1]
     Hh = w_hh_f.shape[1]
     COUNTERS['launches'] += 1
-    L.call('factk_gru_bidir', gi.data_ptr(), w_hh_f.data_ptr(), b_hh_f.data_ptr(), w_hh_b.data_ptr(), b_hh_b.data_ptr(),
+    _call('factk_gru_bidir', None, gi.data_ptr(), w_hh_f.data_ptr(), b_hh_f.data_ptr(), w_hh_b.data_ptr(), b_hh_b.data_ptr(),
            Hh, out.data_ptr(), L.dt(out), _row_ld(out), int(relu), B, slot, nseg.data_ptr(), L.stream())
 
 
 def gather_rows(src, idx, out, E, len=None):
     B, slot = out.shape[0], out.shape[1]
     COUNTERS['launches'] += 1
-    L.call('factk_gather_rows', src.data_ptr(), _row_ld(src), src.shape[1], idx.data_ptr(), out.data_ptr(),
+    _call('factk_gather_rows', None, src.data_ptr(), _row_ld(src), src.shape[1], idx.data_ptr(), out.data_ptr(),
            _row_ld(out), B, slot, L.ptr(len), E, L.stream())
 
 
 def fuse_eval(action_clogit, attn, flogit, weight, pred, M, C, seg_label=None, len=None):
     B, slot = flogit.shape[0], flogit.shape[1]
     COUNTERS['launches'] += 1
-    L.call('factk_fuse_eval', L.ptr(action_clogit), L.ptr(attn), _row_ld(attn) if attn is not None else 0,
+    _call('factk_fuse_eval', None, L.ptr(action_clogit), L.ptr(attn), _row_ld(attn) if attn is not None else 0,
            attn.shape[1] if attn is not None else 0, L.ptr(seg_label), flogit.data_ptr(), _row_ld(flogit),
            float(weight), pred.data_ptr(), B, slot, L.ptr(len), M, C, L.stream())
