@@ -184,6 +184,28 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             const int acc = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ++it;
+            // residual rows do not depend on the MMAs: fetch chunk 0 before waiting, chunk c+1 while chunk c is processed
+            const bool res_vec = p.res != nullptr && p.vec_io;
+            const int lpr = lane >> 3, lcg = (lane & 7) * 4;
+            uint4 rnext[8];
+            auto fetch_res = [&](int c) {
+                const int n = nt * BN + c * 32 + lcg;
+#pragma unroll
+                for (int pass = 0; pass < 8; ++pass) {
+                    const int t = t0 + q * 32 + pass * 4 + lpr;
+                    rnext[pass] = make_uint4(0u, 0u, 0u, 0u);
+                    if (res_vec && t < len_b && n + 4 <= p.N) {
+                        const size_t off = ((size_t)b * p.slot + t) * (size_t)p.ldres + n;
+                        if (p.res_dtype == FACTK_BF16) {
+                            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + off);
+                            rnext[pass].x = u.x; rnext[pass].y = u.y;
+                        } else {
+                            rnext[pass] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res) + off);
+                        }
+                    }
+                }
+            };
+            fetch_res(0);
             tc::mbar_wait(&tfull[acc], aphase);
             tc::tc_fence_after();
             const float* bias = p.bias ? p.bias + (size_t)b * (size_t)p.bias_bstride : nullptr;
@@ -194,6 +216,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                 const int n0 = nt * BN + c * 32;
                 if (n0 >= p.N) break;
                 float v[32];
+                uint4 rcur[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+                if ((c + 1) * 32 + nt * BN < p.N && c + 1 < BN / 32) fetch_res(c + 1);
                 __syncwarp();
                 tc::tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
                 tc::tmem_ld_wait();
@@ -214,7 +240,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         b4 = make_float4(tb[0], tb[1], tb[2], tb[3]);
                     }
                 }
-#pragma unroll 2
+#pragma unroll
                 for (int pass = 0; pass < 8; ++pass) {
                     const int r = pass * 4 + pr;
                     const int t = t0 + q * 32 + r;
@@ -238,7 +264,15 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                     if (p.res) {
                         const size_t rrow = grow * (size_t)p.ldres + n;
                         if (colv && p.vec_io) {
-                            const float4 e = ld_vec4(p.res, p.res_dtype, rrow);
+                            float4 e;
+                            if (p.res_dtype == FACTK_BF16) {
+                                const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rcur[pass].x));
+                                const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rcur[pass].y));
+                                e = make_float4(lo.x, lo.y, hi.x, hi.y);
+                            } else {
+                                e = make_float4(__uint_as_float(rcur[pass].x), __uint_as_float(rcur[pass].y),
+                                                __uint_as_float(rcur[pass].z), __uint_as_float(rcur[pass].w));
+                            }
                             x[0] += e.x; x[1] += e.y; x[2] += e.z; x[3] += e.w;
                         } else {
                             for (int j = 0; j < 4 && n + j < p.N; ++j) x[j] += ld_elem(p.res, p.res_dtype, rrow + j);

@@ -103,10 +103,10 @@ __global__ void __launch_bounds__(128) segment_mean_kernel(const void* __restric
 // the KS = Hh/4 weights of gate row j for K slice kq), so a step reads only the hidden state from shared memory.
 // Per step: (1) every thread accumulates its K slice for the NB chains -> partials in shared memory,
 // (2) one thread per (chain, unit) sums the partials, applies the gates and stores the new hidden value into
-// the next-step buffer of all four CTAs through distributed shared memory, (3) one lane per gate warp does a
-// release-arrive on each CTA's "hidden state ready" mbarrier; consumers acquire-wait on their local barrier.
-// No cluster-wide barrier inside the loop; the global store of the output and the prefetch of the next input
-// gates come after the arrive, off the critical path.
+// the next-step buffer of all four CTAs with st.async (a distributed-shared-memory store that completes
+// transaction bytes on the destination CTA's "hidden state ready" mbarrier), (3) consumers wait on their local
+// barrier.  No fence and no cluster-wide barrier inside the loop; the global store of the output and the
+// prefetch of the next input gates come after the exchange, off the critical path.
 constexpr int GRU_CS = 4;   // CTAs per cluster
 constexpr int GRU_KQ = 4;   // K split of the mat-vec inside a CTA
 
@@ -164,9 +164,13 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             const uint32_t a = (uint32_t)__cvta_generic_to_shared(&hready[i]);
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(GRU_CS * GATE_W) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(1) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 2; ++i) {   // arm both phases: every step delivers NB*Hh floats from the four CTAs
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&hready[i]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(NB * Hh * 4) : "memory");
+        }
     }
 
     int S[NB], vb[NB], maxS = 0;
@@ -176,7 +180,6 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
         S[nb] = (vb[nb] < B) ? min(nseg[vb[nb]], slot) : 0;
         maxS = max(maxS, S[nb]);
     }
-    const bool gate_warp = (tid >> 5) < GATE_W;
     const bool gate = tid < GATE_T;
     const int gnb = gate ? tid / U : 0, gu = gate ? tid % U : 0, unit = rank * U + gu;
     int myS = 0, myv = 0;
@@ -203,7 +206,14 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
 
     for (int t = 0; t < maxS; ++t) {
         const int cur = t & 1;
-        if (t > 0) mbar_wait_acquire_cluster(&hready[cur], ((t - 1) >> 1) & 1);
+        if (t > 0) {
+            if (lane == 0) mbar_wait_acquire_cluster(&hready[cur], ((t - 1) >> 1) & 1);
+            __syncwarp();
+            if (tid == 0) {   // re-arm for this buffer's next use (exchange t+1)
+                const uint32_t a = (uint32_t)__cvta_generic_to_shared(&hready[cur]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(NB * Hh * 4) : "memory");
+            }
+        }
         const float* h = hb + cur * NB * Hh;
         {
             float acc[NB];
@@ -223,9 +233,9 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
             for (int nb = 0; nb < NB; ++nb) part[(nb * GRU_KQ + kq) * R + j] = acc[nb];
         }
         __syncthreads();
-        if (gate_warp) {
-            float hn = 0.f;
-            const bool live = gate && t < myS;
+        if (gate) {
+            const bool live = t < myS;
+            float hn = h[gnb * Hh + unit];      // finished chains re-send their last state: byte counts stay constant
             if (live) {
                 const float* pp = part + gnb * GRU_KQ * R;
                 float a_r = b_r, a_z = b_z, a_n = b_n;
@@ -235,23 +245,16 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
                 }
                 const float r = sigmoidf_(g_r + a_r), z = sigmoidf_(g_z + a_z);
                 const float n = tanhf(g_n + r * a_n);
-                hn = (1.f - z) * n + z * h[gnb * Hh + unit];
-                const int o = (cur ^ 1) * NB * Hh + gnb * Hh + unit;
-#pragma unroll
-                for (int rr = 0; rr < GRU_CS; ++rr) {
-                    uint32_t ra;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(hb_u32 + (uint32_t)o * 4u), "r"(rr));
-                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(hn) : "memory");
-                }
+                hn = (1.f - z) * n + z * hn;
             }
-            __syncwarp();
-            if (lane == 0) {
+            const uint32_t o = (uint32_t)((cur ^ 1) * NB * Hh + gnb * Hh + unit) * 4u;
 #pragma unroll
-                for (int rr = 0; rr < GRU_CS; ++rr) {
-                    uint32_t ra;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar_u32 + (uint32_t)(cur ^ 1) * 8u), "r"(rr));
-                    mbar_arrive_remote_release(ra);
-                }
+            for (int rr = 0; rr < GRU_CS; ++rr) {
+                uint32_t ra, rb;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(hb_u32 + o), "r"(rr));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(bar_u32 + (uint32_t)(cur ^ 1) * 8u), "r"(rr));
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                             ::"r"(ra), "r"(__float_as_uint(hn)), "r"(rb) : "memory");
             }
             if (live) {
                 const int s = dir ? myS - 1 - t : t;
