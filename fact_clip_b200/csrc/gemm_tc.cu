@@ -53,7 +53,7 @@ struct TcCfg {
     static constexpr int STAGE_B = BN * 128;
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int STG = 4 * 32 * 36 * 4;   // per-epilogue-warp staging tile [32][36] fp32
+    static constexpr int STG = 8 * 32 * 36 * 4;   // per-epilogue-warp staging tile [32][36] fp32
     static constexpr int SMEM = NSTAGE * STAGE + 256 + STG + 1024;
 };
 
@@ -70,10 +70,24 @@ __device__ __forceinline__ void ld_row32(const void* base, int dtype, size_t off
     }
 }
 
-template <int BN, bool TF32>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;
+
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// YBF: output dtype is bf16 (else fp32).  RES: 0 = no residual, 1 = bf16 residual, 2 = fp32 residual.
+template <int BN, bool TF32, bool YBF, int RES>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN>;
     constexpr int EPC = TF32 ? 32 : 64;   // elements per 128-byte K chunk
+    constexpr int NC = BN / 32;           // 32-column chunks per tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::NSTAGE * Cfg::STAGE);
@@ -98,7 +112,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             }
             for (int i = 0; i < 2; ++i) {
                 tc::mbar_init(&tfull[i], 1);
-                tc::mbar_init(&tempty[i], 128);
+                tc::mbar_init(&tempty[i], TC_EPI_WARPS * 32);
             }
             tc::fence_barrier_init();
         }
@@ -175,8 +189,13 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             }
         }
     } else {
-        const int q = warp & 3;             // TMEM lane quarter this warp may access
-        float* stg = reinterpret_cast<float*>(smem + Cfg::NSTAGE * Cfg::STAGE + 256) + (warp - 2) * (32 * 36);
+        // ---------------- epilogue: 8 warps; warp -> (TMEM lane quarter q, column half) ----------------
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        constexpr int CPW = NC / 2;                       // chunks per warp
+        const uint32_t stg = tc::smem_u32(smem + Cfg::NSTAGE * Cfg::STAGE + 256) + (uint32_t)ew * (32 * 36 * 4);
+        const int pr = lane >> 3, cg = (lane & 7) * 4;   // phase 2: 8 lanes x 4 columns per row, 4 rows per pass
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int b, t0, nt, len_b;
@@ -184,104 +203,101 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             const int acc = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ++it;
-            // residual rows do not depend on the MMAs: fetch chunk 0 before waiting, chunk c+1 while chunk c is processed
-            const bool res_vec = p.res != nullptr && p.vec_io;
-            const int lpr = lane >> 3, lcg = (lane & 7) * 4;
+            const size_t rowbase = (size_t)b * p.slot + t0 + q * 32;
+            const int rows_valid = len_b - (t0 + q * 32);     // rows r < rows_valid of this warp's 32 are real
+            const float* bias = p.bias ? p.bias + (size_t)b * (size_t)p.bias_bstride : nullptr;
+            const int c_begin = half * CPW;
+
             uint4 rnext[8];
             auto fetch_res = [&](int c) {
-                const int n = nt * BN + c * 32 + lcg;
+                if constexpr (RES != 0) {
+                    const int n = nt * BN + c * 32 + cg;
 #pragma unroll
-                for (int pass = 0; pass < 8; ++pass) {
-                    const int t = t0 + q * 32 + pass * 4 + lpr;
-                    rnext[pass] = make_uint4(0u, 0u, 0u, 0u);
-                    if (res_vec && t < len_b && n + 4 <= p.N) {
-                        const size_t off = ((size_t)b * p.slot + t) * (size_t)p.ldres + n;
-                        if (p.res_dtype == FACTK_BF16) {
-                            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + off);
-                            rnext[pass].x = u.x; rnext[pass].y = u.y;
-                        } else {
-                            rnext[pass] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res) + off);
+                    for (int pass = 0; pass < 8; ++pass) {
+                        const int r = pass * 4 + pr;
+                        rnext[pass] = make_uint4(0u, 0u, 0u, 0u);
+                        if (p.vec_io && r < rows_valid && n + 4 <= p.N) {
+                            const size_t off = (rowbase + r) * (size_t)p.ldres + n;
+                            if constexpr (RES == 1) {
+                                const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + off);
+                                rnext[pass].x = u.x; rnext[pass].y = u.y;
+                            } else {
+                                rnext[pass] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res) + off);
+                            }
                         }
                     }
                 }
             };
-            fetch_res(0);
+            // residual rows do not depend on the MMAs: fetch the first chunk before waiting for the accumulator
+            if (nt * BN + c_begin * 32 < p.N) fetch_res(c_begin);
             tc::mbar_wait(&tfull[acc], aphase);
             tc::tc_fence_after();
-            const float* bias = p.bias ? p.bias + (size_t)b * (size_t)p.bias_bstride : nullptr;
-            // lane -> (row within a 4-row pass, 4 consecutive columns) for the coalesced second phase
-            const int pr = lane >> 3, cg = (lane & 7) * 4;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int ci = 0; ci < CPW; ++ci) {
+                const int c = c_begin + ci;
                 const int n0 = nt * BN + c * 32;
                 if (n0 >= p.N) break;
-                float v[32];
                 uint4 rcur[8];
+                if constexpr (RES != 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-                if ((c + 1) * 32 + nt * BN < p.N && c + 1 < BN / 32) fetch_res(c + 1);
+                    for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+                    if (ci + 1 < CPW && n0 + 32 < p.N) fetch_res(c + 1);
+                }
+                float v[32];
                 __syncwarp();
                 tc::tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
                 tc::tmem_ld_wait();
-                // phase 1: thread = accumulator row -> staging tile [32 rows][36] (conflict-free float4 stores)
+                // phase 1: thread = accumulator row -> staging tile [32 rows][36 floats] (conflict-free 128-bit stores)
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(&stg[lane * 36 + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4) sts128(stg + (uint32_t)(lane * 36 + j) * 4u, v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
-                // phase 2: 8 lanes cover the 32 columns of one row, 4 rows per pass -> contiguous 64/128-byte row segments
+                // phase 2: contiguous 4-column groups per lane -> coalesced row segments
                 const int n = n0 + cg;
-                const bool colv = n + 4 <= p.N;
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool colv = p.vec_io && (n + 4 <= p.N);
+                float b4[4] = {0.f, 0.f, 0.f, 0.f};
                 if (bias) {
-                    if (colv) b4 = make_float4(__ldg(bias + n), __ldg(bias + n + 1), __ldg(bias + n + 2), __ldg(bias + n + 3));
-                    else {
-                        float tb[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int j = 0; j < 4 && n + j < p.N; ++j) tb[j] = __ldg(bias + n + j);
-                        b4 = make_float4(tb[0], tb[1], tb[2], tb[3]);
-                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < p.N) b4[j] = __ldg(bias + n + j);
                 }
 #pragma unroll
                 for (int pass = 0; pass < 8; ++pass) {
                     const int r = pass * 4 + pr;
-                    const int t = t0 + q * 32 + r;
-                    if (t >= len_b || n >= p.N) continue;
-                    const size_t grow = (size_t)b * p.slot + t;
-                    const float4 a4 = *reinterpret_cast<const float4*>(&stg[r * 36 + cg]);
-                    float x[4] = {a4.x * p.alpha + b4.x, a4.y * p.alpha + b4.y, a4.z * p.alpha + b4.z, a4.w * p.alpha + b4.w};
+                    if (r >= rows_valid || n >= p.N) continue;
+                    const size_t grow = rowbase + r;
+                    const float4 a4 = lds128(stg + (uint32_t)(r * 36 + cg) * 4u);
+                    float x[4] = {fmaf(a4.x, p.alpha, b4[0]), fmaf(a4.y, p.alpha, b4[1]), fmaf(a4.z, p.alpha, b4[2]),
+                                  fmaf(a4.w, p.alpha, b4[3])};
                     if (p.pre) {
-                        const size_t prow = (size_t)b * (size_t)p.pre_bstride + (size_t)(p.pre_idx ? p.pre_idx[grow] : t) * (size_t)p.ldpre + n;
-                        if (colv && p.vec_io) {
-                            const float4 e = ld_vec4(p.pre, p.pre_dtype, prow);
-                            x[0] += e.x; x[1] += e.y; x[2] += e.z; x[3] += e.w;
-                        } else {
-                            for (int j = 0; j < 4 && n + j < p.N; ++j) x[j] += ld_elem(p.pre, p.pre_dtype, prow + j);
-                        }
+                        const size_t prow = (size_t)b * (size_t)p.pre_bstride +
+                                            (size_t)(p.pre_idx ? p.pre_idx[grow] : (int)(t0 + q * 32 + r)) * (size_t)p.ldpre + n;
+                        for (int j = 0; j < 4 && n + j < p.N; ++j) x[j] += ld_elem(p.pre, p.pre_dtype, prow + j);
                     }
                     if (p.relu) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
                     }
-                    if (p.res) {
-                        const size_t rrow = grow * (size_t)p.ldres + n;
-                        if (colv && p.vec_io) {
-                            float4 e;
-                            if (p.res_dtype == FACTK_BF16) {
+                    if constexpr (RES != 0) {
+                        if (colv) {
+                            if constexpr (RES == 1) {
                                 const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rcur[pass].x));
                                 const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rcur[pass].y));
-                                e = make_float4(lo.x, lo.y, hi.x, hi.y);
+                                x[0] += lo.x; x[1] += lo.y; x[2] += hi.x; x[3] += hi.y;
                             } else {
-                                e = make_float4(__uint_as_float(rcur[pass].x), __uint_as_float(rcur[pass].y),
-                                                __uint_as_float(rcur[pass].z), __uint_as_float(rcur[pass].w));
+                                x[0] += __uint_as_float(rcur[pass].x); x[1] += __uint_as_float(rcur[pass].y);
+                                x[2] += __uint_as_float(rcur[pass].z); x[3] += __uint_as_float(rcur[pass].w);
                             }
-                            x[0] += e.x; x[1] += e.y; x[2] += e.z; x[3] += e.w;
                         } else {
-                            for (int j = 0; j < 4 && n + j < p.N; ++j) x[j] += ld_elem(p.res, p.res_dtype, rrow + j);
+                            for (int j = 0; j < 4 && n + j < p.N; ++j)
+                                x[j] += ld_elem(p.res, RES == 1 ? FACTK_BF16 : FACTK_F32, grow * (size_t)p.ldres + n + j);
                         }
                     }
-                    const size_t yrow = grow * (size_t)p.ldy + n;
-                    if (colv && p.vec_io) st_vec4(p.Y, p.y_dtype, yrow, make_float4(x[0], x[1], x[2], x[3]));
-                    else
-                        for (int j = 0; j < 4 && n + j < p.N; ++j) st_elem(p.Y, p.y_dtype, yrow + j, x[j]);
+                    const size_t yoff = grow * (size_t)p.ldy + n;
+                    if (colv) {
+                        st_vec4(p.Y, YBF ? FACTK_BF16 : FACTK_F32, yoff, make_float4(x[0], x[1], x[2], x[3]));
+                    } else {
+                        for (int j = 0; j < 4 && n + j < p.N; ++j) st_elem(p.Y, YBF ? FACTK_BF16 : FACTK_F32, yoff + j, x[j]);
+                    }
                 }
             }
             tc::tc_fence_before();
@@ -364,16 +380,30 @@ static const char* tc_unsupported_reason(const factk_gemm_t* g) {
     return nullptr;
 }
 
-template <int BN, bool TF32>
-static int launch_tc(const TcParams& p, int grid, cudaStream_t st) {
+template <int BN, bool TF32, bool YBF, int RES>
+static int launch_tc4(const TcParams& p, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, YBF, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM);
         if (e != cudaSuccess) { set_error("factk_gemm_tc: smem attribute: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; }
         attr_set = true;
     }
-    gemm_tc_kernel<BN, TF32><<<grid, 192, TcCfg<BN>::SMEM, st>>>(p);
+    gemm_tc_kernel<BN, TF32, YBF, RES><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(p);
     return check_launch("factk_gemm_tc");
+}
+
+template <int BN, bool TF32>
+static int launch_tc(const TcParams& p, int grid, cudaStream_t st) {
+    const bool ybf = p.y_dtype == FACTK_BF16;
+    const int res = p.res == nullptr ? 0 : (p.res_dtype == FACTK_BF16 ? 1 : 2);
+    if (ybf) {
+        if (res == 0) return launch_tc4<BN, TF32, true, 0>(p, grid, st);
+        if (res == 1) return launch_tc4<BN, TF32, true, 1>(p, grid, st);
+        return launch_tc4<BN, TF32, true, 2>(p, grid, st);
+    }
+    if (res == 0) return launch_tc4<BN, TF32, false, 0>(p, grid, st);
+    if (res == 1) return launch_tc4<BN, TF32, false, 1>(p, grid, st);
+    return launch_tc4<BN, TF32, false, 2>(p, grid, st);
 }
 
 }  // namespace factk
