@@ -53,7 +53,7 @@ struct TcCfg {
     static constexpr int STAGE_B = BN * 128;
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int STG = 8 * 32 * 36 * 4;   // per-epilogue-warp staging tile [32][36] fp32
+    static constexpr int STG = 8 * 32 * 20 * 4;   // per-epilogue-warp staging tile [32 rows][16 cols + 4 pad] fp32
     static constexpr int SMEM = NSTAGE * STAGE + 256 + STG + 1024;
 };
 
@@ -70,6 +70,7 @@ __device__ __forceinline__ void ld_row32(const void* base, int dtype, size_t off
     }
 }
 
+static_assert(TcCfg<256>::SMEM <= 232448 && TcCfg<128>::SMEM <= 232448 && TcCfg<64>::SMEM <= 232448, "dynamic smem limit");
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;
 
@@ -194,8 +195,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const int q = warp & 3;
         const int half = ew >> 2;
         constexpr int CPW = NC / 2;                       // chunks per warp
-        const uint32_t stg = tc::smem_u32(smem + Cfg::NSTAGE * Cfg::STAGE + 256) + (uint32_t)ew * (32 * 36 * 4);
-        const int pr = lane >> 3, cg = (lane & 7) * 4;   // phase 2: 8 lanes x 4 columns per row, 4 rows per pass
+        const uint32_t stg = tc::smem_u32(smem + Cfg::NSTAGE * Cfg::STAGE + 256) + (uint32_t)ew * (32 * 20 * 4);
+        const int pr = lane >> 2, cg = (lane & 3) * 4;   // phase 2: 4 lanes x 4 columns per row, 8 rows per pass, 16-column halves
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int b, t0, nt, len_b;
@@ -211,10 +212,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             uint4 rnext[8];
             auto fetch_res = [&](int c) {
                 if constexpr (RES != 0) {
-                    const int n = nt * BN + c * 32 + cg;
 #pragma unroll
                     for (int pass = 0; pass < 8; ++pass) {
-                        const int r = pass * 4 + pr;
+                        const int n = nt * BN + c * 32 + (pass >> 2) * 16 + cg;
+                        const int r = (pass & 3) * 8 + pr;
                         rnext[pass] = make_uint4(0u, 0u, 0u, 0u);
                         if (p.vec_io && r < rows_valid && n + 4 <= p.N) {
                             const size_t off = (rowbase + r) * (size_t)p.ldres + n;
@@ -247,56 +248,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                 __syncwarp();
                 tc::tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
                 tc::tmem_ld_wait();
-                // phase 1: thread = accumulator row -> staging tile [32 rows][36 floats] (conflict-free 128-bit stores)
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) sts128(stg + (uint32_t)(lane * 36 + j) * 4u, v[j], v[j + 1], v[j + 2], v[j + 3]);
-                __syncwarp();
-                // phase 2: contiguous 4-column groups per lane -> coalesced row segments
-                const int n = n0 + cg;
-                const bool colv = p.vec_io && (n + 4 <= p.N);
-                float b4[4] = {0.f, 0.f, 0.f, 0.f};
-                if (bias) {
+                for (int sub = 0; sub < 2; ++sub) {
+                    // phase 1: thread = accumulator row -> staging tile [32 rows][16 cols (+4 pad)], conflict-free 128-bit stores
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (n + j < p.N) b4[j] = __ldg(bias + n + j);
-                }
+                    for (int j = 0; j < 16; j += 4)
+                        sts128(stg + (uint32_t)(lane * 20 + j) * 4u, v[sub * 16 + j], v[sub * 16 + j + 1], v[sub * 16 + j + 2], v[sub * 16 + j + 3]);
+                    __syncwarp();
+                    // phase 2: contiguous 4-column groups per lane -> coalesced row segments
+                    const int n = n0 + sub * 16 + cg;
+                    if (n >= p.N) continue;
+                    const bool colv = p.vec_io && (n + 4 <= p.N);
+                    float b4[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (bias) {
 #pragma unroll
-                for (int pass = 0; pass < 8; ++pass) {
-                    const int r = pass * 4 + pr;
-                    if (r >= rows_valid || n >= p.N) continue;
-                    const size_t grow = rowbase + r;
-                    const float4 a4 = lds128(stg + (uint32_t)(r * 36 + cg) * 4u);
-                    float x[4] = {fmaf(a4.x, p.alpha, b4[0]), fmaf(a4.y, p.alpha, b4[1]), fmaf(a4.z, p.alpha, b4[2]),
-                                  fmaf(a4.w, p.alpha, b4[3])};
-                    if (p.pre) {
-                        const size_t prow = (size_t)b * (size_t)p.pre_bstride +
-                                            (size_t)(p.pre_idx ? p.pre_idx[grow] : (int)(t0 + q * 32 + r)) * (size_t)p.ldpre + n;
-                        for (int j = 0; j < 4 && n + j < p.N; ++j) x[j] += ld_elem(p.pre, p.pre_dtype, prow + j);
+                        for (int j = 0; j < 4; ++j)
+                            if (n + j < p.N) b4[j] = __ldg(bias + n + j);
                     }
-                    if (p.relu) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
-                    }
-                    if constexpr (RES != 0) {
-                        if (colv) {
-                            if constexpr (RES == 1) {
-                                const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rcur[pass].x));
-                                const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rcur[pass].y));
-                                x[0] += lo.x; x[1] += lo.y; x[2] += hi.x; x[3] += hi.y;
-                            } else {
-                                x[0] += __uint_as_float(rcur[pass].x); x[1] += __uint_as_float(rcur[pass].y);
-                                x[2] += __uint_as_float(rcur[pass].z); x[3] += __uint_as_float(rcur[pass].w);
-                            }
-                        } else {
-                            for (int j = 0; j < 4 && n + j < p.N; ++j)
-                                x[j] += ld_elem(p.res, RES == 1 ? FACTK_BF16 : FACTK_F32, grow * (size_t)p.ldres + n + j);
+                    for (int ps = 0; ps < 4; ++ps) {
+                        const int r = ps * 8 + pr;
+                        if (r >= rows_valid) continue;
+                        const int pass = sub * 4 + ps;
+                        const size_t grow = rowbase + r;
+                        const float4 a4 = lds128(stg + (uint32_t)(r * 20 + cg) * 4u);
+                        float x[4] = {fmaf(a4.x, p.alpha, b4[0]), fmaf(a4.y, p.alpha, b4[1]), fmaf(a4.z, p.alpha, b4[2]),
+                                      fmaf(a4.w, p.alpha, b4[3])};
+                        if (p.pre) {
+                            const size_t prow = (size_t)b * (size_t)p.pre_bstride +
+                                                (size_t)(p.pre_idx ? p.pre_idx[grow] : (int)(t0 + q * 32 + r)) * (size_t)p.ldpre + n;
+                            for (int j = 0; j < 4 && n + j < p.N; ++j) x[j] += ld_elem(p.pre, p.pre_dtype, prow + j);
                         }
-                    }
-                    const size_t yoff = grow * (size_t)p.ldy + n;
-                    if (colv) {
-                        st_vec4(p.Y, YBF ? FACTK_BF16 : FACTK_F32, yoff, make_float4(x[0], x[1], x[2], x[3]));
-                    } else {
-                        for (int j = 0; j < 4 && n + j < p.N; ++j) st_elem(p.Y, YBF ? FACTK_BF16 : FACTK_F32, yoff + j, x[j]);
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
+                        }
+                        if constexpr (RES != 0) {
+                            if (colv) {
+                                if constexpr (RES == 1) {
+                                    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rcur[pass].x));
+                                    const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rcur[pass].y));
+                                    x[0] += lo.x; x[1] += lo.y; x[2] += hi.x; x[3] += hi.y;
+                                } else {
+                                    x[0] += __uint_as_float(rcur[pass].x); x[1] += __uint_as_float(rcur[pass].y);
+                                    x[2] += __uint_as_float(rcur[pass].z); x[3] += __uint_as_float(rcur[pass].w);
+                                }
+                            } else {
+                                for (int j = 0; j < 4 && n + j < p.N; ++j)
+                                    x[j] += ld_elem(p.res, RES == 1 ? FACTK_BF16 : FACTK_F32, grow * (size_t)p.ldres + n + j);
+                            }
+                        }
+                        const size_t yoff = grow * (size_t)p.ldy + n;
+                        if (colv) {
+                            st_vec4(p.Y, YBF ? FACTK_BF16 : FACTK_F32, yoff, make_float4(x[0], x[1], x[2], x[3]));
+                        } else {
+                            for (int j = 0; j < 4 && n + j < p.N; ++j) st_elem(p.Y, YBF ? FACTK_BF16 : FACTK_F32, yoff + j, x[j]);
+                        }
                     }
                 }
             }
