@@ -31,6 +31,7 @@ class FactEngine:
         self.act = torch.bfloat16 if mode == 'bf16' else torch.float32
         self._bufs, self._zbufs, self._len_sig = {}, {}, None
         self.use_tc = True
+        self._submits, self._copy_stream, self._slot_free = 0, None, [None, None]
         self._wcache, self._wsig = {}, None
 
     # ------------------------------------------------------------------ memory / weights
@@ -364,7 +365,7 @@ class FactEngine:
     # ------------------------------------------------------------------ whole forward
     @torch.no_grad()
     def run(self, seqs, forced_preds=None, keep=False):
-        """seqs: list of (T_i, in_dim) fp32 CUDA tensors (or one packed [B,slot,D] + lengths via run_packed)."""
+        """seqs: list of (T_i, in_dim) fp32 tensors, CUDA or (pinned) host.  Synchronous with respect to the stream."""
         self._refresh_weights()
         lengths = [int(s.shape[0]) for s in seqs]
         B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
@@ -376,7 +377,44 @@ class FactEngine:
         return self.run_packed(x, ln, lengths, forced_preds, keep)
 
     @torch.no_grad()
-    def run_packed(self, x, ln, lengths, forced_preds=None, keep=False):
+    def submit(self, seqs):
+        """Pipelined forward: the host->device copy of this batch runs on a side stream into one of two input
+        buffers and overlaps the kernels of the previously submitted batch; the predictions are copied to pinned
+        host memory asynchronously.  Returns a handle; ``handle.result()`` blocks until this batch is done."""
+        self._refresh_weights()
+        lengths = [int(s.shape[0]) for s in seqs]
+        B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
+        k = self._submits % 2
+        self._submits += 1
+        main = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        x = self.buf(f'input_p{k}', (B, slot, D))
+        ln = self.buf(f'len_p{k}', (B,), torch.int32)
+        pred = self.buf(f'pred64_p{k}', (B, slot), torch.int64)
+        key = (f'pred_host_p{k}', B, slot)
+        if key not in self._bufs:
+            self._bufs[key] = torch.empty(B, slot, dtype=torch.int64, pin_memory=True)
+        host = self._bufs[key]
+        free = self._slot_free[k]
+        with torch.cuda.stream(self._copy_stream):
+            if free is not None:
+                self._copy_stream.wait_event(free)          # the previous user of this input buffer has finished
+            for b, s in enumerate(seqs):
+                x[b, :lengths[b]].copy_(s, non_blocking=True)
+            ln.copy_(torch.tensor(lengths, dtype=torch.int32).pin_memory(), non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self._copy_stream)
+        main.wait_event(copied)
+        out = self.run_packed(x, ln, lengths, pred_out=pred)
+        host.copy_(pred, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        self._slot_free[k] = done
+        return _Pending(done, host, lengths, out)
+
+    @torch.no_grad()
+    def run_packed(self, x, ln, lengths, forced_preds=None, keep=False, pred_out=None):
         self._refresh_weights()
         hp = self.hp
         self.B, self.slot, self.len, self.keep = x.shape[0], x.shape[1], ln, keep
@@ -426,7 +464,7 @@ class FactEngine:
             out['projected_frame_embeddings'], out['clip_logit'] = emb, flogit
         else:
             flogit = last['frame_clogit']
-        pred64 = self.buf('pred64', (B, slot), torch.int64)
+        pred64 = pred_out if pred_out is not None else self.buf('pred64', (B, slot), torch.int64)
         if 'a2f_attn' in last:
             ops.fuse_eval(last['action_clogit'], last['a2f_attn'], flogit, hp['mwt'], pred64, M, C, len=ln)
         elif 'a2f_attn_seg' in last:
@@ -436,6 +474,18 @@ class FactEngine:
             ops.fuse_eval(None, None, flogit, hp['mwt'], pred64, 0, C, len=ln)
         out['pred'] = pred64
         return out
+
+
+class _Pending:
+    """Handle of a submitted batch (FactEngine.submit)."""
+
+    def __init__(self, done, host_pred, lengths, out):
+        self.done, self.host_pred, self.lengths, self.out = done, host_pred, lengths, out
+
+    def result(self):
+        self.done.synchronize()
+        p = self.host_pred.numpy()
+        return [{'pred': p[b, :T].copy()} for b, T in enumerate(self.lengths)]
 
 
 def _pos_table(d_model, length, device):

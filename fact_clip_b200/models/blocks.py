@@ -174,6 +174,16 @@ class _FactBase(nn.Module):
         self.stash_video(len(seqs) - 1)
         return [{'pred': pred[b, :T].copy()} for b, T in enumerate(out['lengths'])]
 
+    def submit(self, seq_list, label_list=None):
+        """Asynchronous variant of ``forward`` for inference loops: enqueue the host->device copy (side stream,
+        double-buffered), the kernels and the device->host copy of the predictions, and return a handle whose
+        ``result()`` gives the same list ``forward`` returns.  Lets batch i+1's input copy overlap batch i's kernels."""
+        if self.action_query.device.type != 'cuda':
+            raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
+        h = self.engine().submit(list(seq_list))
+        self._last = h.out
+        return h
+
     def stash_video(self, b):
         """Expose video ``b`` of the last batch through the reference's per-block attributes
         (blocks.py:305-309, 359-366, 473-483) as views -- shapes (T,1,C), (M,1,C+1), (1,T,M)..."""

@@ -194,3 +194,17 @@ def test_shipped_configs_bf16_tensor_core_path(preset, ncls, lens):
         tot += lens[b]
     print(preset, rows)
     assert agree / tot >= 0.999
+
+
+def test_pipelined_submit_matches_forward():
+    """net.submit(...).result() (double-buffered async H2D) returns what net(...) returns, from pinned host inputs."""
+    g = load_golden('tiny_m_iuU_clip')
+    net = build(g, 'fp32')
+    xs = [v['x'].pin_memory() for v in g['videos']]
+    ys = [v['label'] for v in g['videos']]
+    ref = net([x.to(DEV) for x in xs], ys)
+    handles = [net.submit(xs, ys) for _ in range(3)]
+    for h in handles:
+        got = h.result()
+        for a, b in zip(ref, got):
+            assert np.array_equal(a['pred'], b['pred'])
