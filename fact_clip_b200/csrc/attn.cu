@@ -137,6 +137,173 @@ __global__ void __launch_bounds__(320) attn_rows_partial_kernel(const float* __r
     }
 }
 
+// Same computation on the warp-level tensor-core path for bf16 keys / values (DH a multiple of 16): each warp owns
+// 16 query tokens; K/V tiles of 64 frames are staged in shared memory (register-prefetched one tile ahead),
+// S = Q K^T and O += P V run as mma.sync m16n8k16 (bf16 in, fp32 accumulate), the online softmax stays in the
+// accumulator registers with quad shuffles.  Writes the same partial layout as attn_rows_partial_kernel.
+__device__ __forceinline__ void mma_bf16_16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restrict__ Q, int ldq,
+                                                            const __nv_bfloat16* __restrict__ Kx,
+                                                            const __nv_bfloat16* __restrict__ Vx, int ldkv,
+                                                            float* __restrict__ part, int slot,
+                                                            const int32_t* __restrict__ len, int M, int nhead, int nsplit) {
+    constexpr int TR = 64;              // frames per tile
+    constexpr int LDT = DH + 8;         // padded smem row (bf16 elements): conflict-free fragment loads, 16B-aligned rows
+    constexpr int KS = DH / 16;         // k-steps of the QK^T product
+    constexpr int NT = DH / 8;          // n-tiles of the output
+    constexpr int CH = DH / 8;          // 16-byte chunks per row
+    __shared__ __align__(16) __nv_bfloat16 Ks[TR * LDT];
+    __shared__ __align__(16) __nv_bfloat16 Vs[TR * LDT];
+    const int sp = blockIdx.x % nsplit, qb = blockIdx.x / nsplit, h = blockIdx.y, b = blockIdx.z;
+    const int len_b = len ? min(len[b], slot) : slot;
+    const int r0 = sp * SPLIT_ROWS;
+    if (r0 >= len_b) return;
+    const int r1 = min(r0 + SPLIT_ROWS, len_b);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    const int m_lo = qb * 128 + warp * 16 + g, m_hi = m_lo + 8;   // up to 8 warps x 16 queries per CTA
+    const float scale = rsqrtf((float)DH);
+
+    // Q fragments (A operand, row-major 16 x DH), scaled, bf16
+    uint32_t qa[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int d = ks * 16 + tig * 2;
+        const float* ql = Q + ((size_t)b * M + m_lo) * ldq + h * DH + d;
+        const float* qh = Q + ((size_t)b * M + m_hi) * ldq + h * DH + d;
+        const bool vl = m_lo < M, vh = m_hi < M;
+        qa[ks][0] = pack_bf16(vl ? ql[0] * scale : 0.f, vl ? ql[1] * scale : 0.f);
+        qa[ks][1] = pack_bf16(vh ? qh[0] * scale : 0.f, vh ? qh[1] * scale : 0.f);
+        qa[ks][2] = pack_bf16(vl ? ql[8] * scale : 0.f, vl ? ql[9] * scale : 0.f);
+        qa[ks][3] = pack_bf16(vh ? qh[8] * scale : 0.f, vh ? qh[9] * scale : 0.f);
+    }
+    float o[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float mx_lo = -INFINITY, mx_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+    // cooperative tile load: chunk id -> (row, 16B chunk); register-prefetched one tile ahead
+    constexpr int NCHUNK = TR * CH;
+    const int nthr = blockDim.x;
+    constexpr int MAXPF = 4;            // blockDim.x >= 128 and NCHUNK <= 512, so 4 chunks per thread cover a tile
+    uint4 pk[MAXPF], pv[MAXPF];
+    auto g_load = [&](int t0) {
+#pragma unroll
+        for (int i = 0; i < MAXPF; ++i) {
+            const int c = threadIdx.x + i * nthr;
+            pk[i] = make_uint4(0u, 0u, 0u, 0u);
+            pv[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (c < NCHUNK) {
+                const int r = c / CH, ch = c % CH;
+                if (t0 + r < r1) {
+                    const size_t off = ((size_t)b * slot + t0 + r) * ldkv + h * DH + ch * 8;
+                    pk[i] = *reinterpret_cast<const uint4*>(Kx + off);
+                    pv[i] = *reinterpret_cast<const uint4*>(Vx + off);
+                }
+            }
+        }
+    };
+    auto s_store = [&]() {
+#pragma unroll
+        for (int i = 0; i < MAXPF; ++i) {
+            const int c = threadIdx.x + i * nthr;
+            if (c < NCHUNK) {
+                const int r = c / CH, ch = c % CH;
+                *reinterpret_cast<uint4*>(&Ks[r * LDT + ch * 8]) = pk[i];
+                *reinterpret_cast<uint4*>(&Vs[r * LDT + ch * 8]) = pv[i];
+            }
+        }
+    };
+    g_load(r0);
+    for (int t0 = r0; t0 < r1; t0 += TR) {
+        __syncthreads();                 // previous tile fully consumed
+        s_store();
+        __syncthreads();
+        if (t0 + TR < r1) g_load(t0 + TR);
+        // S = Q K^T  (16 queries x 64 frames)
+        float sacc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const __nv_bfloat16* kr = &Ks[(j * 8 + g) * LDT + ks * 16 + tig * 2];
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
+                mma_bf16_16816(sacc[j], qa[ks], b0, b1);
+            }
+        }
+        // mask frames beyond the split, online softmax (rows g and g+8 of this warp's tile)
+        float nm_lo = mx_lo, nm_hi = mx_hi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int t = t0 + j * 8 + tig * 2;
+            if (t >= r1) { sacc[j][0] = -INFINITY; sacc[j][2] = -INFINITY; }
+            if (t + 1 >= r1) { sacc[j][1] = -INFINITY; sacc[j][3] = -INFINITY; }
+            nm_lo = fmaxf(nm_lo, fmaxf(sacc[j][0], sacc[j][1]));
+            nm_hi = fmaxf(nm_hi, fmaxf(sacc[j][2], sacc[j][3]));
+        }
+        nm_lo = fmaxf(nm_lo, __shfl_xor_sync(0xffffffffu, nm_lo, 1));
+        nm_lo = fmaxf(nm_lo, __shfl_xor_sync(0xffffffffu, nm_lo, 2));
+        nm_hi = fmaxf(nm_hi, __shfl_xor_sync(0xffffffffu, nm_hi, 1));
+        nm_hi = fmaxf(nm_hi, __shfl_xor_sync(0xffffffffu, nm_hi, 2));
+        const float c_lo = __expf(mx_lo - nm_lo), c_hi = __expf(mx_hi - nm_hi);   // exp(-inf) = 0 on the first tile
+        l_lo *= c_lo; l_hi *= c_hi;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) { o[i][0] *= c_lo; o[i][1] *= c_lo; o[i][2] *= c_hi; o[i][3] *= c_hi; }
+        mx_lo = nm_lo; mx_hi = nm_hi;
+        // P = exp(S - max) packed straight into A fragments; O += P V
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t pa[4];
+            {
+                const float p00 = __expf(sacc[2 * kk][0] - nm_lo), p01 = __expf(sacc[2 * kk][1] - nm_lo);
+                const float p10 = __expf(sacc[2 * kk][2] - nm_hi), p11 = __expf(sacc[2 * kk][3] - nm_hi);
+                const float q00 = __expf(sacc[2 * kk + 1][0] - nm_lo), q01 = __expf(sacc[2 * kk + 1][1] - nm_lo);
+                const float q10 = __expf(sacc[2 * kk + 1][2] - nm_hi), q11 = __expf(sacc[2 * kk + 1][3] - nm_hi);
+                l_lo += p00 + p01 + q00 + q01;
+                l_hi += p10 + p11 + q10 + q11;
+                pa[0] = pack_bf16(p00, p01); pa[1] = pack_bf16(p10, p11);
+                pa[2] = pack_bf16(q00, q01); pa[3] = pack_bf16(q10, q11);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                // B fragment (k = frame, n = channel) from row-major V via ldmatrix.trans
+                const int r = kk * 16 + (lane & 15);
+                const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&Vs[r * LDT + nt * 8]);
+                uint32_t b0, b1;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+                mma_bf16_16816(o[nt], pa, b0, b1);
+            }
+        }
+    }
+    // partial results: (running max, running sum, acc[DH]) per query
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    float* base = part + (((size_t)b * nhead + h) * nsplit + sp) * M * (DH + 2);
+    if (m_lo < M) {
+        float* p = base + (size_t)m_lo * (DH + 2);
+        if (tig == 0) { p[0] = mx_lo; p[1] = l_lo; }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { p[2 + nt * 8 + tig * 2] = o[nt][0]; p[2 + nt * 8 + tig * 2 + 1] = o[nt][1]; }
+    }
+    if (m_hi < M) {
+        float* p = base + (size_t)m_hi * (DH + 2);
+        if (tig == 0) { p[0] = mx_hi; p[1] = l_hi; }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { p[2 + nt * 8 + tig * 2] = o[nt][2]; p[2 + nt * 8 + tig * 2 + 1] = o[nt][3]; }
+    }
+}
+
 template <int DH>
 __global__ void attn_rows_combine_kernel(const float* __restrict__ part, float* __restrict__ O, int ldo, int slot,
                                          const int32_t* __restrict__ len, int M, int nhead, int nsplit) {
@@ -323,6 +490,25 @@ extern "C" int factk_attn_rows(const float* Q, int ldq, const void* Kx, const vo
     const int ns = nsplit_of(slot);
     dim3 grid(ns, nhead, B), cgrid(nhead, B);
     const int threads = ((M + 31) / 32) * 32;
+    cudaStream_t st_ = (cudaStream_t)stream;
+    const bool kv16 = ((reinterpret_cast<uintptr_t>(Kx) | reinterpret_cast<uintptr_t>(Vx)) & 15u) == 0 && (ldkv % 8) == 0;
+    if (kv_dtype == FACTK_BF16 && kv16 && (dh == 16 || dh == 32 || dh == 64)) {
+        const int nqb = (M + 127) / 128;
+        int qwarps = (((M + nqb - 1) / nqb) + 15) / 16;
+        if (qwarps < 4) qwarps = 4;                  // extra warps only help staging the K/V tiles
+        const int wthreads = qwarps * 32;
+        const dim3 mgrid(ns * nqb, nhead, B);
+        const __nv_bfloat16* K16 = reinterpret_cast<const __nv_bfloat16*>(Kx);
+        const __nv_bfloat16* V16 = reinterpret_cast<const __nv_bfloat16*>(Vx);
+#define LAUNCH_MMA(DH)                                                                                                  \
+    do {                                                                                                                \
+        attn_rows_mma_kernel<DH><<<mgrid, wthreads, 0, st_>>>(Q, ldq, K16, V16, ldkv, ws, slot, len, M, nhead, ns);       \
+        attn_rows_combine_kernel<DH><<<cgrid, 256, 0, st_>>>(ws, O, ldo, slot, len, M, nhead, ns);                       \
+    } while (0)
+        if (dh == 16) LAUNCH_MMA(16); else if (dh == 32) LAUNCH_MMA(32); else LAUNCH_MMA(64);
+#undef LAUNCH_MMA
+        return check_launch("factk_attn_rows");
+    }
 #define LAUNCH(DH)                                                                                                     \
     do {                                                                                                               \
         attn_rows_partial_kernel<DH><<<grid, threads, 0, (cudaStream_t)stream>>>(Q, ldq, Kx, Vx, kv_dtype, ldkv, ws,    \

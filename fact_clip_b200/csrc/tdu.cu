@@ -120,13 +120,15 @@ __device__ __forceinline__ uint32_t cluster_map_u32(const void* local_smem, int 
 __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t raddr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
+// st.async data is visible to a thread that observes the phase completion; CTA-scope acquire avoids the L1
+// invalidate (CCTL.IVALL) a cluster-scope acquire would emit every step.
 __device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
     uint32_t ok = 0, spins = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(a), "r"(parity) : "memory");
         if (ok) break;
@@ -216,21 +218,22 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
         }
         const float* h = hb + cur * NB * Hh;
         {
-            float acc[NB];
+            float acc[NB][4];            // four independent chains per chain-of-videos: shortens the FMA dependency chain
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) acc[nb] = 0.f;
+            for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
             const float* hk = h + kq * KS;
 #pragma unroll
             for (int k = 0; k < KS; k += 4) {
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
                     const float4 h4 = *reinterpret_cast<const float4*>(&hk[nb * Hh + k]);
-                    acc[nb] = fmaf(w[k], h4.x, acc[nb]); acc[nb] = fmaf(w[k + 1], h4.y, acc[nb]);
-                    acc[nb] = fmaf(w[k + 2], h4.z, acc[nb]); acc[nb] = fmaf(w[k + 3], h4.w, acc[nb]);
+                    acc[nb][0] = fmaf(w[k], h4.x, acc[nb][0]); acc[nb][1] = fmaf(w[k + 1], h4.y, acc[nb][1]);
+                    acc[nb][2] = fmaf(w[k + 2], h4.z, acc[nb][2]); acc[nb][3] = fmaf(w[k + 3], h4.w, acc[nb][3]);
                 }
             }
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) part[(nb * GRU_KQ + kq) * R + j] = acc[nb];
+            for (int nb = 0; nb < NB; ++nb)
+                part[(nb * GRU_KQ + kq) * R + j] = (acc[nb][0] + acc[nb][1]) + (acc[nb][2] + acc[nb][3]);
         }
         __syncthreads();
         if (gate) {
