@@ -174,17 +174,22 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
     const float scale = rsqrtf((float)DH);
 
     // Q fragments (A operand, row-major 16 x DH), scaled, bf16
-    uint32_t qa[KS][4];
+    // (queries are fp32: split q = hi + lo into two bf16 fragments so the logits only carry the keys' rounding)
+    uint32_t qa[KS][4], qb_lo[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         const int d = ks * 16 + tig * 2;
         const float* ql = Q + ((size_t)b * M + m_lo) * ldq + h * DH + d;
         const float* qh = Q + ((size_t)b * M + m_hi) * ldq + h * DH + d;
         const bool vl = m_lo < M, vh = m_hi < M;
-        qa[ks][0] = pack_bf16(vl ? ql[0] * scale : 0.f, vl ? ql[1] * scale : 0.f);
-        qa[ks][1] = pack_bf16(vh ? qh[0] * scale : 0.f, vh ? qh[1] * scale : 0.f);
-        qa[ks][2] = pack_bf16(vl ? ql[8] * scale : 0.f, vl ? ql[9] * scale : 0.f);
-        qa[ks][3] = pack_bf16(vh ? qh[8] * scale : 0.f, vh ? qh[9] * scale : 0.f);
+        float v[8] = {vl ? ql[0] * scale : 0.f, vl ? ql[1] * scale : 0.f, vh ? qh[0] * scale : 0.f, vh ? qh[1] * scale : 0.f,
+                      vl ? ql[8] * scale : 0.f, vl ? ql[9] * scale : 0.f, vh ? qh[8] * scale : 0.f, vh ? qh[9] * scale : 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            qa[ks][i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[ks][i]));
+            qb_lo[ks][i] = pack_bf16(v[2 * i] - hi.x, v[2 * i + 1] - hi.y);
+        }
     }
     float o[NT][4];
 #pragma unroll
@@ -240,6 +245,7 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr);
                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
                 mma_bf16_16816(sacc[j], qa[ks], b0, b1);
+                mma_bf16_16816(sacc[j], qb_lo[ks], b0, b1);
             }
         }
         // mask frames beyond the split, online softmax (rows g and g+8 of this warp's tile)
@@ -494,7 +500,7 @@ extern "C" int factk_attn_rows(const float* Q, int ldq, const void* Kx, const vo
     const bool kv16 = ((reinterpret_cast<uintptr_t>(Kx) | reinterpret_cast<uintptr_t>(Vx)) & 15u) == 0 && (ldkv % 8) == 0;
     if (kv_dtype == FACTK_BF16 && kv16 && (dh == 16 || dh == 32 || dh == 64)) {
         const int nqb = (M + 127) / 128;
-        int qwarps = (((M + nqb - 1) / nqb) + 15) / 16;
+        int qwarps = nqb > 1 ? 8 : (M + 15) / 16;    // a query block is 128 tokens = 8 warps
         if (qwarps < 4) qwarps = 4;                  // extra warps only help staging the K/V tiles
         const int wthreads = qwarps * 32;
         const dim3 mgrid(ns * nqb, nhead, B);

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) fuse_eval_kernel(const float* _
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
-            mstar = bi;
+            mstar = bi < M ? bi : 0;     // NaN attention rows cannot index out of bounds
             qrow = aclogit + ((size_t)b * M + mstar) * (C + 1);
             qm = -INFINITY;
             for (int c = lane; c < C; c += 32) qm = fmaxf(qm, qrow[c]);

@@ -8,6 +8,8 @@
 //                   distributed shared memory once per step.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -136,7 +138,7 @@ __device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_
     }
 }
 
-template <int NB, int KS>
+template <int NB, int KS, int NACC>
 __global__ void __cluster_dims__(GRU_CS, 1, 1) __launch_bounds__(GRU_KQ * 3 * KS, 1)
 gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, const float* __restrict__ bhh_f,
                    const float* __restrict__ whh_b, const float* __restrict__ bhh_b, void* out, int o_dtype,
@@ -218,22 +220,30 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f
         }
         const float* h = hb + cur * NB * Hh;
         {
-            float acc[NB][4];            // four independent chains per chain-of-videos: shortens the FMA dependency chain
+            float acc[NB][NACC];         // NACC independent chains per video shorten the FMA dependency chain
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) acc[nb][a] = 0.f;
             const float* hk = h + kq * KS;
 #pragma unroll
             for (int k = 0; k < KS; k += 4) {
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
                     const float4 h4 = *reinterpret_cast<const float4*>(&hk[nb * Hh + k]);
-                    acc[nb][0] = fmaf(w[k], h4.x, acc[nb][0]); acc[nb][1] = fmaf(w[k + 1], h4.y, acc[nb][1]);
-                    acc[nb][2] = fmaf(w[k + 2], h4.z, acc[nb][2]); acc[nb][3] = fmaf(w[k + 3], h4.w, acc[nb][3]);
+                    acc[nb][0 % NACC] = fmaf(w[k], h4.x, acc[nb][0 % NACC]);
+                    acc[nb][1 % NACC] = fmaf(w[k + 1], h4.y, acc[nb][1 % NACC]);
+                    acc[nb][2 % NACC] = fmaf(w[k + 2], h4.z, acc[nb][2 % NACC]);
+                    acc[nb][3 % NACC] = fmaf(w[k + 3], h4.w, acc[nb][3 % NACC]);
                 }
             }
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb)
-                part[(nb * GRU_KQ + kq) * R + j] = (acc[nb][0] + acc[nb][1]) + (acc[nb][2] + acc[nb][3]);
+            for (int nb = 0; nb < NB; ++nb) {
+                float t = acc[nb][0];
+#pragma unroll
+                for (int a = 1; a < NACC; ++a) t += acc[nb][a];
+                part[(nb * GRU_KQ + kq) * R + j] = t;
+            }
         }
         __syncthreads();
         if (gate) {
@@ -307,9 +317,12 @@ extern "C" int factk_gru_bidir(const float* gi, const float* w_hh_f, const float
     const int KS = Hh / GRU_KQ;
     const int threads = GRU_KQ * 3 * KS;
     cudaStream_t st = (cudaStream_t)stream;
+    static const int nacc = [] { const char* e = getenv("FACTK_GRU_NACC"); return e ? atoi(e) : 1; }();
 #define LAUNCH(N_, K_)                                                                                                  \
-    gru_cluster_kernel<N_, K_><<<groups * 2 * GRU_CS, threads, 0, st>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, \
-                                                                        ldo, relu, B, slot, nseg)
+    do {                                                                                                                \
+        if (nacc == 1) gru_cluster_kernel<N_, K_, 1><<<groups * 2 * GRU_CS, threads, 0, st>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg); \
+        else gru_cluster_kernel<N_, K_, 2><<<groups * 2 * GRU_CS, threads, 0, st>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg); \
+    } while (0)
 #define LAUNCH_K(N_)                                                \
     do {                                                            \
         if (KS == 8) LAUNCH(N_, 8);                                 \
