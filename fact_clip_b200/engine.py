@@ -74,7 +74,7 @@ class FactEngine:
                 assert kw.get('alpha', 1.0) == 1.0
                 d = pos.shape[-1]
                 pre = self.derived(('posW', W.data_ptr(), tuple(W.shape), tuple(W.stride())), lambda: pos @ W[:, :d].t())
-            return ops.gemm([S(x, W)], N, out, tc=True, pre=pre, **kw)
+            return ops.gemm([S(x, W)], N, out, tc=True, pre=pre, tag='tok_tc', **kw)
         return ops.gemm([S(x, W, pos=pos)], N, out, **kw)
 
     def mm(self, srcs, N, out, tf32=False, **kw):
@@ -131,7 +131,7 @@ class FactEngine:
         other = lambda t: fb if t is fa else fa
         if in_map:
             w = pfx + ('conv_1x1_in' if m2 else 'conv_1x1')
-            self.mm([S(x, self.taps(w + '.weight')[0])], F, fa, tf32=True, len=ln, bias=self.p(w + '.bias'))
+            self.mm([S(x, self.taps(w + '.weight')[0])], F, fa, tf32=True, len=ln, bias=self.p(w + '.bias'), tag='in_proj')
             cur, nxt = fa, fb
         else:
             cur, nxt = x, fa
@@ -154,7 +154,7 @@ class FactEngine:
                         bias=self.p(f'{pfx}conv_fusion.{i}.bias'), relu=True, res=cur)
             cur, nxt = nxt, other(nxt)
         out = self.buf('frame_' + tag, (B, slot, H), self.act)
-        self.mm([S(cur, self.taps(pfx + 'conv_out.weight')[0])], H, out, len=ln, bias=self.p(pfx + 'conv_out.bias'))
+        self.mm([S(cur, self.taps(pfx + 'conv_out.weight')[0])], H, out, len=ln, bias=self.p(pfx + 'conv_out.bias'), tag='conv_out')
         clogit = self.buf('fclogit_' + tag, (B, slot, C))
         pred = self.buf('fpred_' + tag, (B, slot), torch.int32)
         ops.softmax_splice(out, C, clogit, pred, len=ln)
@@ -208,7 +208,7 @@ class FactEngine:
             self.lin(tgt, wq, A, cq, pos=qpos, bias=cb[:A])
             if fpos is None:
                 wkv = self.derived(('wkv', c), lambda: torch.cat([wk, wv], 0))
-                self.mm([S(frame, wkv)], 2 * A, kv, len=self.len, bias=cb[A:])
+                self.mm([S(frame, wkv)], 2 * A, kv, len=self.len, bias=cb[A:], tag='sca_kv')
             else:
                 ops.gemm([S(frame, wk, pos=fpos)], A, kv[:, :, :A], len=self.len, bias=cb[A:2 * A])
                 self.mm([S(frame, wv)], A, kv[:, :, A:], len=self.len, bias=cb[2 * A:])
@@ -260,7 +260,7 @@ class FactEngine:
         cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * yq . bk
         self.lin(yq, self.p(pfx + 'X_K.bias')[None, :], 1, cb, alpha=alpha)
         logit = self.buf('f2a_logit_' + tag, (B, slot, Mp))
-        ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc)
+        ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc, tag='x2y_rows')
         attn = self.buf('f2a_attn_' + tag, (B, slot, Mp)) if want_attn else None
         xbar = self.buf('x2y_xbar', (B, M, H))
         ws = self.buf('col_ws', (ops.col_softmax_ws(B, slot, M, H),))
@@ -287,7 +287,7 @@ class FactEngine:
         cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * xk . bq
         self.lin(xk, self.p(pfx + 'Y_Q.bias')[None, :], 1, cb, alpha=alpha)
         logit = self.buf('a2f_logit_' + tag, (B, slot, Mp))
-        ops.gemm([S(rows, kt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc)
+        ops.gemm([S(rows, kt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc, tag='x2y_rows')
         attn = self.buf('a2f_attn_' + tag, (B, slot, Mp))
         Kp = _round_up(M, 64)
         attn16 = self.buf('a2f_attn16', (B, slot, Kp), torch.bfloat16) if tc else None
@@ -299,7 +299,7 @@ class FactEngine:
         if tc:
             vt = self.zbuf('x2y_vt16', (B, F, Kp), torch.bfloat16)          # vt[b,f,m] = sum_h Wa[f,h] xv[b,m,h]; pad cols stay 0
             ops.gemm([S(W[None, :, H:], xv)], M, vt)
-            ops.gemm([S(rows, self.wbf(W[:, :H])), S(attn16, vt)], F, out, len=rlen, bias=self.p(pfx + 'Y_W.bias'), tc=True)
+            ops.gemm([S(rows, self.wbf(W[:, :H])), S(attn16, vt)], F, out, len=rlen, bias=self.p(pfx + 'Y_W.bias'), tc=True, tag='x2y_rows')
         else:
             vt = self.buf('x2y_vt', (B, F, Mp))
             ops.gemm([S(W[None, :, H:], xv)], M, vt)
@@ -339,12 +339,12 @@ class FactEngine:
         g = pfx + 'seg_update.'
         gi = self.buf('gru_gi', (B, slot, 6 * Hh))
         self.mm([S(seg0, self.cat(g + 'weight_ih_l0', g + 'weight_ih_l0_reverse'))], 6 * Hh, gi, len=nseg,
-                bias=self.cat(g + 'bias_ih_l0', g + 'bias_ih_l0_reverse'))
+                bias=self.cat(g + 'bias_ih_l0', g + 'bias_ih_l0_reverse'), tag='gru_in')
         seg1 = self.buf('seg1', (B, slot, H), self.act)
         ops.gru_bidir(gi, self.p(g + 'weight_hh_l0'), self.p(g + 'bias_hh_l0'), self.p(g + 'weight_hh_l0_reverse'),
                       self.p(g + 'bias_hh_l0_reverse'), seg1, nseg, relu=True)
         seg2 = self.buf('seg2', (B, slot, H), self.act)
-        self.mm([S(seg1, self.p(pfx + 'seg_combine.weight'))], H, seg2, len=nseg, bias=self.p(pfx + 'seg_combine.bias'))
+        self.mm([S(seg1, self.p(pfx + 'seg_combine.weight'))], H, seg2, len=nseg, bias=self.p(pfx + 'seg_combine.bias'), tag='seg_combine')
         st['seg_clogit'] = self.buf('seg_clogit_' + tag, (B, slot, C))
         ops.softmax_splice(seg2, C, st['seg_clogit'], None, len=nseg)
         pidx = seg_center if self.frame_pos is not None else None
@@ -356,9 +356,9 @@ class FactEngine:
         fr = self.zbuf('sf_out', (B, slot, F), self.act)
         # cat[s2f, frame] W^T = (seg3 W1^T)[seg_label] + frame W2^T: the gather moves to a segment-level product
         s2f = self.buf('sf_pre', (B, slot, F))
-        self.mm([S(seg3, W[:, :F])], F, s2f, len=nseg)
+        self.mm([S(seg3, W[:, :F])], F, s2f, len=nseg, tag='sf_merge')
         self.mm([S(frame, W[:, F:])], F, fr, len=self.len, bias=self.p(pfx + 'sf_merge.0.bias'), relu=True,
-                pre=s2f, pre_idx=seg_label)
+                pre=s2f, pre_idx=seg_label, tag='sf_merge')
         frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, fr, False, tag)
         return frame, action
 
@@ -451,16 +451,16 @@ class FactEngine:
             P = self.p('frame_projection.projection.0.weight').shape[0]
             h1 = self.buf('clip_h1', (B, slot, P), self.act)
             w0 = self.derived(('clip_w0pad',), lambda: torch.nn.functional.pad(self.p('frame_projection.projection.0.weight'), (0, C)))
-            self.mm([S(frame, w0)], P, h1, len=ln,
+            self.mm([S(frame, w0)], P, h1, len=ln, tag='clip',
                     bias=self.p('frame_projection.projection.0.bias'))
             ops.layernorm(h1, self.p('frame_projection.projection.1.weight'), self.p('frame_projection.projection.1.bias'),
                           h1, relu=True, len=ln)
             emb = self.buf('clip_emb', (B, slot, 512))
-            self.mm([S(h1, self.p('frame_projection.projection.4.weight'))], 512, emb, len=ln,
+            self.mm([S(h1, self.p('frame_projection.projection.4.weight'))], 512, emb, len=ln, tag='clip',
                     bias=self.p('frame_projection.projection.4.bias'))
             ops.l2norm(emb, emb, len=ln)
             flogit = self.buf('clip_logit', (B, slot, C))
-            self.mm([S(emb, self.p('text_embeddings'))], C, flogit, tf32=True, len=ln, alpha=1.0 / hp['temp'])
+            self.mm([S(emb, self.p('text_embeddings'))], C, flogit, tf32=True, len=ln, alpha=1.0 / hp['temp'], tag='clip')
             out['projected_frame_embeddings'], out['clip_logit'] = emb, flogit
         else:
             flogit = last['frame_clogit']

@@ -162,7 +162,10 @@ def test_attn_rows(dtype, M, nh, dh, slot, lens):
         vv = kv[b, :T, E:].float().view(T, nh, dh).transpose(0, 1)
         ref = (torch.softmax(qq @ kk.transpose(1, 2) / math.sqrt(dh), -1) @ vv).transpose(0, 1).reshape(M, E)
         # bf16 keys/values take the HMMA kernel: probabilities are rounded to bf16 before the PV product
-        close(o[b], ref, rtol=2e-4, atol=2e-5) if dtype == torch.float32 else close(o[b], ref, rtol=2e-2, atol=3e-4)
+        if dtype == torch.float32:
+            close(o[b], ref, rtol=2e-4, atol=2e-5)
+        else:
+            assert rel_l2(o[b], ref) < 5e-3
 
 
 @pytest.mark.parametrize('M,E,slot,lens', [(75, 512, 1280, [1280, 600, 1]), (12, 64, 128, [100, 128])])
