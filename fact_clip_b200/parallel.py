@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing for inference sweeps: videos are independent, so each rank owns a
+contiguous shard and there is NO data-path collective.  torch.distributed (NCCL on GPUs, gloo in CPU tests) is
+used only to gather the variable-length per-video predictions on rank 0 for the metrics pass
+(fact_clip/utils/evaluate.py:96,230 in the reference needs whole per-video arrays) and for timing barriers."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced shard [lo, hi) of n_items for `rank` (first n_items % world ranks get one extra)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_by_length(lengths, world):
+    """Assign videos to ranks so that frames per rank are balanced (longest-first greedy); returns a list of
+    index lists, each sorted by length so that batches have similar slot sizes."""
+    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
+    load, out = [0] * world, [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += lengths[i]
+    return [sorted(ix, key=lambda i: (lengths[i], i)) for ix in out]
+
+
+def gather_predictions(local_ids, local_preds, group=None, dst=0):
+    """Gather {video id -> int64 prediction array} on rank `dst`.  Uses padded tensor collectives (int32 payload)
+    rather than pickling.  Returns the merged dict on dst, None elsewhere."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return {i: np.asarray(p, dtype=np.int64) for i, p in zip(local_ids, local_preds)}
+    backend = dist.get_backend(group)
+    dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
+    lens = torch.tensor([len(p) for p in local_preds], dtype=torch.int64)
+    meta = torch.tensor([len(local_ids), int(lens.sum()) if len(lens) else 0], dtype=torch.int64, device=dev)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    max_n, max_tot = max(int(m[0]) for m in metas), max(int(m[1]) for m in metas)
+    head = torch.full((2, max(max_n, 1)), -1, dtype=torch.int64, device=dev)
+    if len(local_ids):
+        head[0, :len(local_ids)] = torch.tensor(list(local_ids), dtype=torch.int64)
+        head[1, :len(local_ids)] = lens
+    body = torch.zeros(max(max_tot, 1), dtype=torch.int32, device=dev)
+    if len(local_preds):
+        flat = np.concatenate([np.asarray(p) for p in local_preds]).astype(np.int32)
+        body[:len(flat)] = torch.from_numpy(flat).to(dev)
+    heads = [torch.zeros_like(head) for _ in range(world)]
+    bodies = [torch.zeros_like(body) for _ in range(world)]
+    dist.all_gather(heads, head, group=group)
+    dist.all_gather(bodies, body, group=group)
+    if rank != dst:
+        return None
+    out = {}
+    for h, b in zip(heads, bodies):
+        h, b, off = h.cpu(), b.cpu().numpy(), 0
+        for vid, n in zip(h[0].tolist(), h[1].tolist()):
+            if vid < 0:
+                continue
+            out[vid] = b[off:off + n].astype(np.int64)
+            off += n
+    return out
