@@ -337,7 +337,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 3-D map {inner K, rows, batch} with a [128 B x box_rows x 1] box, 128B swizzle, zero OOB fill.  Cached.
-static bool get_map(CUtensorMap* out, const void* ptr, int es, uint64_t k, uint64_t rows, uint64_t batch, uint64_t row_stride_el,
+bool tc_get_map(CUtensorMap* out, const void* ptr, int es, uint64_t k, uint64_t rows, uint64_t batch, uint64_t row_stride_el,
                     uint64_t batch_stride_el, uint32_t box_rows) {
     struct Key { const void* p; uint64_t a[7]; };
     Key key{ptr, {(uint64_t)es, k, rows, batch, row_stride_el, batch_stride_el, box_rows}};
@@ -430,9 +430,9 @@ extern "C" int factk_gemm_tc(const factk_gemm_t* g, void* stream) {
     memset(&p, 0, sizeof(p));
     for (int s = 0; s < g->nsrc; ++s) {
         const factk_src_t& x = g->src[s];
-        if (!get_map(&p.amap[s], x.A, es, x.K, x.a_slot, g->B, x.lda, (uint64_t)x.a_slot * x.lda, 128)) return FACTK_ERR_CUDA;
+        if (!tc_get_map(&p.amap[s], x.A, es, x.K, x.a_slot, g->B, x.lda, (uint64_t)x.a_slot * x.lda, 128)) return FACTK_ERR_CUDA;
         const bool batched = x.w_bstride != 0;
-        if (!get_map(&p.wmap[s], x.W, es, x.K, g->N, batched ? g->B : 1, x.ldw, batched ? (uint64_t)x.w_bstride : (uint64_t)g->N * x.ldw, BN))
+        if (!tc_get_map(&p.wmap[s], x.W, es, x.K, g->N, batched ? g->B : 1, x.ldw, batched ? (uint64_t)x.w_bstride : (uint64_t)g->N * x.ldw, BN))
             return FACTK_ERR_CUDA;
         p.kchunks[s] = x.K * es / 128;
         p.row_off[s] = x.row_off;

@@ -6,6 +6,11 @@
 #include <stdint.h>
 
 namespace factk {
+
+// Cached 3-D tensor map {inner K, rows, batch}, box [128 B x box_rows x 1], 128B swizzle, zero OOB fill (gemm_tc.cu).
+bool tc_get_map(CUtensorMap* out, const void* ptr, int es, uint64_t k, uint64_t rows, uint64_t batch, uint64_t row_stride_el,
+                uint64_t batch_stride_el, uint32_t box_rows);
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -31,6 +31,7 @@ class FactEngine:
         self.act = torch.bfloat16 if mode == 'bf16' else torch.float32
         self._bufs, self._zbufs, self._len_sig = {}, {}, None
         self.use_tc = True
+        self.use_fused_tcn = True
         self._submits, self._copy_stream, self._slot_free = 0, None, [None, None]
         self._wcache, self._wsig = {}, None
 
@@ -135,8 +136,15 @@ class FactEngine:
             cur, nxt = fa, fb
         else:
             cur, nxt = x, fa
+        fused = (not m2 and self.mode == 'bf16' and self.use_tc and self.use_fused_tcn and ops.tcn_layer_supported(F)
+                 and cur.dtype == torch.bfloat16 and cur.is_contiguous())
         for i in range(Lr):
-            if not m2:
+            if fused:
+                # conv3 + ReLU + 1x1 + residual in one tcgen05 kernel; the ReLU tile never leaves the SM (tcn_fused.cu)
+                q = f'{pfx}layers.{i}.'
+                ops.tcn_layer(cur, nxt, self.wbf(self.taps(q + 'conv_dilated.weight')), self.p(q + 'conv_dilated.bias'),
+                              self.wbf(self.taps(q + 'conv_1x1.weight')[0]), self.p(q + 'conv_1x1.bias'), 2 ** i, len=ln)
+            elif not m2:
                 q = f'{pfx}layers.{i}.'
                 w3, d = self.taps(q + 'conv_dilated.weight'), 2 ** i
                 tmp = self.buf('f_tmp', (B, slot, F), self.act)

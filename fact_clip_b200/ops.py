@@ -89,6 +89,20 @@ def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None, tag
     COUNTERS['launches'] += 1
 
 
+def tcn_layer_supported(F):
+    return bool(L.load().factk_tcn_layer_supported(int(F)))
+
+
+def tcn_layer(x, y, w3, b3, w1, b1, dilation, len=None, cta_group=2):
+    """Fused dilated residual layer (conv3 + ReLU + 1x1 + residual) on bf16 rows [B, slot, F]."""
+    B, slot, F = x.shape
+    assert x.dtype == y.dtype == w3.dtype == w1.dtype == torch.bfloat16 and x.is_contiguous() and y.is_contiguous()
+    assert w3.is_contiguous() and w1.is_contiguous() and tuple(w3.shape) == (3, F, F) and tuple(w1.shape) == (F, F)
+    COUNTERS['launches'] += 1
+    _call('factk_tcn_layer', 'tcn_layer', x.data_ptr(), y.data_ptr(), w3.data_ptr(), b3.data_ptr(), w1.data_ptr(),
+          b1.data_ptr(), B, slot, F, int(dilation), L.ptr(len), int(cta_group), L.stream())
+
+
 len_ = len   # the builtin (``len`` is also a keyword argument name in this module)
 
 

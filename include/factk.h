@@ -97,6 +97,20 @@ int factk_gemm_tc(const factk_gemm_t* g, void* stream);
 /* 1 if factk_gemm_tc accepts this descriptor, 0 otherwise (no launch). */
 int factk_gemm_tc_supported(const factk_gemm_t* g);
 
+/* Fused DilatedResidualLayer (models/basic.py:154-171; MSTCN.forward :216-217), eval mode:
+ *   y[b,t,:] = x[b,t,:] + W1 relu(sum_k W3[k] x[b, t+(k-1)*dilation, :] + b3) + b1
+ * in ONE persistent tcgen05 kernel (conv3 -> ReLU tile kept in shared memory -> 1x1 -> residual), nothing but x
+ * in and y out touches HBM.  x, y: bf16 [B][slot][F] contiguous, y != x, rows of x in [len[b], slot) must be zero
+ * (convolution zero padding; rows of y >= len[b] are not written); w3: bf16 [3][F][F] = Conv1d weight
+ * (F,F,3) permuted to (tap, out, in); w1: bf16 [F][F]; b3, b1: fp32 [F].  F in {128, 256}
+ * (factk_tcn_layer_supported).  cta_group: 2 = tcgen05 cta_group::2 CTA pairs (default), 1 = single CTA. */
+int factk_tcn_layer_supported(int F);
+int factk_tcn_layer(const void* x, void* y, const void* w3, const float* b3, const void* w1, const float* b1,
+                    int B, int slot, int F, int dilation, const int32_t* len, int cta_group, void* stream);
+/* Same, additionally recording a clock64 timeline of CTA 0 into dbg[64][16] (development aid; dbg may be NULL). */
+int factk_tcn_layer_dbg(const void* x, void* y, const void* w3, const float* b3, const void* w1, const float* b1,
+                        int B, int slot, int F, int dilation, const int32_t* len, int cta_group, long long* dbg, void* stream);
+
 /* Block.process_feature (blocks.py:195-202) in place on rows [B][slot][ld] of width H: the last C
  * channels are logits -> clogit_out fp32 [B][slot][C]; they are overwritten by softmax(logits).
  * pred_out (optional, int32 [B][slot]) = argmax of the probabilities, first index on ties
