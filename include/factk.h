@@ -179,6 +179,19 @@ int factk_gru_bidir(const float* gi, const float* w_hh_f, const float* b_hh_f,
                     void* out, int o_dtype, int ldo, int relu,
                     int B, int slot, const int32_t* nseg, void* stream);
 
+/* Same recurrence on the tensor cores for the bf16 compute mode: 8 videos of a direction advance together as one
+ * [768 x 256] x [256 x 8] mma.sync product per step on an 8-CTA cluster (W_hh as bf16 A fragments in registers, hidden
+ * state exchanged as bf16 through distributed shared memory, fp32 state / gates with MUFU.TANH).  Hh must be 256. */
+int factk_gru_bidir_mma(const float* gi, const float* w_hh_f, const float* b_hh_f,
+                        const float* w_hh_b, const float* b_hh_b, int Hh,
+                        void* out, int o_dtype, int ldo, int relu,
+                        int B, int slot, const int32_t* nseg, void* stream);
+/* Same, recording a clock64 timeline of CTA 0 into dbg[64][8] (development aid; dbg may be NULL). */
+int factk_gru_bidir_mma_dbg(const float* gi, const float* w_hh_f, const float* b_hh_f,
+                            const float* w_hh_b, const float* b_hh_b, int Hh,
+                            void* out, int o_dtype, int ldo, int relu,
+                            int B, int slot, const int32_t* nseg, long long* dbg, void* stream);
+
 /* out[b,t,:E] = in[b, idx[b,t], :E] fp32 (attn_seg2frame, basic.py:645-651). */
 int factk_gather_rows(const float* in, int ldi, int in_slot, const int32_t* idx, float* out, int ldo,
                       int B, int slot, const int32_t* len, int E, void* stream);

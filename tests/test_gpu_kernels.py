@@ -237,6 +237,36 @@ def test_gru_bidir(Hh, nsegs):
         assert bool((out[b, Sg:] == 0).all())
 
 
+@pytest.mark.parametrize('nsegs', [[300, 17], [5, 1, 64, 33, 200, 7, 90, 2, 11, 384]])
+def test_gru_bidir_mma(nsegs):
+    """Tensor-core GRU (bf16 W_hh and exchanged state, MUFU.TANH gates) vs the fp32 recurrence: bf16-level agreement."""
+    Hh = 256
+    B, slot, H = len(nsegs), 384, 2 * Hh
+    gru = torch.nn.GRU(H, Hh, 1, bidirectional=True)
+    sd = {'g.' + k: v.detach() for k, v in gru.state_dict().items()}
+    x = rnd(B, slot, H, seed=31)
+    wih = torch.cat([sd['g.weight_ih_l0'], sd['g.weight_ih_l0_reverse']])
+    bih = torch.cat([sd['g.bias_ih_l0'], sd['g.bias_ih_l0_reverse']])
+    gi = (x @ wih.t() + bih).to(DEV)
+    ns = torch.tensor(nsegs, dtype=torch.int32, device=DEV)
+    args = (gi, sd['g.weight_hh_l0'].to(DEV), sd['g.bias_hh_l0'].to(DEV), sd['g.weight_hh_l0_reverse'].to(DEV),
+            sd['g.bias_hh_l0_reverse'].to(DEV))
+    out = torch.zeros(B, slot, H, device=DEV)
+    ops.gru_bidir(*args, out, ns, relu=False, mma=True)
+    out16 = torch.zeros(B, slot, H, device=DEV, dtype=torch.bfloat16)
+    ops.gru_bidir(*args, out16, ns, relu=True, mma=True)
+    for b, Sg in enumerate(nsegs):
+        ref = O.gru_bidir_fast(sd, 'g.', x[b, :Sg])
+        err = float((out[b, :Sg].cpu() - ref).abs().max())
+        assert err < 1e-2, (b, Sg, err)
+        assert float((out[b, :Sg].cpu() - ref).norm() / ref.norm()) < 5e-3
+        close(out16[b, :Sg].float(), torch.relu(ref), rtol=1e-2, atol=1e-2)
+        assert bool((out[b, Sg:] == 0).all())
+    out2 = torch.zeros(B, slot, H, device=DEV)
+    ops.gru_bidir(*args, out2, ns, relu=False, mma=True)
+    assert torch.equal(out, out2)
+
+
 # ------------------------------------------------------------------------------------------ eval
 def test_fuse_eval_known_answers():
     cases = torch.load(os.path.join(GOLDEN, 'eval_cases.pt'), weights_only=False)
