@@ -123,7 +123,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
-    ap.add_argument('--videos', type=int, default=16, help='videos per GPU per step')
+    ap.add_argument('--videos', type=int, default=64, help='videos per GPU per step')
     ap.add_argument('--mode', default='bf16')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager kernel launches instead of one CUDA graph per batch')

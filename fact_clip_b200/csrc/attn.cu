@@ -442,6 +442,99 @@ __global__ void __launch_bounds__(256) col_apply_partial_kernel(const float* __r
     }
 }
 
+
+// Tensor-core version of col_apply_partial_kernel for bf16 rows: part[b][split][m][e] = sum_{t in split} p[t,m] X[t,e] as
+// mma.sync m16n8k16 (M = tokens, N = channels, K = rows of the split).  One CTA = 80 tokens x 256 channels x one split;
+// the probabilities are formed per 64-row stage as bf16 in shared memory (token-major, the A operand), the rows tile is
+// staged as is (row-major [t][e], read through ldmatrix.trans as the B operand); fp32 accumulators in registers.
+constexpr int CAM_MT = 5, CAM_TOK = CAM_MT * 16, CAM_E = 256, CAM_TR = 64;
+constexpr int CAM_XS = CAM_E * 2 + 16;      // bytes per staged row (padded: conflict-free ldmatrix)
+constexpr int CAM_PS = CAM_TR * 2 + 16;     // bytes per token row of the probability tile
+__global__ void __launch_bounds__(256) col_apply_mma_kernel(const float* __restrict__ L, int ldl, const float* __restrict__ stats,
+                                                            const __nv_bfloat16* __restrict__ X, int ldx, float* __restrict__ part,
+                                                            float* __restrict__ P, int ldp, int slot,
+                                                            const int32_t* __restrict__ len, int M, int E, int nsplit, int etiles) {
+    __shared__ __align__(16) uint8_t Xs[CAM_TR * CAM_XS];
+    __shared__ __align__(16) uint8_t Pt[CAM_TOK * CAM_PS];
+    const int sp = blockIdx.x, b = blockIdx.z;
+    const int mc = blockIdx.y / etiles, et = blockIdx.y % etiles;
+    const int len_b = len ? min(len[b], slot) : slot;
+    const int r0 = sp * SPLIT_ROWS;
+    if (r0 >= len_b) return;
+    const int r1 = min(r0 + SPLIT_ROWS, len_b);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int m0 = mc * CAM_TOK, e0 = et * CAM_E;
+    float acc[CAM_MT][4][4];
+#pragma unroll
+    for (int i = 0; i < CAM_MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+    const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(Xs), pt_u32 = (uint32_t)__cvta_generic_to_shared(Pt);
+    // ldmatrix lane addresses: A (tokens x rows) from Pt, B (rows x channels, transposed on load) from Xs
+    const uint32_t a_lane = pt_u32 + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * CAM_PS + (uint32_t)(lane >> 4) * 16u;
+    const uint32_t b_lane = xs_u32 + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * CAM_XS + (uint32_t)(w * 32 + (lane >> 4) * 8) * 2u;
+
+    for (int t0 = r0; t0 < r1; t0 += CAM_TR) {
+        const int nr = min(CAM_TR, r1 - t0);
+        __syncthreads();
+        // probabilities of this stage, bf16, token-major
+        for (int i = tid; i < CAM_TR * CAM_TOK; i += 256) {
+            const int r = i / CAM_TOK, mm = i % CAM_TOK;
+            float p = 0.f;
+            if (r < nr && m0 + mm < M) {
+                const size_t row = (size_t)b * slot + t0 + r;
+                const float* st = stats + ((size_t)b * M + m0 + mm) * 2;
+                p = __expf(L[row * ldl + m0 + mm] - st[0]) * st[1];
+                if (P != nullptr && et == 0) P[row * ldp + m0 + mm] = p;
+            }
+            *reinterpret_cast<__nv_bfloat16*>(Pt + mm * CAM_PS + r * 2) = __float2bfloat16_rn(p);
+        }
+        // rows tile: 64 rows x 256 channels, 16-byte chunks; rows past the split end are zero (they may hold anything)
+        for (int i = tid; i < CAM_TR * (CAM_E / 8); i += 256) {
+            const int r = i / (CAM_E / 8), c = i % (CAM_E / 8);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (r < nr && e0 + c * 8 < E) v = *reinterpret_cast<const uint4*>(X + ((size_t)b * slot + t0 + r) * ldx + e0 + c * 8);
+            *reinterpret_cast<uint4*>(Xs + r * CAM_XS + c * 16) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < CAM_TR / 16; ++ks) {
+            uint32_t bf[4][2];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(bf[2 * jj][0]), "=r"(bf[2 * jj][1]), "=r"(bf[2 * jj + 1][0]), "=r"(bf[2 * jj + 1][1])
+                             : "r"(b_lane + (uint32_t)(ks * 16) * CAM_XS + (uint32_t)jj * 32u));
+#pragma unroll
+            for (int i = 0; i < CAM_MT; ++i) {
+                uint32_t a[4];
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                             : "r"(a_lane + (uint32_t)(i * 16) * CAM_PS + (uint32_t)ks * 32u));
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(acc[i][j][0]), "+f"(acc[i][j][1]), "+f"(acc[i][j][2]), "+f"(acc[i][j][3])
+                                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bf[j][0]), "r"(bf[j][1]));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CAM_MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = e0 + w * 32 + j * 8 + (lane & 3) * 2;
+            if (e >= E) continue;
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int m = m0 + i * 16 + (lane >> 2) + hrow * 8;
+                if (m < M)
+                    *reinterpret_cast<float2*>(part + (((size_t)b * nsplit + sp) * M + m) * E + e) =
+                        make_float2(acc[i][j][2 * hrow], acc[i][j][2 * hrow + 1]);
+            }
+        }
+}
+
 __global__ void col_apply_combine_kernel(const float* __restrict__ part, float* __restrict__ out, int ldo, int slot,
                                          const int32_t* __restrict__ len, int M, int E, int nsplit) {
     const int b = blockIdx.y;
@@ -549,9 +642,15 @@ extern "C" int factk_col_softmax_apply(const float* L, int ldl, const void* X, i
     cudaStream_t st = (cudaStream_t)stream;
     col_stats_partial_kernel<<<dim3(ns, B), 256, 0, st>>>(L, ldl, sp, slot, len, M, ns);
     col_stats_combine_kernel<<<B, 256, 0, st>>>(sp, stats, slot, len, M, ns);
-    const int etiles = (E + 127) / 128, mtiles = (M + 31) / 32;
-    col_apply_partial_kernel<<<dim3(ns, mtiles * etiles, B), 256, 0, st>>>(L, ldl, stats, X, x_dtype, ldx, part, P, ldp,
-                                                                           slot, len, M, E, ns, etiles);
+    if (x_dtype == FACTK_BF16 && (E % 8) == 0 && (ldx % 8) == 0 && aligned16(X)) {
+        const int etiles = (E + CAM_E - 1) / CAM_E, mchunks = (M + CAM_TOK - 1) / CAM_TOK;
+        col_apply_mma_kernel<<<dim3(ns, mchunks * etiles, B), 256, 0, st>>>(L, ldl, stats, reinterpret_cast<const __nv_bfloat16*>(X), ldx,
+                                                                           part, P, ldp, slot, len, M, E, ns, etiles);
+    } else {
+        const int etiles = (E + 127) / 128, mtiles = (M + 31) / 32;
+        col_apply_partial_kernel<<<dim3(ns, mtiles * etiles, B), 256, 0, st>>>(L, ldl, stats, X, x_dtype, ldx, part, P, ldp,
+                                                                               slot, len, M, E, ns, etiles);
+    }
     col_apply_combine_kernel<<<dim3((M * E + 255) / 256, B), 256, 0, st>>>(part, out, ldo, slot, len, M, E, ns);
     return check_launch("factk_col_softmax_apply");
 }

@@ -70,31 +70,100 @@ __global__ void __launch_bounds__(1024) tdu_segment_kernel(const int32_t* __rest
     }
 }
 
-__global__ void __launch_bounds__(128) segment_mean_kernel(const void* __restrict__ X, int x_dtype, int ldx, void* seg,
-                                                           int s_dtype, int lds, const int32_t* __restrict__ seg_start,
-                                                           const int32_t* __restrict__ seg_len,
-                                                           const int32_t* __restrict__ nseg, int slot, int E) {
-    const int s = blockIdx.x, b = blockIdx.y;
-    if (s >= nseg[b]) return;
+// Frame-parallel: one CTA owns the segments that START inside its chunk of SEGM_CHUNK frames (found through seg_label, two
+// dependent loads), so consecutive CTAs stream consecutive frames and every frame is read exactly once; a segment that
+// extends past the chunk is finished by the CTA that started it.  1024 threads = 8 row lanes x 128 channel threads: short
+// segments (<= 4 rows) are summed by lane 0 alone in row order; longer ones (random-init predictions produce videos that
+// are ONE 4096-frame segment) are split over the eight lanes with eight row loads in flight each and combined in fixed
+// lane order -- deterministic, no atomics.
+constexpr int SEGM_CHUNK = 32;
+constexpr int SEGM_LANES = 8;
+__global__ void __launch_bounds__(128 * SEGM_LANES) segment_mean_kernel(const void* __restrict__ X, int x_dtype, int ldx, void* seg,
+                                                                        int s_dtype, int lds, const int32_t* __restrict__ seg_label,
+                                                                        const int32_t* __restrict__ seg_start,
+                                                                        const int32_t* __restrict__ seg_len,
+                                                                        const int32_t* __restrict__ nseg, int slot, int E) {
+    __shared__ float4 red[SEGM_LANES][128];
+    const int b = blockIdx.y;
+    const int S = min(nseg[b], slot);
+    if (S <= 0) return;
     const size_t base = (size_t)b * slot;
-    const int st = seg_start[base + s], n = seg_len[base + s];
-    const float inv = 1.f / (float)n;
+    const int T = seg_start[base + S - 1] + seg_len[base + S - 1];
+    const int f0 = blockIdx.x * SEGM_CHUNK, f1 = f0 + SEGM_CHUNK;
+    if (f0 >= T) return;
+    const int l0 = seg_label[base + f0];
+    const int s_first = l0 + (seg_start[base + l0] != f0 ? 1 : 0);
+    int s_end = S;
+    if (f1 < T) {
+        const int l1 = seg_label[base + f1];
+        s_end = l1 + (seg_start[base + l1] != f1 ? 1 : 0);
+    }
+    const int cl = threadIdx.x & 127, rl = threadIdx.x >> 7;
     const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && ((ldx & 3) == 0) && ((E & 3) == 0) &&
                      ((reinterpret_cast<uintptr_t>(seg) & 15u) == 0) && ((lds & 3) == 0);
-    if (vec) {
-        for (int c = threadIdx.x * 4; c < E; c += blockDim.x * 4) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < n; ++r) {
-                const float4 v = ld_vec4(X, x_dtype, (base + st + r) * (size_t)ldx + c);
-                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    // (start, length) of the chunk's segments -> shared memory once: no dependent global loads inside the loops
+    __shared__ int s_st[SEGM_CHUNK], s_n[SEGM_CHUNK];
+    const int nsc = s_end - s_first;            // <= SEGM_CHUNK: every segment starts on a distinct frame of the chunk
+    if ((int)threadIdx.x < nsc) {
+        s_st[threadIdx.x] = seg_start[base + s_first + threadIdx.x];
+        s_n[threadIdx.x] = seg_len[base + s_first + threadIdx.x];
+    }
+    __syncthreads();
+    if (!vec) {
+        for (int i = rl; i < nsc; i += SEGM_LANES) {
+            const int st = s_st[i], n = s_n[i];
+            for (int c = cl; c < E; c += 128) {
+                float a = 0.f;
+                for (int r = 0; r < n; ++r) a += ld_elem(X, x_dtype, (base + st + r) * (size_t)ldx + c);
+                st_elem(seg, s_dtype, (base + s_first + i) * (size_t)lds + c, a / (float)n);
             }
-            st_vec4(seg, s_dtype, (base + s) * (size_t)lds + c, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
         }
-    } else {
-        for (int c = threadIdx.x; c < E; c += blockDim.x) {
-            float a = 0.f;
-            for (int r = 0; r < n; ++r) a += ld_elem(X, x_dtype, (base + st + r) * (size_t)ldx + c);
-            st_elem(seg, s_dtype, (base + s) * (size_t)lds + c, a * inv);
+        return;
+    }
+    // short segments (the common case): one row lane per segment, eight segments in flight per CTA, rows summed in order
+    for (int i = rl; i < nsc; i += SEGM_LANES) {
+        const int st = s_st[i], n = s_n[i];
+        if (n > 4) continue;
+        const float inv = 1.f / (float)n;
+        for (int c = cl * 4; c < E; c += 512) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = (j < n) ? ld_vec4(X, x_dtype, (base + st + j) * (size_t)ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 a = v[0];
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (j < n) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+            st_vec4(seg, s_dtype, (base + s_first + i) * (size_t)lds + c, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
+        }
+    }
+    // long segments: all row lanes cooperate on one segment (uniform control flow: the barriers are reached by every thread)
+    for (int i = 0; i < nsc; ++i) {
+        const int st = s_st[i], n = s_n[i];
+        if (n <= 4) continue;
+        const float inv = 1.f / (float)n;
+        for (int c0 = 0; c0 < E; c0 += 512) {
+            const int c = c0 + cl * 4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < E)
+                for (int r = rl; r < n; r += 8 * SEGM_LANES) {
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        v[j] = (r + j * SEGM_LANES < n) ? ld_vec4(X, x_dtype, (base + st + r + j * SEGM_LANES) * (size_t)ldx + c)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+                }
+            __syncthreads();
+            red[rl][cl] = a;
+            __syncthreads();
+            if (rl == 0 && c < E) {
+                float4 t = red[0][cl];
+#pragma unroll
+                for (int j = 1; j < SEGM_LANES; ++j) { t.x += red[j][cl].x; t.y += red[j][cl].y; t.z += red[j][cl].z; t.w += red[j][cl].w; }
+                st_vec4(seg, s_dtype, (base + s_first + i) * (size_t)lds + c, make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv));
+            }
         }
     }
 }
@@ -292,11 +361,11 @@ extern "C" int factk_tdu_segment(const int32_t* pred, int B, int slot, const int
 }
 
 extern "C" int factk_segment_mean(const void* X, int x_dtype, int ldx, void* seg, int s_dtype, int lds,
-                                  const int32_t* seg_start, const int32_t* seg_len, const int32_t* nseg, int B, int slot,
-                                  int E, void* stream) {
-    FACTK_REQUIRE(X && seg && seg_start && seg_len && nseg && B > 0 && slot > 0 && E > 0, "factk_segment_mean: bad args");
+                                  const int32_t* seg_label, const int32_t* seg_start, const int32_t* seg_len, const int32_t* nseg,
+                                  int B, int slot, int E, void* stream) {
+    FACTK_REQUIRE(X && seg && seg_label && seg_start && seg_len && nseg && B > 0 && slot > 0 && E > 0, "factk_segment_mean: bad args");
     FACTK_REQUIRE(B <= 65535, "factk_segment_mean: B too large");
-    segment_mean_kernel<<<dim3(slot, B), 128, 0, (cudaStream_t)stream>>>(X, x_dtype, ldx, seg, s_dtype, lds, seg_start,
+    segment_mean_kernel<<<dim3((slot + SEGM_CHUNK - 1) / SEGM_CHUNK, B), 128 * SEGM_LANES, 0, (cudaStream_t)stream>>>(X, x_dtype, ldx, seg, s_dtype, lds, seg_label, seg_start,
                                                                           seg_len, nseg, slot, E);
     return check_launch("factk_segment_mean");
 }

@@ -166,9 +166,10 @@ int factk_tdu_segment(const int32_t* pred, int B, int slot, const int32_t* len,
                       int32_t* nseg, void* stream);
 
 /* TemporalDownsampleUpsample.feature_frame2seg (basic.py:615-625): deterministic segment mean.
- * X rows of dtype [B][slot][ldx] -> seg fp32/bf16 [B][slot][lds], first nseg[b] rows. */
+ * X rows of dtype [B][slot][ldx] -> seg fp32/bf16 [B][slot][lds], first nseg[b] rows.  seg_label / seg_start / seg_len /
+ * nseg as written by factk_tdu_segment. */
 int factk_segment_mean(const void* X, int x_dtype, int ldx, void* seg, int s_dtype, int lds,
-                       const int32_t* seg_start, const int32_t* seg_len, const int32_t* nseg,
+                       const int32_t* seg_label, const int32_t* seg_start, const int32_t* seg_len, const int32_t* nseg,
                        int B, int slot, int E, void* stream);
 
 /* Bidirectional GRU recurrence (nn.GRU(H, H/2, 1, bidirectional=True), blocks.py:401,432) over the

@@ -183,6 +183,30 @@ def test_col_softmax_apply(M, E, slot, lens):
         close(out[b], p.t() @ x[b, :T], rtol=2e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize('M,E,slot,lens', [(75, 512, 1280, [1280, 600, 1]), (300, 512, 640, [640, 77]), (12, 64, 128, [100, 128])])
+def test_col_softmax_apply_bf16_rows(M, E, slot, lens):
+    """bf16 rows take the mma.sync kernel (probabilities rounded to bf16 before the product); garbage past the end is ignored."""
+    B, Mp = len(lens), (M + 3) // 4 * 4
+    logit = rnd(B, slot, Mp, seed=25, scale=3.0)
+    x = rnd(B, slot, E, seed=26).to(torch.bfloat16)
+    xd = x.to(DEV).clone()
+    for b, T in enumerate(lens):
+        xd[b, T:] = float('nan')            # rows past len[b] may hold anything
+    out = torch.zeros(B, M, E, device=DEV)
+    attn = torch.zeros(B, slot, Mp, device=DEV)
+    ws = torch.empty(ops.col_softmax_ws(B, slot, M, E), device=DEV)
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    ops.col_softmax_apply(logit.to(DEV), xd, out, M, ws, attn=attn, len=ln)
+    out2 = torch.zeros(B, M, E, device=DEV)
+    ops.col_softmax_apply(logit.to(DEV), xd, out2, M, ws, len=ln)
+    assert torch.equal(out, out2)
+    for b, T in enumerate(lens):
+        p = torch.softmax(logit[b, :T, :M], dim=0)
+        close(attn[b, :T, :M], p, rtol=1e-4, atol=1e-6)
+        ref = p.t() @ x[b, :T].float()
+        assert rel_l2(out[b], ref) < 4e-3, rel_l2(out[b], ref)
+
+
 # ------------------------------------------------------------------------------------------ TDU
 def test_tdu_segment_and_mean():
     g = torch.Generator().manual_seed(27)
@@ -202,7 +226,7 @@ def test_tdu_segment_and_mean():
     ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
     ops.tdu_segment(pred.to(DEV), o['seg_label'], o['seg_start'], o['seg_len'], o['seg_center'], nseg, len=ln)
     seg = torch.zeros(B, slot, E, device=DEV)
-    ops.segment_mean(x.to(DEV), seg, o['seg_start'], o['seg_len'], nseg)
+    ops.segment_mean(x.to(DEV), seg, o['seg_label'], o['seg_start'], o['seg_len'], nseg)
     for b, T in enumerate(lens):
         lab, start, slen = O.run_length(pred[b, :T].numpy())
         S = len(slen)
@@ -215,7 +239,7 @@ def test_tdu_segment_and_mean():
         close(seg[b, :S], ref, rtol=1e-4, atol=1e-5)
     # determinism: bit-identical on a second run
     seg2 = torch.zeros(B, slot, E, device=DEV)
-    ops.segment_mean(x.to(DEV), seg2, o['seg_start'], o['seg_len'], nseg)
+    ops.segment_mean(x.to(DEV), seg2, o['seg_label'], o['seg_start'], o['seg_len'], nseg)
     assert torch.equal(seg, seg2)
 
 
