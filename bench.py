@@ -24,6 +24,11 @@ PRESET = 'havid_view0_lh_pt_holdout'
 METRIC, UNIT = 'frames/sec FACT_CLIP fwd (T=4096,2048-d)', 'frames/s'
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one tcn_layer_kernel launch (ncu --set full), keyed by videos per step;
+# algorithmic bytes at 64 videos: x in + y out = 2 * 64 * 4096 * 256 * 2 B = 268.4 MB
+TCN_DRAM_BYTES_PER_LAUNCH = {64: 227.36e6}
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -99,7 +104,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = 2
+    n = 8               # videos per step: a bounded sample of the workload (~1.5 s of CPU work per step on 16 cores)
     vals = []
     for _ in range(args.warmup + args.steps):
         v, dt = cpu_baseline(n, threads)
@@ -253,16 +258,18 @@ def main():
                 'd2h_bytes_per_step': B * T * 8 * world, 'ms_per_step': ms_e2e / args.steps},
         'roofline': {'bound': 'tensor', 'kernel': 'tcn_layer_kernel: fused dilated residual layer (conv3+ReLU+1x1+residual), 40 launches per forward',
                      'achieved': ach_tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': ach_tf / pk['tf_sust'],
-                     'traffic': None, 'peak_source': pk['src'] + ' (sustained bf16, kernel timed inside a long step)',
+                     'traffic': TCN_DRAM_BYTES_PER_LAUNCH.get(B), 'traffic_source': 'profiles/r1_tcn_layer_ncu_full.txt (dram read + write per launch, ncu --set full)',
+                     'peak_source': pk['src'] + ' (sustained bf16, kernel timed inside a long step)',
                      'ms_per_layer': t_layer_ms, 'share_of_step': tcn_ms / args.steps / (ms_eager / args.steps),
                      'timed_in': 'eager pass of the same steps (CUDA events around each launch); the headline loop replays one CUDA graph per step'},
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            fps, dt = cpu_baseline(2, threads)
+            n_cpu = 64      # ~10 s of CPU work on the box's 16 cores
+            fps, dt = cpu_baseline(n_cpu, threads)
             res['cpu_baseline'] = {'value': fps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                   'sample': f'2 videos x T={T} of the same workload, oracle port (torch CPU fp32), {dt:.1f} s'}
+                                   'sample': f'{n_cpu} videos x T={T} of the same workload, oracle port (torch CPU fp32), {dt:.1f} s'}
         print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
