@@ -18,6 +18,7 @@
 //     for this exchange, the flag-in-data stores at one remote-store latency.)
 //   * output stores and the prefetch of the next input gates are off the critical path.
 // Hidden size per direction is fixed at 256 (hid_dim 512: every shipped configuration, SURVEY.md note N3).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -56,14 +57,21 @@ __device__ __forceinline__ uint32_t gm_mapa(uint32_t local_addr, uint32_t rank) 
     return r;
 }
 
+constexpr int GM_PART = 4 * GM_NV * GM_PSTRIDE;                                  // floats per partial-sum buffer
+constexpr int gm_smem_bytes(int nc) { return nc * 2 * GM_HBUF + nc * 2 * GM_PART * 4; }   // dynamic shared memory
+
+// GM_NC = independent 8-video groups (chains) interleaved on one cluster.  With two chains, while the hidden state of chain A travels through distributed shared memory (~700 cycles), the
+// cluster computes the step of chain B (~600 cycles), so a pair of steps costs about what one step costs alone.
+template <int GM_NC>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, const float* __restrict__ bhh_f,
                const float* __restrict__ whh_b, const float* __restrict__ bhh_b, void* out, int o_dtype, int ldo, int relu,
                int B, int slot, const int32_t* __restrict__ nseg, long long* dbg) {
-    __shared__ __align__(16) uint8_t hb[2 * GM_HBUF];             // double-buffered hidden state, bf16 [video][unit]
-    // K-slice partial sums [step parity][warp][video][gate row]: double-buffered because a warp only waits for the two CTAs
-    // that own its K slice, so it may start step t+1 while other warps of this CTA still read the partials of step t
-    __shared__ __align__(16) float part[2 * 4 * GM_NV * GM_PSTRIDE];
+    extern __shared__ __align__(16) uint8_t gm_smem[];
+    uint8_t* hb = gm_smem;                                                       // [chain][parity] hidden state, bf16 [video][unit]
+    // K-slice partial sums [chain][step parity][warp][video][gate row]: parity-double-buffered because a warp only waits for
+    // the two CTAs that own its K slice, so it may start the next step while other warps still read the partials of this one
+    float* part = reinterpret_cast<float*>(gm_smem + GM_NC * 2 * GM_HBUF);
 
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -91,48 +99,72 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
             A[t6][s][3] = gm_pack(x3.x, x3.y);
         }
     }
-    // buffer 0 = h_0 = 0; buffer 1 = "empty" (filled by the exchange of step 0)
-    for (int i = tid; i < 2 * GM_HBUF / 4; i += GM_THREADS) reinterpret_cast<uint32_t*>(hb)[i] = i < GM_HBUF / 4 ? 0u : GM_EMPTY;
+    // per chain: buffer 0 = h_0 = 0; buffer 1 = "empty" (filled by the exchange of step 0)
+    for (int i = tid; i < GM_NC * 2 * GM_HBUF / 4; i += GM_THREADS)
+        reinterpret_cast<uint32_t*>(hb)[i] = ((i / (GM_HBUF / 4)) & 1) == 0 ? 0u : GM_EMPTY;
     const uint32_t hb_u32 = (uint32_t)__cvta_generic_to_shared(hb);
 
-    // ---- gate-phase role of this thread: video n, units (2 up, 2 up + 1) of this CTA
+    // ---- gate-phase role of this thread: video n of each chain, units (2 up, 2 up + 1) of this CTA
     const int n = tid & 7, up = tid >> 3;
-    const int vb = grp * GM_NV + n;
-    const int myS = vb < B ? min(nseg[vb], slot) : 0;
-    int maxS = 0;
-#pragma unroll
-    for (int i = 0; i < GM_NV; ++i) {
-        const int v = grp * GM_NV + i;
-        maxS = max(maxS, v < B ? min(nseg[v], slot) : 0);
-    }
     const int unit = rank * GM_U + 2 * up;
     const float2 b_r = *reinterpret_cast<const float2*>(bhh + unit);
     const float2 b_z = *reinterpret_cast<const float2*>(bhh + GM_HH + unit);
     const float2 b_n = *reinterpret_cast<const float2*>(bhh + 2 * GM_HH + unit);
-    float2 hprev = make_float2(0.f, 0.f);
     const size_t gstride = (size_t)6 * GM_HH;
-    float2 g_r = make_float2(0.f, 0.f), g_z = g_r, g_n = g_r;
-    // The input gates stream from HBM (B x S x 6 Hh floats): the loads for step t+1 are issued one step ahead, and the lines
-    // of step t+GM_PF are pulled into L2 so that those loads hit L2 (an HBM miss costs about one whole step).
-    constexpr int GM_PF = 8;
-    auto load_gi = [&](int t) {
-        if (t >= 0 && t < myS) {
-            const int s = dir ? myS - 1 - t : t;
-            const float* p = gi + ((size_t)vb * slot + s) * gstride + (size_t)dir * 3 * GM_HH + unit;
-            g_r = __ldg(reinterpret_cast<const float2*>(p));
-            g_z = __ldg(reinterpret_cast<const float2*>(p + GM_HH));
-            g_n = __ldg(reinterpret_cast<const float2*>(p + 2 * GM_HH));
+    int vb[GM_NC], myS[GM_NC], maxS[GM_NC];
+    float2 hprev[GM_NC], g_r[GM_NC], g_z[GM_NC], g_n[GM_NC];
+    int maxAll = 0;
+#pragma unroll
+    for (int c = 0; c < GM_NC; ++c) {
+        vb[c] = (grp * GM_NC + c) * GM_NV + n;
+        myS[c] = vb[c] < B ? min(nseg[vb[c]], slot) : 0;
+        maxS[c] = 0;
+        for (int i = 0; i < GM_NV; ++i) {
+            const int v = (grp * GM_NC + c) * GM_NV + i;
+            maxS[c] = max(maxS[c], v < B ? min(nseg[v], slot) : 0);
         }
-        if (t + GM_PF >= 0 && t + GM_PF < myS && (up & 3) == 0) {      // one prefetch per 32-byte sector
-            const int s = dir ? myS - 1 - (t + GM_PF) : t + GM_PF;
-            const float* p = gi + ((size_t)vb * slot + s) * gstride + (size_t)dir * 3 * GM_HH + unit;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + GM_HH));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 2 * GM_HH));
+        maxAll = max(maxAll, maxS[c]);
+        hprev[c] = g_r[c] = g_z[c] = g_n[c] = make_float2(0.f, 0.f);
+    }
+    // The input gates stream from HBM (B x S x 6 Hh floats): the loads for step t+1 are issued one step ahead, and the lines
+    // of step t+GM_PF are pulled into L2 so that those loads hit L2 (an HBM miss costs about one whole step).  Running
+    // pointers (one add per step) keep the address arithmetic off the step's critical path.
+    constexpr int GM_PF = 8;
+    const long long gstep = dir ? -(long long)gstride : (long long)gstride;     // segment order: forward / reverse
+    const long long ostep = dir ? -(long long)ldo : (long long)ldo;
+    const float* gp[GM_NC];          // input gates of step t (this thread's video / units)
+    long long oidx[GM_NC];           // output element index of step t
+#pragma unroll
+    for (int c = 0; c < GM_NC; ++c) {
+        const int s0 = dir ? myS[c] - 1 : 0;
+        gp[c] = gi + ((size_t)vb[c] * slot + (myS[c] > 0 ? s0 : 0)) * gstride + (size_t)dir * 3 * GM_HH + unit;
+        oidx[c] = ((long long)vb[c] * slot + (myS[c] > 0 ? s0 : 0)) * (long long)ldo + (long long)dir * GM_HH + unit;
+    }
+    // load the gates of step t into registers and prefetch those of step t + GM_PF; gp[c] must point at step t
+    auto load_gi = [&](int c, int t) {
+        if (t < myS[c]) {
+            g_r[c] = __ldg(reinterpret_cast<const float2*>(gp[c]));
+            g_z[c] = __ldg(reinterpret_cast<const float2*>(gp[c] + GM_HH));
+            g_n[c] = __ldg(reinterpret_cast<const float2*>(gp[c] + 2 * GM_HH));
+            if (t + GM_PF < myS[c] && (up & 3) == 0) {                     // one prefetch per 32-byte sector
+                const float* p = gp[c] + GM_PF * gstep;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + GM_HH));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 2 * GM_HH));
+            }
         }
     };
-    for (int t = -GM_PF; t < 0; ++t) load_gi(t);   // warm the prefetch window (the loads of t < 0 are skipped)
-    load_gi(0);
+#pragma unroll
+    for (int c = 0; c < GM_NC; ++c) {
+        if ((up & 3) == 0)
+            for (int t = 1; t < GM_PF && t < myS[c]; ++t) {                // warm the prefetch window
+                const float* p = gp[c] + t * gstep;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + GM_HH));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 2 * GM_HH));
+            }
+        load_gi(c, 0);
+    }
     // exchange: lanes (n, n+8, n+16, n+24) of a warp hold 8 consecutive units of video n; lane group j = lane / 8 stores that
     // 16-byte packet into the next-step buffer of CTAs 2j and 2j+1
     const uint32_t xoff = (uint32_t)n * GM_HSTRIDE + (uint32_t)(rank * GM_U + 8 * w) * 2u;
@@ -147,88 +179,92 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
     const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    for (int t = 0; t < maxS; ++t) {
+    for (int t = 0; t < maxAll; ++t) {
         const int cur = t & 1;
-        if (dbg_on && t < 64) dbg[t * 8 + 0] = clock64();
-        // ---- B fragments of this warp's K slice: spin until every word has landed, then mark the words empty again
-        uint32_t b[4][2];
-        {
-            const uint32_t ba = bsrc + (uint32_t)cur * GM_HBUF;
-            uint32_t spins = 0;
-            while (true) {
+#pragma unroll
+        for (int c = 0; c < GM_NC; ++c) {
+            if (t >= maxS[c]) continue;          // uniform over the cluster: this chain has finished everywhere
+            if (dbg_on && t < 64) dbg[t * 16 + c * 8 + 0] = clock64();
+            // ---- B fragments of this warp's K slice: spin until every word has landed, then mark the words empty again
+            uint32_t b[4][2];
+            {
+                const uint32_t ba = bsrc + (uint32_t)(c * 2 + cur) * GM_HBUF;
+                uint32_t spins = 0;
+                while (true) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(b[s][0]) : "r"(ba + 32u * s) : "memory");
+                        asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(b[s][1]) : "r"(ba + 32u * s + 16u) : "memory");
+                    }
+                    bool ok = true;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) ok = ok && (b[s][0] != GM_EMPTY) && (b[s][1] != GM_EMPTY);
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (++spins > (1u << 22)) __trap();   // protocol bug: fail loudly instead of hanging the GPU
+                }
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(b[s][0]) : "r"(ba + 32u * s) : "memory");
-                    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(b[s][1]) : "r"(ba + 32u * s + 16u) : "memory");
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ba + 32u * s), "r"(GM_EMPTY) : "memory");
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ba + 32u * s + 16u), "r"(GM_EMPTY) : "memory");
                 }
-                bool ok = true;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) ok = ok && (b[s][0] != GM_EMPTY) && (b[s][1] != GM_EMPTY);
-                if (__all_sync(0xffffffffu, ok)) break;
-                if (++spins > (1u << 22)) __trap();   // protocol bug: fail loudly instead of hanging the GPU
             }
+            if (dbg_on && t < 64) dbg[t * 16 + c * 8 + 1] = clock64();
+            // ---- [96 x 64] x [64 x 8] per warp on the tensor cores
+            float acc[6][4];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(ba + 32u * s), "r"(GM_EMPTY) : "memory");
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(ba + 32u * s + 16u), "r"(GM_EMPTY) : "memory");
+            for (int t6 = 0; t6 < 6; ++t6) acc[t6][0] = acc[t6][1] = acc[t6][2] = acc[t6][3] = 0.f;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int t6 = 0; t6 < 6; ++t6) gm_mma(acc[t6], A[t6][s], b[s][0], b[s][1]);
+            float* pwc = pw + (size_t)(c * 2 + cur) * GM_PART;
+#pragma unroll
+            for (int t6 = 0; t6 < 6; ++t6) {
+                pwc[16 * t6] = acc[t6][0];
+                pwc[GM_PSTRIDE + 16 * t6] = acc[t6][1];
+                pwc[16 * t6 + 8] = acc[t6][2];
+                pwc[GM_PSTRIDE + 16 * t6 + 8] = acc[t6][3];
             }
+            if (dbg_on && t < 64) dbg[t * 16 + c * 8 + 2] = clock64();
+            __syncthreads();
+            if (dbg_on && t < 64) dbg[t * 16 + c * 8 + 3] = clock64();
+            // ---- gates for (video n, units 2up, 2up+1)
+            float2 a_r = b_r, a_z = b_z, a_n = b_n;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float* pq = pr + (size_t)(c * 2 + cur) * GM_PART + (size_t)q * GM_NV * GM_PSTRIDE;
+                const float2 x0 = *reinterpret_cast<const float2*>(pq), x1 = *reinterpret_cast<const float2*>(pq + GM_U),
+                             x2 = *reinterpret_cast<const float2*>(pq + 2 * GM_U);
+                a_r.x += x0.x; a_r.y += x0.y; a_z.x += x1.x; a_z.y += x1.y; a_n.x += x2.x; a_n.y += x2.y;
+            }
+            const bool live = t < myS[c];
+            float2 hn = hprev[c];               // finished videos re-send their last state: every word is written every step
+            if (live) {
+                const float r0 = gm_sigmoid(g_r[c].x + a_r.x), r1 = gm_sigmoid(g_r[c].y + a_r.y);
+                const float z0 = gm_sigmoid(g_z[c].x + a_z.x), z1 = gm_sigmoid(g_z[c].y + a_z.y);
+                const float n0 = gm_tanh(fmaf(r0, a_n.x, g_n[c].x)), n1 = gm_tanh(fmaf(r1, a_n.y, g_n[c].y));
+                hn.x = fmaf(z0, hprev[c].x - n0, n0);
+                hn.y = fmaf(z1, hprev[c].y - n1, n1);
+                hprev[c] = hn;
+            }
+            const uint32_t word = gm_pack(hn.x, hn.y);
+            const uint32_t w0 = __shfl_sync(0xffffffffu, word, lane & 7), w1 = __shfl_sync(0xffffffffu, word, (lane & 7) + 8),
+                           w2 = __shfl_sync(0xffffffffu, word, (lane & 7) + 16), w3 = __shfl_sync(0xffffffffu, word, (lane & 7) + 24);
+            const uint32_t nxt = (uint32_t)(c * 2 + (cur ^ 1));
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_h[i] + nxt * GM_HBUF), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            if (dbg_on && t < 64) dbg[t * 16 + c * 8 + 4] = clock64();
+            if (live) {
+                const float y0 = relu ? fmaxf(hn.x, 0.f) : hn.x, y1 = relu ? fmaxf(hn.y, 0.f) : hn.y;
+                if (o_dtype == FACTK_BF16) *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(out) + oidx[c]) = gm_pack(y0, y1);
+                else *reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + oidx[c]) = make_float2(y0, y1);
+                oidx[c] += ostep;
+                gp[c] += gstep;
+            }
+            load_gi(c, t + 1);
+            if (dbg_on && t < 64) dbg[t * 16 + c * 8 + 5] = clock64();
         }
-        if (dbg_on && t < 64) dbg[t * 8 + 1] = clock64();
-        // ---- [96 x 64] x [64 x 8] per warp on the tensor cores
-        float acc[6][4];
-#pragma unroll
-        for (int t6 = 0; t6 < 6; ++t6) acc[t6][0] = acc[t6][1] = acc[t6][2] = acc[t6][3] = 0.f;
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-#pragma unroll
-            for (int t6 = 0; t6 < 6; ++t6) gm_mma(acc[t6], A[t6][s], b[s][0], b[s][1]);
-        float* pwc = pw + (size_t)cur * 4 * GM_NV * GM_PSTRIDE;
-#pragma unroll
-        for (int t6 = 0; t6 < 6; ++t6) {
-            pwc[16 * t6] = acc[t6][0];
-            pwc[GM_PSTRIDE + 16 * t6] = acc[t6][1];
-            pwc[16 * t6 + 8] = acc[t6][2];
-            pwc[GM_PSTRIDE + 16 * t6 + 8] = acc[t6][3];
-        }
-        if (dbg_on && t < 64) dbg[t * 8 + 2] = clock64();
-        __syncthreads();
-        if (dbg_on && t < 64) dbg[t * 8 + 3] = clock64();
-        // ---- gates for (video n, units 2up, 2up+1)
-        float2 a_r = b_r, a_z = b_z, a_n = b_n;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float* pq = pr + (size_t)(cur * 4 + q) * GM_NV * GM_PSTRIDE;
-            const float2 x0 = *reinterpret_cast<const float2*>(pq), x1 = *reinterpret_cast<const float2*>(pq + GM_U),
-                         x2 = *reinterpret_cast<const float2*>(pq + 2 * GM_U);
-            a_r.x += x0.x; a_r.y += x0.y; a_z.x += x1.x; a_z.y += x1.y; a_n.x += x2.x; a_n.y += x2.y;
-        }
-        const bool live = t < myS;
-        float2 hn = hprev;                  // finished chains re-send their last state: every word is written every step
-        if (live) {
-            const float r0 = gm_sigmoid(g_r.x + a_r.x), r1 = gm_sigmoid(g_r.y + a_r.y);
-            const float z0 = gm_sigmoid(g_z.x + a_z.x), z1 = gm_sigmoid(g_z.y + a_z.y);
-            const float n0 = gm_tanh(fmaf(r0, a_n.x, g_n.x)), n1 = gm_tanh(fmaf(r1, a_n.y, g_n.y));
-            hn.x = fmaf(z0, hprev.x - n0, n0);
-            hn.y = fmaf(z1, hprev.y - n1, n1);
-            hprev = hn;
-        }
-        const uint32_t word = gm_pack(hn.x, hn.y);
-        const uint32_t w0 = __shfl_sync(0xffffffffu, word, lane & 7), w1 = __shfl_sync(0xffffffffu, word, (lane & 7) + 8),
-                       w2 = __shfl_sync(0xffffffffu, word, (lane & 7) + 16), w3 = __shfl_sync(0xffffffffu, word, (lane & 7) + 24);
-        const uint32_t nxt = (uint32_t)(cur ^ 1);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_h[i] + nxt * GM_HBUF), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-        if (dbg_on && t < 64) dbg[t * 8 + 4] = clock64();
-        if (live) {
-            const int s = dir ? myS - 1 - t : t;
-            const size_t o = ((size_t)vb * slot + s) * (size_t)ldo + (size_t)dir * GM_HH + unit;
-            const float y0 = relu ? fmaxf(hn.x, 0.f) : hn.x, y1 = relu ? fmaxf(hn.y, 0.f) : hn.y;
-            if (o_dtype == FACTK_BF16) *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = gm_pack(y0, y1);
-            else *reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + o) = make_float2(y0, y1);
-        }
-        load_gi(t + 1);
-        if (dbg_on && t < 64) dbg[t * 8 + 5] = clock64();
     }
     // nobody may exit while peers can still write into its shared memory
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -255,12 +291,26 @@ extern "C" int factk_gru_bidir_mma_dbg(const float* gi, const float* w_hh_f, con
     FACTK_REQUIRE((ldo % 2) == 0 && aligned16(gi) && aligned16(b_hh_f) && aligned16(b_hh_b) &&
                       (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
                   "factk_gru_bidir_mma: alignment");
-    const int groups = (B + GM_NV - 1) / GM_NV;
+    // one chain per cluster while all clusters are co-resident (lowest latency per step); two interleaved chains beyond that
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int nc_env = [] { const char* e = getenv("FACTK_GRU_CHAINS"); return e ? atoi(e) : 0; }();
+    const int groups8 = (B + GM_NV - 1) / GM_NV;
+    const int NC = nc_env == 1 || nc_env == 2 ? nc_env : (groups8 * 2 * GM_CS <= sms ? 1 : 2);
+    const int groups = (groups8 + NC - 1) / NC;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t ea = cudaFuncSetAttribute(gru_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem_bytes(1));
+        if (ea == cudaSuccess) ea = cudaFuncSetAttribute(gru_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem_bytes(2));
+        if (ea != cudaSuccess) { set_error("factk_gru_bidir_mma: smem attribute: %s", cudaGetErrorString(ea)); return FACTK_ERR_CUDA; }
+        attr_set = true;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(groups * 2 * GM_CS, 1, 1);
     cfg.blockDim = dim3(GM_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = gm_smem_bytes(NC);
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -269,7 +319,8 @@ extern "C" int factk_gru_bidir_mma_dbg(const float* gi, const float* w_hh_f, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gru_mma_kernel, gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg, dbg);
+    cudaError_t e = NC == 1 ? cudaLaunchKernelEx(&cfg, gru_mma_kernel<1>, gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg, dbg)
+                            : cudaLaunchKernelEx(&cfg, gru_mma_kernel<2>, gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg, dbg);
     if (e != cudaSuccess) { set_error("factk_gru_bidir_mma: launch: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; }
     return check_launch("factk_gru_bidir_mma");
 }

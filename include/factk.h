@@ -187,7 +187,7 @@ int factk_gru_bidir_mma(const float* gi, const float* w_hh_f, const float* b_hh_
                         const float* w_hh_b, const float* b_hh_b, int Hh,
                         void* out, int o_dtype, int ldo, int relu,
                         int B, int slot, const int32_t* nseg, void* stream);
-/* Same, recording a clock64 timeline of CTA 0 into dbg[64][8] (development aid; dbg may be NULL). */
+/* Same, recording a clock64 timeline of CTA 0 into dbg[64][16] (development aid; dbg may be NULL). */
 int factk_gru_bidir_mma_dbg(const float* gi, const float* w_hh_f, const float* b_hh_f,
                             const float* w_hh_b, const float* b_hh_b, int Hh,
                             void* out, int o_dtype, int ldo, int relu,
