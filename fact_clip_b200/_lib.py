@@ -35,6 +35,8 @@ _SIGS = {
     'factk_gemm': (i32, [C.POINTER(Gemm), vp]),
     'factk_gemm_tc': (i32, [C.POINTER(Gemm), vp]),
     'factk_gemm_tc_supported': (i32, [C.POINTER(Gemm)]),
+    'factk_gemm_pair_supported': (i32, [i32, i32]),
+    'factk_gemm_pair': (i32, [vp, i32, i32, vp, i32, i32, i32, vp, vp, i32, i64, vp, i32, vp, i32, i32, i32, vp, vp]),
     'factk_tcn_layer_supported': (i32, [i32]),
     'factk_tcn_layer': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp]),
     'factk_tcn_layer_dbg': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp, vp]),

@@ -32,6 +32,7 @@ class FactEngine:
         self._bufs, self._zbufs, self._len_sig = {}, {}, None
         self.use_tc = True
         self.use_fused_tcn = True
+        self.use_pair_gemm = True
         self._submits, self._copy_stream, self._slot_free = 0, None, [None, None]
         self._wcache, self._wsig = {}, None
         self._graphs = {}
@@ -84,6 +85,15 @@ class FactEngine:
     def mm(self, srcs, N, out, tf32=False, **kw):
         """GEMM dispatch: tcgen05 kernel when the operands qualify (bf16 mode), CUDA-core kernel otherwise."""
         if self.mode == 'bf16' and self.use_tc:
+            s0 = srcs[0]
+            if (self.use_pair_gemm and len(srcs) == 1 and s0['gather'] is None and s0['pos'] is None and s0['off'] == 0 and s0['K'] is None
+                    and s0['W'].dim() == 2 and s0['A'].dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+                    and kw.get('res') is None and kw.get('alpha', 1.0) == 1.0 and (kw.get('bias') is None or kw['bias'].dim() == 1)
+                    and s0['W'].shape[1] % 64 == 0 and N % 128 == 0):
+                Wb = self.wbf(s0['W'])
+                if ops.gemm_pair_ok(s0['A'], Wb, N, out, kw.get('pre')):
+                    return ops.gemm_pair(s0['A'], Wb, N, out, len=kw.get('len'), bias=kw.get('bias'), relu=kw.get('relu', False),
+                                         pre=kw.get('pre'), pre_idx=kw.get('pre_idx'), tag=kw.get('tag'))
             dts = {s['A'].dtype for s in srcs}
             plain = all(s['gather'] is None and s['pos'] is None and s['W'].dim() == 2 for s in srcs)
             if plain and dts == {torch.bfloat16} and all((s['K'] or s['W'].shape[-1]) % 64 == 0 for s in srcs):

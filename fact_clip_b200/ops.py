@@ -89,6 +89,34 @@ def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None, tag
     COUNTERS['launches'] += 1
 
 
+def gemm_pair_ok(A, W, N, out, pre=None):
+    """True when factk_gemm_pair can run y = act(A W^T + bias + pre): bf16 rows / weights / output, aligned, K % 64, N % 128."""
+    bf = torch.bfloat16
+    if not (A.dtype == W.dtype == out.dtype == bf and W.dim() == 2 and A.dim() == 3 and A.shape[0] == out.shape[0]):
+        return False
+    K = W.shape[1]
+    if K % 64 or N % 128 or W.shape[0] != N or A.stride(-1) != 1 or W.stride(-1) != 1 or out.stride(-1) != 1:
+        return False
+    lda, ldw, ldy = A.stride(-2), W.stride(-2), out.stride(-2)
+    if lda % 8 or ldw % 8 or ldy % 8 or A.data_ptr() % 16 or W.data_ptr() % 16 or out.data_ptr() % 16:
+        return False
+    if A.stride(0) % lda or A.stride(0) // lda < out.shape[1] or out.stride(0) != out.shape[1] * ldy:
+        return False
+    if pre is not None and (pre.dtype != torch.float32 or pre.stride(-1) != 1 or pre.stride(-2) % 4 or pre.data_ptr() % 16):
+        return False
+    return True
+
+
+def gemm_pair(A, W, N, out, len=None, bias=None, relu=False, pre=None, pre_idx=None, tag=None):
+    B, slot = out.shape[0], out.shape[1]
+    lda = A.stride(-2)
+    pre_bstride = pre.stride(0) if (pre is not None and pre.dim() == 3) else 0
+    COUNTERS['launches'] += 1
+    _call('factk_gemm_pair', tag or 'gemm_pair', A.data_ptr(), lda, A.stride(0) // lda, W.data_ptr(), W.stride(-2), W.shape[1], N,
+          L.ptr(bias), L.ptr(pre), pre.stride(-2) if pre is not None else 0, pre_bstride, L.ptr(pre_idx), int(relu),
+          out.data_ptr(), out.stride(-2), B, slot, L.ptr(len), L.stream())
+
+
 def tcn_layer_supported(F):
     return bool(L.load().factk_tcn_layer_supported(int(F)))
 

@@ -97,6 +97,17 @@ int factk_gemm_tc(const factk_gemm_t* g, void* stream);
 /* 1 if factk_gemm_tc accepts this descriptor, 0 otherwise (no launch). */
 int factk_gemm_tc_supported(const factk_gemm_t* g);
 
+/* Frame-side bf16 GEMM on CTA pairs (tcgen05 cta_group::2, two TMEM accumulators, bf16-staged coalesced epilogue):
+ *   y[b,t,:N] = act(x[b,t,:K] W^T + bias + pre[b*pre_bstride + idx(t)*ldpre + :N]),  x / W / y bf16, bias / pre fp32.
+ * Replaces the plain Linear / 1x1 Conv1d call sites on frames and segments: conv_out (basic.py:182,213), the SCA key /
+ * value projection (basic.py:465,513), sf_merge (blocks.py:414,445, `pre` = the gathered segment term), the CLIP projection
+ * (blocks.py:153-159), seg_combine (blocks.py:402).  K % 64 == 0, N % 128 == 0 (factk_gemm_pair_supported), 16-byte aligned
+ * rows; rows >= len[b] are not written. */
+int factk_gemm_pair_supported(int K, int N);
+int factk_gemm_pair(const void* x, int lda, int a_slot, const void* W, int ldw, int K, int N, const float* bias,
+                    const float* pre, int ldpre, long long pre_bstride, const int32_t* pre_idx, int relu,
+                    void* y, int ldy, int B, int slot, const int32_t* len, void* stream);
+
 /* Fused DilatedResidualLayer (models/basic.py:154-171; MSTCN.forward :216-217), eval mode:
  *   y[b,t,:] = x[b,t,:] + W1 relu(sum_k W3[k] x[b, t+(k-1)*dilation, :] + b3) + b1
  * in ONE persistent tcgen05 kernel (conv3 -> ReLU tile kept in shared memory -> 1x1 -> residual), nothing but x

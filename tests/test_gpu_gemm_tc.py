@@ -99,3 +99,45 @@ def test_many_tiles_persistent():
     torch.cuda.synchronize()
     ref = x.float() @ w.float().t()
     assert rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize('B,slot,K,N,lens', [(2, 512, 256, 512, [512, 300]), (3, 384, 512, 256, [384, 1, 129]), (1, 128, 64, 128, [77]),
+                                              (5, 4096, 512, 512, [4096, 4000, 3000, 4096, 77])])
+@pytest.mark.parametrize('relu', [False, True])
+def test_gemm_pair(B, slot, K, N, lens, relu):
+    """CTA-pair bf16 GEMM (factk_gemm_pair): bias, ReLU, rows past the end untouched; strided input / output rows."""
+    x = rnd(B, slot, K + 64, seed=41).to(BF)[:, :, :K]              # lda = K + 64
+    w = rnd(N, K, seed=42, scale=K ** -0.5).to(BF)
+    bias = rnd(N, seed=43)
+    full = torch.full((B, slot, N + 128), 7.0, dtype=BF, device=DEV)
+    out = full[:, :, :N]                                            # ldy = N + 128
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    xd = x.to(DEV)
+    assert ops.gemm_pair_ok(xd, w.to(DEV), N, out)
+    ops.gemm_pair(xd, w.to(DEV), N, out, len=ln, bias=bias.to(DEV), relu=relu)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + bias
+    ref = torch.relu(ref) if relu else ref
+    for b, T in enumerate(lens):
+        assert rel(out[b, :T], ref[b, :T]) < 6e-3, (b, rel(out[b, :T], ref[b, :T]))
+        assert bool((out[b, T:].float() == 7.0).all())
+    assert bool((full[:, :, N:].float() == 7.0).all())
+
+
+def test_gemm_pair_pre_gather():
+    """sf_merge form: relu(frame W2^T + bias + (seg W1^T)[seg_label]) with the gathered term as a pre-activation addend."""
+    B, slot, K, N, S = 2, 512, 512, 256, 40
+    x = rnd(B, slot, K, seed=44).to(BF)
+    w = rnd(N, K, seed=45, scale=K ** -0.5).to(BF)
+    bias = rnd(N, seed=46)
+    pre = rnd(B, slot, N, seed=47)
+    idx = torch.randint(0, S, (B, slot), generator=torch.Generator().manual_seed(48), dtype=torch.int32)
+    lens = [512, 200]
+    out = torch.zeros(B, slot, N, dtype=BF, device=DEV)
+    ops.gemm_pair(x.to(DEV), w.to(DEV), N, out, len=torch.tensor(lens, dtype=torch.int32, device=DEV), bias=bias.to(DEV), relu=True,
+                  pre=pre.to(DEV), pre_idx=idx.to(DEV))
+    torch.cuda.synchronize()
+    for b, T in enumerate(lens):
+        ref = torch.relu(x[b, :T].float() @ w.float().t() + bias + pre[b][idx[b, :T].long()])
+        assert rel(out[b, :T], ref) < 6e-3
+        assert bool((out[b, T:] == 0).all())
