@@ -458,6 +458,10 @@ class FactEngine:
             self.last_launches = ent[2]
             g.replay()          # the capture itself did not execute
             return out
+        if self._len_sig != tuple(lengths):      # another batch shape ran in between: restore the zero tails the taps rely on
+            for t in self._zbufs.values():
+                t.zero_()
+            self._len_sig = tuple(lengths)
         ent[0].replay()
         ops.COUNTERS['launches'] += ent[2]
         self.last_launches = ent[2]

@@ -208,3 +208,24 @@ def test_pipelined_submit_matches_forward():
         got = h.result()
         for a, b in zip(ref, got):
             assert np.array_equal(a['pred'], b['pred'])
+
+
+def test_graph_replay_alternating_batch_shapes():
+    """The CUDA-graph path (net.submit) replays correctly when batches of different lengths alternate: the zero tails that
+    stand in for Conv1d padding are restored when a shorter batch follows a longer one."""
+    g = load_golden('tiny_m_iuU_clip')
+    net = build(g, 'fp32')
+    vids = g['videos']
+    xs = [v['x'] for v in vids]
+    long_ = [torch.cat([x, x.flip(0)], 0).pin_memory() for x in xs]          # twice as long
+    short = [x.pin_memory() for x in xs]
+    ref_long = net([x.to(DEV) for x in long_], None)
+    ref_short = net([x.to(DEV) for x in short], None)
+    for rep in range(2):
+        for batch, ref in ((long_, ref_long), (short, ref_short)):
+            for _ in range(2):                                               # capture, then replay
+                got = net.submit(batch, None).result()
+                for a, b in zip(got, ref):
+                    assert np.array_equal(a['pred'], b['pred'])
+    for b, v in enumerate(vids):
+        assert np.array_equal(ref_short[b]['pred'], v['pred'].numpy())
