@@ -228,6 +228,10 @@ def main():
             sys.stderr.write(f"  {k:28s} n/step={v['n'] // 2:4d} {v['ms'] / 2:8.3f} ms/step {100 * v['ms'] / tot:5.1f}%\n")
         sys.stderr.write(f"  total {tot / 2:.3f} ms/step (sum of kernel times)\n")
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3), drain=drain_e2e)
+    # same pipeline with the features stored as bf16 on the host (input staging): half the PCIe bytes
+    host16 = host.to(torch.bfloat16).pin_memory()
+    seq_host = [host16[b] for b in range(B)]
+    ms_e2e16 = timed(step_e2e, args.steps, max(args.warmup, 3), drain=drain_e2e)
 
     frames_step = B * T * world
     value = frames_step * args.steps / (ms * 1e-3)
@@ -255,7 +259,12 @@ def main():
                    'segments_per_U_block_rank0': [[min(s), max(s)] for s in nseg]},
         'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': B * T * IN_DIM * 4 * world,
-                'd2h_bytes_per_step': B * T * 8 * world, 'ms_per_step': ms_e2e / args.steps},
+                'd2h_bytes_per_step': B * T * 8 * world, 'ms_per_step': ms_e2e / args.steps,
+                'features': 'fp32 on the host (the reference format)'},
+        'e2e_bf16_features': {'value': frames_step * args.steps / (ms_e2e16 * 1e-3), 'unit': UNIT,
+                              'h2d_bytes_per_step': B * T * IN_DIM * 2 * world, 'd2h_bytes_per_step': B * T * 8 * world,
+                              'ms_per_step': ms_e2e16 / args.steps,
+                              'features': 'pre-converted to bf16 on the host (input staging option; not the headline)'},
         'roofline': {'bound': 'tensor', 'kernel': 'tcn_layer_kernel: fused dilated residual layer (conv3+ReLU+1x1+residual), 40 launches per forward',
                      'achieved': ach_tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': ach_tf / pk['tf_sust'],
                      'traffic': TCN_DRAM_BYTES_PER_LAUNCH.get(B), 'traffic_source': 'profiles/r1_tcn_layer_ncu_full.txt (dram read + write per launch, ncu --set full)',

@@ -425,7 +425,21 @@ extern "C" int factk_gemm_tc(const factk_gemm_t* g, void* stream) {
     if (why) { set_error("factk_gemm_tc: unsupported descriptor (%s)", why); return FACTK_ERR_UNSUPPORTED; }
     const bool tf32 = g->src[0].a_dtype == FACTK_F32;
     const int es = tf32 ? 4 : 2;
-    const int BN = g->N <= 64 ? 64 : (g->N <= 128 ? 128 : 256);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // N tile: the widest tile that covers N re-reads A least, but small problems (token rows: one 128-row tile per video)
+    // do not fill the GPU with it -- pick the width that minimises waves x bytes loaded per tile and K chunk
+    int BN = g->N <= 64 ? 64 : (g->N <= 128 ? 128 : 256);
+    {
+        const long long tm = (long long)g->B * ((g->slot + 127) / 128);
+        long long best = -1;
+        for (int bn = BN; bn >= 64; bn >>= 1) {
+            const long long tiles = tm * ((g->N + bn - 1) / bn);
+            const long long cost = ((tiles + sms - 1) / sms) * (16384 + bn * 128);
+            if (best < 0 || cost < best) { best = cost; BN = bn; }
+        }
+    }
     TcParams p;
     memset(&p, 0, sizeof(p));
     for (int s = 0; s < g->nsrc; ++s) {
@@ -452,9 +466,6 @@ extern "C" int factk_gemm_tc(const factk_gemm_t* g, void* stream) {
     };
     p.vec_io = al(g->Y, g->ldy, g->y_dtype) && al(g->res, g->ldres, g->res_dtype) && al(g->pre, g->ldpre, g->pre_dtype) &&
                (g->pre == nullptr || (g->pre_bstride * (g->pre_dtype == FACTK_BF16 ? 2 : 4)) % 16 == 0);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     cudaStream_t st = (cudaStream_t)stream;
     if (tf32) {

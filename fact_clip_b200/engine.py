@@ -386,13 +386,23 @@ class FactEngine:
         return frame, action
 
     # ------------------------------------------------------------------ whole forward
+    def _feature_dtype(self, seqs):
+        """fp32 features (the reference's format, dataset.py:12-21) or, in bf16 mode, features already stored as bf16: half the
+        host->device bytes (input staging) and the input projection runs as a bf16 tensor-core GEMM."""
+        dts = {s.dtype for s in seqs}
+        if dts == {torch.float32}:
+            return torch.float32
+        if dts == {torch.bfloat16} and self.mode == 'bf16':
+            return torch.bfloat16
+        raise TypeError(f'features must all be float32 (or all bfloat16 in bf16 compute mode), got {sorted(map(str, dts))}')
+
     @torch.no_grad()
     def run(self, seqs, forced_preds=None, keep=False):
         """seqs: list of (T_i, in_dim) fp32 tensors, CUDA or (pinned) host.  Synchronous with respect to the stream."""
         self._refresh_weights()
         lengths = [int(s.shape[0]) for s in seqs]
         B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
-        x = self.buf('input', (B, slot, D))
+        x = self.buf('input', (B, slot, D), self._feature_dtype(seqs))
         for b, s in enumerate(seqs):
             x[b, :lengths[b]].copy_(s, non_blocking=True)
         ln = self.buf('len', (B,), torch.int32)
@@ -412,7 +422,7 @@ class FactEngine:
         main = torch.cuda.current_stream()
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.dev)
-        x = self.buf(f'input_p{k}', (B, slot, D))
+        x = self.buf(f'input_p{k}', (B, slot, D), self._feature_dtype(seqs))
         ln = self.buf(f'len_p{k}', (B,), torch.int32)
         pred = self.buf(f'pred64_p{k}', (B, slot), torch.int64)
         key = (f'pred_host_p{k}', B, slot)

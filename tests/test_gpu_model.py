@@ -229,3 +229,28 @@ def test_graph_replay_alternating_batch_shapes():
                     assert np.array_equal(a['pred'], b['pred'])
     for b, v in enumerate(vids):
         assert np.array_equal(ref_short[b]['pred'], v['pred'].numpy())
+
+
+def test_bf16_host_features():
+    """Features stored as bf16 (input staging option): same predictions and logits (2e-2) as the fp32-feature path fed the
+    same bf16-representable values; fp32 compute mode refuses bf16 features."""
+    cfg = C.PRESETS['havid_view0_lh_pt_holdout']()
+    torch.manual_seed(0)
+    net = FACT_CLIP(cfg, 2048, 75, make_text_embeddings(75)).eval()
+    net.compute_mode = 'bf16'
+    net = net.to(DEV)
+    lens = [384, 200]
+    xs, ys = make_batch(lens, 2048, 75, base_seed=77, nseg=8)
+    x16 = [x.to(torch.bfloat16) for x in xs]
+    a = net([x.float().to(DEV) for x in x16], None)
+    net.stash_video(0)
+    fa = net.block_list[0].frame_clogit.clone()
+    b = net([x.pin_memory() for x in x16], None)
+    net.stash_video(0)
+    fb = net.block_list[0].frame_clogit.clone()
+    assert rel(fb, fa) < 2e-2
+    agree = sum(int((p['pred'] == q['pred']).sum()) for p, q in zip(a, b))
+    assert agree >= 0.99 * sum(lens)
+    net.compute_mode = 'fp32'
+    with pytest.raises(TypeError):
+        net([x.to(DEV) for x in x16], None)
