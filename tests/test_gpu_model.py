@@ -254,3 +254,38 @@ def test_bf16_host_features():
     net.compute_mode = 'fp32'
     with pytest.raises(TypeError):
         net([x.to(DEV) for x in x16], None)
+
+
+def test_full_size_batch_invariance_and_determinism():
+    """BASELINE config 3/4 at full size (T = 4096, D = 2048, bf16 tensor-core path), size-independent properties: a video's
+    result does not depend on what it is batched with (ragged lengths, zero tails, tile scheduling, GRU grouping), and
+    re-runs are bit-identical (no atomics anywhere)."""
+    cfg = C.PRESETS['havid_view0_lh_pt_holdout']()
+    torch.manual_seed(0)
+    net = FACT_CLIP(cfg, 2048, 75, make_text_embeddings(75)).eval()
+    net.compute_mode = 'bf16'
+    net = net.to(DEV)
+    lens = [4096, 3000, 4096, 129]
+    xs, ys = make_batch(lens, 2048, 75, base_seed=90, nseg=8)
+    xd = [x.to(DEV) for x in xs]
+
+    def run(idx):
+        out = net([xd[i] for i in idx], None)
+        logits, nsegs = [], []
+        for j in range(len(idx)):
+            net.stash_video(j)
+            logits.append(net.block_list[-1].frame_clogit.clone())
+            nsegs.append([int(st['nseg'][j]) for st in net._last['blocks'] if 'nseg' in st])
+        return out, logits, nsegs
+
+    full, lf, nf = run([0, 1, 2, 3])
+    again, la, na = run([0, 1, 2, 3])
+    for a, b, x, y in zip(full, again, lf, la):
+        assert np.array_equal(a['pred'], b['pred']) and torch.equal(x, y)
+    assert nf == na
+    for i in range(4):
+        alone, l1, n1 = run([i])
+        assert n1[0] == nf[i], (i, n1, nf[i])
+        assert np.array_equal(alone[0]['pred'], full[i]['pred']), i
+        assert torch.equal(l1[0], lf[i]), (i, float((l1[0] - lf[i]).abs().max()))
+        assert alone[0]['pred'].shape == (lens[i],)
