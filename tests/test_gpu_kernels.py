@@ -261,7 +261,8 @@ def test_gru_bidir(Hh, nsegs):
         assert bool((out[b, Sg:] == 0).all())
 
 
-@pytest.mark.parametrize('nsegs', [[300, 17], [5, 1, 64, 33, 200, 7, 90, 2, 11, 384]])
+@pytest.mark.parametrize('nsegs', [[300, 17], [5, 1, 64, 33, 200, 7, 90, 2, 11, 384],
+                                   [(7 * i) % 41 + 1 for i in range(83)]])   # > 72 videos: two interleaved chains per cluster
 def test_gru_bidir_mma(nsegs):
     """Tensor-core GRU (bf16 W_hh and exchanged state, MUFU.TANH gates) vs the fp32 recurrence: bf16-level agreement."""
     Hh = 256
