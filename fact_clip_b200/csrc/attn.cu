@@ -5,6 +5,8 @@
 //  * col_softmax_apply: softmax over the frame/segment axis of a logit matrix and the weighted row sum
 //    (the f2a direction of X2Y_map), again split over rows and combined in fixed order.
 // All softmax state lives in registers; fp32 throughout.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace factk {
@@ -151,7 +153,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int DH>
+template <int DH, bool QSPLIT>
 __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restrict__ Q, int ldq,
                                                             const __nv_bfloat16* __restrict__ Kx,
                                                             const __nv_bfloat16* __restrict__ Vx, int ldkv,
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr);
                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
                 mma_bf16_16816(sacc[j], qa[ks], b0, b1);
-                mma_bf16_16816(sacc[j], qb_lo[ks], b0, b1);
+                if constexpr (QSPLIT) mma_bf16_16816(sacc[j], qb_lo[ks], b0, b1);
             }
         }
         // mask frames beyond the split, online softmax (rows g and g+8 of this warp's tile)
@@ -599,9 +601,12 @@ extern "C" int factk_attn_rows(const float* Q, int ldq, const void* Kx, const vo
         const dim3 mgrid(ns * nqb, nhead, B);
         const __nv_bfloat16* K16 = reinterpret_cast<const __nv_bfloat16*>(Kx);
         const __nv_bfloat16* V16 = reinterpret_cast<const __nv_bfloat16*>(Vx);
+        // FACTK_ATTN_QSPLIT=1: queries as hi + lo bf16 pairs (logits carry only the keys' rounding) at +50 % QK^T tensor work
+        static const bool qsplit = [] { const char* e = getenv("FACTK_ATTN_QSPLIT"); return e && atoi(e) != 0; }();
 #define LAUNCH_MMA(DH)                                                                                                  \
     do {                                                                                                                \
-        attn_rows_mma_kernel<DH><<<mgrid, wthreads, 0, st_>>>(Q, ldq, K16, V16, ldkv, ws, slot, len, M, nhead, ns);       \
+        if (qsplit) attn_rows_mma_kernel<DH, true><<<mgrid, wthreads, 0, st_>>>(Q, ldq, K16, V16, ldkv, ws, slot, len, M, nhead, ns);   \
+        else attn_rows_mma_kernel<DH, false><<<mgrid, wthreads, 0, st_>>>(Q, ldq, K16, V16, ldkv, ws, slot, len, M, nhead, ns);             \
         attn_rows_combine_kernel<DH><<<cgrid, 256, 0, st_>>>(ws, O, ldo, slot, len, M, nhead, ns);                       \
     } while (0)
         if (dh == 16) LAUNCH_MMA(16); else if (dh == 32) LAUNCH_MMA(32); else LAUNCH_MMA(64);
