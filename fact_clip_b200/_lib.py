@@ -50,7 +50,8 @@ _SIGS = {
     'factk_col_softmax_ws_floats': (C.c_size_t, [i32, i32, i32, i32]),
     'factk_col_softmax_apply': (i32, [vp, i32, vp, i32, i32, vp, i32, vp, i32, i32, i32, vp, i32, i32, vp, vp]),
     'factk_tdu_segment': (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
-    'factk_segment_mean': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp]),
+    'factk_segment_mean_ws_floats': (C.c_size_t, [i32, i32, i32]),
+    'factk_segment_mean': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     'factk_gru_bidir': (i32, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
     'factk_gru_bidir_mma': (i32, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
     'factk_gru_bidir_mma_dbg': (i32, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp]),

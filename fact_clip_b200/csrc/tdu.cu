@@ -2,10 +2,10 @@
 //  * tdu_segment  : run-length segmentation of the per-frame argmax (utils/utils.py:25-48,
 //                   models/basic.py:597-607, models/blocks.py:454) -- block scan per video.
 //  * segment_mean : deterministic mean over each contiguous run (models/basic.py:615-625).
-//  * gru_bidir    : the bidirectional GRU recurrence over segments (models/blocks.py:401,432) as a
-//                   persistent kernel on 4-CTA clusters: each CTA keeps the W_hh rows of a quarter of the
-//                   hidden units resident in shared memory and the new hidden state is exchanged through
-//                   distributed shared memory once per step.
+//  * gru_bidir    : the bidirectional GRU recurrence over segments (models/blocks.py:401,432) in fp32 (the fp32 compute
+//                   mode and hidden sizes other than 256): a persistent kernel on 4-CTA clusters, each CTA keeps the
+//                   W_hh rows of a quarter of the hidden units in registers and the new hidden state is exchanged through
+//                   distributed shared memory once per step.  The bf16 mode uses gru_mma.cu.
 #include <cooperative_groups.h>
 
 #include <cstdlib>
@@ -165,6 +165,121 @@ __global__ void __launch_bounds__(128 * SEGM_LANES) segment_mean_kernel(const vo
                 st_vec4(seg, s_dtype, (base + s_first + i) * (size_t)lds + c, make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv));
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming segment mean in two passes (rows with 16-byte aligned row starts).
+//  pass 1, one CTA per 32-frame chunk: the 32 rows are fetched with fully independent coalesced loads into shared memory
+//          while the chunk's labels are read; the chunk is cut into "pieces" at the label changes, each piece is summed in
+//          row order by one of eight row lanes.  A piece that is a whole segment is finished here; a piece whose segment
+//          started in an earlier chunk goes to head[b][chunk], one whose segment continues past the chunk to tail[b][chunk].
+//  pass 2, one CTA per chunk: if a segment starting in this chunk continues past it, total = tail[chunk] + head[chunk+1]
+//          + ... in chunk order.
+// Every frame is read exactly once, nothing but a short index chain depends on the segmentation, and the summation order
+// is fixed (deterministic, no atomics -- SURVEY D5): the time no longer depends on how pathological the segmentation is
+// (S ~ 0.6 T in one block, S = 1 in the next under random-init weights).
+constexpr int SM2_CHUNK = 32, SM2_LANES = 2;      // 256-thread CTAs: several resident per SM (occupancy hides the index chain)
+__global__ void __launch_bounds__(128 * SM2_LANES) segment_mean_pass1_kernel(const void* __restrict__ X, int x_dtype, int ldx,
+                                                                              void* seg, int s_dtype, int lds,
+                                                                              const int32_t* __restrict__ seg_label,
+                                                                              const int32_t* __restrict__ seg_start,
+                                                                              const int32_t* __restrict__ seg_len,
+                                                                              const int32_t* __restrict__ nseg, int slot, int E,
+                                                                              float* __restrict__ head, float* __restrict__ tail) {
+    extern __shared__ __align__(16) uint8_t sm2_rows[];          // [32 rows][E] in the rows' dtype
+    __shared__ int lab[SM2_CHUNK + 2];                           // labels of frames f0-1 .. f0+32 (-1 outside the video)
+    __shared__ int p_begin[SM2_CHUNK + 1], n_piece_s;
+    const int b = blockIdx.y, c = blockIdx.x, nchunks = gridDim.x;
+    const int S = min(nseg[b], slot);
+    if (S <= 0) return;
+    const size_t base = (size_t)b * slot;
+    const int f0 = c * SM2_CHUNK;
+    const int es = x_dtype == FACTK_BF16 ? 2 : 4;
+    const int row_bytes = E * es, chunks16 = row_bytes / 16;
+    // rows -> shared memory: independent loads, issued before anything that depends on the segmentation
+    for (int i = threadIdx.x; i < SM2_CHUNK * chunks16; i += blockDim.x) {
+        const int r = i / chunks16, k = i % chunks16;
+        if (f0 + r < slot)
+            *reinterpret_cast<uint4*>(sm2_rows + (size_t)r * row_bytes + k * 16) =
+                *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(X) + ((base + f0 + r) * (size_t)ldx) * es + k * 16);
+    }
+    const int T = seg_start[base + S - 1] + seg_len[base + S - 1];   // frames of this video (labels exist for t < T)
+    if (f0 >= T) return;                                             // uniform
+    if (threadIdx.x < SM2_CHUNK + 2) {
+        const int t = f0 - 1 + (int)threadIdx.x;
+        lab[threadIdx.x] = (t >= 0 && t < T) ? seg_label[base + t] : -1;
+    }
+    __syncthreads();
+    const int nrows = min(SM2_CHUNK, T - f0);
+    if (threadIdx.x < 32) {                                      // piece boundaries: one ballot instead of a serial scan
+        const int r = threadIdx.x;
+        const bool flag = r < nrows && (r == 0 || lab[r + 1] != lab[r]);
+        const unsigned mask = __ballot_sync(0xffffffffu, flag);
+        if (flag) p_begin[__popc(mask & ((2u << r) - 1u)) - 1] = r;
+        if (r == 0) {
+            p_begin[__popc(mask)] = nrows;
+            n_piece_s = __popc(mask);
+        }
+    }
+    __syncthreads();
+    const int np = n_piece_s;
+    const int cl = threadIdx.x & 127, rl = threadIdx.x >> 7;
+    for (int k = rl; k < np; k += SM2_LANES) {
+        const int r0 = p_begin[k], r1 = p_begin[k + 1];
+        const int s = lab[r0 + 1];
+        const bool is_head = (k == 0) && (lab[0] == s);              // the segment started in an earlier chunk
+        const bool is_tail = (k == np - 1) && (lab[nrows + 1] == s);  // the segment continues in the next chunk
+        for (int c4 = cl * 4; c4 < E; c4 += 512) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = r0; r < r1; ++r) {
+                const float4 v = ld_vec4(sm2_rows + (size_t)r * row_bytes, x_dtype, c4);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            if (is_head) {
+                *reinterpret_cast<float4*>(head + ((size_t)b * nchunks + c) * E + c4) = a;
+            } else if (is_tail) {
+                *reinterpret_cast<float4*>(tail + ((size_t)b * nchunks + c) * E + c4) = a;
+            } else {
+                const float inv = 1.f / (float)(r1 - r0);
+                st_vec4(seg, s_dtype, (base + s) * (size_t)lds + c4, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) segment_mean_pass2_kernel(void* seg, int s_dtype, int lds,
+                                                                 const int32_t* __restrict__ seg_label,
+                                                                 const int32_t* __restrict__ seg_start,
+                                                                 const int32_t* __restrict__ seg_len,
+                                                                 const int32_t* __restrict__ nseg, int slot, int E,
+                                                                 const float* __restrict__ head, const float* __restrict__ tail) {
+    const int b = blockIdx.y, c = blockIdx.x, nchunks = gridDim.x;
+    const int S = min(nseg[b], slot);
+    if (S <= 0) return;
+    const size_t base = (size_t)b * slot;
+    const int f1 = (c + 1) * SM2_CHUNK;
+    const int T = seg_start[base + S - 1] + seg_len[base + S - 1];
+    if (f1 >= T) return;                                   // nothing continues past the last chunk of the video
+    const int s = seg_label[base + f1 - 1];
+    if (seg_label[base + f1] != s) return;                 // no segment crosses this chunk's end
+    const int st = seg_start[base + s];
+    if (st < f1 - SM2_CHUNK) return;                       // it started in an earlier chunk: that chunk's CTA sums it
+    const int n = seg_len[base + s];
+    const int c_end = (st + n - 1) / SM2_CHUNK;            // last chunk the segment touches
+    const float inv = 1.f / (float)n;
+    for (int c4 = threadIdx.x * 4; c4 < E; c4 += 512) {
+        float4 a = *reinterpret_cast<const float4*>(tail + ((size_t)b * nchunks + c) * E + c4);
+        for (int cc = c + 1; cc <= c_end; cc += 4) {       // four independent loads in flight, added in chunk order
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = (cc + j <= c_end) ? *reinterpret_cast<const float4*>(head + ((size_t)b * nchunks + cc + j) * E + c4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+        }
+        st_vec4(seg, s_dtype, (base + s) * (size_t)lds + c4, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
     }
 }
 
@@ -360,13 +475,37 @@ extern "C" int factk_tdu_segment(const int32_t* pred, int B, int slot, const int
     return check_launch("factk_tdu_segment");
 }
 
+extern "C" size_t factk_segment_mean_ws_floats(int B, int slot, int E) {
+    const size_t nchunks = (size_t)(slot + SM2_CHUNK - 1) / SM2_CHUNK;
+    return 2 * (size_t)B * nchunks * (size_t)E;
+}
+
 extern "C" int factk_segment_mean(const void* X, int x_dtype, int ldx, void* seg, int s_dtype, int lds,
                                   const int32_t* seg_label, const int32_t* seg_start, const int32_t* seg_len, const int32_t* nseg,
-                                  int B, int slot, int E, void* stream) {
+                                  int B, int slot, int E, float* ws, void* stream) {
     FACTK_REQUIRE(X && seg && seg_label && seg_start && seg_len && nseg && B > 0 && slot > 0 && E > 0, "factk_segment_mean: bad args");
     FACTK_REQUIRE(B <= 65535, "factk_segment_mean: B too large");
-    segment_mean_kernel<<<dim3((slot + SEGM_CHUNK - 1) / SEGM_CHUNK, B), 128 * SEGM_LANES, 0, (cudaStream_t)stream>>>(X, x_dtype, ldx, seg, s_dtype, lds, seg_label, seg_start,
-                                                                          seg_len, nseg, slot, E);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int es = x_dtype == FACTK_BF16 ? 2 : 4, ss = s_dtype == FACTK_BF16 ? 2 : 4;
+    const size_t smem = (size_t)SM2_CHUNK * E * es;
+    const bool stream_ok = ws != nullptr && aligned16(X) && aligned16(seg) && aligned16(ws) && (E % 8) == 0 && ((size_t)ldx * es) % 16 == 0 &&
+                           ((size_t)lds * ss) % 16 == 0 && smem <= 160 * 1024;
+    if (stream_ok) {
+        const int nchunks = (slot + SM2_CHUNK - 1) / SM2_CHUNK;
+        float* head = ws;
+        float* tail = ws + (size_t)B * nchunks * E;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(segment_mean_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr_set = true;
+        }
+        segment_mean_pass1_kernel<<<dim3(nchunks, B), 128 * SM2_LANES, smem, st>>>(X, x_dtype, ldx, seg, s_dtype, lds, seg_label, seg_start,
+                                                                                   seg_len, nseg, slot, E, head, tail);
+        segment_mean_pass2_kernel<<<dim3(nchunks, B), 128, 0, st>>>(seg, s_dtype, lds, seg_label, seg_start, seg_len, nseg, slot, E, head, tail);
+        return check_launch("factk_segment_mean");
+    }
+    segment_mean_kernel<<<dim3((slot + SEGM_CHUNK - 1) / SEGM_CHUNK, B), 128 * SEGM_LANES, 0, st>>>(X, x_dtype, ldx, seg, s_dtype, lds, seg_label,
+                                                                                                   seg_start, seg_len, nseg, slot, E);
     return check_launch("factk_segment_mean");
 }
 
@@ -386,12 +525,9 @@ extern "C" int factk_gru_bidir(const float* gi, const float* w_hh_f, const float
     const int KS = Hh / GRU_KQ;
     const int threads = GRU_KQ * 3 * KS;
     cudaStream_t st = (cudaStream_t)stream;
-    static const int nacc = [] { const char* e = getenv("FACTK_GRU_NACC"); return e ? atoi(e) : 1; }();
 #define LAUNCH(N_, K_)                                                                                                  \
-    do {                                                                                                                \
-        if (nacc == 1) gru_cluster_kernel<N_, K_, 1><<<groups * 2 * GRU_CS, threads, 0, st>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg); \
-        else gru_cluster_kernel<N_, K_, 2><<<groups * 2 * GRU_CS, threads, 0, st>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg); \
-    } while (0)
+    gru_cluster_kernel<N_, K_, 1><<<groups * 2 * GRU_CS, threads, 0, st>>>(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, \
+                                                                             slot, nseg)
 #define LAUNCH_K(N_)                                                \
     do {                                                            \
         if (KS == 8) LAUNCH(N_, 8);                                 \

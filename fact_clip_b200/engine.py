@@ -357,7 +357,8 @@ class FactEngine:
         ops.tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=self.len)
         st.update(seg_label=seg_label, seg_lens=seg_len, nseg=nseg, tdu_pred=pred)
         seg0 = self.buf('seg0', (B, slot, H), self.act)
-        ops.segment_mean(frame, seg0, seg_label, seg_start, seg_len, nseg)
+        ws = self.buf('segmean_ws', (ops.segment_mean_ws(B, slot, H),))
+        ops.segment_mean(frame, seg0, seg_label, seg_start, seg_len, nseg, ws=ws)
         g = pfx + 'seg_update.'
         gi = self.buf('gru_gi', (B, slot, 6 * Hh))
         self.mm([S(seg0, self.cat(g + 'weight_ih_l0', g + 'weight_ih_l0_reverse'))], 6 * Hh, gi, len=nseg,

@@ -209,12 +209,16 @@ def tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=None)
            seg_len.data_ptr(), seg_center.data_ptr(), nseg.data_ptr(), L.stream())
 
 
-def segment_mean(x, seg, seg_label, seg_start, seg_len, nseg, E=None):
+def segment_mean_ws(B, slot, E):
+    return int(L.load().factk_segment_mean_ws_floats(B, slot, E))
+
+
+def segment_mean(x, seg, seg_label, seg_start, seg_len, nseg, E=None, ws=None):
     B, slot = x.shape[0], x.shape[1]
     E = x.shape[-1] if E is None else E
-    COUNTERS['launches'] += 1
+    COUNTERS['launches'] += 2 if ws is not None else 1
     _call('factk_segment_mean', None, x.data_ptr(), L.dt(x), _row_ld(x), seg.data_ptr(), L.dt(seg), _row_ld(seg),
-           seg_label.data_ptr(), seg_start.data_ptr(), seg_len.data_ptr(), nseg.data_ptr(), B, slot, E, L.stream())
+           seg_label.data_ptr(), seg_start.data_ptr(), seg_len.data_ptr(), nseg.data_ptr(), B, slot, E, L.ptr(ws), L.stream())
 
 
 def gru_bidir(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, nseg, relu=True, mma=False):

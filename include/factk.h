@@ -178,10 +178,12 @@ int factk_tdu_segment(const int32_t* pred, int B, int slot, const int32_t* len,
 
 /* TemporalDownsampleUpsample.feature_frame2seg (basic.py:615-625): deterministic segment mean.
  * X rows of dtype [B][slot][ldx] -> seg fp32/bf16 [B][slot][lds], first nseg[b] rows.  seg_label / seg_start / seg_len /
- * nseg as written by factk_tdu_segment. */
+ * nseg as written by factk_tdu_segment.  ws: fp32 scratch of factk_segment_mean_ws_floats(...) floats for the streaming
+ * two-pass kernel (every frame read once, time independent of the segmentation); ws == NULL selects the one-pass kernel. */
+size_t factk_segment_mean_ws_floats(int B, int slot, int E);
 int factk_segment_mean(const void* X, int x_dtype, int ldx, void* seg, int s_dtype, int lds,
                        const int32_t* seg_label, const int32_t* seg_start, const int32_t* seg_len, const int32_t* nseg,
-                       int B, int slot, int E, void* stream);
+                       int B, int slot, int E, float* ws, void* stream);
 
 /* Bidirectional GRU recurrence (nn.GRU(H, H/2, 1, bidirectional=True), blocks.py:401,432) over the
  * nseg[b] segments of each video.  gi fp32 [B][slot][6*Hh] = x W_ih^T + b_ih for (fwd r,z,n | bwd r,z,n);

@@ -227,6 +227,16 @@ def test_tdu_segment_and_mean():
     ops.tdu_segment(pred.to(DEV), o['seg_label'], o['seg_start'], o['seg_len'], o['seg_center'], nseg, len=ln)
     seg = torch.zeros(B, slot, E, device=DEV)
     ops.segment_mean(x.to(DEV), seg, o['seg_label'], o['seg_start'], o['seg_len'], nseg)
+    # streaming two-pass kernel (workspace given), fp32 and bf16 rows
+    ws = torch.empty(ops.segment_mean_ws(B, slot, E), device=DEV)
+    seg_s = torch.zeros(B, slot, E, device=DEV)
+    ops.segment_mean(x.to(DEV), seg_s, o['seg_label'], o['seg_start'], o['seg_len'], nseg, ws=ws)
+    seg_s2 = torch.zeros(B, slot, E, device=DEV)
+    ops.segment_mean(x.to(DEV), seg_s2, o['seg_label'], o['seg_start'], o['seg_len'], nseg, ws=ws)
+    assert torch.equal(seg_s, seg_s2)
+    x16 = x.to(torch.bfloat16)
+    seg_h = torch.zeros(B, slot, E, device=DEV, dtype=torch.bfloat16)
+    ops.segment_mean(x16.to(DEV), seg_h, o['seg_label'], o['seg_start'], o['seg_len'], nseg, ws=ws)
     for b, T in enumerate(lens):
         lab, start, slen = O.run_length(pred[b, :T].numpy())
         S = len(slen)
@@ -237,6 +247,10 @@ def test_tdu_segment_and_mean():
         assert np.array_equal(o['seg_center'][b, :S].cpu().numpy(), (start + start + slen - 1) // 2)
         ref = torch.zeros(S, E).index_add_(0, torch.from_numpy(lab), x[b, :T]) / torch.from_numpy(slen)[:, None]
         close(seg[b, :S], ref, rtol=1e-4, atol=1e-5)
+        close(seg_s[b, :S], ref, rtol=1e-4, atol=1e-5)
+        ref16 = torch.zeros(S, E).index_add_(0, torch.from_numpy(lab), x16[b, :T].float()) / torch.from_numpy(slen)[:, None]
+        close(seg_h[b, :S].float(), ref16, rtol=1e-2, atol=1e-2)
+        assert bool((seg_s[b, S:] == 0).all())
     # determinism: bit-identical on a second run
     seg2 = torch.zeros(B, slot, E, device=DEV)
     ops.segment_mean(x.to(DEV), seg2, o['seg_label'], o['seg_start'], o['seg_len'], nseg)
