@@ -452,12 +452,19 @@ __global__ void __launch_bounds__(256) col_apply_partial_kernel(const float* __r
 constexpr int CAM_MT = 5, CAM_TOK = CAM_MT * 16, CAM_E = 256, CAM_TR = 64;
 constexpr int CAM_XS = CAM_E * 2 + 16;      // bytes per staged row (padded: conflict-free ldmatrix)
 constexpr int CAM_PS = CAM_TR * 2 + 16;     // bytes per token row of the probability tile
+constexpr int CAM_SMEM = 2 * CAM_TR * CAM_XS + CAM_TOK * CAM_PS + 2 * CAM_TOK * 4;
 __global__ void __launch_bounds__(256) col_apply_mma_kernel(const float* __restrict__ L, int ldl, const float* __restrict__ stats,
                                                             const __nv_bfloat16* __restrict__ X, int ldx, float* __restrict__ part,
                                                             float* __restrict__ P, int ldp, int slot,
                                                             const int32_t* __restrict__ len, int M, int E, int nsplit, int etiles) {
-    __shared__ __align__(16) uint8_t Xs[CAM_TR * CAM_XS];
-    __shared__ __align__(16) uint8_t Pt[CAM_TOK * CAM_PS];
+    // The rows tile is double-buffered with cp.async and the logits of the next stage are prefetched into registers, so the
+    // global loads of stage s+1 are in flight under the MMAs of stage s (ncu: the single-buffered version stalled 67 % of its
+    // issue slots on the loads, at 2 CTAs per SM).
+    extern __shared__ __align__(16) uint8_t cam_smem[];
+    uint8_t* Xs = cam_smem;                                      // [2][64 rows][CAM_XS]
+    uint8_t* Pt = cam_smem + 2 * CAM_TR * CAM_XS;                // [80 tokens][CAM_PS]
+    float* st_mx = reinterpret_cast<float*>(Pt + CAM_TOK * CAM_PS);
+    float* st_inv = st_mx + CAM_TOK;
     const int sp = blockIdx.x, b = blockIdx.z;
     const int mc = blockIdx.y / etiles, et = blockIdx.y % etiles;
     const int len_b = len ? min(len[b], slot) : slot;
@@ -466,6 +473,11 @@ __global__ void __launch_bounds__(256) col_apply_mma_kernel(const float* __restr
     const int r1 = min(r0 + SPLIT_ROWS, len_b);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int m0 = mc * CAM_TOK, e0 = et * CAM_E;
+    if (tid < CAM_TOK) {
+        const bool ok = m0 + tid < M;
+        st_mx[tid] = ok ? stats[((size_t)b * M + m0 + tid) * 2] : 0.f;
+        st_inv[tid] = ok ? stats[((size_t)b * M + m0 + tid) * 2 + 1] : 0.f;
+    }
     float acc[CAM_MT][4][4];
 #pragma unroll
     for (int i = 0; i < CAM_MT; ++i)
@@ -476,29 +488,58 @@ __global__ void __launch_bounds__(256) col_apply_mma_kernel(const float* __restr
     const uint32_t a_lane = pt_u32 + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * CAM_PS + (uint32_t)(lane >> 4) * 16u;
     const uint32_t b_lane = xs_u32 + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * CAM_XS + (uint32_t)(w * 32 + (lane >> 4) * 8) * 2u;
 
-    for (int t0 = r0; t0 < r1; t0 += CAM_TR) {
+    // logits: thread -> one token (tid % 80; threads 240..255 idle) and rows tid / 80 + 3 k: cheap incremental addressing
+    constexpr int LPT = (CAM_TR + 2) / 3;                        // 22 rows per thread and stage
+    const int lmm = tid % CAM_TOK, lr0 = tid / CAM_TOK;
+    const bool lactive = tid < 3 * CAM_TOK && m0 + lmm < M;
+    float lreg[LPT];
+    auto load_logits = [&](int t0) {
         const int nr = min(CAM_TR, r1 - t0);
-        __syncthreads();
-        // probabilities of this stage, bf16, token-major
-        for (int i = tid; i < CAM_TR * CAM_TOK; i += 256) {
-            const int r = i / CAM_TOK, mm = i % CAM_TOK;
-            float p = 0.f;
-            if (r < nr && m0 + mm < M) {
-                const size_t row = (size_t)b * slot + t0 + r;
-                const float* st = stats + ((size_t)b * M + m0 + mm) * 2;
-                p = __expf(L[row * ldl + m0 + mm] - st[0]) * st[1];
-                if (P != nullptr && et == 0) P[row * ldp + m0 + mm] = p;
+        const float* lp = L + ((size_t)b * slot + t0 + lr0) * ldl + m0 + lmm;
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) lreg[k] = (lactive && lr0 + 3 * k < nr) ? lp[(size_t)(3 * k) * ldl] : -INFINITY;
+    };
+    auto issue_rows = [&](int t0, int buf) {                     // 64 rows x 256 channels, 16-byte cp.async; rows past the end zero-filled
+        const int nr = min(CAM_TR, r1 - t0);
+#pragma unroll
+        for (int k = 0; k < CAM_TR * (CAM_E / 8) / 256; ++k) {
+            const int i = tid + k * 256, r = i / (CAM_E / 8), c = i % (CAM_E / 8);
+            const bool ok = r < nr && e0 + c * 8 < E;
+            const __nv_bfloat16* src = X + ((size_t)b * slot + t0 + (ok ? r : 0)) * ldx + (ok ? e0 + c * 8 : 0);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xs_u32 + (uint32_t)(buf * CAM_TR * CAM_XS + r * CAM_XS + c * 16)),
+                         "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue_rows(r0, 0);
+    load_logits(r0);
+    __syncthreads();                                             // stats in shared memory
+    int buf = 0;
+    for (int t0 = r0; t0 < r1; t0 += CAM_TR, buf ^= 1) {
+        const int nr = min(CAM_TR, r1 - t0);
+        // probabilities of this stage, bf16, token-major (the previous stage's MMAs are done: trailing barrier)
+        if (tid < 3 * CAM_TOK) {
+            const float smx = st_mx[lmm], sinv = st_inv[lmm];
+#pragma unroll
+            for (int k = 0; k < LPT; ++k) {
+                const int r = lr0 + 3 * k;
+                if (r < CAM_TR) {
+                    const float p = __expf(lreg[k] - smx) * sinv;            // exp(-inf) = 0 past the end / beyond M
+                    if (P != nullptr && et == 0 && r < nr && lactive) P[((size_t)b * slot + t0 + r) * ldp + m0 + lmm] = p;
+                    *reinterpret_cast<__nv_bfloat16*>(Pt + lmm * CAM_PS + r * 2) = __float2bfloat16_rn(p);
+                }
             }
-            *reinterpret_cast<__nv_bfloat16*>(Pt + mm * CAM_PS + r * 2) = __float2bfloat16_rn(p);
         }
-        // rows tile: 64 rows x 256 channels, 16-byte chunks; rows past the split end are zero (they may hold anything)
-        for (int i = tid; i < CAM_TR * (CAM_E / 8); i += 256) {
-            const int r = i / (CAM_E / 8), c = i % (CAM_E / 8);
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (r < nr && e0 + c * 8 < E) v = *reinterpret_cast<const uint4*>(X + ((size_t)b * slot + t0 + r) * ldx + e0 + c * 8);
-            *reinterpret_cast<uint4*>(Xs + r * CAM_XS + c * 16) = v;
+        const bool more = t0 + CAM_TR < r1;
+        if (more) {
+            issue_rows(t0 + CAM_TR, buf ^ 1);
+            load_logits(t0 + CAM_TR);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        const uint32_t b_cur = b_lane + (uint32_t)(buf * CAM_TR * CAM_XS);
 #pragma unroll
         for (int ks = 0; ks < CAM_TR / 16; ++ks) {
             uint32_t bf[4][2];
@@ -506,7 +547,7 @@ __global__ void __launch_bounds__(256) col_apply_mma_kernel(const float* __restr
             for (int jj = 0; jj < 2; ++jj)
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                              : "=r"(bf[2 * jj][0]), "=r"(bf[2 * jj][1]), "=r"(bf[2 * jj + 1][0]), "=r"(bf[2 * jj + 1][1])
-                             : "r"(b_lane + (uint32_t)(ks * 16) * CAM_XS + (uint32_t)jj * 32u));
+                             : "r"(b_cur + (uint32_t)(ks * 16) * CAM_XS + (uint32_t)jj * 32u));
 #pragma unroll
             for (int i = 0; i < CAM_MT; ++i) {
                 uint32_t a[4];
@@ -520,6 +561,7 @@ __global__ void __launch_bounds__(256) col_apply_mma_kernel(const float* __restr
                                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bf[j][0]), "r"(bf[j][1]));
             }
         }
+        __syncthreads();                                         // Pt and the other rows buffer are free again
     }
 #pragma unroll
     for (int i = 0; i < CAM_MT; ++i)
@@ -649,7 +691,12 @@ extern "C" int factk_col_softmax_apply(const float* L, int ldl, const void* X, i
     col_stats_combine_kernel<<<B, 256, 0, st>>>(sp, stats, slot, len, M, ns);
     if (x_dtype == FACTK_BF16 && (E % 8) == 0 && (ldx % 8) == 0 && aligned16(X)) {
         const int etiles = (E + CAM_E - 1) / CAM_E, mchunks = (M + CAM_TOK - 1) / CAM_TOK;
-        col_apply_mma_kernel<<<dim3(ns, mchunks * etiles, B), 256, 0, st>>>(L, ldl, stats, reinterpret_cast<const __nv_bfloat16*>(X), ldx,
+        static bool cam_attr = false;
+        if (!cam_attr) {
+            cudaFuncSetAttribute(col_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAM_SMEM);
+            cam_attr = true;
+        }
+        col_apply_mma_kernel<<<dim3(ns, mchunks * etiles, B), 256, CAM_SMEM, st>>>(L, ldl, stats, reinterpret_cast<const __nv_bfloat16*>(X), ldx,
                                                                            part, P, ldp, slot, len, M, E, ns, etiles);
     } else {
         const int etiles = (E + 127) / 128, mtiles = (M + 31) / 32;
