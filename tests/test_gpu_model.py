@@ -289,3 +289,13 @@ def test_full_size_batch_invariance_and_determinism():
         assert np.array_equal(alone[0]['pred'], full[i]['pred']), i
         assert torch.equal(l1[0], lf[i]), (i, float((l1[0] - lf[i]).abs().max()))
         assert alone[0]['pred'].shape == (lens[i],)
+
+
+def test_sweep_shard_forward_gather_metrics():
+    """tools/sweep.py at world size 1: length-balanced shard -> pipelined forward -> prediction gather -> metrics dict."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import sweep
+    out = sweep.run(n_videos=5, batch=2, t_min=130, t_max=400)
+    assert out['videos'] == 5 and out['frames'] > 0 and out['frames_per_s'] > 0
+    for k in ('Edit', 'AccB', 'Acc', 'F1@0.10', 'F1@0.25', 'F1@0.50'):
+        assert k in out['metrics'] and 0.0 <= out['metrics'][k] <= 100.0
