@@ -58,7 +58,9 @@ __device__ __forceinline__ uint32_t gm_mapa(uint32_t local_addr, uint32_t rank) 
 }
 
 constexpr int GM_PART = 4 * GM_NV * GM_PSTRIDE;                                  // floats per partial-sum buffer
-constexpr int gm_smem_bytes(int nc) { return nc * 2 * GM_HBUF + nc * 2 * GM_PART * 4; }   // dynamic shared memory
+constexpr int GM_GDEPTH = 6;                                                      // input-gate ring: loads issued 5 steps ahead
+constexpr int GM_GRING = GM_GDEPTH * 3 * GM_THREADS * 8;                          // bytes per chain: [depth][gate][thread] float2
+constexpr int gm_smem_bytes(int nc) { return nc * 2 * GM_HBUF + nc * 2 * GM_PART * 4 + nc * GM_GRING; }   // dynamic shared memory
 
 // GM_NC = independent 8-video groups (chains) interleaved on one cluster.  With two chains, while the hidden state of chain A travels through distributed shared memory (~700 cycles), the
 // cluster computes the step of chain B (~600 cycles), so a pair of steps costs about what one step costs alone.
@@ -72,6 +74,7 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
     // K-slice partial sums [chain][step parity][warp][video][gate row]: parity-double-buffered because a warp only waits for
     // the two CTAs that own its K slice, so it may start the next step while other warps still read the partials of this one
     float* part = reinterpret_cast<float*>(gm_smem + GM_NC * 2 * GM_HBUF);
+    uint8_t* gring = gm_smem + GM_NC * 2 * GM_HBUF + GM_NC * 2 * GM_PART * 4;        // [chain][depth][gate][thread] float2
 
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -126,45 +129,39 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
         maxAll = max(maxAll, maxS[c]);
         hprev[c] = g_r[c] = g_z[c] = g_n[c] = make_float2(0.f, 0.f);
     }
-    // The input gates stream from HBM (B x S x 6 Hh floats): the loads for step t+1 are issued one step ahead, and the lines
-    // of step t+GM_PF are pulled into L2 so that those loads hit L2 (an HBM miss costs about one whole step).  Running
-    // pointers (one add per step) keep the address arithmetic off the step's critical path.
-    constexpr int GM_PF = 8;
+    // The input gates stream from HBM (B x S x 6 Hh floats).  They are fetched GM_GDEPTH-1 steps ahead with cp.async into a
+    // per-thread ring in shared memory: a real load cannot be dropped the way an L2 prefetch hint is under load (with 16
+    // clusters the hinted version lost 0.3 us per step to HBM misses), and five steps (~4 us) cover the HBM latency.
+    // Running pointers (one add per step) keep the address arithmetic off the step's critical path.
     const long long gstep = dir ? -(long long)gstride : (long long)gstride;     // segment order: forward / reverse
     const long long ostep = dir ? -(long long)ldo : (long long)ldo;
-    const float* gp[GM_NC];          // input gates of step t (this thread's video / units)
+    const float* gp[GM_NC];          // input gates of the NEXT step to fetch (this thread's video / units)
     long long oidx[GM_NC];           // output element index of step t
+    int gfetched[GM_NC];             // steps fetched so far
+    const uint32_t gring_u32 = (uint32_t)__cvta_generic_to_shared(gring) + (uint32_t)tid * 8u;
 #pragma unroll
     for (int c = 0; c < GM_NC; ++c) {
         const int s0 = dir ? myS[c] - 1 : 0;
         gp[c] = gi + ((size_t)vb[c] * slot + (myS[c] > 0 ? s0 : 0)) * gstride + (size_t)dir * 3 * GM_HH + unit;
         oidx[c] = ((long long)vb[c] * slot + (myS[c] > 0 ? s0 : 0)) * (long long)ldo + (long long)dir * GM_HH + unit;
+        gfetched[c] = 0;
     }
-    // load the gates of step t into registers and prefetch those of step t + GM_PF; gp[c] must point at step t
-    auto load_gi = [&](int c, int t) {
-        if (t < myS[c]) {
-            g_r[c] = __ldg(reinterpret_cast<const float2*>(gp[c]));
-            g_z[c] = __ldg(reinterpret_cast<const float2*>(gp[c] + GM_HH));
-            g_n[c] = __ldg(reinterpret_cast<const float2*>(gp[c] + 2 * GM_HH));
-            if (t + GM_PF < myS[c] && (up & 3) == 0) {                     // one prefetch per 32-byte sector
-                const float* p = gp[c] + GM_PF * gstep;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + GM_HH));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 2 * GM_HH));
-            }
-        }
-    };
+    // fetch the gates of step gfetched[c] into ring slot gfetched[c] % depth; one commit group per call (possibly empty)
+    auto fetch_gi = [&](int c) {
+        if (gfetched[c] < myS[c]) {
+            const uint32_t dst = gring_u32 + (uint32_t)(c * GM_GRING + (gfetched[c] % GM_GDEPTH) * 3 * GM_THREADS * 8);
 #pragma unroll
-    for (int c = 0; c < GM_NC; ++c) {
-        if ((up & 3) == 0)
-            for (int t = 1; t < GM_PF && t < myS[c]; ++t) {                // warm the prefetch window
-                const float* p = gp[c] + t * gstep;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + GM_HH));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 2 * GM_HH));
-            }
-        load_gi(c, 0);
-    }
+            for (int g = 0; g < 3; ++g)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)(g * GM_THREADS * 8)), "l"(gp[c] + g * GM_HH) : "memory");
+            gp[c] += gstep;
+        }
+        ++gfetched[c];
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // the chains share one cp.async group sequence: prologue fetches GM_GDEPTH-1 steps of every chain, chain-major per step
+    for (int d = 0; d < GM_GDEPTH - 1; ++d)
+#pragma unroll
+        for (int c = 0; c < GM_NC; ++c) fetch_gi(c);
     // exchange: lanes (n, n+8, n+16, n+24) of a warp hold 8 consecutive units of video n; lane group j = lane / 8 stores that
     // 16-byte packet into the next-step buffer of CTAs 2j and 2j+1
     const uint32_t xoff = (uint32_t)n * GM_HSTRIDE + (uint32_t)(rank * GM_U + 8 * w) * 2u;
@@ -183,7 +180,10 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
         const int cur = t & 1;
 #pragma unroll
         for (int c = 0; c < GM_NC; ++c) {
-            if (t >= maxS[c]) continue;          // uniform over the cluster: this chain has finished everywhere
+            if (t >= maxS[c]) {                  // uniform over the cluster: this chain has finished everywhere
+                asm volatile("cp.async.commit_group;" ::: "memory");   // keep one group per (step, chain)
+                continue;
+            }
             if (dbg_on && t < 64) dbg[t * 16 + c * 8 + 0] = clock64();
             // ---- B fragments of this warp's K slice: spin until every word has landed, then mark the words empty again
             uint32_t b[4][2];
@@ -238,6 +238,16 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
                 a_r.x += x0.x; a_r.y += x0.y; a_z.x += x1.x; a_z.y += x1.y; a_n.x += x2.x; a_n.y += x2.y;
             }
             const bool live = t < myS[c];
+            // groups are committed chain-major, one per (step, chain): everything up to (t, c) must have landed
+            if (GM_NC == 1) asm volatile("cp.async.wait_group %0;" ::"n"(GM_GDEPTH - 2) : "memory");
+            else if (c == 0) asm volatile("cp.async.wait_group %0;" ::"n"(2 * (GM_GDEPTH - 2) + 1) : "memory");
+            else asm volatile("cp.async.wait_group %0;" ::"n"(2 * (GM_GDEPTH - 2)) : "memory");
+            if (live) {
+                const uint8_t* gsrc = gring + (size_t)c * GM_GRING + (size_t)(t % GM_GDEPTH) * 3 * GM_THREADS * 8 + (size_t)tid * 8;
+                g_r[c] = *reinterpret_cast<const float2*>(gsrc);
+                g_z[c] = *reinterpret_cast<const float2*>(gsrc + GM_THREADS * 8);
+                g_n[c] = *reinterpret_cast<const float2*>(gsrc + 2 * GM_THREADS * 8);
+            }
             float2 hn = hprev[c];               // finished videos re-send their last state: every word is written every step
             if (live) {
                 const float r0 = gm_sigmoid(g_r[c].x + a_r.x), r1 = gm_sigmoid(g_r[c].y + a_r.y);
@@ -260,9 +270,8 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
                 if (o_dtype == FACTK_BF16) *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(out) + oidx[c]) = gm_pack(y0, y1);
                 else *reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + oidx[c]) = make_float2(y0, y1);
                 oidx[c] += ostep;
-                gp[c] += gstep;
             }
-            load_gi(c, t + 1);
+            fetch_gi(c);                        // step t + GM_GDEPTH - 1 of this chain
             if (dbg_on && t < 64) dbg[t * 16 + c * 8 + 5] = clock64();
         }
     }
