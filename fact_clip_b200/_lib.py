@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libfactk.so')
 
 F32, BF16 = 0, 1
-MAX_SRC = 4
+MAX_SRC = 6
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float

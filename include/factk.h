@@ -30,7 +30,7 @@ extern "C" {
 
 #define FACTK_F32 0
 #define FACTK_BF16 1
-#define FACTK_MAX_SRC 4
+#define FACTK_MAX_SRC 6
 
 #define FACTK_OK 0
 #define FACTK_ERR_ARG (-1)
