@@ -104,6 +104,67 @@ __global__ void __launch_bounds__(EV_WARPS * 32) fuse_eval_kernel(const float* _
     }
 }
 
+
+// Block._eval_w_transcript (models/blocks.py:263-275), FACT.trans models: the tokens ARE the video's transcript, so the
+// fusion runs over the N transcript positions: prob[n] = (1-w) softmax_n(attn[t, :N]) + w softmax_c(frame logits)[transcript[n]],
+// pred[t] = transcript[argmax_n prob].  One warp per frame.
+__global__ void __launch_bounds__(EV_WARPS * 32) fuse_eval_transcript_kernel(const float* __restrict__ attn, int lda, int attn_slot,
+                                                                             const int32_t* __restrict__ seg_label,
+                                                                             const float* __restrict__ flogit, int ldf, float weight,
+                                                                             const int32_t* __restrict__ transcript, int ldt,
+                                                                             const int32_t* __restrict__ ntr, int64_t* __restrict__ pred,
+                                                                             int slot, const int32_t* __restrict__ len, int C,
+                                                                             int chunks_per_video) {
+    const int b = blockIdx.x / chunks_per_video;
+    const int t0 = (blockIdx.x % chunks_per_video) * EV_FRAMES;
+    const int T = len ? min(len[b], slot) : slot;
+    if (t0 >= T) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int N = ntr[b];
+    const int32_t* tr = transcript + (size_t)b * ldt;
+    for (int f = w; f < EV_FRAMES; f += EV_WARPS) {
+        const int t = t0 + f;
+        if (t >= T) break;
+        const size_t row = (size_t)b * slot + t;
+        const float* fl = flogit + row * (size_t)ldf;
+        float fm = -INFINITY;
+        for (int c = lane; c < C; c += 32) fm = fmaxf(fm, fl[c]);
+        fm = warp_max(fm);
+        float fs = 0.f;
+        for (int c = lane; c < C; c += 32) fs += __expf(fl[c] - fm);
+        fs = 1.f / warp_sum(fs);
+        const float* ar = attn + ((size_t)b * attn_slot + (seg_label ? seg_label[row] : t)) * (size_t)lda;
+        float am = -INFINITY;
+        for (int n = lane; n < N; n += 32) am = fmaxf(am, ar[n]);
+        am = warp_max(am);
+        float as = 0.f;
+        for (int n = lane; n < N; n += 32) as += __expf(ar[n] - am);
+        as = 1.f / warp_sum(as);
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int n = lane; n < N; n += 32) {
+            const float p = (1.f - weight) * (__expf(ar[n] - am) * as) + weight * (__expf(fl[tr[n]] - fm) * fs);
+            if (p > best) { best = p; bi = n; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) pred[row] = (int64_t)tr[bi < N ? bi : 0];
+    }
+}
+
+// Token initialisation of FACT.trans models (models/blocks.py:74-79): out[n, :] = action_embed[transcript[n], :] + pe[n, :].
+__global__ void embed_tokens_kernel(const float* __restrict__ embed, int lde, const int32_t* __restrict__ transcript,
+                                    const float* __restrict__ pe, int ldpe, float* __restrict__ out, int ldo, int N, int A) {
+    const int n = blockIdx.x;
+    if (n >= N) return;
+    const int cls = transcript[n];
+    for (int a = threadIdx.x; a < A; a += blockDim.x) out[(size_t)n * ldo + a] = embed[(size_t)cls * lde + a] + pe[(size_t)n * ldpe + a];
+}
+
 }  // namespace factk
 
 using namespace factk;
@@ -118,4 +179,21 @@ extern "C" int factk_fuse_eval(const float* action_clogit, const float* attn, in
     fuse_eval_kernel<<<(unsigned)(cpv * B), EV_WARPS * 32, 0, (cudaStream_t)stream>>>(
         action_clogit, attn, lda, attn_slot, seg_label, flogit, ldf, weight, pred, slot, len, M, C, cpv);
     return check_launch("factk_fuse_eval");
+}
+
+extern "C" int factk_fuse_eval_transcript(const float* attn, int lda, int attn_slot, const int32_t* seg_label, const float* flogit,
+                                          int ldf, float weight, const int32_t* transcript, int ldt, const int32_t* ntr,
+                                          int64_t* pred, int B, int slot, const int32_t* len, int C, void* stream) {
+    FACTK_REQUIRE(attn && flogit && transcript && ntr && pred && B > 0 && slot > 0 && C > 0, "factk_fuse_eval_transcript: bad args");
+    const int cpv = (slot + EV_FRAMES - 1) / EV_FRAMES;
+    fuse_eval_transcript_kernel<<<(unsigned)(cpv * B), EV_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        attn, lda, attn_slot, seg_label, flogit, ldf, weight, transcript, ldt, ntr, pred, slot, len, C, cpv);
+    return check_launch("factk_fuse_eval_transcript");
+}
+
+extern "C" int factk_embed_tokens(const float* embed, int lde, const int32_t* transcript, const float* pe, int ldpe, float* out,
+                                  int ldo, int N, int A, void* stream) {
+    FACTK_REQUIRE(embed && transcript && pe && out && N > 0 && A > 0, "factk_embed_tokens: bad args");
+    embed_tokens_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(embed, lde, transcript, pe, ldpe, out, ldo, N, A);
+    return check_launch("factk_embed_tokens");
 }

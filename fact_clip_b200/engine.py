@@ -226,10 +226,13 @@ class FactEngine:
 
     def sca_decoder(self, pfx, bc, frame, tag):
         """SCADecoder over SCALayer (models/basic.py:542-557, 494-523): tokens attend frames. -> [B,M,H] fp32."""
-        B, slot, M, A, H, nh = self.B, self.slot, self.hp['ntoken'], bc['a_dim'], bc['hid_dim'], bc['a_nhead']
-        qpos = self.p('action_query')[:, 0]
+        B, slot, M, A, H, nh = self.B, self.slot, self.ntok, bc['a_dim'], bc['hid_dim'], bc['a_nhead']
+        qpos = self.qpos()
         tgt = self.buf('tok_x', (B, M, A))
-        tgt.zero_()
+        if self.action_init is None:
+            tgt.zero_()
+        else:
+            tgt.copy_(self.action_init)
         t = self.buf('tok_t', (B, M, A))
         kv = self.buf('sca_kv', (B, slot, 2 * A), self.act)
         ws = self.buf('attn_ws', (max(ops.attn_rows_ws(B, slot, M, nh, A // nh), 1),))
@@ -267,8 +270,8 @@ class FactEngine:
 
     def sa_decoder(self, pfx, bc, x, tag):
         """SADecoder over SALayer (models/basic.py:578-593, 429-452). x: [B,M,A] fp32 -> [B,M,H] fp32."""
-        B, M, A, H, nh = self.B, self.hp['ntoken'], bc['a_dim'], bc['hid_dim'], bc['a_nhead']
-        qpos = self.p('action_query')[:, 0]
+        B, M, A, H, nh = self.B, self.ntok, bc['a_dim'], bc['hid_dim'], bc['a_nhead']
+        qpos = self.qpos()
         t = self.buf('tok_t', (B, M, A))
         for i in range(bc['a_layers']):
             q = f'{pfx}layers.{i}.'
@@ -283,7 +286,7 @@ class FactEngine:
 
     def token_splice(self, action, tag):
         C = self.hp['n_classes']
-        clogit = self.buf('aclogit_' + tag, (self.B, self.hp['ntoken'], C + 1))
+        clogit = self.buf('aclogit_' + tag, (self.B, self.ntok, C + 1))
         ops.softmax_splice(action, C + 1, clogit)
         return clogit
 
@@ -291,9 +294,9 @@ class FactEngine:
     def f2a(self, pfx, bc, rows, rlen, pos_idx, action, tag, want_attn):
         """X2Y_map with X = rows (frames or segments), Y = tokens (basic.py:349-389). -> tokens [B,M,A] fp32,
         attn_logit [B,slot,Mp] (row = x, col = token), attn (or None)."""
-        B, slot, M, A, H = self.B, self.slot, self.hp['ntoken'], bc['a_dim'], bc['hid_dim']
+        B, slot, M, A, H = self.B, self.slot, self.ntok, bc['a_dim'], bc['hid_dim']
         Mp = _round_up(M, 4)
-        qpos = self.p('action_query')[:, 0]
+        qpos = self.qpos()
         alpha = 1.0 / math.sqrt(H)
         yq = self.buf('x2y_tokH', (B, M, H))
         self.lin(action, self.p(pfx + 'Y_Q.weight'), H, yq, pos=qpos, bias=self.p(pfx + 'Y_Q.bias'))
@@ -318,9 +321,9 @@ class FactEngine:
     def a2f(self, pfx, bc, action, rows, rlen, pos_idx, tag):
         """X2Y_map with X = tokens, Y = rows (frames or segments). -> rows [B,slot,F] act dtype,
         attn_logit [B,slot,Mp], attn [B,slot,Mp] (row = y, col = token)."""
-        B, slot, M, F, H = self.B, self.slot, self.hp['ntoken'], bc['f_dim'], bc['hid_dim']
+        B, slot, M, F, H = self.B, self.slot, self.ntok, bc['f_dim'], bc['hid_dim']
         Mp = _round_up(M, 4)
-        qpos = self.p('action_query')[:, 0]
+        qpos = self.qpos()
         alpha = 1.0 / math.sqrt(H)
         xk = self.buf('x2y_tokH', (B, M, H))
         self.lin(action, self.p(pfx + 'X_K.weight'), H, xk, pos=qpos, bias=self.p(pfx + 'X_K.bias'))
@@ -408,6 +411,11 @@ class FactEngine:
         return frame, action
 
     # ------------------------------------------------------------------ whole forward
+    def qpos(self):
+        """Query position of the action tokens: the learned action_query, or none for FACT.trans models (blocks.py:79 sets
+        it to zero there; the tokens themselves are embed(transcript) + positional encoding)."""
+        return None if self.hp['trans'] else self.p('action_query')[:, 0]
+
     def _feature_dtype(self, seqs):
         """fp32 features (the reference's format, dataset.py:12-21) or, in bf16 mode, features already stored as bf16: half the
         host->device bytes (input staging) and the input projection runs as a bf16 tensor-core GEMM."""
@@ -419,9 +427,19 @@ class FactEngine:
         raise TypeError(f'features must all be float32 (or all bfloat16 in bf16 compute mode), got {sorted(map(str, dts))}')
 
     @torch.no_grad()
-    def run(self, seqs, forced_preds=None, keep=False):
-        """seqs: list of (T_i, in_dim) fp32 tensors, CUDA or (pinned) host.  Synchronous with respect to the stream."""
+    def run(self, seqs, forced_preds=None, keep=False, transcript=None):
+        """seqs: list of (T_i, in_dim) fp32 tensors, CUDA or (pinned) host.  Synchronous with respect to the stream.
+        transcript (FACT.trans models, one video per call): int32 CUDA tensor [N] of the video's action sequence."""
         self._refresh_weights()
+        self.ntok, self.action_init, self.transcript = self.hp['ntoken'], None, None
+        if self.hp['trans']:
+            assert transcript is not None and len(seqs) == 1, 'FACT.trans: one video per call, with its transcript'
+            N, A = int(transcript.numel()), self.hp['blocks'][0]['a_dim']
+            self.ntok, self.transcript = N, transcript.to(torch.int32).contiguous()
+            n_pe = 1000 if N <= 1000 else N + 10        # basic.py:125-127: the table regrows past max_len
+            pe = self.derived(('tok_pe', A, n_pe), lambda: _pos_table(A, n_pe, self.dev))
+            self.action_init = self.buf('tok_init', (1, N, A))
+            ops.embed_tokens(self.p('action_embed.weight'), self.transcript, pe, self.action_init)
         lengths = [int(s.shape[0]) for s in seqs]
         B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
         x = self.buf('input', (B, slot, D), self._feature_dtype(seqs))
@@ -437,6 +455,9 @@ class FactEngine:
         buffers and overlaps the kernels of the previously submitted batch; the predictions are copied to pinned
         host memory asynchronously.  Returns a handle; ``handle.result()`` blocks until this batch is done."""
         self._refresh_weights()
+        if self.hp['trans']:
+            raise NotImplementedError('FACT.trans models run one video per call through forward() (the transcript sets the token count)')
+        self.ntok, self.action_init, self.transcript = self.hp['ntoken'], None, None
         lengths = [int(s.shape[0]) for s in seqs]
         B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
         k = self._submits % 2
@@ -508,7 +529,7 @@ class FactEngine:
             for t in self._zbufs.values():
                 t.zero_()
             self._len_sig = tuple(lengths)
-        B, slot, M, C, H = self.B, self.slot, hp['ntoken'], hp['n_classes'], hp['blocks'][0]['hid_dim']
+        B, slot, M, C, H = self.B, self.slot, self.ntok, hp['n_classes'], hp['blocks'][0]['hid_dim']
         self.frame_pos = None
         if hp['fpos']:
             self.frame_pos = self.derived(('pe', slot, H), lambda: _pos_table(H, slot, self.dev))
@@ -551,7 +572,15 @@ class FactEngine:
         else:
             flogit = last['frame_clogit']
         pred64 = pred_out if pred_out is not None else self.buf('pred64', (B, slot), torch.int64)
-        if 'a2f_attn' in last:
+        if self.hp['trans'] and 'clip_logit' not in out:
+            # Block._eval_w_transcript (blocks.py:263-275); FACT_CLIP with text embeddings keeps the token / CLIP fusion
+            ntr = self.buf('ntr', (B,), torch.int32)
+            ntr.fill_(self.ntok)
+            seg = last.get('a2f_attn_seg')
+            ops.fuse_eval_transcript(seg if seg is not None else last['a2f_attn'], last['frame_clogit'], hp['mwt'],
+                                     self.transcript[None], ntr, pred64, C,
+                                     seg_label=last['seg_label'] if seg is not None else None, len=ln)
+        elif 'a2f_attn' in last:
             ops.fuse_eval(last['action_clogit'], last['a2f_attn'], flogit, hp['mwt'], pred64, M, C, len=ln)
         elif 'a2f_attn_seg' in last:
             ops.fuse_eval(last['action_clogit'], last['a2f_attn_seg'], flogit, hp['mwt'], pred64, M, C,

@@ -129,9 +129,11 @@ class _FactBase(nn.Module):
         base = cfg.Bi
         self.frame_pe = basic.PositionalEncoding(base.hid_dim, max_len=10000, empty=(not cfg.FACT.fpos))
         self.channel_masking_dropout = nn.Dropout2d(p=cfg.FACT.cmr)
-        if cfg.FACT.trans:
-            raise NotImplementedError('FACT.trans=True (transcript-conditioned model) is SURVEY 8(f) rank 4')
-        self.action_query = nn.Parameter(torch.randn([cfg.FACT.ntoken, 1, base.a_dim]))
+        if not cfg.FACT.trans:      # no transcript at training / inference: learned action queries (blocks.py:30-31)
+            self.action_query = nn.Parameter(torch.randn([cfg.FACT.ntoken, 1, base.a_dim]))
+        else:                       # transcript available: the tokens are its embedded actions (blocks.py:32-34)
+            self.action_pe = basic.PositionalEncoding(base.a_dim, max_len=1000)
+            self.action_embed = nn.Embedding(n_classes, base.a_dim)
         return base
 
     def _build_blocks(self, cfg, in_dim, n_classes, base):
@@ -164,21 +166,44 @@ class _FactBase(nn.Module):
     def forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
         if compute_loss or (self.training and torch.is_grad_enabled() and compute_loss):
             raise NotImplementedError('compute_loss=True (training step) is not built yet: SURVEY.md 8(f) rank 1')
-        dev = self.action_query.device
+        dev = next(self.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
         seqs = list(seq_list)        # CUDA tensors, or (pinned) host tensors copied straight into the packed batch
+        if self.cfg.FACT.trans:
+            return self._forward_with_transcripts(seqs, label_list, forced_preds)
         out = self.engine().run(seqs, forced_preds=forced_preds, keep=getattr(self, 'keep_attn', False))
         self._last = out
         pred = out['pred'].cpu().numpy()            # the one D2H sync of the call (blocks.py:900)
         self.stash_video(len(seqs) - 1)
         return [{'pred': pred[b, :T].copy()} for b, T in enumerate(out['lengths'])]
 
+    def _forward_with_transcripts(self, seqs, label_list, forced_preds=None):
+        """FACT.trans (blocks.py:74-79, 113-118): every video brings its own token count (the length of its transcript), so
+        the videos run one per call like the reference; the transcript is the run-length coding of the label sequence
+        (basic.py:38-54, vectorised: one unique_consecutive instead of a Python loop over the frames)."""
+        assert label_list is not None and len(label_list) == len(seqs), 'FACT.trans needs the frame labels of every video'
+        saves, keep, dev = [], getattr(self, 'keep_attn', False), next(self.parameters()).device
+        self._per_video = []
+        for i, (seq, label) in enumerate(zip(seqs, label_list)):
+            transcript = torch.unique_consecutive(torch.as_tensor(label).long()).to(dev)
+            forced = None if forced_preds is None else [[u[i]] for u in forced_preds]
+            out = self.engine().run([seq], forced_preds=forced, keep=keep, transcript=transcript)
+            pred = out['pred'].cpu().numpy()
+            saves.append({'pred': pred[0, :out['lengths'][0]].copy()})
+            if keep:        # the engine's buffers are reused by the next video: keep copies for stash_video(i)
+                self._per_video.append(_clone_tree(out))
+        self._last = out
+        self.stash_video(len(seqs) - 1)
+        return saves
+
     def submit(self, seq_list, label_list=None):
         """Asynchronous variant of ``forward`` for inference loops: enqueue the host->device copy (side stream,
         double-buffered), the kernels and the device->host copy of the predictions, and return a handle whose
         ``result()`` gives the same list ``forward`` returns.  Lets batch i+1's input copy overlap batch i's kernels."""
-        if self.action_query.device.type != 'cuda':
+        if self.cfg.FACT.trans:
+            raise NotImplementedError('FACT.trans models run one video per call through forward() (the transcript sets the token count)')
+        if next(self.parameters()).device.type != 'cuda':
             raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
         h = self.engine().submit(list(seq_list))
         self._last = h.out
@@ -188,7 +213,12 @@ class _FactBase(nn.Module):
         """Expose video ``b`` of the last batch through the reference's per-block attributes
         (blocks.py:305-309, 359-366, 473-483) as views -- shapes (T,1,C), (M,1,C+1), (1,T,M)..."""
         out = self._last
-        T, M = out['lengths'][b], self.cfg.FACT.ntoken
+        if self.cfg.FACT.trans:           # one engine call per video (see _forward_with_transcripts)
+            if getattr(self, '_per_video', None):
+                out, b = self._per_video[b], 0
+            else:
+                b = 0
+        T, M = out['lengths'][b], int(out['blocks'][0]['action_clogit'].shape[1])
         for blk, st in zip(self.block_list, out['blocks']):
             C = self.num_classes
             blk.frame_clogit = st['frame_clogit'][b, :T].unsqueeze(1)
@@ -215,6 +245,16 @@ class _FactBase(nn.Module):
 
     def save_model(self, fname):
         torch.save(self.state_dict(), fname)
+
+
+def _clone_tree(o):
+    if torch.is_tensor(o):
+        return o.clone()
+    if isinstance(o, dict):
+        return {k: _clone_tree(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return type(o)(_clone_tree(v) for v in o)
+    return o
 
 
 class FACT(_FactBase):

@@ -243,3 +243,20 @@ def fuse_eval(action_clogit, attn, flogit, weight, pred, M, C, seg_label=None, l
     _call('factk_fuse_eval', None, L.ptr(action_clogit), L.ptr(attn), _row_ld(attn) if attn is not None else 0,
            attn.shape[1] if attn is not None else 0, L.ptr(seg_label), flogit.data_ptr(), _row_ld(flogit),
            float(weight), pred.data_ptr(), B, slot, L.ptr(len), M, C, L.stream())
+
+
+def fuse_eval_transcript(attn, flogit, weight, transcript, ntr, pred, C, seg_label=None, len=None):
+    """transcript: int32 [B, ldt]; ntr: int32 [B] entries per video (FACT.trans models)."""
+    B, slot = flogit.shape[0], flogit.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_fuse_eval_transcript', None, attn.data_ptr(), _row_ld(attn), attn.shape[1], L.ptr(seg_label), flogit.data_ptr(),
+          _row_ld(flogit), float(weight), transcript.data_ptr(), transcript.stride(0), ntr.data_ptr(), pred.data_ptr(), B, slot,
+          L.ptr(len), C, L.stream())
+
+
+def embed_tokens(embed, transcript, pe, out):
+    """out[n] = embed[transcript[n]] + pe[n]  (fp32; transcript int32 [N])."""
+    N, A = out.shape[-2], out.shape[-1]
+    COUNTERS['launches'] += 1
+    _call('factk_embed_tokens', None, embed.data_ptr(), embed.stride(0), transcript.data_ptr(), pe.data_ptr(), pe.stride(0),
+          out.data_ptr(), _row_ld(out), N, A, L.stream())

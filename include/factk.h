@@ -218,6 +218,18 @@ int factk_fuse_eval(const float* action_clogit, const float* attn, int lda, int 
                     const int32_t* seg_label, const float* flogit, int ldf, float weight,
                     int64_t* pred, int B, int slot, const int32_t* len, int M, int C, void* stream);
 
+/* Block._eval_w_transcript (blocks.py:263-275), FACT.trans models (the tokens are the video's transcript): per frame
+ * prob[n] = (1 - weight) softmax_n(attn[row, :N]) + weight softmax_c(flogit)[transcript[n]], pred = transcript[argmax_n].
+ * attn fp32 [B][attn_slot][lda] (row = frame, or segment when seg_label != NULL); transcript int32 [B][ldt], ntr[b] entries. */
+int factk_fuse_eval_transcript(const float* attn, int lda, int attn_slot, const int32_t* seg_label,
+                               const float* flogit, int ldf, float weight,
+                               const int32_t* transcript, int ldt, const int32_t* ntr,
+                               int64_t* pred, int B, int slot, const int32_t* len, int C, void* stream);
+
+/* Token initialisation of FACT.trans models (blocks.py:74-79): out[n,:A] = embed[transcript[n],:A] + pe[n,:A]. */
+int factk_embed_tokens(const float* embed, int lde, const int32_t* transcript, const float* pe, int ldpe,
+                       float* out, int ldo, int N, int A, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

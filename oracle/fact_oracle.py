@@ -350,21 +350,41 @@ def fuse_eval(action_clogit, a2f_attn, fprob, weight):
 # whole model
 
 
-def forward_video(sd, hp, seq, clip=False, forced_preds=None, fast_gru=False):
+def transcript_of(label):
+    """basic.py:38-54 (torch_class_label_to_segment_label)[0]: the run-length transcript of a frame label sequence."""
+    return torch.unique_consecutive(torch.as_tensor(label).long())
+
+
+def eval_w_transcript(transcript, a2f_attn, frame_clogit, weight):
+    """blocks.py:263-275: frame-branch probability restricted to the transcript classes, softmax over the (already
+    normalised) token attention, mixture, argmax over the transcript positions."""
+    fprob = torch.softmax(frame_clogit, -1)[:, transcript]
+    aprob = torch.softmax(a2f_attn[:, :len(transcript)], -1)
+    return transcript[((1 - weight) * aprob + weight * fprob).argmax(1)]
+
+
+def forward_video(sd, hp, seq, clip=False, forced_preds=None, fast_gru=False, transcript=None):
     """FACT._forward_one_video + eval (blocks.py:56-88,118) or the FACT_CLIP equivalents
-    (blocks.py:610-675, 788-887), eval mode, ``FACT.trans`` False.
+    (blocks.py:610-675, 788-887), eval mode.  ``FACT.trans`` True needs ``transcript`` (blocks.py:74-79: the tokens are
+    action_embed(transcript) + action_pe, the query position is zero, and vanilla FACT ends in _eval_w_transcript).
 
     sd: reference-keyed state_dict (fp32 CPU tensors); seq: (T, in_dim).
     Returns a dict: 'blocks' (list of per-block stashes), 'pred' (T,) int64 and, for clip,
     'projected_frame_embeddings' (T,512), 'clip_logit' (T,C).
     """
-    assert not hp['trans'], 'FACT.trans=True is out of scope (SURVEY 8f rank 4)'
     C, H = hp['n_classes'], hp['blocks'][0]['hid_dim']
     T = seq.shape[0]
     frame_pos = positional_table(H, max(T, 1)) if hp['fpos'] else None        # basic.py:114-129
     # NB basic.py:93 leaves the table all-zero when FACT.fpos is False; adding zeros == no-op.
-    action_pos = sd['action_query'][:, 0]
-    frame, action = seq, torch.zeros_like(action_pos)
+    if hp['trans']:
+        assert transcript is not None, 'FACT.trans=True needs the transcript'
+        A = sd['action_embed.weight'].shape[1]
+        action = sd['action_embed.weight'][transcript] + positional_table(A, len(transcript))     # blocks.py:75-78
+        action_pos = torch.zeros_like(action)
+        frame = seq
+    else:
+        action_pos = sd['action_query'][:, 0]
+        frame, action = seq, torch.zeros_like(action_pos)
     out = {'blocks': []}
     u = 0
     for i, bc in enumerate(hp['blocks']):
@@ -387,7 +407,9 @@ def forward_video(sd, hp, seq, clip=False, forced_preds=None, fast_gru=False):
         fprob = torch.softmax(out['clip_logit'], -1)
     else:
         fprob = torch.softmax(last['frame_clogit'], -1)
-    if 'a2f_attn' in last:
+    if hp['trans'] and not (clip and 'text_embeddings' in sd):
+        out['pred'] = eval_w_transcript(transcript, last['a2f_attn'], last['frame_clogit'], hp['mwt'])
+    elif 'a2f_attn' in last:
         out['pred'] = fuse_eval(last['action_clogit'], last['a2f_attn'], fprob, hp['mwt'])
     else:   # a lone input block has no a2f attention; the reference would raise AttributeError
         out['pred'] = fprob.argmax(1)

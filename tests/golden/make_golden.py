@@ -34,6 +34,7 @@ CASES = [
     ('tiny_m2_iuUU', dict(f='m2', block='iuUU', F=32, A=64, H=64), False, [80], 5, 24),
     ('tiny_m2_iUU_fpos_clip', dict(f='m2', block='iUU', fpos=True), True, [64, 1, 3], 6, 24),
     ('tiny_m_iu', dict(f='m', block='iu', M=9), False, [50], 4, 16),
+    ('tiny_m_iuU_trans', dict(f='m', block='iuU', trans=True), False, [90, 41, 2], 6, 24),   # FACT.trans: tokens = transcript
 ]
 
 

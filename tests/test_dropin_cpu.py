@@ -78,8 +78,15 @@ def test_no_cpu_fallback():
         net([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)])
 
 
+def test_trans_variant_registers_reference_parameters():
+    """FACT.trans (blocks.py:32-34): action_pe + action_embed instead of action_query, same state_dict keys."""
+    net = FACT(C.tiny(trans=True), 24, 7)
+    keys = set(net.state_dict().keys())
+    assert 'action_embed.weight' in keys and 'action_pe.pe' in keys and 'action_query' not in keys
+    assert tuple(net.action_embed.weight.shape) == (7, 32)
+    with pytest.raises(NotImplementedError):
+        net.submit([torch.zeros(8, 24)])
+
+
 def test_unsupported_variants_raise():
     cfg = C.tiny()
-    cfg.FACT.trans = True
-    with pytest.raises(NotImplementedError):
-        FACT(cfg, 24, 7)

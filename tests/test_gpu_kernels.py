@@ -330,3 +330,28 @@ def test_fuse_eval_segment_gather():
                   seg_label=lab.int()[None].to(DEV))
     ref = O.fuse_eval(ac, attn_seg[lab], torch.softmax(fl, -1), 0.1)
     assert torch.equal(pred[0].cpu(), ref)
+
+
+def test_fuse_eval_transcript_and_embed_tokens():
+    """FACT.trans pieces: _eval_w_transcript (blocks.py:263-275) frame-level and through a segment gather, and the
+    token initialisation action_embed(transcript) + action_pe (blocks.py:75-78)."""
+    g = torch.Generator().manual_seed(31)
+    Cc, A = 9, 32
+    for T, N, Sg in ((70, 6, 11), (3, 1, 2), (200, 25, 40)):
+        tr = torch.randint(0, Cc, (N,), generator=g)
+        fl = torch.randn(T, Cc, generator=g) * 2
+        attn = torch.softmax(torch.randn(T, N, generator=g) * 2, -1)
+        ntr = torch.tensor([N], dtype=torch.int32, device=DEV)
+        pred = torch.full((1, T), -1, dtype=torch.int64, device=DEV)
+        ops.fuse_eval_transcript(attn[None].contiguous().to(DEV), fl[None].to(DEV), 0.1, tr.int()[None].to(DEV), ntr, pred, Cc)
+        assert torch.equal(pred[0].cpu(), O.eval_w_transcript(tr, attn, fl, 0.1))
+        attn_seg = torch.softmax(torch.randn(Sg, N, generator=g) * 2, -1)
+        lab = torch.sort(torch.randint(0, Sg, (T,), generator=g)).values
+        ops.fuse_eval_transcript(attn_seg[None].contiguous().to(DEV), fl[None].to(DEV), 0.1, tr.int()[None].to(DEV), ntr, pred, Cc,
+                                 seg_label=lab.int()[None].to(DEV))
+        assert torch.equal(pred[0].cpu(), O.eval_w_transcript(tr, attn_seg[lab], fl, 0.1))
+        emb = torch.randn(Cc, A, generator=g)
+        pe = O.positional_table(A, 64)
+        out = torch.empty(1, N, A, device=DEV)
+        ops.embed_tokens(emb.to(DEV), tr.int().to(DEV), pe.to(DEV), out)
+        assert torch.equal(out[0].cpu(), emb[tr] + pe[:N])
