@@ -132,12 +132,13 @@ def epic_shape():
                         Loss=dict(match='o2m', nullw=0.05, bgw=0.5), TM=dict(use=False)))
 
 
-def tiny(f='m', block='iuU', fpos=False, F=32, A=32, H=64, M=12, layers=4, a_layers=2, nhead=4, ffdim=48, trans=False):
+def tiny(f='m', block='iuU', fpos=False, F=32, A=32, H=64, M=12, layers=4, a_layers=2, nhead=4, ffdim=48, trans=False,
+         f_ln=False, f_ngp=1, a_i='sca', a_u='sa'):
     """A small configuration for golden fixtures and fast parity tests (not a shipped YAML)."""
     cfg = defaults()
-    upd = dict(a_nhead=nhead, f_layers=layers)
-    cfg.merge(dict(Bi=dict(a='sca', a_dim=A, a_ffdim=ffdim, a_layers=a_layers, a_nhead=nhead, dropout=0.0,
-                           f=f, f_dim=F, f_layers=layers, f_ln=False, f_ngp=1, hid_dim=H),
+    upd = dict(a_nhead=nhead, f_layers=layers, a=a_u)
+    cfg.merge(dict(Bi=dict(a=a_i, a_dim=A, a_ffdim=ffdim, a_layers=a_layers, a_nhead=nhead, dropout=0.0,
+                           f=f, f_dim=F, f_layers=layers, f_ln=f_ln, f_ngp=f_ngp, hid_dim=H),
                    Bu=upd, BU=upd,
                    FACT=dict(block=block, cmr=0.0, fpos=fpos, ntoken=M, mwt=0.1, trans=trans),
                    CLIP=dict(temp=0.1, projection_hidden_dim=40), use_clip=True))

@@ -126,8 +126,20 @@ class FactEngine:
             self._wcache[key] = t
         return t
 
-    def taps(self, name):      # Conv1d weight (Cout, Cin, k) -> [k][Cout][Cin]
-        return self.derived(('taps', name), lambda: self.p(name).permute(2, 0, 1))
+    def taps(self, name, groups=1):
+        """Conv1d weight (Cout, Cin/groups, k) -> [k][Cout][Cin].  A grouped convolution (f_ngp > 1, basic.py:139) becomes
+        its block-diagonal dense matrix so every GEMM path (fused layer, folded MSTCN++ taps) serves it unchanged."""
+        if groups == 1:
+            return self.derived(('taps', name), lambda: self.p(name).permute(2, 0, 1))
+
+        def dense():
+            w = self.p(name)
+            co, ci = w.shape[0] // groups, w.shape[1]
+            full = w.new_zeros(w.shape[0], ci * groups, w.shape[2])
+            for j in range(groups):
+                full[j * co:(j + 1) * co, j * ci:(j + 1) * ci] = w[j * co:(j + 1) * co]
+            return full.permute(2, 0, 1)
+        return self.derived(('taps', name, groups), dense)
 
     def tr(self, name):        # W^T
         return self.derived(('tr', name), lambda: self.p(name).t())
@@ -142,7 +154,7 @@ class FactEngine:
         B, slot, F, H, Lr, C = self.B, self.slot, bc['f_dim'], bc['hid_dim'], bc['f_layers'], self.hp['n_classes']
         ln = self.len
         fa, fb = self.zbuf('f_a', (B, slot, F), self.act), self.zbuf('f_b', (B, slot, F), self.act)
-        m2 = bc['f'] == 'm2'
+        m2, ng = bc['f'] == 'm2', bc['f_ngp']
         other = lambda t: fb if t is fa else fa
         if in_map:
             w = pfx + ('conv_1x1_in' if m2 else 'conv_1x1')
@@ -156,11 +168,11 @@ class FactEngine:
             if fused:
                 # conv3 + ReLU + 1x1 + residual in one tcgen05 kernel; the ReLU tile never leaves the SM (tcn_fused.cu)
                 q = f'{pfx}layers.{i}.'
-                ops.tcn_layer(cur, nxt, self.wbf(self.taps(q + 'conv_dilated.weight')), self.p(q + 'conv_dilated.bias'),
+                ops.tcn_layer(cur, nxt, self.wbf(self.taps(q + 'conv_dilated.weight', ng)), self.p(q + 'conv_dilated.bias'),
                               self.wbf(self.taps(q + 'conv_1x1.weight')[0]), self.p(q + 'conv_1x1.bias'), 2 ** i, len=ln)
             elif not m2:
                 q = f'{pfx}layers.{i}.'
-                w3, d = self.taps(q + 'conv_dilated.weight'), 2 ** i
+                w3, d = self.taps(q + 'conv_dilated.weight', ng), 2 ** i
                 tmp = self.buf('f_tmp', (B, slot, F), self.act)
                 self.mm([S(cur, w3[k], off=(k - 1) * d) for k in range(3)], F, tmp, len=ln,
                         bias=self.p(q + 'conv_dilated.bias'), relu=True, tag='tcn_conv3')
@@ -171,9 +183,12 @@ class FactEngine:
                 # folds into ONE 5-tap convolution with weights Wf1 W1_k / Wf2 W2_k (centre taps merged): 10 F^2 instead of
                 # 16 F^2 FLOP per frame, one launch instead of three, no 2F-wide intermediate.
                 offs = self._m2_offsets(i, Lr)
-                Wt = self.derived(('m2fold_w', pfx, i), lambda: self._m2_fold(pfx, i, Lr)[0])
-                bt = self.derived(('m2fold_b', pfx, i), lambda: self._m2_fold(pfx, i, Lr)[1])
+                Wt = self.derived(('m2fold_w', pfx, i), lambda: self._m2_fold(pfx, i, Lr, ng)[0])
+                bt = self.derived(('m2fold_b', pfx, i), lambda: self._m2_fold(pfx, i, Lr, ng)[1])
                 self.mm([S(cur, Wt[j], off=o) for j, o in enumerate(offs)], F, nxt, len=ln, bias=bt, relu=True, res=cur, tag='tcn_m2')
+            if bc['f_ln'] and not m2:      # DilatedResidualLayer.norm (basic.py:166-169): LayerNorm over the channels, in place
+                q = f'{pfx}layers.{i}.'
+                ops.layernorm(nxt, self.p(q + 'norm.weight'), self.p(q + 'norm.bias'), nxt, len=ln)
             cur, nxt = nxt, other(nxt)
         out = self.buf('frame_' + tag, (B, slot, H), self.act)
         self.mm([S(cur, self.taps(pfx + 'conv_out.weight')[0])], H, out, len=ln, bias=self.p(pfx + 'conv_out.bias'), tag='conv_out')
@@ -187,9 +202,10 @@ class FactEngine:
         d1, d2 = 2 ** (Lr - 1 - i), 2 ** i
         return sorted({-d1, 0, d1, -d2, d2})
 
-    def _m2_fold(self, pfx, i, Lr):
+    def _m2_fold(self, pfx, i, Lr, groups=1):
         """Folded taps [n_offsets, F, F] (in _m2_offsets order) and bias [F] of MSTCN2 layer i."""
-        w1, w2 = self.p(f'{pfx}conv_dilated_1.{i}.weight'), self.p(f'{pfx}conv_dilated_2.{i}.weight')        # (F, F, 3)
+        w1 = self.taps(f'{pfx}conv_dilated_1.{i}.weight', groups).permute(1, 2, 0)                              # (F, F, 3)
+        w2 = self.taps(f'{pfx}conv_dilated_2.{i}.weight', groups).permute(1, 2, 0)
         b1, b2 = self.p(f'{pfx}conv_dilated_1.{i}.bias'), self.p(f'{pfx}conv_dilated_2.{i}.bias')
         wf, bf = self.p(f'{pfx}conv_fusion.{i}.weight')[:, :, 0], self.p(f'{pfx}conv_fusion.{i}.bias')       # (F, 2F)
         F = w1.shape[0]
@@ -284,6 +300,39 @@ class FactEngine:
         self.lin(x, self.p(pfx + 'out_linear.weight'), H, out, bias=self.p(pfx + 'out_linear.bias'))
         return out
 
+    def gru_decoder(self, pfx, bc, x, tag):
+        """ActionUpdate_GRU (models/basic.py:283-308; FACT.trans models): stacked bidirectional GRU over the tokens,
+        LayerNorm, optional out_map.  x: [B,M,A] fp32 -> [B,M,H] fp32.  The recurrence is the fp32 cluster kernel the
+        segment GRU uses in fp32 mode (a transcript is tens of tokens: latency, not throughput)."""
+        B, M, A, H = self.B, self.ntok, bc['a_dim'], bc['hid_dim']
+        Hh, g = A // 2, pfx + 'gru.'
+        ntok = self.buf('agru_n', (B,), torch.int32)
+        ntok.fill_(M)
+        for l in range(bc['a_layers']):
+            gi = self.buf('agru_gi', (B, M, 6 * Hh))
+            ops.gemm([S(x, self.cat(f'{g}weight_ih_l{l}', f'{g}weight_ih_l{l}_reverse'))], 6 * Hh, gi,
+                     bias=self.cat(f'{g}bias_ih_l{l}', f'{g}bias_ih_l{l}_reverse'))
+            y = self.buf(f'agru_y{l % 2}', (B, M, A))
+            ops.gru_bidir(gi, self.p(f'{g}weight_hh_l{l}'), self.p(f'{g}bias_hh_l{l}'), self.p(f'{g}weight_hh_l{l}_reverse'),
+                          self.p(f'{g}bias_hh_l{l}_reverse'), y, ntok, relu=False)
+            x = y
+        out = self.buf('action_' + tag, (B, M, H))
+        if bc['a'] == 'gru_om':
+            t = self.buf('agru_ln', (B, M, A))
+            ops.layernorm(x, self.p(pfx + 'layernorm.weight'), self.p(pfx + 'layernorm.bias'), t)
+            self.lin(t, self.p(pfx + 'out_map.weight'), H, out, bias=self.p(pfx + 'out_map.bias'))
+        else:
+            ops.layernorm(x, self.p(pfx + 'layernorm.weight'), self.p(pfx + 'layernorm.bias'), out)
+        return out
+
+    def action_branch(self, pfx, bc, x, tag, frame=None):
+        """Block.create_abranch dispatch (models/blocks.py:215-232)."""
+        if bc['a'] in ('gru', 'gru_om'):
+            return self.gru_decoder(pfx, bc, self.action_init if frame is not None else x, tag)
+        if frame is not None:
+            return self.sca_decoder(pfx, bc, frame, tag)
+        return self.sa_decoder(pfx, bc, x, tag)
+
     def token_splice(self, action, tag):
         C = self.hp['n_classes']
         clogit = self.buf('aclogit_' + tag, (self.B, self.ntok, C + 1))
@@ -356,14 +405,14 @@ class FactEngine:
     def input_block(self, i, bc, x, st):
         pfx = f'block_list.{i}.'
         frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, x, True, f'b{i}')
-        action = self.sca_decoder(pfx + 'action_branch.', bc, frame, f'b{i}')
+        action = self.action_branch(pfx + 'action_branch.', bc, None, f'b{i}', frame=frame)
         st['action_clogit'] = self.token_splice(action, f'b{i}')
         return frame, action
 
     def update_block(self, i, bc, frame, action, st):
         pfx, tag = f'block_list.{i}.', f'b{i}'
         tok, st['f2a_attn_logit'], st['f2a_attn'] = self.f2a(pfx + 'f2a_layer.', bc, frame, self.len, None, action, tag, self.keep)
-        action = self.sa_decoder(pfx + 'action_branch.', bc, tok, tag)
+        action = self.action_branch(pfx + 'action_branch.', bc, tok, tag)
         st['action_clogit'] = self.token_splice(action, tag)
         fr, st['a2f_attn_logit'], st['a2f_attn'] = self.a2f(pfx + 'a2f_layer.', bc, action, frame, self.len, None, tag)
         frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, fr, False, tag)
@@ -397,7 +446,7 @@ class FactEngine:
         ops.softmax_splice(seg2, C, st['seg_clogit'], None, len=nseg)
         pidx = seg_center if self.frame_pos is not None else None
         tok, st['f2a_attn_logit'], st['f2a_attn_seg'] = self.f2a(pfx + 'f2a_layer.', bc, seg2, nseg, pidx, action, tag, self.keep)
-        action = self.sa_decoder(pfx + 'action_branch.', bc, tok, tag)
+        action = self.action_branch(pfx + 'action_branch.', bc, tok, tag)
         st['action_clogit'] = self.token_splice(action, tag)
         seg3, st['a2f_attn_logit'], st['a2f_attn_seg'] = self.a2f(pfx + 'a2f_layer.', bc, action, seg2, nseg, pidx, tag)
         W = self.p(pfx + 'sf_merge.0.weight')                               # [F, F+H], input = cat[s2f, frame]

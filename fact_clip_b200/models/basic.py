@@ -40,16 +40,17 @@ class PositionalEncoding(nn.Module):
 
 
 class DilatedResidualLayer(nn.Module):
-    def __init__(self, dilation, nchannels, dropout=0.5, layernorm=True, ngroup=1):
+    def __init__(self, dilation, nchannels, dropout=0.5, layernorm=True, layernorm_eps=1e-5, ngroup=1):
         super().__init__()
-        if layernorm or ngroup != 1:
-            raise NotImplementedError('f_ln / f_ngp>1 are used by no shipped config (SURVEY 8f rank 4)')
         self.dilation, self.nchannels, self.dropout_rate = dilation, nchannels, dropout
-        self.conv_dilated = nn.Conv1d(nchannels, nchannels, 3, padding=dilation, dilation=dilation)
+        self.conv_dilated = nn.Conv1d(nchannels, nchannels, 3, padding=dilation, dilation=dilation, groups=ngroup)
         self.conv_1x1 = nn.Conv1d(nchannels, nchannels, 1)
+        self.use_layernorm, self.ngroup = layernorm, ngroup
+        self.norm = nn.LayerNorm(nchannels, eps=layernorm_eps) if layernorm else None
 
     def __repr__(self):
-        return f'DilatedResidualLayer(Conv(d={self.dilation},h={self.nchannels}), 1x1(h={self.nchannels}), Dropout={self.dropout_rate})'
+        return (f'DilatedResidualLayer(Conv(d={self.dilation},h={self.nchannels}), 1x1(h={self.nchannels}), '
+                f'Dropout={self.dropout_rate}, ln={self.use_layernorm})')
 
 
 class _FrameBranch(nn.Module):
@@ -80,17 +81,17 @@ class MSTCN(_FrameBranch):
 class MSTCN2(_FrameBranch):
     def __init__(self, dim, num_f_maps, out_dim, num_layers, dropout=0.5, dilation_factor=2, ngroup=1, ln=False, in_map=True):
         super().__init__()
-        if ln or ngroup != 1:
-            raise NotImplementedError('f_ln / f_ngp>1 are used by no shipped config (SURVEY 8f rank 4)')
-        self.num_layers = num_layers
+        assert not ln, 'MSTCN++ has no layer norm (basic.py:226)'
+        self.num_layers, self.ngroup = num_layers, ngroup
         if in_map:
             self.conv_1x1_in = nn.Conv1d(dim, num_f_maps, 1)
         else:
             assert dim == num_f_maps
         d = dilation_factor
         self.conv_dilated_1 = nn.ModuleList(nn.Conv1d(num_f_maps, num_f_maps, 3, padding=d ** (num_layers - 1 - i),
-                                                      dilation=d ** (num_layers - 1 - i)) for i in range(num_layers))
-        self.conv_dilated_2 = nn.ModuleList(nn.Conv1d(num_f_maps, num_f_maps, 3, padding=d ** i, dilation=d ** i)
+                                                      dilation=d ** (num_layers - 1 - i), groups=ngroup)
+                                            for i in range(num_layers))
+        self.conv_dilated_2 = nn.ModuleList(nn.Conv1d(num_f_maps, num_f_maps, 3, padding=d ** i, dilation=d ** i, groups=ngroup)
                                             for i in range(num_layers))
         self.conv_fusion = nn.ModuleList(nn.Conv1d(2 * num_f_maps, num_f_maps, 1) for i in range(num_layers))
         self.conv_out = nn.Conv1d(num_f_maps, out_dim, 1)
@@ -156,6 +157,22 @@ class SCADecoder(nn.Module):
         self.layers = _clones(decoder_layer, num_layers)
         self.out_linear = nn.Linear(hid_dim, out_dim)
         self.num_layers, self.norm = num_layers, norm
+
+
+class ActionUpdate_GRU(nn.Module):
+    """Parameter holder of the GRU action branch for transcript-conditioned models (basic.py:283-308): a bidirectional
+    multi-layer nn.GRU over the tokens, LayerNorm, optional output map."""
+
+    def __init__(self, in_dim, hid_dim, out_dim, n_layers, dropout=0.5, layer_norm_eps=1e-5, out_map=False):
+        super().__init__()
+        self.in_dim, self.hid_dim, self.n_layers = in_dim, hid_dim, n_layers
+        self.gru = nn.GRU(in_dim, hid_dim // 2, n_layers, dropout=dropout, bidirectional=True)
+        self.layernorm = nn.LayerNorm(hid_dim, eps=layer_norm_eps)
+        if out_map:
+            self.out_map = nn.Linear(hid_dim, out_dim)
+        else:
+            assert hid_dim == out_dim
+            self.out_map = nn.Identity()
 
 
 class SADecoder(nn.Module):

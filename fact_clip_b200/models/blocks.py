@@ -61,8 +61,7 @@ class Block(nn.Module):
                                 ngroup=cfg.f_ngp, in_map=f_inmap)
         raise ValueError(f"frame branch {cfg.f!r}: only 'm' (MSTCN) and 'm2' (MSTCN++) exist (blocks.py:208-213)")
 
-    @staticmethod
-    def create_abranch(cfg):
+    def create_abranch(self, cfg):
         if cfg.a == 'sa':
             layer = basic.SALayer(cfg.a_dim, cfg.a_nhead, dim_feedforward=cfg.a_ffdim, dropout=cfg.dropout, attn_dropout=cfg.dropout)
             return basic.SADecoder(cfg.a_dim, cfg.a_dim, cfg.hid_dim, layer, cfg.a_layers, in_map=False)
@@ -70,8 +69,10 @@ class Block(nn.Module):
             layer = basic.SCALayer(cfg.a_dim, cfg.hid_dim, cfg.a_nhead, cfg.a_ffdim, dropout=cfg.dropout, attn_dropout=cfg.dropout)
             norm = nn.LayerNorm(cfg.a_dim)
             return basic.SCADecoder(cfg.a_dim, cfg.a_dim, cfg.hid_dim, layer, cfg.a_layers, norm=norm, in_map=False)
-        if cfg.a in ('gru', 'gru_om'):
-            raise NotImplementedError("action branch 'gru' needs FACT.trans=True: SURVEY 8(f) rank 4")
+        if cfg.a in ('gru', 'gru_om'):      # GRU over the transcript tokens (blocks.py:225-228)
+            assert self.cfg.FACT.trans
+            return basic.ActionUpdate_GRU(cfg.a_dim, cfg.a_dim, cfg.hid_dim, cfg.a_layers, dropout=cfg.dropout,
+                                          out_map=(cfg.a == 'gru_om'))
         raise ValueError(cfg.a)
 
     @staticmethod

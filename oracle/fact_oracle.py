@@ -97,7 +97,13 @@ def process_feature(x, nclass):
 
 
 def conv1d_k3(x, w, b, dil):
-    """nn.Conv1d(C, C, 3, padding=dil, dilation=dil) on channels-last x (T, Cin); w (Cout, Cin, 3)."""
+    """nn.Conv1d(C, C, 3, padding=dil, dilation=dil, groups=g) on channels-last x (T, Cin); w (Cout, Cin/g, 3):
+    output group j reads input group j only."""
+    g = x.shape[1] // w.shape[1]
+    if g > 1:
+        ci, co = w.shape[1], w.shape[0] // g
+        return torch.cat([conv1d_k3(x[:, j * ci:(j + 1) * ci], w[j * co:(j + 1) * co], b[j * co:(j + 1) * co], dil)
+                          for j in range(g)], 1)
     T = x.shape[0]
     z = torch.zeros(dil, x.shape[1])
     xp = torch.cat([z, x, z], 0)
@@ -115,14 +121,17 @@ def conv1x1(x, w, b):
 # frame branch
 
 
-def mstcn(sd, p, x, n_layers, in_map):
-    """basic.py:200-220 (+ DilatedResidualLayer.forward :154-171), eval mode, f_ln False."""
+def mstcn(sd, p, x, n_layers, in_map, ln=False):
+    """basic.py:200-220 (+ DilatedResidualLayer.forward :154-171), eval mode; ``ln``: LayerNorm over the channels after
+    the residual of every layer (f_ln, basic.py:166-169)."""
     if in_map:
         x = conv1x1(x, sd[p + 'conv_1x1.weight'], sd[p + 'conv_1x1.bias'])
     for i in range(n_layers):
         q = f'{p}layers.{i}.'
         h = torch.relu(conv1d_k3(x, sd[q + 'conv_dilated.weight'], sd[q + 'conv_dilated.bias'], 2 ** i))
         x = x + conv1x1(h, sd[q + 'conv_1x1.weight'], sd[q + 'conv_1x1.bias'])
+        if ln:
+            x = layer_norm(x, sd[q + 'norm.weight'], sd[q + 'norm.bias'])
     return conv1x1(x, sd[p + 'conv_out.weight'], sd[p + 'conv_out.bias'])
 
 
@@ -139,9 +148,10 @@ def mstcn2(sd, p, x, n_layers, in_map):
 
 
 def frame_branch(sd, p, x, bc, in_map):
-    assert not bc['f_ln'] and bc['f_ngp'] == 1, 'f_ln / f_ngp>1 are exercised by no shipped config'
-    fn = mstcn if bc['f'] == 'm' else mstcn2
-    return fn(sd, p, x, bc['f_layers'], in_map)
+    if bc['f'] == 'm':
+        return mstcn(sd, p, x, bc['f_layers'], in_map, ln=bool(bc['f_ln']))
+    assert not bc['f_ln'], 'MSTCN++ has no layer norm (basic.py:226)'
+    return mstcn2(sd, p, x, bc['f_layers'], in_map)
 
 
 # --------------------------------------------------------------------------------------------
@@ -236,13 +246,13 @@ def run_length(pred):
     return seg_label.astype(np.int64), start.astype(np.int64), lens.astype(np.int64)
 
 
-def gru_bidir(sd, p, x):
-    """nn.GRU(H, H/2, 1, bidirectional=True), h0 = 0, seq-first, B=1 (blocks.py:401,432)."""
+def gru_bidir(sd, p, x, layer=0):
+    """One layer of nn.GRU(H, H/2, n, bidirectional=True), h0 = 0, seq-first, B=1 (blocks.py:401,432)."""
     S = x.shape[0]
     outs = []
     for suffix, order in (('', range(S)), ('_reverse', range(S - 1, -1, -1))):
-        w_ih, w_hh = sd[f'{p}weight_ih_l0{suffix}'], sd[f'{p}weight_hh_l0{suffix}']
-        b_ih, b_hh = sd[f'{p}bias_ih_l0{suffix}'], sd[f'{p}bias_hh_l0{suffix}']
+        w_ih, w_hh = sd[f'{p}weight_ih_l{layer}{suffix}'], sd[f'{p}weight_hh_l{layer}{suffix}']
+        b_ih, b_hh = sd[f'{p}bias_ih_l{layer}{suffix}'], sd[f'{p}bias_hh_l{layer}{suffix}']
         Hh = w_hh.shape[1]
         gi = x @ w_ih.t() + b_ih                    # (S, 3Hh) gate order r, z, n
         h = torch.zeros(Hh)
@@ -256,6 +266,27 @@ def gru_bidir(sd, p, x):
             out[t] = h
         outs.append(out)
     return torch.cat(outs, -1)
+
+
+def action_gru(sd, p, x, bc):
+    """basic.py:283-308 (ActionUpdate_GRU): stacked bidirectional GRU over the tokens (eval: no inter-layer dropout),
+    LayerNorm, optional out_map ('gru_om')."""
+    for l in range(bc['a_layers']):
+        x = gru_bidir(sd, p + 'gru.', x, layer=l)
+    x = layer_norm(x, sd[p + 'layernorm.weight'], sd[p + 'layernorm.bias'])
+    if bc['a'] == 'gru_om':
+        x = linear(x, sd[p + 'out_map.weight'], sd[p + 'out_map.bias'])
+    return x
+
+
+def action_branch(sd, p, bc, action, action_pos, frame=None, frame_pos=None):
+    """blocks.py:215-232: 'sca' (input block), 'sa' (update blocks), 'gru' / 'gru_om' (either; ignores the memory)."""
+    if bc['a'] in ('gru', 'gru_om'):
+        return action_gru(sd, p, action, bc)
+    if bc['a'] == 'sca':
+        return sca_decoder(sd, p, action, frame, frame_pos, action_pos, bc)
+    assert bc['a'] == 'sa', bc['a']
+    return sa_decoder(sd, p, action, action_pos, bc)
 
 
 def gru_bidir_fast(sd, p, x):
@@ -275,8 +306,7 @@ def input_block(sd, p, bc, C, frame, action, frame_pos, action_pos, st):
     """blocks.py:295-311."""
     frame = frame_branch(sd, p + 'frame_branch.', frame, bc, True)
     frame, st['frame_clogit'] = process_feature(frame, C)
-    assert bc['a'] == 'sca', "only the 'sca' action branch is exercised by shipped configs"
-    action = sca_decoder(sd, p + 'action_branch.', action, frame, frame_pos, action_pos, bc)
+    action = action_branch(sd, p + 'action_branch.', bc, action, action_pos, frame, frame_pos)
     action, st['action_clogit'] = process_feature(action, C + 1)
     return frame, action
 
@@ -284,7 +314,7 @@ def input_block(sd, p, bc, C, frame, action, frame_pos, action_pos, st):
 def update_block(sd, p, bc, C, frame, action, frame_pos, action_pos, st):
     """blocks.py:343-367."""
     action, st['f2a_attn_logit'], st['f2a_attn'] = x2y_map(sd, p + 'f2a_layer.', frame, action, frame_pos, action_pos)
-    action = sa_decoder(sd, p + 'action_branch.', action, action_pos, bc)
+    action = action_branch(sd, p + 'action_branch.', bc, action, action_pos)
     action, st['action_clogit'] = process_feature(action, C + 1)
     frame, st['a2f_attn_logit'], st['a2f_attn'] = x2y_map(sd, p + 'a2f_layer.', action, frame, action_pos, frame_pos)
     frame = frame_branch(sd, p + 'frame_branch.', frame, bc, False)
@@ -309,7 +339,7 @@ def update_block_tdu(sd, p, bc, C, frame, action, frame_pos, action_pos, st, for
     center = torch.from_numpy((seg_start + (seg_start + seg_len - 1)) // 2)
     seg_pos = frame_pos[center] if frame_pos is not None else None
     action, f2a_logit, f2a_attn = x2y_map(sd, p + 'f2a_layer.', seg, action, seg_pos, action_pos)
-    action = sa_decoder(sd, p + 'action_branch.', action, action_pos, bc)
+    action = action_branch(sd, p + 'action_branch.', bc, action, action_pos)
     action, st['action_clogit'] = process_feature(action, C + 1)
     seg_out, a2f_logit, a2f_attn = x2y_map(sd, p + 'a2f_layer.', action, seg, action_pos, seg_pos)
     # blocks.py:439-447: cat[s2f, frame] order matters

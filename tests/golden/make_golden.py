@@ -35,6 +35,10 @@ CASES = [
     ('tiny_m2_iUU_fpos_clip', dict(f='m2', block='iUU', fpos=True), True, [64, 1, 3], 6, 24),
     ('tiny_m_iu', dict(f='m', block='iu', M=9), False, [50], 4, 16),
     ('tiny_m_iuU_trans', dict(f='m', block='iuU', trans=True), False, [90, 41, 2], 6, 24),   # FACT.trans: tokens = transcript
+    ('tiny_m_iuU_ln_ngp', dict(f='m', block='iuU', f_ln=True, f_ngp=4), False, [77, 30], 6, 24),     # LayerNorm + grouped conv
+    ('tiny_m2_iuU_ngp', dict(f='m2', block='iuU', f_ngp=2), False, [70], 5, 24),                     # grouped MSTCN++
+    # GRU action branch over the transcript tokens (2 stacked layers in the input block, out_map in the update blocks)
+    ('tiny_m_iuU_trans_gru', dict(f='m', block='iuU', trans=True, A=64, a_i='gru', a_u='gru_om'), False, [85, 33, 1], 6, 24),
 ]
 
 

@@ -88,5 +88,21 @@ def test_trans_variant_registers_reference_parameters():
         net.submit([torch.zeros(8, 24)])
 
 
+def test_variant_parameters_match_reference_layout():
+    """f_ln / f_ngp (basic.py:132-146) and the GRU action branch (basic.py:283-308) register the reference's parameters."""
+    net = FACT(C.tiny(f_ln=True, f_ngp=4), 24, 7)
+    sd = net.state_dict()
+    assert tuple(sd['block_list.0.frame_branch.layers.0.conv_dilated.weight'].shape) == (32, 8, 3)
+    assert 'block_list.1.frame_branch.layers.3.norm.weight' in sd
+    net = FACT(C.tiny(trans=True, A=64, a_i='gru', a_u='gru_om'), 24, 7)
+    sd = net.state_dict()
+    assert tuple(sd['block_list.0.action_branch.gru.weight_hh_l1_reverse'].shape) == (96, 32)
+    assert 'block_list.1.action_branch.out_map.weight' in sd and 'block_list.0.action_branch.out_map.weight' not in sd
+    with pytest.raises(AssertionError):
+        FACT(C.tiny(a_i='gru'), 24, 7)          # the GRU branch needs the transcript (blocks.py:226)
+
+
 def test_unsupported_variants_raise():
-    cfg = C.tiny()
+    with pytest.raises(NotImplementedError, match='compute_loss'):
+        net = FACT(C.tiny(), 24, 7)
+        net.forward([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)], compute_loss=True)
