@@ -1,0 +1,178 @@
+"""Training-loss VALUE of a batched forward, computed on the device (csrc/loss.cu).
+
+Mirrors the reference's ``MatchCriterion`` (models/loss.py:47-277), ``infonce_contrastive_loss`` (loss.py:280-341) and the
+``compute_loss`` / ``_loss_one_video`` methods of the model (models/blocks.py:90-106, 313-320, 369-382, 487-497, 677-786)
+for all videos of a step at once.  What crosses PCIe per step: the ground-truth segment counts (B ints), the [M, S]
+matching costs (the assignment itself is ``scipy.optimize.linear_sum_assignment`` on the host, like the reference) and the
+final per-video numbers.  The reference instead moves every (1, T, M) attention map to the host and builds a (T, M, S)
+numpy temporary per video (loss.py:91-106).
+
+Values only: there is no backward pass (second half).
+"""
+import numpy as np
+import torch
+from scipy.optimize import linear_sum_assignment
+
+from . import ops
+
+_TYPE = {'i': 0, 'u': 1, 'U': 2}
+
+
+class MatchCriterion:
+    """Configuration holder with the reference's constructor (loss.py:49-53, built in scripts/train.py:207 as
+    ``net.mcriterion = MatchCriterion(cfg, dataset.nclasses, dataset.bg_class)``)."""
+
+    def __init__(self, cfg, nclasses, bg_ids=[], class_weight=None):
+        self.cfg, self.nclasses, self.bg_ids, self._class_weight = cfg, nclasses, list(bg_ids), class_weight
+
+    def class_weights(self):
+        """cweight of set_label (loss.py:62-70): ones, null class last, background or per-class weights."""
+        L = self.cfg.Loss
+        cw = torch.ones(self.nclasses + 1)
+        cw[-1] = float(L.nullw)
+        if self._class_weight is not None:
+            cw[:self.nclasses] = torch.as_tensor(self._class_weight, dtype=torch.float32)[:self.nclasses]
+        else:
+            for i in self.bg_ids:
+                cw[i] = float(L.bgw)
+        return cw
+
+
+def one_to_many(cost, transcript):
+    """MatchCriterion._one_to_many_match (loss.py:155-194): Hungarian assignment of tokens to action CLASSES on the summed
+    cost, leftover tokens to their cheapest class, then every ground-truth segment takes the cheapest token of its class.
+    Returns (token index, segment index) lists grouped by ascending class, ascending segment inside a class."""
+    actions, cls_of_seg = np.unique(transcript, return_inverse=True)
+    t2a = np.stack([cost[:, cls_of_seg == j].sum(1) for j in range(len(actions))], axis=1)
+    rows, cols = linear_sum_assignment(t2a)
+    token_cls = np.full(cost.shape[0], -1, dtype=np.int64)
+    token_cls[rows] = cols
+    rest = token_cls < 0
+    if rest.any():
+        token_cls[rest] = t2a[rest].argmin(1)
+    aind, sind = [], []
+    for j in range(len(actions)):
+        segs, toks = np.nonzero(cls_of_seg == j)[0], np.nonzero(token_cls == j)[0]
+        assert len(toks), 'fewer tokens than action classes in the transcript'
+        aind.extend(toks[cost[np.ix_(toks, segs)].argmin(0)].tolist())
+        sind.extend(segs.tolist())
+    return aind, sind
+
+
+def assign(cost, transcript, mode):
+    """cost (M, S) -> matched (token, segment) index lists (loss.py:119-153)."""
+    M, S = cost.shape
+    if mode == 'seq':
+        assert M >= S, (M, S)
+        return list(range(S)), list(range(S))
+    if mode == 'o2o':
+        a, s = linear_sum_assignment(cost)
+        return a.tolist(), s.tolist()
+    if mode == 'o2m':
+        return one_to_many(cost, transcript)
+    raise ValueError(mode)
+
+
+class LossRunner:
+    """Loss value of one engine forward (``FactEngine.run`` output) for the whole batch."""
+
+    def __init__(self, engine, criterion):
+        self.e, self.crit = engine, criterion
+
+    def run(self, out, labels):
+        e, cfg = self.e, self.crit.cfg
+        hp, Lc = e.hp, cfg.Loss
+        B, slot, ln, dev = e.B, e.slot, e.len, e.dev
+        C, M, nb = hp['n_classes'], e.ntok, len(hp['blocks'])
+        assert nb <= 8 and not hp['trans'], 'loss value: at most 8 blocks, query-token models'
+        I32, buf = torch.int32, e.buf
+        # ---- labels -> ground-truth segments (the TDU run-length kernel serves MatchCriterion.set_label, loss.py:56-60)
+        label = buf('loss_label', (B, slot), I32)
+        label.zero_()
+        for b, y in enumerate(labels):
+            label[b, :out['lengths'][b]].copy_(torch.as_tensor(y).to(I32), non_blocking=True)
+        gseg, gstart = buf('loss_gseg', (B, slot), I32), buf('loss_gstart', (B, slot), I32)
+        glen, gcen, gn = buf('loss_glen', (B, slot), I32), buf('loss_gcen', (B, slot), I32), buf('loss_gn', (B,), I32)
+        ops.tdu_segment(label, gseg, gstart, glen, gcen, gn, len=ln)
+        nseg = gn.cpu().numpy()                                    # host sync 1: B ints
+        smax = int(nseg.max())
+        cweight = e.derived(('loss_cw', id(self.crit)), lambda: self.crit.class_weights().to(dev))
+        transcript, sweight = buf('loss_tr', (B, smax), I32), buf('loss_sw', (B, smax))
+        # ---- InfoNCE bookkeeping (blocks.py:697-748): seen-class list, label remapping, per-class frame counts
+        clip = 'projected_frame_embeddings' in out
+        seen = cmap = inv_count = nvalid = None
+        if clip:
+            hold = set(cfg.holdout_classes) if 'holdout_classes' in cfg and cfg.holdout_classes else set()
+            seen_l = [i for i in range(C) if i not in hold]
+            seen = e.derived(('loss_seen', tuple(seen_l)), lambda: torch.tensor(seen_l, dtype=I32, device=dev))
+            m = np.full(C, -1, dtype=np.int32)
+            m[seen_l] = np.arange(len(seen_l), dtype=np.int32)
+            cmap = e.derived(('loss_cmap', tuple(seen_l)), lambda: torch.from_numpy(m).to(dev))
+            inv_count, nvalid = buf('loss_invc', (B, C)), buf('loss_nvalid', (B,), I32)
+        ops.label_prep(label, gstart, gn, cweight, C, transcript, sweight, ln, cmap=cmap, inv_count=inv_count, nvalid=nvalid)
+        # ---- matching on the LAST block (blocks.py:94-96): cost on device, assignment on the host
+        last = out['blocks'][-1]
+        Mp = last['a2f_attn_logit'].shape[2]
+        overlap, cost = buf('loss_ov', (B, smax, Mp)), buf('loss_cost', (B, M, smax))
+        if 'a2f_attn_seg' in last:
+            ops.match_cost(last['a2f_attn_seg'], last['action_clogit'], transcript, gstart, glen, gn, Lc.pc, Lc.a2fc, overlap, cost,
+                           M, ridx=last['seg_label'])
+        else:
+            ops.match_cost(last['a2f_attn'], last['action_clogit'], transcript, gstart, glen, gn, Lc.pc, Lc.a2fc, overlap, cost, M)
+        cost_h, tr_h = cost.cpu().numpy(), transcript.cpu().numpy()     # host sync 2: B x M x S floats
+        kmax = max(smax, 1)
+        aind_h, sind_h = np.zeros((B, kmax), np.int32), np.zeros((B, kmax), np.int32)
+        inv_h, nm_h = np.full((B, smax), -1, np.int32), np.zeros(B, np.int32)
+        matches = []
+        for b in range(B):
+            S = int(nseg[b])
+            a, s = assign(cost_h[b, :, :S], tr_h[b, :S], Lc.match)
+            # QUIRK kept from loss.py:221-222: sweight multiplies the k-th matched column, which needs K == S
+            assert len(a) == S, f'video {b}: {len(a)} matched pairs for {S} segments (the reference cannot broadcast sweight)'
+            aind_h[b, :S], sind_h[b, :S], nm_h[b] = a, s, S
+            inv_h[b, s] = np.arange(S, dtype=np.int32)
+            matches.append((a, s))
+        up = lambda name, arr: buf(name, arr.shape, I32).copy_(torch.from_numpy(arr), non_blocking=True)
+        aind, sind, inv, nm = up('loss_aind', aind_h), up('loss_sind', sind_h), up('loss_inv', inv_h), up('loss_nm', nm_h)
+        # ---- per-block terms
+        nchunk = ops.loss_nchunk(slot)
+        ws = buf('loss_ws', (8 * nb + 3, B, nchunk))
+        ws.zero_()
+        npred = buf('loss_npred', (nb, B), I32)
+        types = []
+        for i, (st, bc) in enumerate(zip(out['blocks'], hp['blocks'])):
+            t0, ty = 8 * i, _TYPE[bc['type']]
+            types.append(ty)
+            fc = st['frame_clogit']
+            ops.loss_pick(fc, C, label, ws[t0 + 0], ln, w=cweight)                               # frame_loss, loss.py:249-261
+            ops.loss_smooth(fc, C, ws[t0 + 1], ln)
+            ops.token_loss(st['action_clogit'], aind, sind, nm, transcript, cweight, ws[t0 + 2])
+            if ty == 0:
+                continue
+            f2a, a2f = st['f2a_attn_logit'], st['a2f_attn_logit']                              # rows: frames / segments
+            lse = buf('loss_collse', (B, f2a.shape[2]))
+            if ty == 1:
+                ops.col_lse(f2a, M, ln, lse)
+                ops.loss_pick(f2a, M, gseg, ws[t0 + 3], ln, cols=aind, ncols=nm, col_lse=lse, tmap=inv, w=sweight)
+                ops.loss_pick(a2f, M, gseg, ws[t0 + 4], ln, cols=aind, ncols=nm, tmap=inv, w=sweight)
+                ops.loss_smooth(f2a, M, ws[t0 + 5], ln)
+                ops.loss_smooth(a2f, M, ws[t0 + 6], ln)
+            else:
+                ridx, rlen, ns = st['seg_label'], st['seg_lens'], st['nseg']
+                npred[i].copy_(ns)
+                ops.col_lse(f2a, M, ns, lse)
+                ops.loss_pick(f2a, M, gseg, ws[t0 + 3], ln, cols=aind, ncols=nm, col_lse=lse, tmap=inv, w=sweight, ridx=ridx, rlen=rlen)
+                ops.loss_pick(a2f, M, gseg, ws[t0 + 4], ln, cols=aind, ncols=nm, tmap=inv, w=sweight, ridx=ridx, rlen=rlen)
+                ops.loss_pick(st['seg_clogit'], C, label, ws[t0 + 7], ln, w=cweight, ridx=ridx, rlen=rlen)   # frame_loss_tdu
+        if clip:
+            sim = out['clip_logit']                                                             # emb @ text^T / temp
+            ops.loss_pick(sim, len(seen), label, ws[8 * nb + 0], ln, cols=seen, tmap=cmap)     # frame -> class
+            lse = buf('loss_clslse', (B, C))
+            ops.col_lse(sim, C, ln, lse, rmask0=label, rmap=cmap)
+            ops.loss_pick(sim, len(seen), label, ws[8 * nb + 1], ln, cols=seen, tmap=cmap, col_lse=lse, w=inv_count)
+        res = buf('loss_out', (B, 4 + nb))
+        ops.loss_combine(ws, types, ln, npred, C, M, float(Lc.sw), res, use_clip=clip,
+                         fact_w=float(cfg.CLIP.fact_loss_weight) if clip else 1.0,
+                         con_w=float(cfg.CLIP.contrastive_weight) if clip else 0.0,
+                         nseen=len(seen) if clip else 0, nvalid=nvalid)
+        return dict(values=res, matches=matches)

@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from .. import config as cfgmod
 from ..engine import FactEngine
+from ..loss import LossRunner
 from . import basic
 
 try:  # the reference refuses to build FACT_CLIP without transformers (blocks.py:526-527); we do not need it
@@ -165,8 +166,11 @@ class _FactBase(nn.Module):
         return self._engine
 
     def forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
-        if compute_loss or (self.training and torch.is_grad_enabled() and compute_loss):
-            raise NotImplementedError('compute_loss=True (training step) is not built yet: SURVEY.md 8(f) rank 1')
+        if compute_loss and (self.training or self.cfg.FACT.trans):
+            raise NotImplementedError('compute_loss=True is built for eval mode of the query-token models: the loss VALUE on '
+                                      'device (no backward, no dropout / masking). The training step is SURVEY.md 8(f) rank 1')
+        if compute_loss and self.mcriterion is None:
+            raise RuntimeError('compute_loss=True needs net.mcriterion = MatchCriterion(cfg, nclasses, bg_ids) (scripts/train.py:207)')
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
@@ -175,9 +179,23 @@ class _FactBase(nn.Module):
             return self._forward_with_transcripts(seqs, label_list, forced_preds)
         out = self.engine().run(seqs, forced_preds=forced_preds, keep=getattr(self, 'keep_attn', False))
         self._last = out
+        if compute_loss:
+            res = LossRunner(self.engine(), self.mcriterion).run(out, label_list)
+            self.last_match = res['matches']
         pred = out['pred'].cpu().numpy()            # the one D2H sync of the call (blocks.py:900)
         self.stash_video(len(seqs) - 1)
-        return [{'pred': pred[b, :T].copy()} for b, T in enumerate(out['lengths'])]
+        saves = [{'pred': pred[b, :T].copy()} for b, T in enumerate(out['lengths'])]
+        if not compute_loss:
+            return saves
+        # (final_loss, save_list) like blocks.py:120-130 / 902-914; the loss carries no graph (value only)
+        vals = res['values'].cpu().numpy()
+        nb = len(self.block_list)
+        for b, s in enumerate(saves):
+            s['loss'] = {'loss': float(vals[b, 0])}
+            if vals[b, 3] > 0:
+                s['loss'].update(fact_loss=float(vals[b, 1]), contrastive_loss=float(vals[b, 2]))
+            s['block_losses'] = vals[b, 4:4 + nb].tolist()
+        return res['values'][:, 0].mean(), saves
 
     def _forward_with_transcripts(self, seqs, label_list, forced_preds=None):
         """FACT.trans (blocks.py:74-79, 113-118): every video brings its own token count (the length of its transcript), so

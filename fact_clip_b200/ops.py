@@ -260,3 +260,71 @@ def embed_tokens(embed, transcript, pe, out):
     COUNTERS['launches'] += 1
     _call('factk_embed_tokens', None, embed.data_ptr(), embed.stride(0), transcript.data_ptr(), pe.data_ptr(), pe.stride(0),
           out.data_ptr(), _row_ld(out), N, A, L.stream())
+
+
+# ---------------------------------------------------------------------------------------------- loss value (loss.cu)
+LOSS_CHUNK = 64
+
+
+def loss_nchunk(slot):
+    return (slot + LOSS_CHUNK - 1) // LOSS_CHUNK
+
+
+def label_prep(label, seg_start, nseg, cweight, C, transcript, sweight, len, cmap=None, inv_count=None, nvalid=None):
+    B, slot = label.shape
+    COUNTERS['launches'] += 1
+    _call('factk_label_prep', None, label.data_ptr(), seg_start.data_ptr(), nseg.data_ptr(), cweight.data_ptr(), L.ptr(cmap), C,
+          transcript.data_ptr(), sweight.data_ptr(), transcript.shape[1], L.ptr(inv_count), L.ptr(nvalid), B, slot,
+          len.data_ptr(), L.stream())
+
+
+def match_cost(attn, aclogit, transcript, seg_start, seg_len, nseg, pc, a2fc, overlap, cost, M, ridx=None):
+    """attn [B, aslot, >=M] (frame rows, or predicted-segment rows with ridx), aclogit [B, M, C+1] -> cost [B, M, smax]."""
+    B, slot = seg_start.shape
+    COUNTERS['launches'] += 2
+    _call('factk_match_cost', None, attn.data_ptr(), _row_ld(attn), attn.shape[1], L.ptr(ridx), aclogit.data_ptr(), M,
+          aclogit.shape[2], transcript.data_ptr(), seg_start.data_ptr(), seg_len.data_ptr(), nseg.data_ptr(),
+          transcript.shape[1], float(pc), float(a2fc), overlap.data_ptr(), _row_ld(overlap), cost.data_ptr(), B, slot, L.stream())
+
+
+def loss_pick(X, ncol, tgt0, part, len, cols=None, ncols=None, ridx=None, rlen=None, col_lse=None, tmap=None, w=None,
+              part_cnt=None):
+    """See factk_loss_pick (include/factk.h).  cols / tmap / w: [B, n] per video, or 1-D shared tables."""
+    B, slot = tgt0.shape
+    bs = lambda t: 0 if t is None or t.dim() == 1 else t.stride(0)
+    COUNTERS['launches'] += 1
+    _call('factk_loss_pick', None, X.data_ptr(), _row_ld(X), X.shape[1], ncol, L.ptr(cols), bs(cols), L.ptr(ncols), L.ptr(ridx),
+          L.ptr(rlen), L.ptr(col_lse), col_lse.stride(0) if col_lse is not None else 0, tgt0.data_ptr(), L.ptr(tmap), bs(tmap),
+          L.ptr(w), bs(w), part.data_ptr(), L.ptr(part_cnt), B, slot, len.data_ptr(), part.shape[-1], L.stream())
+
+
+def loss_smooth(X, ncol, part, len):
+    B, slot = X.shape[0], X.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_loss_smooth', None, X.data_ptr(), _row_ld(X), ncol, part.data_ptr(), B, slot, len.data_ptr(), part.shape[-1],
+          L.stream())
+
+
+def col_lse(X, ncol, nrows, out, rmask0=None, rmap=None):
+    B = X.shape[0]
+    COUNTERS['launches'] += 1
+    _call('factk_col_lse', None, X.data_ptr(), _row_ld(X), X.shape[1], ncol, nrows.data_ptr(), L.ptr(rmask0), L.ptr(rmap),
+          0 if rmap is None or rmap.dim() == 1 else rmap.stride(0), out.data_ptr(), out.stride(0), B, L.stream())
+
+
+def token_loss(aclogit, aind, sind, nmatch, transcript, cweight, out):
+    """out: [B, nchunk] slice of the workspace; the value lands in out[:, 0]."""
+    B, M, C1 = aclogit.shape
+    COUNTERS['launches'] += 1
+    _call('factk_token_loss', None, aclogit.data_ptr(), M, C1, aind.data_ptr(), sind.data_ptr(), nmatch.data_ptr(), aind.shape[1],
+          transcript.data_ptr(), transcript.shape[1], cweight.data_ptr(), out.data_ptr(), out.stride(0), B, L.stream())
+
+
+def loss_combine(ws, block_types, len, npred, C, M, sw, out, use_clip=False, fact_w=1.0, con_w=0.0, nseen=0, nvalid=None):
+    import ctypes
+    nb, B, nchunk = len_(block_types), ws.shape[1], ws.shape[2]
+    bt = (ctypes.c_int32 * nb)(*block_types)
+    COUNTERS['launches'] += 1
+    _call('factk_loss_combine', None, ws.data_ptr(), nb, ctypes.cast(bt, ctypes.c_void_p), B, nchunk, len.data_ptr(), L.ptr(npred),
+          C, M, float(sw), int(use_clip), float(fact_w), float(con_w), int(nseen), L.ptr(nvalid), out.data_ptr(), out.stride(0),
+          L.stream())

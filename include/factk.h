@@ -31,6 +31,7 @@ extern "C" {
 #define FACTK_F32 0
 #define FACTK_BF16 1
 #define FACTK_MAX_SRC 6
+#define FACTK_LOSS_MAX_BLOCKS 8
 
 #define FACTK_OK 0
 #define FACTK_ERR_ARG (-1)
@@ -229,6 +230,57 @@ int factk_fuse_eval_transcript(const float* attn, int lda, int attn_slot, const 
 /* Token initialisation of FACT.trans models (blocks.py:74-79): out[n,:A] = embed[transcript[n],:A] + pe[n,:A]. */
 int factk_embed_tokens(const float* embed, int lde, const int32_t* transcript, const float* pe, int ldpe,
                        float* out, int ldo, int N, int A, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training-loss VALUE on device (reference models/loss.py and the compute_loss methods of models/blocks.py:313-320,
+ * 369-382, 487-497, 90-106, 677-786), batched over the videos of a step.  Partial sums live in a workspace
+ * ws[term][B][nchunk] (nchunk * 64 >= slot); factk_loss_combine applies the per-block formulas.  No gradients.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Labels -> criterion state (MatchCriterion.set_label, loss.py:56-87): transcript[b][s] = label at the start of
+ * ground-truth segment s, sweight[b][s] = cweight[transcript]; optionally inv_count[b][k] = 1 / max(#frames whose
+ * (mapped) label is k, 1) and nvalid[b] = #frames with a mapped label >= 0 (InfoNCE class->frame term, loss.py:324-331).
+ * cmap: optional [C] class remapping (holdout classes -> -1, blocks.py:706-725). */
+int factk_label_prep(const int32_t* label, const int32_t* seg_start, const int32_t* nseg, const float* cweight,
+                     const int32_t* cmap, int C, int32_t* transcript, float* sweight, int smax, float* inv_count,
+                     int32_t* nvalid, int B, int slot, const int32_t* len, void* stream);
+
+/* Matching cost (MatchCriterion.match / a2f_soft_iou, loss.py:91-136): cost[b][a][s] = -pc * softmax(aclogit)[a,
+ * transcript[s]] - a2fc * IoU(a, s); attn rows are frames, or predicted segments reached through ridx[b][t].
+ * overlap: scratch [B][smax][ldo]. */
+int factk_match_cost(const float* attn, int lda, int aslot, const int32_t* ridx, const float* aclogit, int M, int C1,
+                     const int32_t* transcript, const int32_t* seg_start, const int32_t* seg_len, const int32_t* nseg,
+                     int smax, float pc, float a2fc, float* overlap, int ldo, float* cost, int B, int slot, void* stream);
+
+/* part_sum[b][chunk] = sum over the chunk's frames t of  -(X[b][r][c] - lse) * w[b*w_bstride + k] / rlen[b][r]  with
+ * k = tmap ? tmap[b*tmap_bstride + tgt0[b][t]] : tgt0[b][t] (frames with k < 0 are skipped), c = cols ? cols[b*cols_bstride
+ * + k] : k, r = ridx ? ridx[b][t] : t, and lse = col_lse ? col_lse[b][c] : log-sum-exp of row r over the selected columns.
+ * Serves frame_loss(_tdu), cross_attn_loss(_tdu) in both directions and both InfoNCE terms (loss.py:211-277, 280-341). */
+int factk_loss_pick(const float* X, int ldx, int xslot, int ncol, const int32_t* cols, int cols_bstride,
+                    const int32_t* ncols, const int32_t* ridx, const int32_t* rlen, const float* col_lse, int ld_lse,
+                    const int32_t* tgt0, const int32_t* tmap, int tmap_bstride, const float* w, int w_bstride,
+                    float* part_sum, float* part_cnt, int B, int slot, const int32_t* len, int nchunk, void* stream);
+
+/* smooth_loss numerator (loss.py:8-19): sum over t < len-1 and c of min((logp[t+1][c] - logp[t][c])^2, 16). */
+int factk_loss_smooth(const float* X, int ldx, int ncol, float* part, int B, int slot, const int32_t* len, int nchunk,
+                      void* stream);
+
+/* out[b][c] = log-sum-exp over rows r < nrows[b] of X[b][r][c]; rows whose (mapped) rmask0 entry is negative are skipped. */
+int factk_col_lse(const float* X, int ldx, int xslot, int ncol, const int32_t* nrows, const int32_t* rmask0,
+                  const int32_t* rmap, int rmap_bstride, float* out, int ldo, int B, void* stream);
+
+/* action_token_loss (loss.py:196-209): out[b*out_stride] = class-weighted cross entropy of the tokens, unmatched tokens
+ * labelled with the null class C1-1. */
+int factk_token_loss(const float* aclogit, int M, int C1, const int32_t* aind, const int32_t* sind, const int32_t* nmatch,
+                     int kmax, const int32_t* transcript, int smax, const float* cweight, float* out, int out_stride,
+                     int B, void* stream);
+
+/* Per-block formulas, block mean and the FACT / InfoNCE mix.  block_type: HOST array [nb] (0 input, 1 update, 2 update
+ * with temporal down/up-sampling); npred: [nb][B] predicted segment counts (type 2 blocks).  out[b] = {loss, fact_loss,
+ * contrastive_loss, has_contrastive, block losses...}. */
+int factk_loss_combine(const float* ws, int nb, const int32_t* block_type, int B, int nchunk, const int32_t* len,
+                       const int32_t* npred, int C, int M, float sw, int use_clip, float fact_w, float con_w, int nseen,
+                       const int32_t* nvalid, float* out, int ldo, void* stream);
 
 #ifdef __cplusplus
 }
