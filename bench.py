@@ -146,6 +146,9 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    from fact_clip_b200.parallel import bind_to_gpu_numa_node
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)      # before the pinned feature buffers exist
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
@@ -263,7 +266,7 @@ def main():
                    'videos_per_gpu': B, 'frames_per_step': frames_step,
                    'launch': 'cuda-graph' if eng.use_graph else 'eager',
                    'l2_policy': f'inputs larger than L2 ({B * T * IN_DIM * 4 / 2**20:.0f} MiB of fp32 features per step)',
-                   'segments_per_U_block_rank0': [[min(s), max(s)] for s in nseg]},
+                   'segments_per_U_block_rank0': [[min(s), max(s)] for s in nseg], 'numa_rank0': numa},
         'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': B * T * IN_DIM * 4 * world,
                 'd2h_bytes_per_step': B * T * 8 * world, 'ms_per_step': ms_e2e / args.steps,
@@ -278,10 +281,15 @@ def main():
                      'traffic': TCN_DRAM_BYTES_PER_LAUNCH.get(B), 'traffic_source': 'profiles/r1_tcn_layer_ncu_full.txt (dram read + write per launch, ncu --set full)',
                      'peak_source': pk['src'] + ' (sustained bf16, kernel timed inside a long step)',
                      'ms_per_layer': t_layer_ms, 'share_of_step': tcn_ms / args.steps / (ms_eager / args.steps),
-                     'timed_in': 'eager pass of the same steps (CUDA events around each launch); the headline loop replays one CUDA graph per step'},
+                     'timed_in': 'eager pass of the same steps (CUDA events around each launch); the headline loop replays one CUDA graph per step',
+                     # 34.6 MFLOP of algorithmic work per frame at this config (segment-count dependent terms
+                     # excluded) -> the whole forward against the same tensor peak, per GPU
+                     'whole_forward': {'flops_per_frame': 34.6e6, 'achieved': value / world * 34.6e6 / 1e12, 'unit': 'TFLOP/s',
+                                       'frac': value / world * 34.6e6 / 1e12 / pk['tf_sust']}},
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)       # the CPU baseline may use every host core
             threads = os.cpu_count() or 1
             n_cpu = 64      # ~10 s of CPU work on the box's 16 cores
             fps, dt = cpu_baseline(n_cpu, threads)

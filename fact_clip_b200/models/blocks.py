@@ -195,6 +195,10 @@ class _FactBase(nn.Module):
             if vals[b, 3] > 0:
                 s['loss'].update(fact_loss=float(vals[b, 1]), contrastive_loss=float(vals[b, 2]))
             s['block_losses'] = vals[b, 4:4 + nb].tolist()
+        # attributes the training script reads after the call (scripts/train.py:286-289): those of the last video
+        self.loss_list = [res['values'][-1, 4 + i] for i in range(nb)]
+        if vals[-1, 3] > 0:
+            self.fact_loss, self.contrastive_loss = res['values'][-1, 1], res['values'][-1, 2]
         return res['values'][:, 0].mean(), saves
 
     def _forward_with_transcripts(self, seqs, label_list, forced_preds=None):

@@ -63,3 +63,44 @@ def gather_predictions(local_ids, local_preds, group=None, dst=0):
             out[vid] = b[off:off + n].astype(np.int64)
             off += n
     return out
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated:
+    pinned pages are placed on the allocating thread's node, and a feature buffer that sits behind the inter-socket link
+    caps the host->device copies of an 8-GPU sweep well below what the two sockets' memory can feed.  Reads sysfs only
+    (PCI address from the CUDA device properties); returns a small report dict, never raises.  FACTK_NUMA_BIND=0 disables."""
+    import os
+    rep = {'bound': False}
+    if os.environ.get('FACTK_NUMA_BIND', '1') == '0':
+        rep['why'] = 'disabled'
+        return rep
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f'{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as f:
+            node = int(f.read().strip())
+        rep.update(pci=bdf, node=node)
+        if node < 0:
+            rep['why'] = 'no NUMA information for the device'
+            return rep
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpus = _parse_cpulist(f.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            rep['why'] = 'no allowed CPU on the node'
+            return rep
+        os.sched_setaffinity(0, cpus)
+        rep.update(bound=True, cpus=len(cpus))
+    except Exception as e:          # topology files missing in a container, old torch without pci ids, ...
+        rep['why'] = f'{type(e).__name__}: {e}'
+    return rep
