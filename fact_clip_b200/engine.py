@@ -37,6 +37,8 @@ class FactEngine:
         self._wcache, self._wsig = {}, None
         self._graphs = {}
         self.use_graph = True        # replay the whole batched forward as ONE CUDA graph (no per-kernel host launch cost)
+        # token state of a call: query-token models always use these; FACT.trans models set them per video in run()
+        self.ntok, self.action_init, self.transcript = hp['ntoken'], None, None
         self.last_launches = 0
 
     # ------------------------------------------------------------------ memory / weights
