@@ -37,7 +37,7 @@ def hparams_from_cfg(cfg, in_dim, n_classes):
     blocks = []
     base = bi
     for t in g(g(cfg, 'FACT'), 'block'):
-        if t == 'i':
+        if t in 'iI':
             cur = dict(bi)
         else:
             node = g(cfg, 'Bu' if t == 'u' else 'BU')
@@ -51,6 +51,7 @@ def hparams_from_cfg(cfg, in_dim, n_classes):
         ntoken=g(g(cfg, 'FACT'), 'ntoken'), fpos=bool(g(g(cfg, 'FACT'), 'fpos')),
         mwt=float(g(g(cfg, 'FACT'), 'mwt')), trans=bool(g(g(cfg, 'FACT'), 'trans')),
         temp=float(g(clip, 'temp')) if clip is not None else 0.07,
+        s_layers=int(g(g(cfg, 'BU'), 's_layers')),
     )
 
 
