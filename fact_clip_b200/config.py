@@ -156,11 +156,11 @@ def hparams(cfg, in_dim, n_classes):
     """Flatten the cfg keys the forward reads (after the constructor's update_from) into plain dicts."""
     blocks = []
     for t in cfg.FACT.block:
-        node = {'i': cfg.Bi, 'u': cfg.Bu, 'U': cfg.BU}[t]
+        node = {'i': cfg.Bi, 'I': cfg.Bi, 'u': cfg.Bu, 'U': cfg.BU}[t]
         bc = {k: node[k] for k in _BLOCK_KEYS}
         bc['type'] = t
         blocks.append(bc)
     clip = cfg.CLIP if 'CLIP' in cfg else None
     return dict(in_dim=in_dim, n_classes=n_classes, blocks=blocks, ntoken=cfg.FACT.ntoken, fpos=bool(cfg.FACT.fpos),
-                mwt=float(cfg.FACT.mwt), trans=bool(cfg.FACT.trans),
+                mwt=float(cfg.FACT.mwt), trans=bool(cfg.FACT.trans), s_layers=int(cfg.BU.s_layers),
                 temp=float(clip.temp) if clip is not None else 0.07)

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) fuse_eval_kernel(const float* _
                                                                   const float* __restrict__ flogit, int ldf, float weight,
                                                                   int64_t* __restrict__ pred, int slot,
                                                                   const int32_t* __restrict__ len, int M, int C,
-                                                                  int chunks_per_video) {
+                                                                  int chunks_per_video, int f_logp) {
     __shared__ int valid[EV_MAXM];
     __shared__ int any_valid;
     const int b = blockIdx.x / chunks_per_video;
@@ -53,12 +53,15 @@ __global__ void __launch_bounds__(EV_WARPS * 32) fuse_eval_kernel(const float* _
         const size_t row = (size_t)b * slot + t;
         const float* fl = flogit + row * (size_t)ldf;
         // frame-branch softmax statistics
-        float fm = -INFINITY;
-        for (int c = lane; c < C; c += 32) fm = fmaxf(fm, fl[c]);
-        fm = warp_max(fm);
-        float fs = 0.f;
-        for (int c = lane; c < C; c += 32) fs += __expf(fl[c] - fm);
-        fs = 1.f / warp_sum(fs);
+        float fm = 0.f, fs = 1.f;        // f_logp: the row already holds log-probabilities, used as exp(.) un-normalised
+        if (!f_logp) {                   // (blocks_SepVerbNoun.py:308: products of verb and noun probabilities)
+            fm = -INFINITY;
+            for (int c = lane; c < C; c += 32) fm = fmaxf(fm, fl[c]);
+            fm = warp_max(fm);
+            fs = 0.f;
+            for (int c = lane; c < C; c += 32) fs += __expf(fl[c] - fm);
+            fs = 1.f / warp_sum(fs);
+        }
 
         int mstar = -1;
         float qm = 0.f, qs = 0.f;
@@ -171,13 +174,13 @@ using namespace factk;
 
 extern "C" int factk_fuse_eval(const float* action_clogit, const float* attn, int lda, int attn_slot,
                                const int32_t* seg_label, const float* flogit, int ldf, float weight, int64_t* pred, int B,
-                               int slot, const int32_t* len, int M, int C, void* stream) {
+                               int slot, const int32_t* len, int M, int C, int f_logp, void* stream) {
     FACTK_REQUIRE((M == 0 || action_clogit) && flogit && pred && B > 0 && slot > 0 && C > 0, "factk_fuse_eval: bad args");
     FACTK_REQUIRE(M >= 0 && M <= EV_MAXM, "factk_fuse_eval: at most %d tokens", EV_MAXM);
     FACTK_REQUIRE(M == 0 || attn != nullptr, "factk_fuse_eval: attention required when M > 0");
     const int cpv = (slot + EV_FRAMES - 1) / EV_FRAMES;
     fuse_eval_kernel<<<(unsigned)(cpv * B), EV_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        action_clogit, attn, lda, attn_slot, seg_label, flogit, ldf, weight, pred, slot, len, M, C, cpv);
+        action_clogit, attn, lda, attn_slot, seg_label, flogit, ldf, weight, pred, slot, len, M, C, cpv, f_logp);
     return check_launch("factk_fuse_eval");
 }
 

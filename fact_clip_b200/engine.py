@@ -37,6 +37,8 @@ class FactEngine:
         self._wcache, self._wsig = {}, None
         self._graphs = {}
         self.use_graph = True        # replay the whole batched forward as ONE CUDA graph (no per-kernel host launch cost)
+        # Epic verb/noun model (blocks_SepVerbNoun.py): two class heads, action table (verb id, noun id) per action
+        self.vn = hp.get('vn')
         # token state of a call: query-token models always use these; FACT.trans models set them per video in run()
         self.ntok, self.action_init, self.transcript = hp['ntoken'], None, None
         self.last_launches = 0
@@ -149,11 +151,34 @@ class FactEngine:
     def cat(self, *names):
         return self.derived(('cat',) + names, lambda: torch.cat([self.p(n) for n in names], 0))
 
+    # ------------------------------------------------------------------ class heads
+    def ncls(self, tokens=False):
+        """Width of the class-logit tail of a feature row: C (+1 null class for tokens), or both verb/noun heads."""
+        if self.vn is None:
+            return self.hp['n_classes'] + (1 if tokens else 0)
+        n1, n2 = self.hp['n_classes']
+        return n1 + n2 + (2 if tokens else 0)
+
+    def vn_table(self):
+        mk = lambda k: torch.tensor(self.vn[k], dtype=torch.int32, device=self.dev)
+        return self.derived(('vn_vids',), lambda: mk(0)), self.derived(('vn_nids',), lambda: mk(1))
+
+    def splice(self, x, clogit, len=None, tokens=False, pred=None):
+        """Block.process_feature in place on the class tail of x (blocks.py:195-202; blocks_SepVerbNoun.py:229-234 for the
+        two-head model) + the segmentation argmax for the next TDU block when ``pred`` is given."""
+        if self.vn is None:
+            return ops.softmax_splice(x, self.ncls(tokens), clogit, pred, len=len)
+        n1, n2 = self.hp['n_classes']
+        vids, nids = self.vn_table()
+        k = 1 if tokens else 0
+        ops.vn_splice(x, n1 + k, n2 + k, clogit, vids if pred is not None else None, nids if pred is not None else None,
+                      pred, len=len)
+
     # ------------------------------------------------------------------ frame branch
     def frame_branch(self, pfx, bc, x, in_map, tag):
         """MSTCN / MSTCN2 (models/basic.py:200-220, 263-281) + process_feature (models/blocks.py:195-202).
         x: [B, slot, Din].  Returns (frame_feature [B,slot,H] act dtype, frame_clogit fp32, pred int32)."""
-        B, slot, F, H, Lr, C = self.B, self.slot, bc['f_dim'], bc['hid_dim'], bc['f_layers'], self.hp['n_classes']
+        B, slot, F, H, Lr, C = self.B, self.slot, bc['f_dim'], bc['hid_dim'], bc['f_layers'], self.ncls()
         ln = self.len
         fa, fb = self.zbuf('f_a', (B, slot, F), self.act), self.zbuf('f_b', (B, slot, F), self.act)
         m2, ng = bc['f'] == 'm2', bc['f_ngp']
@@ -196,7 +221,7 @@ class FactEngine:
         self.mm([S(cur, self.taps(pfx + 'conv_out.weight')[0])], H, out, len=ln, bias=self.p(pfx + 'conv_out.bias'), tag='conv_out')
         clogit = self.buf('fclogit_' + tag, (B, slot, C))
         pred = self.buf('fpred_' + tag, (B, slot), torch.int32)
-        ops.softmax_splice(out, C, clogit, pred, len=ln)
+        self.splice(out, clogit, len=ln, pred=pred)
         return out, clogit, pred
 
     @staticmethod
@@ -242,9 +267,11 @@ class FactEngine:
         self.lin(h, self.p(q + 'linear2.weight'), A, t, bias=self.p(q + 'linear2.bias'), res=x)
         ops.layernorm(t, self.p(q + n_a), self.p(q + n_b), x)
 
-    def sca_decoder(self, pfx, bc, frame, tag):
-        """SCADecoder over SCALayer (models/basic.py:542-557, 494-523): tokens attend frames. -> [B,M,H] fp32."""
+    def sca_decoder(self, pfx, bc, frame, tag, rlen=None, pos_idx=None):
+        """SCADecoder over SCALayer (models/basic.py:542-557, 494-523): tokens attend the memory rows ``frame`` (frames; or
+        segments with ``rlen`` rows per video and positions frame_pos[pos_idx], blocks_SepVerbNoun.py:380-382). -> [B,M,H] fp32."""
         B, slot, M, A, H, nh = self.B, self.slot, self.ntok, bc['a_dim'], bc['hid_dim'], bc['a_nhead']
+        rlen = self.len if rlen is None else rlen
         qpos = self.qpos()
         tgt = self.buf('tok_x', (B, M, A))
         if self.action_init is None:
@@ -272,12 +299,12 @@ class FactEngine:
             self.lin(tgt, wq, A, cq, pos=qpos, bias=cb[:A])
             if fpos is None:
                 wkv = self.derived(('wkv', c), lambda: torch.cat([wk, wv], 0))
-                self.mm([S(frame, wkv)], 2 * A, kv, len=self.len, bias=cb[A:], tag='sca_kv')
+                self.mm([S(frame, wkv)], 2 * A, kv, len=rlen, bias=cb[A:], tag='sca_kv')
             else:
-                ops.gemm([S(frame, wk, pos=fpos)], A, kv[:, :, :A], len=self.len, bias=cb[A:2 * A])
-                self.mm([S(frame, wv)], A, kv[:, :, A:], len=self.len, bias=cb[2 * A:])
+                ops.gemm([S(frame, wk, pos=fpos, pos_idx=pos_idx)], A, kv[:, :, :A], len=rlen, bias=cb[A:2 * A])
+                self.mm([S(frame, wv)], A, kv[:, :, A:], len=rlen, bias=cb[2 * A:])
             o = self.buf('tok_o', (B, M, A))
-            ops.attn_rows(cq, kv[:, :, :A], kv[:, :, A:], o, nh, ws, len=self.len)
+            ops.attn_rows(cq, kv[:, :, :A], kv[:, :, A:], o, nh, ws, len=rlen)
             self.lin(o, self.p(c + 'out_proj.weight'), A, t, bias=self.p(c + 'out_proj.bias'), res=tgt)
             ops.layernorm(t, self.p(q + 'norm2.weight'), self.p(q + 'norm2.bias'), tgt)
             self._ffn_ln(q, tgt, 'norm3.weight', 'norm3.bias', tag)
@@ -327,18 +354,17 @@ class FactEngine:
             ops.layernorm(x, self.p(pfx + 'layernorm.weight'), self.p(pfx + 'layernorm.bias'), out)
         return out
 
-    def action_branch(self, pfx, bc, x, tag, frame=None):
+    def action_branch(self, pfx, bc, x, tag, frame=None, rlen=None, pos_idx=None):
         """Block.create_abranch dispatch (models/blocks.py:215-232)."""
         if bc['a'] in ('gru', 'gru_om'):
             return self.gru_decoder(pfx, bc, self.action_init if frame is not None else x, tag)
         if frame is not None:
-            return self.sca_decoder(pfx, bc, frame, tag)
+            return self.sca_decoder(pfx, bc, frame, tag, rlen=rlen, pos_idx=pos_idx)
         return self.sa_decoder(pfx, bc, x, tag)
 
     def token_splice(self, action, tag):
-        C = self.hp['n_classes']
-        clogit = self.buf('aclogit_' + tag, (self.B, self.ntok, C + 1))
-        ops.softmax_splice(action, C + 1, clogit)
+        clogit = self.buf('aclogit_' + tag, (self.B, self.ntok, self.ncls(tokens=True)))
+        self.splice(action, clogit, tokens=True)
         return clogit
 
     # ------------------------------------------------------------------ cross attention
@@ -420,10 +446,12 @@ class FactEngine:
         frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, fr, False, tag)
         return frame, action
 
-    def update_block_tdu(self, i, bc, frame, action, pred, st):
-        """UpdateBlockTDU.forward (models/blocks.py:417-485) with the segmentation kept on device."""
+    def downsample(self, i, bc, frame, pred, st, gru_layers):
+        """temporal_downsample (models/blocks.py:417-437; blocks_SepVerbNoun.py:279-303) with the segmentation kept on device:
+        run-length segments of ``pred``, segment mean, (stacked) bi-GRU, ReLU, seg_combine, process_feature.
+        Returns (seg rows [B,slot,H], segment count [B], position index or None)."""
         pfx, tag = f'block_list.{i}.', f'b{i}'
-        B, slot, H, F, C = self.B, self.slot, bc['hid_dim'], bc['f_dim'], self.hp['n_classes']
+        B, slot, H = self.B, self.slot, bc['hid_dim']
         Hh = H // 2
         I32 = torch.int32
         seg_label, seg_start = self.buf('seg_label_' + tag, (B, slot), I32), self.buf('seg_start_' + tag, (B, slot), I32)
@@ -435,18 +463,38 @@ class FactEngine:
         ws = self.buf('segmean_ws', (ops.segment_mean_ws(B, slot, H),))
         ops.segment_mean(frame, seg0, seg_label, seg_start, seg_len, nseg, ws=ws)
         g = pfx + 'seg_update.'
-        gi = self.buf('gru_gi', (B, slot, 6 * Hh))
-        self.mm([S(seg0, self.cat(g + 'weight_ih_l0', g + 'weight_ih_l0_reverse'))], 6 * Hh, gi, len=nseg,
-                bias=self.cat(g + 'bias_ih_l0', g + 'bias_ih_l0_reverse'), tag='gru_in')
-        seg1 = self.buf('seg1', (B, slot, H), self.act)
-        ops.gru_bidir(gi, self.p(g + 'weight_hh_l0'), self.p(g + 'bias_hh_l0'), self.p(g + 'weight_hh_l0_reverse'),
-                      self.p(g + 'bias_hh_l0_reverse'), seg1, nseg, relu=True,
-                      mma=(self.mode == 'bf16' and self.use_tc and Hh == 256))
-        seg2 = self.buf('seg2', (B, slot, H), self.act)
-        self.mm([S(seg1, self.p(pfx + 'seg_combine.weight'))], H, seg2, len=nseg, bias=self.p(pfx + 'seg_combine.bias'), tag='seg_combine')
-        st['seg_clogit'] = self.buf('seg_clogit_' + tag, (B, slot, C))
-        ops.softmax_splice(seg2, C, st['seg_clogit'], None, len=nseg)
-        pidx = seg_center if self.frame_pos is not None else None
+        cur = seg0
+        for l in range(gru_layers):       # layer l > 0 reads the concatenated directions of layer l-1 (nn.GRU stacking)
+            gi = self.buf('gru_gi', (B, slot, 6 * Hh))
+            self.mm([S(cur, self.cat(f'{g}weight_ih_l{l}', f'{g}weight_ih_l{l}_reverse'))], 6 * Hh, gi, len=nseg,
+                    bias=self.cat(f'{g}bias_ih_l{l}', f'{g}bias_ih_l{l}_reverse'), tag='gru_in')
+            nxt = self.buf(f'seg1_{l % 2}', (B, slot, H), self.act)
+            ops.gru_bidir(gi, self.p(f'{g}weight_hh_l{l}'), self.p(f'{g}bias_hh_l{l}'), self.p(f'{g}weight_hh_l{l}_reverse'),
+                          self.p(f'{g}bias_hh_l{l}_reverse'), nxt, nseg, relu=(l == gru_layers - 1),
+                          mma=(self.mode == 'bf16' and self.use_tc and Hh == 256))
+            cur = nxt
+        seg2 = self.buf('seg2_' + tag if self.vn is not None else 'seg2', (B, slot, H), self.act)
+        self.mm([S(cur, self.p(pfx + 'seg_combine.weight'))], H, seg2, len=nseg, bias=self.p(pfx + 'seg_combine.bias'), tag='seg_combine')
+        st['seg_clogit'] = self.buf('seg_clogit_' + tag, (B, slot, self.ncls()))
+        self.splice(seg2, st['seg_clogit'], len=nseg)
+        return seg2, nseg, (seg_center if self.frame_pos is not None else None)
+
+    def input_block_tdu(self, i, bc, x, st, forced_pred=None):
+        """InputBlockTDU.forward (blocks_SepVerbNoun.py:367-398): the tokens attend the SEGMENTS of the frame branch's own
+        prediction; the frame feature leaves the block as the frame branch produced it."""
+        pfx, tag = f'block_list.{i}.', f'b{i}'
+        frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, x, True, tag)
+        seg, nseg, pidx = self.downsample(i, bc, frame, st['pred'] if forced_pred is None else forced_pred, st, 2)
+        action = self.action_branch(pfx + 'action_branch.', bc, None, tag, frame=seg, rlen=nseg, pos_idx=pidx)
+        st['action_clogit'] = self.token_splice(action, tag)
+        return frame, action
+
+    def update_block_tdu(self, i, bc, frame, action, pred, st):
+        """UpdateBlockTDU.forward (models/blocks.py:417-485; blocks_SepVerbNoun.py:445-483)."""
+        pfx, tag = f'block_list.{i}.', f'b{i}'
+        B, slot, H, F = self.B, self.slot, bc['hid_dim'], bc['f_dim']
+        seg2, nseg, pidx = self.downsample(i, bc, frame, pred, st, self.hp['s_layers'])
+        seg_label = st['seg_label']
         tok, st['f2a_attn_logit'], st['f2a_attn_seg'] = self.f2a(pfx + 'f2a_layer.', bc, seg2, nseg, pidx, action, tag, self.keep)
         action = self.action_branch(pfx + 'action_branch.', bc, tok, tag)
         st['action_clogit'] = self.token_splice(action, tag)
@@ -540,6 +588,32 @@ class FactEngine:
         self._slot_free[k] = done
         return _Pending(done, host, lengths, out)
 
+    def _vn_eval(self, out, pred_out):
+        """Verb/noun model: action log-probabilities (combine_verb_noun_to_action, blocks_SepVerbNoun.py:188-226) of the last
+        block -- of every block when the attributes are kept -- and Block._eval on them (:307-329)."""
+        B, slot, M, ln = self.B, self.slot, self.ntok, self.len
+        n1, n2 = self.hp['n_classes']
+        vids, nids = self.vn_table()
+        A = vids.numel()
+        for i, st in enumerate(out['blocks']):
+            if not (self.keep or st is out['blocks'][-1]):
+                continue
+            tag = f'b{i}'
+            st['frame_logp'] = self.buf('frame_logp_' + tag, (B, slot, A))
+            ops.vn_combine(st['frame_clogit'], n1, n2, vids, nids, st['frame_logp'], len=ln)
+            st['action_logp'] = self.buf('action_logp_' + tag, (B, M, A + 1))
+            ops.vn_combine(st['action_clogit'], n1 + 1, n2 + 1, vids, nids, st['action_logp'], with_null=True)
+            if self.keep:
+                st['seg_logp'] = self.buf('seg_logp_' + tag, (B, slot, A))
+                ops.vn_combine(st['seg_clogit'], n1, n2, vids, nids, st['seg_logp'], len=st['nseg'])
+        last = out['blocks'][-1]
+        assert 'a2f_attn_seg' in last, 'the verb/noun model ends in an update block (its eval reads a2f_attn)'
+        pred64 = pred_out if pred_out is not None else self.buf('pred64', (B, slot), torch.int64)
+        ops.fuse_eval(last['action_logp'], last['a2f_attn_seg'], last['frame_logp'], self.hp['mwt'], pred64, M, A,
+                      seg_label=last['seg_label'], len=ln, f_logp=True)
+        out['pred'] = pred64
+        return out
+
     @torch.no_grad()
     def run_packed_graphed(self, x, ln, lengths, pred_out=None):
         """``run_packed`` captured once per (input buffer, lengths) into a CUDA graph and replayed afterwards: the forward has
@@ -590,6 +664,14 @@ class FactEngine:
             st = {}
             if bc['type'] == 'i':
                 frame, action = self.input_block(i, bc, frame, st)
+            elif bc['type'] == 'I':
+                fp = None
+                if forced_preds is not None:
+                    fp = self.buf(f'forced_pred_{u}', (B, slot), torch.int32)
+                    for b in range(B):
+                        fp[b, :lengths[b]].copy_(forced_preds[u][b].to(torch.int32), non_blocking=True)
+                frame, action = self.input_block_tdu(i, bc, frame, st, fp)
+                u += 1
             elif bc['type'] == 'u':
                 frame, action = self.update_block(i, bc, frame, action, st)
             else:
@@ -605,6 +687,8 @@ class FactEngine:
             stash.append(st)
         last = stash[-1]
         out = dict(blocks=stash, lengths=lengths)
+        if self.vn is not None:
+            return self._vn_eval(out, pred_out)
         if self.clip and 'text_embeddings' in self._p and self._p['text_embeddings'] is not None:
             P = self.p('frame_projection.projection.0.weight').shape[0]
             h1 = self.buf('clip_h1', (B, slot, P), self.act)

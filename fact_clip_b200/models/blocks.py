@@ -112,8 +112,6 @@ class UpdateBlockTDU(Block):
         self.action_branch = self.create_abranch(c)
         self.a2f_layer = self.create_cross_attention(c, c.f_dim)
         self.sf_merge = nn.Sequential(nn.Linear(c.hid_dim + c.f_dim, c.f_dim), nn.ReLU())
-        if c.s_layers != 1:
-            raise NotImplementedError('BU.s_layers != 1 is used by no shipped config')
 
 
 class TDU:
@@ -162,6 +160,8 @@ class _FactBase(nn.Module):
     def engine(self):
         if self._engine is None or self._engine.mode != self.compute_mode:
             hp = cfgmod.hparams(self.cfg, self.in_dim, self.num_classes)
+            if hasattr(self, 'vids'):       # Epic verb/noun model: action id -> (verb id, noun id)
+                hp['vn'] = (self.vids, self.nids)
             self._engine = FactEngine(self, hp, clip=isinstance(self, FACT_CLIP), mode=self.compute_mode)
         return self._engine
 

@@ -237,12 +237,28 @@ def gather_rows(src, idx, out, E, len=None):
            _row_ld(out), B, slot, L.ptr(len), E, L.stream())
 
 
-def fuse_eval(action_clogit, attn, flogit, weight, pred, M, C, seg_label=None, len=None):
+def fuse_eval(action_clogit, attn, flogit, weight, pred, M, C, seg_label=None, len=None, f_logp=False):
     B, slot = flogit.shape[0], flogit.shape[1]
     COUNTERS['launches'] += 1
     _call('factk_fuse_eval', None, L.ptr(action_clogit), L.ptr(attn), _row_ld(attn) if attn is not None else 0,
            attn.shape[1] if attn is not None else 0, L.ptr(seg_label), flogit.data_ptr(), _row_ld(flogit),
-           float(weight), pred.data_ptr(), B, slot, L.ptr(len), M, C, L.stream())
+           float(weight), pred.data_ptr(), B, slot, L.ptr(len), M, C, int(f_logp), L.stream())
+
+
+def vn_splice(x, n1, n2, clogit, vids=None, nids=None, pred=None, len=None, H=None):
+    """Verb/noun process_feature in place on x [B, slot, ld]; with pred: segmentation argmax over the action table."""
+    B, slot = x.shape[0], x.shape[1]
+    H = x.shape[-1] if H is None else H
+    COUNTERS['launches'] += 1
+    _call('factk_vn_splice', None, x.data_ptr(), L.dt(x), B, slot, L.ptr(len), _row_ld(x), H, n1, n2, clogit.data_ptr(),
+          L.ptr(vids), L.ptr(nids), vids.numel() if vids is not None else 0, L.ptr(pred), L.stream())
+
+
+def vn_combine(clogit, k1, k2, vids, nids, out, with_null=False, len=None):
+    B, slot = clogit.shape[0], clogit.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_vn_combine', None, clogit.data_ptr(), _row_ld(clogit), k1, k2, vids.data_ptr(), nids.data_ptr(), vids.numel(),
+          int(with_null), out.data_ptr(), _row_ld(out), B, slot, L.ptr(len), L.stream())
 
 
 def fuse_eval_transcript(attn, flogit, weight, transcript, ntr, pred, C, seg_label=None, len=None):

@@ -214,10 +214,11 @@ int factk_gather_rows(const float* in, int ldi, int in_slot, const int32_t* idx,
 /* Prob fusion + argmax: Block._eval (blocks.py:242-261) / FACT_CLIP.eval_with_clip (blocks.py:854-887).
  * action_clogit fp32 [B][M][C+1]; attn fp32 [B][attn_slot][lda] (a2f attention, row = frame, or row =
  * segment when seg_label != NULL); flogit fp32 [B][slot][ldf] frame-branch logits (frame_clogit, or
- * CLIP similarity / temp) -> pred int64 [B][slot]. */
+ * CLIP similarity / temp) -> pred int64 [B][slot].  f_logp != 0: flogit rows are log-probabilities used as exp(.)
+ * WITHOUT re-normalisation (blocks_SepVerbNoun.py:307-329, where they are verb x noun products). */
 int factk_fuse_eval(const float* action_clogit, const float* attn, int lda, int attn_slot,
                     const int32_t* seg_label, const float* flogit, int ldf, float weight,
-                    int64_t* pred, int B, int slot, const int32_t* len, int M, int C, void* stream);
+                    int64_t* pred, int B, int slot, const int32_t* len, int M, int C, int f_logp, void* stream);
 
 /* Block._eval_w_transcript (blocks.py:263-275), FACT.trans models (the tokens are the video's transcript): per frame
  * prob[n] = (1 - weight) softmax_n(attn[row, :N]) + weight softmax_c(flogit)[transcript[n]], pred = transcript[argmax_n].
@@ -230,6 +231,17 @@ int factk_fuse_eval_transcript(const float* attn, int lda, int attn_slot, const 
 /* Token initialisation of FACT.trans models (blocks.py:74-79): out[n,:A] = embed[transcript[n],:A] + pe[n,:A]. */
 int factk_embed_tokens(const float* embed, int lde, const int32_t* transcript, const float* pe, int ldpe,
                        float* out, int ldo, int N, int A, void* stream);
+
+/* Epic verb/noun heads (blocks_SepVerbNoun.py).  factk_vn_splice: process_feature (:229-234) in place on the last n1+n2
+ * channels of X (two softmaxes), raw logits to clogit_out [B][slot][n1+n2]; with pred_out, also the segmentation argmax
+ * over the nact action classes a = (vids[a], nids[a]) of verb-prob x noun-prob (:281-290). */
+int factk_vn_splice(void* X, int dtype, int B, int slot, const int32_t* len, int ld, int H, int n1, int n2,
+                    float* clogit_out, const int32_t* vids, const int32_t* nids, int nact, int32_t* pred_out, void* stream);
+
+/* combine_verb_noun_to_action(apply_log=True) (:188-226): out[b][t][a] = log_softmax(clogit[:k1])[vids[a]] +
+ * log_softmax(clogit[k1:k1+k2])[nids[a]]; with_null appends the null action (last class of both heads). */
+int factk_vn_combine(const float* clogit, int ldc, int k1, int k2, const int32_t* vids, const int32_t* nids, int nact,
+                     int with_null, float* out, int ldo, int B, int slot, const int32_t* len, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Training-loss VALUE on device (reference models/loss.py and the compute_loss methods of models/blocks.py:313-320,

@@ -1,0 +1,79 @@
+"""Epic verb/noun model (fact_clip_b200.models.blocks_SepVerbNoun.FACT) on the GPU against fixtures generated from the
+unmodified reference (tests/golden/vn_*.pt)."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, GOLDEN
+
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import fact_oracle as O  # noqa: E402
+import vn_oracle as VO  # noqa: E402
+from fact_clip_b200 import config as C  # noqa: E402
+from fact_clip_b200.models.blocks_SepVerbNoun import FACT  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+VN_CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, 'vn_*.pt')))
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def build(g, mode):
+    n1, n2 = g['n_classes']
+    net = FACT(C.tiny(**g['tiny_kwargs']), g['in_dim'], n1, n2, action_pairs=list(zip(g['vids'], g['nids'])))
+    net.load_state_dict(g['state_dict'], strict=False)
+    net.compute_mode, net.keep_attn = mode, True
+    return net.to(DEV).eval()
+
+
+def check(net, vids, tol, seg=True):
+    for b, v in enumerate(vids):
+        net.stash_video(b)
+        for i, (blk, ref) in enumerate(zip(net.block_list, v['blocks'])):
+            if seg:
+                assert torch.equal(blk.tdu.seg_label.cpu(), ref['seg_label']), f'block {i} seg_label'
+                assert torch.equal(blk.tdu.seg_lens.cpu(), ref['seg_lens'])
+            for k in ('frame_logp', 'seg_logp', 'action_logp', 'f2a_attn_logit', 'f2a_attn', 'a2f_attn_logit', 'a2f_attn'):
+                if k in ref:
+                    got = getattr(blk, k)
+                    assert tuple(got.shape) == tuple(ref[k].shape), (k, got.shape, ref[k].shape)
+                    r = rel(got, ref[k])
+                    if ref[k].numel() < 16 and r >= tol:
+                        assert float((got.float().cpu() - ref[k]).abs().max()) < tol, (i, k)
+                        continue
+                    assert r < tol, f'video {b} block {i} {k}: rel-L2 {r:.3e}'
+
+
+@pytest.mark.parametrize('name', VN_CASES)
+def test_vn_golden_fp32(name):
+    g = torch.load(os.path.join(GOLDEN, name + '.pt'), weights_only=False)
+    net = build(g, 'fp32')
+    saves = net([v['x'].to(DEV) for v in g['videos']], [v['label'].to(DEV) for v in g['videos']])
+    check(net, g['videos'], 1e-4)
+    for s, v in zip(saves, g['videos']):
+        assert np.array_equal(s['pred'], v['pred'].numpy()) and s['pred'].dtype == np.int64
+
+
+@pytest.mark.parametrize('name', VN_CASES)
+def test_vn_golden_bf16_teacher_forced(name):
+    g = torch.load(os.path.join(GOLDEN, name + '.pt'), weights_only=False)
+    net = build(g, 'bf16')
+    hp = O.hparams_from_cfg(C.tiny(**g['tiny_kwargs']), g['in_dim'], g['n_classes'])
+    forced = [[] for _ in hp['blocks']]
+    for v in g['videos']:
+        with torch.no_grad():
+            o = VO.forward_video(g['state_dict'], hp, v['x'], g['vids'], g['nids'])
+        for u, st in enumerate(o['blocks']):
+            forced[u].append(st['tdu_pred'].to(DEV))
+    saves = net([v['x'].to(DEV) for v in g['videos']], [v['label'].to(DEV) for v in g['videos']], forced_preds=forced)
+    check(net, g['videos'], 2e-2)
+    agree = sum(int((s['pred'] == v['pred'].numpy()).sum()) for s, v in zip(saves, g['videos']))
+    assert agree / sum(len(v['pred']) for v in g['videos']) >= 0.999
