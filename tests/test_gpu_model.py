@@ -122,7 +122,8 @@ def test_batch_equals_single_and_deterministic():
 
 
 CFGS = [('gtea', 11, [1024]), ('havid_view0_lh_pt_holdout', 75, [1024, 700, 333]), ('breakfast', 48, [600, 450]),
-        ('epic_shape', 98, [1100])]
+        ('epic_shape', 98, [1100]),
+        ('havid_view0_lh_pt_holdout', 75, [4096, 4096])]       # the metric configuration at its full length
 
 
 @pytest.mark.parametrize('preset,ncls,lens', CFGS)
