@@ -49,6 +49,65 @@ __global__ void __launch_bounds__(256) softmax_splice_kernel(void* X, int dtype,
     }
 }
 
+// The same for C <= 32 * NV classes with the row's class tail held in registers: one load, one exp and one store per
+// element (the generic kernel above re-reads the tail three times and is instruction-issue bound, 90 % issue-active in
+// ncu on the frame-level launches).
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) splice_small_kernel(T* __restrict__ X, int B, int slot, const int32_t* __restrict__ len,
+                                                           int ld, int H, int C, float* __restrict__ clogit,
+                                                           int32_t* __restrict__ pred) {
+    int b, t;
+    if (!row_of_warp(B, slot, len, b, t)) return;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)b * slot + t;
+    T* x = X + row * (size_t)ld + (H - C);
+    float* cl = clogit + row * (size_t)C;
+    float v[NV];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < C ? to_f<T>(x[c]) : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+    }
+    mx = warp_max(mx);
+    float e[NV], sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        e[i] = __expf(v[i] - mx);          // exp(-inf) = 0 for the padding lanes
+        sum += e[i];
+    }
+    const float inv = 1.f / warp_sum(sum);
+    float best = -1.f;
+    int besti = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) {
+            const float p = e[i] * inv;
+            cl[c] = v[i];
+            x[c] = from_f<T>(p);
+            if (p > best) { best = p; besti = c; }   // strict > keeps the first index within a lane
+        }
+    }
+    if (pred) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) pred[row] = besti;
+    }
+}
+
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* X, int x_dtype, int ldx, const void* R, int r_dtype,
                                                         int ldr, const float* w, const float* bb, float eps, int relu,
                                                         void* Y, int y_dtype, int ldy, int B, int slot,
@@ -117,6 +176,41 @@ __global__ void __launch_bounds__(256) row_softmax_kernel(const float* L, int ld
         for (int c = M + lane; c < pad16; c += 32) P16[row * ldp16 + c] = __float2bfloat16_rn(0.f);
 }
 
+// Row softmax for M <= 32 * NV columns with the row held in registers (same arithmetic as above, one load / exp per element).
+template <int NV>
+__global__ void __launch_bounds__(256) row_softmax_small_kernel(const float* __restrict__ L, int ldl, float* __restrict__ P, int ldp,
+                                                                int B, int slot, const int32_t* __restrict__ len, int M, float scale,
+                                                                __nv_bfloat16* __restrict__ P16, int ldp16, int pad16) {
+    int b, t;
+    if (!row_of_warp(B, slot, len, b, t)) return;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)b * slot + t;
+    const float* l = L + row * (size_t)ldl;
+    float v[NV], mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < M ? l[c] * scale : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i] = __expf(v[i] - mx); sum += v[i]; }
+    const float inv = 1.f / warp_sum(sum);
+    float* p = P + row * (size_t)ldp;
+    __nv_bfloat16* p16 = P16 ? P16 + row * (size_t)ldp16 : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        const float pv = v[i] * inv;
+        if (c < M) p[c] = pv;
+        if (p16 && c < pad16) p16[c] = __float2bfloat16_rn(c < M ? pv : 0.f);
+    }
+    if (p16)
+        for (int c = 32 * NV + lane; c < pad16; c += 32) p16[c] = __float2bfloat16_rn(0.f);
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* in, int ldi, int in_slot, const int32_t* idx,
                                                           float* out, int ldo, int B, int slot, const int32_t* len, int E) {
     int b, t;
@@ -136,7 +230,20 @@ using namespace factk;
 extern "C" int factk_softmax_splice(void* X, int dtype, int B, int slot, const int32_t* len, int ld, int H, int C,
                                     float* clogit_out, int32_t* pred_out, void* stream) {
     FACTK_REQUIRE(X && clogit_out && B > 0 && slot > 0 && C > 0 && C <= H && H <= ld, "factk_softmax_splice: bad args");
-    softmax_splice_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(X, dtype, B, slot, len, ld, H, C, clogit_out, pred_out);
+    const cudaStream_t st = (cudaStream_t)stream;
+    const int nv = (C + 31) / 32;
+#define SPLICE(NV_)                                                                                                              \
+    (dtype == FACTK_BF16 ? splice_small_kernel<__nv_bfloat16, NV_><<<row_grid(B, slot), 256, 0, st>>>(                          \
+                               reinterpret_cast<__nv_bfloat16*>(X), B, slot, len, ld, H, C, clogit_out, pred_out)               \
+                         : splice_small_kernel<float, NV_><<<row_grid(B, slot), 256, 0, st>>>(reinterpret_cast<float*>(X), B,    \
+                                                                                                slot, len, ld, H, C, clogit_out, \
+                                                                                                pred_out))
+    if (nv == 1) SPLICE(1);
+    else if (nv == 2) SPLICE(2);
+    else if (nv == 3) SPLICE(3);
+    else if (nv == 4) SPLICE(4);
+    else softmax_splice_kernel<<<row_grid(B, slot), 256, 0, st>>>(X, dtype, B, slot, len, ld, H, C, clogit_out, pred_out);
+#undef SPLICE
     return check_launch("factk_softmax_splice");
 }
 
@@ -159,8 +266,14 @@ extern "C" int factk_row_softmax(const float* L, int ldl, float* P, int ldp, int
                                  float scale, void* P16, int ldp16, int pad16, void* stream) {
     FACTK_REQUIRE(L && P && B > 0 && slot > 0 && M > 0, "factk_row_softmax: bad args");
     FACTK_REQUIRE(P16 == nullptr || (pad16 >= M && pad16 <= ldp16), "factk_row_softmax: bad bf16 copy shape");
-    row_softmax_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(L, ldl, P, ldp, B, slot, len, M, scale,
-                                                                              reinterpret_cast<__nv_bfloat16*>(P16), ldp16, pad16);
+    const cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(P16);
+    const int nv = (M + 31) / 32;
+    if (nv == 1) row_softmax_small_kernel<1><<<row_grid(B, slot), 256, 0, st>>>(L, ldl, P, ldp, B, slot, len, M, scale, p16, ldp16, pad16);
+    else if (nv == 2) row_softmax_small_kernel<2><<<row_grid(B, slot), 256, 0, st>>>(L, ldl, P, ldp, B, slot, len, M, scale, p16, ldp16, pad16);
+    else if (nv == 3) row_softmax_small_kernel<3><<<row_grid(B, slot), 256, 0, st>>>(L, ldl, P, ldp, B, slot, len, M, scale, p16, ldp16, pad16);
+    else if (nv == 4) row_softmax_small_kernel<4><<<row_grid(B, slot), 256, 0, st>>>(L, ldl, P, ldp, B, slot, len, M, scale, p16, ldp16, pad16);
+    else row_softmax_kernel<<<row_grid(B, slot), 256, 0, st>>>(L, ldl, P, ldp, B, slot, len, M, scale, p16, ldp16, pad16);
     return check_launch("factk_row_softmax");
 }
 
