@@ -166,9 +166,14 @@ class _FactBase(nn.Module):
         return self._engine
 
     def forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
-        if compute_loss and (self.training or self.cfg.FACT.trans):
-            raise NotImplementedError('compute_loss=True is built for eval mode of the query-token models: the loss VALUE on '
-                                      'device (no backward, no dropout / masking). The training step is SURVEY.md 8(f) rank 1')
+        if self.training:
+            raise RuntimeError('the forward is built for eval mode: call net.eval() first. Training mode would need the '
+                               "reference's dropout, channel masking and time masking (blocks.py:58-70), which are part of the "
+                               'training step that is not built (SURVEY.md 8f rank 1); silently returning eval-mode results '
+                               'would be wrong')
+        if compute_loss and self.cfg.FACT.trans:
+            raise NotImplementedError('compute_loss=True is built for the query-token models (the loss VALUE on device, no '
+                                      'backward); the transcript-conditioned variant is not')
         if compute_loss and self.mcriterion is None:
             raise RuntimeError('compute_loss=True needs net.mcriterion = MatchCriterion(cfg, nclasses, bg_ids) (scripts/train.py:207)')
         dev = next(self.parameters()).device
@@ -226,6 +231,8 @@ class _FactBase(nn.Module):
         ``result()`` gives the same list ``forward`` returns.  Lets batch i+1's input copy overlap batch i's kernels."""
         if self.cfg.FACT.trans:
             raise NotImplementedError('FACT.trans models run one video per call through forward() (the transcript sets the token count)')
+        if self.training:
+            raise RuntimeError('the forward is built for eval mode: call net.eval() first (see forward())')
         if next(self.parameters()).device.type != 'cuda':
             raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
         h = self.engine().submit(list(seq_list))

@@ -102,9 +102,14 @@ def test_variant_parameters_match_reference_layout():
         FACT(C.tiny(a_i='gru'), 24, 7)          # the GRU branch needs the transcript (blocks.py:226)
 
 
-def test_unsupported_variants_raise():
+def test_unsupported_modes_raise():
+    net = FACT(C.tiny(), 24, 7)                  # a fresh nn.Module is in training mode, like the reference's
+    with pytest.raises(RuntimeError, match='eval mode'):
+        net.forward([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)])
+    with pytest.raises(RuntimeError, match='eval mode'):
+        net.forward([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)], compute_loss=True)
+    net = FACT(C.tiny(trans=True), 24, 7).eval()
     with pytest.raises(NotImplementedError, match='compute_loss'):
-        net = FACT(C.tiny(), 24, 7)
         net.forward([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)], compute_loss=True)
 
 
