@@ -429,7 +429,11 @@ class FactEngine:
         out = self.zbuf('a2f_out', (B, slot, F), self.act)
         if tc:
             vt = self.zbuf('x2y_vt16', (B, F, Kp), torch.bfloat16)          # vt[b,f,m] = sum_h Wa[f,h] xv[b,m,h]; pad cols stay 0
-            ops.gemm([S(W[None, :, H:], xv)], M, vt)
+            if H % 32 == 0:      # tf32 tensor-core GEMM: rows = the (replicated) weight, per-video "weights" = the token values
+                wa = self.derived(('wa_rep', pfx, B), lambda: W[:, H:].unsqueeze(0).expand(B, -1, -1))
+                ops.gemm([S(wa, xv)], M, vt, tc=True, tag='x2y_vt')
+            else:
+                ops.gemm([S(W[None, :, H:], xv)], M, vt)
             ops.gemm([S(rows, self.wbf(W[:, :H])), S(attn16, vt)], F, out, len=rlen, bias=self.p(pfx + 'Y_W.bias'), tc=True, tag='x2y_rows')
         else:
             vt = self.buf('x2y_vt', (B, F, Mp))
