@@ -376,25 +376,55 @@ class FactEngine:
         Mp = _round_up(M, 4)
         qpos = self.qpos()
         alpha = 1.0 / math.sqrt(H)
-        yq = self.buf('x2y_tokH', (B, M, H))
-        self.lin(action, self.p(pfx + 'Y_Q.weight'), H, yq, pos=qpos, bias=self.p(pfx + 'Y_Q.bias'))
         tc = self.x2y_tc(rows, H)
         qt = self.buf('x2y_qt16' if tc else 'x2y_qt', (B, M, H), torch.bfloat16 if tc else torch.float32)   # alpha * Wk^T yq
-        self.lin(yq, self.tr(pfx + 'X_K.weight'), H, qt, alpha=alpha)
         cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * yq . bk
-        self.lin(yq, self.p(pfx + 'X_K.bias')[None, :], 1, cb, alpha=alpha)
+        fold = self.mode == 'bf16' and self.use_tc
+        if fold:
+            # yq = Y_Q(action + pos) only feeds linear maps: fold Y_Q into them (one GEMM instead of two, no yq buffer)
+            Wf, bf_, u, c0 = self._x2y_fold(pfx, 'Y_Q', 'X_K', alpha)
+            self.lin(action, Wf, H, qt, pos=qpos, bias=bf_)
+            self.lin(action, u, 1, cb, pos=qpos, bias=c0)
+        else:
+            yq = self.buf('x2y_tokH', (B, M, H))
+            self.lin(action, self.p(pfx + 'Y_Q.weight'), H, yq, pos=qpos, bias=self.p(pfx + 'Y_Q.bias'))
+            self.lin(yq, self.tr(pfx + 'X_K.weight'), H, qt, alpha=alpha)
+            self.lin(yq, self.p(pfx + 'X_K.bias')[None, :], 1, cb, alpha=alpha)
         logit = self.buf('f2a_logit_' + tag, (B, slot, Mp))
         ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc, tag='x2y_rows')
         attn = self.buf('f2a_attn_' + tag, (B, slot, Mp)) if want_attn else None
         xbar = self.buf('x2y_xbar', (B, M, H))
         ws = self.buf('col_ws', (ops.col_softmax_ws(B, slot, M, H),))
         ops.col_softmax_apply(logit, rows, xbar, M, ws, attn=attn, len=rlen, E=H)
-        feat = self.buf('x2y_tokH', (B, M, H))
-        self.lin(xbar, self.p(pfx + 'X_V.weight'), H, feat, bias=self.p(pfx + 'X_V.bias'))
         W = self.p(pfx + 'Y_W.weight')
         out = self.buf('tok_x', (B, M, A))
-        self.mm([S(action, W[:, :H]), S(feat, W[:, H:])], A, out, tf32=True, bias=self.p(pfx + 'Y_W.bias'))
+        if fold:     # Y_W(cat[action, X_V(xbar)]) = action W1^T + xbar (W2 Wv)^T + (b + W2 bv)
+            W2v, b2 = self._yw_fold(pfx)
+            self.mm([S(action, W[:, :H]), S(xbar, W2v)], A, out, tf32=True, bias=b2)
+        else:
+            feat = self.buf('x2y_tokH', (B, M, H))
+            self.lin(xbar, self.p(pfx + 'X_V.weight'), H, feat, bias=self.p(pfx + 'X_V.bias'))
+            self.mm([S(action, W[:, :H]), S(feat, W[:, H:])], A, out, tf32=True, bias=self.p(pfx + 'Y_W.bias'))
         return out, logit, attn
+
+    def _x2y_fold(self, pfx, first, second, alpha):
+        """Two chained Linears with nothing in between, q = first(x) then alpha * q W2 (the transposed use of the second
+        weight in the logit, basic.py:367-372) and alpha * q . b2:  W' = alpha W2^T W1, b' = alpha W2^T b1,
+        u = alpha W1^T b2, c0 = alpha b1 . b2.  Products formed once in fp64."""
+        def make():
+            W1, b1 = self.p(f'{pfx}{first}.weight').double(), self.p(f'{pfx}{first}.bias').double()
+            W2, b2 = self.p(f'{pfx}{second}.weight').double(), self.p(f'{pfx}{second}.bias').double()
+            return [(alpha * W2.t() @ W1).float().contiguous(), (alpha * W2.t() @ b1).float().contiguous(),
+                    (alpha * W1.t() @ b2).float()[None, :].contiguous(), (alpha * b1 @ b2).float().reshape(1).contiguous()]
+        return [self.derived(('x2yfold', pfx, first, i), lambda i=i: make()[i]) for i in range(4)]
+
+    def _yw_fold(self, pfx):
+        def make():
+            W, b = self.p(pfx + 'Y_W.weight').double(), self.p(pfx + 'Y_W.bias').double()
+            Wv, bv = self.p(pfx + 'X_V.weight').double(), self.p(pfx + 'X_V.bias').double()
+            H = Wv.shape[0]
+            return [(W[:, H:] @ Wv).float().contiguous(), (b + W[:, H:] @ bv).float().contiguous()]
+        return [self.derived(('ywfold', pfx, i), lambda i=i: make()[i]) for i in range(2)]
 
     def a2f(self, pfx, bc, action, rows, rlen, pos_idx, tag):
         """X2Y_map with X = tokens, Y = rows (frames or segments). -> rows [B,slot,F] act dtype,
@@ -403,30 +433,42 @@ class FactEngine:
         Mp = _round_up(M, 4)
         qpos = self.qpos()
         alpha = 1.0 / math.sqrt(H)
-        xk = self.buf('x2y_tokH', (B, M, H))
-        self.lin(action, self.p(pfx + 'X_K.weight'), H, xk, pos=qpos, bias=self.p(pfx + 'X_K.bias'))
         tc = self.x2y_tc(rows, H)
         kt = self.buf('x2y_qt16' if tc else 'x2y_qt', (B, M, H), torch.bfloat16 if tc else torch.float32)   # alpha * Wq^T xk
-        self.lin(xk, self.tr(pfx + 'Y_Q.weight'), H, kt, alpha=alpha)
         cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * xk . bq
-        self.lin(xk, self.p(pfx + 'Y_Q.bias')[None, :], 1, cb, alpha=alpha)
+        fold = tc and H % 32 == 0
+        if fold:     # xk = X_K(action + pos) only feeds linear maps (see f2a)
+            Wf, bf_, u, c0 = self._x2y_fold(pfx, 'X_K', 'Y_Q', alpha)
+            self.lin(action, Wf, H, kt, pos=qpos, bias=bf_)
+            self.lin(action, u, 1, cb, pos=qpos, bias=c0)
+        else:
+            xk = self.buf('x2y_tokH', (B, M, H))
+            self.lin(action, self.p(pfx + 'X_K.weight'), H, xk, pos=qpos, bias=self.p(pfx + 'X_K.bias'))
+            self.lin(xk, self.tr(pfx + 'Y_Q.weight'), H, kt, alpha=alpha)
+            self.lin(xk, self.p(pfx + 'Y_Q.bias')[None, :], 1, cb, alpha=alpha)
         logit = self.buf('a2f_logit_' + tag, (B, slot, Mp))
         ops.gemm([S(rows, kt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc, tag='x2y_rows')
         attn = self.buf('a2f_attn_' + tag, (B, slot, Mp))
         Kp = _round_up(M, 64)
         attn16 = self.buf('a2f_attn16', (B, slot, Kp), torch.bfloat16) if tc else None
         ops.row_softmax(logit, attn, M, len=rlen, out16=attn16)
-        xv = self.buf('x2y_xv', (B, M, H))
-        self.lin(action, self.p(pfx + 'X_V.weight'), H, xv, bias=self.p(pfx + 'X_V.bias'))
         W = self.p(pfx + 'Y_W.weight')                                      # [F, 2H] = [Wy | Wa]
         out = self.zbuf('a2f_out', (B, slot, F), self.act)
+        if fold:
+            # vt[b,f,m] = sum_h Wa[f,h] X_V(action)[b,m,h] = (Wa Wv) action^T + Wa bv; the attention rows sum to one, so the
+            # constant Wa bv moves into the output bias.  tf32 tensor-core GEMM: rows = the (replicated) folded weight,
+            # per-video "weights" = the tokens themselves.
+            vt = self.zbuf('x2y_vt16', (B, F, Kp), torch.bfloat16)          # pad cols stay 0
+            Wav, b2 = self._yw_fold(pfx)
+            wa = self.derived(('wav_rep', pfx, B), lambda: Wav.unsqueeze(0).expand(B, -1, -1))
+            ops.gemm([S(wa, action)], M, vt, tc=True, tag='x2y_vt')
+            ops.gemm([S(rows, self.wbf(W[:, :H])), S(attn16, vt)], F, out, len=rlen, bias=b2, tc=True, tag='x2y_rows')
+            return out, logit, attn
+        xv = self.buf('x2y_xv', (B, M, H))
+        self.lin(action, self.p(pfx + 'X_V.weight'), H, xv, bias=self.p(pfx + 'X_V.bias'))
         if tc:
             vt = self.zbuf('x2y_vt16', (B, F, Kp), torch.bfloat16)          # vt[b,f,m] = sum_h Wa[f,h] xv[b,m,h]; pad cols stay 0
-            if H % 32 == 0:      # tf32 tensor-core GEMM: rows = the (replicated) weight, per-video "weights" = the token values
-                wa = self.derived(('wa_rep', pfx, B), lambda: W[:, H:].unsqueeze(0).expand(B, -1, -1))
-                ops.gemm([S(wa, xv)], M, vt, tc=True, tag='x2y_vt')
-            else:
-                ops.gemm([S(W[None, :, H:], xv)], M, vt)
+            ops.gemm([S(W[None, :, H:], xv)], M, vt)
             ops.gemm([S(rows, self.wbf(W[:, :H])), S(attn16, vt)], F, out, len=rlen, bias=self.p(pfx + 'Y_W.bias'), tc=True, tag='x2y_rows')
         else:
             vt = self.buf('x2y_vt', (B, F, Mp))
