@@ -44,7 +44,7 @@ _SIGS = {
     'factk_layernorm': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, f32, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
     'factk_l2norm': (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, f32, vp]),
     'factk_row_softmax': (i32, [vp, i32, vp, i32, i32, i32, vp, i32, f32, vp, i32, i32, vp]),
-    'factk_mha_tokens': (i32, [vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    'factk_mha_tokens': (i32, [vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
     'factk_attn_rows_ws_floats': (C.c_size_t, [i32, i32, i32, i32, i32]),
     'factk_attn_rows': (i32, [vp, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]),
     'factk_col_softmax_ws_floats': (C.c_size_t, [i32, i32, i32, i32]),

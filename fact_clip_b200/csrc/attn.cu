@@ -54,6 +54,126 @@ __global__ void __launch_bounds__(128) mha_tokens_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same on the tensor cores (tf32 mma.sync m16n8k8, fp32 accumulate), bf16 compute mode: one CTA per (head, video),
+// one warp per 16-query tile, keys in chunks of 80 with a running max / sum (flash style), K and V of the head staged in
+// shared memory as tf32.  The thread-per-query kernel above is a 75-iteration dependent chain on 75 of 128 threads
+// (43 us per launch at 64 videos x 8 heads); the tensor-core form is a few hundred MMAs per CTA.
+//   QK^T: A = Q tile (row-major, straight from global, pre-scaled), B[k = dh][n = key] = Ks[key][dh]
+//   P V : A = P in the accumulator layout of QK^T with the key index inside each 8-block relabelled (k = t <-> key 2t,
+//         k = t+4 <-> key 2t+1: a sum over keys does not care), B[k][n = dh] = Vs[key(k)][dh]  -> no shuffles
+// Row strides of 36 floats make both B-fragment patterns bank-conflict free.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int MT_WARPS = 5, MT_KCH = 80, MT_LD = 36 + 0;     // key chunk, smem row stride (floats) for DH = 32
+
+template <int DH>
+__global__ void __launch_bounds__(MT_WARPS * 32) mha_tokens_mma_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                                                                       const float* __restrict__ V, int ld, float* __restrict__ O,
+                                                                       int ldo, int M) {
+    constexpr int LDS_ = DH + 4;          // 4 * key + dh and 8 * t + g bank patterns are conflict free for DH % 32 == 0 or 16
+    extern __shared__ uint32_t smu[];
+    const int Mp = (M + 7) & ~7;
+    uint32_t* Ks = smu;                   // [Mp][LDS_] tf32
+    uint32_t* Vs = smu + (size_t)Mp * LDS_;
+    const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const size_t base = (size_t)b * M;
+    for (int i = threadIdx.x; i < Mp * DH; i += blockDim.x) {
+        const int m = i / DH, d = i % DH;
+        const bool ok = m < M;
+        Ks[m * LDS_ + d] = to_tf32(ok ? K[(base + m) * ld + h * DH + d] : 0.f);
+        Vs[m * LDS_ + d] = to_tf32(ok ? V[(base + m) * ld + h * DH + d] : 0.f);
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)DH);
+    for (int m0 = warp * 16; m0 < M; m0 += MT_WARPS * 16) {
+        // Q tile fragments: a0 = Q[g][t], a1 = Q[g+8][t], a2 = Q[g][t+4], a3 = Q[g+8][t+4] per k-step of 8
+        uint32_t qa[DH / 8][4];
+        const int r0 = m0 + g, r1 = m0 + g + 8;
+#pragma unroll
+        for (int kk = 0; kk < DH / 8; ++kk) {
+            const int d = h * DH + kk * 8 + t;
+            qa[kk][0] = to_tf32(r0 < M ? Q[(base + r0) * ld + d] * scale : 0.f);
+            qa[kk][1] = to_tf32(r1 < M ? Q[(base + r1) * ld + d] * scale : 0.f);
+            qa[kk][2] = to_tf32(r0 < M ? Q[(base + r0) * ld + d + 4] * scale : 0.f);
+            qa[kk][3] = to_tf32(r1 < M ? Q[(base + r1) * ld + d + 4] * scale : 0.f);
+        }
+        float acc[DH / 8][4];
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        for (int k0 = 0; k0 < Mp; k0 += MT_KCH) {
+            const int nkt = min(MT_KCH, Mp - k0) / 8;           // 8-key tiles in this chunk
+            float sc[MT_KCH / 8][4];
+#pragma unroll
+            for (int j = 0; j < MT_KCH / 8; ++j) {
+                sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+                if (j < nkt) {
+                    const uint32_t* kr = Ks + (size_t)(k0 + j * 8 + g) * LDS_;
+#pragma unroll
+                    for (int kk = 0; kk < DH / 8; ++kk) mma_tf32(sc[j], qa[kk], kr[kk * 8 + t], kr[kk * 8 + t + 4]);
+                }
+            }
+            // running softmax over the chunk: thread holds rows g (c0,c1) and g+8 (c2,c3), keys 2t, 2t+1 of each 8-tile
+            float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < MT_KCH / 8; ++j) {
+                if (j < nkt) {
+                    const int key = k0 + j * 8 + 2 * t;
+                    if (key >= M) sc[j][0] = sc[j][2] = -INFINITY;
+                    if (key + 1 >= M) sc[j][1] = sc[j][3] = -INFINITY;
+                    cm0 = fmaxf(cm0, fmaxf(sc[j][0], sc[j][1]));
+                    cm1 = fmaxf(cm1, fmaxf(sc[j][2], sc[j][3]));
+                }
+            }
+            cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+            cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+            cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+            cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+            const float n0 = fmaxf(mx0, cm0), n1 = fmaxf(mx1, cm1);
+            const float f0 = __expf(mx0 - n0), f1 = __expf(mx1 - n1);
+            mx0 = n0; mx1 = n1;
+            l0 *= f0; l1 *= f1;
+#pragma unroll
+            for (int n = 0; n < DH / 8; ++n) { acc[n][0] *= f0; acc[n][1] *= f0; acc[n][2] *= f1; acc[n][3] *= f1; }
+#pragma unroll
+            for (int j = 0; j < MT_KCH / 8; ++j) {
+                if (j < nkt) {
+                    const float p0 = __expf(sc[j][0] - n0), p1 = __expf(sc[j][1] - n0);
+                    const float p2 = __expf(sc[j][2] - n1), p3 = __expf(sc[j][3] - n1);
+                    l0 += p0 + p1;
+                    l1 += p2 + p3;
+                    // A fragment of P with the relabelled key order: k = t <-> key 2t, k = t+4 <-> key 2t+1
+                    const uint32_t pa[4] = {to_tf32(p0), to_tf32(p2), to_tf32(p1), to_tf32(p3)};
+                    const uint32_t* v0 = Vs + (size_t)(k0 + j * 8 + 2 * t) * LDS_;
+#pragma unroll
+                    for (int n = 0; n < DH / 8; ++n) mma_tf32(acc[n], pa, v0[n * 8 + g], v0[LDS_ + n * 8 + g]);
+                }
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n) {
+            const int d = h * DH + n * 8 + 2 * t;
+            if (r0 < M) *reinterpret_cast<float2*>(O + (base + r0) * ldo + d) = make_float2(acc[n][0] * i0, acc[n][1] * i0);
+            if (r1 < M) *reinterpret_cast<float2*>(O + (base + r1) * ldo + d) = make_float2(acc[n][2] * i1, acc[n][3] * i1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // SCALayer cross attention core (models/basic.py:507-514): partial over one split of rows.
 // partial layout: [B][nhead][nsplit][M][DH+2] = (running max, running sum, acc[DH]).
 template <int DH>
@@ -599,8 +719,24 @@ static inline int nsplit_of(int slot) { return (slot + SPLIT_ROWS - 1) / SPLIT_R
 using namespace factk;
 
 extern "C" int factk_mha_tokens(const float* Q, const float* K, const float* V, int ld, float* O, int ldo, int B, int M,
-                                int nhead, int dh, void* stream) {
+                                int nhead, int dh, int tf32, void* stream) {
     FACTK_REQUIRE(Q && K && V && O && B > 0 && M > 0 && nhead > 0, "factk_mha_tokens: bad args");
+    if (tf32 && (dh == 16 || dh == 32 || dh == 64) && (ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(O) & 7u) == 0) {
+        const int Mp = (M + 7) & ~7;
+        const size_t smem_t = (size_t)2 * Mp * (dh + 4) * sizeof(float);
+        FACTK_REQUIRE(smem_t <= 200 * 1024, "factk_mha_tokens: M*dh too large for shared memory (%zu B)", smem_t);
+        const dim3 tgrid(nhead, B);
+#define LAUNCH_T(DH)                                                                                                \
+    do {                                                                                                            \
+        cudaFuncSetAttribute(mha_tokens_mma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   \
+        mha_tokens_mma_kernel<DH><<<tgrid, MT_WARPS * 32, smem_t, (cudaStream_t)stream>>>(Q, K, V, ld, O, ldo, M);  \
+    } while (0)
+        if (dh == 16) LAUNCH_T(16);
+        else if (dh == 32) LAUNCH_T(32);
+        else LAUNCH_T(64);
+#undef LAUNCH_T
+        return check_launch("factk_mha_tokens(tf32)");
+    }
     const size_t smem = (size_t)2 * M * dh * sizeof(float);
     FACTK_REQUIRE(smem <= 200 * 1024, "factk_mha_tokens: M*dh too large for shared memory (%zu B)", smem);
     dim3 grid(nhead, B);

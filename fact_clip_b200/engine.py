@@ -256,7 +256,7 @@ class FactEngine:
         self.lin(x, W[2 * A:], A, qkv[:, :, 2 * A:], bias=bias[2 * A:])
         # (one merged q|k|v launch was measured slower: 192 tiles = two waves on 148 SMs, 45 us against 19 + 14 us)
         o = self.buf('tok_o', (B, M, A))
-        ops.mha_tokens(qkv[:, :, :A], qkv[:, :, A:2 * A], qkv[:, :, 2 * A:], o, nhead)
+        ops.mha_tokens(qkv[:, :, :A], qkv[:, :, A:2 * A], qkv[:, :, 2 * A:], o, nhead, tf32=(self.mode == 'bf16' and self.use_tc))
         return o
 
     def _ffn_ln(self, q, x, n_a, n_b, tag):

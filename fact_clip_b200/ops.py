@@ -167,13 +167,13 @@ def row_softmax(logit, out, M, scale=1.0, len=None, out16=None):
            out16.shape[-1] if out16 is not None else 0, L.stream())
 
 
-def mha_tokens(q, k, v, out, nhead):
+def mha_tokens(q, k, v, out, nhead, tf32=False):
     B, M = q.shape[0], q.shape[1]
     E = out.shape[-1]
     assert _row_ld(q) == _row_ld(k) == _row_ld(v)
     COUNTERS['launches'] += 1
     _call('factk_mha_tokens', None, q.data_ptr(), k.data_ptr(), v.data_ptr(), _row_ld(q), out.data_ptr(), _row_ld(out),
-           B, M, nhead, E // nhead, L.stream())
+           B, M, nhead, E // nhead, int(tf32), L.stream())
 
 
 def attn_rows_ws(B, slot, M, nhead, dh):

@@ -147,9 +147,10 @@ int factk_row_softmax(const float* L, int ldl, float* P, int ldp, int B, int slo
                       float scale, void* P16, int ldp16, int pad16, void* stream);
 
 /* Token self-attention core of nn.MultiheadAttention (basic.py:500, 437): Q,K,V fp32 [B][M][ld]
- * already projected; O[b,m,h*dh:(h+1)*dh] = softmax(q k^T / sqrt(dh)) v per head. */
+ * already projected; O[b,m,h*dh:(h+1)*dh] = softmax(q k^T / sqrt(dh)) v per head.  tf32 != 0: tensor-core kernel
+ * (tf32 operands, fp32 accumulate; dh 16/32/64), the bf16 compute mode's choice; 0: fp32 CUDA-core kernel. */
 int factk_mha_tokens(const float* Q, const float* K, const float* V, int ld, float* O, int ldo,
-                     int B, int M, int nhead, int dh, void* stream);
+                     int B, int M, int nhead, int dh, int tf32, void* stream);
 
 /* Tokens-attend-rows core of the SCALayer cross attention (basic.py:507-514): Q fp32 [B][M][ldq]
  * (projected), Kx/Vx rows [B][slot][ldkv] of dtype (projected keys / values, column offsets applied

@@ -146,6 +146,20 @@ def test_mha_tokens(M, nh, dh):
     close(o, ref, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize('M,nh,dh', [(75, 8, 32), (1, 8, 32), (300, 8, 32), (60, 8, 64), (83, 4, 16)])
+def test_mha_tokens_tf32_tensor_core(M, nh, dh):
+    """tf32 mma.sync variant (bf16 compute mode): tf32 operands, fp32 accumulate -> 2e-3 relative to the fp32 reference."""
+    B, E = 3, nh * dh
+    qkv = rnd(B, M, 3 * E, seed=23)
+    d = qkv.to(DEV)
+    o = torch.zeros(B, M, E, device=DEV)
+    ops.mha_tokens(d[..., :E], d[..., E:2 * E], d[..., 2 * E:], o, nh, tf32=True)
+    q, k, v = [t.view(B, M, nh, dh).transpose(1, 2) for t in (qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:])]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), -1) @ v).transpose(1, 2).reshape(B, M, E)
+    err = float((o.cpu() - ref).norm() / ref.norm())
+    assert err < 2e-3, err
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('M,nh,dh,slot,lens', [(75, 8, 32, 1280, [1280, 700, 3]), (12, 4, 8, 128, [37, 128]), (300, 8, 32, 640, [640])])
 def test_attn_rows(dtype, M, nh, dh, slot, lens):
