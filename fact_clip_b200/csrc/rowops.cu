@@ -139,6 +139,41 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* X, int x_dty
     }
 }
 
+// LayerNorm with the row in registers (E = 32 * NV columns): one load per element instead of three dtype-dispatched passes.
+// Same two-pass mean / variance arithmetic as the generic kernel.
+template <typename TX, typename TY, int NV>
+__global__ void __launch_bounds__(256) layernorm_small_kernel(const TX* X, int ldx, const float* R, int ldr,   // Y may alias X or R
+                                                              const float* __restrict__ w, const float* __restrict__ bb, float eps,
+                                                              int relu, TY* Y, int ldy, int B, int slot,
+                                                              const int32_t* __restrict__ len) {
+    int b, t;
+    if (!row_of_warp(B, slot, len, b, t)) return;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)b * slot + t;
+    constexpr int E = 32 * NV;
+    const TX* x = X + row * (size_t)ldx;
+    float v[NV], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = to_f<TX>(x[lane + 32 * i]);
+        if (R) v[i] += R[row * (size_t)ldr + lane + 32 * i];
+        s += v[i];
+    }
+    const float mu = warp_sum(s) / E;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) q += (v[i] - mu) * (v[i] - mu);
+    const float rstd = rsqrtf(warp_sum(q) / E + eps);
+    TY* y = Y + row * (size_t)ldy;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        float o = (v[i] - mu) * rstd * w[c] + bb[c];
+        if (relu) o = fmaxf(o, 0.f);
+        y[c] = from_f<TY>(o);
+    }
+}
+
 __global__ void __launch_bounds__(256) l2norm_kernel(const void* X, int x_dtype, int ldx, void* Y, int y_dtype, int ldy,
                                                      int B, int slot, const int32_t* len, int E, float eps) {
     int b, t;
@@ -251,7 +286,24 @@ extern "C" int factk_layernorm(const void* X, int x_dtype, int ldx, const void* 
                                const float* b, float eps, int relu, void* Y, int y_dtype, int ldy, int B, int slot,
                                const int32_t* len, int E, void* stream) {
     FACTK_REQUIRE(X && Y && w && b && B > 0 && slot > 0 && E > 0, "factk_layernorm: bad args");
-    layernorm_kernel<<<row_grid(B, slot), 256, 0, (cudaStream_t)stream>>>(X, x_dtype, ldx, R, r_dtype, ldr, w, b, eps, relu, Y, y_dtype, ldy, B, slot, len, E);
+    const cudaStream_t st = (cudaStream_t)stream;
+    const bool r_ok = R == nullptr || r_dtype == FACTK_F32;
+#define LN_GO(TX, TY, NV_)                                                                                                       \
+    layernorm_small_kernel<TX, TY, NV_><<<row_grid(B, slot), 256, 0, st>>>(reinterpret_cast<const TX*>(X), ldx,                  \
+                                                                           reinterpret_cast<const float*>(R), ldr, w, b, eps,    \
+                                                                           relu, reinterpret_cast<TY*>(Y), ldy, B, slot, len)
+#define LN_NV(TX, TY)                                                                                                            \
+    do {                                                                                                                         \
+        if (E == 128) { LN_GO(TX, TY, 4); return check_launch("factk_layernorm"); }                                              \
+        if (E == 256) { LN_GO(TX, TY, 8); return check_launch("factk_layernorm"); }                                              \
+        if (E == 512) { LN_GO(TX, TY, 16); return check_launch("factk_layernorm"); }                                             \
+    } while (0)
+    if (r_ok && x_dtype == FACTK_F32 && y_dtype == FACTK_F32) LN_NV(float, float);
+    if (r_ok && x_dtype == FACTK_BF16 && y_dtype == FACTK_BF16) LN_NV(__nv_bfloat16, __nv_bfloat16);
+    if (r_ok && x_dtype == FACTK_F32 && y_dtype == FACTK_BF16) LN_NV(float, __nv_bfloat16);
+#undef LN_NV
+#undef LN_GO
+    layernorm_kernel<<<row_grid(B, slot), 256, 0, st>>>(X, x_dtype, ldx, R, r_dtype, ldr, w, b, eps, relu, Y, y_dtype, ldy, B, slot, len, E);
     return check_launch("factk_layernorm");
 }
 
