@@ -68,7 +68,7 @@ template <int GM_NC>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, const float* __restrict__ bhh_f,
                const float* __restrict__ whh_b, const float* __restrict__ bhh_b, void* out, int o_dtype, int ldo, int relu,
-               int B, int slot, const int32_t* __restrict__ nseg, long long* dbg) {
+               int B, int slot, const int32_t* __restrict__ nseg, const int32_t* __restrict__ order, long long* dbg) {
     extern __shared__ __align__(16) uint8_t gm_smem[];
     uint8_t* hb = gm_smem;                                                       // [chain][parity] hidden state, bf16 [video][unit]
     // K-slice partial sums [chain][step parity][warp][video][gate row]: parity-double-buffered because a warp only waits for
@@ -119,11 +119,14 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
     int maxAll = 0;
 #pragma unroll
     for (int c = 0; c < GM_NC; ++c) {
-        vb[c] = (grp * GM_NC + c) * GM_NV + n;
+        // chain slot -> video: by index, or through `order` (videos sorted by segment count, so that chains of similar
+        // length share a cluster and whole clusters retire early: fewer co-running clusters = shorter steps for the rest)
+        auto video_of = [&](int sidx) { return sidx < B ? (order ? order[sidx] : sidx) : B; };
+        vb[c] = video_of((grp * GM_NC + c) * GM_NV + n);
         myS[c] = vb[c] < B ? min(nseg[vb[c]], slot) : 0;
         maxS[c] = 0;
         for (int i = 0; i < GM_NV; ++i) {
-            const int v = (grp * GM_NC + c) * GM_NV + i;
+            const int v = video_of((grp * GM_NC + c) * GM_NV + i);
             maxS[c] = max(maxS[c], v < B ? min(nseg[v], slot) : 0);
         }
         maxAll = max(maxAll, maxS[c]);
@@ -283,18 +286,48 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
 
 using namespace factk;
 
-extern "C" int factk_gru_bidir_mma_dbg(const float*, const float*, const float*, const float*, const float*, int, void*, int, int, int,
-                                       int, int, const int32_t*, long long*, void*);
+// order[r] = index of the video with the r-th largest segment count (ties by index): one small CTA, O(B^2 / 256).
+__global__ void gru_rank_kernel(const int32_t* __restrict__ nseg, int B, int32_t* __restrict__ order) {
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const int si = nseg[i];
+        int r = 0;
+        for (int j = 0; j < B; ++j) {
+            const int sj = nseg[j];
+            r += (sj > si) || (sj == si && j < i);
+        }
+        order[r] = i;
+    }
+}
+
+static int gru_mma_launch(const float* gi, const float* w_hh_f, const float* b_hh_f, const float* w_hh_b, const float* b_hh_b, int Hh,
+                          void* out, int o_dtype, int ldo, int relu, int B, int slot, const int32_t* nseg, const int32_t* order,
+                          long long* dbg, void* stream);
 
 extern "C" int factk_gru_bidir_mma(const float* gi, const float* w_hh_f, const float* b_hh_f, const float* w_hh_b,
                                    const float* b_hh_b, int Hh, void* out, int o_dtype, int ldo, int relu, int B, int slot,
                                    const int32_t* nseg, void* stream) {
-    return factk_gru_bidir_mma_dbg(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, Hh, out, o_dtype, ldo, relu, B, slot, nseg, nullptr, stream);
+    return gru_mma_launch(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, Hh, out, o_dtype, ldo, relu, B, slot, nseg, nullptr, nullptr, stream);
+}
+
+extern "C" int factk_gru_bidir_mma_sorted(const float* gi, const float* w_hh_f, const float* b_hh_f, const float* w_hh_b,
+                                          const float* b_hh_b, int Hh, void* out, int o_dtype, int ldo, int relu, int B, int slot,
+                                          const int32_t* nseg, int32_t* order_ws, void* stream) {
+    FACTK_REQUIRE(nseg && order_ws && B > 0, "factk_gru_bidir_mma_sorted: bad args");
+    gru_rank_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(nseg, B, order_ws);
+    int rc = check_launch("factk_gru_bidir_mma_sorted(rank)");
+    if (rc) return rc;
+    return gru_mma_launch(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, Hh, out, o_dtype, ldo, relu, B, slot, nseg, order_ws, nullptr, stream);
 }
 
 extern "C" int factk_gru_bidir_mma_dbg(const float* gi, const float* w_hh_f, const float* b_hh_f, const float* w_hh_b,
                                        const float* b_hh_b, int Hh, void* out, int o_dtype, int ldo, int relu, int B, int slot,
                                        const int32_t* nseg, long long* dbg, void* stream) {
+    return gru_mma_launch(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, Hh, out, o_dtype, ldo, relu, B, slot, nseg, nullptr, dbg, stream);
+}
+
+static int gru_mma_launch(const float* gi, const float* w_hh_f, const float* b_hh_f, const float* w_hh_b, const float* b_hh_b, int Hh,
+                          void* out, int o_dtype, int ldo, int relu, int B, int slot, const int32_t* nseg, const int32_t* order,
+                          long long* dbg, void* stream) {
     FACTK_REQUIRE(gi && w_hh_f && b_hh_f && w_hh_b && b_hh_b && out && nseg && B > 0 && slot > 0, "factk_gru_bidir_mma: bad args");
     FACTK_REQUIRE(Hh == GM_HH, "factk_gru_bidir_mma: hidden size per direction must be %d (got %d)", GM_HH, Hh);
     FACTK_REQUIRE((ldo % 2) == 0 && aligned16(gi) && aligned16(b_hh_f) && aligned16(b_hh_b) &&
@@ -328,8 +361,8 @@ extern "C" int factk_gru_bidir_mma_dbg(const float* gi, const float* w_hh_f, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = NC == 1 ? cudaLaunchKernelEx(&cfg, gru_mma_kernel<1>, gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg, dbg)
-                            : cudaLaunchKernelEx(&cfg, gru_mma_kernel<2>, gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg, dbg);
+    cudaError_t e = NC == 1 ? cudaLaunchKernelEx(&cfg, gru_mma_kernel<1>, gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg, order, dbg)
+                            : cudaLaunchKernelEx(&cfg, gru_mma_kernel<2>, gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg, order, dbg);
     if (e != cudaSuccess) { set_error("factk_gru_bidir_mma: launch: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; }
     return check_launch("factk_gru_bidir_mma");
 }

@@ -516,9 +516,10 @@ class FactEngine:
             self.mm([S(cur, self.cat(f'{g}weight_ih_l{l}', f'{g}weight_ih_l{l}_reverse'))], 6 * Hh, gi, len=nseg,
                     bias=self.cat(f'{g}bias_ih_l{l}', f'{g}bias_ih_l{l}_reverse'), tag='gru_in')
             nxt = self.buf(f'seg1_{l % 2}', (B, slot, H), self.act)
+            mma = self.mode == 'bf16' and self.use_tc and Hh == 256
             ops.gru_bidir(gi, self.p(f'{g}weight_hh_l{l}'), self.p(f'{g}bias_hh_l{l}'), self.p(f'{g}weight_hh_l{l}_reverse'),
-                          self.p(f'{g}bias_hh_l{l}_reverse'), nxt, nseg, relu=(l == gru_layers - 1),
-                          mma=(self.mode == 'bf16' and self.use_tc and Hh == 256))
+                          self.p(f'{g}bias_hh_l{l}_reverse'), nxt, nseg, relu=(l == gru_layers - 1), mma=mma,
+                          order_ws=self.buf('gru_order', (B,), I32) if (mma and B > 8) else None)
             cur = nxt
         seg2 = self.buf('seg2_' + tag if self.vn is not None else 'seg2', (B, slot, H), self.act)
         self.mm([S(cur, self.p(pfx + 'seg_combine.weight'))], H, seg2, len=nseg, bias=self.p(pfx + 'seg_combine.bias'), tag='seg_combine')

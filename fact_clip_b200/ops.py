@@ -221,13 +221,19 @@ def segment_mean(x, seg, seg_label, seg_start, seg_len, nseg, E=None, ws=None):
            seg_label.data_ptr(), seg_start.data_ptr(), seg_len.data_ptr(), nseg.data_ptr(), B, slot, E, L.ptr(ws), L.stream())
 
 
-def gru_bidir(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, nseg, relu=True, mma=False):
-    """mma=True: tensor-core kernel batched over videos (bf16 weights / exchanged state; Hh = 256 only)."""
+def gru_bidir(gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, nseg, relu=True, mma=False, order_ws=None):
+    """mma=True: tensor-core kernel batched over videos (bf16 weights / exchanged state; Hh = 256 only); with order_ws
+    (int32 [B] scratch) the videos are grouped by decreasing segment count on the device first."""
     B, slot = gi.shape[0], gi.shape[1]
     Hh = w_hh_f.shape[1]
     COUNTERS['launches'] += 1
-    _call('factk_gru_bidir_mma' if mma else 'factk_gru_bidir', 'factk_gru_bidir', gi.data_ptr(), w_hh_f.data_ptr(), b_hh_f.data_ptr(), w_hh_b.data_ptr(), b_hh_b.data_ptr(),
-           Hh, out.data_ptr(), L.dt(out), _row_ld(out), int(relu), B, slot, nseg.data_ptr(), L.stream())
+    args = (gi.data_ptr(), w_hh_f.data_ptr(), b_hh_f.data_ptr(), w_hh_b.data_ptr(), b_hh_b.data_ptr(),
+            Hh, out.data_ptr(), L.dt(out), _row_ld(out), int(relu), B, slot, nseg.data_ptr())
+    if mma and order_ws is not None:
+        COUNTERS['launches'] += 1
+        _call('factk_gru_bidir_mma_sorted', 'factk_gru_bidir', *args, order_ws.data_ptr(), L.stream())
+    else:
+        _call('factk_gru_bidir_mma' if mma else 'factk_gru_bidir', 'factk_gru_bidir', *args, L.stream())
 
 
 def gather_rows(src, idx, out, E, len=None):

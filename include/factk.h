@@ -203,6 +203,13 @@ int factk_gru_bidir_mma(const float* gi, const float* w_hh_f, const float* b_hh_
                         void* out, int o_dtype, int ldo, int relu,
                         int B, int slot, const int32_t* nseg, void* stream);
 /* Same, recording a clock64 timeline of CTA 0 into dbg[64][16] (development aid; dbg may be NULL). */
+/* The same with the videos assigned to the 8-video chain groups in order of decreasing segment count (ranked on the
+ * device into order_ws, int32 [B]): chains of similar length share a cluster, whole clusters retire early, and the
+ * remaining ones step faster (2.32 -> 2.08 ms at 64 videos with 564..2572 segments).  Results are identical. */
+int factk_gru_bidir_mma_sorted(const float* gi, const float* w_hh_f, const float* b_hh_f,
+                               const float* w_hh_b, const float* b_hh_b, int Hh, void* out, int o_dtype, int ldo,
+                               int relu, int B, int slot, const int32_t* nseg, int32_t* order_ws, void* stream);
+
 int factk_gru_bidir_mma_dbg(const float* gi, const float* w_hh_f, const float* b_hh_f,
                             const float* w_hh_b, const float* b_hh_b, int Hh,
                             void* out, int o_dtype, int ldo, int relu,

@@ -318,6 +318,14 @@ def test_gru_bidir_mma(nsegs):
     out2 = torch.zeros(B, slot, H, device=DEV)
     ops.gru_bidir(*args, out2, ns, relu=False, mma=True)
     assert torch.equal(out, out2)
+    # videos grouped by decreasing segment count (ranked on the device): every video's chain is computed in its own MMA
+    # column, so the grouping must not change a single bit
+    out3 = torch.zeros(B, slot, H, device=DEV)
+    order = torch.full((B,), -1, dtype=torch.int32, device=DEV)
+    ops.gru_bidir(*args, out3, ns, relu=False, mma=True, order_ws=order)
+    assert torch.equal(out, out3)
+    rank = sorted(range(B), key=lambda i: (-nsegs[i], i))
+    assert order.tolist() == rank
 
 
 # ------------------------------------------------------------------------------------------ eval
