@@ -68,3 +68,25 @@ def test_soft_iou_closed_form():
     union = attn.sum(0)[None] - overlap + onehot.sum(0)[:, None]
     iou = torch.nan_to_num(overlap / union, nan=0.0).t()
     assert torch.allclose(iou, torch.from_numpy(ref), atol=1e-6)
+
+
+def test_host_matching_equals_oracle_and_reference_semantics():
+    """fact_clip_b200.loss.assign (the product's host-side Hungarian / one-to-many / sequential step on the device-computed
+    costs) against the oracle's restatement of loss.py:119-194 on random cost matrices, repeated transcript classes included."""
+    import numpy as np
+    from fact_clip_b200 import loss as PL
+    rng = np.random.default_rng(7)
+    for M, S, ncls in ((12, 5, 3), (30, 9, 4), (8, 8, 8), (75, 11, 6), (5, 1, 1)):
+        for _ in range(5):
+            cost = rng.standard_normal((M, S)).astype(np.float32)
+            tr = rng.integers(0, ncls, S)
+            a, s = PL.assign(cost, tr, 'o2m')
+            ra, rs = LO.one_to_many(cost, torch.from_numpy(tr))
+            assert [int(x) for x in a] == [int(x) for x in ra] and [int(x) for x in s] == [int(x) for x in rs]
+            assert sorted(s) == list(range(S))                       # every ground-truth segment is matched exactly once
+            a, s = PL.assign(cost, tr, 'o2o')
+            assert len(set(a)) == len(a) == S and sorted(s) == list(range(S))
+            a, s = PL.assign(cost, tr, 'seq')
+            assert a == list(range(S)) and s == list(range(S))
+    with pytest.raises(ValueError):
+        PL.assign(np.zeros((3, 2), np.float32), np.zeros(2, np.int64), 'nope')
