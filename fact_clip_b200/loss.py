@@ -96,7 +96,7 @@ class LossRunner:
         ops.tdu_segment(label, gseg, gstart, glen, gcen, gn, len=ln)
         nseg = gn.cpu().numpy()                                    # host sync 1: B ints
         smax = int(nseg.max())
-        cweight = e.derived(('loss_cw', id(self.crit)), lambda: self.crit.class_weights().to(dev))
+        cweight = self.crit.class_weights().to(dev)          # C+1 floats; the criterion's cfg may change between calls
         transcript, sweight = buf('loss_tr', (B, smax), I32), buf('loss_sw', (B, smax))
         # ---- InfoNCE bookkeeping (blocks.py:697-748): seen-class list, label remapping, per-class frame counts
         clip = 'projected_frame_embeddings' in out

@@ -4,6 +4,8 @@ Every function takes CUDA torch tensors (torch is only the allocator / stream pr
 hand-written kernels on the current stream and returns nothing (outputs are written in place).
 Layout: "rows" tensors are [B, slot, ld] with ``len`` (int32 [B], device) valid rows per video.
 """
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -343,7 +345,6 @@ def token_loss(aclogit, aind, sind, nmatch, transcript, cweight, out):
 
 
 def loss_combine(ws, block_types, len, npred, C, M, sw, out, use_clip=False, fact_w=1.0, con_w=0.0, nseen=0, nvalid=None):
-    import ctypes
     nb, B, nchunk = len_(block_types), ws.shape[1], ws.shape[2]
     bt = (ctypes.c_int32 * nb)(*block_types)
     COUNTERS['launches'] += 1
