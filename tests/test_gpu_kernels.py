@@ -377,3 +377,27 @@ def test_fuse_eval_transcript_and_embed_tokens():
         out = torch.empty(1, N, A, device=DEV)
         ops.embed_tokens(emb.to(DEV), tr.int().to(DEV), pe.to(DEV), out)
         assert torch.equal(out[0].cpu(), emb[tr] + pe[:N])
+
+
+@pytest.mark.parametrize('C,M,f_logp', [(300, 40, False), (300, 40, True), (97, 12, True), (1200, 75, True)])
+def test_fuse_eval_wide_class_rows(C, M, f_logp):
+    """Prob fusion with more classes than the register-resident kernel holds (the Epic action table has thousands): generic
+    kernel, with softmaxed frame logits and with un-normalised frame log-probabilities (blocks_SepVerbNoun.py:307-329)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import vn_oracle as VO
+    g = torch.Generator().manual_seed(41)
+    T = 150
+    ac = torch.randn(M, C + 1, generator=g) * 3
+    ac[::3, -1] += 6.0                                            # some tokens predict the null class
+    attn = torch.softmax(torch.randn(T, M, generator=g) * 2, -1)
+    fl = torch.randn(T, C, generator=g) * 2
+    pred = torch.full((1, T), -1, dtype=torch.int64, device=DEV)
+    if f_logp:
+        alp, flp = torch.log_softmax(ac, -1), torch.log_softmax(fl, -1) - 0.3       # frame rows do NOT sum to one
+        ops.fuse_eval(alp[None].to(DEV), attn[None].contiguous().to(DEV), flp[None].to(DEV), 0.1, pred, M, C, f_logp=True)
+        ref = VO.evaluate(alp, attn, flp, 0.1)
+    else:
+        ops.fuse_eval(ac[None].to(DEV), attn[None].contiguous().to(DEV), fl[None].to(DEV), 0.1, pred, M, C)
+        ref = O.fuse_eval(ac, attn, torch.softmax(fl, -1), 0.1)
+    agree = float((pred[0].cpu() == ref).float().mean())
+    assert agree >= 0.99, agree                                   # __expf vs exp can flip a near-tie among hundreds of classes
