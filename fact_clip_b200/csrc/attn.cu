@@ -284,8 +284,8 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
     constexpr int KS = DH / 16;         // k-steps of the QK^T product
     constexpr int NT = DH / 8;          // n-tiles of the output
     constexpr int CH = DH / 8;          // 16-byte chunks per row
-    __shared__ __align__(16) __nv_bfloat16 Ks[TR * LDT];
-    __shared__ __align__(16) __nv_bfloat16 Vs[TR * LDT];
+    __shared__ __align__(16) __nv_bfloat16 Ksm[2][TR * LDT];      // double-buffered by cp.async: the copy of tile i+1 runs
+    __shared__ __align__(16) __nv_bfloat16 Vsm[2][TR * LDT];      // under the MMAs of tile i without holding registers
     const int sp = blockIdx.x % nsplit, qb = blockIdx.x / nsplit, h = blockIdx.y, b = blockIdx.z;
     const int len_b = len ? min(len[b], slot) : slot;
     const int r0 = sp * SPLIT_ROWS;
@@ -318,44 +318,39 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
     for (int i = 0; i < NT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
     float mx_lo = -INFINITY, mx_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 
-    // cooperative tile load: chunk id -> (row, 16B chunk); register-prefetched one tile ahead
+    // cooperative tile load: chunk id -> (row, 16B chunk), 16-byte cp.async (rows beyond the split are zero-filled)
     constexpr int NCHUNK = TR * CH;
     const int nthr = blockDim.x;
     constexpr int MAXPF = 4;            // blockDim.x >= 128 and NCHUNK <= 512, so 4 chunks per thread cover a tile
-    uint4 pk[MAXPF], pv[MAXPF];
-    auto g_load = [&](int t0) {
-#pragma unroll
-        for (int i = 0; i < MAXPF; ++i) {
-            const int c = threadIdx.x + i * nthr;
-            pk[i] = make_uint4(0u, 0u, 0u, 0u);
-            pv[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (c < NCHUNK) {
-                const int r = c / CH, ch = c % CH;
-                if (t0 + r < r1) {
-                    const size_t off = ((size_t)b * slot + t0 + r) * ldkv + h * DH + ch * 8;
-                    pk[i] = *reinterpret_cast<const uint4*>(Kx + off);
-                    pv[i] = *reinterpret_cast<const uint4*>(Vx + off);
-                }
-            }
-        }
-    };
-    auto s_store = [&]() {
+    auto issue_tile = [&](int t0, int buf) {
 #pragma unroll
         for (int i = 0; i < MAXPF; ++i) {
             const int c = threadIdx.x + i * nthr;
             if (c < NCHUNK) {
                 const int r = c / CH, ch = c % CH;
-                *reinterpret_cast<uint4*>(&Ks[r * LDT + ch * 8]) = pk[i];
-                *reinterpret_cast<uint4*>(&Vs[r * LDT + ch * 8]) = pv[i];
+                const bool ok = t0 + r < r1;
+                const size_t off = ((size_t)b * slot + (ok ? t0 + r : r0)) * ldkv + h * DH + ch * 8;
+                const uint32_t dk = (uint32_t)__cvta_generic_to_shared(&Ksm[buf][r * LDT + ch * 8]);
+                const uint32_t dv = (uint32_t)__cvta_generic_to_shared(&Vsm[buf][r * LDT + ch * 8]);
+                const int nbytes = ok ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk), "l"(Kx + off), "r"(nbytes) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dv), "l"(Vx + off), "r"(nbytes) : "memory");
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    g_load(r0);
-    for (int t0 = r0; t0 < r1; t0 += TR) {
-        __syncthreads();                 // previous tile fully consumed
-        s_store();
+    issue_tile(r0, 0);
+    int buf = 0;
+    for (int t0 = r0; t0 < r1; t0 += TR, buf ^= 1) {
+        if (t0 + TR < r1) {
+            issue_tile(t0 + TR, buf ^ 1);        // its previous contents were consumed before the barrier that ended tile i-1
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         __syncthreads();
-        if (t0 + TR < r1) g_load(t0 + TR);
+        const __nv_bfloat16* Ks = Ksm[buf];
+        const __nv_bfloat16* Vs = Vsm[buf];
         // S = Q K^T  (16 queries x 64 frames)
         float sacc[8][4];
 #pragma unroll
@@ -413,6 +408,7 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
                 mma_bf16_16816(o[nt], pa, b0, b1);
             }
         }
+        __syncthreads();                 // tile fully consumed: the next iteration refills the other buffer's partner
     }
     // partial results: (running max, running sum, acc[DH]) per query
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
