@@ -84,7 +84,7 @@ class LossRunner:
         hp, Lc = e.hp, cfg.Loss
         B, slot, ln, dev = e.B, e.slot, e.len, e.dev
         C, M, nb = hp['n_classes'], e.ntok, len(hp['blocks'])
-        assert nb <= 8 and not hp['trans'], 'loss value: at most 8 blocks, query-token models'
+        assert nb <= 8, 'loss value: at most 8 blocks'
         I32, buf = torch.int32, e.buf
         # ---- labels -> ground-truth segments (the TDU run-length kernel serves MatchCriterion.set_label, loss.py:56-60)
         label = buf('loss_label', (B, slot), I32)

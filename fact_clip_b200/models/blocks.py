@@ -171,9 +171,6 @@ class _FactBase(nn.Module):
                                "reference's dropout, channel masking and time masking (blocks.py:58-70), which are part of the "
                                'training step that is not built (SURVEY.md 8f rank 1); silently returning eval-mode results '
                                'would be wrong')
-        if compute_loss and self.cfg.FACT.trans:
-            raise NotImplementedError('compute_loss=True is built for the query-token models (the loss VALUE on device, no '
-                                      'backward); the transcript-conditioned variant is not')
         if compute_loss and self.mcriterion is None:
             raise RuntimeError('compute_loss=True needs net.mcriterion = MatchCriterion(cfg, nclasses, bg_ids) (scripts/train.py:207)')
         dev = next(self.parameters()).device
@@ -181,7 +178,7 @@ class _FactBase(nn.Module):
             raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
         seqs = list(seq_list)        # CUDA tensors, or (pinned) host tensors copied straight into the packed batch
         if self.cfg.FACT.trans:
-            return self._forward_with_transcripts(seqs, label_list, forced_preds)
+            return self._forward_with_transcripts(seqs, label_list, forced_preds, compute_loss)
         out = self.engine().run(seqs, forced_preds=forced_preds, keep=getattr(self, 'keep_attn', False))
         self._last = out
         if compute_loss:
@@ -206,23 +203,35 @@ class _FactBase(nn.Module):
             self.fact_loss, self.contrastive_loss = res['values'][-1, 1], res['values'][-1, 2]
         return res['values'][:, 0].mean(), saves
 
-    def _forward_with_transcripts(self, seqs, label_list, forced_preds=None):
+    def _forward_with_transcripts(self, seqs, label_list, forced_preds=None, compute_loss=False):
         """FACT.trans (blocks.py:74-79, 113-118): every video brings its own token count (the length of its transcript), so
         the videos run one per call like the reference; the transcript is the run-length coding of the label sequence
         (basic.py:38-54, vectorised: one unique_consecutive instead of a Python loop over the frames)."""
         assert label_list is not None and len(label_list) == len(seqs), 'FACT.trans needs the frame labels of every video'
         saves, keep, dev = [], getattr(self, 'keep_attn', False), next(self.parameters()).device
         self._per_video = []
+        total, matches = None, []
         for i, (seq, label) in enumerate(zip(seqs, label_list)):
             transcript = torch.unique_consecutive(torch.as_tensor(label).long()).to(dev)
             forced = None if forced_preds is None else [[u[i]] for u in forced_preds]
             out = self.engine().run([seq], forced_preds=forced, keep=keep, transcript=transcript)
             pred = out['pred'].cpu().numpy()
             saves.append({'pred': pred[0, :out['lengths'][0]].copy()})
+            if compute_loss:      # the loss of this video (one token per transcript entry), blocks.py:120-126
+                res = LossRunner(self.engine(), self.mcriterion).run(out, [label])
+                vals = res['values'].cpu().numpy()
+                nb = len(self.block_list)
+                saves[-1]['loss'] = {'loss': float(vals[0, 0])}
+                saves[-1]['block_losses'] = vals[0, 4:4 + nb].tolist()
+                matches.append(res['matches'][0])
+                total = res['values'][0, 0].clone() if total is None else total + res['values'][0, 0]
             if keep:        # the engine's buffers are reused by the next video: keep copies for stash_video(i)
                 self._per_video.append(_clone_tree(out))
         self._last = out
         self.stash_video(len(seqs) - 1)
+        if compute_loss:
+            self.last_match = matches
+            return total / len(seqs), saves
         return saves
 
     def submit(self, seq_list, label_list=None):

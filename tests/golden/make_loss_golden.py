@@ -36,6 +36,9 @@ CASES = [
     ('o2o', 'tiny_m2_iuUU', dict(pc=0.2, a2fc=1.0, match='o2o', bgw=0.3, nullw=0.05, sw=5.0), [1], []),
     ('o2m', 'tiny_m2_iUU_fpos_clip', dict(pc=0.2, a2fc=1.0, match='o2m', bgw=1.0, nullw=0.05, sw=5.0), [0], []),
     ('seq', 'tiny_m_iu', dict(pc=0.0, a2fc=1.0, match='seq', bgw=1.0, nullw=0.2, sw=1.0), [], []),
+    # transcript-conditioned model: one token per transcript entry, sequential matching (gtea_transcript.yaml style)
+    ('trans_seq', 'tiny_m_iuU_trans', dict(pc=1.0, a2fc=1.0, match='seq', bgw=0.5, nullw=0.1, sw=2.0), [0], []),
+    ('trans_o2o', 'tiny_m_iuU_trans', dict(pc=0.5, a2fc=1.0, match='o2o', bgw=1.0, nullw=0.1, sw=0.0), [], []),
 ]
 
 

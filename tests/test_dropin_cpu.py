@@ -108,8 +108,8 @@ def test_unsupported_modes_raise():
         net.forward([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)])
     with pytest.raises(RuntimeError, match='eval mode'):
         net.forward([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)], compute_loss=True)
-    net = FACT(C.tiny(trans=True), 24, 7).eval()
-    with pytest.raises(NotImplementedError, match='compute_loss'):
+    net = FACT(C.tiny(), 24, 7).eval()
+    with pytest.raises(RuntimeError, match='mcriterion'):
         net.forward([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)], compute_loss=True)
 
 

@@ -77,3 +77,16 @@ def test_vn_golden_bf16_teacher_forced(name):
     check(net, g['videos'], 2e-2)
     agree = sum(int((s['pred'] == v['pred'].numpy()).sum()) for s, v in zip(saves, g['videos']))
     assert agree / sum(len(v['pred']) for v in g['videos']) >= 0.999
+
+
+def test_vn_pipelined_submit_matches_forward():
+    """The graph-captured, double-buffered path (net.submit) serves the verb/noun model too."""
+    g = torch.load(os.path.join(GOLDEN, 'vn_m2_IUU.pt'), weights_only=False)
+    net = build(g, 'fp32')
+    xs = [v['x'].pin_memory() for v in g['videos']]
+    ys = [v['label'] for v in g['videos']]
+    ref = net([x.to(DEV) for x in xs], ys)
+    for h in [net.submit(xs, ys) for _ in range(3)]:
+        got = h.result()
+        for a, b in zip(got, ref):
+            assert np.array_equal(a['pred'], b['pred'])

@@ -41,7 +41,8 @@ def test_loss_oracle_matches_reference_values(name):
     totals = []
     for v, ref in zip(g['videos'], lg['videos']):
         with torch.no_grad():
-            out = O.forward_video(g['state_dict'], hp, v['x'], clip=g['clip'])
+            out = O.forward_video(g['state_dict'], hp, v['x'], clip=g['clip'],
+                                  transcript=O.transcript_of(v['label']) if hp['trans'] else None)
             res = LO.loss_video(out, hp, v['label'], lp, text_embeddings=text)
         assert [m.tolist() for m in res['match']] == ref['match']
         for a, b in zip(res['block_losses'], ref['block_losses']):
