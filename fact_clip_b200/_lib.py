@@ -67,6 +67,7 @@ _SIGS = {
     'factk_token_loss': (i32, [vp, i32, i32, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, vp]),
     'factk_loss_combine': (i32, [vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, i32, f32, f32, i32, vp, vp, i32, vp]),
     'factk_fuse_eval': (i32, [vp, vp, i32, i32, vp, vp, i32, f32, vp, i32, i32, vp, i32, i32, i32, vp]),
+    'factk_transpose_rows': (i32, [vp, C.c_longlong, vp, i32, i32, i32, i32, i32, vp, vp]),
     'factk_vn_splice': (i32, [vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
     'factk_vn_combine': (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp, vp]),
 }

@@ -256,6 +256,33 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* in, int l
     for (int c = lane; c < E; c += 32) out[row * ldo + c] = in[src * ldi + c];
 }
 
+// Input staging: features stored channel-major on disk ((D, T) arrays that the reference transposes on the host,
+// utils/dataset.py:12-21) are copied to the device as they are and transposed here into the packed [B][slot][D] rows
+// (optionally cast to bf16).  src video b starts at src + b * src_bstride and is a dense [D][len[b]] fp32 array.
+// 32 x 32 tiles through shared memory (padded: conflict-free), coalesced on both sides.
+template <typename TY>
+__global__ void __launch_bounds__(256) transpose_rows_kernel(const float* __restrict__ src, long long src_bstride, TY* __restrict__ dst,
+                                                             int ldd, int D, int slot, const int32_t* __restrict__ len) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, T = min(len[b], slot);
+    const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    if (t0 >= T) return;
+    const float* s = src + (size_t)b * (size_t)src_bstride;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int d = d0 + ty + i, t = t0 + tx;
+        tile[ty + i][tx] = (d < D && t < T) ? s[(size_t)d * T + t] : 0.f;
+    }
+    __syncthreads();
+    TY* o = dst + (size_t)b * slot * ldd;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int t = t0 + ty + i, d = d0 + tx;
+        if (t < T && d < D) o[(size_t)t * ldd + d] = from_f<TY>(tile[tx][ty + i]);
+    }
+}
+
 static inline unsigned row_grid(int B, int slot) { return (unsigned)(((long)B * slot + ROWS_PER_CTA - 1) / ROWS_PER_CTA); }
 
 }  // namespace factk
@@ -327,6 +354,17 @@ extern "C" int factk_row_softmax(const float* L, int ldl, float* P, int ldp, int
     else if (nv == 4) row_softmax_small_kernel<4><<<row_grid(B, slot), 256, 0, st>>>(L, ldl, P, ldp, B, slot, len, M, scale, p16, ldp16, pad16);
     else row_softmax_kernel<<<row_grid(B, slot), 256, 0, st>>>(L, ldl, P, ldp, B, slot, len, M, scale, p16, ldp16, pad16);
     return check_launch("factk_row_softmax");
+}
+
+extern "C" int factk_transpose_rows(const float* src, long long src_bstride, void* dst, int dst_dtype, int ldd, int B, int slot,
+                                    int D, const int32_t* len, void* stream) {
+    FACTK_REQUIRE(src && dst && len && B > 0 && slot > 0 && D > 0 && ldd >= D, "factk_transpose_rows: bad args");
+    const dim3 grid((slot + 31) / 32, (D + 31) / 32, B);
+    if (dst_dtype == FACTK_BF16)
+        transpose_rows_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_bstride, reinterpret_cast<__nv_bfloat16*>(dst), ldd, D, slot, len);
+    else
+        transpose_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_bstride, reinterpret_cast<float*>(dst), ldd, D, slot, len);
+    return check_launch("factk_transpose_rows");
 }
 
 extern "C" int factk_gather_rows(const float* in, int ldi, int in_slot, const int32_t* idx, float* out, int ldo, int B,

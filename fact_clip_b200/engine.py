@@ -597,22 +597,30 @@ class FactEngine:
         return self.run_packed(x, ln, lengths, forced_preds, keep)
 
     @torch.no_grad()
-    def submit(self, seqs):
+    def submit(self, seqs, channel_major=False):
         """Pipelined forward: the host->device copy of this batch runs on a side stream into one of two input
         buffers and overlaps the kernels of the previously submitted batch; the predictions are copied to pinned
-        host memory asynchronously.  Returns a handle; ``handle.result()`` blocks until this batch is done."""
+        host memory asynchronously.  Returns a handle; ``handle.result()`` blocks until this batch is done.
+        channel_major: ``seqs[i]`` is the (D, T_i) fp32 array as stored on disk (what the reference transposes on the host,
+        utils/dataset.py:12-21); it is copied as it is and transposed on the device, on the copy stream."""
         self._refresh_weights()
         if self.hp['trans']:
             raise NotImplementedError('FACT.trans models run one video per call through forward() (the transcript sets the token count)')
         self.ntok, self.action_init, self.transcript = self.hp['ntoken'], None, None
-        lengths = [int(s.shape[0]) for s in seqs]
+        lengths = [int(s.shape[1 if channel_major else 0]) for s in seqs]
         B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
         k = self._submits % 2
         self._submits += 1
         main = torch.cuda.current_stream()
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.dev)
-        x = self.buf(f'input_p{k}', (B, slot, D), self._feature_dtype(seqs))
+        if channel_major:
+            assert all(s.dtype == torch.float32 and s.shape[0] == D and s.is_contiguous() for s in seqs), \
+                'channel-major staging takes contiguous (D, T) float32 arrays'
+            x = self.buf(f'input_p{k}', (B, slot, D), self.act)        # bf16 rows in bf16 mode: the cast rides on the transpose
+            raw = self.buf(f'input_cm_p{k}', (B, D * slot))
+        else:
+            x = self.buf(f'input_p{k}', (B, slot, D), self._feature_dtype(seqs))
         ln = self.buf(f'len_p{k}', (B,), torch.int32)
         pred = self.buf(f'pred64_p{k}', (B, slot), torch.int64)
         key = (f'pred_host_p{k}', B, slot)
@@ -623,9 +631,14 @@ class FactEngine:
         with torch.cuda.stream(self._copy_stream):
             if free is not None:
                 self._copy_stream.wait_event(free)          # the previous user of this input buffer has finished
-            for b, s in enumerate(seqs):
-                x[b, :lengths[b]].copy_(s, non_blocking=True)
             ln.copy_(torch.tensor(lengths, dtype=torch.int32).pin_memory(), non_blocking=True)
+            if channel_major:
+                for b, s in enumerate(seqs):
+                    raw[b, :D * lengths[b]].copy_(s.reshape(-1), non_blocking=True)
+                ops.transpose_rows(raw, raw.stride(0), x, ln, D)
+            else:
+                for b, s in enumerate(seqs):
+                    x[b, :lengths[b]].copy_(s, non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(self._copy_stream)
         main.wait_event(copied)

@@ -234,7 +234,7 @@ class _FactBase(nn.Module):
             return total / len(seqs), saves
         return saves
 
-    def submit(self, seq_list, label_list=None):
+    def submit(self, seq_list, label_list=None, channel_major=False):
         """Asynchronous variant of ``forward`` for inference loops: enqueue the host->device copy (side stream,
         double-buffered), the kernels and the device->host copy of the predictions, and return a handle whose
         ``result()`` gives the same list ``forward`` returns.  Lets batch i+1's input copy overlap batch i's kernels."""
@@ -244,7 +244,7 @@ class _FactBase(nn.Module):
             raise RuntimeError('the forward is built for eval mode: call net.eval() first (see forward())')
         if next(self.parameters()).device.type != 'cuda':
             raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
-        h = self.engine().submit(list(seq_list))
+        h = self.engine().submit(list(seq_list), channel_major=channel_major)
         self._last = h.out
         return h
 

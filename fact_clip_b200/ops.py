@@ -351,3 +351,11 @@ def loss_combine(ws, block_types, len, npred, C, M, sw, out, use_clip=False, fac
     _call('factk_loss_combine', None, ws.data_ptr(), nb, ctypes.cast(bt, ctypes.c_void_p), B, nchunk, len.data_ptr(), L.ptr(npred),
           C, M, float(sw), int(use_clip), float(fact_w), float(con_w), int(nseen), L.ptr(nvalid), out.data_ptr(), out.stride(0),
           L.stream())
+
+
+def transpose_rows(src, src_bstride, dst, len, D):
+    """dst[b, t, :D] = src_b[:, t] for channel-major host features copied to the device as they are (staging.py)."""
+    B, slot = dst.shape[0], dst.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_transpose_rows', None, src.data_ptr(), int(src_bstride), dst.data_ptr(), L.dt(dst), _row_ld(dst), B, slot, D,
+          len.data_ptr(), L.stream())

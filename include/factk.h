@@ -240,6 +240,11 @@ int factk_fuse_eval_transcript(const float* attn, int lda, int attn_slot, const 
 int factk_embed_tokens(const float* embed, int lde, const int32_t* transcript, const float* pe, int ldpe,
                        float* out, int ldo, int N, int A, void* stream);
 
+/* Input staging: dst[b][t][d] = src_b[d][t] for t < len[b], src_b = src + b * src_bstride a dense [D][len[b]] fp32 array
+ * (features stored channel-major, which the reference transposes on the host: utils/dataset.py:12-21); dst fp32 or bf16. */
+int factk_transpose_rows(const float* src, long long src_bstride, void* dst, int dst_dtype, int ldd, int B, int slot, int D,
+                         const int32_t* len, void* stream);
+
 /* Epic verb/noun heads (blocks_SepVerbNoun.py).  factk_vn_splice: process_feature (:229-234) in place on the last n1+n2
  * channels of X (two softmaxes), raw logits to clogit_out [B][slot][n1+n2]; with pred_out, also the segmentation argmax
  * over the nact action classes a = (vids[a], nids[a]) of verb-prob x noun-prob (:281-290). */

@@ -307,3 +307,26 @@ def test_sweep_shard_forward_gather_metrics():
     assert out['videos'] == 5 and out['frames'] > 0 and out['frames_per_s'] > 0
     for k in ('Edit', 'AccB', 'Acc', 'F1@0.10', 'F1@0.25', 'F1@0.50'):
         assert k in out['metrics'] and 0.0 <= out['metrics'][k] <= 100.0
+
+
+def test_staged_sweep_from_npy_files(tmp_path):
+    """Dataset -> device staging (fact_clip_b200/staging.py): .npy files in (D, T) float64 layout, pinned arena ring, pipelined
+    submit -- same predictions as the plain forward on the same features."""
+    from fact_clip_b200.staging import FeatureStager, run_sweep, load_feature
+    g = load_golden('tiny_m_iuU_clip')
+    net = build(g, 'fp32')
+    rng = np.random.default_rng(3)
+    lens = dict(v0=70, v1=33, v2=128, v3=9, v4=51)
+    for n, T in lens.items():
+        np.save(tmp_path / f'{n}.npy', rng.standard_normal((g['in_dim'], T)))
+    for dev_t in (False, True):          # host transpose into the arena / file layout in the arena + transpose on the device
+        st = FeatureStager(str(tmp_path), list(lens), transpose=True, batch_videos=2, pin=True, depth=3, device_transpose=dev_t)
+        got = {}
+        for names, saves in run_sweep(net, st):
+            got.update({n: s['pred'] for n, s in zip(names, saves)})
+        assert list(got) == list(lens)
+        for n in lens:
+            x = torch.from_numpy(load_feature(str(tmp_path), n, True)).to(DEV)
+            ref = net([x], [torch.zeros(lens[n], dtype=torch.long)])
+            assert np.array_equal(got[n], ref[0]['pred']), (dev_t, n)
+        st.close()
