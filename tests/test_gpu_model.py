@@ -264,8 +264,9 @@ def test_bf16_host_features():
         net([x.to(DEV) for x in x16], None)
 
 
-def test_full_size_batch_invariance_and_determinism():
-    """BASELINE config 3/4 at full size (T = 4096, D = 2048, bf16 tensor-core path), size-independent properties: a video's
+@pytest.mark.parametrize('lens', [[4096, 3000, 4096, 129], [1, 127, 128, 129, 255, 257, 384, 2, 640]])
+def test_full_size_batch_invariance_and_determinism(lens):
+    """BASELINE config 3/4 at full size (and at lengths around the 128-frame tile boundaries) (T = 4096, D = 2048, bf16 tensor-core path), size-independent properties: a video's
     result does not depend on what it is batched with (ragged lengths, zero tails, tile scheduling, GRU grouping), and
     re-runs are bit-identical (no atomics anywhere)."""
     cfg = C.PRESETS['havid_view0_lh_pt_holdout']()
@@ -273,7 +274,6 @@ def test_full_size_batch_invariance_and_determinism():
     net = FACT_CLIP(cfg, 2048, 75, make_text_embeddings(75)).eval()
     net.compute_mode = 'bf16'
     net = net.to(DEV)
-    lens = [4096, 3000, 4096, 129]
     xs, ys = make_batch(lens, 2048, 75, base_seed=90, nseg=8)
     xd = [x.to(DEV) for x in xs]
 
@@ -286,12 +286,13 @@ def test_full_size_batch_invariance_and_determinism():
             nsegs.append([int(st['nseg'][j]) for st in net._last['blocks'] if 'nseg' in st])
         return out, logits, nsegs
 
-    full, lf, nf = run([0, 1, 2, 3])
-    again, la, na = run([0, 1, 2, 3])
+    everyone = list(range(len(lens)))
+    full, lf, nf = run(everyone)
+    again, la, na = run(everyone)
     for a, b, x, y in zip(full, again, lf, la):
         assert np.array_equal(a['pred'], b['pred']) and torch.equal(x, y)
     assert nf == na
-    for i in range(4):
+    for i in everyone:
         alone, l1, n1 = run([i])
         assert n1[0] == nf[i], (i, n1, nf[i])
         assert np.array_equal(alone[0]['pred'], full[i]['pred']), i
