@@ -87,3 +87,31 @@ def test_loss_havid_shape_vs_oracle():
         assert close(saves[b]['loss']['contrastive_loss'], float(ref['contrastive_loss']), 5e-4)
         ref_tot.append(float(ref['loss']))
     assert len(ref_tot) >= 2
+
+
+def test_loss_epic_shape_vs_oracle():
+    """BASELINE config 5 shape (epic hyper-parameters on blocks.FACT_CLIP: MSTCN2, 300 tokens, fpos, one-to-many matching,
+    nullw 0.05), shortened T, fp32 mode: loss value, InfoNCE term and match against the oracle."""
+    cfg = C.PRESETS['epic_shape']()
+    ncls, lens = 98, [900, 1100]
+    torch.manual_seed(0)
+    net = FACT_CLIP(cfg, 2048, ncls, make_text_embeddings(ncls)).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    hp = O.hparams_from_cfg(cfg, 2048, ncls)
+    lp = LO.loss_params(cfg, bg_ids=[])
+    xs, ys = make_batch(lens, 2048, ncls, base_seed=71, nseg=52)
+    net.compute_mode = 'fp32'
+    net = net.to(DEV)
+    net.mcriterion = MatchCriterion(cfg, ncls, [])
+    loss, saves = net([x.to(DEV) for x in xs], [y.to(DEV) for y in ys], compute_loss=True)
+    checked = 0
+    for b, (x, y) in enumerate(zip(xs, ys)):
+        with torch.no_grad():
+            out = O.forward_video(sd, hp, x, clip=True, fast_gru=True)
+            ref = LO.loss_video(out, hp, y, lp, text_embeddings=sd['text_embeddings'])
+        if not np.array_equal(out['pred'].numpy(), saves[b]['pred']):
+            continue            # a flipped argmax changes the segmentation, and with it every U-block term
+        assert [list(m) for m in net.last_match[b]] == [m.tolist() for m in ref['match']]
+        assert close(saves[b]['loss']['loss'], float(ref['loss']), 5e-4), (saves[b]['loss'], float(ref['loss']))
+        checked += 1
+    assert checked >= 1
