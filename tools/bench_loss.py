@@ -29,15 +29,16 @@ def wall(fn, n):
 
 
 def main():
-    videos, T, ncls = int(os.environ.get('VIDEOS', 64)), 4096, 75
-    cfg = C.PRESETS['havid_view0_lh_pt_holdout']()
+    epic = os.environ.get('PRESET', 'havid') == 'epic'      # BASELINE config 5 shape: T = 16384, 300 tokens, o2m matching
+    videos, T, ncls = int(os.environ.get('VIDEOS', 2 if epic else 64)), (16384 if epic else 4096), (98 if epic else 75)
+    cfg = C.PRESETS['epic_shape' if epic else 'havid_view0_lh_pt_holdout']()
     cfg.merge(dict(Loss=dict(nullw=0.05, bgw=0.5)))
     torch.manual_seed(0)
     net = FACT_CLIP(cfg, 2048, ncls, make_text_embeddings(ncls)).eval()
     net.compute_mode = 'bf16'
     net = net.cuda()
     net.mcriterion = MatchCriterion(cfg, ncls, [0])
-    xs, ys = make_batch([T] * videos, 2048, ncls, base_seed=7, nseg=8)
+    xs, ys = make_batch([T] * videos, 2048, ncls, base_seed=7, nseg=52 if epic else 8)
     xd, yd = [x.cuda() for x in xs], [y.cuda() for y in ys]
     for _ in range(2):
         net(xd, yd, compute_loss=True)
@@ -51,9 +52,9 @@ def main():
     t0 = time.perf_counter()
     rng = np.random.default_rng(0)
     for _ in range(videos):
-        Lm.assign(rng.standard_normal((75, 8)).astype(np.float32), np.arange(8), cfg.Loss.match)
+        Lm.assign(rng.standard_normal((300, 52) if epic else (75, 8)).astype(np.float32), np.arange(52 if epic else 8) % 40, cfg.Loss.match)
     host_match = (time.perf_counter() - t0) * 1e3
-    line = dict(workload=f'havid holdout FACT_CLIP, {videos} videos x {T} frames, eager launches',
+    line = dict(workload=f'{"epic shape" if epic else "havid holdout"} FACT_CLIP, {videos} videos x {T} frames, eager launches',
                 forward_ms=round(fwd, 2), forward_plus_loss_ms=round(both, 2), loss_ms=round(both - fwd, 2),
                 host_matching_ms=round(host_match, 2), launches_forward_plus_loss=launches, loss=float(loss),
                 finite=bool(np.isfinite(float(loss))))
@@ -66,7 +67,7 @@ def main():
         text = net.text_embeddings.cpu()
         net.keep_attn = True
         net(xd, yd)
-        n = 4
+        n = min(4, videos)
         t_cpu = 0.0
         diffs = []
         for b in range(n):
