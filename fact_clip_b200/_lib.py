@@ -55,6 +55,7 @@ _SIGS = {
     'factk_gru_bidir': (i32, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
     'factk_gru_bidir_mma': (i32, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
     'factk_gru_bidir_mma_sorted': (i32, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    'factk_gru_max_clusters': (i32, []),
     'factk_gru_bidir_mma_dbg': (i32, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     'factk_gather_rows': (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp]),
     'factk_fuse_eval_transcript': (i32, [vp, i32, i32, vp, vp, i32, f32, vp, i32, vp, vp, i32, i32, vp, i32, vp]),

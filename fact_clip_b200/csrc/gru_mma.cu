@@ -34,6 +34,9 @@ constexpr int GM_HSTRIDE = GM_HH * 2 + 16;  // bytes per video row of the hidden
 constexpr int GM_HBUF = GM_NV * GM_HSTRIDE; // 4224 bytes per buffer
 constexpr int GM_PSTRIDE = GM_ROWS + 4;     // floats per video row of the partial-sum buffer
 constexpr int GM_THREADS = 128;
+#ifndef GM_SPIN_SLEEP
+#define GM_SPIN_SLEEP 0
+#endif
 constexpr uint32_t GM_EMPTY = 0xFFFFFFFFu;  // "not written yet" marker of a hidden-state word
 
 __device__ __forceinline__ uint32_t gm_pack(float lo, float hi) {
@@ -188,6 +191,19 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
                 continue;
             }
             if (dbg_on && t < 64) dbg[t * 16 + c * 8 + 0] = clock64();
+            // ---- this step's input gates out of the ring (fetched GM_GDEPTH-1 steps ago: the wait never stalls); done BEFORE
+            // waiting for the hidden state so that it is off the critical path of the exchange
+            const bool live = t < myS[c];
+            // groups are committed chain-major, one per (step, chain): everything up to (t, c) must have landed
+            if (GM_NC == 1) asm volatile("cp.async.wait_group %0;" ::"n"(GM_GDEPTH - 2) : "memory");
+            else if (c == 0) asm volatile("cp.async.wait_group %0;" ::"n"(2 * (GM_GDEPTH - 2) + 1) : "memory");
+            else asm volatile("cp.async.wait_group %0;" ::"n"(2 * (GM_GDEPTH - 2)) : "memory");
+            if (live) {
+                const uint8_t* gsrc = gring + (size_t)c * GM_GRING + (size_t)(t % GM_GDEPTH) * 3 * GM_THREADS * 8 + (size_t)tid * 8;
+                g_r[c] = *reinterpret_cast<const float2*>(gsrc);
+                g_z[c] = *reinterpret_cast<const float2*>(gsrc + GM_THREADS * 8);
+                g_n[c] = *reinterpret_cast<const float2*>(gsrc + 2 * GM_THREADS * 8);
+            }
             // ---- B fragments of this warp's K slice: spin until every word has landed, then mark the words empty again
             uint32_t b[4][2];
             {
@@ -203,6 +219,7 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
 #pragma unroll
                     for (int s = 0; s < 4; ++s) ok = ok && (b[s][0] != GM_EMPTY) && (b[s][1] != GM_EMPTY);
                     if (__all_sync(0xffffffffu, ok)) break;
+                    if (GM_SPIN_SLEEP) __nanosleep(GM_SPIN_SLEEP);
                     if (++spins > (1u << 22)) __trap();   // protocol bug: fail loudly instead of hanging the GPU
                 }
 #pragma unroll
@@ -239,17 +256,6 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
                 const float2 x0 = *reinterpret_cast<const float2*>(pq), x1 = *reinterpret_cast<const float2*>(pq + GM_U),
                              x2 = *reinterpret_cast<const float2*>(pq + 2 * GM_U);
                 a_r.x += x0.x; a_r.y += x0.y; a_z.x += x1.x; a_z.y += x1.y; a_n.x += x2.x; a_n.y += x2.y;
-            }
-            const bool live = t < myS[c];
-            // groups are committed chain-major, one per (step, chain): everything up to (t, c) must have landed
-            if (GM_NC == 1) asm volatile("cp.async.wait_group %0;" ::"n"(GM_GDEPTH - 2) : "memory");
-            else if (c == 0) asm volatile("cp.async.wait_group %0;" ::"n"(2 * (GM_GDEPTH - 2) + 1) : "memory");
-            else asm volatile("cp.async.wait_group %0;" ::"n"(2 * (GM_GDEPTH - 2)) : "memory");
-            if (live) {
-                const uint8_t* gsrc = gring + (size_t)c * GM_GRING + (size_t)(t % GM_GDEPTH) * 3 * GM_THREADS * 8 + (size_t)tid * 8;
-                g_r[c] = *reinterpret_cast<const float2*>(gsrc);
-                g_z[c] = *reinterpret_cast<const float2*>(gsrc + GM_THREADS * 8);
-                g_n[c] = *reinterpret_cast<const float2*>(gsrc + 2 * GM_THREADS * 8);
             }
             float2 hn = hprev[c];               // finished videos re-send their last state: every word is written every step
             if (live) {
@@ -343,8 +349,8 @@ static int gru_mma_launch(const float* gi, const float* w_hh_f, const float* b_h
     const int groups = (groups8 + NC - 1) / NC;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t ea = cudaFuncSetAttribute(gru_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem_bytes(1));
-        if (ea == cudaSuccess) ea = cudaFuncSetAttribute(gru_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem_bytes(2));
+        cudaError_t ea = cudaFuncSetAttribute(gru_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ea == cudaSuccess) ea = cudaFuncSetAttribute(gru_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ea != cudaSuccess) { set_error("factk_gru_bidir_mma: smem attribute: %s", cudaGetErrorString(ea)); return FACTK_ERR_CUDA; }
         attr_set = true;
     }
@@ -353,6 +359,13 @@ static int gru_mma_launch(const float* gi, const float* w_hh_f, const float* b_h
     cfg.gridDim = dim3(groups * 2 * GM_CS, 1, 1);
     cfg.blockDim = dim3(GM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = gm_smem_bytes(NC);
+    // Two of these CTAs fit one SM, and with 16 clusters (64 videos) the scheduler does co-locate CTAs of different clusters:
+    // 0.71 us per step up to 8 clusters, 0.80 up to 14, 1.01 at 16 (tools/bench_gru_scale.py).  Forbidding the co-location
+    // (FACTK_GRU_SMEM_KB=120: more than half of an SM's shared memory) is WORSE at 16 clusters -- only 15 exclusive 8-CTA
+    // clusters fit the 148 SMs, the 16th becomes a second wave (1.43 us per step) -- so it is off by default; grouping the
+    // videos by segment count (factk_gru_bidir_mma_sorted) is what recovers most of the loss.
+    static const int excl_kb = [] { const char* e = getenv("FACTK_GRU_SMEM_KB"); return e ? atoi(e) : 0; }();
+    if (excl_kb * 1024 > (int)cfg.dynamicSmemBytes) cfg.dynamicSmemBytes = (size_t)excl_kb * 1024;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -365,4 +378,24 @@ static int gru_mma_launch(const float* gi, const float* w_hh_f, const float* b_h
                             : cudaLaunchKernelEx(&cfg, gru_mma_kernel<2>, gi, w_hh_f, b_hh_f, w_hh_b, b_hh_b, out, o_dtype, ldo, relu, B, slot, nseg, order, dbg);
     if (e != cudaSuccess) { set_error("factk_gru_bidir_mma: launch: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; }
     return check_launch("factk_gru_bidir_mma");
+}
+
+// Diagnostic: how many 8-CTA clusters of gru_mma_kernel<1> can be co-resident on the current device.
+extern "C" int factk_gru_max_clusters(void) {
+    cudaFuncSetAttribute(gru_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem_bytes(1));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(32 * GM_CS, 1, 1);
+    cfg.blockDim = dim3(GM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = gm_smem_bytes(1);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = GM_CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = -1;
+    if (cudaOccupancyMaxActiveClusters(&n, gru_mma_kernel<1>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
 }

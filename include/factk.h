@@ -210,6 +210,9 @@ int factk_gru_bidir_mma_sorted(const float* gi, const float* w_hh_f, const float
                                const float* w_hh_b, const float* b_hh_b, int Hh, void* out, int o_dtype, int ldo,
                                int relu, int B, int slot, const int32_t* nseg, int32_t* order_ws, void* stream);
 
+/* Diagnostic: number of 8-CTA clusters of the tensor-core GRU kernel that can be co-resident on the current device. */
+int factk_gru_max_clusters(void);
+
 int factk_gru_bidir_mma_dbg(const float* gi, const float* w_hh_f, const float* b_hh_f,
                             const float* w_hh_b, const float* b_hh_b, int Hh,
                             void* out, int o_dtype, int ldo, int relu,
