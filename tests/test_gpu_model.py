@@ -331,3 +331,53 @@ def test_staged_sweep_from_npy_files(tmp_path):
             ref = net([x], [torch.zeros(lens[n], dtype=torch.long)])
             assert np.array_equal(got[n], ref[0]['pred']), (dev_t, n)
         st.close()
+
+
+VARIANTS = [
+    dict(f='m', block='iuU', f_ln=True, fpos=True),
+    dict(f='m', block='iUU', f_ngp=2, M=7),
+    dict(f='m2', block='iuuU', f_ngp=4, fpos=True),
+    dict(f='m', block='iu', f_ln=True, f_ngp=4, M=20),
+    dict(f='m2', block='iU', trans=True, fpos=True),
+    dict(f='m', block='iuU', trans=True, A=64, a_i='gru', a_u='sa', f_ln=True),
+    dict(f='m', block='iUU', trans=True, A=64, a_i='sca', a_u='gru_om', f_ngp=2),
+    dict(f='m2', block='iuUU', layers=3, a_layers=3, nhead=2),
+]
+
+
+@pytest.mark.parametrize('kw', VARIANTS, ids=lambda kw: '-'.join(f'{k}{v}' for k, v in kw.items()))
+@pytest.mark.parametrize('clip', [False, True])
+def test_variant_combinations_vs_oracle_fp32(kw, clip):
+    """Combinations of the model options (TCN flavour, layer norm, grouped convs, frame positions, block strings, transcript
+    tokens, GRU action branch, CLIP head) that no single reference fixture covers, fp32 mode against the oracle (which is
+    pinned to the reference on every option separately): logits within 1e-4, identical segmentation and predictions."""
+    cfg = C.tiny(**kw)
+    torch.manual_seed(11)
+    ncls, D, lens = 6, 24, [75, 33, 130]
+    net = (FACT_CLIP(cfg, D, ncls, make_text_embeddings(ncls)) if clip else FACT(cfg, D, ncls)).eval()
+    with torch.no_grad():
+        for k, v in net.state_dict().items():
+            if k.endswith(('out_linear.weight', 'conv_out.weight', 'seg_combine.weight')):
+                v.mul_(3.0)                       # several predicted classes -> multi-segment TDU paths
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    hp = O.hparams_from_cfg(cfg, D, ncls)
+    xs, ys = make_batch(lens, D, ncls, base_seed=123, nseg=5)
+    net.compute_mode, net.keep_attn = 'fp32', True
+    net = net.to(DEV)
+    saves = net([x.to(DEV) for x in xs], [y.to(DEV) for y in ys])
+    for b, (x, y) in enumerate(zip(xs, ys)):
+        with torch.no_grad():
+            o = O.forward_video(sd, hp, x, clip=clip, transcript=O.transcript_of(y) if hp['trans'] else None)
+        net.stash_video(b)
+        seg_ok = True
+        for i, (blk, st) in enumerate(zip(net.block_list, o['blocks'])):
+            if 'seg_label' in st:
+                seg_ok = seg_ok and torch.equal(blk.tdu.seg_label.cpu(), st['seg_label'])
+            if not seg_ok:
+                break
+            for k in ('frame_clogit', 'action_clogit', 'seg_clogit'):
+                if k in st:
+                    r = rel(getattr(blk, k)[:, 0], st[k])
+                    assert r < 1e-4, (b, i, k, r)
+        assert seg_ok, f'video {b}: segmentation differs'
+        assert np.array_equal(saves[b]['pred'], o['pred'].numpy())
