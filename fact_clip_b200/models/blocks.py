@@ -166,6 +166,13 @@ class _FactBase(nn.Module):
         return self._engine
 
     def forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
+        dev = next(self.parameters()).device
+        if dev.type == 'cuda':
+            with torch.cuda.device(dev):          # kernels launch on the current stream of the MODEL's device
+                return self._forward(seq_list, label_list, compute_loss, forced_preds)
+        return self._forward(seq_list, label_list, compute_loss, forced_preds)
+
+    def _forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
         if self.training:
             raise RuntimeError('the forward is built for eval mode: call net.eval() first. Training mode would need the '
                                "reference's dropout, channel masking and time masking (blocks.py:58-70), which are part of the "
@@ -242,9 +249,11 @@ class _FactBase(nn.Module):
             raise NotImplementedError('FACT.trans models run one video per call through forward() (the transcript sets the token count)')
         if self.training:
             raise RuntimeError('the forward is built for eval mode: call net.eval() first (see forward())')
-        if next(self.parameters()).device.type != 'cuda':
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
             raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
-        h = self.engine().submit(list(seq_list), channel_major=channel_major)
+        with torch.cuda.device(dev):
+            h = self.engine().submit(list(seq_list), channel_major=channel_major)
         self._last = h.out
         return h
 

@@ -98,10 +98,10 @@ class FACT(_FactBase):
         self.compute_mode = 'bf16'
         self._engine = None
 
-    def forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
+    def _forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
         if compute_loss:
             raise NotImplementedError('compute_loss for the verb/noun model is not built (SURVEY.md 8f rank 1)')
-        return super().forward(seq_list, label_list, False, forced_preds)
+        return super()._forward(seq_list, label_list, False, forced_preds)
 
     def stash_video(self, b):
         """Per-block attributes of video ``b`` as the reference leaves them (:386-396, 470-481): frame_logp (T,1,A),

@@ -421,3 +421,22 @@ def test_tcn_options_on_the_tensor_core_path(kw):
         tot += lens[b]
     # 429 frames of a random 9-class model: a handful of near-tie frames may flip under bf16; the logits above are the bar
     assert agree / tot >= 0.97
+
+
+def test_model_on_a_non_current_device():
+    """A model placed on cuda:1 runs there (kernels on that device's current stream) while the process' current device
+    stays cuda:0, and gives what cuda:0 gives."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    g = load_golden('tiny_m_iuU_clip')
+    xs, ys = [v['x'] for v in g['videos']], [v['label'] for v in g['videos']]
+    net0 = build(g, 'fp32')
+    ref = net0([x.to('cuda:0') for x in xs], ys)
+    net1 = build(g, 'fp32').to('cuda:1')
+    assert torch.cuda.current_device() == 0
+    got = net1([x.to('cuda:1') for x in xs], ys)
+    pipelined = net1.submit([x.pin_memory() for x in xs], ys).result()
+    assert torch.cuda.current_device() == 0
+    for a, b, c in zip(got, ref, pipelined):
+        assert np.array_equal(a['pred'], b['pred']) and np.array_equal(c['pred'], b['pred'])
+    assert net1._last['pred'].device.index == 1
