@@ -823,11 +823,9 @@ extern "C" int factk_col_softmax_apply(const float* L, int ldl, const void* X, i
     col_stats_combine_kernel<<<B, 256, 0, st>>>(sp, stats, slot, len, M, ns);
     if (x_dtype == FACTK_BF16 && (E % 8) == 0 && (ldx % 8) == 0 && aligned16(X)) {
         const int etiles = (E + CAM_E - 1) / CAM_E, mchunks = (M + CAM_TOK - 1) / CAM_TOK;
-        static bool cam_attr = false;
-        if (!cam_attr) {
+        static unsigned long long cam_devs = 0;
+        if (first_use_on_device(cam_devs))
             cudaFuncSetAttribute(col_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAM_SMEM);
-            cam_attr = true;
-        }
         col_apply_mma_kernel<<<dim3(ns, mchunks * etiles, B), 256, CAM_SMEM, st>>>(L, ldl, stats, reinterpret_cast<const __nv_bfloat16*>(X), ldx,
                                                                            part, P, ldp, slot, len, M, E, ns, etiles);
     } else {

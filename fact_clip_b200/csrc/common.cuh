@@ -11,6 +11,16 @@ namespace factk {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// Function attributes (opt-in shared memory) are per device: remember which devices of this process were configured.
+inline bool first_use_on_device(unsigned long long& mask) {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    const bool first = (mask & bit) == 0;
+    mask |= bit;
+    return first;
+}
+
 #define FACTK_REQUIRE(cond, ...)                  \
     do {                                          \
         if (!(cond)) {                            \

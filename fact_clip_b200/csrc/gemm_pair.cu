@@ -282,11 +282,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_pair_kernel(const __grid_c
 template <int BN>
 static int launch_pair(const PairParams& p, int sms, cudaStream_t st) {
     using Cfg = PairCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_device(attr_devs)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) { set_error("factk_gemm_pair: smem attribute: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; }
-        attr_set = true;
     }
     int units = sms / 2;
     if (units > p.total) units = p.total;

@@ -390,11 +390,10 @@ static const char* tc_unsupported_reason(const factk_gemm_t* g) {
 
 template <int BN, bool TF32, bool YBF, int RES>
 static int launch_tc4(const TcParams& p, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_device(attr_devs)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, YBF, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM);
         if (e != cudaSuccess) { set_error("factk_gemm_tc: smem attribute: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; }
-        attr_set = true;
     }
     gemm_tc_kernel<BN, TF32, YBF, RES><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(p);
     return check_launch("factk_gemm_tc");

@@ -347,12 +347,11 @@ static int gru_mma_launch(const float* gi, const float* w_hh_f, const float* b_h
     const int groups8 = (B + GM_NV - 1) / GM_NV;
     const int NC = nc_env == 1 || nc_env == 2 ? nc_env : (groups8 * 2 * GM_CS <= sms ? 1 : 2);
     const int groups = (groups8 + NC - 1) / NC;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_device(attr_devs)) {
         cudaError_t ea = cudaFuncSetAttribute(gru_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ea == cudaSuccess) ea = cudaFuncSetAttribute(gru_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ea != cudaSuccess) { set_error("factk_gru_bidir_mma: smem attribute: %s", cudaGetErrorString(ea)); return FACTK_ERR_CUDA; }
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

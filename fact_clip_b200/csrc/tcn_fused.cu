@@ -422,11 +422,10 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_layer_kernel(const __grid_
 template <int F, int CG>
 static int launch_tcn(const TcnParams& p, int sms, cudaStream_t st) {
     using Cfg = TcnCfg<F, CG>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_device(attr_devs)) {
         cudaError_t e = cudaFuncSetAttribute(tcn_layer_kernel<F, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) { set_error("factk_tcn_layer: smem attribute: %s", cudaGetErrorString(e)); return FACTK_ERR_CUDA; }
-        attr_set = true;
     }
     int units = sms / CG;
     if (units > p.total) units = p.total;

@@ -494,10 +494,9 @@ extern "C" int factk_segment_mean(const void* X, int x_dtype, int ldx, void* seg
         const int nchunks = (slot + SM2_CHUNK - 1) / SM2_CHUNK;
         float* head = ws;
         float* tail = ws + (size_t)B * nchunks * E;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned long long attr_devs = 0;
+        if (first_use_on_device(attr_devs)) {
             cudaFuncSetAttribute(segment_mean_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            attr_set = true;
         }
         segment_mean_pass1_kernel<<<dim3(nchunks, B), 128 * SM2_LANES, smem, st>>>(X, x_dtype, ldx, seg, s_dtype, lds, seg_label, seg_start,
                                                                                    seg_len, nseg, slot, E, head, tail);

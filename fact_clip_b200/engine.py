@@ -115,7 +115,11 @@ class FactEngine:
         if sig != self._wsig:
             self._wsig, self._wcache, self._p = sig, {}, params
             self._graphs = {}                     # captured graphs hold pointers of derived weights
-        self.dev = next(self.m.parameters()).device
+        dev = next(self.m.parameters()).device
+        if getattr(self, 'dev', dev) != dev:      # the module moved to another GPU: every cached buffer lives on the old one
+            self._bufs, self._zbufs, self._len_sig, self._graphs = {}, {}, None, {}
+            self._copy_stream, self._slot_free = None, [None, None]
+        self.dev = dev
 
     def p(self, name):
         t = self._p[name]

@@ -440,3 +440,14 @@ def test_model_on_a_non_current_device():
     for a, b, c in zip(got, ref, pipelined):
         assert np.array_equal(a['pred'], b['pred']) and np.array_equal(c['pred'], b['pred'])
     assert net1._last['pred'].device.index == 1
+    # the tensor-core path too (kernels with opt-in shared memory: the attribute is per device)
+    cfg = C.PRESETS['havid_view0_lh_pt_holdout']()
+    torch.manual_seed(0)
+    big = FACT_CLIP(cfg, 2048, 75, make_text_embeddings(75)).eval()
+    big.compute_mode = 'bf16'
+    xs, _ = make_batch([700, 300], 2048, 75, base_seed=5, nseg=8)
+    a = big.to('cuda:0')([x.to('cuda:0') for x in xs], None)
+    b = big.to('cuda:1')([x.to('cuda:1') for x in xs], None)
+    for p, q in zip(a, b):
+        assert np.array_equal(p['pred'], q['pred'])
+    assert all(t.device.index == 1 for t in big.engine()._bufs.values() if t.is_cuda)      # no buffer left on the old GPU
