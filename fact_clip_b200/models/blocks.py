@@ -180,10 +180,15 @@ class _FactBase(nn.Module):
                                'would be wrong')
         if compute_loss and self.mcriterion is None:
             raise RuntimeError('compute_loss=True needs net.mcriterion = MatchCriterion(cfg, nclasses, bg_ids) (scripts/train.py:207)')
+        seqs = list(seq_list)        # CUDA tensors, or (pinned) host tensors copied straight into the packed batch
+        if not seqs and not compute_loss:
+            return []                # the reference's per-video loop simply does not run (blocks.py:113)
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('FACT forward runs only on a CUDA device through libfactk.so (no CPU fallback)')
-        seqs = list(seq_list)        # CUDA tensors, or (pinned) host tensors copied straight into the packed batch
+        if any(s.dim() != 2 or s.shape[0] == 0 or s.shape[1] != self.in_dim for s in seqs):
+            raise ValueError(f'every video must be a non-empty (T, {self.in_dim}) feature matrix, got '
+                             f'{[tuple(s.shape) for s in seqs]}')
         if self.cfg.FACT.trans:
             return self._forward_with_transcripts(seqs, label_list, forced_preds, compute_loss)
         out = self.engine().run(seqs, forced_preds=forced_preds, keep=getattr(self, 'keep_attn', False))

@@ -132,3 +132,10 @@ def test_verb_noun_model_matches_reference_state_dict():
     assert torch.equal(again.state_dict()[k], g['state_dict'][k])
     with pytest.raises(AssertionError):
         VNFACT(C.tiny(**g['tiny_kwargs']), g['in_dim'], n1 + 1, n2, action_pairs=list(zip(g['vids'], g['nids'])))
+
+
+def test_input_validation_messages():
+    net = FACT(C.tiny(), 24, 7).eval()
+    assert net([], []) == []                                   # no videos: the reference's loop does not run either
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        net([torch.zeros(5, 24)], None)
