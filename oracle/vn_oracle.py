@@ -120,3 +120,43 @@ def forward_video(sd, hp, seq, vids, nids, forced_preds=None):
     last = out['blocks'][-1]
     out['pred'] = evaluate(last['action_logp'], last['a2f_attn'], last['frame_logp'], hp['mwt'])
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# loss value (blocks_SepVerbNoun.py:95-112, 254-266, 400-413, 485-497 on loss.py's MatchCriterion)
+
+
+def action_token_loss(crit, match, action_logp):
+    """Block.action_token_loss (:254-266): unmatched tokens are labelled null, matched ones with their segment's action;
+    class-weighted negative log-probability, MEAN over the tokens (no normalisation by the weights, unlike loss.py:196)."""
+    aind, sind = match
+    A, C1 = action_logp.shape
+    clabel = torch.full((A,), C1 - 1, dtype=torch.long)
+    clabel[aind] = crit.transcript[sind]
+    return (-(action_logp[torch.arange(A), clabel]) * crit.cweight[clabel]).mean()
+
+
+def loss_video(out, hp, label, lp, vids):
+    """FACT._loss_one_video of the verb/noun model on forward_video()'s output: log-probability forms of the frame /
+    segment losses (is_logit=False), (frame/2 + seg/2)/2 + token/2 (+ both cross-attention losses in update blocks) +
+    sw * smooth, mean over the blocks.  The criterion sees the ACTION classes (len(vids) of them)."""
+    import loss_oracle as LO
+    A = len(vids)
+    crit = LO.Criterion(label, A, lp)
+    last = out['blocks'][-1]
+    match = LO.match_tokens(crit, torch.exp(last['action_logp']), last['a2f_attn'])
+    losses = []
+    for st, bc in zip(out['blocks'], hp['blocks']):
+        flp, slp = st['frame_logp'], st['seg_logp']
+        sl, ln = st['seg_label'], st['seg_lens'].float()
+        frame = (-(flp * crit.onehot_class) * crit.cweight[:A]).sum() / crit.onehot_class.sum() / 2
+        z = LO.zoom(crit.onehot_class, sl, ln)
+        seg = (-(slp * z) * crit.cweight[:A]).sum() / z.sum() / 2
+        atk = action_token_loss(crit, match, st['action_logp']) / 2
+        smooth = torch.clamp((flp[1:] - flp[:-1]) ** 2, min=0, max=16).mean()
+        l = (frame + seg) / 2 + atk + lp['sw'] * smooth
+        if bc['type'] == 'U':
+            l = l + LO.cross_attn_loss_tdu(crit, match, st['f2a_attn_logit'].t(), sl, ln, 1) \
+                  + LO.cross_attn_loss_tdu(crit, match, st['a2f_attn_logit'], sl, ln, 2)
+        losses.append(l)
+    return dict(loss=sum(losses) / len(losses), block_losses=losses, match=match)

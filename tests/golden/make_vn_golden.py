@@ -30,6 +30,9 @@ CASES = [
     ('vn_m2_IUU', dict(f='m2', block='IUU'), [88, 35, 1], 24),
     ('vn_m_IU_fpos', dict(f='m', block='IU', fpos=True, M=10), [60], 16),
 ]
+# loss settings per case (Loss section, background action ids): one-to-one and one-to-many matching
+LOSS = {'vn_m2_IUU': (dict(pc=0.5, a2fc=1.0, match='o2o', bgw=0.5, nullw=0.1, sw=2.0), [0]),
+        'vn_m_IU_fpos': (dict(pc=1.0, a2fc=1.0, match='o2m', bgw=1.0, nullw=0.05, sw=5.0), [])}
 
 
 def write_tables(d):
@@ -50,8 +53,13 @@ def main():
     from fact_clip.models import blocks_SepVerbNoun as VN
     for name, kw, Ts, D in CASES:
         cfg = ref_cfg(ours.tiny(**kw))
+        loss_kw, bg = LOSS[name]
+        for k, v in loss_kw.items():
+            cfg.Loss[k] = v
         torch.manual_seed(SEED)
         net = VN.FACT(cfg, D, N1, N2)
+        from fact_clip.models.loss import MatchCriterion
+        net.mcriterion = MatchCriterion(cfg, len(PAIRS), bg)
         assert VN._VIDS == [v for v, _ in PAIRS] and VN._NIDS == [n for _, n in PAIRS]
         net.eval()
         with torch.no_grad():
@@ -64,6 +72,10 @@ def main():
             x, y = make_video(T, D, len(PAIRS), seed=300 + i, nseg=min(5, T))
             with torch.no_grad():
                 save = net([x], [y])
+                loss, lsave = net([x], [y], compute_loss=True)
+                crit = net.mcriterion
+                match = crit.match(torch.exp(net.block_list[-1].action_logp), net.block_list[-1].a2f_attn)
+            loss_rec = dict(loss=float(loss), block_losses=[float(v) for v in net.loss_list], match=[m.tolist() for m in match])
             blocks = []
             for b in net.block_list:
                 st = dict(frame_logp=b.frame_logp.detach().clone(), seg_logp=b.seg_logp.detach().clone(),
@@ -73,9 +85,9 @@ def main():
                     if getattr(b, k, None) is not None:
                         st[k] = getattr(b, k).detach().clone()
                 blocks.append(st)
-            vids.append(dict(x=x, label=y, pred=torch.from_numpy(save[0]['pred']), blocks=blocks))
+            vids.append(dict(x=x, label=y, pred=torch.from_numpy(save[0]['pred']), blocks=blocks, loss=loss_rec))
         torch.save(dict(name=name, tiny_kwargs=kw, n_classes=(N1, N2), vids=[v for v, _ in PAIRS], nids=[n for _, n in PAIRS],
-                        in_dim=D, state_dict=sd, videos=vids), os.path.join(ROOT, 'tests', 'golden', name + '.pt'))
+                        in_dim=D, state_dict=sd, videos=vids, loss=loss_kw, bg_ids=bg), os.path.join(ROOT, 'tests', 'golden', name + '.pt'))
         print(name, 'ok', [[int(s['seg_lens'].numel()) for s in v['blocks']] for v in vids],
               [int(v['pred'].unique().numel()) for v in vids])
 

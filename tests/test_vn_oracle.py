@@ -36,3 +36,25 @@ def test_vn_oracle_matches_reference(name):
                 if k in ref:
                     assert rel(st[k], ref[k][0]) < 1e-5, k
         assert torch.equal(out['pred'], v['pred'])
+
+
+@pytest.mark.parametrize('name', VN_CASES)
+def test_vn_loss_oracle_matches_reference(name):
+    """Loss value of the verb/noun model (oracle/vn_oracle.loss_video) against the reference's compute_loss=True numbers."""
+    import math
+    import loss_oracle as LO
+    g = torch.load(os.path.join(GOLDEN, name + '.pt'), weights_only=False)
+    cfg = C.tiny(**g['tiny_kwargs'])
+    cfg.merge(dict(Loss=g['loss']))
+    hp = O.hparams_from_cfg(cfg, g['in_dim'], g['n_classes'])
+    lp = LO.loss_params(cfg, bg_ids=g['bg_ids'])
+    for v in g['videos']:
+        with torch.no_grad():
+            out = VO.forward_video(g['state_dict'], hp, v['x'], g['vids'], g['nids'])
+            res = VO.loss_video(out, hp, v['label'], lp, g['vids'])
+        ref = v['loss']
+        assert [m.tolist() for m in res['match']] == ref['match']
+        for a, b in zip(res['block_losses'], ref['block_losses']):
+            assert (math.isnan(b) and math.isnan(float(a))) or abs(float(a) - b) <= 2e-5 * max(1.0, abs(b)), (float(a), b)
+        b = ref['loss']
+        assert (math.isnan(b) and math.isnan(float(res['loss']))) or abs(float(res['loss']) - b) <= 2e-5 * max(1.0, abs(b))
