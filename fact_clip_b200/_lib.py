@@ -61,11 +61,11 @@ _SIGS = {
     'factk_fuse_eval_transcript': (i32, [vp, i32, i32, vp, vp, i32, f32, vp, i32, vp, vp, i32, i32, vp, i32, vp]),
     'factk_embed_tokens': (i32, [vp, i32, vp, vp, i32, vp, i32, i32, i32, vp]),
     'factk_label_prep': (i32, [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, i32, vp, vp]),
-    'factk_match_cost': (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32, f32, f32, vp, i32, vp, i32, i32, vp]),
+    'factk_match_cost': (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32, f32, f32, vp, i32, vp, i32, i32, i32, vp]),
     'factk_loss_pick': (i32, [vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i32, vp, i32, vp]),
-    'factk_loss_smooth': (i32, [vp, i32, i32, vp, i32, i32, vp, i32, vp]),
+    'factk_loss_smooth': (i32, [vp, i32, i32, vp, i32, i32, vp, i32, i32, vp]),
     'factk_col_lse': (i32, [vp, i32, i32, i32, vp, vp, vp, i32, vp, i32, i32, vp]),
-    'factk_token_loss': (i32, [vp, i32, i32, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, vp]),
+    'factk_token_loss': (i32, [vp, i32, i32, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, vp]),
     'factk_loss_combine': (i32, [vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, i32, f32, f32, i32, vp, vp, i32, vp]),
     'factk_fuse_eval': (i32, [vp, vp, i32, i32, vp, vp, i32, f32, vp, i32, i32, vp, i32, i32, i32, vp]),
     'factk_transpose_rows': (i32, [vp, C.c_longlong, vp, i32, i32, i32, i32, i32, vp, vp]),

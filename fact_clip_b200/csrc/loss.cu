@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) loss_pick_kernel(
 
 __global__ void __launch_bounds__(256) smooth_kernel(const float* __restrict__ X, int ldx, int ncol,
                                                      float* __restrict__ part, int B, int slot,
-                                                     const int32_t* __restrict__ len, int nchunk) {
+                                                     const int32_t* __restrict__ len, int nchunk, int is_logp) {
     __shared__ float sm[LS_WARPS];
     const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int T = len ? len[b] : slot;
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256) smooth_kernel(const float* __restrict__ X
         if (t + 1 >= T) break;
         const float* r0 = X + ((size_t)b * slot + t) * ldx;
         const float* r1 = r0 + ldx;
-        const float l0 = warp_lse(r0, nullptr, ncol, lane), l1 = warp_lse(r1, nullptr, ncol, lane);
+        // is_logp: the rows already hold log-probabilities (smooth_loss(..., is_logit=False), loss.py:12-15)
+        const float l0 = is_logp ? 0.f : warp_lse(r0, nullptr, ncol, lane), l1 = is_logp ? 0.f : warp_lse(r1, nullptr, ncol, lane);
         float s = 0.f;
         for (int c = lane; c < ncol; c += 32) {
             const float d = (r1[c] - l1) - (r0[c] - l0);
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(256) match_cost_kernel(const float* __restrict
                                                          const int32_t* __restrict__ transcript, const int32_t* __restrict__ seg_len,
                                                          const int32_t* __restrict__ nseg, const float* __restrict__ overlap,
                                                          int smax, int ldo, int slot, float pc, float a2fc,
-                                                         float* __restrict__ cost) {
+                                                         float* __restrict__ cost, int logp) {
     extern __shared__ float smf[];     // colsum[M], lse[M]
     float* colsum = smf;
     float* lse = smf + M;
@@ -196,8 +197,8 @@ __global__ void __launch_bounds__(256) match_cost_kernel(const float* __restrict
         for (int s = 0; s < S; ++s) acc += overlap[((size_t)b * smax + s) * ldo + a];
         colsum[a] = acc;
     }
-    for (int a = wid; a < M; a += 8) {
-        const float l = warp_lse(aclogit + ((size_t)b * M + a) * C1, nullptr, C1, lane);
+    for (int a = wid; a < M; a += 8) {       // logp: the rows are log-probabilities, used as exp(.) (blocks_SepVerbNoun.py:101)
+        const float l = logp ? 0.f : warp_lse(aclogit + ((size_t)b * M + a) * C1, nullptr, C1, lane);
         if (lane == 0) lse[a] = l;
     }
     __syncthreads();
@@ -219,7 +220,8 @@ __global__ void __launch_bounds__(256) token_loss_kernel(const float* __restrict
                                                          const int32_t* __restrict__ aind, const int32_t* __restrict__ sind,
                                                          const int32_t* __restrict__ nmatch, int kmax,
                                                          const int32_t* __restrict__ transcript, int smax,
-                                                         const float* __restrict__ cweight, float* __restrict__ out, int out_stride) {
+                                                         const float* __restrict__ cweight, float* __restrict__ out, int out_stride,
+                                                         int logp_mean) {
     extern __shared__ float smf[];     // num[M], den[M], clabel[M]
     float* num = smf;
     float* den = smf + M;
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(256) token_loss_kernel(const float* __restrict
     __syncthreads();
     for (int a = wid; a < M; a += 8) {
         const float* row = aclogit + ((size_t)b * M + a) * C1;
-        const float l = warp_lse(row, nullptr, C1, lane);
+        const float l = logp_mean ? 0.f : warp_lse(row, nullptr, C1, lane);
         if (lane == 0) {
             const float wgt = cweight[clabel[a]];
             num[a] = -(row[clabel[a]] - l) * wgt;
@@ -244,13 +246,15 @@ __global__ void __launch_bounds__(256) token_loss_kernel(const float* __restrict
     if (threadIdx.x == 0) {
         float n = 0.f, d = 0.f;
         for (int a = 0; a < M; ++a) { n += num[a]; d += den[a]; }
-        out[(size_t)b * out_stride] = n / d;
+        // logp_mean: the verb/noun model's own token loss (blocks_SepVerbNoun.py:254-266) takes log-probabilities and
+        // averages over the tokens instead of normalising by the class weights
+        out[(size_t)b * out_stride] = logp_mean ? n / (float)M : n / d;
     }
 }
 
 struct LossPlan {
     int nb;
-    int type[FACTK_LOSS_MAX_BLOCKS];      // 0 input, 1 update, 2 update with temporal down/up-sampling
+    int type[FACTK_LOSS_MAX_BLOCKS];      // 0 input, 1 update, 2 update with temporal down/up-sampling; 3 / 4: verb/noun input / update
 };
 
 __device__ __forceinline__ float chunk_sum(const float* ws, int term, int b, int B, int nchunk) {
@@ -283,11 +287,18 @@ __global__ void loss_combine_kernel(const float* __restrict__ ws, LossPlan plan,
             const float fs = chunk_sum(ws, t0 + 5, b, B, nchunk) / ((T - 1.f) * (float)M);
             const float as = chunk_sum(ws, t0 + 6, b, B, nchunk) / ((T - 1.f) * (float)M);
             l = atk + f2a + a2f + fl + sw * (as + fs + sm);
-        } else {
+        } else if (plan.type[i] == 2) {
             const float S = (float)npred[(size_t)i * B + b];
             const float f2a = chunk_sum(ws, t0 + 3, b, B, nchunk) / S, a2f = chunk_sum(ws, t0 + 4, b, B, nchunk) / S;
             const float seg = chunk_sum(ws, t0 + 7, b, B, nchunk) / S;
             l = (fl + seg) / 2.f + atk + f2a + a2f + sw * sm;
+        } else {
+            // verb/noun blocks (blocks_SepVerbNoun.py:400-413, 485-497): frame, segment and token terms enter halved
+            const float S = (float)npred[(size_t)i * B + b];
+            const float seg = chunk_sum(ws, t0 + 7, b, B, nchunk) / S;
+            l = (fl / 2.f + seg / 2.f) / 2.f + atk / 2.f + sw * sm;
+            if (plan.type[i] == 4)
+                l += chunk_sum(ws, t0 + 3, b, B, nchunk) / S + chunk_sum(ws, t0 + 4, b, B, nchunk) / S;
         }
         out[(size_t)b * ldo + 4 + i] = l;
         fact += l;
@@ -324,10 +335,10 @@ extern "C" int factk_loss_pick(const float* X, int ldx, int xslot, int ncol, con
 }
 
 extern "C" int factk_loss_smooth(const float* X, int ldx, int ncol, float* part, int B, int slot, const int32_t* len,
-                                 int nchunk, void* stream) {
+                                 int nchunk, int is_logp, void* stream) {
     FACTK_REQUIRE(X && part && B > 0 && slot > 0 && ncol > 0, "factk_loss_smooth: bad args");
     FACTK_REQUIRE(nchunk * LS_CHUNK >= slot, "factk_loss_smooth: %d partial slots do not cover %d frames", nchunk, slot);
-    smooth_kernel<<<dim3(nchunk, B), 256, 0, (cudaStream_t)stream>>>(X, ldx, ncol, part, B, slot, len, nchunk);
+    smooth_kernel<<<dim3(nchunk, B), 256, 0, (cudaStream_t)stream>>>(X, ldx, ncol, part, B, slot, len, nchunk, is_logp);
     return check_launch("factk_loss_smooth");
 }
 
@@ -353,7 +364,7 @@ extern "C" int factk_label_prep(const int32_t* label, const int32_t* seg_start, 
 extern "C" int factk_match_cost(const float* attn, int lda, int aslot, const int32_t* ridx, const float* aclogit, int M,
                                 int C1, const int32_t* transcript, const int32_t* seg_start, const int32_t* seg_len,
                                 const int32_t* nseg, int smax, float pc, float a2fc, float* overlap, int ldo, float* cost,
-                                int B, int slot, void* stream) {
+                                int B, int slot, int logp, void* stream) {
     FACTK_REQUIRE(attn && aclogit && transcript && seg_start && seg_len && nseg && overlap && cost && B > 0 && M > 0 && smax > 0,
                   "factk_match_cost: bad args");
     FACTK_REQUIRE(ldo >= M && M <= 4096, "factk_match_cost: bad token count %d / overlap stride %d", M, ldo);
@@ -362,17 +373,17 @@ extern "C" int factk_match_cost(const float* attn, int lda, int aslot, const int
     int rc = check_launch("factk_match_cost(overlap)");
     if (rc) return rc;
     match_cost_kernel<<<B, 256, 2 * M * sizeof(float), (cudaStream_t)stream>>>(aclogit, M, C1, transcript, seg_len, nseg, overlap,
-                                                                               smax, ldo, slot, pc, a2fc, cost);
+                                                                               smax, ldo, slot, pc, a2fc, cost, logp);
     return check_launch("factk_match_cost");
 }
 
 extern "C" int factk_token_loss(const float* aclogit, int M, int C1, const int32_t* aind, const int32_t* sind,
                                 const int32_t* nmatch, int kmax, const int32_t* transcript, int smax, const float* cweight,
-                                float* out, int out_stride, int B, void* stream) {
+                                float* out, int out_stride, int B, int logp_mean, void* stream) {
     FACTK_REQUIRE(aclogit && aind && sind && nmatch && transcript && cweight && out && B > 0 && M > 0 && M <= 4096,
                   "factk_token_loss: bad args");
     token_loss_kernel<<<B, 256, 3 * M * sizeof(float), (cudaStream_t)stream>>>(aclogit, M, C1, aind, sind, nmatch, kmax, transcript,
-                                                                               smax, cweight, out, out_stride);
+                                                                               smax, cweight, out, out_stride, logp_mean);
     return check_launch("factk_token_loss");
 }
 
@@ -385,7 +396,7 @@ extern "C" int factk_loss_combine(const float* ws, int nb, const int32_t* block_
     LossPlan plan;
     plan.nb = nb;
     for (int i = 0; i < nb; ++i) {
-        FACTK_REQUIRE(block_type[i] >= 0 && block_type[i] <= 2 && (block_type[i] != 2 || npred), "factk_loss_combine: bad block type");
+        FACTK_REQUIRE(block_type[i] >= 0 && block_type[i] <= 4 && (block_type[i] < 2 || npred), "factk_loss_combine: bad block type");
         plan.type[i] = block_type[i];
     }
     loss_combine_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ws, plan, B, nchunk, len, npred, C, M, sw, use_clip,

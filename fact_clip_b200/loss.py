@@ -16,6 +16,7 @@ from scipy.optimize import linear_sum_assignment
 from . import ops
 
 _TYPE = {'i': 0, 'u': 1, 'U': 2}
+_TYPE_VN = {'I': 3, 'U': 4}          # verb/noun model (blocks_SepVerbNoun.py): halved frame / segment / token terms
 
 
 class MatchCriterion:
@@ -83,8 +84,10 @@ class LossRunner:
         e, cfg = self.e, self.crit.cfg
         hp, Lc = e.hp, cfg.Loss
         B, slot, ln, dev = e.B, e.slot, e.len, e.dev
-        C, M, nb = hp['n_classes'], e.ntok, len(hp['blocks'])
+        vn = e.vn is not None              # verb/noun model: the criterion sees the ACTION classes, the blocks' log-probs
+        C, M, nb = (len(e.vn[0]) if vn else hp['n_classes']), e.ntok, len(hp['blocks'])
         assert nb <= 8, 'loss value: at most 8 blocks'
+        assert C == self.crit.nclasses, f'criterion built for {self.crit.nclasses} classes, model has {C}'
         I32, buf = torch.int32, e.buf
         # ---- labels -> ground-truth segments (the TDU run-length kernel serves MatchCriterion.set_label, loss.py:56-60)
         label = buf('loss_label', (B, slot), I32)
@@ -114,7 +117,10 @@ class LossRunner:
         last = out['blocks'][-1]
         Mp = last['a2f_attn_logit'].shape[2]
         overlap, cost = buf('loss_ov', (B, smax, Mp)), buf('loss_cost', (B, M, smax))
-        if 'a2f_attn_seg' in last:
+        if vn:         # cprob = exp(action_logp) (blocks_SepVerbNoun.py:100-101)
+            ops.match_cost(last['a2f_attn_seg'], last['action_logp'], transcript, gstart, glen, gn, Lc.pc, Lc.a2fc, overlap, cost,
+                           M, ridx=last['seg_label'], logp=True)
+        elif 'a2f_attn_seg' in last:
             ops.match_cost(last['a2f_attn_seg'], last['action_clogit'], transcript, gstart, glen, gn, Lc.pc, Lc.a2fc, overlap, cost,
                            M, ridx=last['seg_label'])
         else:
@@ -140,9 +146,26 @@ class LossRunner:
         ws.zero_()
         npred = buf('loss_npred', (nb, B), I32)
         types = []
+        zero_lse = e.zbuf('loss_zero_lse', (B, C), torch.float32) if vn else None      # log-prob inputs: nothing to subtract
         for i, (st, bc) in enumerate(zip(out['blocks'], hp['blocks'])):
-            t0, ty = 8 * i, _TYPE[bc['type']]
+            t0, ty = 8 * i, (_TYPE_VN if vn else _TYPE)[bc['type']]
             types.append(ty)
+            if vn:
+                # frame / segment losses and smoothing on the action log-probabilities (is_logit=False forms, loss.py:249-277),
+                # the model's own token loss (blocks_SepVerbNoun.py:254-266)
+                ridx, rlen, ns = st['seg_label'], st['seg_lens'], st['nseg']
+                npred[i].copy_(ns)
+                ops.loss_pick(st['frame_logp'], C, label, ws[t0 + 0], ln, w=cweight, col_lse=zero_lse)
+                ops.loss_smooth(st['frame_logp'], C, ws[t0 + 1], ln, is_logp=True)
+                ops.token_loss(st['action_logp'], aind, sind, nm, transcript, cweight, ws[t0 + 2], logp_mean=True)
+                ops.loss_pick(st['seg_logp'], C, label, ws[t0 + 7], ln, w=cweight, ridx=ridx, rlen=rlen, col_lse=zero_lse)
+                if ty == 4:
+                    f2a, a2f = st['f2a_attn_logit'], st['a2f_attn_logit']
+                    lse = buf('loss_collse', (B, f2a.shape[2]))
+                    ops.col_lse(f2a, M, ns, lse)
+                    ops.loss_pick(f2a, M, gseg, ws[t0 + 3], ln, cols=aind, ncols=nm, col_lse=lse, tmap=inv, w=sweight, ridx=ridx, rlen=rlen)
+                    ops.loss_pick(a2f, M, gseg, ws[t0 + 4], ln, cols=aind, ncols=nm, tmap=inv, w=sweight, ridx=ridx, rlen=rlen)
+                continue
             fc = st['frame_clogit']
             ops.loss_pick(fc, C, label, ws[t0 + 0], ln, w=cweight)                               # frame_loss, loss.py:249-261
             ops.loss_smooth(fc, C, ws[t0 + 1], ln)

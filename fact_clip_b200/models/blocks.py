@@ -191,7 +191,9 @@ class _FactBase(nn.Module):
                              f'{[tuple(s.shape) for s in seqs]}')
         if self.cfg.FACT.trans:
             return self._forward_with_transcripts(seqs, label_list, forced_preds, compute_loss)
-        out = self.engine().run(seqs, forced_preds=forced_preds, keep=getattr(self, 'keep_attn', False))
+        # the verb/noun model's loss reads the action log-probabilities of EVERY block: keep them
+        keep = getattr(self, 'keep_attn', False) or (compute_loss and hasattr(self, 'vids'))
+        out = self.engine().run(seqs, forced_preds=forced_preds, keep=keep)
         self._last = out
         if compute_loss:
             res = LossRunner(self.engine(), self.mcriterion).run(out, label_list)

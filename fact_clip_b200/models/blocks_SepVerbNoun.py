@@ -5,7 +5,8 @@ Same constructor (``FACT(cfg, in_dim, n_classes1=98, n_classes2=301)``), paramet
 (so the random init under a seed and ``state_dict`` round trips match), same ``forward(seq_list, label_list)`` result.  The
 action table comes from ``./data/epic-kitchens/processed/{verb_mapping,noun_mapping,mapping}.txt`` like the reference
 (:147-170), or from the ``action_pairs`` argument (list of (verb id, noun id) per action id).  The forward runs on the GPU
-through libfactk.so (fact_clip_b200/engine.py); FACT.trans and compute_loss are not built for this model.
+through libfactk.so (fact_clip_b200/engine.py); ``compute_loss=True`` (eval mode) gives the reference's loss value with
+``net.mcriterion = MatchCriterion(cfg, n_actions, bg_ids)``; FACT.trans is not built for this model.
 """
 import torch
 import torch.nn as nn
@@ -97,11 +98,6 @@ class FACT(_FactBase):
         self.mcriterion = None
         self.compute_mode = 'bf16'
         self._engine = None
-
-    def _forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
-        if compute_loss:
-            raise NotImplementedError('compute_loss for the verb/noun model is not built (SURVEY.md 8f rank 1)')
-        return super()._forward(seq_list, label_list, False, forced_preds)
 
     def stash_video(self, b):
         """Per-block attributes of video ``b`` as the reference leaves them (:386-396, 470-481): frame_logp (T,1,A),

@@ -302,13 +302,14 @@ def label_prep(label, seg_start, nseg, cweight, C, transcript, sweight, len, cma
           len.data_ptr(), L.stream())
 
 
-def match_cost(attn, aclogit, transcript, seg_start, seg_len, nseg, pc, a2fc, overlap, cost, M, ridx=None):
+def match_cost(attn, aclogit, transcript, seg_start, seg_len, nseg, pc, a2fc, overlap, cost, M, ridx=None, logp=False):
     """attn [B, aslot, >=M] (frame rows, or predicted-segment rows with ridx), aclogit [B, M, C+1] -> cost [B, M, smax]."""
     B, slot = seg_start.shape
     COUNTERS['launches'] += 2
     _call('factk_match_cost', None, attn.data_ptr(), _row_ld(attn), attn.shape[1], L.ptr(ridx), aclogit.data_ptr(), M,
           aclogit.shape[2], transcript.data_ptr(), seg_start.data_ptr(), seg_len.data_ptr(), nseg.data_ptr(),
-          transcript.shape[1], float(pc), float(a2fc), overlap.data_ptr(), _row_ld(overlap), cost.data_ptr(), B, slot, L.stream())
+          transcript.shape[1], float(pc), float(a2fc), overlap.data_ptr(), _row_ld(overlap), cost.data_ptr(), B, slot, int(logp),
+          L.stream())
 
 
 def loss_pick(X, ncol, tgt0, part, len, cols=None, ncols=None, ridx=None, rlen=None, col_lse=None, tmap=None, w=None,
@@ -322,11 +323,11 @@ def loss_pick(X, ncol, tgt0, part, len, cols=None, ncols=None, ridx=None, rlen=N
           L.ptr(w), bs(w), part.data_ptr(), L.ptr(part_cnt), B, slot, len.data_ptr(), part.shape[-1], L.stream())
 
 
-def loss_smooth(X, ncol, part, len):
+def loss_smooth(X, ncol, part, len, is_logp=False):
     B, slot = X.shape[0], X.shape[1]
     COUNTERS['launches'] += 1
     _call('factk_loss_smooth', None, X.data_ptr(), _row_ld(X), ncol, part.data_ptr(), B, slot, len.data_ptr(), part.shape[-1],
-          L.stream())
+          int(is_logp), L.stream())
 
 
 def col_lse(X, ncol, nrows, out, rmask0=None, rmap=None):
@@ -336,12 +337,12 @@ def col_lse(X, ncol, nrows, out, rmask0=None, rmap=None):
           0 if rmap is None or rmap.dim() == 1 else rmap.stride(0), out.data_ptr(), out.stride(0), B, L.stream())
 
 
-def token_loss(aclogit, aind, sind, nmatch, transcript, cweight, out):
+def token_loss(aclogit, aind, sind, nmatch, transcript, cweight, out, logp_mean=False):
     """out: [B, nchunk] slice of the workspace; the value lands in out[:, 0]."""
     B, M, C1 = aclogit.shape
     COUNTERS['launches'] += 1
     _call('factk_token_loss', None, aclogit.data_ptr(), M, C1, aind.data_ptr(), sind.data_ptr(), nmatch.data_ptr(), aind.shape[1],
-          transcript.data_ptr(), transcript.shape[1], cweight.data_ptr(), out.data_ptr(), out.stride(0), B, L.stream())
+          transcript.data_ptr(), transcript.shape[1], cweight.data_ptr(), out.data_ptr(), out.stride(0), B, int(logp_mean), L.stream())
 
 
 def loss_combine(ws, block_types, len, npred, C, M, sw, out, use_clip=False, fact_w=1.0, con_w=0.0, nseen=0, nvalid=None):

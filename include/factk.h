@@ -275,10 +275,10 @@ int factk_label_prep(const int32_t* label, const int32_t* seg_start, const int32
 
 /* Matching cost (MatchCriterion.match / a2f_soft_iou, loss.py:91-136): cost[b][a][s] = -pc * softmax(aclogit)[a,
  * transcript[s]] - a2fc * IoU(a, s); attn rows are frames, or predicted segments reached through ridx[b][t].
- * overlap: scratch [B][smax][ldo]. */
+ * overlap: scratch [B][smax][ldo].  logp != 0: aclogit rows are log-probabilities used as exp(.) (verb/noun model). */
 int factk_match_cost(const float* attn, int lda, int aslot, const int32_t* ridx, const float* aclogit, int M, int C1,
                      const int32_t* transcript, const int32_t* seg_start, const int32_t* seg_len, const int32_t* nseg,
-                     int smax, float pc, float a2fc, float* overlap, int ldo, float* cost, int B, int slot, void* stream);
+                     int smax, float pc, float a2fc, float* overlap, int ldo, float* cost, int B, int slot, int logp, void* stream);
 
 /* part_sum[b][chunk] = sum over the chunk's frames t of  -(X[b][r][c] - lse) * w[b*w_bstride + k] / rlen[b][r]  with
  * k = tmap ? tmap[b*tmap_bstride + tgt0[b][t]] : tgt0[b][t] (frames with k < 0 are skipped), c = cols ? cols[b*cols_bstride
@@ -289,22 +289,24 @@ int factk_loss_pick(const float* X, int ldx, int xslot, int ncol, const int32_t*
                     const int32_t* tgt0, const int32_t* tmap, int tmap_bstride, const float* w, int w_bstride,
                     float* part_sum, float* part_cnt, int B, int slot, const int32_t* len, int nchunk, void* stream);
 
-/* smooth_loss numerator (loss.py:8-19): sum over t < len-1 and c of min((logp[t+1][c] - logp[t][c])^2, 16). */
+/* smooth_loss numerator (loss.py:8-19): sum over t < len-1 and c of min((logp[t+1][c] - logp[t][c])^2, 16); is_logp != 0:
+ * X already holds log-probabilities (is_logit=False). */
 int factk_loss_smooth(const float* X, int ldx, int ncol, float* part, int B, int slot, const int32_t* len, int nchunk,
-                      void* stream);
+                      int is_logp, void* stream);
 
 /* out[b][c] = log-sum-exp over rows r < nrows[b] of X[b][r][c]; rows whose (mapped) rmask0 entry is negative are skipped. */
 int factk_col_lse(const float* X, int ldx, int xslot, int ncol, const int32_t* nrows, const int32_t* rmask0,
                   const int32_t* rmap, int rmap_bstride, float* out, int ldo, int B, void* stream);
 
 /* action_token_loss (loss.py:196-209): out[b*out_stride] = class-weighted cross entropy of the tokens, unmatched tokens
- * labelled with the null class C1-1. */
+ * labelled with the null class C1-1.  logp_mean != 0: the verb/noun model's form (blocks_SepVerbNoun.py:254-266): rows
+ * are log-probabilities, mean over the tokens of weight * (-logp[label]). */
 int factk_token_loss(const float* aclogit, int M, int C1, const int32_t* aind, const int32_t* sind, const int32_t* nmatch,
                      int kmax, const int32_t* transcript, int smax, const float* cweight, float* out, int out_stride,
-                     int B, void* stream);
+                     int B, int logp_mean, void* stream);
 
 /* Per-block formulas, block mean and the FACT / InfoNCE mix.  block_type: HOST array [nb] (0 input, 1 update, 2 update
- * with temporal down/up-sampling); npred: [nb][B] predicted segment counts (type 2 blocks).  out[b] = {loss, fact_loss,
+ * with temporal down/up-sampling, 3 / 4 verb/noun input / update block); npred: [nb][B] predicted segment counts (types >= 2).  out[b] = {loss, fact_loss,
  * contrastive_loss, has_contrastive, block losses...}. */
 int factk_loss_combine(const float* ws, int nb, const int32_t* block_type, int B, int nchunk, const int32_t* len,
                        const int32_t* npred, int C, int M, float sw, int use_clip, float fact_w, float con_w, int nseen,

@@ -90,3 +90,31 @@ def test_vn_pipelined_submit_matches_forward():
         got = h.result()
         for a, b in zip(got, ref):
             assert np.array_equal(a['pred'], b['pred'])
+
+
+@pytest.mark.parametrize('name', VN_CASES)
+def test_vn_loss_values_match_reference(name):
+    """compute_loss=True of the verb/noun model (halved frame / segment / token terms on action log-probabilities, the
+    model's own token loss, matching on exp(action_logp)) against the reference's numbers, fp32 mode."""
+    import math
+    from fact_clip_b200.models.loss import MatchCriterion
+    g = torch.load(os.path.join(GOLDEN, name + '.pt'), weights_only=False)
+    n1, n2 = g['n_classes']
+    cfg = C.tiny(**g['tiny_kwargs'])
+    cfg.merge(dict(Loss=g['loss']))
+    net = FACT(cfg, g['in_dim'], n1, n2, action_pairs=list(zip(g['vids'], g['nids'])))
+    net.load_state_dict(g['state_dict'], strict=False)
+    net.compute_mode = 'fp32'
+    net = net.to(DEV).eval()
+    net.mcriterion = MatchCriterion(cfg, len(g['vids']), g['bg_ids'])
+    loss, saves = net([v['x'].to(DEV) for v in g['videos']], [v['label'].to(DEV) for v in g['videos']], compute_loss=True)
+    close = lambda a, b: (math.isnan(b) and math.isnan(a)) or abs(a - b) <= 1e-4 * max(1.0, abs(b))
+    for b, (sv, v) in enumerate(zip(saves, g['videos'])):
+        ref = v['loss']
+        assert [list(m) for m in net.last_match[b]] == ref['match'], b
+        for a, r in zip(sv['block_losses'], ref['block_losses']):
+            assert close(a, r), (b, sv['block_losses'], ref['block_losses'])
+        assert close(sv['loss']['loss'], ref['loss'])
+        assert np.array_equal(sv['pred'], v['pred'].numpy())
+    refs = [v['loss']['loss'] for v in g['videos']]
+    assert close(float(loss), sum(refs) / len(refs))
