@@ -590,7 +590,13 @@ class FactEngine:
             n_pe = 1000 if N <= 1000 else N + 10        # basic.py:125-127: the table regrows past max_len
             pe = self.derived(('tok_pe', A, n_pe), lambda: _pos_table(A, n_pe, self.dev))
             self.action_init = self.buf('tok_init', (1, N, A))
-            ops.embed_tokens(self.p('action_embed.weight'), self.transcript, pe, self.action_init)
+            if self.vn is None:
+                ops.embed_tokens(self.p('action_embed.weight'), self.transcript, pe, self.action_init)
+            else:       # verb/noun model (blocks_SepVerbNoun.py:74-83): halves from the verb and the noun of every action
+                vids, nids = self.vn_table()
+                tr, h = self.transcript.long(), A // 2
+                ops.embed_tokens(self.p('verb_embed.weight'), vids[tr].contiguous(), pe, self.action_init[:, :, :h])
+                ops.embed_tokens(self.p('noun_embed.weight'), nids[tr].contiguous(), pe[:, h:], self.action_init[:, :, h:])
         lengths = [int(s.shape[0]) for s in seqs]
         B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
         x = self.buf('input', (B, slot, D), self._feature_dtype(seqs))
@@ -674,8 +680,16 @@ class FactEngine:
         last = out['blocks'][-1]
         assert 'a2f_attn_seg' in last, 'the verb/noun model ends in an update block (its eval reads a2f_attn)'
         pred64 = pred_out if pred_out is not None else self.buf('pred64', (B, slot), torch.int64)
-        ops.fuse_eval(last['action_logp'], last['a2f_attn_seg'], last['frame_logp'], self.hp['mwt'], pred64, M, A,
-                      seg_label=last['seg_label'], len=ln, f_logp=True)
+        if self.hp['trans']:
+            # _eval_w_transcript (blocks_SepVerbNoun.py:331-336): the transcript entry whose token attends the frame most --
+            # the transcript fusion kernel with a zero frame weight (softmax keeps the arg max of the attention)
+            ntr = self.buf('ntr', (B,), torch.int32)
+            ntr.fill_(self.ntok)
+            ops.fuse_eval_transcript(last['a2f_attn_seg'], last['frame_logp'], 0.0, self.transcript[None], ntr, pred64, A,
+                                     seg_label=last['seg_label'], len=ln)
+        else:
+            ops.fuse_eval(last['action_logp'], last['a2f_attn_seg'], last['frame_logp'], self.hp['mwt'], pred64, M, A,
+                          seg_label=last['seg_label'], len=ln, f_logp=True)
         out['pred'] = pred64
         return out
 

@@ -222,7 +222,8 @@ class _FactBase(nn.Module):
         the videos run one per call like the reference; the transcript is the run-length coding of the label sequence
         (basic.py:38-54, vectorised: one unique_consecutive instead of a Python loop over the frames)."""
         assert label_list is not None and len(label_list) == len(seqs), 'FACT.trans needs the frame labels of every video'
-        saves, keep, dev = [], getattr(self, 'keep_attn', False), next(self.parameters()).device
+        saves, dev = [], next(self.parameters()).device
+        keep = getattr(self, 'keep_attn', False) or (compute_loss and hasattr(self, 'vids'))
         self._per_video = []
         total, matches = None, []
         for i, (seq, label) in enumerate(zip(seqs, label_list)):
@@ -239,7 +240,7 @@ class _FactBase(nn.Module):
                 saves[-1]['block_losses'] = vals[0, 4:4 + nb].tolist()
                 matches.append(res['matches'][0])
                 total = res['values'][0, 0].clone() if total is None else total + res['values'][0, 0]
-            if keep:        # the engine's buffers are reused by the next video: keep copies for stash_video(i)
+            if getattr(self, 'keep_attn', False):        # the engine's buffers are reused by the next video: keep copies for stash_video(i)
                 self._per_video.append(_clone_tree(out))
         self._last = out
         self.stash_video(len(seqs) - 1)

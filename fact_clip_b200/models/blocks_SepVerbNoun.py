@@ -6,7 +6,8 @@ Same constructor (``FACT(cfg, in_dim, n_classes1=98, n_classes2=301)``), paramet
 action table comes from ``./data/epic-kitchens/processed/{verb_mapping,noun_mapping,mapping}.txt`` like the reference
 (:147-170), or from the ``action_pairs`` argument (list of (verb id, noun id) per action id).  The forward runs on the GPU
 through libfactk.so (fact_clip_b200/engine.py); ``compute_loss=True`` (eval mode) gives the reference's loss value with
-``net.mcriterion = MatchCriterion(cfg, n_actions, bg_ids)``; FACT.trans is not built for this model.
+``net.mcriterion = MatchCriterion(cfg, n_actions, bg_ids)``; FACT.trans models take their tokens from the verb / noun
+embeddings of the transcript (:74-85) and run one video per call.
 """
 import torch
 import torch.nn as nn
@@ -75,15 +76,18 @@ class FACT(_FactBase):
         self.vids, self.nids = [v for v, _ in pairs], [n for _, n in pairs]
         assert max(self.vids) + 1 == n_classes1 and max(self.nids) + 1 == n_classes2, \
             'the action table must use every verb / noun id range (blocks_SepVerbNoun.py:203-208)'
-        if cfg.FACT.trans:
-            raise NotImplementedError('FACT.trans for the verb/noun model (verb_embed / noun_embed tokens) is not built')
         self.cfg, self.in_dim = cfg, in_dim
         self.num_classes1, self.num_classes2 = n_classes1, n_classes2
         self.num_classes = (n_classes1, n_classes2)
         base = cfg.Bi
         self.frame_pe = basic.PositionalEncoding(base.hid_dim, max_len=10000, empty=(not cfg.FACT.fpos))
         self.channel_masking_dropout = nn.Dropout2d(p=cfg.FACT.cmr)
-        self.action_query = nn.Parameter(torch.randn([cfg.FACT.ntoken, 1, base.a_dim]))
+        if not cfg.FACT.trans:
+            self.action_query = nn.Parameter(torch.randn([cfg.FACT.ntoken, 1, base.a_dim]))
+        else:       # transcript tokens: halves from the verb and the noun of every action (:34-37)
+            self.action_pe = basic.PositionalEncoding(base.a_dim, max_len=1000)
+            self.verb_embed = nn.Embedding(n_classes1, base.a_dim // 2)
+            self.noun_embed = nn.Embedding(n_classes2, base.a_dim // 2)
         blocks = []
         for t in cfg.FACT.block:
             if t == 'I':
@@ -103,7 +107,12 @@ class FACT(_FactBase):
         """Per-block attributes of video ``b`` as the reference leaves them (:386-396, 470-481): frame_logp (T,1,A),
         seg_logp (S,1,A), action_logp (M,1,A+1), tdu, and the attention maps of the update blocks."""
         out = self._last
-        T, M = out['lengths'][b], self.cfg.FACT.ntoken
+        if self.cfg.FACT.trans:           # one engine call per video (see _forward_with_transcripts)
+            if getattr(self, '_per_video', None):
+                out, b = self._per_video[b], 0
+            else:
+                b = 0
+        T, M = out['lengths'][b], int(out['blocks'][0]['action_clogit'].shape[1])
         for blk, st in zip(self.block_list, out['blocks']):
             S = int(st['nseg'][b])
             lab = st['seg_label'][b, :T].long()

@@ -94,16 +94,26 @@ def evaluate(action_logp, a2f_attn, frame_logp, weight):
     return ((1 - weight) * qprob[tok] + weight * fprob).argmax(1)
 
 
-def forward_video(sd, hp, seq, vids, nids, forced_preds=None):
-    """FACT._forward_one_video + eval (:58-93, 126, 337-341), query-token models (FACT.trans False), eval mode.
-    hp: fact_oracle.hparams_from_cfg(...) with n_classes = (n1, n2); block string of 'I' / 'U'."""
+def forward_video(sd, hp, seq, vids, nids, forced_preds=None, transcript=None):
+    """FACT._forward_one_video + eval (:58-93, 126, 337-341), eval mode.  hp: fact_oracle.hparams_from_cfg(...) with
+    n_classes = (n1, n2); block string of 'I' / 'U'.  FACT.trans (:74-85): the tokens are cat[verb_embed(verb of the action),
+    noun_embed(noun of the action)] + positional encoding, the query position is zero, and the prediction is the transcript
+    entry whose token attends the frame most (_eval_w_transcript :331-336)."""
     n1, n2 = hp['n_classes']
     H = hp['blocks'][0]['hid_dim']
     T = seq.shape[0]
     frame_pos = O.positional_table(H, max(T, 1)) if hp['fpos'] else None
-    action_pos = sd['action_query'][:, 0]
-    frame, action = seq, torch.zeros_like(action_pos)
     vids, nids = torch.as_tensor(vids), torch.as_tensor(nids)
+    if hp['trans']:
+        assert transcript is not None
+        A = 2 * sd['verb_embed.weight'].shape[1]
+        action = torch.cat([sd['verb_embed.weight'][vids[transcript]], sd['noun_embed.weight'][nids[transcript]]], -1) \
+            + O.positional_table(A, len(transcript))
+        action_pos = torch.zeros_like(action)
+    else:
+        action_pos = sd['action_query'][:, 0]
+        action = torch.zeros_like(action_pos)
+    frame = seq
     out = {'blocks': []}
     for i, bc in enumerate(hp['blocks']):
         st, p = {}, f'block_list.{i}.'
@@ -118,7 +128,10 @@ def forward_video(sd, hp, seq, vids, nids, forced_preds=None):
         st['action_logp'] = combine(st['action_clogit'], n1, vids, nids, action=True)
         out['blocks'].append(st)
     last = out['blocks'][-1]
-    out['pred'] = evaluate(last['action_logp'], last['a2f_attn'], last['frame_logp'], hp['mwt'])
+    if hp['trans']:
+        out['pred'] = transcript[last['a2f_attn'][:, :len(transcript)].argmax(1)]
+    else:
+        out['pred'] = evaluate(last['action_logp'], last['a2f_attn'], last['frame_logp'], hp['mwt'])
     return out
 
 

@@ -29,10 +29,12 @@ CASES = [
     # name, tiny() kwargs, T list, in_dim
     ('vn_m2_IUU', dict(f='m2', block='IUU'), [88, 35, 1], 24),
     ('vn_m_IU_fpos', dict(f='m', block='IU', fpos=True, M=10), [60], 16),
+    ('vn_m_IUU_trans', dict(f='m', block='IUU', trans=True), [70, 31, 2], 24),      # tokens = verb / noun embeddings of the transcript
 ]
 # loss settings per case (Loss section, background action ids): one-to-one and one-to-many matching
 LOSS = {'vn_m2_IUU': (dict(pc=0.5, a2fc=1.0, match='o2o', bgw=0.5, nullw=0.1, sw=2.0), [0]),
-        'vn_m_IU_fpos': (dict(pc=1.0, a2fc=1.0, match='o2m', bgw=1.0, nullw=0.05, sw=5.0), [])}
+        'vn_m_IU_fpos': (dict(pc=1.0, a2fc=1.0, match='o2m', bgw=1.0, nullw=0.05, sw=5.0), []),
+        'vn_m_IUU_trans': (dict(pc=1.0, a2fc=1.0, match='seq', bgw=1.0, nullw=0.1, sw=1.0), [])}
 
 
 def write_tables(d):
@@ -74,6 +76,7 @@ def main():
                 save = net([x], [y])
                 loss, lsave = net([x], [y], compute_loss=True)
                 crit = net.mcriterion
+                crit.set_label(y)
                 match = crit.match(torch.exp(net.block_list[-1].action_logp), net.block_list[-1].a2f_attn)
             loss_rec = dict(loss=float(loss), block_losses=[float(v) for v in net.loss_list], match=[m.tolist() for m in match])
             blocks = []

@@ -132,6 +132,11 @@ def test_verb_noun_model_matches_reference_state_dict():
     assert torch.equal(again.state_dict()[k], g['state_dict'][k])
     with pytest.raises(AssertionError):
         VNFACT(C.tiny(**g['tiny_kwargs']), g['in_dim'], n1 + 1, n2, action_pairs=list(zip(g['vids'], g['nids'])))
+    # transcript variant: verb / noun embeddings instead of the action queries, the fixture's keys
+    gt = torch.load(os.path.join(ROOT, 'tests', 'golden', 'vn_m_IUU_trans.pt'), weights_only=False)
+    nt = VNFACT(C.tiny(**gt['tiny_kwargs']), gt['in_dim'], n1, n2, action_pairs=list(zip(gt['vids'], gt['nids'])))
+    assert {k for k in nt.state_dict() if not k.endswith('.pe')} == set(gt['state_dict'])
+    assert tuple(nt.verb_embed.weight.shape) == (n1, 16) and tuple(nt.noun_embed.weight.shape) == (n2, 16)
 
 
 def test_input_validation_messages():

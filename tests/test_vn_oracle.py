@@ -27,7 +27,8 @@ def test_vn_oracle_matches_reference(name):
     hp = O.hparams_from_cfg(C.tiny(**g['tiny_kwargs']), g['in_dim'], g['n_classes'])
     for v in g['videos']:
         with torch.no_grad():
-            out = VO.forward_video(g['state_dict'], hp, v['x'], g['vids'], g['nids'])
+            out = VO.forward_video(g['state_dict'], hp, v['x'], g['vids'], g['nids'],
+                                   transcript=O.transcript_of(v['label']) if hp['trans'] else None)
         for st, ref in zip(out['blocks'], v['blocks']):
             assert torch.equal(st['seg_label'], ref['seg_label']) and torch.equal(st['seg_lens'], ref['seg_lens'])
             for k in ('frame_logp', 'seg_logp', 'action_logp'):
@@ -50,7 +51,8 @@ def test_vn_loss_oracle_matches_reference(name):
     lp = LO.loss_params(cfg, bg_ids=g['bg_ids'])
     for v in g['videos']:
         with torch.no_grad():
-            out = VO.forward_video(g['state_dict'], hp, v['x'], g['vids'], g['nids'])
+            out = VO.forward_video(g['state_dict'], hp, v['x'], g['vids'], g['nids'],
+                                   transcript=O.transcript_of(v['label']) if hp['trans'] else None)
             res = VO.loss_video(out, hp, v['label'], lp, g['vids'])
         ref = v['loss']
         assert [m.tolist() for m in res['match']] == ref['match']
