@@ -281,6 +281,10 @@ def main():
                      'traffic': TCN_DRAM_BYTES_PER_LAUNCH.get(B), 'traffic_source': 'profiles/r1_tcn_layer_ncu_full.txt (dram read + write per launch, ncu --set full)',
                      'peak_source': pk['src'] + ' (sustained bf16, kernel timed inside a long step)',
                      'ms_per_layer': t_layer_ms, 'share_of_step': tcn_ms / args.steps / (ms_eager / args.steps),
+                     # both one-sided fractions of the same launch (algorithmic bytes: x in + y out, bf16)
+                     'one_sided': {'tensor': ach_tf / pk['tf_sust'],
+                                   'hbm': (4.0 * F * B * T / (t_layer_ms * 1e-3) / 1e9 / pk['hbm']) if t_layer_ms > 0 else 0.0,
+                                   'hbm_peak_gbs': pk['hbm']},
                      'timed_in': 'eager pass of the same steps (CUDA events around each launch); the headline loop replays one CUDA graph per step',
                      # 34.6 MFLOP of algorithmic work per frame at this config (segment-count dependent terms
                      # excluded) -> the whole forward against the same tensor peak, per GPU
