@@ -280,7 +280,15 @@ gru_mma_kernel(const float* __restrict__ gi, const float* __restrict__ whh_f, co
             }
             fetch_gi(c);                        // step t + GM_GDEPTH - 1 of this chain
 #endif
-            const uint32_t word = gm_pack(hn.x, hn.y);
+            // The data word doubles as the arrival flag, so it must never equal GM_EMPTY.  cvt.rn.bf16x2 canonicalises NaN to
+            // 0x7FFF and finite values never produce 0xFFFF; the select below makes that explicit (two NaN inputs with any
+            // payload still exchange as canonical NaNs instead of looking "not written yet" and spinning into the trap).
+            // Ordering assumption of the protocol (documented, not enforced by fences): a reader re-marks a word EMPTY with a
+            // plain st.shared only AFTER it has consumed the peer's value, and the peer overwrites the same word two steps
+            // later, after it has itself consumed a value this CTA produced after the re-mark (causality through the
+            // exchanged data); sm_100 executes same-address shared-memory stores of one SM in arrival order.
+            uint32_t word = gm_pack(hn.x, hn.y);
+            word = (word == GM_EMPTY) ? 0x7FFF7FFFu : word;
             const uint32_t w0 = __shfl_sync(0xffffffffu, word, lane & 7), w1 = __shfl_sync(0xffffffffu, word, (lane & 7) + 8),
                            w2 = __shfl_sync(0xffffffffu, word, (lane & 7) + 16), w3 = __shfl_sync(0xffffffffu, word, (lane & 7) + 24);
             const uint32_t nxt = (uint32_t)(c * 2 + (cur ^ 1));

@@ -30,13 +30,16 @@ class FactEngine:
         assert mode in ('bf16', 'fp32')
         self.m, self.hp, self.clip, self.mode = module, hp, clip, mode
         self.act = torch.bfloat16 if mode == 'bf16' else torch.float32
-        self._bufs, self._zbufs, self._len_sig = {}, {}, None
+        # activation buffers live in one ARENA per batch shape (B, slot); the arenas form an LRU (max_arenas) and an evicted
+        # arena takes the CUDA graphs captured over its pointers with it, so a sweep over videos of many different lengths
+        # holds a bounded amount of HBM (~25 KB per frame slot of the newest shapes) instead of one arena per shape ever seen
+        self._arenas, self._arena, self.max_arenas = {}, None, 4
+        self._set_arena(('init',))
         self.use_tc = True
         self.use_fused_tcn = True
         self.use_pair_gemm = True
-        self._submits, self._copy_stream, self._slot_free = 0, None, [None, None]
+        self._submits, self._copy_stream, self._slot_free, self._slot_pending = 0, None, [None, None], [None, None]
         self._wcache, self._wsig = {}, None
-        self._graphs = {}
         # FACTK_FLAT_TOKENS=1 tiles the token rows of all videos as ONE dense matrix (38 instead of 64 tiles at 64 x 75 tokens).
         # Measured: 1.46 instead of 1.41 ms per step for the 73 token GEMMs -- fewer, fuller tiles stream more per CTA and the
         # launches are one wave either way -- so it stays off.
@@ -49,6 +52,30 @@ class FactEngine:
         self.last_launches = 0
 
     # ------------------------------------------------------------------ memory / weights
+    def _set_arena(self, ctx):
+        """Make the arena of batch shape ``ctx`` current (most recently used); evict the least recently used beyond
+        ``max_arenas`` together with every graph captured over it."""
+        a = self._arenas.pop(ctx, None)
+        if a is None:
+            a = dict(bufs={}, zbufs={}, len_sig=None, graphs={}, warmed=False)
+        self._arenas[ctx] = a                       # dicts keep insertion order: last = most recent
+        while len(self._arenas) > self.max_arenas:
+            self._arenas.pop(next(iter(self._arenas)))
+        self._arena = a
+        self._bufs, self._zbufs = a['bufs'], a['zbufs']
+
+    @property
+    def _len_sig(self):
+        return self._arena['len_sig']
+
+    @_len_sig.setter
+    def _len_sig(self, v):
+        self._arena['len_sig'] = v
+
+    @property
+    def _graphs(self):
+        return self._arena['graphs']
+
     def buf(self, name, shape, dtype=torch.float32):
         key = (name, tuple(shape), dtype)
         t = self._bufs.get(key)
@@ -148,11 +175,13 @@ class FactEngine:
         sig = tuple((k, v.data_ptr(), v._version) for k, v in params.items())
         if sig != self._wsig:
             self._wsig, self._wcache, self._p = sig, {}, params
-            self._graphs = {}                     # captured graphs hold pointers of derived weights
+            for a in self._arenas.values():       # captured graphs hold pointers of derived weights
+                a['graphs'] = {}
         dev = next(self.m.parameters()).device
         if getattr(self, 'dev', dev) != dev:      # the module moved to another GPU: every cached buffer lives on the old one
-            self._bufs, self._zbufs, self._len_sig, self._graphs = {}, {}, None, {}
-            self._copy_stream, self._slot_free = None, [None, None]
+            self._arenas = {}
+            self._set_arena(('init',))
+            self._copy_stream, self._slot_free, self._slot_pending = None, [None, None], [None, None]
         self.dev = dev
 
     def p(self, name):
@@ -617,8 +646,13 @@ class FactEngine:
         transcript (FACT.trans models, one video per call): int32 CUDA tensor [N] of the video's action sequence."""
         self._refresh_weights()
         self.ntok, self.action_init, self.transcript = self.hp['ntoken'], None, None
+        lengths = [int(s.shape[0]) for s in seqs]
+        B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
         if self.hp['trans']:
             assert transcript is not None and len(seqs) == 1, 'FACT.trans: one video per call, with its transcript'
+            self.ntok = int(transcript.numel())
+        self._set_arena((B, slot, self.ntok))
+        if self.hp['trans']:
             N, A = int(transcript.numel()), self.hp['blocks'][0]['a_dim']
             self.ntok, self.transcript = N, transcript.to(torch.int32).contiguous()
             n_pe = 1000 if N <= 1000 else N + 10        # basic.py:125-127: the table regrows past max_len
@@ -631,8 +665,6 @@ class FactEngine:
                 tr, h = self.transcript.long(), A // 2
                 ops.embed_tokens(self.p('verb_embed.weight'), vids[tr].contiguous(), pe, self.action_init[:, :, :h])
                 ops.embed_tokens(self.p('noun_embed.weight'), nids[tr].contiguous(), pe[:, h:], self.action_init[:, :, h:])
-        lengths = [int(s.shape[0]) for s in seqs]
-        B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
         x = self.buf('input', (B, slot, D), self._feature_dtype(seqs))
         for b, s in enumerate(seqs):
             x[b, :lengths[b]].copy_(s, non_blocking=True)
@@ -645,6 +677,8 @@ class FactEngine:
         """Pipelined forward: the host->device copy of this batch runs on a side stream into one of two input
         buffers and overlaps the kernels of the previously submitted batch; the predictions are copied to pinned
         host memory asynchronously.  Returns a handle; ``handle.result()`` blocks until this batch is done.
+        At most TWO batches are in flight: submitting a third waits for the oldest one and keeps its predictions (the
+        two device / pinned-host slots alternate), so a handle's ``result()`` is valid whenever it is called.
         channel_major: ``seqs[i]`` is the (D, T_i) fp32 array as stored on disk (what the reference transposes on the host,
         utils/dataset.py:12-21); it is copied as it is and transposed on the device, on the copy stream."""
         self._refresh_weights()
@@ -655,6 +689,10 @@ class FactEngine:
         B, slot, D = len(seqs), _round_up(max(lengths), 128), self.hp['in_dim']
         k = self._submits % 2
         self._submits += 1
+        old = self._slot_pending[k]
+        if old is not None:                 # the batch that last used this slot: take its predictions out of the pinned buffer
+            old.detach_result()
+        self._set_arena((B, slot, self.ntok))
         main = torch.cuda.current_stream()
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.dev)
@@ -671,7 +709,7 @@ class FactEngine:
         if key not in self._bufs:
             self._bufs[key] = torch.empty(B, slot, dtype=torch.int64, pin_memory=True)
         host = self._bufs[key]
-        free = self._slot_free[k]
+        free = self._slot_free[k]           # (an event of ANY arena: input buffers of different shapes do not alias, waiting is harmless)
         with torch.cuda.stream(self._copy_stream):
             if free is not None:
                 self._copy_stream.wait_event(free)          # the previous user of this input buffer has finished
@@ -691,7 +729,8 @@ class FactEngine:
         done = torch.cuda.Event()
         done.record(main)
         self._slot_free[k] = done
-        return _Pending(done, host, lengths, out)
+        h = self._slot_pending[k] = _Pending(done, host, lengths, out)
+        return h
 
     def _vn_eval(self, out, pred_out):
         """Verb/noun model: action log-probabilities (combine_verb_noun_to_action, blocks_SepVerbNoun.py:188-226) of the last
@@ -735,33 +774,46 @@ class FactEngine:
         if not self.use_graph or ops.TIMER is not None:
             return self.run_packed(x, ln, lengths, pred_out=pred_out)
         self._refresh_weights()
-        key = (x.data_ptr(), tuple(x.shape), ln.data_ptr(), tuple(lengths), None if pred_out is None else pred_out.data_ptr())
+        self._set_arena((x.shape[0], x.shape[1], self.ntok))
+        # the captured launches depend on B, slot and the buffer pointers only: the lengths reach the kernels through the
+        # device tensor ``ln``, so batches of the same shape with other lengths replay the same graph
+        key = (x.data_ptr(), tuple(x.shape), x.dtype, ln.data_ptr(), None if pred_out is None else pred_out.data_ptr())
         ent = self._graphs.get(key)
         if ent is None:
-            out = self.run_packed(x, ln, lengths, pred_out=pred_out)      # eager: allocates buffers, fills the weight caches
+            if not self._arena['warmed']:       # eager once per arena: allocates its buffers, fills the weight caches
+                self.run_packed(x, ln, lengths, pred_out=pred_out)
+                self._arena['warmed'] = True
+            elif self._len_sig != tuple(lengths):
+                for t in self._zbufs.values():
+                    t.zero_()
+                self._len_sig = tuple(lengths)
             n0 = ops.COUNTERS['launches']
+            nb = len(self._bufs)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self.run_packed(x, ln, lengths, pred_out=pred_out)
+            assert len(self._bufs) == nb, 'a buffer was allocated during graph capture (it would live in the graph pool)'
             if len(self._graphs) >= 8:
                 self._graphs.pop(next(iter(self._graphs)))
             ent = self._graphs[key] = (g, out, ops.COUNTERS['launches'] - n0)
             self.last_launches = ent[2]
             g.replay()          # the capture itself did not execute
             return out
-        if self._len_sig != tuple(lengths):      # another batch shape ran in between: restore the zero tails the taps rely on
+        if self._len_sig != tuple(lengths):      # other lengths than the last run of this arena: restore the zero tails the taps rely on
             for t in self._zbufs.values():
                 t.zero_()
             self._len_sig = tuple(lengths)
         ent[0].replay()
         ops.COUNTERS['launches'] += ent[2]
         self.last_launches = ent[2]
+        ent[1]['lengths'] = lengths
         return ent[1]
 
     @torch.no_grad()
     def run_packed(self, x, ln, lengths, forced_preds=None, keep=False, pred_out=None):
         self._refresh_weights()
         hp = self.hp
+        self._set_arena((x.shape[0], x.shape[1], self.ntok))
         self.B, self.slot, self.len, self.keep = x.shape[0], x.shape[1], ln, keep
         if self._len_sig != tuple(lengths):
             for t in self._zbufs.values():
@@ -845,10 +897,19 @@ class _Pending:
     def __init__(self, done, host_pred, lengths, out):
         self.done, self.host_pred, self.lengths, self.out = done, host_pred, lengths, out
 
+        self._res = None
+
+    def detach_result(self):
+        """Copy the predictions out of the shared pinned buffer (called before the buffer's slot is reused)."""
+        if self._res is None:
+            self.done.synchronize()
+            p = self.host_pred.numpy()
+            self._res = [{'pred': p[b, :T].copy()} for b, T in enumerate(self.lengths)]
+            self.host_pred = None
+        return self._res
+
     def result(self):
-        self.done.synchronize()
-        p = self.host_pred.numpy()
-        return [{'pred': p[b, :T].copy()} for b, T in enumerate(self.lengths)]
+        return self.detach_result()
 
 
 def _pos_table(d_model, length, device):

@@ -22,6 +22,10 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import torch
 
+# read-only memory maps make torch.from_numpy warn; the stager only reads them.  Installed ONCE at import: the filter list
+# is process-global and warnings.catch_warnings() is not thread-safe inside the pool threads.
+warnings.filterwarnings('ignore', message='The given NumPy array is not writ', category=UserWarning)
+
 
 def load_feature(feature_dir, video, transpose):
     """The reference's ``load_feature`` semantics (utils/dataset.py:12-21) as one array: (T, D) float32."""
@@ -101,9 +105,7 @@ class FeatureStager:
         if self.dtype == torch.float32:
             np.copyto(dst.numpy(), src, casting='unsafe')          # transpose + cast in one pass over the mapped file
         else:
-            with warnings.catch_warnings():
-                warnings.simplefilter('ignore')                    # read-only mapping -> from_numpy warns; we only read
-                dst.copy_(torch.from_numpy(np.asarray(src)))       # strided, converting copy (round-to-nearest-even)
+            dst.copy_(torch.from_numpy(np.asarray(src)))           # strided, converting copy (round-to-nearest-even)
 
     def _stage(self, names, slot):
         arena, seqs, row = self._arena(slot), [], 0

@@ -41,6 +41,14 @@ CASES = [
     ('tiny_m_iuU_trans_gru', dict(f='m', block='iuU', trans=True, A=64, a_i='gru', a_u='gru_om'), False, [85, 33, 1], 6, 24),
 ]
 
+# Fixtures whose weights come from a short run of the reference's OWN training loop (Adam on its own loss) instead of a
+# sharpened random init: under random init the final ``pred`` collapses to one class (SURVEY finding 6), which makes
+# ``pred`` equality vacuous.  After ~60 steps the reference predicts >= 4 distinct classes per video.
+TRAINED = [
+    ('tiny_m_iuU_clip_trained', dict(f='m', block='iuU'), True, [96, 37, 60], 7, 24, 60),
+    ('tiny_m2_iuUU_trained', dict(f='m2', block='iuUU', F=32, A=64, H=64), False, [80, 51], 6, 24, 140),
+]
+
 
 def ref_cfg(tiny_cfg):
     cfg = get_cfg_defaults()
@@ -97,6 +105,45 @@ def main():
               [[int(s['seg_lens'].numel()) for s in v['blocks'] if 'seg_lens' in s] for v in vids])
 
 
+def trained():
+    import contextlib
+    import io
+    from fact_clip.models.loss import MatchCriterion
+    for name, kw, clip, Ts, C, D, steps in TRAINED:
+        tcfg = ours.tiny(**kw)
+        cfg = ref_cfg(tcfg)
+        cfg.Loss.match, cfg.Loss.nullw, cfg.Loss.sw, cfg.Loss.pc = 'o2o', 0.1, 0.5, 0.2
+        torch.manual_seed(SEED)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = FACT_CLIP(cfg, D, C, make_text_embeddings(C)) if clip else FACT(cfg, D, C)
+        net.mcriterion = MatchCriterion(cfg, C, [])
+        data = [make_video(T, D, C, seed=300 + i, nseg=min(8, T)) for i, T in enumerate(Ts)]
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+        net.train()
+        for _ in range(steps):
+            opt.zero_grad()
+            with contextlib.redirect_stdout(io.StringIO()):
+                loss, _ = net([x for x, _ in data], [y for _, y in data], compute_loss=True)
+            loss.backward()
+            opt.step()
+        net.eval()
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items() if not k.endswith('.pe')}
+        vids = []
+        for x, y in data:
+            with torch.no_grad():
+                save = net([x], [y])
+            v = dict(x=x, label=y, pred=torch.from_numpy(save[0]['pred']), blocks=stash(net))
+            if clip:
+                v['projected_frame_embeddings'] = net.projected_frame_embeddings.detach().clone()
+            vids.append(v)
+        ncls = [int(v['pred'].unique().numel()) for v in vids]
+        assert max(ncls) >= 4, ncls
+        torch.save(dict(name=name, tiny_kwargs=kw, clip=clip, n_classes=C, in_dim=D, state_dict=sd, videos=vids),
+                   os.path.join(ROOT, 'tests', 'golden', name + '.pt'))
+        print(name, 'ok: distinct pred classes per video', ncls, 'final loss', float(loss),
+              [[int(s['seg_lens'].numel()) for s in v['blocks'] if 'seg_lens' in s] for v in vids])
+
+
 def eval_cases():
     """Known-answer vectors for the prob-fusion/argmax (blocks.py:242-261) on diverse random inputs."""
     from fact_clip.models.blocks import Block
@@ -114,5 +161,9 @@ def eval_cases():
 
 
 if __name__ == '__main__':
-    eval_cases()
-    main()
+    if 'trained' in sys.argv[1:]:
+        trained()
+    else:
+        eval_cases()
+        main()
+        trained()

@@ -141,7 +141,29 @@ def test_shipped_configs_vs_oracle_fp32(preset, ncls, lens):
     net.compute_mode, net.keep_attn = 'fp32', True
     net = net.to(DEV)
     saves = net([x.to(DEV) for x in xs], [y.to(DEV) for y in ys])
-    rows = []
+    rows = compare_free_running(net, saves, xs, sd, hp, clip, 1e-4, max_diverged=0)
+    report(f'fp32_{preset}_{"x".join(map(str, lens))}', rows)
+
+
+def report(name, rows):
+    """Parity numbers of a test, kept next to the run (gpurun_out/ travels back from the GPU box; the summaries under
+    profiles/ are copied from there)."""
+    import json
+    d = os.path.join(ROOT, 'gpurun_out', 'parity')
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, name + '.json'), 'w') as f:
+            json.dump(rows, f, indent=1)
+    except OSError:
+        pass
+    print(name, rows)
+
+
+def compare_free_running(net, saves, xs, sd, hp, clip, tol, max_diverged):
+    """Un-forced run against the oracle: every block BEFORE a video's first segmentation divergence must meet ``tol``;
+    at most ``max_diverged`` videos may diverge at all (a flipped near-tie argmax legitimately changes what follows);
+    |dS| per U block and the final argmax agreement are reported, the latter asserted >= 99.9 % over all frames."""
+    rows, diverged, agree, tot = [], 0, 0, 0
     for b, x in enumerate(xs):
         with torch.no_grad():
             o = O.forward_video(sd, hp, x, clip=clip, fast_gru=True)
@@ -150,17 +172,62 @@ def test_shipped_configs_vs_oracle_fp32(preset, ncls, lens):
         for i, (blk, st) in enumerate(zip(net.block_list, o['blocks'])):
             if 'seg_label' in st:
                 same = torch.equal(blk.tdu.seg_label.cpu(), st['seg_label'])
-                rows.append((b, i, 'S', int(st['seg_lens'].numel()), blk.tdu.num_seg, same))
+                rows.append(dict(video=b, block=i, S_oracle=int(st['seg_lens'].numel()), S=int(blk.tdu.num_seg),
+                                 dS=abs(int(st['seg_lens'].numel()) - int(blk.tdu.num_seg)), identical=bool(same)))
                 seg_ok = seg_ok and same
-            if not seg_ok:
-                break                                   # a flipped near-tie argmax legitimately changes what follows
             for k in ('frame_clogit', 'action_clogit'):
                 r = rel(getattr(blk, k)[:, 0], st[k])
-                rows.append((b, i, k, r))
-                assert r < 1e-4, (preset, b, i, k, r)
-        if seg_ok:
-            assert (saves[b]['pred'] == o['pred'].numpy()).mean() >= 0.999
-    print(preset, rows)
+                rows.append(dict(video=b, block=i, key=k, rel_l2=r, before_divergence=bool(seg_ok)))
+                if seg_ok:
+                    assert r < tol, (b, i, k, r)
+        if clip and 'clip_logit' in o:
+            r = rel(net._last['clip_logit'][b, :x.shape[0]], o['clip_logit'])
+            rows.append(dict(video=b, key='clip_logit', rel_l2=r, before_divergence=bool(seg_ok)))
+            if seg_ok:
+                assert r < tol, (b, 'clip_logit', r)
+        diverged += 0 if seg_ok else 1
+        a = int((saves[b]['pred'] == o['pred'].numpy()).sum())
+        rows.append(dict(video=b, pred_agree=a / x.shape[0], pred_classes=int(np.unique(o['pred'].numpy()).size)))
+        agree, tot = agree + a, tot + x.shape[0]
+    rows.append(dict(videos=len(xs), diverged=diverged, argmax_agreement=agree / tot))
+    assert diverged <= max_diverged, f'{diverged} of {len(xs)} videos diverged from the oracle segmentation (allowed {max_diverged})'
+    assert agree / tot >= 0.999, f'final argmax agreement {agree / tot:.5f}'
+    return rows
+
+
+def _free_run(preset, ncls, lens, mode, tol, max_diverged, seed=40):
+    cfg = C.PRESETS[preset]()
+    clip = bool(cfg.use_clip)
+    torch.manual_seed(0)
+    net = (FACT_CLIP(cfg, 2048, ncls, make_text_embeddings(ncls)) if clip else FACT(cfg, 2048, ncls)).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    hp = O.hparams_from_cfg(cfg, 2048, ncls)
+    xs, ys = make_batch(lens, 2048, ncls, base_seed=seed, nseg=8)
+    net.compute_mode, net.keep_attn = mode, True
+    net = net.to(DEV)
+    saves = net([x.to(DEV) for x in xs], [y.to(DEV) for y in ys])
+    rows = compare_free_running(net, saves, xs, sd, hp, clip, tol, max_diverged)
+    report(f'{mode}_free_{preset}_{"x".join(map(str, lens))}', rows)
+    return rows
+
+
+def test_free_running_bf16_metric_config():
+    """north_star's bar without teacher forcing: bf16 mode at the metric configuration (2 x 4096 frames), per-block logits
+    within 2e-2 relative up to each video's first segmentation divergence, |dS| reported, argmax agreement >= 99.9 %."""
+    _free_run('havid_view0_lh_pt_holdout', 75, [4096, 4096], 'bf16', 2e-2, max_diverged=2)
+
+
+def test_free_running_bf16_short_videos():
+    _free_run('havid_view0_lh_pt_holdout', 75, [1024, 700, 333], 'bf16', 2e-2, max_diverged=3)
+    _free_run('gtea', 11, [1024], 'bf16', 2e-2, max_diverged=1)
+
+
+@pytest.mark.parametrize('preset,ncls,lens', [('breakfast', 48, [5771]), ('epic_shape', 98, [16384])])
+def test_full_size_configs_vs_oracle_fp32(preset, ncls, lens):
+    """BASELINE configs 2 and 5 at their full lengths against the oracle (fp32 mode, 1e-4): MSTCN++ at F=512 over a
+    5771-frame video; the Epic shape at T=16384 with M=300 tokens -- split-T column softmax, positional-encoding table
+    regrown past 10000 rows (basic.py:125-127)."""
+    _free_run(preset, ncls, lens, 'fp32', 1e-4, max_diverged=0)
 
 
 @pytest.mark.parametrize('preset,ncls,lens', CFGS)
@@ -239,6 +306,32 @@ def test_graph_replay_alternating_batch_shapes():
                     assert np.array_equal(a['pred'], b['pred'])
     for b, v in enumerate(vids):
         assert np.array_equal(ref_short[b]['pred'], v['pred'].numpy())
+
+
+def test_graph_reused_across_lengths_and_arenas_bounded():
+    """One captured graph serves every batch of the same (B, slot) whatever the lengths (they reach the kernels through a
+    device tensor); the activation arenas are an LRU, so a sweep over many shapes holds a bounded number of them; and a
+    handle stays valid when later submits reuse its pinned slot."""
+    g = load_golden('tiny_m_iuU_clip')
+    net = build(g, 'fp32')
+    eng = net.engine()
+    x0 = torch.cat([v['x'] for v in g['videos']] * 4, 0)                    # a long feature sequence to cut videos from
+    def batch(lens):
+        return [x0[o:o + n].contiguous().pin_memory() for o, n in zip((0, 17), lens)]
+    shapes = [(100, 90), (128, 5), (70, 101), (1, 120)]                     # all slot = 128
+    refs = [net([x.to(DEV) for x in batch(l)], None) for l in shapes]
+    handles = [net.submit(batch(l), None) for l in shapes]                  # 4 in flight through 2 slots
+    for h, ref in zip(handles, refs):
+        for a, b in zip(h.result(), ref):
+            assert np.array_equal(a['pred'], b['pred'])
+    arena = eng._arenas[(2, 128, eng.ntok)]
+    assert len(arena['graphs']) == 2, 'one graph per input slot, not one per lengths tuple'
+    for n in (130, 260, 390, 520, 650, 780):                                # six more slot sizes
+        got = net.submit(batch((n, n // 2)), None).result()
+        ref = net([x.to(DEV) for x in batch((n, n // 2))], None)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a['pred'], b['pred'])
+    assert len(eng._arenas) <= eng.max_arenas
 
 
 def test_bf16_host_features():
@@ -452,4 +545,4 @@ def test_model_on_a_non_current_device():
     b = big.to('cuda:1')([x.to('cuda:1') for x in xs], None)
     for p, q in zip(a, b):
         assert np.array_equal(p['pred'], q['pred'])
-    assert all(t.device.index == 1 for t in big.engine()._bufs.values() if t.is_cuda)      # no buffer left on the old GPU
+    assert all(t.device.index == 1 for a in big.engine()._arenas.values() for t in a['bufs'].values() if t.is_cuda)   # no buffer left on the old GPU
