@@ -27,16 +27,22 @@ class MatchCriterion:
         self.cfg, self.nclasses, self.bg_ids, self._class_weight = cfg, nclasses, list(bg_ids), class_weight
 
     def class_weights(self):
-        """cweight of set_label (loss.py:62-70): ones, null class last, background or per-class weights."""
-        L = self.cfg.Loss
-        cw = torch.ones(self.nclasses + 1)
-        cw[-1] = float(L.nullw)
-        if self._class_weight is not None:
-            cw[:self.nclasses] = torch.as_tensor(self._class_weight, dtype=torch.float32)[:self.nclasses]
-        else:
-            for i in self.bg_ids:
-                cw[i] = float(L.bgw)
-        return cw
+        return class_weights(self)
+
+
+def class_weights(crit):
+    """cweight of set_label (loss.py:62-70): ones, null class last, background or per-class weights.  Reads only the
+    attributes the reference's own MatchCriterion also has (cfg, nclasses, bg_ids, _class_weight), so the criterion the
+    unchanged training script builds from ``fact_clip.models.loss`` (scripts/train.py:207) serves as well."""
+    L = crit.cfg.Loss
+    cw = torch.ones(crit.nclasses + 1)
+    cw[-1] = float(L.nullw)
+    if crit._class_weight is not None:
+        cw[:crit.nclasses] = torch.as_tensor(crit._class_weight, dtype=torch.float32)[:crit.nclasses]
+    else:
+        for i in crit.bg_ids:
+            cw[i] = float(L.bgw)
+    return cw
 
 
 def one_to_many(cost, transcript):
@@ -99,7 +105,7 @@ class LossRunner:
         ops.tdu_segment(label, gseg, gstart, glen, gcen, gn, len=ln)
         nseg = gn.cpu().numpy()                                    # host sync 1: B ints
         smax = int(nseg.max())
-        cweight = self.crit.class_weights().to(dev)          # C+1 floats; the criterion's cfg may change between calls
+        cweight = class_weights(self.crit).to(dev)          # C+1 floats; the criterion's cfg may change between calls
         transcript, sweight = buf('loss_tr', (B, smax), I32), buf('loss_sw', (B, smax))
         # ---- InfoNCE bookkeeping (blocks.py:697-748): seen-class list, label remapping, per-class frame counts
         clip = 'projected_frame_embeddings' in out

@@ -12,8 +12,9 @@ Differences from the reference that a caller can observe:
   * stashed attributes (``block.frame_clogit`` ...) are produced on request (``net.stash_video(i)``)
     rather than on every call; they refer to the LAST video of the batch by default, like the
     reference where each video overwrites the previous one.
-  * training (``compute_loss=True``) is not implemented yet: SURVEY.md section 8(f) rank 1.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -153,7 +154,9 @@ class _FactBase(nn.Module):
                 raise ValueError(f'FACT.block type {t!r} (the reference handles i/u/U only, blocks.py:38-48)')
         self.block_list = nn.ModuleList(blocks)
         self.mcriterion = None
-        self.compute_mode = 'bf16'      # 'bf16' (default) or 'fp32'; see DESIGN.md
+        # 'bf16' (default) or 'fp32'; see DESIGN.md.  FACTK_MODE sets the default for scripts that only call the constructor
+        self.compute_mode = os.environ.get('FACTK_MODE', 'bf16')
+        assert self.compute_mode in ('bf16', 'fp32'), f'FACTK_MODE={self.compute_mode!r}'
         self._engine = None
 
     # -------------------------------------------------------------- engine plumbing
@@ -199,6 +202,7 @@ class _FactBase(nn.Module):
             res = LossRunner(self.engine(), self.mcriterion).run(out, label_list)
             self.last_match = res['matches']
         pred = out['pred'].cpu().numpy()            # the one D2H sync of the call (blocks.py:900)
+        self._fire_branch_hooks(out)
         self.stash_video(len(seqs) - 1)
         saves = [{'pred': pred[b, :T].copy()} for b, T in enumerate(out['lengths'])]
         if not compute_loss:
@@ -264,6 +268,28 @@ class _FactBase(nn.Module):
             h = self.engine().submit(list(seq_list), channel_major=channel_major)
         self._last = h.out
         return h
+
+    def _fire_branch_hooks(self, out):
+        """Forward hooks registered on ``block.frame_branch`` / ``block.action_branch`` (what
+        scripts/fact_input_emb_logit_viz.py:24-30,62-63 does) fire once per video, in video order, with the tensor the
+        reference's sub-module returns: the (T,1,H) / (M,1,H) feature BEFORE process_feature, i.e. the raw class logits in
+        the class tail (the engine splices the probabilities in place, the logits are kept beside it).  The hook's
+        ``input`` argument is an empty tuple: the engine never materialises per-module inputs."""
+        blocks = [(blk, st) for blk, st in zip(self.block_list, out['blocks'])
+                  if blk.frame_branch._forward_hooks or blk.action_branch._forward_hooks]
+        if not blocks:
+            return
+        for b, T in enumerate(out['lengths']):
+            for blk, st in blocks:
+                for mod, feat, logit, rows in ((blk.frame_branch, st['frame_feature'], st['frame_clogit'], T),
+                                               (blk.action_branch, st['action_feature'], st['action_clogit'], None)):
+                    if not mod._forward_hooks:
+                        continue
+                    n = logit.shape[-1]
+                    f, lg = feat[b, :rows].float(), logit[b, :rows, :n].float()
+                    o = torch.cat([f[:, :f.shape[1] - n], lg], -1).unsqueeze(1)
+                    for hook in list(mod._forward_hooks.values()):
+                        hook(mod, (), o)
 
     def stash_video(self, b):
         """Expose video ``b`` of the last batch through the reference's per-block attributes
