@@ -71,6 +71,33 @@ _SIGS = {
     'factk_transpose_rows': (i32, [vp, C.c_longlong, vp, i32, i32, i32, i32, i32, vp, vp]),
     'factk_vn_splice': (i32, [vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
     'factk_vn_combine': (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp, vp]),
+    # training step (csrc/train*.cu)
+    'factk_wgrad_ws_floats': (C.c_size_t, [i32, i32, i32, i32]),
+    'factk_wgrad': (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, i32, C.c_longlong, f32, i32, i32, i32,
+                          vp, vp, vp]),
+    'factk_colsum_ws_floats': (C.c_size_t, [i32, i32, i32]),
+    'factk_colsum': (i32, [vp, i32, i32, vp, i32, i32, i32, vp, C.c_longlong, f32, i32, i32, i32, vp, vp, vp]),
+    'factk_rows_elementwise': (i32, [i32, vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp, f32, f32, C.c_ulonglong,
+                                     C.c_uint, i32, vp]),
+    'factk_transpose': (i32, [vp, i32, C.c_longlong, vp, i32, C.c_longlong, i32, i32, i32, vp]),
+    'factk_splice_bwd': (i32, [vp, i32, i32, vp, i32, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    'factk_row_softmax_bwd': (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
+    'factk_layernorm_bwd_ws_floats': (C.c_size_t, [i32, i32, i32]),
+    'factk_layernorm_bwd': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, f32, i32, vp, i32, i32, vp, i32, i32, i32, vp, vp, i32, i32, vp,
+                                  i32, vp, vp]),
+    'factk_l2norm_bwd': (i32, [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, f32, vp]),
+    'factk_col_softmax_train_ws_floats': (C.c_size_t, [i32, i32, i32]),
+    'factk_col_softmax': (i32, [vp, i32, vp, i32, i32, f32, i32, i32, vp, vp, vp]),
+    'factk_col_softmax_bwd': (i32, [vp, i32, vp, i32, vp, i32, i32, f32, i32, i32, i32, vp, vp, vp]),
+    'factk_segment_reduce': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    'factk_segment_expand': (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
+    'factk_gru_bwd': (i32, [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, i32, i32, vp, vp]),
+    'factk_loss_grad_ce_rows': (i32, [vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    'factk_loss_grad_smooth': (i32, [vp, i32, i32, vp, i32, vp, vp, f32, i32, i32, vp]),
+    'factk_loss_grad_token': (i32, [vp, i32, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, vp]),
+    'factk_loss_grad_xattn': (i32, [i32, vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32,
+                                    i32, vp]),
+    'factk_loss_grad_infonce': (i32, [vp, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, vp]),
 }
 
 _lib = None

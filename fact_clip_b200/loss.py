@@ -7,7 +7,8 @@ matching costs (the assignment itself is ``scipy.optimize.linear_sum_assignment`
 final per-video numbers.  The reference instead moves every (1, T, M) attention map to the host and builds a (T, M, S)
 numpy temporary per video (loss.py:91-106).
 
-Values only: there is no backward pass (second half).
+``LossRunner.seeds`` gives the gradient of the loss w.r.t. every logit tensor it reads (csrc/train_loss.cu): the entry points of
+the hand-written backward pass of fact_clip_b200/train.py.
 """
 import numpy as np
 import torch
@@ -204,4 +205,81 @@ class LossRunner:
                          fact_w=float(cfg.CLIP.fact_loss_weight) if clip else 1.0,
                          con_w=float(cfg.CLIP.contrastive_weight) if clip else 0.0,
                          nseen=len(seen) if clip else 0, nvalid=nvalid)
-        return dict(values=res, matches=matches)
+        ctx = dict(label=label, gseg=gseg, gstart=gstart, glen=glen, gn=gn, transcript=transcript, tr_h=tr_h, aind=aind, sind=sind,
+                   nm=nm, aind_h=aind_h, sind_h=sind_h, inv_h=inv_h, nseg_h=nseg, cweight=cweight, cmap=cmap, seen=seen,
+                   nvalid=nvalid, smax=smax, types=types, clip=clip, lse_cls=lse if clip else None)
+        return dict(values=res, matches=matches, ctx=ctx)
+
+    def seeds(self, out, res, scale=1.0):
+        """Gradient of ``scale * mean_b loss_b`` w.r.t. every logit tensor the loss reads, for the training step
+        (fact_clip_b200/train.py): list of (Var, gradient).  Mirrors the formulas of ``run`` / factk_loss_combine term by term
+        (csrc/train_loss.cu); the matching is a constant of the backward pass, like in the reference (loss.py:131 no_grad)."""
+        e, cfg, c = self.e, self.crit.cfg, res['ctx']
+        hp, Lc = e.hp, cfg.Loss
+        B, slot, ln, dev = e.B, e.slot, e.len, e.dev
+        C, M, nb = hp['n_classes'], e.ntok, len(hp['blocks'])
+        F32 = torch.float32
+        clip = c['clip']
+        fact_w = float(cfg.CLIP.fact_loss_weight) if clip else 1.0
+        con_w = float(cfg.CLIP.contrastive_weight) if clip else 0.0
+        coef_f = np.full(B, scale * fact_w / (nb * B), np.float32)
+        coef_c = np.full(B, scale * con_w / B, np.float32)
+        if clip:                     # no frame with a seen label: the reference returns the un-weighted FACT loss (blocks.py:744-746)
+            nv = c['nvalid'].cpu().numpy()
+            coef_f[nv == 0] = scale / (nb * B)
+            coef_c[nv == 0] = 0.0
+        dv = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+        cf, cf_half, cc = dv(coef_f), dv(coef_f * 0.5), dv(coef_c)
+        # per ground-truth segment: the matched token (column) and the weight at its match position; per token: multiplicity
+        smax = max(c['smax'], 1)
+        colmap_h, wmap_h = np.full((B, smax), -1, np.int32), np.zeros((B, smax), np.float32)
+        mult_h = np.zeros((B, M), np.float32)
+        cw_h = c['cweight'].cpu().numpy()
+        for b in range(B):
+            S = int(c['nseg_h'][b])
+            for gs in range(S):
+                k = int(c['inv_h'][b, gs])
+                if k >= 0:
+                    colmap_h[b, gs] = c['aind_h'][b, k]
+                    wmap_h[b, gs] = cw_h[c['tr_h'][b, k]]       # QUIRK (loss.py:221-222): weight by match POSITION
+            for k in range(S):
+                mult_h[b, c['aind_h'][b, k]] += 1.0
+        colmap, wmap, mult = dv(colmap_h), dv(wmap_h), dv(mult_h)
+        z = lambda t: torch.zeros_like(t)
+        seeds = []
+        sw = float(Lc.sw)
+        for i, (st, bc) in enumerate(zip(out['blocks'], hp['blocks'])):
+            ty = c['types'][i]
+            tdu = ty == 2
+            fc, ac = st['frame_clogit_v'], st['action_clogit_v']
+            gfc, gac = z(fc.v), z(ac.v)
+            ops.loss_grad_ce_rows(fc.v, C, gfc, c['label'], c['cweight'], ln, cf_half if tdu else cf)
+            if sw != 0.0:
+                ops.loss_grad_smooth(fc.v, C, gfc, ln, cf, sw)
+            ops.loss_grad_token(ac.v, gac, c['aind'], c['sind'], c['nm'], c['transcript'], c['cweight'], cf)
+            seeds += [(fc, gfc), (ac, gac)]
+            if ty == 0:
+                continue
+            f2a, a2f = st['f2a_logit_v'], st['a2f_logit_v']
+            gf2a, ga2f = z(f2a.v), z(a2f.v)
+            seg = dict(seg_label=st['seg_label'], seg_start=st['seg_start'], seg_len=st['seg_lens']) if tdu else None
+            nrows = st['nseg'] if tdu else ln
+            lse = torch.empty(B, f2a.v.shape[2], dtype=F32, device=dev)
+            ops.col_lse(f2a.v, M, nrows, lse)
+            ops.loss_grad_xattn(1, f2a.v, M, gf2a, c, colmap, wmap, smax, nrows, cf, seg=seg, col_lse=lse)
+            ops.loss_grad_xattn(0, a2f.v, M, ga2f, c, colmap, wmap, smax, nrows, cf, seg=seg, mult=mult)
+            if ty == 1 and sw != 0.0:
+                ops.loss_grad_smooth(f2a.v, M, gf2a, ln, cf, sw)
+                ops.loss_grad_smooth(a2f.v, M, ga2f, ln, cf, sw)
+            seeds += [(f2a, gf2a), (a2f, ga2f)]
+            if tdu:
+                sc = st['seg_clogit_v']
+                gsc = z(sc.v)
+                ops.loss_grad_ce_rows(sc.v, C, gsc, c['label'], c['cweight'], nrows, cf_half, seg=seg)
+                seeds.append((sc, gsc))
+        if clip:
+            sim = out['clip_logit_v']
+            gs = z(sim.v)
+            ops.loss_grad_infonce(sim.v, C, gs, c['label'], c['cmap'], c['lse_cls'], c['nvalid'], int(c['seen'].numel()), ln, cc)
+            seeds.append((sim, gs))
+        return seeds

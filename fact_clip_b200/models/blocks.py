@@ -176,11 +176,6 @@ class _FactBase(nn.Module):
         return self._forward(seq_list, label_list, compute_loss, forced_preds)
 
     def _forward(self, seq_list, label_list=None, compute_loss=False, forced_preds=None):
-        if self.training:
-            raise RuntimeError('the forward is built for eval mode: call net.eval() first. Training mode would need the '
-                               "reference's dropout, channel masking and time masking (blocks.py:58-70), which are part of the "
-                               'training step that is not built (SURVEY.md 8f rank 1); silently returning eval-mode results '
-                               'would be wrong')
         if compute_loss and self.mcriterion is None:
             raise RuntimeError('compute_loss=True needs net.mcriterion = MatchCriterion(cfg, nclasses, bg_ids) (scripts/train.py:207)')
         seqs = list(seq_list)        # CUDA tensors, or (pinned) host tensors copied straight into the packed batch
@@ -192,6 +187,8 @@ class _FactBase(nn.Module):
         if any(s.dim() != 2 or s.shape[0] == 0 or s.shape[1] != self.in_dim for s in seqs):
             raise ValueError(f'every video must be a non-empty (T, {self.in_dim}) feature matrix, got '
                              f'{[tuple(s.shape) for s in seqs]}')
+        if self.training:
+            return self._forward_train(seqs, label_list, compute_loss, forced_preds)
         if self.cfg.FACT.trans:
             return self._forward_with_transcripts(seqs, label_list, forced_preds, compute_loss)
         # the verb/noun model's loss reads the action log-probabilities of EVERY block: keep them
@@ -220,6 +217,50 @@ class _FactBase(nn.Module):
         if vals[-1, 3] > 0:
             self.fact_loss, self.contrastive_loss = res['values'][-1, 1], res['values'][-1, 2]
         return res['values'][:, 0].mean(), saves
+
+    # -------------------------------------------------------------- training step
+    def train_engine(self):
+        from ..train import TrainEngine
+        if getattr(self, '_train_engine', None) is None or self._train_engine.mode != self.compute_mode:
+            hp = cfgmod.hparams(self.cfg, self.in_dim, self.num_classes)
+            if hasattr(self, 'vids'):
+                hp['vn'] = (self.vids, self.nids)
+            self._train_engine = TrainEngine(self, hp, clip=isinstance(self, FACT_CLIP), mode=self.compute_mode)
+        return self._train_engine
+
+    def _forward_train(self, seqs, label_list, compute_loss, forced_preds=None):
+        """``net.train(); loss, saves = net(seqs, labels, compute_loss=True); loss.backward()`` (scripts/train.py:262-264):
+        train-mode forward (channel masking, time masking, dropouts: blocks.py:614-622) over the batch, loss on the device,
+        and a loss tensor whose backward runs the hand-written gradient kernels (fact_clip_b200/train.py) and fills
+        ``param.grad`` of every parameter.  ``net.grad_ready_hook(names, grads)``, when set, is called as soon as the gradients of
+        a block's parameters are final (data-parallel all-reduce overlapped with the rest of the backward pass)."""
+        eng = self.train_engine()
+        with torch.no_grad():
+            out = eng.forward_train(seqs, forced_preds=forced_preds)
+            self._last = out
+            res = LossRunner(eng, self.mcriterion).run(out, label_list) if compute_loss else None
+            pred = out['pred'].cpu().numpy()
+        self._fire_branch_hooks(out)
+        self.stash_video(len(seqs) - 1)
+        saves = [{'pred': pred[b, :T].copy()} for b, T in enumerate(out['lengths'])]
+        if not compute_loss:
+            eng.tape = []
+            return saves
+        self.last_match = res['matches']
+        vals = res['values'].cpu().numpy()
+        nb = len(self.block_list)
+        for b, s in enumerate(saves):
+            s['loss'] = {'loss': float(vals[b, 0])}
+            if vals[b, 3] > 0:
+                s['loss'].update(fact_loss=float(vals[b, 1]), contrastive_loss=float(vals[b, 2]))
+            s['block_losses'] = vals[b, 4:4 + nb].tolist()
+        self.loss_list = [res['values'][-1, 4 + i] for i in range(nb)]
+        if vals[-1, 3] > 0:
+            self.fact_loss, self.contrastive_loss = res['values'][-1, 1], res['values'][-1, 2]
+        names = [n for n, p in self.named_parameters() if p.requires_grad]
+        params = [p for _, p in self.named_parameters() if p.requires_grad]
+        loss = _TrainStep.apply(self, out, res, names, res['values'][:, 0].mean(), *params)
+        return loss, saves
 
     def _forward_with_transcripts(self, seqs, label_list, forced_preds=None, compute_loss=False):
         """FACT.trans (blocks.py:74-79, 113-118): every video brings its own token count (the length of its transcript), so
@@ -327,6 +368,31 @@ class _FactBase(nn.Module):
 
     def save_model(self, fname):
         torch.save(self.state_dict(), fname)
+
+
+class _TrainStep(torch.autograd.Function):
+    """Autograd glue of the training step: the forward is already done (kernels, no graph); ``backward`` seeds the tape with
+    the loss gradients and returns the parameter gradients the hand-written kernels produced."""
+
+    @staticmethod
+    def forward(ctx, net, out, res, names, value, *params):
+        ctx.net, ctx.out, ctx.res, ctx.names = net, out, res, names
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        net = ctx.net
+        eng = net._train_engine
+        dev = next(net.parameters()).device
+        with torch.no_grad(), torch.cuda.device(dev):
+            seeds = LossRunner(eng, net.mcriterion).seeds(ctx.out, ctx.res)
+            grads = eng.backward(seeds)
+            gl = [grads.get(n) for n in ctx.names]
+            have = [g for g in gl if g is not None]
+            if have:
+                torch._foreach_mul_(have, gout)
+        ctx.out = ctx.res = None
+        return (None, None, None, None, None) + tuple(gl)
 
 
 def _clone_tree(o):

@@ -360,3 +360,174 @@ def transpose_rows(src, src_bstride, dst, len, D):
     COUNTERS['launches'] += 1
     _call('factk_transpose_rows', None, src.data_ptr(), int(src_bstride), dst.data_ptr(), L.dt(dst), _row_ld(dst), B, slot, D,
           len.data_ptr(), L.stream())
+
+
+# ---------------------------------------------------------------------------------------------- training step (train*.cu)
+EW_RELU_BWD, EW_AXPY, EW_DROPOUT, EW_DROPOUT_CH, EW_COPY, EW_MUL, EW_ADD, EW_RELU = range(8)
+_WS = {}
+
+
+def _ws(dev, n):
+    """Scratch of at least n floats on ``dev`` (grown geometrically, reused by every reduction of the backward pass --
+    launches on one stream are ordered, so consecutive users cannot overlap)."""
+    t = _WS.get(dev)
+    if t is None or t.numel() < n:
+        t = _WS[dev] = torch.empty(max(int(n * 1.25), 1 << 20), dtype=torch.float32, device=dev)
+    return t
+
+
+def wgrad(dz, a, N, K, dw, off=0, len=None, alpha=1.0, accumulate=True, pos=None, pos_d=None, pos_idx=None, per_video=False):
+    """dw[(b)][n][k] (+)= alpha * sum_rows dz[b,t,n] * (a[b,t+off,k] + pos).  dz / a: rows tensors; dw: [N, K] view (unit
+    stride in k), or [B, N, K] with per_video."""
+    B, slot = dz.shape[0], dz.shape[1]
+    assert dw.stride(-1) == 1 and dw.dtype == torch.float32
+    a_slot = 0 if (a.shape[0] == 1 and B > 1) else a.stride(0) // _row_ld(a)
+    ws = _ws(dz.device, L.load().factk_wgrad_ws_floats(B, slot, N, K))
+    COUNTERS['launches'] += 2
+    _call('factk_wgrad', 'wgrad', dz.data_ptr(), L.dt(dz), _row_ld(dz), a.data_ptr(), L.dt(a), _row_ld(a), a_slot, int(off),
+          L.ptr(pos), pos.stride(0) if pos is not None else 0, (pos_d if pos_d is not None else pos.shape[-1]) if pos is not None else 0,
+          L.ptr(pos_idx), N, K, dw.data_ptr(), dw.stride(-2), dw.stride(0) if per_video else 0, float(alpha), int(accumulate),
+          B, slot, L.ptr(len), ws.data_ptr(), L.stream())
+
+
+def colsum(x, N, out, y=None, len=None, alpha=1.0, accumulate=True, per_video=False):
+    """out[(b)][n] (+)= alpha * sum_rows x[b,t,n] (* y[b,t,n])."""
+    B, slot = x.shape[0], x.shape[1]
+    ws = _ws(x.device, L.load().factk_colsum_ws_floats(B, slot, N))
+    COUNTERS['launches'] += 2
+    _call('factk_colsum', None, x.data_ptr(), L.dt(x), _row_ld(x), L.ptr(y), L.dt(y) if y is not None else 0,
+          _row_ld(y) if y is not None else 0, N, out.data_ptr(), out.stride(0) if per_video else 0, float(alpha), int(accumulate),
+          B, slot, L.ptr(len), ws.data_ptr(), L.stream())
+
+
+def ew(op, x, y, N, r=None, len=None, alpha=1.0, p=0.0, seed=0, site=0, bcast=False):
+    """Elementwise pass over the valid rows of y ([B, slot, ld]); see factk_rows_elementwise.  bcast: x is one [slot, ld] table."""
+    B, slot = y.shape[0], y.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_rows_elementwise', None, int(op), x.data_ptr(), L.dt(x), _row_ld(x), L.ptr(r), L.dt(r) if r is not None else 0,
+          _row_ld(r) if r is not None else 0, y.data_ptr(), L.dt(y), _row_ld(y), N, B, slot, L.ptr(len), float(alpha), float(p),
+          int(seed), int(site), 0 if bcast else -1, L.stream())
+
+
+def transpose(src, dst):
+    """dst[b, c, r] = src[b, r, c] (fp32, last dims contiguous)."""
+    B, R, Cc = src.shape
+    assert src.dtype == dst.dtype == torch.float32 and src.stride(-1) == 1 and dst.stride(-1) == 1
+    COUNTERS['launches'] += 1
+    _call('factk_transpose', None, src.data_ptr(), src.stride(1), src.stride(0), dst.data_ptr(), dst.stride(1), dst.stride(0), R, Cc, B,
+          L.stream())
+
+
+def splice_bwd(y, dy, dcl, dx, H, C, len=None):
+    B, slot = y.shape[0], y.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_splice_bwd', None, y.data_ptr(), L.dt(y), _row_ld(y), L.ptr(dy), L.dt(dy) if dy is not None else 0,
+          _row_ld(dy) if dy is not None else 0, L.ptr(dcl), _row_ld(dcl) if dcl is not None else 0, dx.data_ptr(), L.dt(dx), _row_ld(dx),
+          H, C, B, slot, L.ptr(len), L.stream())
+
+
+def row_softmax_bwd(p, dp, dl, M, len=None, accumulate=False):
+    B, slot = p.shape[0], p.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_row_softmax_bwd', None, p.data_ptr(), _row_ld(p), dp.data_ptr(), _row_ld(dp), dl.data_ptr(), _row_ld(dl), M,
+          int(accumulate), B, slot, L.ptr(len), L.stream())
+
+
+def layernorm_bwd(x, w, b, dy, dv, dw, db, res=None, eps=1e-5, relu=False, len=None, accumulate=False, E=None):
+    B, slot = x.shape[0], x.shape[1]
+    E = x.shape[-1] if E is None else E
+    ws = _ws(x.device, L.load().factk_layernorm_bwd_ws_floats(B, slot, E))
+    COUNTERS['launches'] += 3
+    _call('factk_layernorm_bwd', None, x.data_ptr(), L.dt(x), _row_ld(x), L.ptr(res), L.dt(res) if res is not None else 0,
+          _row_ld(res) if res is not None else 0, w.data_ptr(), b.data_ptr(), float(eps), int(relu), dy.data_ptr(), L.dt(dy), _row_ld(dy),
+          dv.data_ptr(), L.dt(dv), _row_ld(dv), int(accumulate), dw.data_ptr(), db.data_ptr(), B, slot, L.ptr(len), E, ws.data_ptr(),
+          L.stream())
+
+
+def l2norm_bwd(x, dy, dx, eps=1e-12, len=None):
+    B, slot, E = x.shape
+    COUNTERS['launches'] += 1
+    _call('factk_l2norm_bwd', None, x.data_ptr(), L.dt(x), _row_ld(x), dy.data_ptr(), L.dt(dy), _row_ld(dy), dx.data_ptr(), L.dt(dx),
+          _row_ld(dx), B, slot, L.ptr(len), E, float(eps), L.stream())
+
+
+def col_softmax(logit, p, M, scale=1.0, len=None):
+    B, slot = logit.shape[0], logit.shape[1]
+    ws = _ws(logit.device, L.load().factk_col_softmax_train_ws_floats(B, slot, M))
+    COUNTERS['launches'] += 3
+    _call('factk_col_softmax', None, logit.data_ptr(), _row_ld(logit), p.data_ptr(), _row_ld(p), M, float(scale), B, slot, L.ptr(len),
+          ws.data_ptr(), L.stream())
+
+
+def col_softmax_bwd(p, dp, dl, M, scale=1.0, len=None, accumulate=False):
+    B, slot = p.shape[0], p.shape[1]
+    ws = _ws(p.device, L.load().factk_colsum_ws_floats(B, slot, M) + B * M)
+    COUNTERS['launches'] += 3
+    _call('factk_col_softmax_bwd', None, p.data_ptr(), _row_ld(p), dp.data_ptr(), _row_ld(dp), dl.data_ptr(), _row_ld(dl), M, float(scale),
+          int(accumulate), B, slot, L.ptr(len), ws.data_ptr(), L.stream())
+
+
+def segment_reduce(x, out, seg_start, seg_len, nseg, E, mean=False, accumulate=True):
+    B, slot = x.shape[0], x.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_segment_reduce', None, x.data_ptr(), L.dt(x), _row_ld(x), out.data_ptr(), L.dt(out), _row_ld(out), seg_start.data_ptr(),
+          seg_len.data_ptr(), nseg.data_ptr(), B, slot, E, int(mean), int(accumulate), L.stream())
+
+
+def segment_expand(seg, seg_label, seg_len, out, E, len=None, inv_len=False, accumulate=True):
+    B, slot = out.shape[0], out.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_segment_expand', None, seg.data_ptr(), L.dt(seg), _row_ld(seg), seg_label.data_ptr(), L.ptr(seg_len), out.data_ptr(),
+          L.dt(out), _row_ld(out), B, slot, L.ptr(len), E, int(inv_len), int(accumulate), L.stream())
+
+
+def gru_bwd(gi, gh, hout, dout, w_hh_f, w_hh_b, dgi, dgh, nseg):
+    B, slot = gi.shape[0], gi.shape[1]
+    Hh = w_hh_f.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_gru_bwd', None, gi.data_ptr(), gh.data_ptr(), hout.data_ptr(), L.dt(hout), _row_ld(hout), dout.data_ptr(), L.dt(dout),
+          _row_ld(dout), w_hh_f.data_ptr(), w_hh_b.data_ptr(), Hh, dgi.data_ptr(), dgh.data_ptr(), B, slot, nseg.data_ptr(), L.stream())
+
+
+def loss_grad_ce_rows(x, C, dx, label, cweight, nrows, coef, seg=None):
+    B, slot = label.shape
+    COUNTERS['launches'] += 1
+    _call('factk_loss_grad_ce_rows', None, x.data_ptr(), _row_ld(x), C, dx.data_ptr(), _row_ld(dx), label.data_ptr(), cweight.data_ptr(),
+          L.ptr(seg['seg_start']) if seg else None, L.ptr(seg['seg_len']) if seg else None, nrows.data_ptr(), coef.data_ptr(), B, slot,
+          L.stream())
+
+
+def loss_grad_smooth(x, C, dx, len, coef, mult):
+    B, slot = x.shape[0], x.shape[1]
+    COUNTERS['launches'] += 1
+    _call('factk_loss_grad_smooth', None, x.data_ptr(), _row_ld(x), C, dx.data_ptr(), _row_ld(dx), len.data_ptr(), coef.data_ptr(),
+          float(mult), B, slot, L.stream())
+
+
+def loss_grad_token(aclogit, dx, aind, sind, nmatch, transcript, cweight, coef):
+    B, M, C1 = aclogit.shape
+    assert aclogit.is_contiguous() and dx.is_contiguous()
+    COUNTERS['launches'] += 1
+    _call('factk_loss_grad_token', None, aclogit.data_ptr(), M, C1, dx.data_ptr(), aind.data_ptr(), sind.data_ptr(), nmatch.data_ptr(),
+          aind.shape[1], transcript.data_ptr(), transcript.shape[1], cweight.data_ptr(), coef.data_ptr(), B, L.stream())
+
+
+def loss_grad_xattn(mode, x, M, dx, c, colmap, wmap, smax, nrows, coef, seg=None, mult=None, col_lse=None):
+    """c: the criterion context of LossRunner.run (ground-truth segmentation of the labels)."""
+    B, slot = c['gseg'].shape
+    colmass = torch.empty(B, M, dtype=torch.float32, device=x.device) if mode == 1 else None
+    COUNTERS['launches'] += 2 if mode == 1 else 1
+    _call('factk_loss_grad_xattn', None, int(mode), x.data_ptr(), _row_ld(x), M, dx.data_ptr(), _row_ld(dx), c['gseg'].data_ptr(),
+          c['gstart'].data_ptr(), c['glen'].data_ptr(), c['gn'].data_ptr(), colmap.data_ptr(), wmap.data_ptr(), smax, L.ptr(mult),
+          L.ptr(colmass), L.ptr(col_lse), col_lse.stride(0) if col_lse is not None else 0,
+          L.ptr(seg['seg_label']) if seg else None, L.ptr(seg['seg_start']) if seg else None, L.ptr(seg['seg_len']) if seg else None,
+          nrows.data_ptr(), coef.data_ptr(), B, slot, L.stream())
+
+
+def loss_grad_infonce(sim, C, ds, label, cmap, col_lse, nvalid, nseen, len, coef):
+    B, slot = label.shape
+    count = torch.empty(B, C, dtype=torch.float32, device=sim.device)
+    COUNTERS['launches'] += 2
+    _call('factk_loss_grad_infonce', None, sim.data_ptr(), _row_ld(sim), C, ds.data_ptr(), _row_ld(ds), label.data_ptr(), cmap.data_ptr(),
+          count.data_ptr(), col_lse.data_ptr(), col_lse.stride(0), nvalid.data_ptr(), nseen, len.data_ptr(), coef.data_ptr(), B, slot,
+          L.stream())

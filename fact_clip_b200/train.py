@@ -1,0 +1,842 @@
+"""Training step of FACT / FACT_CLIP on the factk kernels: train-mode forward, loss, hand-written backward.
+
+The reference trains with ``loss, saves = net(seqs, labels, compute_loss=True); loss.backward()`` (scripts/train.py:262-264),
+i.e. torch autograd over eager cuDNN / cuBLAS ops, one video at a time.  Here the whole batch runs as ONE train-mode forward
+over the same kernels the inference engine uses (GEMMs, segmentation, GRU, softmax-splice ...), every intermediate that a
+gradient needs is kept in HBM, and the backward pass is a tape of closures that launch the kernels of csrc/train*.cu:
+
+  * data gradient of a Conv1d tap / Linear  = the forward GEMM with the transposed weight and the negated tap offset
+  * weight gradient                         = ``factk_wgrad`` (rows^T x rows, split over the frames, fixed-order reduction)
+  * attention (token self-attention, tokens-attend-frames, X2Y f2a / a2f) is spelled out as logit GEMM -> softmax ->
+    apply, so its backward is the same three primitives again (no attention-specific gradient kernel)
+  * bi-GRU: back-propagation through time on a 4-CTA cluster per (video, direction) (``factk_gru_bwd``)
+  * LayerNorm, softmax-splice (process_feature), L2-normalise, segment mean / gather: one row kernel each
+  * the loss gradients w.r.t. every logit tensor: csrc/train_loss.cu
+
+Derived weights (Conv1d taps re-laid as [tap][out][in], the folded MSTCN++ layer, concatenated GRU input weights, the padded
+CLIP projection) are differentiable torch functions of the parameters: the kernels produce the gradient of the DERIVED
+tensor and one ``torch.autograd.grad`` over those parameter-sized functions carries it to the parameters.  Nothing
+activation-sized ever goes through torch autograd.
+
+Train-mode augmentations of the reference forward (blocks.py:614-622): ``Dropout2d`` channel masking of the input features
+(FACT.cmr), ``time_mask`` (TM.*), and the dropouts inside the network (cfg dropout, CLIP.projection_dropout).  Masks come from a
+counter-based hash of (seed, site, element) so the backward pass regenerates them; ``engine.seed`` changes every step.
+"""
+import math
+import random
+
+import torch
+
+from . import ops
+from .engine import FactEngine, _pos_table, _round_up
+from .ops import S
+
+
+class Var:
+    """One activation of the training forward: value, lazily allocated gradient, valid-row vector."""
+    __slots__ = ('v', 'g', 'len', 'needs_grad')
+
+    def __init__(self, v, ln=None, g=None, needs_grad=True):
+        self.v, self.g, self.len, self.needs_grad = v, g, ln, needs_grad
+
+
+class Wt:
+    """A weight as the kernels see it: value ``w`` and gradient accumulator ``g`` (same shape; views slice both)."""
+    __slots__ = ('w', 'g', '_t')
+
+    def __init__(self, w, g):
+        self.w, self.g, self._t = w, g, None
+
+    def __getitem__(self, idx):
+        return Wt(self.w[idx], None if self.g is None else self.g[idx])
+
+    def T(self):
+        if self._t is None:
+            self._t = self.w.t().contiguous()
+        return self._t
+
+
+def src(x, W, off=0, pos=None, pos_idx=None, K=None):
+    return dict(x=x, W=W, off=off, pos=pos, pos_idx=pos_idx, K=K)
+
+
+class TrainEngine(FactEngine):
+    def __init__(self, module, hp, clip, mode='fp32'):
+        super().__init__(module, hp, clip, mode)
+        self.seed, self.step_no = 0x5EED, 0
+        self.forced_masks = None          # tests: {'cmr': keep mask [B, D]} injected instead of the hashed one
+        if hp['trans'] or self.vn is not None:
+            raise NotImplementedError('training step: FACT.trans and the Epic verb/noun model are not built (query-token FACT / '
+                                      'FACT_CLIP only)')
+
+    # ------------------------------------------------------------------ bookkeeping
+    def begin(self):
+        self.tape, self._site = [], 0
+        self._params = dict(self.m.named_parameters())
+        self._pg = {}                     # parameter name -> fp32 gradient accumulator
+        self._derived = []                # (tensor with autograd graph, gradient accumulator)
+        self._wt = {}
+        self.step_no += 1
+
+    def new(self, shape, dtype=torch.float32, zero=False):
+        return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
+
+    def G(self, var):
+        if var.g is None:
+            var.g = torch.zeros_like(var.v)
+        return var.g
+
+    def cols(self, var, a, b):
+        """Column slice of a Var sharing value and gradient storage."""
+        self.G(var)
+        return Var(var.v[..., a:b], var.len, var.g[..., a:b])
+
+    def W(self, name):
+        """Parameter as a weight handle (gradient accumulates in a buffer of the parameter's shape)."""
+        h = self._wt.get(name)
+        if h is None:
+            p = self._params[name]
+            g = self._pg.get(name)
+            if g is None:
+                g = self._pg[name] = torch.zeros_like(p, dtype=torch.float32)
+            h = self._wt[name] = Wt(p.detach(), g)
+        return h
+
+    def const(self, t):
+        return Wt(t, None)
+
+    def D(self, key, fn):
+        """Derived weight: ``fn()`` is a differentiable torch function of the parameters (parameter-sized)."""
+        h = self._wt.get(key)
+        if h is None:
+            with torch.enable_grad():
+                t = fn()
+            t = t if t.is_contiguous() else t.contiguous()
+            g = torch.zeros_like(t, dtype=torch.float32)
+            self._derived.append((t, g))
+            h = self._wt[key] = Wt(t.detach(), g)
+        return h
+
+    def P(self, name):
+        return self._params[name]
+
+    def taps_w(self, name, groups=1):
+        """Conv1d weight (Cout, Cin/groups, k) as [k][Cout][Cin] (dense block-diagonal for grouped convolutions)."""
+        def make():
+            w = self.P(name)
+            if groups > 1:
+                co, ci = w.shape[0] // groups, w.shape[1]
+                full = w.new_zeros(w.shape[0], ci * groups, w.shape[2])
+                for j in range(groups):
+                    full[j * co:(j + 1) * co, j * ci:(j + 1) * ci] = w[j * co:(j + 1) * co]
+                w = full
+            return w.permute(2, 0, 1).contiguous()
+        return self.D(('taps', name, groups), make)
+
+    def next_site(self):
+        self._site += 1
+        return self._site
+
+    # ------------------------------------------------------------------ primitive ops (forward + tape entry)
+    def linear(self, srcs, N, bias=None, relu=False, res=None, pre=None, pre_seg=None, alpha=1.0, ln=None, dtype=None, B=None,
+               rows=None, tag=None):
+        """y = act(alpha * sum_s (x_s[t + off_s] + pos_s) W_s^T + bias + pre[idx]) + res.  W: Wt (shared) or Var ([B,N,K] per video);
+        bias: Wt [N] or Var [B,N]; pre: Var of rows gathered by pre_seg['label'] (a segmentation dict) or taken row for row."""
+        assert not (relu and res is not None), 'ReLU and residual in one training GEMM: the mask would need the pre-residual value'
+        x0 = srcs[0]['x']
+        B = x0.v.shape[0] if B is None else B
+        rows = x0.v.shape[1] if rows is None else rows
+        dtype = dtype or (self.act if x0.v.dtype == torch.bfloat16 else torch.float32)
+        y = Var(self.new((B, rows, N), dtype), ln)
+        wv = lambda W: W.v if isinstance(W, Var) else W.w
+        ss = [S(s['x'].v, wv(s['W']), K=s['K'], off=s['off'], pos=s['pos'], pos_idx=s['pos_idx']) for s in srcs]
+        bv = None if bias is None else (bias.v if isinstance(bias, Var) else bias.w)
+        self.mm(ss, N, y.v, len=ln, bias=bv, relu=relu, res=None if res is None else res.v, alpha=alpha,
+                pre=None if pre is None else pre.v, pre_idx=None if pre_seg is None else pre_seg['label'], tag=tag)
+
+        def bwd():
+            if y.g is None:
+                return
+            dz = y.g
+            if res is not None and res.needs_grad:
+                ops.ew(ops.EW_AXPY, dz, self.G(res), N, len=ln)
+            if relu:
+                ops.ew(ops.EW_RELU_BWD, dz, dz, N, r=y.v, len=ln)
+            if bias is not None:
+                if isinstance(bias, Var):
+                    ops.colsum(dz, N, self.G(bias), len=ln, per_video=True)
+                elif bias.g is not None:
+                    ops.colsum(dz, N, bias.g, len=ln)
+            if pre is not None:
+                if pre_seg is None:
+                    ops.ew(ops.EW_AXPY, dz, self.G(pre), N, len=ln)
+                else:
+                    ops.segment_reduce(dz, self.G(pre), pre_seg['start'], pre_seg['len'], pre_seg['nseg'], N, mean=False, accumulate=True)
+            done = set()
+            for i, s in enumerate(srcs):
+                x, Wh = s['x'], s['W']
+                K = s['K'] if s['K'] is not None else wv(Wh).shape[-1]
+                # weight gradient
+                if isinstance(Wh, Var):
+                    ops.wgrad(dz, x.v, N, K, self.G(Wh), off=s['off'], len=ln, alpha=alpha, pos=s['pos'], pos_idx=s['pos_idx'],
+                              per_video=True)
+                elif Wh.g is not None:
+                    ops.wgrad(dz, x.v, N, K, Wh.g, off=s['off'], len=ln, alpha=alpha, pos=s['pos'], pos_idx=s['pos_idx'])
+                # data gradient: every tap of the same x in one multi-source GEMM accumulating into x.g
+                if not x.needs_grad or i in done:
+                    continue
+                group = [j for j, s2 in enumerate(srcs) if s2['x'] is x]
+                done.update(group)
+                gs = []
+                for j in group:
+                    Wj = srcs[j]['W']
+                    Kj = srcs[j]['K'] if srcs[j]['K'] is not None else wv(Wj).shape[-1]
+                    assert Kj == K
+                    if isinstance(Wj, Var):
+                        wt = self.new((Wj.v.shape[0], Kj, N))
+                        ops.transpose(Wj.v[:, :, :Kj], wt)
+                    else:
+                        wt = Wj.T() if Kj == Wj.w.shape[-1] else Wj.w[:, :Kj].t().contiguous()
+                    gs.append(S(dz, wt, off=-srcs[j]['off']))
+                xg = self.G(x)
+                self.mm(gs, K, xg[..., :K] if xg.shape[-1] != K else xg, len=ln, alpha=alpha, res=xg[..., :K] if xg.shape[-1] != K else xg,
+                        tag='dgrad')
+        self.tape.append(bwd)
+        return y
+
+    def mm(self, srcs, N, out, **kw):
+        """GEMM dispatch of the training step: fp32 CUDA-core kernel (the tensor-core variants come with bf16 mode)."""
+        kw = {k: v for k, v in kw.items() if v is not None}
+        return ops.gemm(srcs, N, out, **kw)
+
+    def add(self, a, b, N=None):
+        N = a.v.shape[-1] if N is None else N
+        y = Var(torch.empty_like(a.v), a.len)
+        ops.ew(ops.EW_ADD, a.v, y.v, N, r=b.v, len=a.len)
+
+        def bwd():
+            if y.g is None:
+                return
+            for t in (a, b):
+                if t.needs_grad:
+                    ops.ew(ops.EW_AXPY, y.g, self.G(t), N, len=a.len)
+        self.tape.append(bwd)
+        return y
+
+    def relu(self, x):
+        N = x.v.shape[-1]
+        y = Var(torch.empty_like(x.v), x.len)
+        ops.ew(ops.EW_RELU, x.v, y.v, N, len=x.len)
+
+        def bwd():
+            if y.g is None:
+                return
+            t = torch.empty_like(y.g)
+            ops.ew(ops.EW_RELU_BWD, y.g, t, N, r=y.v, len=x.len)
+            ops.ew(ops.EW_AXPY, t, self.G(x), N, len=x.len)
+        self.tape.append(bwd)
+        return y
+
+    def dropout(self, x, p, channel=False):
+        """nn.Dropout (or nn.Dropout2d over whole channels) in training mode; identity when p == 0."""
+        if p <= 0.0:
+            return x
+        N, site = x.v.shape[-1], self.next_site()
+        op = ops.EW_DROPOUT_CH if channel else ops.EW_DROPOUT
+        y = Var(torch.empty_like(x.v), x.len, needs_grad=x.needs_grad)
+        forced = None if self.forced_masks is None else self.forced_masks.get(site)
+        if forced is not None:          # tests inject the keep mask (already scaled by 1/(1-p)) instead of the hash
+            ops.ew(ops.EW_MUL, x.v, y.v, N, r=forced, len=x.len)
+        else:
+            ops.ew(op, x.v, y.v, N, len=x.len, p=p, seed=self.seed + self.step_no, site=site)
+
+        def bwd():
+            if y.g is None or not x.needs_grad:
+                return
+            t = torch.empty_like(y.g)
+            if forced is not None:
+                ops.ew(ops.EW_MUL, y.g, t, N, r=forced, len=x.len)
+            else:
+                ops.ew(op, y.g, t, N, len=x.len, p=p, seed=self.seed + self.step_no, site=site)
+            ops.ew(ops.EW_AXPY, t, self.G(x), N, len=x.len)
+        self.tape.append(bwd)
+        return y
+
+    def addpos(self, x, qpos):
+        """add_positional_encoding (basic.py:313-320) with a learned table: y = x, y[..., :d] += qpos (d = table width)."""
+        if qpos is None:
+            return x
+        d, H = qpos.w.shape[-1], x.v.shape[-1]
+        y = Var(x.v.clone(), x.len)
+        ops.ew(ops.EW_AXPY, qpos.w, y.v, d, bcast=True)
+
+        def bwd():
+            if y.g is None:
+                return
+            ops.ew(ops.EW_AXPY, y.g, self.G(x), H)
+            if qpos.g is not None:
+                B, M = y.g.shape[0], y.g.shape[1]
+                if y.g.is_contiguous() and d == H:
+                    ops.colsum(y.g.view(1, B, M * H), M * H, qpos.g.view(-1))
+                else:
+                    tmp = self.new((1, M, H))
+                    ops.colsum(y.g.reshape(1, B, M * H), M * H, tmp.view(-1), accumulate=False)
+                    ops.ew(ops.EW_AXPY, tmp, qpos.g.view(1, M, d), d)
+        self.tape.append(bwd)
+        return y
+
+    def layernorm(self, x, wname, bname, res=None, relu=False, ln=None):
+        w, b = self.W(wname), self.W(bname)
+        E = x.v.shape[-1]
+        y = Var(torch.empty_like(x.v), ln)
+        ops.layernorm(x.v, w.w, b.w, y.v, res=None if res is None else res.v, relu=relu, len=ln)
+
+        def bwd():
+            if y.g is None:
+                return
+            dv = self.new(x.v.shape, y.g.dtype)
+            ops.layernorm_bwd(x.v, w.w, b.w, y.g, dv, w.g, b.g, res=None if res is None else res.v, relu=relu, len=ln)
+            for t in (x, res):
+                if t is not None and t.needs_grad:
+                    ops.ew(ops.EW_AXPY, dv, self.G(t), E, len=ln)
+        self.tape.append(bwd)
+        return y
+
+    def splice(self, x, n, ln=None, want_pred=False):
+        """Block.process_feature (blocks.py:195-202) in place on x's storage -> (spliced rows Var, raw logits Var, argmax)."""
+        B, rows, H = x.v.shape
+        clogit = Var(self.new((B, rows, n)), ln)
+        pred = self.new((B, rows), torch.int32) if want_pred else None
+        ops.softmax_splice(x.v, n, clogit.v, pred, len=ln)
+        y = Var(x.v, ln)
+
+        def bwd():
+            if y.g is None and clogit.g is None:
+                return
+            x.g = self.new(x.v.shape, x.v.dtype)
+            ops.splice_bwd(y.v, y.g, clogit.g, x.g, H, n, len=ln)
+        self.tape.append(bwd)
+        return y, clogit, pred
+
+    def l2norm(self, x, ln=None):
+        y = Var(torch.empty_like(x.v), ln)
+        ops.l2norm(x.v, y.v, len=ln)
+
+        def bwd():
+            if y.g is None:
+                return
+            x.g = self.new(x.v.shape, x.v.dtype)
+            ops.l2norm_bwd(x.v, y.g, x.g, len=ln)
+        self.tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ attention
+    def mha_self(self, q, k, v, nhead, p_drop=0.0):
+        """Token self-attention core of nn.MultiheadAttention (basic.py:437,500): per head logits GEMM -> row softmax ->
+        (attention dropout) -> apply GEMM, every operand a [B, M, *] rows tensor; q, k, v: Vars [B, M, A]."""
+        B, M, A = q.v.shape
+        dh, Mp = A // nhead, _round_up(M, 4)
+        alpha = 1.0 / math.sqrt(dh)
+        hs = lambda t, h: t[:, :, h * dh:(h + 1) * dh]
+        hm = lambda t, h: t[:, :, h * Mp:(h + 1) * Mp]
+        L_ = self.new((B, M, nhead * Mp), zero=True)
+        for h in range(nhead):
+            ops.gemm([S(hs(q.v, h), hs(k.v, h))], M, hm(L_, h), alpha=alpha)
+        Pv = Var(self.new((B, M, nhead * Mp), zero=True))
+        Pr = Pv.v.view(B, M * nhead, Mp)
+        ops.row_softmax(L_.view(B, M * nhead, Mp), Pr, M)
+        del L_
+
+        def bwd_softmax():                       # P -> logits -> q, k
+            if Pv.g is None:
+                return
+            dL = self.new((B, M, nhead * Mp), zero=True)
+            ops.row_softmax_bwd(Pr, Pv.g.view(B, M * nhead, Mp), dL.view(B, M * nhead, Mp), M)
+            kT, qg, kg = self.new((B, A, Mp), zero=True), self.G(q), self.G(k)
+            ops.transpose(k.v, kT[:, :, :M])
+            for h in range(nhead):
+                ops.gemm([S(hm(dL, h), kT[:, h * dh:(h + 1) * dh, :], K=M)], dh, hs(qg, h), alpha=alpha, res=hs(qg, h))
+                ops.wgrad(hm(dL, h), hs(q.v, h), M, dh, hs(kg, h), alpha=alpha, per_video=True)
+        self.tape.append(bwd_softmax)
+        Pd = self.dropout(Pv, p_drop)            # nn.MultiheadAttention drops attention weights (its own tape entry)
+        vT = self.new((B, A, Mp), zero=True)
+        ops.transpose(v.v, vT[:, :, :M])
+        o = Var(self.new((B, M, A)))
+        for h in range(nhead):
+            ops.gemm([S(hm(Pd.v, h), vT[:, h * dh:(h + 1) * dh, :], K=M)], dh, hs(o.v, h))
+
+        def bwd_apply():                         # o -> P, v
+            if o.g is None:
+                return
+            dP, vg = self.G(Pd), self.G(v)
+            for h in range(nhead):
+                ops.gemm([S(hs(o.g, h), hs(v.v, h))], M, hm(dP, h), res=hm(dP, h))
+                ops.wgrad(hm(Pd.v, h), hs(o.g, h), M, dh, hs(vg, h), per_video=True)
+        self.tape.append(bwd_apply)
+        return o
+
+    def cross_attn(self, q, kk, vv, nhead, rlen, p_drop=0.0):
+        """Tokens attend rows (SCALayer cross attention core, basic.py:507-514): softmax over the valid rows per (head, token).
+        q: Var [B, M, A] (projected queries); kk, vv: Vars [B, slot, A] (projected keys / values, fp32)."""
+        B, M, A = q.v.shape
+        slot = kk.v.shape[1]
+        dh, Mp = A // nhead, _round_up(M, 4)
+        alpha = 1.0 / math.sqrt(dh)
+        hs = lambda t, h: t[:, :, h * dh:(h + 1) * dh]
+        hm = lambda t, h: t[:, :, h * Mp:(h + 1) * Mp]
+        L_ = self.new((B, slot, nhead * Mp), zero=True)
+        for h in range(nhead):
+            ops.gemm([S(hs(kk.v, h), hs(q.v, h))], M, hm(L_, h), len=rlen, alpha=alpha)
+        Pv = Var(self.new((B, slot, nhead * Mp), zero=True), rlen)
+        ops.col_softmax(L_, Pv.v, nhead * Mp, len=rlen)
+        del L_
+
+        def bwd_softmax():
+            if Pv.g is None:
+                return
+            dL = Pv.g                                   # in place: element-wise in P and dP once the column sums exist
+            ops.col_softmax_bwd(Pv.v, Pv.g, dL, nhead * Mp, len=rlen)
+            qT, kg, qg = self.new((B, A, Mp), zero=True), self.G(kk), self.G(q)
+            ops.transpose(q.v, qT[:, :, :M])
+            for h in range(nhead):
+                ops.gemm([S(hm(dL, h), qT[:, h * dh:(h + 1) * dh, :], K=M)], dh, hs(kg, h), len=rlen, alpha=alpha, res=hs(kg, h))
+                ops.wgrad(hm(dL, h), hs(kk.v, h), M, dh, hs(qg, h), len=rlen, alpha=alpha, per_video=True)
+        self.tape.append(bwd_softmax)
+        Pd = self.dropout(Pv, p_drop)
+        o = Var(self.new((B, M, A)))
+        for h in range(nhead):
+            ops.wgrad(hm(Pd.v, h), hs(vv.v, h), M, dh, hs(o.v, h), len=rlen, accumulate=False, per_video=True)
+
+        def bwd_apply():
+            if o.g is None:
+                return
+            dP, vg = self.G(Pd), self.G(vv)
+            oT = self.new((B, A, Mp), zero=True)
+            ops.transpose(o.g, oT[:, :, :M])
+            for h in range(nhead):
+                ops.gemm([S(hs(vv.v, h), hs(o.g, h))], M, hm(dP, h), len=rlen, res=hm(dP, h))
+                ops.gemm([S(hm(Pd.v, h), oT[:, h * dh:(h + 1) * dh, :], K=M)], dh, hs(vg, h), len=rlen, res=hs(vg, h))
+        self.tape.append(bwd_apply)
+        return o
+
+    # ------------------------------------------------------------------ frame branch
+    def _m2_fold(self, pfx, i, Lr, groups):
+        """Folded MSTCN++ layer (see FactEngine._m2_fold) as a differentiable function of the six parameters."""
+        def dense(name):
+            w = self.P(name)
+            if groups > 1:
+                co, ci = w.shape[0] // groups, w.shape[1]
+                full = w.new_zeros(w.shape[0], ci * groups, w.shape[2])
+                for j in range(groups):
+                    full[j * co:(j + 1) * co, j * ci:(j + 1) * ci] = w[j * co:(j + 1) * co]
+                w = full
+            return w.double()
+        w1, w2 = dense(f'{pfx}conv_dilated_1.{i}.weight'), dense(f'{pfx}conv_dilated_2.{i}.weight')     # (F, F, 3)
+        b1, b2 = self.P(f'{pfx}conv_dilated_1.{i}.bias').double(), self.P(f'{pfx}conv_dilated_2.{i}.bias').double()
+        wf, bf = self.P(f'{pfx}conv_fusion.{i}.weight')[:, :, 0].double(), self.P(f'{pfx}conv_fusion.{i}.bias').double()
+        F = w1.shape[0]
+        A1, A2 = wf[:, :F], wf[:, F:]
+        d1, d2 = 2 ** (Lr - 1 - i), 2 ** i
+        acc = {}
+        for k in range(3):
+            acc[(k - 1) * d1] = acc.get((k - 1) * d1, 0) + A1 @ w1[:, :, k]
+            acc[(k - 1) * d2] = acc.get((k - 1) * d2, 0) + A2 @ w2[:, :, k]
+        Wt_ = torch.stack([acc[o] for o in self._m2_offsets(i, Lr)]).float()
+        bt = (A1 @ b1 + A2 @ b2 + bf).float()
+        return Wt_, bt
+
+    def frame_branch_t(self, pfx, bc, x, in_map, ln):
+        F, H, Lr, C = bc['f_dim'], bc['hid_dim'], bc['f_layers'], self.ncls()
+        m2, ng, p = bc['f'] == 'm2', bc['f_ngp'], float(bc['dropout'])
+        cur = x
+        if in_map:
+            w = pfx + ('conv_1x1_in' if m2 else 'conv_1x1')
+            cur = self.linear([src(x, self.taps_w(w + '.weight')[0])], F, bias=self.W(w + '.bias'), ln=ln, tag='in_proj')
+        for i in range(Lr):
+            if not m2:
+                q = f'{pfx}layers.{i}.'
+                w3, d = self.taps_w(q + 'conv_dilated.weight', ng), 2 ** i
+                h = self.linear([src(cur, w3[k], off=(k - 1) * d) for k in range(3)], F, bias=self.W(q + 'conv_dilated.bias'),
+                                relu=True, ln=ln, tag='tcn_conv3')
+                w1 = self.taps_w(q + 'conv_1x1.weight')[0]
+                if p > 0:
+                    t = self.linear([src(h, w1)], F, bias=self.W(q + 'conv_1x1.bias'), ln=ln, tag='tcn_1x1')
+                    nxt = self.add(cur, self.dropout(t, p))
+                else:
+                    nxt = self.linear([src(h, w1)], F, bias=self.W(q + 'conv_1x1.bias'), res=cur, ln=ln, tag='tcn_1x1')
+                if bc['f_ln']:
+                    nxt = self.layernorm(nxt, q + 'norm.weight', q + 'norm.bias', ln=ln)
+            else:
+                offs = self._m2_offsets(i, Lr)
+                Wf = self.D(('m2fold_w', pfx, i), lambda: self._m2_fold(pfx, i, Lr, ng)[0])
+                bf = self.D(('m2fold_b', pfx, i), lambda: self._m2_fold(pfx, i, Lr, ng)[1])
+                f = self.linear([src(cur, Wf[j], off=o) for j, o in enumerate(offs)], F, bias=bf, relu=True, ln=ln, tag='tcn_m2')
+                if i != Lr - 1:
+                    f = self.dropout(f, p)
+                nxt = self.add(f, cur)
+            cur = nxt
+        out = self.linear([src(cur, self.taps_w(pfx + 'conv_out.weight')[0])], H, bias=self.W(pfx + 'conv_out.bias'), ln=ln, tag='conv_out')
+        return self.splice(out, C, ln=ln, want_pred=True)
+
+    # ------------------------------------------------------------------ token side
+    def _mha_block(self, pfx, x, qpos, nhead, p):
+        """q = k = x + pos, v = x through the packed in_proj (basic.py:437,500) + out_proj; returns the attention output."""
+        A = x.v.shape[-1]
+        Win, bin_ = self.W(pfx + 'in_proj_weight'), self.W(pfx + 'in_proj_bias')
+        xq = self.addpos(x, qpos)
+        qk = self.linear([src(xq, Win[:2 * A])], 2 * A, bias=bin_[:2 * A])
+        v = self.linear([src(x, Win[2 * A:])], A, bias=bin_[2 * A:])
+        o = self.mha_self(self.cols(qk, 0, A), self.cols(qk, A, 2 * A), v, nhead, p)
+        return self.linear([src(o, self.W(pfx + 'out_proj.weight'))], A, bias=self.W(pfx + 'out_proj.bias'))
+
+    def _ffn(self, q, x, p):
+        ff = self.P(q + 'linear1.weight').shape[0]
+        A = x.v.shape[-1]
+        h = self.linear([src(x, self.W(q + 'linear1.weight'))], ff, bias=self.W(q + 'linear1.bias'), relu=True)
+        h = self.dropout(h, p)
+        return self.linear([src(h, self.W(q + 'linear2.weight'))], A, bias=self.W(q + 'linear2.bias'))
+
+    def sca_decoder_t(self, pfx, bc, frame, rlen, pos_idx=None):
+        B, M, A, H, nh, p = self.B, self.ntok, bc['a_dim'], bc['hid_dim'], bc['a_nhead'], float(bc['dropout'])
+        qpos = self.qpos_w()
+        tgt = Var(self.new((B, M, A), zero=True), needs_grad=False)
+        for i in range(bc['a_layers']):
+            q = f'{pfx}layers.{i}.'
+            t2 = self._mha_block(q + 'self_attn.', tgt, qpos, nh, p)
+            tgt = self.layernorm(self.dropout(t2, p), q + 'norm1.weight', q + 'norm1.bias', res=tgt)
+            c = q + 'multihead_attn.'
+            cb = self.W(c + 'in_proj_bias')
+            if (c + 'in_proj_weight') in self._params:
+                Wc = self.W(c + 'in_proj_weight')
+                wq, wk, wv = Wc[:A], Wc[A:2 * A], Wc[2 * A:]
+            else:
+                wq, wk, wv = self.W(c + 'q_proj_weight'), self.W(c + 'k_proj_weight'), self.W(c + 'v_proj_weight')
+            cq = self.linear([src(self.addpos(tgt, qpos), wq)], A, bias=cb[:A])
+            kk = self.linear([src(frame, wk, pos=self.frame_pos, pos_idx=pos_idx)], A, bias=cb[A:2 * A], ln=rlen, dtype=torch.float32, tag='sca_kv')
+            vv = self.linear([src(frame, wv)], A, bias=cb[2 * A:], ln=rlen, dtype=torch.float32, tag='sca_kv')
+            o = self.cross_attn(cq, kk, vv, nh, rlen, p)
+            t2 = self.linear([src(o, self.W(c + 'out_proj.weight'))], A, bias=self.W(c + 'out_proj.bias'))
+            tgt = self.layernorm(self.dropout(t2, p), q + 'norm2.weight', q + 'norm2.bias', res=tgt)
+            t2 = self._ffn(q, tgt, p)
+            tgt = self.layernorm(self.dropout(t2, p), q + 'norm3.weight', q + 'norm3.bias', res=tgt)
+        t = self.layernorm(tgt, pfx + 'norm.weight', pfx + 'norm.bias')
+        return self.linear([src(t, self.W(pfx + 'out_linear.weight'))], H, bias=self.W(pfx + 'out_linear.bias'))
+
+    def sa_decoder_t(self, pfx, bc, x):
+        A, H, nh, p = bc['a_dim'], bc['hid_dim'], bc['a_nhead'], float(bc['dropout'])
+        qpos = self.qpos_w()
+        for i in range(bc['a_layers']):
+            q = f'{pfx}layers.{i}.'
+            t2 = self._mha_block(q + 'multihead_attn.', x, qpos, nh, p)
+            x = self.layernorm(self.dropout(t2, p), q + 'norm1.weight', q + 'norm1.bias', res=x)
+            t2 = self._ffn(q, x, p)
+            x = self.layernorm(self.dropout(t2, p), q + 'norm2.weight', q + 'norm2.bias', res=x)
+        return self.linear([src(x, self.W(pfx + 'out_linear.weight'))], H, bias=self.W(pfx + 'out_linear.bias'))
+
+    def qpos_w(self):
+        h = self._wt.get('qpos')
+        if h is None:
+            a = self.W('action_query')
+            h = self._wt['qpos'] = Wt(a.w[:, 0], a.g[:, 0])
+        return h
+
+    # ------------------------------------------------------------------ X2Y_map (basic.py:349-389)
+    def _x2y_logit(self, pfx, rows, rlen, pos_idx, action, q_name, k_name):
+        """logit[t, m] = (rows[t] + pos) . (alpha Wr^T tq[m]) + alpha tq[m] . br with tq = Linear_t(action + qpos): the
+        projection of all rows (Linear_r, weight Wr / bias br) is never formed.  f2a: t = Y_Q, r = X_K; a2f: t = X_K, r = Y_Q."""
+        H, M = rows.v.shape[-1], self.ntok
+        alpha = 1.0 / math.sqrt(H)
+        tq = self.linear([src(self.addpos(action, self.qpos_w()), self.W(pfx + q_name + '.weight'))], H, bias=self.W(pfx + q_name + '.bias'))
+        WrT = self.D(('tr', pfx + k_name), lambda: self.P(pfx + k_name + '.weight').t())
+        br = self.D(('b1', pfx + k_name), lambda: self.P(pfx + k_name + '.bias')[None, :])
+        qt = self.linear([src(tq, WrT)], H, alpha=alpha)
+        cb = self.linear([src(tq, br)], 1, alpha=alpha)
+        Mp = _round_up(M, 4)
+        logit = Var(self.new((self.B, self.slot, Mp), zero=True), rlen)
+        cbv = Var(cb.v[:, :, 0], None, None)
+        ops.gemm([S(rows.v, qt.v, pos=self.frame_pos, pos_idx=pos_idx)], M, logit.v, len=rlen, bias=cbv.v)
+
+        def bwd():
+            if logit.g is None:
+                return
+            ops.colsum(logit.g, M, self.G(cb)[:, :, 0], len=rlen, per_video=True)
+            ops.wgrad(logit.g, rows.v, M, H, self.G(qt), len=rlen, pos=self.frame_pos, pos_idx=pos_idx, per_video=True)
+            if rows.needs_grad:
+                qT = self.new((self.B, H, Mp), zero=True)
+                ops.transpose(qt.v, qT[:, :, :M])
+                rg = self.G(rows)
+                self.mm([S(logit.g, qT, K=M)], H, rg, len=rlen, res=rg)
+        self.tape.append(bwd)
+        return logit
+
+    def f2a_t(self, pfx, bc, rows, rlen, pos_idx, action):
+        M, A, H, p = self.ntok, bc['a_dim'], bc['hid_dim'], float(bc['dropout'])
+        logit = self._x2y_logit(pfx, rows, rlen, pos_idx, action, 'Y_Q', 'X_K')
+        Mp = logit.v.shape[-1]
+        attn = Var(self.new((self.B, self.slot, Mp), zero=True), rlen)
+        ops.col_softmax(logit.v, attn.v, M, len=rlen)
+        xbar = Var(self.new((self.B, M, H)))
+        ops.wgrad(attn.v, rows.v, M, H, xbar.v, len=rlen, accumulate=False, per_video=True)
+
+        def bwd():
+            if xbar.g is None:
+                return
+            dA = self.new((self.B, self.slot, Mp), zero=True)
+            ops.gemm([S(rows.v, xbar.g)], M, dA, len=rlen)
+            if rows.needs_grad:
+                xT = self.new((self.B, H, Mp), zero=True)
+                ops.transpose(xbar.g, xT[:, :, :M])
+                rg = self.G(rows)
+                self.mm([S(attn.v, xT, K=M)], H, rg, len=rlen, res=rg)
+            ops.col_softmax_bwd(attn.v, dA, self.G(logit), M, len=rlen, accumulate=True)
+        self.tape.append(bwd)
+        feat = self.linear([src(xbar, self.W(pfx + 'X_V.weight'))], H, bias=self.W(pfx + 'X_V.bias'))
+        Wy = self.W(pfx + 'Y_W.weight')
+        out = self.linear([src(self.dropout(action, p), Wy[:, :H]), src(self.dropout(feat, p), Wy[:, H:])], A, bias=self.W(pfx + 'Y_W.bias'))
+        return out, logit, attn
+
+    def a2f_t(self, pfx, bc, action, rows, rlen, pos_idx):
+        M, F, H, p = self.ntok, bc['f_dim'], bc['hid_dim'], float(bc['dropout'])
+        logit = self._x2y_logit(pfx, rows, rlen, pos_idx, action, 'X_K', 'Y_Q')
+        Mp = logit.v.shape[-1]
+        attn = Var(self.new((self.B, self.slot, Mp), zero=True), rlen)
+        ops.row_softmax(logit.v, attn.v, M, len=rlen)
+
+        def bwd():
+            if attn.g is None:
+                return
+            ops.row_softmax_bwd(attn.v, attn.g, self.G(logit), M, len=rlen, accumulate=True)
+        self.tape.append(bwd)
+        xv = self.linear([src(action, self.W(pfx + 'X_V.weight'))], H, bias=self.W(pfx + 'X_V.bias'))
+        xvT = Var(self.new((self.B, H, Mp), zero=True))
+        ops.transpose(xv.v, xvT.v[:, :, :M])
+
+        def bwd_t():
+            if xvT.g is None:
+                return
+            t = self.new((self.B, M, H))
+            ops.transpose(xvT.g[:, :, :M], t)
+            ops.ew(ops.EW_AXPY, t, self.G(xv), H)
+        self.tape.append(bwd_t)
+        u = self.linear([src(attn, xvT, K=M)], H, ln=rlen, dtype=torch.float32)
+        Wy = self.W(pfx + 'Y_W.weight')
+        out = self.linear([src(self.dropout(rows, p), Wy[:, :H]), src(self.dropout(u, p), Wy[:, H:])], F, bias=self.W(pfx + 'Y_W.bias'),
+                          ln=rlen, tag='x2y_rows')
+        return out, logit, attn
+
+    # ------------------------------------------------------------------ temporal down / up-sampling
+    def downsample_t(self, i, bc, frame, pred, st):
+        pfx = f'block_list.{i}.'
+        B, slot, H = self.B, self.slot, bc['hid_dim']
+        Hh, I32 = H // 2, torch.int32
+        seg = dict(label=self.new((B, slot), I32), start=self.new((B, slot), I32), len=self.new((B, slot), I32),
+                   center=self.new((B, slot), I32), nseg=self.new((B,), I32))
+        ops.tdu_segment(pred, seg['label'], seg['start'], seg['len'], seg['center'], seg['nseg'], len=self.len)
+        nseg = seg['nseg']
+        st.update(seg_label=seg['label'], seg_lens=seg['len'], seg_start=seg['start'], nseg=nseg, tdu_pred=pred)
+        seg0 = Var(self.new((B, slot, H), frame.v.dtype), nseg)
+        ops.segment_mean(frame.v, seg0.v, seg['label'], seg['start'], seg['len'], nseg)
+
+        def bwd_mean():
+            if seg0.g is None:
+                return
+            ops.segment_expand(seg0.g, seg['label'], seg['len'], self.G(frame), H, len=self.len, inv_len=True, accumulate=True)
+        self.tape.append(bwd_mean)
+        g = pfx + 'seg_update.'
+        cur = seg0
+        for l in range(self.hp['s_layers']):
+            Wih = self.D(('cat', g, 'w_ih', l), lambda l=l: torch.cat([self.P(f'{g}weight_ih_l{l}'), self.P(f'{g}weight_ih_l{l}_reverse')], 0))
+            bih = self.D(('cat', g, 'b_ih', l), lambda l=l: torch.cat([self.P(f'{g}bias_ih_l{l}'), self.P(f'{g}bias_ih_l{l}_reverse')], 0))
+            gi = self.linear([src(cur, Wih)], 6 * Hh, bias=bih, ln=nseg, dtype=torch.float32, tag='gru_in')
+            cur = self.gru(g, l, gi, nseg)
+        hr = self.relu(cur)
+        seg2 = self.linear([src(hr, self.W(pfx + 'seg_combine.weight'))], H, bias=self.W(pfx + 'seg_combine.bias'), ln=nseg, tag='seg_combine')
+        segf, st['seg_clogit_v'], _ = self.splice(seg2, self.ncls(), ln=nseg)
+        return segf, seg
+
+    def gru(self, g, l, gi, nseg):
+        """One bidirectional GRU layer (forward: the fp32 cluster kernel; backward: gate pre-activations of all steps by one
+        GEMM over the saved hidden states, then BPTT, then weight / bias gradients by the generic kernels)."""
+        B, slot = gi.v.shape[0], gi.v.shape[1]
+        Whf, Whb = self.W(f'{g}weight_hh_l{l}'), self.W(f'{g}weight_hh_l{l}_reverse')
+        bhf, bhb = self.W(f'{g}bias_hh_l{l}'), self.W(f'{g}bias_hh_l{l}_reverse')
+        Hh = Whf.w.shape[1]
+        y = Var(self.new((B, slot, 2 * Hh), zero=True), nseg)
+        ops.gru_bidir(gi.v, Whf.w, bhf.w, Whb.w, bhb.w, y.v, nseg, relu=False)
+
+        def bwd():
+            if y.g is None:
+                return
+            gh = self.new((B, slot, 6 * Hh))
+            ops.gemm([S(y.v[:, :, :Hh], Whf.w, off=-1)], 3 * Hh, gh[:, :, :3 * Hh], len=nseg, bias=bhf.w)
+            ops.gemm([S(y.v[:, :, Hh:], Whb.w, off=1)], 3 * Hh, gh[:, :, 3 * Hh:], len=nseg, bias=bhb.w)
+            gi.g = self.new((B, slot, 6 * Hh))
+            dgh = self.new((B, slot, 6 * Hh))
+            ops.gru_bwd(gi.v, gh, y.v, y.g, Whf.w, Whb.w, gi.g, dgh, nseg)
+            ops.wgrad(dgh[:, :, :3 * Hh], y.v[:, :, :Hh], 3 * Hh, Hh, Whf.g, off=-1, len=nseg)
+            ops.wgrad(dgh[:, :, 3 * Hh:], y.v[:, :, Hh:], 3 * Hh, Hh, Whb.g, off=1, len=nseg)
+            ops.colsum(dgh[:, :, :3 * Hh], 3 * Hh, bhf.g, len=nseg)
+            ops.colsum(dgh[:, :, 3 * Hh:], 3 * Hh, bhb.g, len=nseg)
+        self.tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ blocks
+    def token_splice_t(self, action):
+        y, cl, _ = self.splice(action, self.ncls(tokens=True))
+        return y, cl
+
+    def input_block_t(self, i, bc, x, st):
+        pfx = f'block_list.{i}.'
+        frame, st['frame_clogit_v'], st['pred'] = self.frame_branch_t(pfx + 'frame_branch.', bc, x, True, self.len)
+        action = self.sca_decoder_t(pfx + 'action_branch.', bc, frame, self.len)
+        action, st['action_clogit_v'] = self.token_splice_t(action)
+        return frame, action
+
+    def update_block_t(self, i, bc, frame, action, st):
+        pfx = f'block_list.{i}.'
+        tok, st['f2a_logit_v'], f2a_attn = self.f2a_t(pfx + 'f2a_layer.', bc, frame, self.len, None, action)
+        st['f2a_attn'] = f2a_attn.v
+        action = self.sa_decoder_t(pfx + 'action_branch.', bc, tok)
+        action, st['action_clogit_v'] = self.token_splice_t(action)
+        fr, st['a2f_logit_v'], a2f_attn = self.a2f_t(pfx + 'a2f_layer.', bc, action, frame, self.len, None)
+        st['a2f_attn'] = a2f_attn.v
+        frame, st['frame_clogit_v'], st['pred'] = self.frame_branch_t(pfx + 'frame_branch.', bc, fr, False, self.len)
+        return frame, action
+
+    def update_block_tdu_t(self, i, bc, frame, action, pred, st):
+        pfx = f'block_list.{i}.'
+        F = bc['f_dim']
+        seg2, seg = self.downsample_t(i, bc, frame, pred, st)
+        nseg = seg['nseg']
+        pidx = seg['center'] if self.frame_pos is not None else None
+        tok, st['f2a_logit_v'], f2a_attn = self.f2a_t(pfx + 'f2a_layer.', bc, seg2, nseg, pidx, action)
+        st['f2a_attn_seg'] = f2a_attn.v
+        action = self.sa_decoder_t(pfx + 'action_branch.', bc, tok)
+        action, st['action_clogit_v'] = self.token_splice_t(action)
+        seg3, st['a2f_logit_v'], a2f_attn = self.a2f_t(pfx + 'a2f_layer.', bc, action, seg2, nseg, pidx)
+        st['a2f_attn_seg'] = a2f_attn.v
+        Wm = self.W(pfx + 'sf_merge.0.weight')                                  # [F, F+H], input = cat[s2f, frame]
+        s2f = self.linear([src(seg3, Wm[:, :F])], F, ln=nseg, dtype=torch.float32, tag='sf_merge')
+        fr = self.linear([src(frame, Wm[:, F:])], F, bias=self.W(pfx + 'sf_merge.0.bias'), relu=True, pre=s2f, pre_seg=seg, ln=self.len,
+                         tag='sf_merge')
+        frame, st['frame_clogit_v'], st['pred'] = self.frame_branch_t(pfx + 'frame_branch.', bc, fr, False, self.len)
+        return frame, action
+
+    # ------------------------------------------------------------------ whole step
+    @staticmethod
+    def time_mask_spans(T, cfg_tm):
+        """basic.time_mask (basic.py:10-36) with replace_with_zero=True: TM.m spans, each of length
+        min(int(TM.p * T), randrange(TM.t)) at start randrange(T - length); a zero-length draw ENDS the masking (the
+        reference returns there).  Same calls to Python's ``random`` in the same order as the reference."""
+        spans = []
+        for _ in range(int(cfg_tm.m)):
+            t = random.randrange(0, int(cfg_tm.t))
+            t = min(int(float(cfg_tm.p) * T), t)
+            t0 = random.randrange(0, T - t)
+            if t == 0:
+                break
+            spans.append((t0, t0 + t))
+        return spans
+
+    def forward_train(self, seqs, forced_preds=None):
+        """Train-mode forward of a batch.  Returns the ``out`` dict of FactEngine.run_packed (values) with the Vars of every
+        tensor the loss reads under ``*_v`` keys."""
+        self._refresh_weights()
+        self.begin()
+        hp, cfg = self.hp, self.m.cfg
+        self.ntok, self.action_init, self.transcript = hp['ntoken'], None, None
+        lengths = [int(s.shape[0]) for s in seqs]
+        B, slot, D = len(seqs), _round_up(max(lengths), 128), hp['in_dim']
+        self._set_arena(('train', B, slot))
+        self.B, self.slot, self.keep = B, slot, True
+        x = self.new((B, slot, D), torch.float32, zero=True)
+        for b, s in enumerate(seqs):
+            x[b, :lengths[b]].copy_(s, non_blocking=True)
+        ln = self.new((B,), torch.int32)
+        ln.copy_(torch.tensor(lengths, dtype=torch.int32), non_blocking=True)
+        self.len = ln
+        C, H = hp['n_classes'], hp['blocks'][0]['hid_dim']
+        self.frame_pos = self.derived(('pe', slot, H), lambda: _pos_table(H, slot, self.dev)) if hp['fpos'] else None
+        xin = Var(x, ln, needs_grad=False)
+        if float(cfg.FACT.cmr) > 0:                        # nn.Dropout2d over whole feature channels (blocks.py:614-617)
+            xin = self.dropout(xin, float(cfg.FACT.cmr), channel=True)
+        if cfg.TM.use:                                     # time_mask in place on the (already channel-masked) features
+            for b, T in enumerate(lengths):
+                for t0, t1 in self.time_mask_spans(T, cfg.TM):
+                    xin.v[b, t0:t1].zero_()
+        frame, action, stash, u, pred = xin, None, [], 0, None
+        for i, bc in enumerate(hp['blocks']):
+            st = {}
+            if bc['type'] == 'i':
+                frame, action = self.input_block_t(i, bc, frame, st)
+            elif bc['type'] == 'u':
+                frame, action = self.update_block_t(i, bc, frame, action, st)
+            elif bc['type'] == 'U':
+                if forced_preds is not None:
+                    fp = self.new((B, slot), torch.int32, zero=True)
+                    for b in range(B):
+                        fp[b, :lengths[b]].copy_(forced_preds[u][b].to(torch.int32), non_blocking=True)
+                    pred = fp
+                frame, action = self.update_block_tdu_t(i, bc, frame, action, pred, st)
+                u += 1
+            else:
+                raise NotImplementedError(f'training step: block type {bc["type"]!r}')
+            pred = st['pred']
+            st['frame_feature'], st['action_feature'] = frame.v, action.v
+            for k in ('frame_clogit', 'action_clogit', 'seg_clogit', 'f2a_logit', 'a2f_logit'):
+                if k + '_v' in st:      # plain tensors under the inference engine's keys (LossRunner, stash_video, eval)
+                    st[{'f2a_logit': 'f2a_attn_logit', 'a2f_logit': 'a2f_attn_logit'}.get(k, k)] = st[k + '_v'].v
+            stash.append(st)
+        out = dict(blocks=stash, lengths=lengths)
+        last = stash[-1]
+        if self.clip and self.m.text_embeddings is not None:
+            P = self.P('frame_projection.projection.0.weight').shape[0]
+            w0 = self.D(('clip_w0pad',), lambda: torch.nn.functional.pad(self.P('frame_projection.projection.0.weight'), (0, C)))
+            h1 = self.linear([src(frame, w0)], P, bias=self.W('frame_projection.projection.0.bias'), ln=ln, tag='clip')
+            h2 = self.layernorm(h1, 'frame_projection.projection.1.weight', 'frame_projection.projection.1.bias', relu=True, ln=ln)
+            h2 = self.dropout(h2, float(cfg.CLIP.projection_dropout))
+            e0 = self.linear([src(h2, self.W('frame_projection.projection.4.weight'))], 512, bias=self.W('frame_projection.projection.4.bias'),
+                             ln=ln, dtype=torch.float32, tag='clip')
+            emb = self.l2norm(e0, ln=ln)
+            sim = self.linear([src(emb, self.const(self.m.text_embeddings.detach()))], C, alpha=1.0 / hp['temp'], ln=ln, dtype=torch.float32,
+                              tag='clip')
+            out['projected_frame_embeddings'], out['clip_logit'], out['clip_logit_v'] = emb.v, sim.v, sim
+            flogit = sim.v
+        else:
+            flogit = last['frame_clogit']
+        pred64 = self.new((B, slot), torch.int64, zero=True)
+        M = self.ntok
+        if 'a2f_attn' in last:
+            ops.fuse_eval(last['action_clogit'], last['a2f_attn'], flogit, hp['mwt'], pred64, M, C, len=ln)
+        elif 'a2f_attn_seg' in last:
+            ops.fuse_eval(last['action_clogit'], last['a2f_attn_seg'], flogit, hp['mwt'], pred64, M, C, seg_label=last['seg_label'], len=ln)
+        else:
+            ops.fuse_eval(None, None, flogit, hp['mwt'], pred64, 0, C, len=ln)
+        out['pred'] = pred64
+        return out
+
+    def backward(self, seeds):
+        """seeds: list of (Var, gradient tensor).  Runs the tape; returns {parameter name: gradient} (fp32)."""
+        for var, g in seeds:
+            if var.g is None:
+                var.g = g
+            else:
+                var.g += g
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+        if self._derived:
+            used = [p for p in self._params.values() if p.requires_grad]
+            outs = [t for t, _ in self._derived if t.requires_grad]
+            gouts = [g for t, g in self._derived if t.requires_grad]
+            if outs:
+                gs = torch.autograd.grad(outs, used, gouts, allow_unused=True)
+                names = [n for n, p in self._params.items() if p.requires_grad]
+                for n, g in zip(names, gs):
+                    if g is not None:
+                        if n in self._pg:
+                            self._pg[n] += g
+                        else:
+                            self._pg[n] = g.float()
+        self._derived, self._wt = [], {}
+        return self._pg

