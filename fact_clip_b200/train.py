@@ -52,8 +52,16 @@ class Wt:
 
     def T(self):
         if self._t is None:
-            self._t = self.w.t().contiguous()
+            self._t = dense(self.w.t())
         return self._t
+
+
+def dense(t):
+    """Copy with standard row-major strides (``contiguous()`` keeps odd strides on size-1 dimensions; the kernels take the
+    row stride as the leading dimension)."""
+    out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+    out.copy_(t)
+    return out
 
 
 def src(x, W, off=0, pos=None, pos_idx=None, K=None):
@@ -111,10 +119,9 @@ class TrainEngine(FactEngine):
         if h is None:
             with torch.enable_grad():
                 t = fn()
-            t = t if t.is_contiguous() else t.contiguous()
-            g = torch.zeros_like(t, dtype=torch.float32)
+            g = torch.zeros(t.shape, dtype=torch.float32, device=t.device)
             self._derived.append((t, g))
-            h = self._wt[key] = Wt(t.detach(), g)
+            h = self._wt[key] = Wt(dense(t.detach()), g)
         return h
 
     def P(self, name):
@@ -196,7 +203,7 @@ class TrainEngine(FactEngine):
                         wt = self.new((Wj.v.shape[0], Kj, N))
                         ops.transpose(Wj.v[:, :, :Kj], wt)
                     else:
-                        wt = Wj.T() if Kj == Wj.w.shape[-1] else Wj.w[:, :Kj].t().contiguous()
+                        wt = Wj.T() if Kj == Wj.w.shape[-1] else dense(Wj.w[:, :Kj].t())
                     gs.append(S(dz, wt, off=-srcs[j]['off']))
                 xg = self.G(x)
                 self.mm(gs, K, xg[..., :K] if xg.shape[-1] != K else xg, len=ln, alpha=alpha, res=xg[..., :K] if xg.shape[-1] != K else xg,

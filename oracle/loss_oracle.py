@@ -105,9 +105,9 @@ def match_tokens(crit, action_prob, a2f_attn):
         return idx, idx
     cost = np.zeros((action_prob.shape[0], crit.S), dtype=np.float32)
     if lp['pc'] > 0:
-        cost = cost - lp['pc'] * action_prob[:, crit.transcript].numpy()
+        cost = cost - lp['pc'] * action_prob.detach()[:, crit.transcript].numpy()
     if lp['a2fc'] > 0:
-        cost = cost - lp['a2fc'] * soft_iou(a2f_attn, crit.onehot_seg)
+        cost = cost - lp['a2fc'] * soft_iou(a2f_attn.detach(), crit.onehot_seg)
     if lp['match'] == 'o2o':
         aind, sind = linear_sum_assignment(cost)
     else:

@@ -184,7 +184,6 @@ def test_dropout_mask_is_reproducible_and_unbiased():
     assert torch.equal(y1, y2) and not torch.equal(y1, y3)
     keep = (y1 > 0).float().mean().item()
     assert abs(keep - (1 - p)) < 5e-3 and abs(y1.mean().item() - 1.0) < 1e-2
-    assert set(torch.unique(y1).tolist()) <= {0.0, pytest.approx(1 / (1 - p))} or True
     ch = torch.empty_like(x)
     ops.ew(ops.EW_DROPOUT_CH, x, ch, N, p=p, seed=11, site=6)
     assert torch.equal(ch[:, 0], ch[:, 100])            # one decision per (video, channel): every frame sees the same mask
@@ -237,7 +236,7 @@ def test_gradients_vs_reference_fixtures(name):
     net.mcriterion = _criterion(cfg, g['n_classes'], gr['bg_ids'])
     vids = [g['videos'][i] for i in gr['videos']]
     loss, saves = net([v['x'].to(DEV) for v in vids], [v['label'].to(DEV) for v in vids], compute_loss=True)
-    assert abs(float(loss) - gr['batch_loss']) <= 1e-4 * abs(gr['batch_loss'])
+    assert abs(float(loss.detach()) - gr["batch_loss"]) <= 1e-4 * abs(gr["batch_loss"])
     loss.backward()
     worst = _check_grads(net, gr['grads'], 1e-3, 1e-4)
     print(name, 'worst relative gradient error', worst)
