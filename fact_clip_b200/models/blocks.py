@@ -376,7 +376,7 @@ class _TrainStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, net, out, res, names, value, *params):
-        ctx.net, ctx.out, ctx.res, ctx.names = net, out, res, names
+        ctx.net, ctx.out, ctx.res, ctx.names, ctx.params = net, out, res, names, params
         return value.clone()
 
     @staticmethod
@@ -385,14 +385,20 @@ class _TrainStep(torch.autograd.Function):
         eng = net._train_engine
         dev = next(net.parameters()).device
         with torch.no_grad(), torch.cuda.device(dev):
-            seeds = LossRunner(eng, net.mcriterion).seeds(ctx.out, ctx.res)
+            seeds = LossRunner(eng, net.mcriterion).seeds(ctx.out, ctx.res, scale=float(gout))
             grads = eng.backward(seeds)
-            gl = [grads.get(n) for n in ctx.names]
-            have = [g for g in gl if g is not None]
-            if have:
-                torch._foreach_mul_(have, gout)
+            # hand the gradient views (slices of the per-section flat buffers) to the parameters directly: no copy, and an
+            # in-place all-reduce of a flat buffer is an all-reduce of the .grad tensors
+            ret = []
+            for n, p in zip(ctx.names, ctx.params):
+                g = grads.get(n)
+                if g is None or p.grad is not None:
+                    ret.append(g)
+                else:
+                    p.grad = g
+                    ret.append(None)
         ctx.out = ctx.res = None
-        return (None, None, None, None, None) + tuple(gl)
+        return (None, None, None, None, None) + tuple(ret)
 
 
 def _clone_tree(o):

@@ -81,10 +81,68 @@ class TrainEngine(FactEngine):
     def begin(self):
         self.tape, self._site = [], 0
         self._params = dict(self.m.named_parameters())
-        self._pg = {}                     # parameter name -> fp32 gradient accumulator
-        self._derived = []                # (tensor with autograd graph, gradient accumulator)
+        self._derived = []                # (tensor with autograd graph, gradient accumulator) of the current section
         self._wt = {}
         self.step_no += 1
+        self._layout()
+        for f in self._flat:
+            f.zero_()
+
+    def _layout(self):
+        """Gradient buckets: ONE flat fp32 buffer per section of the model -- block i (+ the action queries in block 0), and
+        the CLIP projection head -- with every parameter's gradient a view into it.  A section's buffer is final as soon as
+        the backward pass has left the section, so a data-parallel all-reduce of it (in place, no packing copy) overlaps the
+        backward pass of the earlier sections."""
+        sig = tuple((n, tuple(p.shape), p.device) for n, p in self._params.items())
+        if getattr(self, '_layout_sig', None) == sig:
+            # a parameter still holding last step's gradient view (no zero_grad(set_to_none=True) in between: gradient
+            # accumulation): leave those buffers to the parameters and start fresh ones
+            if not any(p.grad is not None and p.grad.data_ptr() == self._pg[n].data_ptr() for n, p in self._params.items()):
+                return
+        nb = len(self.hp['blocks'])
+        def section(n):
+            if n.startswith('block_list.'):
+                return int(n.split('.')[1])
+            return nb if n.startswith('frame_projection.') else 0
+        names = [[] for _ in range(nb + 1)]
+        for n in self._params:
+            names[section(n)].append(n)
+        self._flat, self._pg, self._sect_names = [], {}, names
+        for k in range(nb + 1):
+            tot = sum(_round_up(self._params[n].numel(), 4) for n in names[k])
+            flat = torch.zeros(max(tot, 1), dtype=torch.float32, device=self.dev)
+            off = 0
+            for n in names[k]:
+                p = self._params[n]
+                self._pg[n] = flat[off:off + p.numel()].view(p.shape)
+                off += _round_up(p.numel(), 4)
+            self._flat.append(flat)
+        self._layout_sig = sig
+
+    def mark_section(self, k):
+        """Tape marker at the START of section k of the forward pass: when the (reversed) tape reaches it, every gradient
+        contribution to the section's parameters has been launched."""
+        self._derived = []
+        derived = self._derived
+
+        def done():
+            self._finish_derived(derived)
+            hook = getattr(self.m, 'grad_ready_hook', None)
+            if hook is not None:
+                hook(k, self._flat[k], self._sect_names[k])
+        self.tape.append(done)
+
+    def _finish_derived(self, derived):
+        """Carry the gradients of a section's derived weights (parameter-sized differentiable functions) to the parameters."""
+        outs = [t for t, _ in derived if t.requires_grad]
+        if not outs:
+            return
+        gouts = [g for t, g in derived if t.requires_grad]
+        names = [n for n, p in self._params.items() if p.requires_grad]
+        gs = torch.autograd.grad(outs, [self._params[n] for n in names], gouts, allow_unused=True)
+        for n, g in zip(names, gs):
+            if g is not None:
+                self._pg[n] += g
 
     def new(self, shape, dtype=torch.float32, zero=False):
         return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
@@ -103,11 +161,7 @@ class TrainEngine(FactEngine):
         """Parameter as a weight handle (gradient accumulates in a buffer of the parameter's shape)."""
         h = self._wt.get(name)
         if h is None:
-            p = self._params[name]
-            g = self._pg.get(name)
-            if g is None:
-                g = self._pg[name] = torch.zeros_like(p, dtype=torch.float32)
-            h = self._wt[name] = Wt(p.detach(), g)
+            h = self._wt[name] = Wt(self._params[name].detach(), self._pg[name])
         return h
 
     def const(self, t):
@@ -774,6 +828,7 @@ class TrainEngine(FactEngine):
         frame, action, stash, u, pred = xin, None, [], 0, None
         for i, bc in enumerate(hp['blocks']):
             st = {}
+            self.mark_section(i)
             if bc['type'] == 'i':
                 frame, action = self.input_block_t(i, bc, frame, st)
             elif bc['type'] == 'u':
@@ -797,6 +852,7 @@ class TrainEngine(FactEngine):
         out = dict(blocks=stash, lengths=lengths)
         last = stash[-1]
         if self.clip and self.m.text_embeddings is not None:
+            self.mark_section(len(hp['blocks']))
             P = self.P('frame_projection.projection.0.weight').shape[0]
             w0 = self.D(('clip_w0pad',), lambda: torch.nn.functional.pad(self.P('frame_projection.projection.0.weight'), (0, C)))
             h1 = self.linear([src(frame, w0)], P, bias=self.W('frame_projection.projection.0.bias'), ln=ln, tag='clip')
@@ -831,19 +887,5 @@ class TrainEngine(FactEngine):
                 var.g += g
         for fn in reversed(self.tape):
             fn()
-        self.tape = []
-        if self._derived:
-            used = [p for p in self._params.values() if p.requires_grad]
-            outs = [t for t, _ in self._derived if t.requires_grad]
-            gouts = [g for t, g in self._derived if t.requires_grad]
-            if outs:
-                gs = torch.autograd.grad(outs, used, gouts, allow_unused=True)
-                names = [n for n, p in self._params.items() if p.requires_grad]
-                for n, g in zip(names, gs):
-                    if g is not None:
-                        if n in self._pg:
-                            self._pg[n] += g
-                        else:
-                            self._pg[n] = g.float()
-        self._derived, self._wt = [], {}
+        self.tape, self._derived, self._wt = [], [], {}
         return self._pg
