@@ -171,6 +171,113 @@ def run_reference(args):
     }))
 
 
+def run_train(args):
+    """BASELINE config 5: FACT_CLIP training step (train-mode forward + loss + hand-written backward + data-parallel
+    gradient all-reduce over NVLink + clip_grad_norm_ + Adam step, scripts/train.py:262-268) on synthetic
+    Epic-Kitchens-shape videos: epic-kitchens.yaml hyper-parameters with block iUUU, T = 16384, C = 98, one
+    video per GPU per step.  Prints one JSON line (rank 0)."""
+    import torch.distributed as dist
+    from fact_clip_b200 import _lib, config as C, ops
+    from fact_clip_b200.loss import MatchCriterion
+    from fact_clip_b200.models.blocks import FACT_CLIP
+    from fact_clip_b200.parallel import GradAllReducer
+    from fact_clip_b200.utils.synth import make_text_embeddings, make_video
+
+    world, rank, local = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.check(_lib.load().factk_device_check(), 'device_check')
+    T, ncls, D = args.train_frames, 98, IN_DIM
+    cfg = C.PRESETS['epic_shape']()
+    torch.manual_seed(0)
+    net = FACT_CLIP(cfg, D, ncls, make_text_embeddings(ncls))
+    net.compute_mode = args.mode
+    net = net.to(dev).train()
+    net.mcriterion = MatchCriterion(cfg, ncls, [0])
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=0.0)          # epic-kitchens.yaml:74-80
+    red = GradAllReducer()
+    net.grad_ready_hook = red.on_bucket
+    nparam = sum(p.numel() for p in net.parameters())
+    # one pinned host video per rank and step slot (two alternate), copied to the device inside the step
+    hosts = []
+    for k in range(2):
+        x, y = make_video(T, D, ncls, seed=9000 + 2 * rank + k, nseg=args.train_nseg)
+        hosts.append((x.pin_memory(), y.pin_memory()))
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    phases = {'fwd_loss': 0.0, 'bwd': 0.0, 'allreduce_wait': 0.0, 'clip_opt': 0.0}
+    info = {}
+
+    def step(i, timed):
+        x, y = hosts[i % 2]
+        e = [ev() for _ in range(5)]
+        e[0].record()
+        xs, ys = [x.to(dev, non_blocking=True)], [y.to(dev, non_blocking=True)]
+        opt.zero_grad(set_to_none=True)
+        loss, saves = net(xs, ys, compute_loss=True)
+        e[1].record()
+        loss.backward()
+        e[2].record()
+        info['allreduce_bytes'] = red.finish()
+        e[3].record()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 10.0)                   # epic-kitchens.yaml: clip_grad_norm 10.0
+        opt.step()
+        e[4].record()
+        info['loss'] = saves[0]['loss']['loss']
+        info['nseg'] = [int(st['nseg'][0]) for st in net._last['blocks'] if 'nseg' in st]
+        return e
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        step(i, False)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.COUNTERS['launches'] = 0
+    e0, e1 = ev(), ev()
+    e0.record()
+    evs = [step(W + i, True) for i in range(args.steps)]
+    e1.record()
+    barrier()
+    clocks = sampler.summary()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    for e in evs:
+        for k, (a, b) in zip(phases, zip(e[:-1], e[1:])):
+            phases[k] += a.elapsed_time(b) / args.steps
+    frames = T * world * args.steps
+    res = {
+        'metric': 'frames/sec FACT_CLIP training step (T=16384, 2048-d, data parallel)', 'value': frames / (ms * 1e-3), 'unit': UNIT,
+        'n_gpus': world, 'steps': args.steps, 'warmup': W, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': args.mode if args.mode == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': {'workload': f'FACT_CLIP training step, epic-kitchens.yaml shape (block iUUU, MSTCN++, F=A=256, M=300, fpos, o2m matching), '
+                               f'T={T}, D={D}, C={ncls}, one video per GPU per step; train-mode forward + loss + backward + DP all-reduce + '
+                               f'clip_grad_norm_ + Adam step; random-init weights (segments per U block below)',
+                   'segments_per_U_block_rank0': info.get('nseg'), 'params': nparam, 'loss_rank0': info.get('loss'),
+                   'l2_policy': f'inputs larger than L2 ({T * D * 4 / 2**20:.0f} MiB of fp32 features per step; activations far larger)'},
+        'clocks': clocks, 'gpu_launches': ops.COUNTERS['launches'] // args.steps,
+        'e2e': {'value': frames / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': (T * D * 4 + T * 8) * world, 'd2h_bytes_per_step': T * 8 * world,
+                'note': 'the timed step includes the pinned-host -> device copy of the video and the device -> host copy of the predictions and the loss'},
+        'phases_ms_rank0': phases,
+        'allreduce': {'bytes_per_step_per_rank': info.get('allreduce_bytes'), 'buckets': len(cfg.FACT.block) + 1,
+                      'overlap': 'each section (CLIP head, then blocks last to first) is all-reduced in place as soon as the backward pass leaves it',
+                      'wait_ms_after_backward': phases['allreduce_wait']},
+    }
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -183,9 +290,14 @@ def main():
     ap.add_argument('--e2e-split', type=int, default=4, help='sub-batches per step on the end-to-end (pipelined) path')
     ap.add_argument('--no-graph', action='store_true', help='eager kernel launches instead of one CUDA graph per batch')
     ap.add_argument('--profile', action='store_true', help='print a CUDA-event breakdown per kernel family to stderr')
+    ap.add_argument('--train', action='store_true', help='BASELINE config 5: data-parallel training step (Epic-Kitchens shape, T=16384)')
+    ap.add_argument('--train-frames', type=int, default=16384)
+    ap.add_argument('--train-nseg', type=int, default=52, help='ground-truth segments per synthetic training video (epic o2m average)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.train:
+        return run_train(args)
 
     import torch.distributed as dist
     from fact_clip_b200 import _lib, ops

@@ -65,6 +65,38 @@ def gather_predictions(local_ids, local_preds, group=None, dst=0):
     return out
 
 
+class GradAllReducer:
+    """Data-parallel gradient averaging for the training step (the reference trains on one GPU, the training
+    bench of BASELINE config 5 is data parallel: one video per GPU per step).
+
+    ``net.grad_ready_hook = reducer.on_bucket`` -- the training engine calls it with each section's flat gradient buffer as
+    soon as the backward pass has left that section (CLIP head first, input block last); the all-reduce (SUM, in place, NCCL
+    over NVLink on GPUs, gloo in CPU tests) is launched asynchronously and overlaps the rest of the backward pass.
+    ``finish()`` waits for the collectives and divides by the world size: the loss is a mean over videos (blocks.py:130, 914),
+    so with equal videos per rank the averaged gradient IS the single-process batch gradient.  ``clip_grad_norm_`` and the
+    optimizer step (scripts/train.py:266-268) must come after ``finish()``."""
+
+    def __init__(self, group=None):
+        self.group, self.handles, self.buckets = group, [], []
+        self.bytes = 0
+
+    def on_bucket(self, k, flat, names=None):
+        self.buckets.append(flat)
+        self.bytes += flat.numel() * flat.element_size()
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self.handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        for h in self.handles:
+            h.wait()
+        if world > 1 and self.buckets:
+            torch._foreach_mul_(self.buckets, 1.0 / world)
+        n = self.bytes
+        self.handles, self.buckets, self.bytes = [], [], 0
+        return n
+
+
 def _parse_cpulist(text):
     cpus = set()
     for part in text.strip().split(','):
