@@ -251,6 +251,18 @@ def run_train(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
+    if args.profile and rank == 0:
+        ops.TIMER = ops.KernelTimer(None)
+        t0 = time.perf_counter()
+        step(W + args.steps, False)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        prof = ops.TIMER.collect(skip_steps=0, steps=1)
+        ops.TIMER = None
+        tot = sum(v['ms'] for v in prof.values())
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+            sys.stderr.write(f"  {k:28s} n={v['n']:5d} {v['ms']:9.3f} ms {100 * v['ms'] / tot:5.1f}%\n")
+        sys.stderr.write(f"  sum of kernel times {tot:.2f} ms; wall of the profiled step {wall:.1f} ms\n")
     for e in evs:
         for k, (a, b) in zip(phases, zip(e[:-1], e[1:])):
             phases[k] += a.elapsed_time(b) / args.steps

@@ -75,6 +75,9 @@ _SIGS = {
     'factk_wgrad_ws_floats': (C.c_size_t, [i32, i32, i32, i32]),
     'factk_wgrad': (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, i32, C.c_longlong, f32, i32, i32, i32,
                           vp, vp, vp]),
+    'factk_wgrad_tc_supported': (i32, [i32, i32, i32, i32, i32, i32, i32]),
+    'factk_wgrad_tc_ws_floats': (C.c_size_t, [i32, i32, i32, i32]),
+    'factk_wgrad_tc': (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, C.c_longlong, f32, i32, i32, i32, vp, vp, vp]),
     'factk_colsum_ws_floats': (C.c_size_t, [i32, i32, i32]),
     'factk_colsum': (i32, [vp, i32, i32, vp, i32, i32, i32, vp, C.c_longlong, f32, i32, i32, i32, vp, vp, vp]),
     'factk_rows_elementwise': (i32, [i32, vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp, f32, f32, C.c_ulonglong,

@@ -96,6 +96,10 @@ __device__ __forceinline__ float block_max(float v, float* sm) {
     return r;
 }
 
+// Fixed-order sum of per-(video, chunk) partial results (train.cu): out[(b)][i / K][i % K] = alpha * sum (+ out).
+void launch_partial_reduce(const float* ws, size_t pstride, int psz, int K, float* out, int ldo, long long out_bstride, int B, int slot,
+                           const int32_t* len, int nchunk, int rows_per_chunk, float alpha, int accumulate, cudaStream_t st);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace factk

@@ -118,6 +118,13 @@ __global__ void partial_reduce_kernel(const float* __restrict__ ws, size_t pstri
     *o = alpha * s + (accumulate ? *o : 0.f);
 }
 
+void launch_partial_reduce(const float* ws, size_t pstride, int psz, int K, float* out, int ldo, long long out_bstride, int B, int slot,
+                           const int32_t* len, int nchunk, int rows_per_chunk, float alpha, int accumulate, cudaStream_t st) {
+    const int per_video = out_bstride != 0;
+    partial_reduce_kernel<<<dim3((psz + 255) / 256, per_video ? B : 1), 256, 0, st>>>(ws, pstride, psz, K, out, ldo, out_bstride, B, slot, len,
+                                                                                     nchunk, rows_per_chunk, alpha, accumulate, per_video);
+}
+
 // ------------------------------------------------------------------------------------------------ column sums
 // ws[(b, chunk)][n] = sum over the chunk's valid rows of X[b,t,n] (* Y[b,t,n] when Y != NULL)
 __global__ void colsum_partial_kernel(const void* __restrict__ X, int x_dtype, int ldx, const void* __restrict__ Y, int y_dtype,

@@ -376,13 +376,21 @@ def _ws(dev, n):
     return t
 
 
-def wgrad(dz, a, N, K, dw, off=0, len=None, alpha=1.0, accumulate=True, pos=None, pos_d=None, pos_idx=None, per_video=False):
+def wgrad(dz, a, N, K, dw, off=0, len=None, alpha=1.0, accumulate=True, pos=None, pos_d=None, pos_idx=None, per_video=False, tc=False):
     """dw[(b)][n][k] (+)= alpha * sum_rows dz[b,t,n] * (a[b,t+off,k] + pos).  dz / a: rows tensors; dw: [N, K] view (unit
     stride in k), or [B, N, K] with per_video."""
     B, slot = dz.shape[0], dz.shape[1]
     assert dw.stride(-1) == 1 and dw.dtype == torch.float32
     a_slot = 0 if (a.shape[0] == 1 and B > 1) else a.stride(0) // _row_ld(a)
-    ws = _ws(dz.device, L.load().factk_wgrad_ws_floats(B, slot, N, K))
+    lib = L.load()
+    if (tc and pos is None and a_slot > 0 and dz.data_ptr() % 16 == 0 and a.data_ptr() % 16 == 0
+            and lib.factk_wgrad_tc_supported(L.dt(dz), _row_ld(dz), L.dt(a), _row_ld(a), N, K, slot)):
+        ws = _ws(dz.device, lib.factk_wgrad_tc_ws_floats(B, slot, N, K))
+        COUNTERS['launches'] += 2
+        _call('factk_wgrad_tc', 'wgrad_tc', dz.data_ptr(), _row_ld(dz), a.data_ptr(), _row_ld(a), a_slot, int(off), N, K, dw.data_ptr(),
+              dw.stride(-2), dw.stride(0) if per_video else 0, float(alpha), int(accumulate), B, slot, L.ptr(len), ws.data_ptr(), L.stream())
+        return
+    ws = _ws(dz.device, lib.factk_wgrad_ws_floats(B, slot, N, K))
     COUNTERS['launches'] += 2
     _call('factk_wgrad', 'wgrad', dz.data_ptr(), L.dt(dz), _row_ld(dz), a.data_ptr(), L.dt(a), _row_ld(a), a_slot, int(off),
           L.ptr(pos), pos.stride(0) if pos is not None else 0, (pos_d if pos_d is not None else pos.shape[-1]) if pos is not None else 0,

@@ -331,6 +331,16 @@ int factk_wgrad(const void* dZ, int dz_dtype, int lddz, const void* A, int a_dty
                 long long dw_bstride, float alpha, int accumulate, int B, int slot, const int32_t* len, float* ws,
                 void* stream);
 
+/* The same contraction on the tensor cores (csrc/wgrad_tc.cu): bf16 dZ and A, both consumed as MN-major tcgen05 operands straight
+ * from their row-major layout (TMA boxes of 64 frames x 64 channels), fp32 accumulation in tensor memory, per-chunk partial
+ * tiles summed in a fixed order.  Needs N % 64 == 0, K % 64 == 0, 16-byte aligned rows, slot % 64 == 0, and ZERO rows in
+ * dZ at [len[b], slot).  ws: factk_wgrad_tc_ws_floats(...) floats. */
+int factk_wgrad_tc_supported(int dz_dtype, int lddz, int a_dtype, int lda, int N, int K, int slot);
+size_t factk_wgrad_tc_ws_floats(int B, int slot, int N, int K);
+int factk_wgrad_tc(const void* dZ, int lddz, const void* A, int lda, int a_slot, int row_off, int N, int K, float* dW,
+                   int lddw, long long dw_bstride, float alpha, int accumulate, int B, int slot, const int32_t* len,
+                   float* ws, void* stream);
+
 /* out[(b)][n] (+)= alpha * sum over valid rows of X[b,t,n] (* Y[b,t,n] when Y != NULL): bias gradients, softmax column
  * terms.  out_bstride == 0 sums the videos too. */
 size_t factk_colsum_ws_floats(int B, int slot, int N);

@@ -67,6 +67,40 @@ def test_wgrad_and_colsum(B, slot, N, K, off, lens):
     assert rel(bs, refb) < 1e-5
 
 
+@pytest.mark.parametrize('B,slot,N,K,off,lens', [(1, 2048, 256, 256, 0, [2048]), (2, 1024, 256, 256, -4, [1000, 333]), (1, 16384, 256, 256, 512, [16000]),
+                                                (2, 512, 512, 256, 1, [512, 65]), (1, 1280, 256, 2048, 0, [1200]), (3, 256, 64, 128, -1, [256, 1, 130]),
+                                                (1, 384, 192, 64, 0, [300])])
+def test_wgrad_tensor_core(B, slot, N, K, off, lens):
+    """tcgen05 weight gradient (MN-major operands straight from the row-major activations) against fp64."""
+    g = torch.Generator().manual_seed(5)
+    dz = torch.zeros(B, slot, N)
+    a = torch.zeros(B, slot, K)
+    for b, T in enumerate(lens):
+        dz[b, :T] = torch.randn(T, N, generator=g)
+        a[b, :T] = torch.randn(T, K, generator=g)
+    dz16, a16 = dz.to(torch.bfloat16), a.to(torch.bfloat16)
+    ref = torch.zeros(N, K, dtype=torch.double)
+    per = torch.zeros(B, N, K, dtype=torch.double)
+    for b, T in enumerate(lens):
+        sh = torch.zeros(T, K, dtype=torch.double)
+        lo, hi = max(0, -off), min(T, T - off)
+        if hi > lo:
+            sh[lo:hi] = a16[b, lo + off:hi + off].double()
+        per[b] = dz16[b, :T].double().t() @ sh
+        ref += per[b]
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    dw = torch.zeros(N, K, device=DEV)
+    n0 = ops.COUNTERS['launches']
+    ops.wgrad(dz16.to(DEV), a16.to(DEV), N, K, dw, off=off, len=ln, accumulate=False, tc=True)
+    assert rel(dw, ref) < 1e-5, rel(dw, ref)
+    pv = torch.zeros(B, N, K, device=DEV)
+    ops.wgrad(dz16.to(DEV), a16.to(DEV), N, K, pv, off=off, len=ln, accumulate=False, per_video=True, tc=True)
+    assert rel(pv, per) < 1e-5
+    dw2 = dw.clone()
+    ops.wgrad(dz16.to(DEV), a16.to(DEV), N, K, dw2, off=off, len=ln, alpha=0.5, accumulate=True, tc=True)
+    assert rel(dw2, 1.5 * ref) < 1e-5
+
+
 def test_row_kernels_backward():
     B, slot, H, Cc = 2, 200, 48, 7
     x, ln = _rows(B, slot, H, 5, [200, 99])
