@@ -83,6 +83,7 @@ class TrainEngine(FactEngine):
         self._params = dict(self.m.named_parameters())
         self._derived = []                # (tensor with autograd graph, gradient accumulator) of the current section
         self._wt = {}
+        self._wcache = {}                 # bf16 / transposed copies are keyed by address: never let them outlive a step
         self.step_no += 1
         self._layout()
         for f in self._flat:
@@ -208,7 +209,7 @@ class TrainEngine(FactEngine):
         B = x0.v.shape[0] if B is None else B
         rows = x0.v.shape[1] if rows is None else rows
         dtype = dtype or (self.act if x0.v.dtype == torch.bfloat16 else torch.float32)
-        y = Var(self.new((B, rows, N), dtype), ln)
+        y = Var(self.new((B, rows, N), dtype, zero=(self.mode == 'bf16' and ln is not None)), ln)      # zero tails feed TMA taps
         wv = lambda W: W.v if isinstance(W, Var) else W.w
         ss = [S(s['x'].v, wv(s['W']), K=s['K'], off=s['off'], pos=s['pos'], pos_idx=s['pos_idx']) for s in srcs]
         bv = None if bias is None else (bias.v if isinstance(bias, Var) else bias.w)
@@ -239,10 +240,10 @@ class TrainEngine(FactEngine):
                 K = s['K'] if s['K'] is not None else wv(Wh).shape[-1]
                 # weight gradient
                 if isinstance(Wh, Var):
-                    ops.wgrad(dz, x.v, N, K, self.G(Wh), off=s['off'], len=ln, alpha=alpha, pos=s['pos'], pos_idx=s['pos_idx'],
-                              per_video=True)
+                    self.wgrad(dz, x.v, N, K, self.G(Wh), off=s['off'], len=ln, alpha=alpha, pos=s['pos'], pos_idx=s['pos_idx'],
+                               per_video=True)
                 elif Wh.g is not None:
-                    ops.wgrad(dz, x.v, N, K, Wh.g, off=s['off'], len=ln, alpha=alpha, pos=s['pos'], pos_idx=s['pos_idx'])
+                    self.wgrad(dz, x.v, N, K, Wh.g, off=s['off'], len=ln, alpha=alpha, pos=s['pos'], pos_idx=s['pos_idx'])
                 # data gradient: every tap of the same x in one multi-source GEMM accumulating into x.g
                 if not x.needs_grad or i in done:
                     continue
@@ -266,9 +267,16 @@ class TrainEngine(FactEngine):
         return y
 
     def mm(self, srcs, N, out, **kw):
-        """GEMM dispatch of the training step: fp32 CUDA-core kernel (the tensor-core variants come with bf16 mode)."""
+        """GEMM dispatch of the training step.  fp32 mode: the fp32 CUDA-core kernel (1e-3 gradient parity).  bf16 mode: the
+        inference engine's dispatch -- tcgen05 CTA-pair / multi-source kernels for bf16 operands, tf32 tcgen05 for fp32
+        operands, CUDA cores for what they reject (positional terms on a source, odd widths)."""
         kw = {k: v for k, v in kw.items() if v is not None}
+        if self.mode == 'bf16':
+            return FactEngine.mm(self, srcs, N, out, tf32=True, **kw)
         return ops.gemm(srcs, N, out, **kw)
+
+    def wgrad(self, dz, a, N, K, dw, **kw):
+        return ops.wgrad(dz, a, N, K, dw, tc=(self.mode == 'bf16'), **kw)
 
     def add(self, a, b, N=None):
         N = a.v.shape[-1] if N is None else N
@@ -298,13 +306,20 @@ class TrainEngine(FactEngine):
         self.tape.append(bwd)
         return y
 
-    def dropout(self, x, p, channel=False):
-        """nn.Dropout (or nn.Dropout2d over whole channels) in training mode; identity when p == 0."""
+    def dropout(self, x, p, channel=False, dtype=None):
+        """nn.Dropout (or nn.Dropout2d over whole channels) in training mode; identity when p == 0 (a cast when ``dtype``
+        differs from the input's)."""
+        dtype = dtype or x.v.dtype
         if p <= 0.0:
-            return x
+            if dtype == x.v.dtype:
+                return x
+            assert not x.needs_grad
+            y = Var(torch.zeros(x.v.shape, dtype=dtype, device=self.dev), x.len, needs_grad=False)
+            ops.ew(ops.EW_COPY, x.v, y.v, x.v.shape[-1], len=x.len)
+            return y
         N, site = x.v.shape[-1], self.next_site()
         op = ops.EW_DROPOUT_CH if channel else ops.EW_DROPOUT
-        y = Var(torch.empty_like(x.v), x.len, needs_grad=x.needs_grad)
+        y = Var(torch.zeros(x.v.shape, dtype=dtype, device=self.dev), x.len, needs_grad=x.needs_grad)
         forced = None if self.forced_masks is None else self.forced_masks.get(site)
         if forced is not None:          # tests inject the keep mask (already scaled by 1/(1-p)) instead of the hash
             ops.ew(ops.EW_MUL, x.v, y.v, N, r=forced, len=x.len)
@@ -355,7 +370,7 @@ class TrainEngine(FactEngine):
         def bwd():
             if y.g is None:
                 return
-            dv = self.new(x.v.shape, y.g.dtype)
+            dv = self.new(x.v.shape, y.g.dtype, zero=True)
             ops.layernorm_bwd(x.v, w.w, b.w, y.g, dv, w.g, b.g, res=None if res is None else res.v, relu=relu, len=ln)
             for t in (x, res):
                 if t is not None and t.needs_grad:
@@ -374,7 +389,7 @@ class TrainEngine(FactEngine):
         def bwd():
             if y.g is None and clogit.g is None:
                 return
-            x.g = self.new(x.v.shape, x.v.dtype)
+            x.g = self.new(x.v.shape, x.v.dtype, zero=True)
             ops.splice_bwd(y.v, y.g, clogit.g, x.g, H, n, len=ln)
         self.tape.append(bwd)
         return y, clogit, pred
@@ -386,7 +401,7 @@ class TrainEngine(FactEngine):
         def bwd():
             if y.g is None:
                 return
-            x.g = self.new(x.v.shape, x.v.dtype)
+            x.g = self.new(x.v.shape, x.v.dtype, zero=True)
             ops.l2norm_bwd(x.v, y.g, x.g, len=ln)
         self.tape.append(bwd)
         return y
@@ -731,11 +746,11 @@ class TrainEngine(FactEngine):
             gh = self.new((B, slot, 6 * Hh))
             ops.gemm([S(y.v[:, :, :Hh], Whf.w, off=-1)], 3 * Hh, gh[:, :, :3 * Hh], len=nseg, bias=bhf.w)
             ops.gemm([S(y.v[:, :, Hh:], Whb.w, off=1)], 3 * Hh, gh[:, :, 3 * Hh:], len=nseg, bias=bhb.w)
-            gi.g = self.new((B, slot, 6 * Hh))
-            dgh = self.new((B, slot, 6 * Hh))
+            gi.g = self.new((B, slot, 6 * Hh), zero=True)
+            dgh = self.new((B, slot, 6 * Hh), zero=True)
             ops.gru_bwd(gi.v, gh, y.v, y.g, Whf.w, Whb.w, gi.g, dgh, nseg)
-            ops.wgrad(dgh[:, :, :3 * Hh], y.v[:, :, :Hh], 3 * Hh, Hh, Whf.g, off=-1, len=nseg)
-            ops.wgrad(dgh[:, :, 3 * Hh:], y.v[:, :, Hh:], 3 * Hh, Hh, Whb.g, off=1, len=nseg)
+            self.wgrad(dgh[:, :, :3 * Hh], y.v[:, :, :Hh], 3 * Hh, Hh, Whf.g, off=-1, len=nseg)
+            self.wgrad(dgh[:, :, 3 * Hh:], y.v[:, :, Hh:], 3 * Hh, Hh, Whb.g, off=1, len=nseg)
             ops.colsum(dgh[:, :, :3 * Hh], 3 * Hh, bhf.g, len=nseg)
             ops.colsum(dgh[:, :, 3 * Hh:], 3 * Hh, bhb.g, len=nseg)
         self.tape.append(bwd)
@@ -819,8 +834,8 @@ class TrainEngine(FactEngine):
         C, H = hp['n_classes'], hp['blocks'][0]['hid_dim']
         self.frame_pos = self.derived(('pe', slot, H), lambda: _pos_table(H, slot, self.dev)) if hp['fpos'] else None
         xin = Var(x, ln, needs_grad=False)
-        if float(cfg.FACT.cmr) > 0:                        # nn.Dropout2d over whole feature channels (blocks.py:614-617)
-            xin = self.dropout(xin, float(cfg.FACT.cmr), channel=True)
+        # nn.Dropout2d over whole feature channels (blocks.py:614-617); in bf16 mode the same pass casts the features to bf16
+        xin = self.dropout(xin, float(cfg.FACT.cmr), channel=True, dtype=self.act)
         if cfg.TM.use:                                     # time_mask in place on the (already channel-masked) features
             for b, T in enumerate(lengths):
                 for t0, t1 in self.time_mask_spans(T, cfg.TM):

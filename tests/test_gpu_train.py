@@ -322,6 +322,50 @@ def test_gradients_vs_oracle_autograd_shipped_widths(preset, ncls, lens):
     print(preset, 'loss', float(loss), 'worst relative gradient error', worst)
 
 
+@pytest.mark.parametrize('preset,ncls,lens', [('havid_view0_lh_pt_holdout', 75, [384, 200]), ('epic_shape', 98, [512])])
+def test_bf16_training_step_vs_oracle(preset, ncls, lens):
+    """bf16 mode (tcgen05 forward / data-gradient GEMMs, tcgen05 weight gradients, bf16 activations and activation gradients,
+    fp32 master gradients) with the oracle's segmentation teacher-forced: loss within 2e-2, the whole gradient within 2e-2
+    relative L2 of fp32 autograd through the oracle, no parameter off by more than 10 % of its own gradient norm."""
+    cfg = C.PRESETS[preset]()
+    for blk in (cfg.Bi, cfg.Bu, cfg.BU):
+        if blk.dropout is not None:
+            blk.dropout = 0.0
+    cfg.FACT.cmr, cfg.TM.use, cfg.CLIP.projection_dropout = 0.0, False, 0.0
+    clip = bool(cfg.use_clip)
+    holdout = list(cfg.holdout_classes) if clip else []
+    torch.manual_seed(0)
+    net = (FACT_CLIP(cfg, 2048, ncls, make_text_embeddings(ncls)) if clip else FACT(cfg, 2048, ncls))
+    xs, ys = make_batch(lens, 2048, ncls, base_seed=60, nseg=6)
+    ref_loss, ref = _oracle_grads(net, cfg, ncls, xs, ys, clip, [0], holdout)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    hp = O.hparams_from_cfg(cfg, 2048, ncls)
+    with torch.no_grad():
+        outs = [O.forward_video(sd, hp, x, clip=clip, fast_gru=True) for x in xs]
+    nU = sum(1 for b in hp['blocks'] if b['type'] == 'U')
+    forced = [[[b_['tdu_pred'] for b_ in o['blocks'] if 'tdu_pred' in b_][u].to(DEV) for o in outs] for u in range(nU)]
+    net.compute_mode = 'bf16'
+    net = net.to(DEV).train()
+    net.mcriterion = _criterion(cfg, ncls, [0])
+    loss, _ = net([x.to(DEV) for x in xs], [y.to(DEV) for y in ys], compute_loss=True, forced_preds=forced)
+    assert abs(float(loss.detach()) - ref_loss) <= 2e-2 * abs(ref_loss), (float(loss.detach()), ref_loss)
+    loss.backward()
+    num = den = 0.0
+    worst = ('', 0.0)
+    gref = float(torch.sqrt(sum((g.double() ** 2).sum() for g in ref.values())))
+    for n, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        g, r = p.grad.double().cpu(), ref[n].double()
+        num += float(((g - r) ** 2).sum())
+        den += float((r ** 2).sum())
+        e = float((g - r).norm()) / max(float(r.norm()), 1e-2 * gref)
+        if e > worst[1]:
+            worst = (n, e)
+    print(preset, 'loss', float(loss.detach()), ref_loss, 'global gradient rel-L2', (num / den) ** 0.5, 'worst parameter', worst)
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5
+    assert worst[1] < 0.1, worst
+
+
 def test_train_mode_augmentations():
     """Channel masking (FACT.cmr), dropout and time masking change the train-mode forward, are regenerated identically in the
     backward pass (finite gradients for every parameter), and vanish in eval mode."""
