@@ -196,6 +196,7 @@ def run_train(args):
     net.compute_mode = args.mode
     net = net.to(dev).train()
     net.mcriterion = MatchCriterion(cfg, ncls, [0])
+    net.train_graphs = not args.no_graph
     opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=0.0)          # epic-kitchens.yaml:74-80
     red = GradAllReducer()
     net.grad_ready_hook = red.on_bucket
@@ -235,7 +236,10 @@ def run_train(args):
         torch.cuda.synchronize()
 
     W = max(args.warmup, 3)
-    for i in range(W):
+    ops.COUNTERS['launches'] = 0
+    step(0, False)                                   # eager: the kernels launched per step are counted here
+    info['launches'] = ops.COUNTERS['launches']
+    for i in range(1, W + 2):                        # graph capture happens on the second and third call of a shape
         step(i, False)
     barrier()
     sampler = ClockSampler(local)
@@ -252,6 +256,8 @@ def run_train(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     if args.profile and rank == 0:
+        net.train_graphs = False
+        step(W + args.steps, False)          # eager warm-up of the un-graphed path
         ops.TIMER = ops.KernelTimer(None)
         t0 = time.perf_counter()
         step(W + args.steps, False)
@@ -276,7 +282,7 @@ def run_train(args):
                                f'clip_grad_norm_ + Adam step; random-init weights (segments per U block below)',
                    'segments_per_U_block_rank0': info.get('nseg'), 'params': nparam, 'loss_rank0': info.get('loss'),
                    'l2_policy': f'inputs larger than L2 ({T * D * 4 / 2**20:.0f} MiB of fp32 features per step; activations far larger)'},
-        'clocks': clocks, 'gpu_launches': ops.COUNTERS['launches'] // args.steps,
+        'clocks': clocks, 'gpu_launches': info.get('launches'), 'launch': 'cuda-graph' if net.train_graphs else 'eager',
         'e2e': {'value': frames / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': (T * D * 4 + T * 8) * world, 'd2h_bytes_per_step': T * 8 * world,
                 'note': 'the timed step includes the pinned-host -> device copy of the video and the device -> host copy of the predictions and the loss'},
         'phases_ms_rank0': phases,

@@ -127,14 +127,17 @@ void launch_partial_reduce(const float* ws, size_t pstride, int psz, int K, floa
 
 // ------------------------------------------------------------------------------------------------ column sums
 // ws[(b, chunk)][n] = sum over the chunk's valid rows of X[b,t,n] (* Y[b,t,n] when Y != NULL)
+constexpr int CSUM_RC = 128;      // rows per partial of the column sums / LayerNorm affine gradients
+__host__ __device__ inline int csum_nchunk(int slot) { return (slot + CSUM_RC - 1) / CSUM_RC; }
+
 __global__ void colsum_partial_kernel(const void* __restrict__ X, int x_dtype, int ldx, const void* __restrict__ Y, int y_dtype,
                                       int ldy, int N, float* __restrict__ ws, int slot, const int32_t* __restrict__ len, int nchunk) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = blockIdx.y, b = blockIdx.z;
     const int len_b = len ? min(len[b], slot) : slot;
-    const int r0 = chunk * WG_RC;
+    const int r0 = chunk * CSUM_RC;
     if (r0 >= len_b || n >= N) return;
-    const int r1 = min(r0 + WG_RC, len_b);
+    const int r1 = min(r0 + CSUM_RC, len_b);
     float s = 0.f;
     for (int r = r0; r < r1; ++r) {
         float v = ld_elem(X, x_dtype, ((size_t)b * slot + r) * (size_t)ldx + n);
@@ -145,7 +148,8 @@ __global__ void colsum_partial_kernel(const void* __restrict__ X, int x_dtype, i
 }
 
 // ------------------------------------------------------------------------------------------------ elementwise on rows
-enum { EW_RELU_BWD = 0, EW_AXPY = 1, EW_DROPOUT = 2, EW_DROPOUT_CH = 3, EW_COPY = 4, EW_MUL = 5, EW_ADD = 6, EW_RELU = 7 };
+enum { EW_RELU_BWD = 0, EW_AXPY = 1, EW_DROPOUT = 2, EW_DROPOUT_CH = 3, EW_COPY = 4, EW_MUL = 5, EW_ADD = 6, EW_RELU = 7, EW_ROWSCALE = 8 };
+constexpr int EW_ROWS = 8;      // rows per CTA
 
 // counter-based uniform in [0,1): a 64-bit mix of (seed, site, element index) -- the same value in the forward and the
 // backward pass, nothing stored
@@ -166,16 +170,19 @@ __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned 
 //   MUL:        Y = X * R
 //   ADD:        Y = X + R
 //   RELU:       Y = max(X, 0)
+//   ROWSCALE:   Y = X * R[row]               (R: one value per row, e.g. the time mask of basic.time_mask)
+// seed_ptr (optional, device): added to ``seed`` -- lets a captured CUDA graph draw new masks on every replay
 // x_slot: row slots per video of X (0 broadcasts one [slot][ldx] table over the videos: positional / query tables)
 __global__ void rows_elementwise_kernel(int op, const void* X, int x_dtype, int ldx, const void* R,
                                         int r_dtype, int ldr, void* Y, int y_dtype, int ldy, int N, int slot,
                                         const int32_t* __restrict__ len, float alpha, float p, unsigned long long seed,
-                                        unsigned site, int x_slot) {
-    const int b = blockIdx.z, t = blockIdx.y;
+                                        unsigned site, int x_slot, const unsigned long long* __restrict__ seed_ptr) {
+    const int b = blockIdx.z;
     const int len_b = len ? min(len[b], slot) : slot;
-    if (t >= len_b) return;
-    const size_t row = (size_t)b * slot + t, xrow = (size_t)b * x_slot + t;
+    if (seed_ptr) seed += *seed_ptr;
     const float keep_scale = (op == EW_DROPOUT || op == EW_DROPOUT_CH) ? 1.f / (1.f - p) : 0.f;
+    for (int t = blockIdx.y * EW_ROWS; t < min((int)(blockIdx.y + 1) * EW_ROWS, len_b); ++t) {
+    const size_t row = (size_t)b * slot + t, xrow = (size_t)b * x_slot + t;
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
         const float x = ld_elem(X, x_dtype, xrow * ldx + n);
         float y;
@@ -187,9 +194,11 @@ __global__ void rows_elementwise_kernel(int op, const void* X, int x_dtype, int 
             case EW_MUL: y = x * ld_elem(R, r_dtype, row * ldr + n); break;
             case EW_ADD: y = x + ld_elem(R, r_dtype, row * ldr + n); break;
             case EW_RELU: y = fmaxf(x, 0.f); break;
+            case EW_ROWSCALE: y = x * ld_elem(R, r_dtype, row * ldr); break;
             default: y = alpha * x; break;
         }
         st_elem(Y, y_dtype, row * ldy + n, y);
+    }
     }
 }
 
@@ -252,6 +261,9 @@ __global__ void row_softmax_bwd_kernel(const float* __restrict__ P, int ldp, con
     }
 }
 
+constexpr int LN_RC = 32;          // rows per CTA of the LayerNorm backward (8 warps x 4 rows)
+__host__ __device__ inline int ln_nchunk(int slot) { return (slot + LN_RC - 1) / LN_RC; }
+
 // LayerNorm backward: y = relu?((v - mu) * rstd * w + b), v = x (+ r).  dV (the gradient of v) is written (or
 // accumulated); per-chunk partial sums of dgamma = dy * xhat and dbeta = dy go to ws[(b,chunk)][2][E].
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ X, int x_dtype, int ldx, const void* __restrict__ R,
@@ -262,9 +274,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
     extern __shared__ float sm[];          // [8 warps][2][E]
     const int chunk = blockIdx.x, b = blockIdx.y;
     const int len_b = len ? min(len[b], slot) : slot;
-    const int r0 = chunk * WG_RC;
+    const int r0 = chunk * LN_RC;
     if (r0 >= len_b) return;
-    const int r1 = min(r0 + WG_RC, len_b);
+    const int r1 = min(r0 + LN_RC, len_b);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     float* mg = sm + (size_t)warp * 2 * E;
     float* mb = mg + E;
@@ -466,32 +478,32 @@ extern "C" int factk_wgrad(const void* dZ, int dz_dtype, int lddz, const void* A
     return check_launch("factk_wgrad");
 }
 
-extern "C" size_t factk_colsum_ws_floats(int B, int slot, int N) { return (size_t)B * wg_nchunk(slot) * (size_t)N; }
+extern "C" size_t factk_colsum_ws_floats(int B, int slot, int N) { return (size_t)B * csum_nchunk(slot) * (size_t)N; }
 
 /* out[(b)][n] (+)= alpha * sum over valid rows of X[b,t,n] (* Y[b,t,n]) */
 extern "C" int factk_colsum(const void* X, int x_dtype, int ldx, const void* Y, int y_dtype, int ldy, int N, float* out,
                             long long out_bstride, float alpha, int accumulate, int B, int slot, const int32_t* len, float* ws,
                             void* stream) {
     FACTK_REQUIRE(X && out && ws && N > 0 && B > 0 && slot > 0, "factk_colsum: bad args");
-    const int nchunk = wg_nchunk(slot), per_video = out_bstride != 0;
+    const int nchunk = csum_nchunk(slot), per_video = out_bstride != 0;
     cudaStream_t st = (cudaStream_t)stream;
-    colsum_partial_kernel<<<dim3((N + 127) / 128, nchunk, B), 128, 0, st>>>(X, x_dtype, ldx, Y, y_dtype, ldy, N, ws, slot, len, nchunk);
-    partial_reduce_kernel<<<dim3((N + 255) / 256, per_video ? B : 1), 256, 0, st>>>(ws, (size_t)N, N, N, out, N, out_bstride, B, slot, len,
-                                                                                   nchunk, WG_RC, alpha, accumulate, per_video);
+    colsum_partial_kernel<<<dim3((N + 63) / 64, nchunk, B), 64, 0, st>>>(X, x_dtype, ldx, Y, y_dtype, ldy, N, ws, slot, len, nchunk);
+    partial_reduce_kernel<<<dim3((N + 63) / 64, per_video ? B : 1), 64, 0, st>>>(ws, (size_t)N, N, N, out, N, out_bstride, B, slot, len,
+                                                                                 nchunk, CSUM_RC, alpha, accumulate, per_video);
     return check_launch("factk_colsum");
 }
 
 extern "C" int factk_rows_elementwise(int op, const void* X, int x_dtype, int ldx, const void* R, int r_dtype, int ldr, void* Y,
                                       int y_dtype, int ldy, int N, int B, int slot, const int32_t* len, float alpha, float p,
-                                      unsigned long long seed, unsigned site, int x_slot, void* stream) {
-    FACTK_REQUIRE(X && Y && N > 0 && B > 0 && slot > 0 && op >= 0 && op <= EW_RELU, "factk_rows_elementwise: bad args");
-    FACTK_REQUIRE(!(op == EW_RELU_BWD || op == EW_MUL || op == EW_ADD) || R, "factk_rows_elementwise: op %d needs R", op);
+                                      unsigned long long seed, unsigned site, int x_slot, const unsigned long long* seed_ptr,
+                                      void* stream) {
+    FACTK_REQUIRE(X && Y && N > 0 && B > 0 && slot > 0 && op >= 0 && op <= EW_ROWSCALE, "factk_rows_elementwise: bad args");
+    FACTK_REQUIRE(!(op == EW_RELU_BWD || op == EW_MUL || op == EW_ADD || op == EW_ROWSCALE) || R, "factk_rows_elementwise: op %d needs R", op);
     FACTK_REQUIRE(p >= 0.f && p < 1.f, "factk_rows_elementwise: p = %f", p);
     const int threads = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
     const int gx = (N + threads * 4 - 1) / (threads * 4);
-    rows_elementwise_kernel<<<dim3(gx > 0 ? gx : 1, slot, B), threads, 0, (cudaStream_t)stream>>>(op, X, x_dtype, ldx, R, r_dtype, ldr, Y,
-                                                                                                y_dtype, ldy, N, slot, len, alpha, p,
-                                                                                                seed, site, x_slot < 0 ? slot : x_slot);
+    rows_elementwise_kernel<<<dim3(gx > 0 ? gx : 1, (slot + EW_ROWS - 1) / EW_ROWS, B), threads, 0, (cudaStream_t)stream>>>(
+        op, X, x_dtype, ldx, R, r_dtype, ldr, Y, y_dtype, ldy, N, slot, len, alpha, p, seed, site, x_slot < 0 ? slot : x_slot, seed_ptr);
     return check_launch("factk_rows_elementwise");
 }
 
@@ -519,14 +531,14 @@ extern "C" int factk_row_softmax_bwd(const float* P, int ldp, const float* dP, i
     return check_launch("factk_row_softmax_bwd");
 }
 
-extern "C" size_t factk_layernorm_bwd_ws_floats(int B, int slot, int E) { return (size_t)B * wg_nchunk(slot) * 2 * (size_t)E; }
+extern "C" size_t factk_layernorm_bwd_ws_floats(int B, int slot, int E) { return (size_t)B * ln_nchunk(slot) * 2 * (size_t)E; }
 
 extern "C" int factk_layernorm_bwd(const void* X, int x_dtype, int ldx, const void* R, int r_dtype, int ldr, const float* w,
                                    const float* b, float eps, int relu, const void* dY, int dy_dtype, int lddy, void* dV, int dv_dtype,
                                    int lddv, int accumulate, float* dw, float* db, int B, int slot, const int32_t* len, int E,
                                    float* ws, void* stream) {
     FACTK_REQUIRE(X && w && b && dY && dV && dw && db && ws && E > 0, "factk_layernorm_bwd: bad args");
-    const int nchunk = wg_nchunk(slot);
+    const int nchunk = ln_nchunk(slot);
     const size_t smem = (size_t)8 * 2 * E * sizeof(float);
     FACTK_REQUIRE(smem <= 200 * 1024, "factk_layernorm_bwd: E = %d too wide", E);
     cudaStream_t st = (cudaStream_t)stream;
@@ -534,8 +546,8 @@ extern "C" int factk_layernorm_bwd(const void* X, int x_dtype, int ldx, const vo
     if (first_use_on_device(devs)) cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     layernorm_bwd_kernel<<<dim3(nchunk, B), 256, smem, st>>>(X, x_dtype, ldx, R, r_dtype, ldr, w, b, eps, relu, dY, dy_dtype, lddy, dV,
                                                            dv_dtype, lddv, accumulate, ws, E, slot, len, nchunk);
-    partial_reduce_kernel<<<dim3((E + 255) / 256, 1), 256, 0, st>>>(ws, (size_t)2 * E, E, E, dw, E, 0, B, slot, len, nchunk, WG_RC, 1.f, 1, 0);
-    partial_reduce_kernel<<<dim3((E + 255) / 256, 1), 256, 0, st>>>(ws + E, (size_t)2 * E, E, E, db, E, 0, B, slot, len, nchunk, WG_RC, 1.f, 1, 0);
+    partial_reduce_kernel<<<dim3((E + 63) / 64, 1), 64, 0, st>>>(ws, (size_t)2 * E, E, E, dw, E, 0, B, slot, len, nchunk, LN_RC, 1.f, 1, 0);
+    partial_reduce_kernel<<<dim3((E + 63) / 64, 1), 64, 0, st>>>(ws + E, (size_t)2 * E, E, E, db, E, 0, B, slot, len, nchunk, LN_RC, 1.f, 1, 0);
     return check_launch("factk_layernorm_bwd");
 }
 

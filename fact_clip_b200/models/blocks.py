@@ -235,6 +235,7 @@ class _FactBase(nn.Module):
         ``param.grad`` of every parameter.  ``net.grad_ready_hook(names, grads)``, when set, is called as soon as the gradients of
         a block's parameters are final (data-parallel all-reduce overlapped with the rest of the backward pass)."""
         eng = self.train_engine()
+        eng.use_graphs = bool(getattr(self, 'train_graphs', False))      # CUDA-graph the step per batch shape (fixed-shape training)
         with torch.no_grad():
             out = eng.forward_train(seqs, forced_preds=forced_preds)
             self._last = out
@@ -244,7 +245,8 @@ class _FactBase(nn.Module):
         self.stash_video(len(seqs) - 1)
         saves = [{'pred': pred[b, :T].copy()} for b, T in enumerate(out['lengths'])]
         if not compute_loss:
-            eng.tape = []
+            if isinstance(eng.tape, list):
+                eng.tape = []
             return saves
         self.last_match = res['matches']
         vals = res['values'].cpu().numpy()

@@ -73,18 +73,34 @@ class TrainEngine(FactEngine):
         super().__init__(module, hp, clip, mode)
         self.seed, self.step_no = 0x5EED, 0
         self.forced_masks = None          # tests: {'cmr': keep mask [B, D]} injected instead of the hashed one
+        self.use_graphs = False           # capture the step into CUDA graphs per batch shape (net.train_graphs = True)
+        self._steps, self._cur, self._cap_stream, self._const, self._seed_dev = {}, None, None, {}, None
+        self.tape = []
         if hp['trans'] or self.vn is not None:
             raise NotImplementedError('training step: FACT.trans and the Epic verb/noun model are not built (query-token FACT / '
                                       'FACT_CLIP only)')
 
     # ------------------------------------------------------------------ bookkeeping
+    @property
+    def seed_dev(self):
+        """Device scalar added to every dropout seed (the step number): static address, new value every step."""
+        if self._seed_dev is None or self._seed_dev.device != self.dev:
+            self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        return self._seed_dev
+
+    def const_table(self, key, fn):
+        """Constant of the model shape (positional table): survives the per-step weight-cache reset."""
+        t = self._const.get((key, self.dev))
+        if t is None:
+            t = self._const[(key, self.dev)] = fn().contiguous()
+        return t
+
     def begin(self):
         self.tape, self._site = [], 0
         self._params = dict(self.m.named_parameters())
         self._derived = []                # (tensor with autograd graph, gradient accumulator) of the current section
         self._wt = {}
         self._wcache = {}                 # bf16 / transposed copies are keyed by address: never let them outlive a step
-        self.step_no += 1
         self._layout()
         for f in self._flat:
             f.zero_()
@@ -124,14 +140,12 @@ class TrainEngine(FactEngine):
         """Tape marker at the START of section k of the forward pass: when the (reversed) tape reaches it, every gradient
         contribution to the section's parameters has been launched."""
         self._derived = []
-        derived = self._derived
+        self.tape.append(('section', k, self._derived))
 
-        def done():
-            self._finish_derived(derived)
-            hook = getattr(self.m, 'grad_ready_hook', None)
-            if hook is not None:
-                hook(k, self._flat[k], self._sect_names[k])
-        self.tape.append(done)
+    def _section_done(self, k):
+        hook = getattr(self.m, 'grad_ready_hook', None)
+        if hook is not None:
+            hook(k, self._flat[k], self._sect_names[k])
 
     def _finish_derived(self, derived):
         """Carry the gradients of a section's derived weights (parameter-sized differentiable functions) to the parameters."""
@@ -324,7 +338,7 @@ class TrainEngine(FactEngine):
         if forced is not None:          # tests inject the keep mask (already scaled by 1/(1-p)) instead of the hash
             ops.ew(ops.EW_MUL, x.v, y.v, N, r=forced, len=x.len)
         else:
-            ops.ew(op, x.v, y.v, N, len=x.len, p=p, seed=self.seed + self.step_no, site=site)
+            ops.ew(op, x.v, y.v, N, len=x.len, p=p, seed=self.seed, site=site, seed_ptr=self.seed_dev)
 
         def bwd():
             if y.g is None or not x.needs_grad:
@@ -333,7 +347,7 @@ class TrainEngine(FactEngine):
             if forced is not None:
                 ops.ew(ops.EW_MUL, y.g, t, N, r=forced, len=x.len)
             else:
-                ops.ew(op, y.g, t, N, len=x.len, p=p, seed=self.seed + self.step_no, site=site)
+                ops.ew(op, y.g, t, N, len=x.len, p=p, seed=self.seed, site=site, seed_ptr=self.seed_dev)
             ops.ew(ops.EW_AXPY, t, self.G(x), N, len=x.len)
         self.tape.append(bwd)
         return y
@@ -816,30 +830,84 @@ class TrainEngine(FactEngine):
 
     def forward_train(self, seqs, forced_preds=None):
         """Train-mode forward of a batch.  Returns the ``out`` dict of FactEngine.run_packed (values) with the Vars of every
-        tensor the loss reads under ``*_v`` keys."""
+        tensor the loss reads under ``*_v`` keys.
+
+        ``use_graphs``: the step is captured ONCE per batch shape (B, slot) into CUDA graphs -- one for the forward pass, one
+        per section of the backward pass (the gradient-ready hooks run between them) -- and replayed afterwards: the ~4000
+        kernel launches of a step cost a handful of graph launches instead of ~40 us of host work each.  Everything that
+        changes from step to step enters through static device buffers: the features, the lengths, the dropout seed (the
+        kernels add a device scalar to their seed), the time mask (one factor per frame), the loss gradients."""
         self._refresh_weights()
-        self.begin()
         hp, cfg = self.hp, self.m.cfg
         self.ntok, self.action_init, self.transcript = hp['ntoken'], None, None
         lengths = [int(s.shape[0]) for s in seqs]
         B, slot, D = len(seqs), _round_up(max(lengths), 128), hp['in_dim']
         self._set_arena(('train', B, slot))
         self.B, self.slot, self.keep = B, slot, True
-        x = self.new((B, slot, D), torch.float32, zero=True)
-        for b, s in enumerate(seqs):
-            x[b, :lengths[b]].copy_(s, non_blocking=True)
-        ln = self.new((B,), torch.int32)
-        ln.copy_(torch.tensor(lengths, dtype=torch.int32), non_blocking=True)
-        self.len = ln
+        st = self._steps.get((B, slot))
+        if st is None:
+            if len(self._steps) >= 2:                       # every entry pins a whole step's activations
+                self._steps.pop(next(iter(self._steps)))
+            st = self._steps[(B, slot)] = dict(
+                x=torch.zeros((B, slot, D), dtype=torch.float32, device=self.dev), ln=torch.zeros((B,), dtype=torch.int32, device=self.dev),
+                tm=torch.ones((B, slot), dtype=torch.float32, device=self.dev) if cfg.TM.use else None, lengths=None, warm=False,
+                ln_host=torch.zeros((B,), dtype=torch.int32).pin_memory())
+        # ---- staging (never captured): features, lengths, seed, time mask into the static buffers
+        if st['lengths'] != lengths and st['lengths'] is not None:
+            st['x'].zero_()
+        for b_, s_ in enumerate(seqs):
+            st['x'][b_, :lengths[b_]].copy_(s_, non_blocking=True)
+        st['ln_host'].copy_(torch.tensor(lengths, dtype=torch.int32))
+        st['ln'].copy_(st['ln_host'], non_blocking=True)
+        st['lengths'] = lengths
+        self.step_no += 1
+        self.seed_dev.fill_(self.step_no)
+        if st['tm'] is not None:                          # basic.time_mask spans as one keep factor per frame
+            tm = torch.ones((B, slot), dtype=torch.float32)
+            for b_, T in enumerate(lengths):
+                for t0, t1 in self.time_mask_spans(T, cfg.TM):
+                    tm[b_, t0:t1] = 0.0
+            st['tm'].copy_(tm, non_blocking=True)
+        self.len, self._cur = st['ln'], st
+        graphable = self.use_graphs and forced_preds is None
+        if graphable and st.get('gF') is not None:
+            if any(p_.grad is not None and p_.grad.data_ptr() == self._pg[n].data_ptr() for n, p_ in self._params.items()):
+                raise RuntimeError('graph-captured training step: call optimizer.zero_grad(set_to_none=True) between steps (the '
+                                   'gradient buffers are static)')
+            for f in self._flat:
+                f.zero_()
+            st['gF'].replay()
+            st['out']['lengths'] = lengths
+            # backward: replay its graphs when they exist, else capture them from the closures of the forward capture
+            self.tape = st['tape_done'] if st.get('gB') is not None else st['tape']
+            return st['out']
+        self.begin()
+        if graphable and st['warm']:
+            if self._cap_stream is None:
+                self._cap_stream = torch.cuda.Stream(device=self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._cap_stream):
+                out = self._forward_body(st, lengths, None)
+            st['gF'], st['out'], st['tape'] = g, out, self.tape
+            g.replay()
+        else:
+            out = self._forward_body(st, lengths, forced_preds)
+            st['warm'] = True
+        return out
+
+    def _forward_body(self, st, lengths, forced_preds):
+        hp, cfg = self.hp, self.m.cfg
+        B, slot = self.B, self.slot
+        ln = st['ln']
         C, H = hp['n_classes'], hp['blocks'][0]['hid_dim']
-        self.frame_pos = self.derived(('pe', slot, H), lambda: _pos_table(H, slot, self.dev)) if hp['fpos'] else None
-        xin = Var(x, ln, needs_grad=False)
+        self.frame_pos = self.const_table(('pe', slot, H), lambda: _pos_table(H, slot, self.dev)) if hp['fpos'] else None
+        xin = Var(st['x'], ln, needs_grad=False)
         # nn.Dropout2d over whole feature channels (blocks.py:614-617); in bf16 mode the same pass casts the features to bf16
         xin = self.dropout(xin, float(cfg.FACT.cmr), channel=True, dtype=self.act)
-        if cfg.TM.use:                                     # time_mask in place on the (already channel-masked) features
-            for b, T in enumerate(lengths):
-                for t0, t1 in self.time_mask_spans(T, cfg.TM):
-                    xin.v[b, t0:t1].zero_()
+        if st['tm'] is not None:                           # time_mask on the (already channel-masked) features (blocks.py:619-622)
+            y = Var(torch.zeros_like(xin.v), ln, needs_grad=False)
+            ops.ew(ops.EW_ROWSCALE, xin.v, y.v, xin.v.shape[-1], r=st['tm'].unsqueeze(-1), len=ln)
+            xin = y
         frame, action, stash, u, pred = xin, None, [], 0, None
         for i, bc in enumerate(hp['blocks']):
             st = {}
@@ -895,12 +963,58 @@ class TrainEngine(FactEngine):
 
     def backward(self, seeds):
         """seeds: list of (Var, gradient tensor).  Runs the tape; returns {parameter name: gradient} (fp32)."""
-        for var, g in seeds:
-            if var.g is None:
-                var.g = g
+        st = self._cur
+        if st is not None and st.get('gB') is not None and self.tape is st.get('tape_done'):       # replay
+            for buf_, (_, g) in zip(st['seed_bufs'], seeds):
+                buf_.copy_(g)
+            for g, k in st['gB']:
+                g.replay()
+                if k is not None:
+                    self._section_done(k)
+            return self._pg
+        capture = st is not None and st.get('gF') is not None and st.get('tape') is self.tape and self.use_graphs
+        if capture:                                         # loss gradients enter through static buffers
+            st['seed_bufs'] = [torch.zeros_like(g) for _, g in seeds]
+            for buf_, (var, g) in zip(st['seed_bufs'], seeds):
+                buf_.copy_(g)
+                assert var.g is None
+                var.g = buf_
+            st['gB'] = []
+        else:
+            for var, g in seeds:
+                if var.g is None:
+                    var.g = g
+                else:
+                    var.g += g
+        # segments of the reversed tape, each ending at a section marker
+        segs, cur = [], []
+        for item in reversed(self.tape):
+            if isinstance(item, tuple):
+                segs.append((cur, item[1], item[2]))
+                cur = []
             else:
-                var.g += g
-        for fn in reversed(self.tape):
-            fn()
-        self.tape, self._derived, self._wt = [], [], {}
+                cur.append(item)
+        if cur:                                             # entries before the first section (input augmentations): no parameters
+            segs.append((cur, None, []))
+        for fns, k, derived in segs:
+            if capture:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._cap_stream):
+                    for fn in fns:
+                        fn()
+                    self._finish_derived(derived)
+                g.replay()
+                st['gB'].append((g, k))
+            else:
+                for fn in fns:
+                    fn()
+                self._finish_derived(derived)
+            if k is not None:
+                self._section_done(k)
+        if capture:
+            st['tape_done'] = self.tape = object()          # the closures live on in the graphs; later steps replay
+            st['tape'] = None
+        else:
+            self.tape = []
+        self._derived, self._wt = [], {}
         return self._pg

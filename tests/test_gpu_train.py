@@ -366,6 +366,37 @@ def test_bf16_training_step_vs_oracle(preset, ncls, lens):
     assert worst[1] < 0.1, worst
 
 
+def test_graph_captured_step_equals_eager():
+    """net.train_graphs: forward and backward captured into CUDA graphs per batch shape; replayed steps give the same loss and
+    bit-identical gradients as eager steps on new data of the same shape, including new dropout masks per step."""
+    g = load_golden('tiny_m_iuU_clip_trained')
+    cfg = C.tiny(**g['tiny_kwargs'])
+    cfg.Loss.match, cfg.Loss.nullw, cfg.Loss.sw, cfg.Loss.pc = 'o2o', 0.1, 0.5, 0.2
+    cfg.FACT.cmr = 0.25
+    nets = []
+    for graphs in (False, True):
+        net = FACT_CLIP(cfg, g['in_dim'], g['n_classes'], make_text_embeddings(g['n_classes']))
+        net.load_state_dict(g['state_dict'], strict=False)
+        net.compute_mode = 'fp32'
+        net = net.to(DEV).train()
+        net.mcriterion = _criterion(cfg, g['n_classes'], [])
+        net.train_graphs = graphs
+        nets.append(net)
+    vids = g['videos']
+    batches = [[vids[0], vids[2]], [vids[2], vids[0]], [vids[0], vids[2]], [vids[2], vids[0]]]     # same (B, slot), other lengths order
+    for step, batch in enumerate(batches):
+        res = []
+        for net in nets:
+            net.zero_grad(set_to_none=True)
+            loss, _ = net([v['x'].to(DEV) for v in batch], [v['label'].to(DEV) for v in batch], compute_loss=True)
+            loss.backward()
+            res.append((float(loss.detach()), {n: p.grad.clone() for n, p in net.named_parameters()}))
+        assert res[0][0] == res[1][0], (step, res[0][0], res[1][0])
+        for n in res[0][1]:
+            assert torch.equal(res[0][1][n], res[1][1][n]), (step, n)
+    assert nets[1].train_engine()._cur.get('gB') is not None, 'the backward pass was never captured'
+
+
 def test_train_mode_augmentations():
     """Channel masking (FACT.cmr), dropout and time masking change the train-mode forward, are regenerated identically in the
     backward pass (finite gradients for every parameter), and vanish in eval mode."""
