@@ -126,3 +126,40 @@ def test_run_eval_script_unmodified(tmp_path):
     for k in m_ref:
         assert abs(m_ref[k] - m_new[k]) < 1e-6, (k, m_ref[k], m_new[k])
     assert m_new['Acc'] > 50, 'the trained fixture predicts most frames right; a collapsed prediction would not'
+
+
+TRAIN_YAML = YAML + """
+epoch: 12
+lr: 0.001
+optimizer: Adam
+weight_decay: 0.0
+clip_grad_norm: 10.0
+Loss: {pc: 0.2, a2fc: 1.0, match: o2o, bgw: 1.0, nullw: 0.1, sw: 0.5}
+TM: {use: true, t: 6, m: 2, p: 0.1}
+"""
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_train_script_unmodified(tmp_path):
+    """scripts/train.py as it is (wandb offline): 12 epochs x 3 batches of the synthetic mini-dataset through
+    ``net(seqs, labels, compute_loss=True)`` -> ``loss.backward()`` -> ``clip_grad_norm_`` -> ``optimizer.step()``
+    (scripts/train.py:262-268) on the hand-written training step, periodic evaluation and checkpointing included.  The run must
+    finish, write its checkpoints and the FINISH_PROOF marker, and the training loss must have dropped."""
+    tmp = str(tmp_path)
+    g = load_golden('tiny_m2_iuUU_trained')
+    make_project(tmp, g, n_videos=6)
+    with open(os.path.join(tmp, 'cfg_train.yaml'), 'w') as f:
+        f.write(TRAIN_YAML.replace('cmr: 0.0', 'cmr: 0.2').replace('aux: {gpu: 0, debug: false}',
+                                                                 'aux: {gpu: 0, debug: false, wandb_offline: true, print_every: 6, eval_every: 18}'))
+    out = run_script(tmp, 'train.py', ['--cfg', os.path.join(tmp, 'cfg_train.yaml')], dropin=True)
+    import glob
+    import re
+    logs = glob.glob(os.path.join(tmp, 'log', '**', 'FINISH_PROOF'), recursive=True)
+    assert logs, out[-3000:]
+    nets = glob.glob(os.path.join(os.path.dirname(logs[0]), 'ckpts', 'network.iter-*.net'))
+    assert nets, 'no checkpoint written'
+    sd = torch.load(nets[0], map_location='cpu')
+    assert 'block_list.0.frame_branch.conv_out.weight' in sd and all(torch.isfinite(v).all() for v in sd.values() if v.is_floating_point())
+    losses = [float(x) for x in re.findall(r'Iter\d+, loss:([0-9.]+)', out)]
+    assert len(losses) >= 4 and losses[-1] < losses[0], losses
