@@ -47,6 +47,7 @@ _SIGS = {
     'factk_mha_tokens': (i32, [vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
     'factk_attn_rows_ws_floats': (C.c_size_t, [i32, i32, i32, i32, i32]),
     'factk_attn_rows': (i32, [vp, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]),
+    'factk_attn_tc_debug': (i32, [vp]),
     'factk_col_softmax_ws_floats': (C.c_size_t, [i32, i32, i32, i32]),
     'factk_col_softmax_apply': (i32, [vp, i32, vp, i32, i32, vp, i32, vp, i32, i32, i32, vp, i32, i32, vp, vp]),
     'factk_tdu_segment': (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),

@@ -710,6 +710,11 @@ __global__ void col_apply_combine_kernel(const float* __restrict__ part, float* 
 
 static inline int nsplit_of(int slot) { return (slot + SPLIT_ROWS - 1) / SPLIT_ROWS; }
 
+// attn_tc.cu
+bool attn_rows_tc_ok(const void* Kx, const void* Vx, int kv_dtype, int ldkv, int slot, int nhead, int dh);
+int attn_rows_tc_launch(const float* Q, int ldq, const void* Kx, const void* Vx, int ldkv, int B, int slot, const int32_t* len, int M,
+                        int nsplit, float* ws, cudaStream_t st);
+
 }  // namespace factk
 
 using namespace factk;
@@ -767,6 +772,19 @@ extern "C" int factk_attn_rows(const float* Q, int ldq, const void* Kx, const vo
     const int threads = ((M + 31) / 32) * 32;
     cudaStream_t st_ = (cudaStream_t)stream;
     const bool kv16 = ((reinterpret_cast<uintptr_t>(Kx) | reinterpret_cast<uintptr_t>(Vx)) & 15u) == 0 && (ldkv % 8) == 0;
+    // tcgen05 / TMEM kernel (attn_tc.cu): 8 heads of 32 channels, bf16 rows.  Measured on B200 (profiles/r2_attn_tc.md): with
+    // M = 300 tokens (three full 128-row query blocks) it matches the mma.sync kernel below (585 vs 598 us at 8 x 16384 frames);
+    // with M = 75 the 128-row MMA wastes 41 % of the softmax lanes -- the kernel is bound by exp2 throughput and by the latency
+    // of two warps per scheduler, not by the tensor pipe -- and it is slower (264 vs 175 us at 64 x 4096), so it is the default
+    // for M > 128 only.  FACTK_ATTN_TC=1 forces it, FACTK_ATTN_TC=0 disables it.
+    static const int tc_mode = [] { const char* e = getenv("FACTK_ATTN_TC"); return e ? atoi(e) : -1; }();
+    const bool use_tc = tc_mode == 1 || (tc_mode < 0 && M > 128);
+    if (use_tc && attn_rows_tc_ok(Kx, Vx, kv_dtype, ldkv, slot, nhead, dh)) {
+        const int rc = attn_rows_tc_launch(Q, ldq, Kx, Vx, ldkv, B, slot, len, M, ns, ws, st_);
+        if (rc) return rc;
+        attn_rows_combine_kernel<32><<<cgrid, 256, 0, st_>>>(ws, O, ldo, slot, len, M, nhead, ns);
+        return check_launch("factk_attn_rows(tcgen05)");
+    }
     if (kv_dtype == FACTK_BF16 && kv16 && (dh == 16 || dh == 32 || dh == 64)) {
         const int nqb = (M + 127) / 128;
         int qwarps = nqb > 1 ? 8 : (M + 15) / 16;    // a query block is 128 tokens = 8 warps

@@ -347,7 +347,8 @@ class FactEngine:
         else:
             tgt.copy_(self.action_init)
         t = self.buf('tok_t', (B, M, A))
-        kv = self.buf('sca_kv', (B, slot, 2 * A), self.act)
+        # zero-initialised: rows >= len are never written and the tensor-core attention multiplies them by exact zeros
+        kv = self.zbuf('sca_kv', (B, slot, 2 * A), self.act)
         ws = self.buf('attn_ws', (max(ops.attn_rows_ws(B, slot, M, nh, A // nh), 1),))
         fpos = self.frame_pos
         for i in range(bc['a_layers']):

@@ -161,6 +161,9 @@ int factk_attn_rows(const float* Q, int ldq, const void* Kx, const void* Vx, int
                     float* O, int ldo, int B, int slot, const int32_t* len, int M, int nhead, int dh,
                     float* ws, void* stream);
 
+/* Development aid of the tcgen05 attention kernel behind factk_attn_rows (csrc/attn_tc.cu): clock64 timeline of one CTA. */
+int factk_attn_tc_debug(long long* dbg);
+
 /* Softmax over ROWS (the X axis of X2Y_map in the f2a direction, basic.py:373-379):
  *   L fp32 [B][slot][ldl] holds logits (row = frame/segment, column = token m < M);
  *   stats[b][m] = (max, sum exp) over valid rows;

@@ -182,6 +182,37 @@ def test_attn_rows(dtype, M, nh, dh, slot, lens):
             assert rel_l2(o[b], ref) < 5e-3
 
 
+@pytest.mark.parametrize('M,slot,lens', [(75, 1280, [1280, 700, 3]), (128, 512, [512, 65]), (300, 640, [640]), (129, 1024, [1000, 513])])
+def test_attn_rows_tcgen05_kernel(M, slot, lens, monkeypatch):
+    """The tcgen05 / TMEM attention kernel (attn_tc.cu) forced on for every M (it is the default only for M > 128): S = Q K^T
+    and O += P V on the tensor cores, softmax on TMEM rows in registers -- against fp32 softmax attention in torch."""
+    import subprocess, sys, os
+    code = f"""
+import math, sys, torch
+sys.path.insert(0, {ROOT!r})
+from fact_clip_b200 import ops
+M, slot, lens, nh, dh = {M}, {slot}, {lens}, 8, 32
+B, E = len(lens), nh * dh
+g = torch.Generator().manual_seed(23)
+q = torch.randn(B, M, E, generator=g)
+kv = torch.randn(B, slot, 2 * E, generator=g).to(torch.bfloat16)
+o = torch.zeros(B, M, E, device='cuda')
+kvd = kv.cuda()
+ws = torch.empty(ops.attn_rows_ws(B, slot, M, nh, dh), device='cuda')
+ops.attn_rows(q.cuda(), kvd[..., :E], kvd[..., E:], o, nh, ws, len=torch.tensor(lens, dtype=torch.int32, device='cuda'))
+for b, T in enumerate(lens):
+    qq = q[b].view(M, nh, dh).transpose(0, 1)
+    kk = kv[b, :T, :E].float().view(T, nh, dh).transpose(0, 1)
+    vv = kv[b, :T, E:].float().view(T, nh, dh).transpose(0, 1)
+    ref = (torch.softmax(qq @ kk.transpose(1, 2) / math.sqrt(dh), -1) @ vv).transpose(0, 1).reshape(M, E)
+    err = float((o[b].cpu() - ref).norm() / ref.norm())
+    assert err < 5e-3, (b, err)
+print('ok')
+"""
+    p = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, FACTK_ATTN_TC='1'), capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and 'ok' in p.stdout, p.stderr[-2000:]
+
+
 @pytest.mark.parametrize('M,E,slot,lens', [(75, 512, 1280, [1280, 600, 1]), (12, 64, 128, [100, 128])])
 def test_col_softmax_apply(M, E, slot, lens):
     B, Mp = len(lens), (M + 3) // 4 * 4
