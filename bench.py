@@ -146,6 +146,41 @@ def cpu_baseline(n_videos, threads, state={}):
     return n_videos * T_FRAMES / dt, dt, 'port'
 
 
+def parity_vs_reference(net, n_videos=2):
+    """Free-running bf16 parity of THIS run against the stock reference (same leg as the CPU baseline: the only place the bench
+    touches baseline/_ref): per-block logits (relative L2, blocks before the first segmentation divergence), |dS| per U block
+    and the final per-frame argmax agreement on the first videos of the CPU sample.  None when the reference is not installed."""
+    import contextlib
+    import io
+    ref = stock_reference()
+    if ref is None:
+        return None
+    from fact_clip_b200.utils.synth import make_batch
+    xs, ys = make_batch([T_FRAMES] * n_videos, IN_DIM, N_CLASSES, base_seed=1000)
+    dev = next(net.parameters()).device
+    keep = getattr(net, 'keep_attn', False)
+    net.keep_attn = True
+    ours = net([x.to(dev) for x in xs], [y.to(dev) for y in ys])
+    worst, ds, agree, tot = 0.0, [], 0, 0
+    rel = lambda a, b: float((a.float().cpu() - b).norm() / b.norm().clamp_min(1e-12))
+    for b, (x, y) in enumerate(zip(xs, ys)):
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            r = ref([x], [y])
+        net.stash_video(b)
+        same = True
+        for blk, rb in zip(net.block_list, ref.block_list):
+            if hasattr(rb, 'tdu'):
+                ds.append(abs(int(rb.tdu.num_seg) - int(blk.tdu.num_seg)))
+                same = same and torch.equal(blk.tdu.seg_label.cpu(), rb.tdu.seg_label.cpu())
+            if same:
+                worst = max(worst, rel(blk.frame_clogit, rb.frame_clogit), rel(blk.action_clogit, rb.action_clogit))
+        agree += int((ours[b]['pred'] == r[0]['pred']).sum())
+        tot += len(r[0]['pred'])
+    net.keep_attn = keep
+    return {'videos': n_videos, 'mode': 'free-running (no teacher forcing)', 'worst_logit_rel_l2_before_divergence': worst,
+            'abs_dS_per_U_block': ds, 'argmax_agreement': agree / tot}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -419,6 +454,13 @@ def main():
         for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
             sys.stderr.write(f"  {k:28s} n/step={v['n'] // 2:4d} {v['ms'] / 2:8.3f} ms/step {100 * v['ms'] / tot:5.1f}%\n")
         sys.stderr.write(f"  total {tot / 2:.3f} ms/step (sum of kernel times)\n")
+    # the ceiling of the host-fed number: all ranks copy their pinned feature buffer to the device at the same time, nothing else
+    xin = torch.empty_like(x)
+    def step_h2d():
+        xin.copy_(host, non_blocking=True)
+    ms_h2d = timed(step_h2d, 4, 2)
+    h2d_ceiling = B * T * IN_DIM * 4 * world * 4 / (ms_h2d * 1e-3) / 1e9          # GB/s aggregate over the ranks
+    del xin
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3), drain=drain_e2e)
     # same pipeline with the features stored as bf16 on the host (input staging): half the PCIe bytes
     host16 = host.to(torch.bfloat16).pin_memory()
@@ -453,7 +495,12 @@ def main():
         'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': B * T * IN_DIM * 4 * world,
                 'd2h_bytes_per_step': B * T * 8 * world, 'ms_per_step': ms_e2e / args.steps,
-                'features': 'fp32 on the host (the reference format)', 'sub_batches_per_step': args.e2e_split},
+                'features': 'fp32 on the host (the reference format)', 'sub_batches_per_step': args.e2e_split,
+                'h2d_gbs': B * T * IN_DIM * 4 * world * args.steps / (ms_e2e * 1e-3) / 1e9,
+                'h2d_ceiling_gbs': h2d_ceiling,
+                'frac_of_h2d_ceiling': (B * T * IN_DIM * 4 * world * args.steps / (ms_e2e * 1e-3) / 1e9) / h2d_ceiling,
+                'h2d_ceiling_note': 'aggregate pinned host -> device copy rate of the same buffers with all ranks copying at once and no '
+                                    'kernels running, measured in this run; the end-to-end path is bound by it (PCIe / host memory), not by a kernel'},
         'e2e_bf16_features': {'value': frames_step * args.steps / (ms_e2e16 * 1e-3), 'unit': UNIT,
                               'h2d_bytes_per_step': B * T * IN_DIM * 2 * world, 'd2h_bytes_per_step': B * T * 8 * world,
                               'ms_per_step': ms_e2e16 / args.steps,
@@ -480,6 +527,12 @@ def main():
             threads = os.cpu_count() or 1
             n_cpu = 24      # ~10-30 s of CPU work on the box's 16 cores
             fps, dt, kind = cpu_baseline(n_cpu, threads)
+            try:
+                par = parity_vs_reference(net) if kind == 'reference' else None
+            except Exception as e:
+                par = {'error': f'{type(e).__name__}: {e}'}
+            if par is not None:
+                res['config']['parity_vs_reference'] = par
             res['cpu_baseline'] = {'value': fps, 'unit': UNIT, 'cores': threads, 'kind': kind,
                                    'sample': f'{n_cpu} videos x T={T} of the same workload, '
                                              + ('stock reference FACT_CLIP from baseline/_ref' if kind == 'reference' else 'oracle port')

@@ -44,12 +44,12 @@ BU: {a: sa, a_nhead: 4, f_layers: 4, a_layers: 1, s_layers: 1}
 """
 
 
-def make_project(tmp, g, n_videos=5):
+def make_project(tmp, g, n_videos=5, n_classes=None):
     """Scratch 'project': reference package + scripts, data/gtea/{mapping.txt, features/*.npy (D,T), groundTruth, splits}."""
     shutil.copytree(os.path.join(REF, 'fact_clip'), os.path.join(tmp, 'fact_clip'),
                     ignore=shutil.ignore_patterns('__pycache__'))
     shutil.copytree(os.path.join(REF, 'scripts'), os.path.join(tmp, 'scripts'))
-    C, D = g['n_classes'], g['in_dim']
+    C, D = n_classes or g['n_classes'], g['in_dim']
     d = os.path.join(tmp, 'data', 'gtea')
     for sub in ('features', 'groundTruth', 'splits'):
         os.makedirs(os.path.join(d, sub))
@@ -59,7 +59,7 @@ def make_project(tmp, g, n_videos=5):
     from fact_clip_b200.utils.synth import make_video
     vids = []
     for i in range(n_videos):
-        x, y = (g['videos'][i]['x'], g['videos'][i]['label']) if i < len(g['videos']) else make_video(40 + 13 * i, D, C, seed=900 + i, nseg=5)
+        x, y = (g['videos'][i]['x'], g['videos'][i]['label']) if i < len(g['videos']) else make_video(40 + 13 * i, D, g['n_classes'], seed=900 + i, nseg=5)
         v = f'vid{i}'
         np.save(os.path.join(d, 'features', v + '.npy'), x.numpy().T.copy())          # stored (D, T): the loader transposes
         with open(os.path.join(d, 'groundTruth', v + '.txt'), 'w') as f:
@@ -148,7 +148,7 @@ def test_train_script_unmodified(tmp_path):
     finish, write its checkpoints and the FINISH_PROOF marker, and the training loss must have dropped."""
     tmp = str(tmp_path)
     g = load_golden('tiny_m2_iuUU_trained')
-    make_project(tmp, g, n_videos=6)
+    make_project(tmp, g, n_videos=6, n_classes=11)      # the gtea loader hard-codes background class 10 (utils/dataset.py:189)
     with open(os.path.join(tmp, 'cfg_train.yaml'), 'w') as f:
         f.write(TRAIN_YAML.replace('cmr: 0.0', 'cmr: 0.2').replace('aux: {gpu: 0, debug: false}',
                                                                  'aux: {gpu: 0, debug: false, wandb_offline: true, print_every: 6, eval_every: 18}'))
