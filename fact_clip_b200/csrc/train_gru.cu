@@ -112,6 +112,139 @@ __global__ void __launch_bounds__(GB_THREADS) gru_bwd_kernel(const float* __rest
     cluster.sync();      // no CTA exits while a peer may still write into its shared memory
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Hh = 256 (every shipped configuration): W_hh^T in REGISTERS.  The shared-memory version above streams its 192 KB weight slice
+// through the LSU every step (>= 1536 cycles of shared-memory bandwidth, measured 4.2 us per step with the cluster barrier);
+// here thread (unit u, slice q) of 512 keeps the 96 weights W_hh[96 q .. 96 q + 95][unit] in registers for the whole kernel,
+// the received dgh vector is read as broadcast 128-bit loads, and the exchange is st.async (16 bytes per store) completing a
+// transaction mbarrier of the destination CTA -- no cluster barrier in the loop (same protocol as the forward kernel, tdu.cu).
+constexpr int GB2_THREADS = 512, GB2_Q = 8, GB2_KS = 96;      // 768 = 8 x 96
+
+__device__ __forceinline__ void gb_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GB2_THREADS, 1)
+gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, const void* __restrict__ hout, int h_dtype, int ldh,
+                  const void* __restrict__ dout, int do_dtype, int lddo, const float* __restrict__ w_hh_f,
+                  const float* __restrict__ w_hh_b, float* __restrict__ dgi, float* __restrict__ dgh, int slot,
+                  const int32_t* __restrict__ nseg) {
+    constexpr int Hh = 256, U = 64, G = 768;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int dir = blockIdx.y, b = blockIdx.z;
+    __shared__ __align__(16) float dfull[2][G];
+    __shared__ __align__(16) float mine[3 * U];
+    __shared__ float part[GB2_Q][U];
+    __shared__ float carry[U];
+    __shared__ __align__(8) uint64_t ready[2];
+    const float* W = dir ? w_hh_b : w_hh_f;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int u = tid & (U - 1), q = tid >> 6;
+    float w[GB2_KS];
+#pragma unroll
+    for (int i = 0; i < GB2_KS; ++i) w[i] = W[(size_t)(q * GB2_KS + i) * Hh + rank * U + u];
+    if (tid < U) carry[tid] = 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&ready[i]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(1) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 2; ++i) {       // arm both phases: every step delivers the 768 dgh values from the four CTAs
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&ready[i]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(G * 4) : "memory");
+        }
+    }
+    const int n = min(nseg[b], slot);
+    const bool unit = tid < U;
+    const int j = rank * U + u;
+    const size_t gbase = (size_t)b * slot;
+    const int goff = dir * G, hoff = dir * Hh;
+    float c_gi[3] = {0.f, 0.f, 0.f}, c_gh[3] = {0.f, 0.f, 0.f}, c_hp = 0.f, c_do = 0.f;
+    auto fetch = [&](int t) {
+        if (!unit) return;
+        const size_t row = gbase + t;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            c_gi[g] = gi[row * (6 * (size_t)Hh) + goff + g * Hh + j];
+            c_gh[g] = gh[row * (6 * (size_t)Hh) + goff + g * Hh + j];
+        }
+        const int tp = dir ? t + 1 : t - 1;
+        c_hp = (tp >= 0 && tp < n) ? ld_elem(hout, h_dtype, (gbase + tp) * (size_t)ldh + hoff + j) : 0.f;
+        c_do = ld_elem(dout, do_dtype, row * (size_t)lddo + hoff + j);
+    };
+    if (n > 0) fetch(dir ? 0 : n - 1);
+    const uint32_t dfull_u32 = (uint32_t)__cvta_generic_to_shared(&dfull[0][0]);
+    const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(&ready[0]);
+    __syncthreads();
+    cluster.sync();
+
+    for (int s = 0; s < n; ++s) {
+        const int t = dir ? s : n - 1 - s;
+        const int buf = s & 1;
+        float dh_dir = 0.f;
+        if (unit) {
+            const float r = sigmoidf_(c_gi[0] + c_gh[0]), z = sigmoidf_(c_gi[1] + c_gh[1]);
+            const float nn = tanhf(c_gi[2] + r * c_gh[2]);
+            const float dh = c_do + carry[u];
+            const float dnp = dh * (1.f - z) * (1.f - nn * nn);
+            const float dzp = dh * (c_hp - nn) * z * (1.f - z);
+            const float drp = dnp * c_gh[2] * r * (1.f - r);
+            dh_dir = dh * z;
+            const size_t row = (gbase + t) * (6 * (size_t)Hh) + goff;
+            dgi[row + j] = drp; dgi[row + Hh + j] = dzp; dgi[row + 2 * Hh + j] = dnp;
+            dgh[row + j] = drp; dgh[row + Hh + j] = dzp; dgh[row + 2 * Hh + j] = dnp * r;
+            mine[u] = drp; mine[U + u] = dzp; mine[2 * U + u] = dnp * r;
+        }
+        __syncthreads();
+        if (tid < 192) {                    // 48 x 16 bytes to each of the four CTAs (this one included)
+            const int dest = tid / 48, c = tid % 48, g = c >> 4, u4 = (c & 15) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(&mine[g * U + u4]);
+            const uint32_t o = dfull_u32 + (uint32_t)(buf * G + g * Hh + rank * U + u4) * 4u;
+            uint32_t ra, rb;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(o), "r"(dest));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(bar_u32 + (uint32_t)buf * 8u), "r"(dest));
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                         ::"r"(ra), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                           "r"(__float_as_uint(v.w)), "r"(rb) : "memory");
+        }
+        if (s + 1 < n) fetch(dir ? s + 1 : n - 2 - s);       // next step's operands: in flight across the exchange
+        if (lane == 0) gb_wait(&ready[buf], (s >> 1) & 1);
+        __syncwarp();
+        {
+            const float* dv = &dfull[buf][q * GB2_KS];
+            float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < GB2_KS; i += 4) {
+                const float4 d4 = *reinterpret_cast<const float4*>(dv + i);
+                a4[0] = fmaf(w[i], d4.x, a4[0]); a4[1] = fmaf(w[i + 1], d4.y, a4[1]);
+                a4[2] = fmaf(w[i + 2], d4.z, a4[2]); a4[3] = fmaf(w[i + 3], d4.w, a4[3]);
+            }
+            part[q][u] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+        }
+        __syncthreads();
+        if (tid == 0) {                     // everyone of this CTA has read dfull[buf]: re-arm it for step s + 2
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&ready[buf]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(G * 4) : "memory");
+        }
+        if (unit) {
+            float a = dh_dir;
+#pragma unroll
+            for (int qq = 0; qq < GB2_Q; ++qq) a += part[qq][u];
+            carry[u] = a;
+        }
+    }
+    cluster.sync();      // no CTA exits while a peer may still write into its shared memory
+}
+
 }  // namespace factk
 
 using namespace factk;
@@ -124,6 +257,11 @@ extern "C" int factk_gru_bwd(const float* gi, const float* gh, const void* hout,
                              const int32_t* nseg, void* stream) {
     FACTK_REQUIRE(gi && gh && hout && dout && w_hh_f && w_hh_b && dgi && dgh && nseg && B > 0 && slot > 0, "factk_gru_bwd: bad args");
     FACTK_REQUIRE(Hh == 32 || Hh == 64 || Hh == 128 || Hh == 256, "factk_gru_bwd: Hh = %d unsupported (32/64/128/256)", Hh);
+    if (Hh == 256) {
+        gru_bwd256_kernel<<<dim3(4, 2, B), GB2_THREADS, 0, (cudaStream_t)stream>>>(gi, gh, hout, h_dtype, ldh, dout, do_dtype, lddo, w_hh_f,
+                                                                                 w_hh_b, dgi, dgh, slot, nseg);
+        return check_launch("factk_gru_bwd");
+    }
     const int U = Hh / 4, G = 3 * Hh;
     const size_t smem = ((size_t)G * U + 2 * G + GB_THREADS + U) * sizeof(float);
     static unsigned long long devs = 0;

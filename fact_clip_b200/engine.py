@@ -863,7 +863,9 @@ class FactEngine:
                     bias=self.p('frame_projection.projection.0.bias'))
             ops.layernorm(h1, self.p('frame_projection.projection.1.weight'), self.p('frame_projection.projection.1.bias'),
                           h1, relu=True, len=ln)
-            emb = self.buf('clip_emb', (B, slot, 512))
+            # bf16 mode: the embedding stays bf16 end to end (CTA-pair GEMM -> in-place L2 normalise -> bf16 text GEMM): half the
+            # bytes of the fp32 round trip the three kernels used to make (1 GB per 64 x 4096 frames for the normalisation alone)
+            emb = self.buf('clip_emb', (B, slot, 512), self.act)
             self.mm([S(h1, self.p('frame_projection.projection.4.weight'))], 512, emb, len=ln, tag='clip',
                     bias=self.p('frame_projection.projection.4.bias'))
             ops.l2norm(emb, emb, len=ln)
