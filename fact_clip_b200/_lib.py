@@ -82,7 +82,7 @@ _SIGS = {
     'factk_colsum_ws_floats': (C.c_size_t, [i32, i32, i32]),
     'factk_colsum': (i32, [vp, i32, i32, vp, i32, i32, i32, vp, C.c_longlong, f32, i32, i32, i32, vp, vp, vp]),
     'factk_rows_elementwise': (i32, [i32, vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp, f32, f32, C.c_ulonglong,
-                                     C.c_uint, i32, vp, vp]),
+                                     C.c_uint, i32, vp, vp, vp]),
     'factk_transpose': (i32, [vp, i32, C.c_longlong, vp, i32, C.c_longlong, i32, i32, i32, vp]),
     'factk_splice_bwd': (i32, [vp, i32, i32, vp, i32, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     'factk_row_softmax_bwd': (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),

@@ -148,7 +148,7 @@ __global__ void colsum_partial_kernel(const void* __restrict__ X, int x_dtype, i
 }
 
 // ------------------------------------------------------------------------------------------------ elementwise on rows
-enum { EW_RELU_BWD = 0, EW_AXPY = 1, EW_DROPOUT = 2, EW_DROPOUT_CH = 3, EW_COPY = 4, EW_MUL = 5, EW_ADD = 6, EW_RELU = 7, EW_ROWSCALE = 8 };
+enum { EW_RELU_BWD = 0, EW_AXPY = 1, EW_DROPOUT = 2, EW_DROPOUT_CH = 3, EW_COPY = 4, EW_MUL = 5, EW_ADD = 6, EW_RELU = 7, EW_ROWSCALE = 8, EW_ADDTAB = 9 };
 constexpr int EW_ROWS = 8;      // rows per CTA
 
 // counter-based uniform in [0,1): a 64-bit mix of (seed, site, element index) -- the same value in the forward and the
@@ -171,12 +171,15 @@ __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned 
 //   ADD:        Y = X + R
 //   RELU:       Y = max(X, 0)
 //   ROWSCALE:   Y = X * R[row]               (R: one value per row, e.g. the time mask of basic.time_mask)
+//   ADDTAB:     Y = X + R[ridx ? ridx[b,t] : t][n]   (R: one table shared by the videos: add_positional_encoding with the
+//                                                     sinusoid table, rows picked by frame index or by segment centre)
 // seed_ptr (optional, device): added to ``seed`` -- lets a captured CUDA graph draw new masks on every replay
 // x_slot: row slots per video of X (0 broadcasts one [slot][ldx] table over the videos: positional / query tables)
 __global__ void rows_elementwise_kernel(int op, const void* X, int x_dtype, int ldx, const void* R,
                                         int r_dtype, int ldr, void* Y, int y_dtype, int ldy, int N, int slot,
                                         const int32_t* __restrict__ len, float alpha, float p, unsigned long long seed,
-                                        unsigned site, int x_slot, const unsigned long long* __restrict__ seed_ptr) {
+                                        unsigned site, int x_slot, const unsigned long long* __restrict__ seed_ptr,
+                                        const int32_t* __restrict__ ridx) {
     const int b = blockIdx.z;
     const int len_b = len ? min(len[b], slot) : slot;
     if (seed_ptr) seed += *seed_ptr;
@@ -195,6 +198,7 @@ __global__ void rows_elementwise_kernel(int op, const void* X, int x_dtype, int 
             case EW_ADD: y = x + ld_elem(R, r_dtype, row * ldr + n); break;
             case EW_RELU: y = fmaxf(x, 0.f); break;
             case EW_ROWSCALE: y = x * ld_elem(R, r_dtype, row * ldr); break;
+            case EW_ADDTAB: y = x + ld_elem(R, r_dtype, (size_t)(ridx ? ridx[row] : t) * ldr + n); break;
             default: y = alpha * x; break;
         }
         st_elem(Y, y_dtype, row * ldy + n, y);
@@ -496,14 +500,15 @@ extern "C" int factk_colsum(const void* X, int x_dtype, int ldx, const void* Y, 
 extern "C" int factk_rows_elementwise(int op, const void* X, int x_dtype, int ldx, const void* R, int r_dtype, int ldr, void* Y,
                                       int y_dtype, int ldy, int N, int B, int slot, const int32_t* len, float alpha, float p,
                                       unsigned long long seed, unsigned site, int x_slot, const unsigned long long* seed_ptr,
-                                      void* stream) {
-    FACTK_REQUIRE(X && Y && N > 0 && B > 0 && slot > 0 && op >= 0 && op <= EW_ROWSCALE, "factk_rows_elementwise: bad args");
-    FACTK_REQUIRE(!(op == EW_RELU_BWD || op == EW_MUL || op == EW_ADD || op == EW_ROWSCALE) || R, "factk_rows_elementwise: op %d needs R", op);
+                                      const int32_t* ridx, void* stream) {
+    FACTK_REQUIRE(X && Y && N > 0 && B > 0 && slot > 0 && op >= 0 && op <= EW_ADDTAB, "factk_rows_elementwise: bad args");
+    FACTK_REQUIRE(!(op == EW_RELU_BWD || op == EW_MUL || op == EW_ADD || op == EW_ROWSCALE || op == EW_ADDTAB) || R,
+                  "factk_rows_elementwise: op %d needs R", op);
     FACTK_REQUIRE(p >= 0.f && p < 1.f, "factk_rows_elementwise: p = %f", p);
     const int threads = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
     const int gx = (N + threads * 4 - 1) / (threads * 4);
     rows_elementwise_kernel<<<dim3(gx > 0 ? gx : 1, (slot + EW_ROWS - 1) / EW_ROWS, B), threads, 0, (cudaStream_t)stream>>>(
-        op, X, x_dtype, ldx, R, r_dtype, ldr, Y, y_dtype, ldy, N, slot, len, alpha, p, seed, site, x_slot < 0 ? slot : x_slot, seed_ptr);
+        op, X, x_dtype, ldx, R, r_dtype, ldr, Y, y_dtype, ldy, N, slot, len, alpha, p, seed, site, x_slot < 0 ? slot : x_slot, seed_ptr, ridx);
     return check_launch("factk_rows_elementwise");
 }
 

@@ -101,8 +101,18 @@ class FactEngine:
         return self.derived(key, lambda: W.to(torch.bfloat16))
 
     def x2y_tc(self, rows, H):
-        return (self.mode == 'bf16' and self.use_tc and rows.dtype == torch.bfloat16 and self.frame_pos is None
-                and H % 64 == 0)
+        return self.mode == 'bf16' and self.use_tc and rows.dtype == torch.bfloat16 and H % 64 == 0
+
+    def with_pos(self, rows, rlen, pos_idx, name):
+        """add_positional_encoding (basic.py:313-320) on frame / segment rows for the tensor-core path: ``rows + frame_pos[t or
+        centre]`` materialised ONCE (one elementwise pass, bf16) and shared by every GEMM that reads positioned rows -- the six
+        key projections of the SCA decoder, the f2a and a2f logits of an update block -- so that FACT.fpos models (Epic) stay
+        on the tcgen05 kernels instead of the CUDA-core GEMM with a per-element positional term."""
+        if self.frame_pos is None:
+            return rows
+        y = self.zbuf(name, tuple(rows.shape), rows.dtype)
+        ops.ew(ops.EW_ADDTAB, rows, y, rows.shape[-1], r=self.frame_pos, len=rlen, ridx=pos_idx)
+        return y
 
     def lin(self, x, W, N, out, pos=None, **kw):
         """Token-side Linear with an optional query-position on the input.  On the tensor-core path (tf32) the
@@ -369,6 +379,11 @@ class FactEngine:
             if fpos is None:
                 wkv = self.derived(('wkv', c), lambda: torch.cat([wk, wv], 0))
                 self.mm([S(frame, wkv)], 2 * A, kv, len=rlen, bias=cb[A:], tag='sca_kv')
+            elif self.mode == 'bf16' and self.use_tc and frame.dtype == torch.bfloat16:
+                if i == 0:
+                    frame_p = self.with_pos(frame, rlen, pos_idx, 'sca_rows_pos')
+                self.mm([S(frame_p, wk)], A, kv[:, :, :A], len=rlen, bias=cb[A:2 * A], tag='sca_kv')
+                self.mm([S(frame, wv)], A, kv[:, :, A:], len=rlen, bias=cb[2 * A:], tag='sca_kv')
             else:
                 ops.gemm([S(frame, wk, pos=fpos, pos_idx=pos_idx)], A, kv[:, :, :A], len=rlen, bias=cb[A:2 * A])
                 self.mm([S(frame, wv)], A, kv[:, :, A:], len=rlen, bias=cb[2 * A:])
@@ -459,7 +474,10 @@ class FactEngine:
             self.lin(yq, self.tr(pfx + 'X_K.weight'), H, qt, alpha=alpha)
             self.lin(yq, self.p(pfx + 'X_K.bias')[None, :], 1, cb, alpha=alpha)
         logit = self.buf('f2a_logit_' + tag, (B, slot, Mp))
-        ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc, tag='x2y_rows')
+        if tc:
+            ops.gemm([S(self.with_pos(rows, rlen, pos_idx, 'x2y_rows_pos'), qt)], M, logit, len=rlen, bias=cb[:, :, 0], tc=True, tag='x2y_rows')
+        else:
+            ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tag='x2y_rows')
         attn = self.buf('f2a_attn_' + tag, (B, slot, Mp)) if want_attn else None
         xbar = self.buf('x2y_xbar', (B, M, H))
         ws = self.buf('col_ws', (ops.col_softmax_ws(B, slot, M, H),))
@@ -515,7 +533,10 @@ class FactEngine:
             self.lin(xk, self.tr(pfx + 'Y_Q.weight'), H, kt, alpha=alpha)
             self.lin(xk, self.p(pfx + 'Y_Q.bias')[None, :], 1, cb, alpha=alpha)
         logit = self.buf('a2f_logit_' + tag, (B, slot, Mp))
-        ops.gemm([S(rows, kt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tc=tc, tag='x2y_rows')
+        if tc:      # (the positioned rows of this block were built by f2a a moment ago when fpos is on: same buffer, same values)
+            ops.gemm([S(self.with_pos(rows, rlen, pos_idx, 'x2y_rows_pos'), kt)], M, logit, len=rlen, bias=cb[:, :, 0], tc=True, tag='x2y_rows')
+        else:
+            ops.gemm([S(rows, kt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tag='x2y_rows')
         attn = self.buf('a2f_attn_' + tag, (B, slot, Mp))
         Kp = _round_up(M, 64)
         attn16 = self.buf('a2f_attn16', (B, slot, Kp), torch.bfloat16) if tc else None

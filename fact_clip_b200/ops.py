@@ -363,7 +363,7 @@ def transpose_rows(src, src_bstride, dst, len, D):
 
 
 # ---------------------------------------------------------------------------------------------- training step (train*.cu)
-EW_RELU_BWD, EW_AXPY, EW_DROPOUT, EW_DROPOUT_CH, EW_COPY, EW_MUL, EW_ADD, EW_RELU, EW_ROWSCALE = range(9)
+EW_RELU_BWD, EW_AXPY, EW_DROPOUT, EW_DROPOUT_CH, EW_COPY, EW_MUL, EW_ADD, EW_RELU, EW_ROWSCALE, EW_ADDTAB = range(10)
 _WS = {}
 
 
@@ -408,13 +408,13 @@ def colsum(x, N, out, y=None, len=None, alpha=1.0, accumulate=True, per_video=Fa
           B, slot, L.ptr(len), ws.data_ptr(), L.stream())
 
 
-def ew(op, x, y, N, r=None, len=None, alpha=1.0, p=0.0, seed=0, site=0, bcast=False, seed_ptr=None):
+def ew(op, x, y, N, r=None, len=None, alpha=1.0, p=0.0, seed=0, site=0, bcast=False, seed_ptr=None, ridx=None):
     """Elementwise pass over the valid rows of y ([B, slot, ld]); see factk_rows_elementwise.  bcast: x is one [slot, ld] table."""
     B, slot = y.shape[0], y.shape[1]
     COUNTERS['launches'] += 1
     _call('factk_rows_elementwise', None, int(op), x.data_ptr(), L.dt(x), _row_ld(x), L.ptr(r), L.dt(r) if r is not None else 0,
           _row_ld(r) if r is not None else 0, y.data_ptr(), L.dt(y), _row_ld(y), N, B, slot, L.ptr(len), float(alpha), float(p),
-          int(seed), int(site), 0 if bcast else -1, L.ptr(seed_ptr), L.stream())
+          int(seed), int(site), 0 if bcast else -1, L.ptr(seed_ptr), L.ptr(ridx), L.stream())
 
 
 def transpose(src, dst):

@@ -355,7 +355,8 @@ int factk_colsum(const void* X, int x_dtype, int ldx, const void* Y, int y_dtype
  * 2 Y = dropout(X) (nn.Dropout, p, mask = hash(seed, site, element) -- identical in forward and backward, nothing stored);
  * 3 Y = channel dropout (nn.Dropout2d over (1,D,T): one decision per (video, channel), blocks.py:28,614-617);
  * 4 Y = alpha * X; 5 Y = X * R; 6 Y = X + R; 7 Y = max(X, 0); 8 Y = X * R[row] (one value per row: the time mask of
- * basic.time_mask).  seed_ptr (optional, device memory) is added to seed, so a captured CUDA graph draws new masks on every replay.  x_slot: row slots per video of X (< 0: slot; 0 broadcasts one
+ * basic.time_mask); 9 Y = X + R[ridx ? ridx[b,t] : t] with R one table shared by the videos (add_positional_encoding with the
+ * sinusoid table, rows by frame index or by segment centre, basic.py:313-320, blocks.py:454-455).  seed_ptr (optional, device memory) is added to seed, so a captured CUDA graph draws new masks on every replay.  x_slot: row slots per video of X (< 0: slot; 0 broadcasts one
  * table over the videos -- the learned action_query / positional terms of add_positional_encoding, basic.py:313-320). */
 #define FACTK_EW_RELU_BWD 0
 #define FACTK_EW_AXPY 1
@@ -366,10 +367,11 @@ int factk_colsum(const void* X, int x_dtype, int ldx, const void* Y, int y_dtype
 #define FACTK_EW_ADD 6
 #define FACTK_EW_RELU 7
 #define FACTK_EW_ROWSCALE 8
+#define FACTK_EW_ADDTAB 9
 int factk_rows_elementwise(int op, const void* X, int x_dtype, int ldx, const void* R, int r_dtype, int ldr, void* Y,
                            int y_dtype, int ldy, int N, int B, int slot, const int32_t* len, float alpha, float p,
                            unsigned long long seed, unsigned site, int x_slot, const unsigned long long* seed_ptr,
-                           void* stream);
+                           const int32_t* ridx, void* stream);
 
 /* dst[b][c][r] = src[b][r][c], fp32 (token-sized operands of the attention gradients). */
 int factk_transpose(const float* src, int lds, long long src_bstride, float* dst, int ldd, long long dst_bstride, int R,
