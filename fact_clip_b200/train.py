@@ -99,7 +99,7 @@ class TrainEngine(FactEngine):
         self.tape, self._site = [], 0
         self._params = dict(self.m.named_parameters())
         self._derived = []                # (tensor with autograd graph, gradient accumulator) of the current section
-        self._wt = {}
+        self._wt, self._leaf = {}, {}
         self._wcache = {}                 # bf16 / transposed copies are keyed by address: never let them outlive a step
         self._layout()
         for f in self._flat:
@@ -153,8 +153,8 @@ class TrainEngine(FactEngine):
         if not outs:
             return
         gouts = [g for t, g in derived if t.requires_grad]
-        names = [n for n, p in self._params.items() if p.requires_grad]
-        gs = torch.autograd.grad(outs, [self._params[n] for n in names], gouts, allow_unused=True)
+        names = [n for n, t in self._leaf.items() if t.requires_grad]
+        gs = torch.autograd.grad(outs, [self._leaf[n] for n in names], gouts, allow_unused=True)
         for n, g in zip(names, gs):
             if g is not None:
                 self._pg[n] += g
@@ -194,7 +194,14 @@ class TrainEngine(FactEngine):
         return h
 
     def P(self, name):
-        return self._params[name]
+        """Parameter as the input of a derived-weight function: a fresh leaf sharing the parameter's storage.  Fresh per step on
+        purpose -- the parameter's own AccumulateGrad node outlives a step while anything (a kept ``loss`` tensor) references
+        last step's graph, and it remembers the stream it was created on; reaching it from inside a stream capture makes
+        autograd synchronise the capturing stream with that (default) stream, which invalidates the capture."""
+        t = self._leaf.get(name)
+        if t is None:
+            t = self._leaf[name] = self._params[name].detach().requires_grad_(self._params[name].requires_grad)
+        return t
 
     def taps_w(self, name, groups=1):
         """Conv1d weight (Cout, Cin/groups, k) as [k][Cout][Cin] (dense block-diagonal for grouped convolutions)."""
@@ -1016,5 +1023,5 @@ class TrainEngine(FactEngine):
             st['tape'] = None
         else:
             self.tape = []
-        self._derived, self._wt = [], {}
+        self._derived, self._wt, self._leaf = [], {}, {}
         return self._pg

@@ -384,11 +384,14 @@ def test_graph_captured_step_equals_eager():
         nets.append(net)
     vids = g['videos']
     batches = [[vids[0], vids[2]], [vids[2], vids[0]], [vids[0], vids[2]], [vids[2], vids[0]]]     # same (B, slot), other lengths order
+    held = []           # losses of earlier steps stay referenced (as in a training loop that logs them): their graphs keep the
+                        # parameters' AccumulateGrad nodes of the eager warm-up step alive -- the capture must not depend on those
     for step, batch in enumerate(batches):
         res = []
         for net in nets:
             net.zero_grad(set_to_none=True)
             loss, _ = net([v['x'].to(DEV) for v in batch], [v['label'].to(DEV) for v in batch], compute_loss=True)
+            held.append(loss)
             loss.backward()
             res.append((float(loss.detach()), {n: p.grad.clone() for n, p in net.named_parameters()}))
         assert res[0][0] == res[1][0], (step, res[0][0], res[1][0])
