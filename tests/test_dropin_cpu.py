@@ -106,9 +106,9 @@ def test_variant_parameters_match_reference_layout():
 
 def test_unsupported_modes_raise():
     net = FACT(C.tiny(), 24, 7)                  # a fresh nn.Module is in training mode, like the reference's
-    with pytest.raises(RuntimeError, match='eval mode'):
+    with pytest.raises(RuntimeError, match='CUDA device'):      # training and inference alike: no CPU fallback
         net.forward([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)])
-    with pytest.raises(RuntimeError, match='eval mode'):
+    with pytest.raises(RuntimeError, match='mcriterion'):
         net.forward([torch.zeros(8, 24)], [torch.zeros(8, dtype=torch.long)], compute_loss=True)
     net = FACT(C.tiny(), 24, 7).eval()
     with pytest.raises(RuntimeError, match='mcriterion'):
