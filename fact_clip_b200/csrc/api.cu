@@ -26,7 +26,7 @@ int check_launch(const char* what) {
 
 }  // namespace factk
 
-extern "C" int factk_version(void) { return 120; }   // 1.2: loss, verb/noun heads, staging transpose; mha_tokens / fuse_eval gained a flag
+extern "C" int factk_version(void) { return 200; }   // 2.0: training step (backward kernels, tcgen05 weight gradient, GRU BPTT, loss gradients), tcgen05 attention
 
 extern "C" const char* factk_last_error(void) { return factk::g_err; }
 
