@@ -432,3 +432,48 @@ def test_train_mode_augmentations():
     assert float(l3) != float(l1)
     net.eval()
     assert float(net(xs, ys, compute_loss=True)[0]) == float(e1)
+
+
+def test_train_mode_input_augmentations_vs_oracle():
+    """Row a5 (blocks.py:614-622): channel masking (nn.Dropout2d over whole feature channels, FACT.cmr) and time masking
+    (basic.time_mask, spans from Python's ``random``).  The masks this step drew are read back -- the channel mask by running
+    the same hashed dropout over a tensor of ones, the spans by replaying ``random`` from the same seed -- applied to the inputs
+    on the host, and the oracle's loss and gradients on those masked inputs must equal the train-mode step's (network dropouts off)."""
+    import random
+    cfg = C.PRESETS['gtea']()
+    for blk in (cfg.Bi, cfg.Bu, cfg.BU):
+        if blk.dropout is not None:
+            blk.dropout = 0.0
+    cfg.FACT.cmr = 0.4
+    cfg.TM.use, cfg.TM.t, cfg.TM.m, cfg.TM.p = True, 40, 4, 0.1
+    ncls, D, lens = 11, 2048, [300, 170]
+    torch.manual_seed(0)
+    net = FACT(cfg, D, ncls)
+    xs, ys = make_batch(lens, D, ncls, base_seed=61, nseg=6)
+    cpu_net = net
+    net.compute_mode = 'fp32'
+    net = net.to(DEV).train()
+    net.mcriterion = _criterion(cfg, ncls, [10])
+    random.seed(1234)
+    loss, _ = net([x.to(DEV) for x in xs], [y.to(DEV) for y in ys], compute_loss=True)
+    loss.backward()
+    eng = net.train_engine()
+    # the channel mask of this step: site 1 (the first dropout of the forward), seed = engine seed + step counter
+    ones = torch.ones(len(lens), 384, D, device=DEV)
+    keep = torch.empty_like(ones)
+    ops.ew(ops.EW_DROPOUT_CH, ones, keep, D, p=0.4, seed=eng.seed + eng.step_no, site=1)
+    keep = keep[:, 0].cpu()                                  # [B, D]: 0 or 1 / (1 - p)
+    assert 0.5 < float((keep > 0).float().mean()) < 0.7
+    random.seed(1234)
+    masked = []
+    for b, (x, T) in enumerate(zip(xs, lens)):
+        xm = x * keep[b][None, :]
+        for t0, t1 in eng.time_mask_spans(T, cfg.TM):
+            xm[t0:t1] = 0.0
+        masked.append(xm)
+    assert any(float((m.abs().sum(1) == 0).sum()) > 0 for m in masked), 'no frame was time-masked: the test would not see TM'
+    ref_loss, ref = _oracle_grads(cpu_net.cpu(), cfg, ncls, masked, ys, False, [10], [])
+    assert abs(float(loss.detach()) - ref_loss) <= 2e-4 * abs(ref_loss), (float(loss.detach()), ref_loss)
+    net = net.to(DEV)
+    worst = _check_grads(net, ref, 2e-3, 1e-4)
+    print('train-mode augmentations vs oracle on the masked inputs: loss', float(loss.detach()), ref_loss, 'worst gradient error', worst)
