@@ -38,6 +38,7 @@ class FactEngine:
         self.use_tc = True
         self.use_fused_tcn = True
         self.use_pair_gemm = True
+        self.use_fused_x2y = os.environ.get('FACTK_FUSED_X2Y', '1') != '0'
         self._submits, self._copy_stream, self._slot_free, self._slot_pending = 0, None, [None, None], [None, None]
         self._wcache, self._wsig = {}, None
         # FACTK_FLAT_TOKENS=1 tiles the token rows of all videos as ONE dense matrix (38 instead of 64 tiles at 64 x 75 tokens).
@@ -512,7 +513,7 @@ class FactEngine:
             return [(W[:, H:] @ Wv).float().contiguous(), (b + W[:, H:] @ bv).float().contiguous()]
         return [self.derived(('ywfold', pfx, i), lambda i=i: make()[i]) for i in range(2)]
 
-    def a2f(self, pfx, bc, action, rows, rlen, pos_idx, tag):
+    def a2f(self, pfx, bc, action, rows, rlen, pos_idx, tag, last=True):
         """X2Y_map with X = tokens, Y = rows (frames or segments). -> rows [B,slot,F] act dtype,
         attn_logit [B,slot,Mp], attn [B,slot,Mp] (row = y, col = token)."""
         B, slot, M, F, H = self.B, self.slot, self.ntok, bc['f_dim'], bc['hid_dim']
@@ -532,6 +533,20 @@ class FactEngine:
             self.lin(action, self.p(pfx + 'X_K.weight'), H, xk, pos=qpos, bias=self.p(pfx + 'X_K.bias'))
             self.lin(xk, self.tr(pfx + 'Y_Q.weight'), H, kt, alpha=alpha)
             self.lin(xk, self.p(pfx + 'Y_Q.bias')[None, :], 1, cb, alpha=alpha)
+        if (fold and self.frame_pos is None and self.use_fused_x2y and rows.is_contiguous() and ops.a2f_fused_ok(M, H, F, slot)):
+            # ONE tcgen05 kernel: logits -> softmax in registers -> value GEMM + Y_W, the rows read once (x2y_fused.cu).  The fp32
+            # logits / attention leave the SM only when something reads them: the loss and keep_attn (self.keep), and the
+            # attention of the LAST block for the eval fusion.
+            Kp = _round_up(M, 64)
+            logit = self.buf('a2f_logit_' + tag, (B, slot, Mp)) if self.keep else None
+            attn = self.buf('a2f_attn_' + tag, (B, slot, Mp)) if (self.keep or last) else None
+            vt = self.zbuf('x2y_vt16', (B, F, Kp), torch.bfloat16)          # pad cols stay 0
+            Wav, b2 = self._yw_fold(pfx)
+            wa = self.derived(('wav_rep', pfx, B), lambda: Wav.unsqueeze(0).expand(B, -1, -1))
+            ops.gemm([S(wa, action)], M, vt, tc=True, tag='x2y_vt')
+            out = self.zbuf('a2f_out', (B, slot, F), self.act)
+            ops.a2f_fused(rows, kt, cb[:, :, 0], self.wbf(self.p(pfx + 'Y_W.weight')[:, :H]), vt, b2, out, M, logit=logit, attn=attn, len=rlen)
+            return out, logit, attn
         logit = self.buf('a2f_logit_' + tag, (B, slot, Mp))
         if tc:      # (the positioned rows of this block were built by f2a a moment ago when fpos is on: same buffer, same values)
             ops.gemm([S(self.with_pos(rows, rlen, pos_idx, 'x2y_rows_pos'), kt)], M, logit, len=rlen, bias=cb[:, :, 0], tc=True, tag='x2y_rows')
@@ -578,7 +593,8 @@ class FactEngine:
         tok, st['f2a_attn_logit'], st['f2a_attn'] = self.f2a(pfx + 'f2a_layer.', bc, frame, self.len, None, action, tag, self.keep)
         action = self.action_branch(pfx + 'action_branch.', bc, tok, tag)
         st['action_clogit'] = self.token_splice(action, tag)
-        fr, st['a2f_attn_logit'], st['a2f_attn'] = self.a2f(pfx + 'a2f_layer.', bc, action, frame, self.len, None, tag)
+        fr, st['a2f_attn_logit'], st['a2f_attn'] = self.a2f(pfx + 'a2f_layer.', bc, action, frame, self.len, None, tag,
+                                                            last=(i == len(self.hp['blocks']) - 1))
         frame, st['frame_clogit'], st['pred'] = self.frame_branch(pfx + 'frame_branch.', bc, fr, False, tag)
         return frame, action
 
@@ -635,7 +651,8 @@ class FactEngine:
         tok, st['f2a_attn_logit'], st['f2a_attn_seg'] = self.f2a(pfx + 'f2a_layer.', bc, seg2, nseg, pidx, action, tag, self.keep)
         action = self.action_branch(pfx + 'action_branch.', bc, tok, tag)
         st['action_clogit'] = self.token_splice(action, tag)
-        seg3, st['a2f_attn_logit'], st['a2f_attn_seg'] = self.a2f(pfx + 'a2f_layer.', bc, action, seg2, nseg, pidx, tag)
+        seg3, st['a2f_attn_logit'], st['a2f_attn_seg'] = self.a2f(pfx + 'a2f_layer.', bc, action, seg2, nseg, pidx, tag,
+                                                                last=(i == len(self.hp['blocks']) - 1))
         W = self.p(pfx + 'sf_merge.0.weight')                               # [F, F+H], input = cat[s2f, frame]
         fr = self.zbuf('sf_out', (B, slot, F), self.act)
         # cat[s2f, frame] W^T = (seg3 W1^T)[seg_label] + frame W2^T: the gather moves to a segment-level product

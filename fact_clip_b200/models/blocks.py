@@ -192,7 +192,8 @@ class _FactBase(nn.Module):
         if self.cfg.FACT.trans:
             return self._forward_with_transcripts(seqs, label_list, forced_preds, compute_loss)
         # the verb/noun model's loss reads the action log-probabilities of EVERY block: keep them
-        keep = getattr(self, 'keep_attn', False) or (compute_loss and hasattr(self, 'vids'))
+        # the loss reads the cross-attention logits of EVERY block (and the verb/noun model its action log-probabilities): keep them
+        keep = getattr(self, 'keep_attn', False) or compute_loss
         out = self.engine().run(seqs, forced_preds=forced_preds, keep=keep)
         self._last = out
         if compute_loss:
@@ -354,14 +355,20 @@ class _FactBase(nn.Module):
                 lab = st['seg_label'][b, :T].long()
                 blk.tdu = TDU(lab, st['seg_lens'][b, :S].long())
                 blk.seg_clogit = st['seg_clogit'][b, :S].unsqueeze(1)
-                blk.a2f_attn_logit = st['a2f_attn_logit'][b, :S, :M].unsqueeze(0)
-                blk.a2f_attn = st['a2f_attn_seg'][b, :S, :M][lab].unsqueeze(0)
+                # (the fused a2f kernel writes logits / attention to HBM only when they are read: net.keep_attn, the loss, and
+                # the attention of the last block for the eval fusion)
+                if st.get('a2f_attn_logit') is not None:
+                    blk.a2f_attn_logit = st['a2f_attn_logit'][b, :S, :M].unsqueeze(0)
+                if st.get('a2f_attn_seg') is not None:
+                    blk.a2f_attn = st['a2f_attn_seg'][b, :S, :M][lab].unsqueeze(0)
                 blk.f2a_attn_logit = st['f2a_attn_logit'][b, :S, :M].t().unsqueeze(0)
                 if st.get('f2a_attn_seg') is not None:
                     blk.f2a_attn = st['f2a_attn_seg'][b, :S, :M][lab].t().unsqueeze(0)
             elif 'a2f_attn' in st:
-                blk.a2f_attn_logit = st['a2f_attn_logit'][b, :T, :M].unsqueeze(0)
-                blk.a2f_attn = st['a2f_attn'][b, :T, :M].unsqueeze(0)
+                if st.get('a2f_attn_logit') is not None:
+                    blk.a2f_attn_logit = st['a2f_attn_logit'][b, :T, :M].unsqueeze(0)
+                if st.get('a2f_attn') is not None:
+                    blk.a2f_attn = st['a2f_attn'][b, :T, :M].unsqueeze(0)
                 blk.f2a_attn_logit = st['f2a_attn_logit'][b, :T, :M].t().unsqueeze(0)
                 if st.get('f2a_attn') is not None:
                     blk.f2a_attn = st['f2a_attn'][b, :T, :M].t().unsqueeze(0)

@@ -204,6 +204,24 @@ def col_softmax_apply(logit, x, out, M, ws, attn=None, len=None, E=None):
            B, slot, L.ptr(len), M, E, ws.data_ptr(), L.stream())
 
 
+def a2f_fused_ok(M, H, F, slot):
+    return bool(L.load().factk_a2f_fused_supported(int(M), int(H), int(F), int(slot)))
+
+
+def a2f_fused(rows, kt, cb, wy, vt, bias, out, M, logit=None, attn=None, len=None):
+    """Fused X2Y_map (a2f direction) on bf16 rows [B, slot, H]; kt [B, M, H] bf16, cb [B, M] fp32, wy [F, H] bf16, vt [B, F, Kp] bf16."""
+    B, slot, H = rows.shape
+    F = wy.shape[0]
+    bf = torch.bfloat16
+    assert rows.dtype == kt.dtype == wy.dtype == vt.dtype == out.dtype == bf and cb.dtype == torch.float32
+    assert cb.dim() == 2 and cb.stride(1) == 1
+    ref = logit if logit is not None else attn
+    COUNTERS['launches'] += 1
+    _call('factk_a2f_fused', 'a2f_fused', rows.data_ptr(), _row_ld(rows), kt.data_ptr(), _row_ld(kt), kt.stride(0), cb.data_ptr(), cb.stride(0),
+          wy.data_ptr(), _row_ld(wy), vt.data_ptr(), _row_ld(vt), vt.stride(0), bias.data_ptr(), out.data_ptr(), _row_ld(out),
+          L.ptr(logit), L.ptr(attn), _row_ld(ref) if ref is not None else 0, B, slot, L.ptr(len), M, H, F, L.stream())
+
+
 def tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=None):
     B, slot = pred.shape
     COUNTERS['launches'] += 1

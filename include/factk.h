@@ -174,6 +174,17 @@ int factk_col_softmax_apply(const float* L, int ldl, const void* X, int x_dtype,
                             float* out, int ldo, float* P, int ldp,
                             int B, int slot, const int32_t* len, int M, int E, float* ws, void* stream);
 
+/* X2Y_map in the a2f direction (basic.py:349-389 with X = tokens, Y = rows) as ONE tcgen05 / TMEM kernel per 128-row tile
+ * (csrc/x2y_fused.cu): S = rows . kt^T + cb -> softmax over the tokens with the row of S in registers -> P (bf16, shared
+ * memory) -> out = rows . Wy^T + P . vt^T + bias; the rows are read once, logits / attention reach HBM only when the
+ * pointers are given (loss, eval fusion).  rows X bf16 [B][slot][ldx] (K = H), kt bf16 [B][M][ldkt] (the token-side fold
+ * alpha Wq^T X_K(tokens)), cb fp32 [B][M], Wy bf16 [F][ldwy], vt bf16 [B][F][ldvt] (columns >= M zero up to a multiple of 64),
+ * bias fp32 [F], out bf16 [B][slot][ldo], logit / attn fp32 [B][slot][ldl] or NULL.  H % 64 == 0, F == 256, M <= 128. */
+int factk_a2f_fused_supported(int M, int H, int F, int slot);
+int factk_a2f_fused(const void* X, int ldx, const void* Kt, int ldkt, long long kt_bstride, const float* cb, long long cb_bstride,
+                    const void* Wy, int ldwy, const void* Vt, int ldvt, long long vt_bstride, const float* bias, void* out, int ldo,
+                    float* logit, float* attn, int ldl, int B, int slot, const int32_t* len, int M, int H, int F, void* stream);
+
 /* Run-length segmentation on device (utils/utils.py:25-48, basic.py:597-607, blocks.py:454):
  * pred int32 [B][slot] -> seg_label[B][slot], seg_start[B][slot], seg_len[B][slot],
  * seg_center[B][slot] (= (start+end)/2 floor), nseg[B]. */

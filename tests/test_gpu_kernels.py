@@ -432,3 +432,33 @@ def test_fuse_eval_wide_class_rows(C, M, f_logp):
         ref = O.fuse_eval(ac, attn, torch.softmax(fl, -1), 0.1)
     agree = float((pred[0].cpu() == ref).float().mean())
     assert agree >= 0.99, agree                                   # __expf vs exp can flip a near-tie among hundreds of classes
+
+
+@pytest.mark.parametrize('M,slot,lens,with_outputs', [(75, 512, [512, 300], True), (128, 256, [256], True), (12, 384, [1, 384, 130], False),
+                                                       (64, 128, [100], True), (75, 4096, [4096, 4000], False)])
+def test_a2f_fused(M, slot, lens, with_outputs):
+    """Fused X2Y_map, a2f direction (x2y_fused.cu): logits -> row softmax -> value GEMM + Y_W in one tcgen05 kernel, against fp32 torch."""
+    B, H, F = len(lens), 512, 256
+    Kp, Mp = (M + 63) // 64 * 64, (M + 3) // 4 * 4
+    bf = torch.bfloat16
+    rows = rnd(B, slot, H, seed=31).to(bf)
+    kt = (rnd(B, M, H, seed=32) * 0.1).to(bf)
+    cb = rnd(B, M, seed=33)
+    wy = (rnd(F, H, seed=34) * H ** -0.5).to(bf)
+    vt = torch.zeros(B, F, Kp, dtype=bf)
+    vt[:, :, :M] = rnd(B, F, M, seed=35).to(bf)
+    bias = rnd(F, seed=36)
+    out = torch.zeros(B, slot, F, dtype=bf, device=DEV)
+    logit = torch.zeros(B, slot, Mp, device=DEV) if with_outputs else None
+    attn = torch.zeros(B, slot, Mp, device=DEV) if with_outputs else None
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    ops.a2f_fused(rows.to(DEV), kt.to(DEV), cb.to(DEV), wy.to(DEV), vt.to(DEV), bias.to(DEV), out, M, logit=logit, attn=attn, len=ln)
+    for b, T in enumerate(lens):
+        x = rows[b, :T].float()
+        lg = x @ kt[b].float().t() + cb[b]
+        p = torch.softmax(lg, -1)
+        ref = x @ wy.float().t() + p.to(bf).float() @ vt[b, :, :M].float().t() + bias
+        assert rel_l2(out[b, :T].float(), ref) < 6e-3, (b, rel_l2(out[b, :T].float(), ref))
+        if with_outputs:
+            assert rel_l2(logit[b, :T, :M], lg) < 1e-5 and rel_l2(attn[b, :T, :M], p) < 1e-4
+        assert float(out[b, T:].float().abs().sum()) == 0.0          # rows past the end are never written
