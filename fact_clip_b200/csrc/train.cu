@@ -130,21 +130,30 @@ void launch_partial_reduce(const float* ws, size_t pstride, int psz, int K, floa
 constexpr int CSUM_RC = 128;      // rows per partial of the column sums / LayerNorm affine gradients
 __host__ __device__ inline int csum_nchunk(int slot) { return (slot + CSUM_RC - 1) / CSUM_RC; }
 
-__global__ void colsum_partial_kernel(const void* __restrict__ X, int x_dtype, int ldx, const void* __restrict__ Y, int y_dtype,
-                                      int ldy, int N, float* __restrict__ ws, int slot, const int32_t* __restrict__ len, int nchunk) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+// 64 columns x 4 row groups per CTA: thread (c, g) sums rows r0 + g, r0 + g + 4, ...; the four partials combine in a fixed order
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restrict__ X, int x_dtype, int ldx, const void* __restrict__ Y,
+                                                             int y_dtype, int ldy, int N, float* __restrict__ ws, int slot,
+                                                             const int32_t* __restrict__ len, int nchunk) {
+    __shared__ float part[4][64];
+    const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const int n = blockIdx.x * 64 + c;
     const int chunk = blockIdx.y, b = blockIdx.z;
     const int len_b = len ? min(len[b], slot) : slot;
     const int r0 = chunk * CSUM_RC;
-    if (r0 >= len_b || n >= N) return;
+    if (r0 >= len_b) return;
     const int r1 = min(r0 + CSUM_RC, len_b);
     float s = 0.f;
-    for (int r = r0; r < r1; ++r) {
-        float v = ld_elem(X, x_dtype, ((size_t)b * slot + r) * (size_t)ldx + n);
-        if (Y) v *= ld_elem(Y, y_dtype, ((size_t)b * slot + r) * (size_t)ldy + n);
-        s += v;
+    if (n < N) {
+#pragma unroll 4
+        for (int r = r0 + g; r < r1; r += 4) {
+            float v = ld_elem(X, x_dtype, ((size_t)b * slot + r) * (size_t)ldx + n);
+            if (Y) v *= ld_elem(Y, y_dtype, ((size_t)b * slot + r) * (size_t)ldy + n);
+            s += v;
+        }
     }
-    ws[(size_t)(b * nchunk + chunk) * N + n] = s;
+    part[g][c] = s;
+    __syncthreads();
+    if (g == 0 && n < N) ws[(size_t)(b * nchunk + chunk) * N + n] = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
 }
 
 // ------------------------------------------------------------------------------------------------ elementwise on rows
@@ -184,8 +193,45 @@ __global__ void rows_elementwise_kernel(int op, const void* X, int x_dtype, int 
     const int len_b = len ? min(len[b], slot) : slot;
     if (seed_ptr) seed += *seed_ptr;
     const float keep_scale = (op == EW_DROPOUT || op == EW_DROPOUT_CH) ? 1.f / (1.f - p) : 0.f;
+    // 4 consecutive elements per thread when every operand allows 8 / 16-byte accesses (the common case: channel counts and
+    // leading dimensions are multiples of 4); the scalar loop below serves the rest
+    const bool v4 = (N & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0 && (!R || (ldr & 3) == 0 || op == EW_ROWSCALE) &&
+                    (reinterpret_cast<uintptr_t>(X) & 15u) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 &&
+                    (!R || (reinterpret_cast<uintptr_t>(R) & 15u) == 0);
     for (int t = blockIdx.y * EW_ROWS; t < min((int)(blockIdx.y + 1) * EW_ROWS, len_b); ++t) {
     const size_t row = (size_t)b * slot + t, xrow = (size_t)b * x_slot + t;
+    if (v4) {
+        const size_t rrow = (op == EW_ADDTAB) ? (size_t)(ridx ? ridx[row] : t) : row;
+        for (int n = (blockIdx.x * blockDim.x + threadIdx.x) * 4; n < N; n += gridDim.x * blockDim.x * 4) {
+            const float4 xv = ld_vec4(X, x_dtype, xrow * ldx + n);
+            float x[4] = {xv.x, xv.y, xv.z, xv.w}, r[4] = {0.f, 0.f, 0.f, 0.f}, y0[4] = {0.f, 0.f, 0.f, 0.f}, y[4];
+            if (op == EW_RELU_BWD || op == EW_MUL || op == EW_ADD || op == EW_ADDTAB) {
+                const float4 rv = ld_vec4(R, r_dtype, rrow * ldr + n);
+                r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
+            } else if (op == EW_ROWSCALE) {
+                r[0] = r[1] = r[2] = r[3] = ld_elem(R, r_dtype, row * ldr);
+            }
+            if (op == EW_AXPY) {
+                const float4 yv = ld_vec4(Y, y_dtype, row * ldy + n);
+                y0[0] = yv.x; y0[1] = yv.y; y0[2] = yv.z; y0[3] = yv.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                switch (op) {
+                    case EW_RELU_BWD: y[j] = r[j] > 0.f ? x[j] : 0.f; break;
+                    case EW_AXPY: y[j] = y0[j] + alpha * x[j]; break;
+                    case EW_DROPOUT: y[j] = hash_uniform(seed, site, row * (size_t)N + n + j) >= p ? x[j] * keep_scale : 0.f; break;
+                    case EW_DROPOUT_CH: y[j] = hash_uniform(seed, site, (size_t)b * N + n + j) >= p ? x[j] * keep_scale : 0.f; break;
+                    case EW_MUL: case EW_ROWSCALE: y[j] = x[j] * r[j]; break;
+                    case EW_ADD: case EW_ADDTAB: y[j] = x[j] + r[j]; break;
+                    case EW_RELU: y[j] = fmaxf(x[j], 0.f); break;
+                    default: y[j] = alpha * x[j]; break;
+                }
+            }
+            st_vec4(Y, y_dtype, row * ldy + n, make_float4(y[0], y[1], y[2], y[3]));
+        }
+        continue;
+    }
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
         const float x = ld_elem(X, x_dtype, xrow * ldx + n);
         float y;
@@ -491,7 +537,7 @@ extern "C" int factk_colsum(const void* X, int x_dtype, int ldx, const void* Y, 
     FACTK_REQUIRE(X && out && ws && N > 0 && B > 0 && slot > 0, "factk_colsum: bad args");
     const int nchunk = csum_nchunk(slot), per_video = out_bstride != 0;
     cudaStream_t st = (cudaStream_t)stream;
-    colsum_partial_kernel<<<dim3((N + 63) / 64, nchunk, B), 64, 0, st>>>(X, x_dtype, ldx, Y, y_dtype, ldy, N, ws, slot, len, nchunk);
+    colsum_partial_kernel<<<dim3((N + 63) / 64, nchunk, B), 256, 0, st>>>(X, x_dtype, ldx, Y, y_dtype, ldy, N, ws, slot, len, nchunk);
     partial_reduce_kernel<<<dim3((N + 63) / 64, per_video ? B : 1), 64, 0, st>>>(ws, (size_t)N, N, N, out, N, out_bstride, B, slot, len,
                                                                                  nchunk, CSUM_RC, alpha, accumulate, per_video);
     return check_launch("factk_colsum");
@@ -505,7 +551,7 @@ extern "C" int factk_rows_elementwise(int op, const void* X, int x_dtype, int ld
     FACTK_REQUIRE(!(op == EW_RELU_BWD || op == EW_MUL || op == EW_ADD || op == EW_ROWSCALE || op == EW_ADDTAB) || R,
                   "factk_rows_elementwise: op %d needs R", op);
     FACTK_REQUIRE(p >= 0.f && p < 1.f, "factk_rows_elementwise: p = %f", p);
-    const int threads = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
+    const int threads = N >= 1024 ? 256 : (N >= 512 ? 128 : 64);
     const int gx = (N + threads * 4 - 1) / (threads * 4);
     rows_elementwise_kernel<<<dim3(gx > 0 ? gx : 1, (slot + EW_ROWS - 1) / EW_ROWS, B), threads, 0, (cudaStream_t)stream>>>(
         op, X, x_dtype, ldx, R, r_dtype, ldr, Y, y_dtype, ldy, N, slot, len, alpha, p, seed, site, x_slot < 0 ? slot : x_slot, seed_ptr, ridx);

@@ -609,8 +609,10 @@ class TrainEngine(FactEngine):
             else:
                 wq, wk, wv = self.W(c + 'q_proj_weight'), self.W(c + 'k_proj_weight'), self.W(c + 'v_proj_weight')
             cq = self.linear([src(self.addpos(tgt, qpos), wq)], A, bias=cb[:A])
-            kk = self.linear([src(frame, wk, pos=self.frame_pos, pos_idx=pos_idx)], A, bias=cb[A:2 * A], ln=rlen, dtype=torch.float32, tag='sca_kv')
-            vv = self.linear([src(frame, wv)], A, bias=cb[2 * A:], ln=rlen, dtype=torch.float32, tag='sca_kv')
+            # keys / values in the activation dtype (bf16 in bf16 mode, like the inference engine): their projections, data and
+            # weight gradients then run on the tensor cores
+            kk = self.linear([src(frame, wk, pos=self.frame_pos, pos_idx=pos_idx)], A, bias=cb[A:2 * A], ln=rlen, tag='sca_kv')
+            vv = self.linear([src(frame, wv)], A, bias=cb[2 * A:], ln=rlen, tag='sca_kv')
             o = self.cross_attn(cq, kk, vv, nh, rlen, p)
             t2 = self.linear([src(o, self.W(c + 'out_proj.weight'))], A, bias=self.W(c + 'out_proj.bias'))
             tgt = self.layernorm(self.dropout(t2, p), q + 'norm2.weight', q + 'norm2.bias', res=tgt)
