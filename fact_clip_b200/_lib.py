@@ -28,11 +28,21 @@ class Gemm(C.Structure):
                 ('res_dtype', i32), ('ldres', i32), ('Y', vp), ('y_dtype', i32), ('ldy', i32)]
 
 
+class HeadsMM(C.Structure):
+    _fields_ = [('A', vp), ('a_dtype', i32), ('lda', i32), ('a_bstride', i64), ('a_hstride', i32), ('a_kmajor', i32),
+                ('Bm', vp), ('b_dtype', i32), ('ldb', i32), ('b_bstride', i64), ('b_hstride', i32), ('b_kmajor', i32),
+                ('C', vp), ('c_dtype', i32), ('ldc', i32), ('c_bstride', i64), ('c_hstride', i32), ('accumulate', i32),
+                ('M', i32), ('N', i32), ('K', i32), ('batch', i32), ('nhead', i32), ('len_mode', i32),
+                ('len', vp), ('ws', vp), ('alpha', f32), ('reserved_', i32)]
+
+
 _SIGS = {
     'factk_version': (i32, []),
     'factk_last_error': (C.c_char_p, []),
     'factk_device_check': (i32, []),
     'factk_gemm': (i32, [C.POINTER(Gemm), vp]),
+    'factk_heads_mm_ws_floats': (C.c_size_t, [i32, i32, i32, i32, i32]),
+    'factk_heads_mm': (i32, [C.POINTER(HeadsMM), vp]),
     'factk_gemm_tc': (i32, [C.POINTER(Gemm), vp]),
     'factk_gemm_tc_supported': (i32, [C.POINTER(Gemm)]),
     'factk_gemm_pair_supported': (i32, [i32, i32]),

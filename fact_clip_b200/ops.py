@@ -5,6 +5,7 @@ hand-written kernels on the current stream and returns nothing (outputs are writ
 Layout: "rows" tensors are [B, slot, ld] with ``len`` (int32 [B], device) valid rows per video.
 """
 import ctypes
+import os
 
 import torch
 
@@ -13,6 +14,7 @@ from . import _lib as L
 
 COUNTERS = {'launches': 0}
 TIMER = None
+PROF_SHAPES = os.environ.get('FACTK_PROF_SHAPES') == '1'        # profiling aid: key SIMT GEMM / wgrad timings by shape
 
 
 class KernelTimer:
@@ -87,6 +89,8 @@ def gemm(srcs, N, out, len=None, bias=None, alpha=1.0, relu=False, res=None, tag
     if res is not None:
         g.res, g.res_dtype, g.ldres = res.data_ptr(), L.dt(res), _row_ld(res)
     g.Y, g.y_dtype, g.ldy = out.data_ptr(), L.dt(out), _row_ld(out)
+    if PROF_SHAPES and not tc:
+        tag = f"{tag or 'gemm_simt'}[{B}x{slot} N={N} K={'+'.join(str(g.src[i].K) for i in range(g.nsrc))} {str(srcs[0]['A'].dtype)[6:]}>{str(out.dtype)[6:]}]"
     _call('factk_gemm_tc' if tc else 'factk_gemm', tag or ('gemm_tc' if tc else 'gemm_simt'), g, L.stream())
     COUNTERS['launches'] += 1
 
@@ -410,10 +414,28 @@ def wgrad(dz, a, N, K, dw, off=0, len=None, alpha=1.0, accumulate=True, pos=None
         return
     ws = _ws(dz.device, lib.factk_wgrad_ws_floats(B, slot, N, K))
     COUNTERS['launches'] += 2
-    _call('factk_wgrad', 'wgrad', dz.data_ptr(), L.dt(dz), _row_ld(dz), a.data_ptr(), L.dt(a), _row_ld(a), a_slot, int(off),
+    _call('factk_wgrad', f"wgrad[{B}x{slot} N={N} K={K} {str(dz.dtype)[6:]},{str(a.dtype)[6:]}{' pos' if pos is not None else ''}{' bcastA' if a_slot == 0 else ''}]" if PROF_SHAPES else 'wgrad', dz.data_ptr(), L.dt(dz), _row_ld(dz), a.data_ptr(), L.dt(a), _row_ld(a), a_slot, int(off),
           L.ptr(pos), pos.stride(0) if pos is not None else 0, (pos_d if pos_d is not None else pos.shape[-1]) if pos is not None else 0,
           L.ptr(pos_idx), N, K, dw.data_ptr(), dw.stride(-2), dw.stride(0) if per_video else 0, float(alpha), int(accumulate),
           B, slot, L.ptr(len), ws.data_ptr(), L.stream())
+
+
+def heads_mm(A, Bm, Cc, M, N, K, nhead, a_hs, b_hs, c_hs, a_kmajor=False, b_kmajor=False, len=None, len_mode=0, alpha=1.0,
+             accumulate=False):
+    """Head-batched C[b][h](m, n) (+)= alpha * sum_k A[b][h](m, k) Bm[b][h](n, k) (csrc/train_attn.cu): A, Bm, Cc rows tensors
+    [B, rows, ld]; head h of an operand starts at column h * hs; k-major operands hold (m, k) at row k."""
+    g = L.HeadsMM()
+    B = Cc.shape[0]
+    bs = lambda t: 0 if (t.shape[0] == 1 and B > 1) else t.stride(0)
+    g.A, g.a_dtype, g.lda, g.a_bstride, g.a_hstride, g.a_kmajor = A.data_ptr(), L.dt(A), _row_ld(A), bs(A), a_hs, int(a_kmajor)
+    g.Bm, g.b_dtype, g.ldb, g.b_bstride, g.b_hstride, g.b_kmajor = Bm.data_ptr(), L.dt(Bm), _row_ld(Bm), bs(Bm), b_hs, int(b_kmajor)
+    g.C, g.c_dtype, g.ldc, g.c_bstride, g.c_hstride, g.accumulate = Cc.data_ptr(), L.dt(Cc), _row_ld(Cc), Cc.stride(0), c_hs, int(accumulate)
+    g.M, g.N, g.K, g.batch, g.nhead, g.len_mode = M, N, K, B, nhead, len_mode
+    g.len, g.alpha = L.ptr(len), float(alpha)
+    n = L.load().factk_heads_mm_ws_floats(B, nhead, M, N, K)
+    g.ws = _ws(Cc.device, n).data_ptr() if n else None
+    COUNTERS['launches'] += 2 if n else 1
+    _call('factk_heads_mm', f"heads_mm[{M}x{N}x{K}]" if PROF_SHAPES else 'heads_mm', g, L.stream())
 
 
 def colsum(x, N, out, y=None, len=None, alpha=1.0, accumulate=True, per_video=False):

@@ -429,16 +429,14 @@ class TrainEngine(FactEngine):
 
     # ------------------------------------------------------------------ attention
     def mha_self(self, q, k, v, nhead, p_drop=0.0):
-        """Token self-attention core of nn.MultiheadAttention (basic.py:437,500): per head logits GEMM -> row softmax ->
-        (attention dropout) -> apply GEMM, every operand a [B, M, *] rows tensor; q, k, v: Vars [B, M, A]."""
+        """Token self-attention core of nn.MultiheadAttention (basic.py:437,500): logits -> row softmax -> (attention
+        dropout) -> apply, each product one head-batched launch (ops.heads_mm); q, k, v: Vars [B, M, A]."""
         B, M, A = q.v.shape
         dh, Mp = A // nhead, _round_up(M, 4)
         alpha = 1.0 / math.sqrt(dh)
-        hs = lambda t, h: t[:, :, h * dh:(h + 1) * dh]
-        hm = lambda t, h: t[:, :, h * Mp:(h + 1) * Mp]
+        mm = lambda a, b, c, m, n, kd, hs, **kw: ops.heads_mm(a, b, c, m, n, kd, nhead, *hs, **kw)
         L_ = self.new((B, M, nhead * Mp), zero=True)
-        for h in range(nhead):
-            ops.gemm([S(hs(q.v, h), hs(k.v, h))], M, hm(L_, h), alpha=alpha)
+        mm(q.v, k.v, L_, M, M, dh, (dh, dh, Mp), alpha=alpha)
         Pv = Var(self.new((B, M, nhead * Mp), zero=True))
         Pr = Pv.v.view(B, M * nhead, Mp)
         ops.row_softmax(L_.view(B, M * nhead, Mp), Pr, M)
@@ -449,41 +447,33 @@ class TrainEngine(FactEngine):
                 return
             dL = self.new((B, M, nhead * Mp), zero=True)
             ops.row_softmax_bwd(Pr, Pv.g.view(B, M * nhead, Mp), dL.view(B, M * nhead, Mp), M)
-            kT, qg, kg = self.new((B, A, Mp), zero=True), self.G(q), self.G(k)
-            ops.transpose(k.v, kT[:, :, :M])
-            for h in range(nhead):
-                ops.gemm([S(hm(dL, h), kT[:, h * dh:(h + 1) * dh, :], K=M)], dh, hs(qg, h), alpha=alpha, res=hs(qg, h))
-                ops.wgrad(hm(dL, h), hs(q.v, h), M, dh, hs(kg, h), alpha=alpha, per_video=True)
+            mm(dL, k.v, self.G(q), M, dh, M, (Mp, dh, dh), b_kmajor=True, alpha=alpha, accumulate=True)
+            mm(dL, q.v, self.G(k), M, dh, M, (Mp, dh, dh), a_kmajor=True, b_kmajor=True, alpha=alpha, accumulate=True)
         self.tape.append(bwd_softmax)
         Pd = self.dropout(Pv, p_drop)            # nn.MultiheadAttention drops attention weights (its own tape entry)
-        vT = self.new((B, A, Mp), zero=True)
-        ops.transpose(v.v, vT[:, :, :M])
         o = Var(self.new((B, M, A)))
-        for h in range(nhead):
-            ops.gemm([S(hm(Pd.v, h), vT[:, h * dh:(h + 1) * dh, :], K=M)], dh, hs(o.v, h))
+        mm(Pd.v, v.v, o.v, M, dh, M, (Mp, dh, dh), b_kmajor=True)
 
         def bwd_apply():                         # o -> P, v
             if o.g is None:
                 return
-            dP, vg = self.G(Pd), self.G(v)
-            for h in range(nhead):
-                ops.gemm([S(hs(o.g, h), hs(v.v, h))], M, hm(dP, h), res=hm(dP, h))
-                ops.wgrad(hm(Pd.v, h), hs(o.g, h), M, dh, hs(vg, h), per_video=True)
+            mm(o.g, v.v, self.G(Pd), M, M, dh, (dh, dh, Mp), accumulate=True)
+            mm(Pd.v, o.g, self.G(v), M, dh, M, (Mp, dh, dh), a_kmajor=True, b_kmajor=True, accumulate=True)
         self.tape.append(bwd_apply)
         return o
 
     def cross_attn(self, q, kk, vv, nhead, rlen, p_drop=0.0):
         """Tokens attend rows (SCALayer cross attention core, basic.py:507-514): softmax over the valid rows per (head, token).
-        q: Var [B, M, A] (projected queries); kk, vv: Vars [B, slot, A] (projected keys / values, fp32)."""
+        q: Var [B, M, A] (projected queries); kk, vv: Vars [B, slot, A] (projected keys / values).  The probabilities live
+        frame-major, [B, slot, nhead * Mp]; the six products are head-batched launches (ops.heads_mm), the reductions over the
+        frames (apply, dq) split the frames across CTAs."""
         B, M, A = q.v.shape
         slot = kk.v.shape[1]
         dh, Mp = A // nhead, _round_up(M, 4)
         alpha = 1.0 / math.sqrt(dh)
-        hs = lambda t, h: t[:, :, h * dh:(h + 1) * dh]
-        hm = lambda t, h: t[:, :, h * Mp:(h + 1) * Mp]
+        mm = lambda a, b, c, m, n, kd, hs, **kw: ops.heads_mm(a, b, c, m, n, kd, nhead, *hs, len=rlen, **kw)
         L_ = self.new((B, slot, nhead * Mp), zero=True)
-        for h in range(nhead):
-            ops.gemm([S(hs(kk.v, h), hs(q.v, h))], M, hm(L_, h), len=rlen, alpha=alpha)
+        mm(kk.v, q.v, L_, slot, M, dh, (dh, dh, Mp), len_mode=1, alpha=alpha)
         Pv = Var(self.new((B, slot, nhead * Mp), zero=True), rlen)
         ops.col_softmax(L_, Pv.v, nhead * Mp, len=rlen)
         del L_
@@ -493,26 +483,18 @@ class TrainEngine(FactEngine):
                 return
             dL = Pv.g                                   # in place: element-wise in P and dP once the column sums exist
             ops.col_softmax_bwd(Pv.v, Pv.g, dL, nhead * Mp, len=rlen)
-            qT, kg, qg = self.new((B, A, Mp), zero=True), self.G(kk), self.G(q)
-            ops.transpose(q.v, qT[:, :, :M])
-            for h in range(nhead):
-                ops.gemm([S(hm(dL, h), qT[:, h * dh:(h + 1) * dh, :], K=M)], dh, hs(kg, h), len=rlen, alpha=alpha, res=hs(kg, h))
-                ops.wgrad(hm(dL, h), hs(kk.v, h), M, dh, hs(qg, h), len=rlen, alpha=alpha, per_video=True)
+            mm(dL, q.v, self.G(kk), slot, dh, M, (Mp, dh, dh), b_kmajor=True, len_mode=1, alpha=alpha, accumulate=True)
+            mm(dL, kk.v, self.G(q), M, dh, slot, (Mp, dh, dh), a_kmajor=True, b_kmajor=True, len_mode=2, alpha=alpha, accumulate=True)
         self.tape.append(bwd_softmax)
         Pd = self.dropout(Pv, p_drop)
         o = Var(self.new((B, M, A)))
-        for h in range(nhead):
-            ops.wgrad(hm(Pd.v, h), hs(vv.v, h), M, dh, hs(o.v, h), len=rlen, accumulate=False, per_video=True)
+        mm(Pd.v, vv.v, o.v, M, dh, slot, (Mp, dh, dh), a_kmajor=True, b_kmajor=True, len_mode=2)
 
         def bwd_apply():
             if o.g is None:
                 return
-            dP, vg = self.G(Pd), self.G(vv)
-            oT = self.new((B, A, Mp), zero=True)
-            ops.transpose(o.g, oT[:, :, :M])
-            for h in range(nhead):
-                ops.gemm([S(hs(vv.v, h), hs(o.g, h))], M, hm(dP, h), len=rlen, res=hm(dP, h))
-                ops.gemm([S(hm(Pd.v, h), oT[:, h * dh:(h + 1) * dh, :], K=M)], dh, hs(vg, h), len=rlen, res=hs(vg, h))
+            mm(vv.v, o.g, self.G(Pd), slot, M, dh, (dh, dh, Mp), len_mode=1, accumulate=True)
+            mm(Pd.v, o.g, self.G(vv), slot, dh, M, (Mp, dh, dh), b_kmajor=True, len_mode=1, accumulate=True)
         self.tape.append(bwd_apply)
         return o
 

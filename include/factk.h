@@ -345,6 +345,37 @@ int factk_wgrad(const void* dZ, int dz_dtype, int lddz, const void* A, int a_dty
                 long long dw_bstride, float alpha, int accumulate, int B, int slot, const int32_t* len, float* ws,
                 void* stream);
 
+/* Head-batched products of nn.MultiheadAttention's forward / backward (models/basic.py:437,500,507-514; csrc/train_attn.cu),
+ * one launch for all heads of all videos:
+ *   C[b][h](m, n) (+)= alpha * sum_k A[b][h](m, k) * Bm[b][h](n, k),   m < M, n < N, k < K
+ * Each operand is a column band of a rows tensor: (video b, head h) starts at element b * bstride + h * hstride; a
+ * k-contiguous operand holds (m, k) at [m * ld + k], a k-major one at [k * ld + m]; C holds (m, n) at [m * ldc + n].
+ * len_mode 1: len[b] bounds m (the frames are the rows of C); 2: len[b] bounds k (a reduction over the frames: k is split
+ * across CTAs and the partials are summed in a fixed order - ws: factk_heads_mm_ws_floats(...) floats, may be NULL when 0).
+ * The six products of one attention are three layouts: logits / dP (A, Bm k-contiguous, K = head dim), apply / dQ-of-rows
+ * (A k-contiguous probabilities, Bm k-major), and the transposed apply (A, Bm k-major). */
+typedef struct {
+    const void* A;
+    int32_t a_dtype, lda;
+    int64_t a_bstride;
+    int32_t a_hstride, a_kmajor;
+    const void* Bm;
+    int32_t b_dtype, ldb;
+    int64_t b_bstride;
+    int32_t b_hstride, b_kmajor;
+    void* C;
+    int32_t c_dtype, ldc;
+    int64_t c_bstride;
+    int32_t c_hstride, accumulate;
+    int32_t M, N, K, batch, nhead, len_mode;
+    const int32_t* len;
+    float* ws;
+    float alpha;
+    int32_t reserved_;
+} factk_heads_mm_t;
+size_t factk_heads_mm_ws_floats(int batch, int nhead, int M, int N, int K);
+int factk_heads_mm(const factk_heads_mm_t* g, void* stream);
+
 /* The same contraction on the tensor cores (csrc/wgrad_tc.cu): bf16 dZ and A, both consumed as MN-major tcgen05 operands straight
  * from their row-major layout (TMA boxes of 64 frames x 64 channels), fp32 accumulation in tensor memory, per-chunk partial
  * tiles summed in a fixed order.  Needs N % 64 == 0, K % 64 == 0, 16-byte aligned rows, slot % 64 == 0, and ZERO rows in

@@ -101,6 +101,47 @@ def test_wgrad_tensor_core(B, slot, N, K, off, lens):
     assert rel(dw2, 1.5 * ref) < 1e-5
 
 
+@pytest.mark.parametrize('B,T,M,nhead,dh,lens,dt', [(2, 700, 75, 8, 32, [700, 333], torch.float32), (1, 5000, 300, 8, 32, [4801], torch.bfloat16),
+                                                    (3, 130, 9, 2, 5, [130, 1, 64], torch.float32), (1, 300, 300, 4, 64, [300], torch.float32)])
+def test_heads_mm_three_layouts(B, T, M, nhead, dh, lens, dt):
+    """ops.heads_mm against einsum in float64: the logits / apply / transposed-apply layouts of the attention cores
+    (train.py mha_self, cross_attn), ragged videos, unaligned sizes, bf16 row operands, accumulate and the k-split path."""
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    A, Mp = nhead * dh, (M + 3) // 4 * 4
+    kk = torch.randn(B, T, A, generator=g).to(dt).to(DEV)
+    q = torch.randn(B, M, A, generator=g).to(DEV)
+    P = torch.randn(B, T, nhead * Mp, generator=g).to(DEV)
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    valid = (torch.arange(T, device=DEV)[None] < ln[:, None]).double()[..., None, None]
+    k64 = kk.double().view(B, T, nhead, dh) * valid
+    q64 = q.double().view(B, M, nhead, dh)
+    P64 = P.double().view(B, T, nhead, Mp)[..., :M] * valid
+    # logits: L[b, t, h, m] = alpha sum_d kk q  (rows beyond len untouched)
+    L_ = torch.full((B, T, nhead * Mp), 7.0, device=DEV)
+    ops.heads_mm(kk, q, L_, T, M, dh, nhead, dh, dh, Mp, len=ln, len_mode=1, alpha=0.5)
+    ref = 0.5 * torch.einsum('bthd,bmhd->bthm', k64, q64)
+    got = L_.view(B, T, nhead, Mp).double()
+    assert rel(got[..., :M] * valid, ref) < 1e-5
+    assert torch.equal(got[..., M:], torch.full_like(got[..., M:], 7.0))
+    for b in range(B):
+        assert torch.equal(L_[b, lens[b]:], torch.full_like(L_[b, lens[b]:], 7.0))
+    # apply along the tokens: dkk[b, t, h, d] += sum_m P q
+    out = torch.ones(B, T, A, device=DEV, dtype=dt)
+    ops.heads_mm(P, q, out, T, dh, M, nhead, Mp, dh, dh, b_kmajor=True, len=ln, len_mode=1, accumulate=True)
+    ref = torch.einsum('bthm,bmhd->bthd', P64, q64) + valid
+    assert rel(out.view(B, T, nhead, dh).double() * valid, ref) < (1e-5 if dt == torch.float32 else 6e-3)
+    # reduction over the frames (k split when T is large): o[b, m, h, d] = sum_t P kk, then accumulated once more
+    o = torch.zeros(B, M, A, device=DEV)
+    for acc in (False, True):
+        ops.heads_mm(P, kk, o, M, dh, T, nhead, Mp, dh, dh, a_kmajor=True, b_kmajor=True, len=ln, len_mode=2, alpha=0.25, accumulate=acc)
+    ref = 0.5 * torch.einsum('bthm,bthd->bmhd', P64, k64)
+    assert rel(o.view(B, M, nhead, dh), ref) < 1e-5
+    o2 = torch.zeros_like(o)
+    for acc in (False, True):
+        ops.heads_mm(P, kk, o2, M, dh, T, nhead, Mp, dh, dh, a_kmajor=True, b_kmajor=True, len=ln, len_mode=2, alpha=0.25, accumulate=acc)
+    assert torch.equal(o, o2)                    # fixed-order reduction: bit-reproducible
+
+
 def test_row_kernels_backward():
     B, slot, H, Cc = 2, 200, 48, 7
     x, ln = _rows(B, slot, H, 5, [200, 99])
