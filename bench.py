@@ -360,6 +360,35 @@ def run_train(args):
         for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
             sys.stderr.write(f"  {k:28s} n={v['n']:5d} {v['ms']:9.3f} ms {100 * v['ms'] / tot:5.1f}%\n")
         sys.stderr.write(f"  sum of kernel times {tot:.2f} ms; wall of the profiled step {wall:.1f} ms\n")
+    if args.timeline and rank == 0:                  # device timeline of one graph-replayed step: busy time, idle gaps
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step(W + args.steps, False)
+            torch.cuda.synchronize()
+        ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                    key=lambda t: t[0])
+        busy, gaps, end = 0.0, [], ks[0][0]
+        for a, b, name in ks:
+            if a > end:
+                gaps.append((a - end, name))
+            busy += max(0.0, b - max(a, end))
+            end = max(end, b)
+        span = end - ks[0][0]
+        sys.stderr.write(f"  timeline: {len(ks)} device activities, span {span / 1e3:.2f} ms, busy {busy / 1e3:.2f} ms, idle {(span - busy) / 1e3:.2f} ms\n")
+        for gdur, name in sorted(gaps, reverse=True)[:12]:
+            sys.stderr.write(f"    gap {gdur / 1e3:7.3f} ms before {name[:90]}\n")
+        small = sum(gd for gd, _ in gaps if gd < 20)
+        sys.stderr.write(f"    gaps < 20 us: {sum(1 for gd, _ in gaps if gd < 20)} totalling {small / 1e3:.2f} ms\n")
+        agg = {}
+        for a, b, name in ks:
+            k = name.split('(')[0].split('<')[0][-60:]
+            if 'at::native' in name:
+                import re as _re
+                m_ = _re.search(r'(\w+Functor|\w+Ops?\b|\w+_kernel_cuda|BinaryFunctor<[^>]*>|\w+Op<[^>]*>)', name.split('at::native::', 2)[-1][20:])
+                k = ('aten:' + name.split('at::native::')[1][:26] + ':' + (m_.group(1) if m_ else ''))[:60]
+            agg[k] = (agg.get(k, (0, 0))[0] + (b - a), agg.get(k, (0, 0))[1] + 1)
+        for k, (d, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+            sys.stderr.write(f"    {k:60s} n={n:5d} {d / 1e3:8.3f} ms\n")
     for e in evs:
         for k, (a, b) in zip(phases, zip(e[:-1], e[1:])):
             phases[k] += a.elapsed_time(b) / args.steps
@@ -398,6 +427,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-split', type=int, default=4, help='sub-batches per step on the end-to-end (pipelined) path')
     ap.add_argument('--no-graph', action='store_true', help='eager kernel launches instead of one CUDA graph per batch')
+    ap.add_argument('--timeline', action='store_true', help='(--train) torch.profiler device timeline of one step: busy / idle / top kernels, to stderr')
     ap.add_argument('--profile', action='store_true', help='print a CUDA-event breakdown per kernel family to stderr')
     ap.add_argument('--train', action='store_true', help='BASELINE config 5: data-parallel training step (Epic-Kitchens shape, T=16384)')
     ap.add_argument('--calibrate-steps', type=int, default=120, help='training steps for the second (calibrated-weights) regime; 0 skips it')

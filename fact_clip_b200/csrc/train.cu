@@ -13,9 +13,10 @@
 
 namespace factk {
 
-constexpr int WG_RC = 1024;     // rows per partial-sum chunk
+// rows per partial-sum chunk: short (token-side) tensors get small chunks so that more than a handful of CTAs share the rows
+__host__ __device__ inline int wg_rc(int slot) { return slot <= 4096 ? 128 : 1024; }
 
-__host__ __device__ inline int wg_nchunk(int slot) { return (slot + WG_RC - 1) / WG_RC; }
+__host__ __device__ inline int wg_nchunk(int slot) { return (slot + wg_rc(slot) - 1) / wg_rc(slot); }
 
 // ------------------------------------------------------------------------------------------------ wgrad (CUDA cores)
 // 64 x 64 tile of dW per CTA, 256 threads, 4 x 4 micro-tile, 16 rows per shared-memory stage.
@@ -27,9 +28,9 @@ __global__ void __launch_bounds__(256) wgrad_partial_kernel(const void* __restri
     const int tn = blockIdx.x / ktiles, tk = blockIdx.x % ktiles;
     const int chunk = blockIdx.y, b = blockIdx.z;
     const int len_b = len ? min(len[b], slot) : slot;
-    const int r0 = chunk * WG_RC;
+    const int r0 = chunk * wg_rc(slot);
     if (r0 >= len_b) return;
-    const int r1 = min(r0 + WG_RC, len_b);
+    const int r1 = min(r0 + wg_rc(slot), len_b);
     __shared__ __align__(16) float Zs[16][68];
     __shared__ __align__(16) float As[16][68];
     const int tid = threadIdx.x, lr = tid >> 4, lc = (tid & 15) * 4, ty = tid >> 4, tx = tid & 15;
@@ -41,41 +42,46 @@ __global__ void __launch_bounds__(256) wgrad_partial_kernel(const void* __restri
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int rb = r0; rb < r1; rb += 16) {
+    float z[4], a[4];
+    auto fetch = [&](int rb) {           // rows rb .. rb + 15 of the chunk into registers (one row of 4 + 4 values per thread)
         const int r = rb + lr;
-        float z[4] = {0.f, 0.f, 0.f, 0.f}, a[4] = {0.f, 0.f, 0.f, 0.f};
-        if (r < r1) {
-            const size_t zb = ((size_t)b * slot + r) * (size_t)lddz;
-            if (zvec && n_ld + 4 <= N) {
-                const float4 v = ld_vec4(dZ, dz_dtype, zb + n_ld);
-                z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[j] = a[j] = 0.f;
+        if (r >= r1) return;
+        const size_t zb = ((size_t)b * slot + r) * (size_t)lddz;
+        if (zvec && n_ld + 4 <= N) {
+            const float4 v = ld_vec4(dZ, dz_dtype, zb + n_ld);
+            z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n_ld + j < N) z[j] = ld_elem(dZ, dz_dtype, zb + n_ld + j);
+        }
+        const int sr = r + row_off;
+        if (sr >= 0 && sr < len_b) {
+            const size_t ab = ((size_t)b * a_slot + sr) * (size_t)lda;
+            if (avec && k_ld + 4 <= K) {
+                const float4 v = ld_vec4(A, a_dtype, ab + k_ld);
+                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (n_ld + j < N) z[j] = ld_elem(dZ, dz_dtype, zb + n_ld + j);
+                    if (k_ld + j < K) a[j] = ld_elem(A, a_dtype, ab + k_ld + j);
             }
-            const int sr = r + row_off;
-            if (sr >= 0 && sr < len_b) {
-                const size_t ab = ((size_t)b * a_slot + sr) * (size_t)lda;
-                if (avec && k_ld + 4 <= K) {
-                    const float4 v = ld_vec4(A, a_dtype, ab + k_ld);
-                    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-                } else {
+            if (pos != nullptr && k_ld < pos_d) {
+                const size_t pi = pos_idx ? (size_t)pos_idx[(size_t)b * slot + r] : (size_t)r;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (k_ld + j < K) a[j] = ld_elem(A, a_dtype, ab + k_ld + j);
-                }
-                if (pos != nullptr && k_ld < pos_d) {
-                    const size_t pi = pos_idx ? (size_t)pos_idx[(size_t)b * slot + r] : (size_t)r;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (k_ld + j < pos_d && k_ld + j < K) a[j] += pos[pi * (size_t)pos_ld + k_ld + j];
-                }
+                for (int j = 0; j < 4; ++j)
+                    if (k_ld + j < pos_d && k_ld + j < K) a[j] += pos[pi * (size_t)pos_ld + k_ld + j];
             }
         }
+    };
+    fetch(r0);
+    for (int rb = r0; rb < r1; rb += 16) {
         *reinterpret_cast<float4*>(&Zs[lr][lc]) = make_float4(z[0], z[1], z[2], z[3]);
         *reinterpret_cast<float4*>(&As[lr][lc]) = make_float4(a[0], a[1], a[2], a[3]);
         __syncthreads();
+        if (rb + 16 < r1) fetch(rb + 16);        // the next stage's loads fly under this stage's FMAs
 #pragma unroll
         for (int rr = 0; rr < 16; ++rr) {
             const float4 zv = *reinterpret_cast<const float4*>(&Zs[rr][ty * 4]);
@@ -103,25 +109,39 @@ __global__ void __launch_bounds__(256) wgrad_partial_kernel(const void* __restri
 
 // out[bo][i / K][i % K] = alpha * sum over the valid (video, chunk) partials (+ out): fixed order.  Partials of `psz`
 // floats spaced `pstride` apart; per_video: one output per video (bo = b), else the videos are summed too.
-__global__ void partial_reduce_kernel(const float* __restrict__ ws, size_t pstride, int psz, int K, float* __restrict__ out,
-                                      int ldo, long long out_bstride, int B, int slot, const int32_t* __restrict__ len,
-                                      int nchunk, int rows_per_chunk, float alpha, int accumulate, int per_video) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= psz) return;
+__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ ws, size_t pstride, int psz, int K,
+                                                             float* __restrict__ out, int ldo, long long out_bstride, int B, int slot,
+                                                             const int32_t* __restrict__ len, int nchunk, int rows_per_chunk, float alpha,
+                                                             int accumulate, int per_video) {
+    // 32 outputs x 8 chunk groups per CTA: group q sums the partials q, q + 8, ... of every video, the eight sums combine in
+    // group order -- the order of additions depends on the shape only
+    __shared__ float part[8][32];
+    const int o = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + o;
     const int b0 = per_video ? blockIdx.y : 0, b1 = per_video ? blockIdx.y + 1 : B;
     float s = 0.f;
-    for (int b = b0; b < b1; ++b) {
-        const int len_b = len ? min(len[b], slot) : slot;
-        for (int c = 0; c < nchunk && c * rows_per_chunk < len_b; ++c) s += ws[(size_t)(b * nchunk + c) * pstride + i];
+    if (i < psz) {
+        for (int b = b0; b < b1; ++b) {
+            const int len_b = len ? min(len[b], slot) : slot;
+            const int live = min(nchunk, (len_b + rows_per_chunk - 1) / rows_per_chunk);
+            const float* w = ws + (size_t)b * nchunk * pstride + i;
+#pragma unroll 4
+            for (int c = q; c < live; c += 8) s += w[(size_t)c * pstride];
+        }
     }
-    float* o = out + (per_video ? (size_t)blockIdx.y * (size_t)out_bstride : 0) + (size_t)(i / K) * ldo + (i % K);
-    *o = alpha * s + (accumulate ? *o : 0.f);
+    part[q][o] = s;
+    __syncthreads();
+    if (q != 0 || i >= psz) return;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) s += part[j][o];
+    float* op = out + (per_video ? (size_t)blockIdx.y * (size_t)out_bstride : 0) + (size_t)(i / K) * ldo + (i % K);
+    *op = alpha * s + (accumulate ? *op : 0.f);
 }
 
 void launch_partial_reduce(const float* ws, size_t pstride, int psz, int K, float* out, int ldo, long long out_bstride, int B, int slot,
                            const int32_t* len, int nchunk, int rows_per_chunk, float alpha, int accumulate, cudaStream_t st) {
     const int per_video = out_bstride != 0;
-    partial_reduce_kernel<<<dim3((psz + 255) / 256, per_video ? B : 1), 256, 0, st>>>(ws, pstride, psz, K, out, ldo, out_bstride, B, slot, len,
+    partial_reduce_kernel<<<dim3((psz + 31) / 32, per_video ? B : 1), 256, 0, st>>>(ws, pstride, psz, K, out, ldo, out_bstride, B, slot, len,
                                                                                      nchunk, rows_per_chunk, alpha, accumulate, per_video);
 }
 
@@ -523,8 +543,8 @@ extern "C" int factk_wgrad(const void* dZ, int dz_dtype, int lddz, const void* A
     wgrad_partial_kernel<<<dim3(ntn * ntk, nchunk, B), 256, 0, st>>>(dZ, dz_dtype, lddz, A, a_dtype, lda, a_slot, row_off, pos, pos_ld,
                                                                      pos_d, pos_idx, N, K, ws, slot, len, nchunk, ntk);
     const int psz = N * K, per_video = dw_bstride != 0;
-    partial_reduce_kernel<<<dim3((psz + 255) / 256, per_video ? B : 1), 256, 0, st>>>(ws, (size_t)psz, psz, K, dW, lddw, dw_bstride, B, slot,
-                                                                                     len, nchunk, WG_RC, alpha, accumulate, per_video);
+    partial_reduce_kernel<<<dim3((psz + 31) / 32, per_video ? B : 1), 256, 0, st>>>(ws, (size_t)psz, psz, K, dW, lddw, dw_bstride, B, slot,
+                                                                                     len, nchunk, wg_rc(slot), alpha, accumulate, per_video);
     return check_launch("factk_wgrad");
 }
 
@@ -538,7 +558,7 @@ extern "C" int factk_colsum(const void* X, int x_dtype, int ldx, const void* Y, 
     const int nchunk = csum_nchunk(slot), per_video = out_bstride != 0;
     cudaStream_t st = (cudaStream_t)stream;
     colsum_partial_kernel<<<dim3((N + 63) / 64, nchunk, B), 256, 0, st>>>(X, x_dtype, ldx, Y, y_dtype, ldy, N, ws, slot, len, nchunk);
-    partial_reduce_kernel<<<dim3((N + 63) / 64, per_video ? B : 1), 64, 0, st>>>(ws, (size_t)N, N, N, out, N, out_bstride, B, slot, len,
+    partial_reduce_kernel<<<dim3((N + 31) / 32, per_video ? B : 1), 256, 0, st>>>(ws, (size_t)N, N, N, out, N, out_bstride, B, slot, len,
                                                                                  nchunk, CSUM_RC, alpha, accumulate, per_video);
     return check_launch("factk_colsum");
 }
@@ -597,8 +617,8 @@ extern "C" int factk_layernorm_bwd(const void* X, int x_dtype, int ldx, const vo
     if (first_use_on_device(devs)) cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     layernorm_bwd_kernel<<<dim3(nchunk, B), 256, smem, st>>>(X, x_dtype, ldx, R, r_dtype, ldr, w, b, eps, relu, dY, dy_dtype, lddy, dV,
                                                            dv_dtype, lddv, accumulate, ws, E, slot, len, nchunk);
-    partial_reduce_kernel<<<dim3((E + 63) / 64, 1), 64, 0, st>>>(ws, (size_t)2 * E, E, E, dw, E, 0, B, slot, len, nchunk, LN_RC, 1.f, 1, 0);
-    partial_reduce_kernel<<<dim3((E + 63) / 64, 1), 64, 0, st>>>(ws + E, (size_t)2 * E, E, E, db, E, 0, B, slot, len, nchunk, LN_RC, 1.f, 1, 0);
+    partial_reduce_kernel<<<dim3((E + 31) / 32, 1), 256, 0, st>>>(ws, (size_t)2 * E, E, E, dw, E, 0, B, slot, len, nchunk, LN_RC, 1.f, 1, 0);
+    partial_reduce_kernel<<<dim3((E + 31) / 32, 1), 256, 0, st>>>(ws + E, (size_t)2 * E, E, E, db, E, 0, B, slot, len, nchunk, LN_RC, 1.f, 1, 0);
     return check_launch("factk_layernorm_bwd");
 }
 

@@ -65,10 +65,10 @@ __device__ __forceinline__ void hb_stash(int kmajor, float (*S)[ROWS + 4], const
     }
 }
 
-// BM x BN tile of C per CTA, 8 x TN micro-tile per thread ((BM / 8) * (BN / TN) == 256).
-template <int BM, int BN, int TN>
-__global__ void __launch_bounds__(HB_NT) heads_mm_kernel(const __grid_constant__ factk_heads_mm_t g, int ntn, int ksplit, int kchunk) {
-    static_assert((BM / 8) * (BN / TN) == HB_NT, "thread layout");
+// BM x BN tile of C per CTA, TM x TN micro-tile per thread ((BM / TM) * (BN / TN) == 256; TM, TN in {4, 8}).
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(HB_NT, 2) heads_mm_kernel(const __grid_constant__ factk_heads_mm_t g, int ntn, int ksplit, int kchunk) {
+    static_assert((BM / TM) * (BN / TN) == HB_NT && (TM == 4 || TM == 8) && (TN == 4 || TN == 8), "thread layout");
     __shared__ __align__(16) float As[2][HB_BK][BM + 4];
     __shared__ __align__(16) float Bs[2][HB_BK][BN + 4];
 
@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(HB_NT) heads_mm_kernel(const __grid_constant__
     constexpr int TX = BN / TN;
     const int tx = tid % TX, ty = tid / TX;
 
-    float acc[8][TN];
+    float acc[TM][TN];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
@@ -112,11 +112,14 @@ __global__ void __launch_bounds__(HB_NT) heads_mm_kernel(const __grid_constant__
         }
 #pragma unroll
         for (int k = 0; k < HB_BK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][BM / 2 + ty * 4]);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            float bv[TN];
+            float av[TM], bv[TN];
             {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+                av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+                if (TM == 8) {
+                    const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][BM / 2 + ty * 4]);
+                    av[TM - 4] = a1.x; av[TM - 3] = a1.y; av[TM - 2] = a1.z; av[TM - 1] = a1.w;
+                }
                 const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
                 bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
                 if (TN == 8) {
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(HB_NT) heads_mm_kernel(const __grid_constant__
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(HB_NT) heads_mm_kernel(const __grid_constant__
     if (ksplit > 1) {       // raw partial; heads_mm_reduce applies alpha / accumulate
         float* w = g.ws + ((size_t)blockIdx.z * ksplit + split) * (size_t)g.M * (size_t)g.N;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
             const int r = m0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
             if (r >= Mb) continue;
 #pragma unroll
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(HB_NT) heads_mm_kernel(const __grid_constant__
     const size_t cbase = (size_t)b * (size_t)g.c_bstride + (size_t)h * g.c_hstride;
     const int esz = g.c_dtype == FACTK_BF16 ? 2 : 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < TM; ++i) {
         const int r = m0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
         if (r >= Mb) continue;
 #pragma unroll
@@ -199,21 +202,21 @@ __global__ void __launch_bounds__(256) heads_mm_reduce_kernel(const __grid_const
 }
 
 struct HeadsPlan {
-    int bn, ntm, ntn, ksplit, kchunk;
+    int bm, bn, ntm, ntn, ksplit, kchunk;
 };
 
 static HeadsPlan heads_plan(int batch, int nhead, int M, int N, int K) {
     HeadsPlan p;
     if (N <= 32) p.bn = 32;
     else p.bn = ((N + 63) / 64) * 64 < ((N + 127) / 128) * 128 ? 64 : 128;
-    const int bm = p.bn == 32 ? 256 : 128;
-    p.ntm = (M + bm - 1) / bm;
+    p.bm = (p.bn == 32 && M >= 2048) ? 256 : 128;
+    p.ntm = (M + p.bm - 1) / p.bm;
     p.ntn = (N + p.bn - 1) / p.bn;
     p.ksplit = 1;
     p.kchunk = ((K + HB_BK - 1) / HB_BK) * HB_BK;
     const long ctas = (long)p.ntm * p.ntn * batch * nhead;
-    if (K >= 2048 && ctas < 2 * 148) {          // a reduction over the frames with a token-sized output: split k
-        int want = (int)((2 * 148 + ctas - 1) / ctas);
+    if (K >= 2048 && ctas < 4 * 148) {          // a reduction over the frames with a token-sized output: split k
+        int want = (int)((4 * 148 + ctas - 1) / ctas);
         int chunk = (K + want - 1) / want;
         chunk = ((chunk + 255) / 256) * 256;    // >= 256 rows per partial, a multiple of the k step
         p.kchunk = chunk;
@@ -241,9 +244,10 @@ extern "C" int factk_heads_mm(const factk_heads_mm_t* g, void* stream) {
     FACTK_REQUIRE(p.ksplit == 1 || g->ws, "factk_heads_mm: this shape needs the k-split workspace (factk_heads_mm_ws_floats)");
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid((unsigned)(p.ntm * p.ntn), (unsigned)p.ksplit, (unsigned)(g->batch * g->nhead));
-    if (p.bn == 32) heads_mm_kernel<256, 32, 4><<<grid, HB_NT, 0, st>>>(*g, p.ntn, p.ksplit, p.kchunk);
-    else if (p.bn == 64) heads_mm_kernel<128, 64, 4><<<grid, HB_NT, 0, st>>>(*g, p.ntn, p.ksplit, p.kchunk);
-    else heads_mm_kernel<128, 128, 8><<<grid, HB_NT, 0, st>>>(*g, p.ntn, p.ksplit, p.kchunk);
+    if (p.bn == 32 && p.bm == 256) heads_mm_kernel<256, 32, 8, 4><<<grid, HB_NT, 0, st>>>(*g, p.ntn, p.ksplit, p.kchunk);
+    else if (p.bn == 32) heads_mm_kernel<128, 32, 4, 4><<<grid, HB_NT, 0, st>>>(*g, p.ntn, p.ksplit, p.kchunk);
+    else if (p.bn == 64) heads_mm_kernel<128, 64, 8, 4><<<grid, HB_NT, 0, st>>>(*g, p.ntn, p.ksplit, p.kchunk);
+    else heads_mm_kernel<128, 128, 8, 8><<<grid, HB_NT, 0, st>>>(*g, p.ntn, p.ksplit, p.kchunk);
     if (p.ksplit > 1)
         heads_mm_reduce_kernel<<<dim3((unsigned)((g->M * g->N + 255) / 256), (unsigned)(g->batch * g->nhead)), 256, 0, st>>>(*g, p.ksplit, p.kchunk);
     return check_launch("factk_heads_mm");

@@ -42,17 +42,21 @@ class Var:
 
 class Wt:
     """A weight as the kernels see it: value ``w`` and gradient accumulator ``g`` (same shape; views slice both)."""
-    __slots__ = ('w', 'g', '_t')
+    __slots__ = ('w', 'g', '_t', '_par')
 
     def __init__(self, w, g):
-        self.w, self.g, self._t = w, g, None
+        self.w, self.g, self._t, self._par = w, g, None, None
 
     def __getitem__(self, idx):
-        return Wt(self.w[idx], None if self.g is None else self.g[idx])
+        c = Wt(self.w[idx], None if self.g is None else self.g[idx])
+        if isinstance(idx, int) and self.w.dim() > 2:
+            c._par = (self, idx)          # a tap of a stacked weight: its transpose is a slice of the stack's (one copy kernel)
+        return c
 
     def T(self):
+        """Transposed (last two dimensions) dense copy, made once per step."""
         if self._t is None:
-            self._t = dense(self.w.t())
+            self._t = self._par[0].T()[self._par[1]] if self._par is not None else dense(self.w.transpose(-1, -2))
         return self._t
 
 
@@ -191,6 +195,20 @@ class TrainEngine(FactEngine):
             g = torch.zeros(t.shape, dtype=torch.float32, device=t.device)
             self._derived.append((t, g))
             h = self._wt[key] = Wt(dense(t.detach()), g)
+        return h
+
+    def Dn(self, key, fn):
+        """Several derived weights from one differentiable function (``fn()`` returns a tuple of tensors)."""
+        h = self._wt.get(key)
+        if h is None:
+            with torch.enable_grad():
+                ts = fn()
+            hs = []
+            for t in ts:
+                g = torch.zeros(t.shape, dtype=torch.float32, device=t.device)
+                self._derived.append((t, g))
+                hs.append(Wt(dense(t.detach()), g))
+            h = self._wt[key] = tuple(hs)
         return h
 
     def P(self, name):
@@ -524,6 +542,34 @@ class TrainEngine(FactEngine):
         bt = (A1 @ b1 + A2 @ b2 + bf).float()
         return Wt_, bt
 
+    def _m2_fold_all(self, pfx, Lr, groups):
+        """Every layer of an MSTCN++ branch folded at once (the same algebra as _m2_fold, batched over the layers: a handful of
+        batched fp64 products instead of six small ones per layer).  Needs five distinct tap offsets in every layer (even
+        layer counts).  Returns ([Lr, 5, F, F] taps in _m2_offsets order, [Lr, F] biases)."""
+        def dense_w(name):
+            w = self.P(name)
+            if groups > 1:
+                co, ci = w.shape[0] // groups, w.shape[1]
+                full = w.new_zeros(w.shape[0], ci * groups, w.shape[2])
+                for j in range(groups):
+                    full[j * co:(j + 1) * co, j * ci:(j + 1) * ci] = w[j * co:(j + 1) * co]
+                w = full
+            return w
+        st = lambda fmt, f=self.P: torch.stack([f(pfx + fmt.format(i)) for i in range(Lr)]).double()
+        w1, w2 = st('conv_dilated_1.{}.weight', dense_w), st('conv_dilated_2.{}.weight', dense_w)       # [L, F, F, 3]
+        b1, b2, bf = st('conv_dilated_1.{}.bias'), st('conv_dilated_2.{}.bias'), st('conv_fusion.{}.bias')
+        wf = st('conv_fusion.{}.weight')[:, :, :, 0]                                                         # [L, F, 2F]
+        F = w1.shape[1]
+        A1, A2 = wf[:, :, :F], wf[:, :, F:]
+        P1 = torch.einsum('lof,lfik->lkoi', A1, w1)                                                          # [L, 3, F, F]
+        P2 = torch.einsum('lof,lfik->lkoi', A2, w2)
+        bt = torch.einsum('lof,lf->lo', A1, b1) + torch.einsum('lof,lf->lo', A2, b2) + bf
+        c = P1[:, 1] + P2[:, 1]
+        h = Lr // 2                  # layers i < h: dilation 2^(Lr-1-i) of conv_dilated_1 is the larger one, so its taps are the outer ones
+        lo = torch.stack([P1[:h, 0], P2[:h, 0], c[:h], P2[:h, 2], P1[:h, 2]], dim=1)
+        hi = torch.stack([P2[h:, 0], P1[h:, 0], c[h:], P1[h:, 2], P2[h:, 2]], dim=1)
+        return torch.cat([lo, hi]).float(), bt.float()
+
     def frame_branch_t(self, pfx, bc, x, in_map, ln):
         F, H, Lr, C = bc['f_dim'], bc['hid_dim'], bc['f_layers'], self.ncls()
         m2, ng, p = bc['f'] == 'm2', bc['f_ngp'], float(bc['dropout'])
@@ -547,8 +593,11 @@ class TrainEngine(FactEngine):
                     nxt = self.layernorm(nxt, q + 'norm.weight', q + 'norm.bias', ln=ln)
             else:
                 offs = self._m2_offsets(i, Lr)
-                Wf = self.D(('m2fold_w', pfx, i), lambda: self._m2_fold(pfx, i, Lr, ng)[0])
-                bf = self.D(('m2fold_b', pfx, i), lambda: self._m2_fold(pfx, i, Lr, ng)[1])
+                if Lr % 2 == 0:
+                    Wall, ball = self.Dn(('m2fold_all', pfx), lambda: self._m2_fold_all(pfx, Lr, ng))
+                    Wf, bf = Wall[i], ball[i]
+                else:
+                    Wf, bf = self.Dn(('m2fold', pfx, i), lambda: self._m2_fold(pfx, i, Lr, ng))
                 f = self.linear([src(cur, Wf[j], off=o) for j, o in enumerate(offs)], F, bias=bf, relu=True, ln=ln, tag='tcn_m2')
                 if i != Lr - 1:
                     f = self.dropout(f, p)
