@@ -36,6 +36,13 @@ class HeadsMM(C.Structure):
                 ('len', vp), ('ws', vp), ('alpha', f32), ('reserved_', i32)]
 
 
+class TokenLayer(C.Structure):
+    _fields_ = [('x', vp), ('B', i32), ('M', i32), ('A', i32), ('nhead', i32), ('ff', i32), ('eps', f32),
+                ('w_in', vp), ('b_in', vp), ('pre_qk', vp), ('o_in', vp), ('w_o', vp), ('b_o', vp), ('ln1_w', vp), ('ln1_b', vp),
+                ('w_q', vp), ('b_q', vp), ('pre_q', vp), ('cq_out', vp), ('w_1', vp), ('b_1', vp), ('w_2', vp), ('b_2', vp),
+                ('ln2_w', vp), ('ln2_b', vp)]
+
+
 _SIGS = {
     'factk_version': (i32, []),
     'factk_last_error': (C.c_char_p, []),
@@ -43,6 +50,9 @@ _SIGS = {
     'factk_gemm': (i32, [C.POINTER(Gemm), vp]),
     'factk_heads_mm_ws_floats': (C.c_size_t, [i32, i32, i32, i32, i32]),
     'factk_heads_mm': (i32, [C.POINTER(HeadsMM), vp]),
+    'factk_token_layer_supported': (i32, [i32, i32, i32, i32]),
+    'factk_token_layer': (i32, [C.POINTER(TokenLayer), vp]),
+    'factk_token_layer_debug': (i32, [vp]),
     'factk_gemm_tc': (i32, [C.POINTER(Gemm), vp]),
     'factk_gemm_tc_supported': (i32, [C.POINTER(Gemm)]),
     'factk_gemm_pair_supported': (i32, [i32, i32]),

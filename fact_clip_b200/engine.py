@@ -45,6 +45,8 @@ class FactEngine:
         # Measured: 1.46 instead of 1.41 ms per step for the 73 token GEMMs -- fewer, fuller tiles stream more per CTA and the
         # launches are one wave either way -- so it stays off.
         self.flat_tokens = os.environ.get('FACTK_FLAT_TOKENS', '0') == '1'
+        # one launch per token-side decoder (half-)layer (csrc/token_layer.cu) instead of 8-11 dependent ones; bf16 mode only
+        self.use_fused_tokens = os.environ.get('FACTK_FUSED_TOKENS', '1') != '0'
         self.use_graph = True        # replay the whole batched forward as ONE CUDA graph (no per-kernel host launch cost)
         # Epic verb/noun model (blocks_SepVerbNoun.py): two class heads, action table (verb id, noun id) per action
         self.vn = hp.get('vn')
@@ -325,6 +327,27 @@ class FactEngine:
         return W, b
 
     # ------------------------------------------------------------------ token side
+    def _tok_fused(self, x, nhead, ff):
+        B, M, A = x.shape
+        return (self.mode == 'bf16' and self.use_tc and self.use_fused_tokens and x.is_contiguous() and x.dtype == torch.float32
+                and ops.token_layer_ok(M, A, nhead, ff))
+
+    def _tokw(self, W):
+        """Weight in the fused token kernel's packed bf16 fragment order (cached like every derived weight)."""
+        return self.derived(('tokw', W.data_ptr(), tuple(W.shape), tuple(W.stride())), lambda: ops.pack_token_weight(W))
+
+    def _posw(self, W, pos):
+        """(x + pos) W^T = x W^T + pos W[:, :d]^T: the position term as a table (shared with lin())."""
+        if pos is None:
+            return None
+        d = pos.shape[-1]
+        return self.derived(('posW', W.data_ptr(), tuple(W.shape), tuple(W.stride())), lambda: pos @ W[:, :d].t())
+
+    def _ffn_args(self, q, n_a, n_b):
+        w1, w2 = self.p(q + 'linear1.weight'), self.p(q + 'linear2.weight')
+        return (self._tokw(w1), self.p(q + 'linear1.bias'), self._tokw(w2), self.p(q + 'linear2.bias'), self.p(q + n_a), self.p(q + n_b),
+                w1.shape[0])
+
     def _mha_self(self, pfx, x, pos, nhead, tag):
         """q = k = x + pos, v = x through a packed in_proj (basic.py:437,500); returns attn output before out_proj."""
         B, M, A = x.shape
@@ -362,12 +385,10 @@ class FactEngine:
         kv = self.zbuf('sca_kv', (B, slot, 2 * A), self.act)
         ws = self.buf('attn_ws', (max(ops.attn_rows_ws(B, slot, M, nh, A // nh), 1),))
         fpos = self.frame_pos
+        ff = self.p(f'{pfx}layers.0.linear1.weight').shape[0]
+        fused = self._tok_fused(tgt, nh, ff)
         for i in range(bc['a_layers']):
             q = f'{pfx}layers.{i}.'
-            o = self._mha_self(q + 'self_attn.', tgt, qpos, nh, tag)
-            self.lin(o, self.p(q + 'self_attn.out_proj.weight'), A, t, bias=self.p(q + 'self_attn.out_proj.bias'), res=tgt)
-            ops.layernorm(t, self.p(q + 'norm1.weight'), self.p(q + 'norm1.bias'), tgt)
-            # cross attention: q from tokens, k from frames (+pos), v from frames
             c = q + 'multihead_attn.'
             cb = self.p(c + 'in_proj_bias')
             if (c + 'in_proj_weight') in self._p:
@@ -376,7 +397,19 @@ class FactEngine:
             else:
                 wq, wk, wv = self.p(c + 'q_proj_weight'), self.p(c + 'k_proj_weight'), self.p(c + 'v_proj_weight')
             cq = self.buf('tok_cq', (B, M, A))
-            self.lin(tgt, wq, A, cq, pos=qpos, bias=cb[:A])
+            if fused:
+                # self attention + out_proj + norm1 + the cross attention's query projection: one launch
+                Wi = self.p(q + 'self_attn.in_proj_weight')
+                ops.token_layer(tgt, nh, self._tokw(self.p(q + 'self_attn.out_proj.weight')), self.p(q + 'self_attn.out_proj.bias'),
+                                self.p(q + 'norm1.weight'), self.p(q + 'norm1.bias'), w_in=self._tokw(Wi),
+                                b_in=self.p(q + 'self_attn.in_proj_bias'), pre_qk=self._posw(Wi[:2 * A], qpos),
+                                w_q=self._tokw(wq), b_q=cb[:A], pre_q=self._posw(wq, qpos), cq_out=cq)
+            else:
+                o = self._mha_self(q + 'self_attn.', tgt, qpos, nh, tag)
+                self.lin(o, self.p(q + 'self_attn.out_proj.weight'), A, t, bias=self.p(q + 'self_attn.out_proj.bias'), res=tgt)
+                ops.layernorm(t, self.p(q + 'norm1.weight'), self.p(q + 'norm1.bias'), tgt)
+                # cross attention: q from tokens, k from frames (+pos), v from frames
+                self.lin(tgt, wq, A, cq, pos=qpos, bias=cb[:A])
             if fpos is None:
                 wkv = self.derived(('wkv', c), lambda: torch.cat([wk, wv], 0))
                 self.mm([S(frame, wkv)], 2 * A, kv, len=rlen, bias=cb[A:], tag='sca_kv')
@@ -390,6 +423,12 @@ class FactEngine:
                 self.mm([S(frame, wv)], A, kv[:, :, A:], len=rlen, bias=cb[2 * A:])
             o = self.buf('tok_o', (B, M, A))
             ops.attn_rows(cq, kv[:, :, :A], kv[:, :, A:], o, nh, ws, len=rlen)
+            if fused:
+                # out_proj + norm2 + FFN + norm3: one launch
+                ops.token_layer(tgt, nh, self._tokw(self.p(c + 'out_proj.weight')), self.p(c + 'out_proj.bias'),
+                                self.p(q + 'norm2.weight'), self.p(q + 'norm2.bias'), o_in=o,
+                                ffn=self._ffn_args(q, 'norm3.weight', 'norm3.bias'))
+                continue
             self.lin(o, self.p(c + 'out_proj.weight'), A, t, bias=self.p(c + 'out_proj.bias'), res=tgt)
             ops.layernorm(t, self.p(q + 'norm2.weight'), self.p(q + 'norm2.bias'), tgt)
             self._ffn_ln(q, tgt, 'norm3.weight', 'norm3.bias', tag)
@@ -403,8 +442,16 @@ class FactEngine:
         B, M, A, H, nh = self.B, self.ntok, bc['a_dim'], bc['hid_dim'], bc['a_nhead']
         qpos = self.qpos()
         t = self.buf('tok_t', (B, M, A))
+        fused = self._tok_fused(x, nh, self.p(f'{pfx}layers.0.linear1.weight').shape[0])
         for i in range(bc['a_layers']):
             q = f'{pfx}layers.{i}.'
+            if fused:                  # the whole SALayer in one launch
+                Wi = self.p(q + 'multihead_attn.in_proj_weight')
+                ops.token_layer(x, nh, self._tokw(self.p(q + 'multihead_attn.out_proj.weight')), self.p(q + 'multihead_attn.out_proj.bias'),
+                                self.p(q + 'norm1.weight'), self.p(q + 'norm1.bias'), w_in=self._tokw(Wi),
+                                b_in=self.p(q + 'multihead_attn.in_proj_bias'), pre_qk=self._posw(Wi[:2 * A], qpos),
+                                ffn=self._ffn_args(q, 'norm2.weight', 'norm2.bias'))
+                continue
             o = self._mha_self(q + 'multihead_attn.', x, qpos, nh, tag)
             self.lin(o, self.p(q + 'multihead_attn.out_proj.weight'), A, t,
                      bias=self.p(q + 'multihead_attn.out_proj.bias'), res=x)

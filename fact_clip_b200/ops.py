@@ -226,6 +226,42 @@ def a2f_fused(rows, kt, cb, wy, vt, bias, out, M, logit=None, attn=None, len=Non
           L.ptr(logit), L.ptr(attn), _row_ld(ref) if ref is not None else 0, B, slot, L.ptr(len), M, H, F, L.stream())
 
 
+def token_layer_ok(M, A, nhead, ff):
+    return bool(L.load().factk_token_layer_supported(M, A, nhead, ff))
+
+
+def pack_token_weight(W):
+    """[N, K] weight -> bf16 in mma.m16n8k16 B-fragment order (include/factk.h factk_token_layer_t): per (32-column task, k-step of
+    16, lane) the eight registers the lane feeds to the four n8 tiles of the task."""
+    N, K = W.shape
+    assert N % 32 == 0 and K % 16 == 0
+    w = W.to(torch.bfloat16).reshape(N // 32, 4, 8, K // 16, 2, 4, 2)        # [task, tile, n % 8, k-step, k half, (k % 8) / 2, k % 2]
+    return w.permute(0, 3, 2, 5, 1, 4, 6).contiguous().view(-1)
+
+
+def token_layer(x, nhead, w_o, b_o, ln1_w, ln1_b, w_in=None, b_in=None, pre_qk=None, o_in=None, w_q=None, b_q=None, pre_q=None, cq_out=None,
+                ffn=None, eps=1e-5):
+    """One launch per token-side decoder (half-)layer (csrc/token_layer.cu).  x: [B, M, A] fp32 contiguous, updated in place;
+    weights packed by pack_token_weight; ffn = (w_1, b_1, w_2, b_2, ln2_w, ln2_b, ff) or None."""
+    B, M, A = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32
+    g = L.TokenLayer()
+    g.x, g.B, g.M, g.A, g.nhead, g.eps = x.data_ptr(), B, M, A, nhead, float(eps)
+    g.w_in, g.b_in, g.pre_qk = L.ptr(w_in), L.ptr(b_in), L.ptr(pre_qk)
+    if o_in is not None:
+        assert o_in.is_contiguous() and o_in.dtype == torch.float32 and o_in.shape == x.shape
+    g.o_in = L.ptr(o_in)
+    g.w_o, g.b_o, g.ln1_w, g.ln1_b = w_o.data_ptr(), b_o.data_ptr(), ln1_w.data_ptr(), ln1_b.data_ptr()
+    if cq_out is not None:
+        assert cq_out.is_contiguous() and cq_out.dtype == torch.float32 and cq_out.shape == x.shape
+    g.w_q, g.b_q, g.pre_q, g.cq_out = L.ptr(w_q), L.ptr(b_q), L.ptr(pre_q), L.ptr(cq_out)
+    if ffn is not None:
+        w1, b1, w2, b2, l2w, l2b, ff = ffn
+        g.w_1, g.b_1, g.w_2, g.b_2, g.ln2_w, g.ln2_b, g.ff = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), l2w.data_ptr(), l2b.data_ptr(), ff
+    COUNTERS['launches'] += 1
+    _call('factk_token_layer', 'token_layer', g, L.stream())
+
+
 def tdu_segment(pred, seg_label, seg_start, seg_len, seg_center, nseg, len=None):
     B, slot = pred.shape
     COUNTERS['launches'] += 1

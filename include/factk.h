@@ -327,6 +327,43 @@ int factk_loss_combine(const float* ws, int nb, const int32_t* block_type, int B
                        const int32_t* nvalid, float* out, int ldo, void* stream);
 
 
+/* One launch per token-side decoder layer (csrc/token_layer.cu; models/basic.py:429-452 SALayer.forward, 494-523
+ * SCALayer.forward), one CTA per video, the token matrix resident in shared memory between the stages:
+ *   [w_in: packed q|k|v projection of x (+ pre_qk[m][:2A], the query positions times W) -> per-head softmax(q k^T) v]
+ *   (or o_in: the rows that enter out_proj, e.g. the cross attention's output) -> out_proj + b_o + x -> LayerNorm(ln1)
+ *   [w_q: cq_out = LN1 rows W_q^T + b_q + pre_q]   [w_1: FFN linear1 / ReLU / linear2 + residual -> LayerNorm(ln2)]
+ * and x <- the last LayerNorm's rows.  x, o_in, cq_out: fp32 [B][M][A]; biases / LayerNorm parameters / tables fp32.
+ * Weights: bf16 in mma.m16n8k16 B-fragment order -- W[N][K] as [N/32][K/16][lane = 4 (n % 8) + (k % 8) / 2][(n / 8) % 4]
+ * [(k / 8) % 2][k % 2] (ops.pack_token_weight).  Limits: M <= 80, A % 64 == 0 <= 256, head dim 16/32/64, ff % 64 == 0
+ * (factk_token_layer_supported). */
+typedef struct {
+    float* x;
+    int32_t B, M, A, nhead, ff;
+    float eps;
+    const void* w_in;
+    const float* b_in;
+    const float* pre_qk;
+    const float* o_in;
+    const void* w_o;
+    const float* b_o;
+    const float* ln1_w;
+    const float* ln1_b;
+    const void* w_q;
+    const float* b_q;
+    const float* pre_q;
+    float* cq_out;
+    const void* w_1;
+    const float* b_1;
+    const void* w_2;
+    const float* b_2;
+    const float* ln2_w;
+    const float* ln2_b;
+} factk_token_layer_t;
+int factk_token_layer_supported(int M, int A, int nhead, int ff);
+int factk_token_layer(const factk_token_layer_t* p, void* stream);
+/* Debug aid: clock64 of CTA 0 at the kernel's ten stage boundaries into buf[10] (int64, device memory); NULL turns it off. */
+int factk_token_layer_debug(void* buf);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Training step: backward-pass primitives (csrc/train.cu, train_gru.cu, train_loss.cu).  The reference leaves the backward
  * to torch autograd over its eager ops (scripts/train.py:262-264 `loss.backward()`); here every gradient is one of the

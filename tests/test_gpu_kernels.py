@@ -462,3 +462,65 @@ def test_a2f_fused(M, slot, lens, with_outputs):
         if with_outputs:
             assert rel_l2(logit[b, :T, :M], lg) < 1e-5 and rel_l2(attn[b, :T, :M], p) < 1e-4
         assert float(out[b, T:].float().abs().sum()) == 0.0          # rows past the end are never written
+
+
+def _ref_token_layer(x, nhead, Wo, bo, ln1, Win=None, bin_=None, pos=None, o_in=None, Wq=None, bq=None, ffn=None):
+    """fp32 torch restatement of SALayer / the two halves of SCALayer (models/basic.py:429-452, 494-523), eval mode."""
+    import torch.nn.functional as Fn
+    B, M, A = x.shape
+    if Win is not None:
+        xq = x + (pos if pos is not None else 0)
+        q, k = (xq @ Win[:2 * A].t() + bin_[:2 * A]).split(A, -1)
+        v = x @ Win[2 * A:].t() + bin_[2 * A:]
+        hd = lambda t: t.view(B, M, nhead, A // nhead).transpose(1, 2)
+        p = torch.softmax(hd(q) @ hd(k).transpose(-1, -2) / (A // nhead) ** 0.5, -1)
+        o = (p @ hd(v)).transpose(1, 2).reshape(B, M, A)
+    else:
+        o = o_in
+    x1 = Fn.layer_norm(o @ Wo.t() + bo + x, (A,), ln1[0], ln1[1])
+    cq = None
+    if Wq is not None:
+        cq = (x1 + (pos if pos is not None else 0)) @ Wq.t() + bq
+    if ffn is not None:
+        W1, b1, W2, b2, l2w, l2b = ffn
+        x1 = Fn.layer_norm(torch.relu(x1 @ W1.t() + b1) @ W2.t() + b2 + x1, (A,), l2w, l2b)
+    return x1, cq
+
+
+@pytest.mark.parametrize('B,M,A,nhead,ff', [(3, 75, 256, 8, 512), (2, 12, 64, 4, 64), (1, 80, 128, 2, 128), (2, 33, 256, 8, 256)])
+def test_token_layer_fused(B, M, A, nhead, ff):
+    """csrc/token_layer.cu: a whole SALayer, and the two halves of an SCALayer, each in ONE launch, against fp32 torch (bf16 GEMM
+    operands, fp32 accumulate / residual / LayerNorm / softmax: 1e-2 relative)."""
+    assert ops.token_layer_ok(M, A, nhead, ff)
+    mk = lambda *s, seed, sc=1.0: (rnd(*s, seed=seed) * sc).to(DEV)
+    x = mk(B, M, A, seed=1)
+    pos = mk(M, A, seed=2, sc=0.5)
+    Win, bin_ = mk(3 * A, A, seed=3, sc=A ** -0.5), mk(3 * A, seed=4, sc=0.1)
+    Wo, bo = mk(A, A, seed=5, sc=A ** -0.5), mk(A, seed=6, sc=0.1)
+    Wq, bq = mk(A, A, seed=7, sc=A ** -0.5), mk(A, seed=8, sc=0.1)
+    W1, b1 = mk(ff, A, seed=9, sc=A ** -0.5), mk(ff, seed=10, sc=0.1)
+    W2, b2 = mk(A, ff, seed=11, sc=ff ** -0.5), mk(A, seed=12, sc=0.1)
+    ln = [(1 + mk(A, seed=20 + i, sc=0.1), mk(A, seed=30 + i, sc=0.1)) for i in range(3)]
+    pk = ops.pack_token_weight
+    pre_qk, pre_q = (pos @ Win[:2 * A].t()).contiguous(), (pos @ Wq.t()).contiguous()
+    # SALayer
+    ref, _ = _ref_token_layer(x, nhead, Wo, bo, ln[0], Win=Win, bin_=bin_, pos=pos, ffn=(W1, b1, W2, b2, *ln[1]))
+    got = x.clone()
+    ops.token_layer(got, nhead, pk(Wo), bo, *ln[0], w_in=pk(Win), b_in=bin_, pre_qk=pre_qk, ffn=(pk(W1), b1, pk(W2), b2, *ln[1], ff))
+    assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)
+    # SCALayer, first half: self attention + norm1 + query projection
+    ref1, refq = _ref_token_layer(x, nhead, Wo, bo, ln[0], Win=Win, bin_=bin_, pos=pos, Wq=Wq, bq=bq)
+    got1, cq = x.clone(), torch.zeros_like(x)
+    ops.token_layer(got1, nhead, pk(Wo), bo, *ln[0], w_in=pk(Win), b_in=bin_, pre_qk=pre_qk, w_q=pk(Wq), b_q=bq, pre_q=pre_q, cq_out=cq)
+    assert rel_l2(got1, ref1) < 1e-2 and rel_l2(cq, refq) < 1e-2, (rel_l2(got1, ref1), rel_l2(cq, refq))
+    # SCALayer, second half: out_proj of the cross attention's output + norm2 + FFN + norm3
+    o_in = mk(B, M, A, seed=40)
+    ref2, _ = _ref_token_layer(x, nhead, Wo, bo, ln[2], o_in=o_in, ffn=(W1, b1, W2, b2, *ln[1]))
+    got2 = x.clone()
+    ops.token_layer(got2, nhead, pk(Wo), bo, *ln[2], o_in=o_in, ffn=(pk(W1), b1, pk(W2), b2, *ln[1], ff))
+    assert rel_l2(got2, ref2) < 1e-2, rel_l2(got2, ref2)
+    # no query positions (FACT.trans): pre tables absent
+    ref3, _ = _ref_token_layer(x, nhead, Wo, bo, ln[0], Win=Win, bin_=bin_, ffn=(W1, b1, W2, b2, *ln[1]))
+    got3 = x.clone()
+    ops.token_layer(got3, nhead, pk(Wo), bo, *ln[0], w_in=pk(Win), b_in=bin_, ffn=(pk(W1), b1, pk(W2), b2, *ln[1], ff))
+    assert rel_l2(got3, ref3) < 1e-2, rel_l2(got3, ref3)
