@@ -428,9 +428,10 @@ _WS = {}
 def _ws(dev, n):
     """Scratch of at least n floats on ``dev`` (grown geometrically, reused by every reduction of the backward pass --
     launches on one stream are ordered, so consecutive users cannot overlap)."""
-    t = _WS.get(dev)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)         # one scratch per stream: users on different streams may overlap
+    t = _WS.get(key)
     if t is None or t.numel() < n:
-        t = _WS[dev] = torch.empty(max(int(n * 1.25), 1 << 20), dtype=torch.float32, device=dev)
+        t = _WS[key] = torch.empty(max(int(n * 1.25), 1 << 20), dtype=torch.float32, device=dev)
     return t
 
 

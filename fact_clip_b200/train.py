@@ -23,6 +23,7 @@ Train-mode augmentations of the reference forward (blocks.py:614-622): ``Dropout
 counter-based hash of (seed, site, element) so the backward pass regenerates them; ``engine.seed`` changes every step.
 """
 import math
+import os
 import random
 
 import torch
@@ -79,6 +80,10 @@ class TrainEngine(FactEngine):
         self.forced_masks = None          # tests: {'cmr': keep mask [B, D]} injected instead of the hashed one
         self.use_graphs = False           # capture the step into CUDA graphs per batch shape (net.train_graphs = True)
         self._steps, self._cur, self._cap_stream, self._const, self._seed_dev = {}, None, None, {}, None
+        # parameter gradients (weight / bias reductions) are off the backward pass's critical path: they run on a second stream and
+        # fill the SMs that the latency-bound stretches (GRU chain, token-side kernels) leave idle; joined at every section's end
+        self.side_wgrad = os.environ.get('FACTK_SIDE_WGRAD', '1') != '0'
+        self._side, self._side_keep, self._side_busy = None, [], False
         self.tape = []
         if hp['trans'] or self.vn is not None:
             raise NotImplementedError('training step: FACT.trans and the Epic verb/noun model are not built (query-token FACT / '
@@ -267,7 +272,7 @@ class TrainEngine(FactEngine):
                 if isinstance(bias, Var):
                     ops.colsum(dz, N, self.G(bias), len=ln, per_video=True)
                 elif bias.g is not None:
-                    ops.colsum(dz, N, bias.g, len=ln)
+                    self.pgrad(lambda: ops.colsum(dz, N, bias.g, len=ln), dz)
             if pre is not None:
                 if pre_seg is None:
                     ops.ew(ops.EW_AXPY, dz, self.G(pre), N, len=ln)
@@ -282,7 +287,8 @@ class TrainEngine(FactEngine):
                     self.wgrad(dz, x.v, N, K, self.G(Wh), off=s['off'], len=ln, alpha=alpha, pos=s['pos'], pos_idx=s['pos_idx'],
                                per_video=True)
                 elif Wh.g is not None:
-                    self.wgrad(dz, x.v, N, K, Wh.g, off=s['off'], len=ln, alpha=alpha, pos=s['pos'], pos_idx=s['pos_idx'])
+                    self.pgrad(lambda x=x, Wh=Wh, K=K, s=s: self.wgrad(dz, x.v, N, K, Wh.g, off=s['off'], len=ln, alpha=alpha, pos=s['pos'],
+                                                                      pos_idx=s['pos_idx']), dz, x.v)
                 # data gradient: every tap of the same x in one multi-source GEMM accumulating into x.g
                 if not x.needs_grad or i in done:
                     continue
@@ -316,6 +322,28 @@ class TrainEngine(FactEngine):
 
     def wgrad(self, dz, a, N, K, dw, **kw):
         return ops.wgrad(dz, a, N, K, dw, tc=(self.mode == 'bf16'), **kw)
+
+    def pgrad(self, fn, *keep):
+        """Run ``fn`` (launches that only produce PARAMETER gradients) on the side stream, after everything launched so far.
+        ``keep``: the tensors it reads -- held until the join so the allocator cannot hand their memory to the main stream."""
+        if not self.side_wgrad:
+            return fn()
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            fn()
+        self._side_keep.extend(keep)
+        self._side_busy = True
+
+    def _side_join(self):
+        if self._side_busy:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_busy = False
+        self._side_keep.clear()
 
     def add(self, a, b, N=None):
         N = a.v.shape[-1] if N is None else N
@@ -803,10 +831,12 @@ class TrainEngine(FactEngine):
             gi.g = self.new((B, slot, 6 * Hh), zero=True)
             dgh = self.new((B, slot, 6 * Hh), zero=True)
             ops.gru_bwd(gi.v, gh, y.v, y.g, Whf.w, Whb.w, gi.g, dgh, nseg)
-            self.wgrad(dgh[:, :, :3 * Hh], y.v[:, :, :Hh], 3 * Hh, Hh, Whf.g, off=-1, len=nseg)
-            self.wgrad(dgh[:, :, 3 * Hh:], y.v[:, :, Hh:], 3 * Hh, Hh, Whb.g, off=1, len=nseg)
-            ops.colsum(dgh[:, :, :3 * Hh], 3 * Hh, bhf.g, len=nseg)
-            ops.colsum(dgh[:, :, 3 * Hh:], 3 * Hh, bhb.g, len=nseg)
+            def param_grads():
+                self.wgrad(dgh[:, :, :3 * Hh], y.v[:, :, :Hh], 3 * Hh, Hh, Whf.g, off=-1, len=nseg)
+                self.wgrad(dgh[:, :, 3 * Hh:], y.v[:, :, Hh:], 3 * Hh, Hh, Whb.g, off=1, len=nseg)
+                ops.colsum(dgh[:, :, :3 * Hh], 3 * Hh, bhf.g, len=nseg)
+                ops.colsum(dgh[:, :, 3 * Hh:], 3 * Hh, bhb.g, len=nseg)
+            self.pgrad(param_grads, dgh, y.v)
         self.tape.append(bwd)
         return y
 
@@ -1042,12 +1072,14 @@ class TrainEngine(FactEngine):
                 with torch.cuda.graph(g, stream=self._cap_stream):
                     for fn in fns:
                         fn()
+                    self._side_join()
                     self._finish_derived(derived)
                 g.replay()
                 st['gB'].append((g, k))
             else:
                 for fn in fns:
                     fn()
+                self._side_join()
                 self._finish_derived(derived)
             if k is not None:
                 self._section_done(k)
