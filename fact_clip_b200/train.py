@@ -820,7 +820,9 @@ class TrainEngine(FactEngine):
         bhf, bhb = self.W(f'{g}bias_hh_l{l}'), self.W(f'{g}bias_hh_l{l}_reverse')
         Hh = Whf.w.shape[1]
         y = Var(self.new((B, slot, 2 * Hh), zero=True), nseg)
-        ops.gru_bidir(gi.v, Whf.w, bhf.w, Whb.w, bhb.w, y.v, nseg, relu=False)
+        # bf16 mode: the inference engine's tensor-core recurrence (bf16 weights and exchanged state, flag-in-data exchange: about
+        # half the per-step latency of the fp32 cluster kernel); the backward pass re-derives the gates from the saved states
+        ops.gru_bidir(gi.v, Whf.w, bhf.w, Whb.w, bhb.w, y.v, nseg, relu=False, mma=(self.mode == 'bf16' and self.use_tc and Hh == 256))
 
         def bwd():
             if y.g is None:
