@@ -301,11 +301,34 @@ def run_train(args):
     phases = {'fwd_loss': 0.0, 'bwd': 0.0, 'allreduce_wait': 0.0, 'clip_opt': 0.0}
     info = {}
 
+    # input pipeline: the pinned-host -> device copy of the NEXT step's video is issued on a copy stream while this step computes
+    # (a prefetching data loader); every timed step still pays for one 134 MB copy inside the timed region, off the critical path
+    copy_stream, staged = torch.cuda.Stream(), {}
+
+    def prefetch(i):
+        x, y = hosts[i % 2]
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
+            xd, yd = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        staged[i % 2] = (xd, yd, done)
+
     def step(i, timed):
         x, y = hosts[i % 2]
         e = [ev() for _ in range(5)]
         e[0].record()
-        xs, ys = [x.to(dev, non_blocking=True)], [y.to(dev, non_blocking=True)]
+        if args.no_prefetch:
+            xs, ys = [x.to(dev, non_blocking=True)], [y.to(dev, non_blocking=True)]
+        else:
+            if i % 2 not in staged:
+                prefetch(i)
+            xd, yd, done = staged.pop(i % 2)
+            torch.cuda.current_stream().wait_event(done)
+            xd.record_stream(torch.cuda.current_stream())
+            yd.record_stream(torch.cuda.current_stream())
+            xs, ys = [xd], [yd]
+            prefetch(i + 1)
         opt.zero_grad(set_to_none=True)
         loss, saves = net(xs, ys, compute_loss=True)
         e[1].record()
@@ -401,7 +424,9 @@ def run_train(args):
                                f'T={T}, D={D}, C={ncls}, one video per GPU per step; train-mode forward + loss + backward + DP all-reduce + '
                                f'clip_grad_norm_ + Adam step; random-init weights (segments per U block below)',
                    'segments_per_U_block_rank0': info.get('nseg'), 'params': nparam, 'loss_rank0': info.get('loss'),
-                   'l2_policy': f'inputs larger than L2 ({T * D * 4 / 2**20:.0f} MiB of fp32 features per step; activations far larger)'},
+                   'l2_policy': f'inputs larger than L2 ({T * D * 4 / 2**20:.0f} MiB of fp32 features per step; activations far larger)',
+                   'input_pipeline': 'per-step copy at the start of the step' if args.no_prefetch else
+                                     'next step\'s video copied pinned-host -> device on a copy stream during this step (one copy per timed step)'},
         'clocks': clocks, 'gpu_launches': info.get('launches'), 'launch': 'cuda-graph' if net.train_graphs else 'eager',
         'e2e': {'value': frames / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': (T * D * 4 + T * 8) * world, 'd2h_bytes_per_step': T * 8 * world,
                 'note': 'the timed step includes the pinned-host -> device copy of the video and the device -> host copy of the predictions and the loss'},
@@ -427,6 +452,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-split', type=int, default=4, help='sub-batches per step on the end-to-end (pipelined) path')
     ap.add_argument('--no-graph', action='store_true', help='eager kernel launches instead of one CUDA graph per batch')
+    ap.add_argument('--no-prefetch', action='store_true', help='(--train) copy each step\'s video to the device at the start of the step instead of during the previous step')
     ap.add_argument('--timeline', action='store_true', help='(--train) torch.profiler device timeline of one step: busy / idle / top kernels, to stderr')
     ap.add_argument('--profile', action='store_true', help='print a CUDA-event breakdown per kernel family to stderr')
     ap.add_argument('--train', action='store_true', help='BASELINE config 5: data-parallel training step (Epic-Kitchens shape, T=16384)')

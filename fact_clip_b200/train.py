@@ -518,9 +518,11 @@ class TrainEngine(FactEngine):
         dh, Mp = A // nhead, _round_up(M, 4)
         alpha = 1.0 / math.sqrt(dh)
         mm = lambda a, b, c, m, n, kd, hs, **kw: ops.heads_mm(a, b, c, m, n, kd, nhead, *hs, len=rlen, **kw)
-        L_ = self.new((B, slot, nhead * Mp), zero=True)
+        # [frames x heads x tokens] fp32 tensors (157 MB at T = 16384, M = 300): not zero-filled -- every reader is bounded by the
+        # valid rows and the M columns per head, which every writer covers
+        L_ = self.new((B, slot, nhead * Mp))
         mm(kk.v, q.v, L_, slot, M, dh, (dh, dh, Mp), len_mode=1, alpha=alpha)
-        Pv = Var(self.new((B, slot, nhead * Mp), zero=True), rlen)
+        Pv = Var(self.new((B, slot, nhead * Mp)), rlen)
         ops.col_softmax(L_, Pv.v, nhead * Mp, len=rlen)
         del L_
 
@@ -539,7 +541,10 @@ class TrainEngine(FactEngine):
         def bwd_apply():
             if o.g is None:
                 return
-            mm(vv.v, o.g, self.G(Pd), slot, M, dh, (dh, dh, Mp), len_mode=1, accumulate=True)
+            fresh = Pd.g is None                        # first (only) writer of dP: no zero fill, no read-modify-write
+            if fresh:
+                Pd.g = self.new(Pd.v.shape)
+            mm(vv.v, o.g, Pd.g, slot, M, dh, (dh, dh, Mp), len_mode=1, accumulate=not fresh)
             mm(Pd.v, o.g, self.G(vv), slot, dh, M, (Mp, dh, dh), b_kmajor=True, len_mode=1, accumulate=True)
         self.tape.append(bwd_apply)
         return o
