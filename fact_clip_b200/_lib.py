@@ -114,8 +114,8 @@ _SIGS = {
                                   i32, vp, vp]),
     'factk_l2norm_bwd': (i32, [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, f32, vp]),
     'factk_col_softmax_train_ws_floats': (C.c_size_t, [i32, i32, i32]),
-    'factk_col_softmax': (i32, [vp, i32, vp, i32, i32, f32, i32, i32, vp, vp, vp]),
-    'factk_col_softmax_bwd': (i32, [vp, i32, vp, i32, vp, i32, i32, f32, i32, i32, i32, vp, vp, vp]),
+    'factk_col_softmax': (i32, [vp, i32, i32, vp, i32, i32, i32, f32, i32, i32, vp, vp, vp]),
+    'factk_col_softmax_bwd': (i32, [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp]),
     'factk_segment_reduce': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'factk_segment_expand': (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
     'factk_gru_bwd': (i32, [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, i32, i32, vp, vp]),

@@ -431,7 +431,7 @@ constexpr int CS_ROWS = 256;      // rows per partial chunk of the column statis
 __host__ __device__ inline int cs_nchunk(int slot) { return (slot + CS_ROWS - 1) / CS_ROWS; }
 
 // ws[(b, chunk)][m] = (max, sum exp(x - max)) over the chunk's rows.  Thread per column, coalesced over m.
-__global__ void colsm_stats_kernel(const float* __restrict__ L, int ldl, float* __restrict__ ws, int M, int slot,
+__global__ void colsm_stats_kernel(const void* __restrict__ L, int l_dtype, int ldl, float* __restrict__ ws, int M, int slot,
                                    const int32_t* __restrict__ len, int nchunk, float scale) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x, chunk = blockIdx.y, b = blockIdx.z;
     const int len_b = len ? min(len[b], slot) : slot;
@@ -439,8 +439,9 @@ __global__ void colsm_stats_kernel(const float* __restrict__ L, int ldl, float* 
     if (m >= M || r0 >= len_b) return;
     const int r1 = min(r0 + CS_ROWS, len_b);
     float mx = -INFINITY, s = 0.f;
+#pragma unroll 4
     for (int r = r0; r < r1; ++r) {
-        const float x = scale * L[((size_t)b * slot + r) * ldl + m];
+        const float x = scale * ld_elem(L, l_dtype, ((size_t)b * slot + r) * ldl + m);
         if (x > mx) { s = s * __expf(mx - x) + 1.f; mx = x; }
         else s += __expf(x - mx);
     }
@@ -465,29 +466,62 @@ __global__ void colsm_combine_kernel(const float* __restrict__ ws, float* __rest
     stats[((size_t)b * M + m) * 2 + 1] = 1.f / s;
 }
 
-__global__ void colsm_normalize_kernel(const float* __restrict__ L, int ldl, const float* __restrict__ stats, float* __restrict__ P, int ldp,
-                                       int M, int slot, const int32_t* __restrict__ len, float scale) {
-    const int b = blockIdx.z, t = blockIdx.y;
+// Four adjacent columns per thread, CS_TR rows per CTA (vector loads / stores when the rows allow it).
+constexpr int CS_TR = 8;
+__global__ void __launch_bounds__(128) colsm_normalize_kernel(const void* __restrict__ L, int l_dtype, int ldl, const float* __restrict__ stats,
+                                                              void* __restrict__ P, int p_dtype, int ldp, int M, int slot,
+                                                              const int32_t* __restrict__ len, float scale, int vec) {
+    const int b = blockIdx.z, m = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int len_b = len ? min(len[b], slot) : slot;
-    if (t >= len_b) return;
-    const size_t row = (size_t)b * slot + t;
-    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
-        const float* s = stats + ((size_t)b * M + m) * 2;
-        P[row * ldp + m] = __expf(scale * L[row * ldl + m] - s[0]) * s[1];
+    if (m >= M) return;
+    float mx[4], is[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float* st = stats + ((size_t)b * M + min(m + j, M - 1)) * 2;
+        mx[j] = st[0]; is[j] = st[1];
+    }
+    const int t1 = min((int)(blockIdx.y + 1) * CS_TR, len_b);
+    for (int t = blockIdx.y * CS_TR; t < t1; ++t) {
+        const size_t row = (size_t)b * slot + t;
+        if (vec && m + 4 <= M) {
+            const float4 x = ld_vec4(L, l_dtype, row * ldl + m);
+            st_vec4(P, p_dtype, row * ldp + m, make_float4(__expf(scale * x.x - mx[0]) * is[0], __expf(scale * x.y - mx[1]) * is[1],
+                                                           __expf(scale * x.z - mx[2]) * is[2], __expf(scale * x.w - mx[3]) * is[3]));
+        } else {
+            for (int j = 0; j < 4 && m + j < M; ++j)
+                st_elem(P, p_dtype, row * ldp + m + j, __expf(scale * ld_elem(L, l_dtype, row * ldl + m + j) - mx[j]) * is[j]);
+        }
     }
 }
 
 // dL[t,m] (+)= scale * P[t,m] * (dP[t,m] - c[m]),  c[m] = sum_t P[t,m] dP[t,m]  (cvec from the colsum of P * dP)
-__global__ void colsm_bwd_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ dP, int lddp, const float* __restrict__ cvec,
-                                 float* __restrict__ dL, int lddl, int M, int slot, const int32_t* __restrict__ len, float scale,
-                                 int accumulate) {
-    const int b = blockIdx.z, t = blockIdx.y;
+__global__ void __launch_bounds__(128) colsm_bwd_kernel(const void* __restrict__ P, int p_dtype, int ldp, const void* __restrict__ dP, int dp_dtype,
+                                                        int lddp, const float* __restrict__ cvec, void* __restrict__ dL, int dl_dtype, int lddl,
+                                                        int M, int slot, const int32_t* __restrict__ len, float scale, int accumulate, int vec) {
+    const int b = blockIdx.z, m = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int len_b = len ? min(len[b], slot) : slot;
-    if (t >= len_b) return;
-    const size_t row = (size_t)b * slot + t;
-    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
-        const float g = scale * P[row * ldp + m] * (dP[row * lddp + m] - cvec[(size_t)b * M + m]);
-        dL[row * lddl + m] = g + (accumulate ? dL[row * lddl + m] : 0.f);
+    if (m >= M) return;
+    float c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = cvec[(size_t)b * M + min(m + j, M - 1)];
+    const int t1 = min((int)(blockIdx.y + 1) * CS_TR, len_b);
+    for (int t = blockIdx.y * CS_TR; t < t1; ++t) {
+        const size_t row = (size_t)b * slot + t;
+        if (vec && m + 4 <= M) {
+            const float4 p = ld_vec4(P, p_dtype, row * ldp + m), d = ld_vec4(dP, dp_dtype, row * lddp + m);
+            float4 g = make_float4(scale * p.x * (d.x - c[0]), scale * p.y * (d.y - c[1]), scale * p.z * (d.z - c[2]), scale * p.w * (d.w - c[3]));
+            if (accumulate) {
+                const float4 o = ld_vec4(dL, dl_dtype, row * lddl + m);
+                g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+            }
+            st_vec4(dL, dl_dtype, row * lddl + m, g);
+        } else {
+            for (int j = 0; j < 4 && m + j < M; ++j) {
+                float g = scale * ld_elem(P, p_dtype, row * ldp + m + j) * (ld_elem(dP, dp_dtype, row * lddp + m + j) - c[j]);
+                if (accumulate) g += ld_elem(dL, dl_dtype, row * lddl + m + j);
+                st_elem(dL, dl_dtype, row * lddl + m + j, g);
+            }
+        }
     }
 }
 
@@ -634,28 +668,35 @@ extern "C" size_t factk_col_softmax_train_ws_floats(int B, int slot, int M) {
     return (size_t)B * cs_nchunk(slot) * M * 2 + (size_t)B * M * 2;
 }
 
-/* P[b,t,m] = softmax over the valid rows t of scale * L[b,t,m]  (normalised attention kept for the backward pass) */
-extern "C" int factk_col_softmax(const float* L, int ldl, float* P, int ldp, int M, float scale, int B, int slot, const int32_t* len,
-                                 float* ws, void* stream) {
+static bool rows_vec4(const void* p, int dtype, int ld) {
+    return (reinterpret_cast<uintptr_t>(p) & (dtype == FACTK_BF16 ? 7u : 15u)) == 0 && (ld & 3) == 0;
+}
+
+/* P[b,t,m] = softmax over the valid rows t of scale * L[b,t,m]  (normalised attention kept for the backward pass); L, P fp32 or bf16 */
+extern "C" int factk_col_softmax(const void* L, int l_dtype, int ldl, void* P, int p_dtype, int ldp, int M, float scale, int B, int slot,
+                                 const int32_t* len, float* ws, void* stream) {
     FACTK_REQUIRE(L && P && ws && M > 0, "factk_col_softmax: bad args");
     const int nchunk = cs_nchunk(slot);
     float* stats = ws + (size_t)B * nchunk * M * 2;
     cudaStream_t st = (cudaStream_t)stream;
-    colsm_stats_kernel<<<dim3((M + 63) / 64, nchunk, B), 64, 0, st>>>(L, ldl, ws, M, slot, len, nchunk, scale);
+    colsm_stats_kernel<<<dim3((M + 63) / 64, nchunk, B), 64, 0, st>>>(L, l_dtype, ldl, ws, M, slot, len, nchunk, scale);
     colsm_combine_kernel<<<dim3((M + 63) / 64, B), 64, 0, st>>>(ws, stats, M, slot, len, nchunk);
-    colsm_normalize_kernel<<<dim3((M + 127) / 128, slot, B), 128, 0, st>>>(L, ldl, stats, P, ldp, M, slot, len, scale);
+    const int vec = rows_vec4(L, l_dtype, ldl) && rows_vec4(P, p_dtype, ldp);
+    colsm_normalize_kernel<<<dim3((M + 511) / 512, (slot + CS_TR - 1) / CS_TR, B), 128, 0, st>>>(L, l_dtype, ldl, stats, P, p_dtype, ldp, M, slot,
+                                                                                                len, scale, vec);
     return check_launch("factk_col_softmax");
 }
 
-/* dL (+)= scale * P * (dP - colsum(P * dP)); ws: factk_colsum_ws_floats(B, slot, M) + B*M floats */
-extern "C" int factk_col_softmax_bwd(const float* P, int ldp, const float* dP, int lddp, float* dL, int lddl, int M, float scale,
-                                     int accumulate, int B, int slot, const int32_t* len, float* ws, void* stream) {
+/* dL (+)= scale * P * (dP - colsum(P * dP)); P, dP, dL fp32 or bf16; ws: factk_colsum_ws_floats(B, slot, M) + B*M floats */
+extern "C" int factk_col_softmax_bwd(const void* P, int p_dtype, int ldp, const void* dP, int dp_dtype, int lddp, void* dL, int dl_dtype, int lddl,
+                                     int M, float scale, int accumulate, int B, int slot, const int32_t* len, float* ws, void* stream) {
     FACTK_REQUIRE(P && dP && dL && ws && M > 0, "factk_col_softmax_bwd: bad args");
     float* cvec = ws + factk_colsum_ws_floats(B, slot, M);
-    int rc = factk_colsum(P, FACTK_F32, ldp, dP, FACTK_F32, lddp, M, cvec, M, 1.f, 0, B, slot, len, ws, stream);
+    int rc = factk_colsum(P, p_dtype, ldp, dP, dp_dtype, lddp, M, cvec, M, 1.f, 0, B, slot, len, ws, stream);
     if (rc) return rc;
-    colsm_bwd_kernel<<<dim3((M + 127) / 128, slot, B), 128, 0, (cudaStream_t)stream>>>(P, ldp, dP, lddp, cvec, dL, lddl, M, slot, len, scale,
-                                                                                     accumulate);
+    const int vec = rows_vec4(P, p_dtype, ldp) && rows_vec4(dP, dp_dtype, lddp) && rows_vec4(dL, dl_dtype, lddl);
+    colsm_bwd_kernel<<<dim3((M + 511) / 512, (slot + CS_TR - 1) / CS_TR, B), 128, 0, (cudaStream_t)stream>>>(
+        P, p_dtype, ldp, dP, dp_dtype, lddp, cvec, dL, dl_dtype, lddl, M, slot, len, scale, accumulate, vec);
     return check_launch("factk_col_softmax_bwd");
 }
 

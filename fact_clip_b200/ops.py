@@ -540,16 +540,16 @@ def col_softmax(logit, p, M, scale=1.0, len=None):
     B, slot = logit.shape[0], logit.shape[1]
     ws = _ws(logit.device, L.load().factk_col_softmax_train_ws_floats(B, slot, M))
     COUNTERS['launches'] += 3
-    _call('factk_col_softmax', None, logit.data_ptr(), _row_ld(logit), p.data_ptr(), _row_ld(p), M, float(scale), B, slot, L.ptr(len),
-          ws.data_ptr(), L.stream())
+    _call('factk_col_softmax', None, logit.data_ptr(), L.dt(logit), _row_ld(logit), p.data_ptr(), L.dt(p), _row_ld(p), M, float(scale), B, slot,
+          L.ptr(len), ws.data_ptr(), L.stream())
 
 
 def col_softmax_bwd(p, dp, dl, M, scale=1.0, len=None, accumulate=False):
     B, slot = p.shape[0], p.shape[1]
     ws = _ws(p.device, L.load().factk_colsum_ws_floats(B, slot, M) + B * M)
     COUNTERS['launches'] += 3
-    _call('factk_col_softmax_bwd', None, p.data_ptr(), _row_ld(p), dp.data_ptr(), _row_ld(dp), dl.data_ptr(), _row_ld(dl), M, float(scale),
-          int(accumulate), B, slot, L.ptr(len), ws.data_ptr(), L.stream())
+    _call('factk_col_softmax_bwd', None, p.data_ptr(), L.dt(p), _row_ld(p), dp.data_ptr(), L.dt(dp), _row_ld(dp), dl.data_ptr(), L.dt(dl), _row_ld(dl),
+          M, float(scale), int(accumulate), B, slot, L.ptr(len), ws.data_ptr(), L.stream())
 
 
 def segment_reduce(x, out, seg_start, seg_len, nseg, E, mean=False, accumulate=True):

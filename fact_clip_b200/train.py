@@ -83,6 +83,7 @@ class TrainEngine(FactEngine):
         # parameter gradients (weight / bias reductions) are off the backward pass's critical path: they run on a second stream and
         # fill the SMs that the latency-bound stretches (GRU chain, token-side kernels) leave idle; joined at every section's end
         self.side_wgrad = os.environ.get('FACTK_SIDE_WGRAD', '1') != '0'
+        self.tc_cross_attn = os.environ.get('FACTK_TC_CROSS_ATTN', '1') != '0'      # SCA cross attention as block-diagonal tcgen05 GEMMs
         self._side, self._side_keep, self._side_busy = None, [], False
         self.tape = []
         if hp['trans'] or self.vn is not None:
@@ -396,12 +397,14 @@ class TrainEngine(FactEngine):
         def bwd():
             if y.g is None or not x.needs_grad:
                 return
-            t = torch.empty_like(y.g)
+            first = x.g is None                      # first writer of x.g: the masked gradient goes straight into it
+            t = self.G(x) if first else torch.empty_like(y.g)
             if forced is not None:
                 ops.ew(ops.EW_MUL, y.g, t, N, r=forced, len=x.len)
             else:
                 ops.ew(op, y.g, t, N, len=x.len, p=p, seed=self.seed, site=site, seed_ptr=self.seed_dev)
-            ops.ew(ops.EW_AXPY, t, self.G(x), N, len=x.len)
+            if not first:
+                ops.ew(ops.EW_AXPY, t, self.G(x), N, len=x.len)
         self.tape.append(bwd)
         return y
 
@@ -517,6 +520,9 @@ class TrainEngine(FactEngine):
         slot = kk.v.shape[1]
         dh, Mp = A // nhead, _round_up(M, 4)
         alpha = 1.0 / math.sqrt(dh)
+        if (self.mode == 'bf16' and self.use_tc and self.tc_cross_attn and kk.v.dtype == torch.bfloat16 and vv.v.dtype == torch.bfloat16
+                and A % 64 == 0 and slot % 64 == 0):
+            return self._cross_attn_tc(q, kk, vv, nhead, rlen, p_drop)
         mm = lambda a, b, c, m, n, kd, hs, **kw: ops.heads_mm(a, b, c, m, n, kd, nhead, *hs, len=rlen, **kw)
         # [frames x heads x tokens] fp32 tensors (157 MB at T = 16384, M = 300): not zero-filled -- every reader is bounded by the
         # valid rows and the M columns per head, which every writer covers
@@ -546,6 +552,68 @@ class TrainEngine(FactEngine):
                 Pd.g = self.new(Pd.v.shape)
             mm(vv.v, o.g, Pd.g, slot, M, dh, (dh, dh, Mp), len_mode=1, accumulate=not fresh)
             mm(Pd.v, o.g, self.G(vv), slot, dh, M, (Mp, dh, dh), b_kmajor=True, len_mode=1, accumulate=True)
+        self.tape.append(bwd_apply)
+        return o
+
+    def _cross_attn_tc(self, q, kk, vv, nhead, rlen, p_drop):
+        """cross_attn on the tcgen05 kernels (bf16 mode).  The per-head products become dense GEMMs against BLOCK-DIAGONAL token
+        operands -- row h * Mp + m of the [heads * Mp, A] operand holds token m's head-h channels in head h's columns, zeros
+        elsewhere -- so all heads share one launch of the generic tensor-core GEMM / weight-gradient kernels: 8x the useful
+        flops at a tensor rate two orders above the CUDA cores', and the [frames x heads x tokens] probability tensors are bf16
+        (half the HBM traffic, which is what bounds these launches).  The reductions over the frames (apply, dq) are the
+        tcgen05 weight-gradient contraction; their block-diagonal part is the result."""
+        B, M, A = q.v.shape
+        slot = kk.v.shape[1]
+        dh = A // nhead
+        Mp = _round_up(M, 64 // math.gcd(nhead, 64))          # heads * Mp % 64 == 0: the K extent of a bf16 tensor-core source
+        NP, bf = nhead * Mp, torch.bfloat16
+        alpha = 1.0 / math.sqrt(dh)
+
+        def blockdiag(x):                         # [B, M, A] -> [B, NP, A] bf16
+            out = self.new((B, NP, A), bf, zero=True)
+            out.view(B, nhead, Mp, nhead, dh).diagonal(dim1=1, dim2=3)[:, :M].copy_(x.view(B, M, nhead, dh).permute(0, 1, 3, 2))
+            return out
+
+        def diag_of(full):                        # [B, NP, A] -> the [B, M, dh, heads] view of its diagonal blocks
+            return full.view(B, nhead, Mp, nhead, dh).diagonal(dim1=1, dim2=3)[:, :M]
+
+        tcg = lambda A_, W_, N_, out, **kw: ops.gemm([S(A_, W_)], N_, out, len=rlen, tc=True, **kw)
+        Qbd = blockdiag(q.v)
+        L_ = self.new((B, slot, NP), bf)
+        tcg(kk.v, Qbd, NP, L_, alpha=alpha)
+        # zero beyond the valid rows: the tcgen05 weight-gradient contraction consumes whole 64-row stages
+        Pv = Var(self.new((B, slot, NP), bf, zero=True), rlen)
+        ops.col_softmax(L_, Pv.v, NP, len=rlen)
+        del L_
+
+        def bwd_softmax():
+            if Pv.g is None:
+                return
+            dL = Pv.g                                   # in place
+            ops.col_softmax_bwd(Pv.v, Pv.g, dL, NP, len=rlen)
+            kg = self.G(kk)
+            tcg(dL, dense(Qbd.transpose(1, 2)), A, kg, alpha=alpha, res=kg)
+            full = self.new((B, NP, A))
+            ops.wgrad(dL, kk.v, NP, A, full, len=rlen, alpha=alpha, accumulate=False, per_video=True, tc=True)
+            self.G(q).view(B, M, nhead, dh).permute(0, 1, 3, 2).add_(diag_of(full))
+        self.tape.append(bwd_softmax)
+        Pd = self.dropout(Pv, p_drop)
+        o = Var(self.new((B, M, A)))
+        full = self.new((B, NP, A))
+        ops.wgrad(Pd.v, vv.v, NP, A, full, len=rlen, accumulate=False, per_video=True, tc=True)
+        o.v.view(B, M, nhead, dh).permute(0, 1, 3, 2).copy_(diag_of(full))
+        del full
+
+        def bwd_apply():
+            if o.g is None:
+                return
+            OGbd = blockdiag(o.g)
+            fresh = Pd.g is None
+            if fresh:
+                Pd.g = self.new(Pd.v.shape, bf, zero=True)
+            tcg(vv.v, OGbd, NP, Pd.g, res=None if fresh else Pd.g)
+            vg = self.G(vv)
+            tcg(Pd.v, dense(OGbd.transpose(1, 2)), A, vg, res=vg)
         self.tape.append(bwd_apply)
         return o
 

@@ -481,11 +481,11 @@ int factk_l2norm_bwd(const void* X, int x_dtype, int ldx, const void* dY, int dy
 /* Softmax over ROWS with the normalised attention kept (training forward of X2Y_map f2a, basic.py:373-376, and of the
  * SCALayer cross attention per head, basic.py:507-514) and its backward dL (+)= scale * P * (dP - colsum(P dP)). */
 size_t factk_col_softmax_train_ws_floats(int B, int slot, int M);
-int factk_col_softmax(const float* L, int ldl, float* P, int ldp, int M, float scale, int B, int slot, const int32_t* len,
-                      float* ws, void* stream);
+int factk_col_softmax(const void* L, int l_dtype, int ldl, void* P, int p_dtype, int ldp, int M, float scale, int B, int slot,
+                      const int32_t* len, float* ws, void* stream);
 /* ws: factk_colsum_ws_floats(B, slot, M) + B * M floats */
-int factk_col_softmax_bwd(const float* P, int ldp, const float* dP, int lddp, float* dL, int lddl, int M, float scale,
-                          int accumulate, int B, int slot, const int32_t* len, float* ws, void* stream);
+int factk_col_softmax_bwd(const void* P, int p_dtype, int ldp, const void* dP, int dp_dtype, int lddp, void* dL, int dl_dtype, int lddl,
+                          int M, float scale, int accumulate, int B, int slot, const int32_t* len, float* ws, void* stream);
 
 /* Segment mean backward / gathered pre-activation backward (basic.py:615-625, blocks.py:439-447):
  * reduce: out[b][s] (+)= (mean ? 1/len : 1) * sum of the segment's frame rows; expand: out[b][t] (+)= (inv_len ? 1/len : 1) *
