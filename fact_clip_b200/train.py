@@ -85,7 +85,7 @@ class TrainEngine(FactEngine):
         self.side_wgrad = os.environ.get('FACTK_SIDE_WGRAD', '1') != '0'
         self.tc_cross_attn = os.environ.get('FACTK_TC_CROSS_ATTN', '1') != '0'      # SCA cross attention as block-diagonal tcgen05 GEMMs
         self._side, self._side_keep, self._side_busy = None, [], False
-        self.tape = []
+        self.tape, self._posrows = [], {}
         if hp['trans'] or self.vn is not None:
             raise NotImplementedError('training step: FACT.trans and the Epic verb/noun model are not built (query-token FACT / '
                                       'FACT_CLIP only)')
@@ -106,7 +106,7 @@ class TrainEngine(FactEngine):
         return t
 
     def begin(self):
-        self.tape, self._site = [], 0
+        self.tape, self._site, self._posrows = [], 0, {}
         self._params = dict(self.m.named_parameters())
         self._derived = []                # (tensor with autograd graph, gradient accumulator) of the current section
         self._wt, self._leaf = {}, {}
@@ -431,6 +431,27 @@ class TrainEngine(FactEngine):
         self.tape.append(bwd)
         return y
 
+    def with_pos_t(self, rows, rlen, pos_idx=None):
+        """rows + frame_pos[t or centre] (add_positional_encoding, basic.py:313-320) materialised once per rows tensor and step
+        (FactEngine.with_pos): every GEMM that reads positioned rows -- the SCA key projections, the f2a / a2f logits -- then takes
+        a plain source and stays on the tensor-core kernels, forward and backward."""
+        if self.frame_pos is None:
+            return rows
+        key = (id(rows), None if pos_idx is None else pos_idx.data_ptr())
+        hit = self._posrows.get(key)
+        if hit is not None and hit[0] is rows:
+            return hit[1]
+        N = rows.v.shape[-1]
+        y = Var(torch.zeros_like(rows.v), rlen, needs_grad=rows.needs_grad)
+        ops.ew(ops.EW_ADDTAB, rows.v, y.v, N, r=self.frame_pos, len=rlen, ridx=pos_idx)
+
+        def bwd():
+            if y.g is not None and rows.needs_grad:
+                ops.ew(ops.EW_AXPY, y.g, self.G(rows), N, len=rlen)
+        self.tape.append(bwd)
+        self._posrows[key] = (rows, y)
+        return y
+
     def layernorm(self, x, wname, bname, res=None, relu=False, ln=None):
         w, b = self.W(wname), self.W(bname)
         E = x.v.shape[-1]
@@ -743,7 +764,7 @@ class TrainEngine(FactEngine):
             cq = self.linear([src(self.addpos(tgt, qpos), wq)], A, bias=cb[:A])
             # keys / values in the activation dtype (bf16 in bf16 mode, like the inference engine): their projections, data and
             # weight gradients then run on the tensor cores
-            kk = self.linear([src(frame, wk, pos=self.frame_pos, pos_idx=pos_idx)], A, bias=cb[A:2 * A], ln=rlen, tag='sca_kv')
+            kk = self.linear([src(self.with_pos_t(frame, rlen, pos_idx), wk)], A, bias=cb[A:2 * A], ln=rlen, tag='sca_kv')
             vv = self.linear([src(frame, wv)], A, bias=cb[2 * A:], ln=rlen, tag='sca_kv')
             o = self.cross_attn(cq, kk, vv, nh, rlen, p)
             t2 = self.linear([src(o, self.W(c + 'out_proj.weight'))], A, bias=self.W(c + 'out_proj.bias'))
@@ -785,17 +806,20 @@ class TrainEngine(FactEngine):
         Mp = _round_up(M, 4)
         logit = Var(self.new((self.B, self.slot, Mp), zero=True), rlen)
         cbv = Var(cb.v[:, :, 0], None, None)
-        ops.gemm([S(rows.v, qt.v, pos=self.frame_pos, pos_idx=pos_idx)], M, logit.v, len=rlen, bias=cbv.v)
+        rp = self.with_pos_t(rows, rlen, pos_idx)
+        tc = self.mode == 'bf16' and self.use_tc and H % 64 == 0           # per-video operand: bf16 or tf32 tcgen05 GEMM
+        Wq = qt.v if (not tc or rp.v.dtype == torch.float32) else qt.v.to(rp.v.dtype)
+        ops.gemm([S(rp.v, Wq)], M, logit.v, len=rlen, bias=cbv.v, tc=tc)
 
         def bwd():
             if logit.g is None:
                 return
             ops.colsum(logit.g, M, self.G(cb)[:, :, 0], len=rlen, per_video=True)
-            ops.wgrad(logit.g, rows.v, M, H, self.G(qt), len=rlen, pos=self.frame_pos, pos_idx=pos_idx, per_video=True)
-            if rows.needs_grad:
+            ops.wgrad(logit.g, rp.v, M, H, self.G(qt), len=rlen, per_video=True)
+            if rp.needs_grad:
                 qT = self.new((self.B, H, Mp), zero=True)
                 ops.transpose(qt.v, qT[:, :, :M])
-                rg = self.G(rows)
+                rg = self.G(rp)
                 self.mm([S(logit.g, qT, K=M)], H, rg, len=rlen, res=rg)
         self.tape.append(bwd)
         return logit
