@@ -88,7 +88,8 @@ _SIGS = {
     'factk_match_cost': (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32, f32, f32, vp, i32, vp, i32, i32, i32, vp]),
     'factk_loss_pick': (i32, [vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i32, vp, i32, vp]),
     'factk_loss_smooth': (i32, [vp, i32, i32, vp, i32, i32, vp, i32, i32, vp]),
-    'factk_col_lse': (i32, [vp, i32, i32, i32, vp, vp, vp, i32, vp, i32, i32, vp]),
+    'factk_col_lse_ws_floats': (C.c_size_t, [i32, i32, i32]),
+    'factk_col_lse': (i32, [vp, i32, i32, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp]),
     'factk_token_loss': (i32, [vp, i32, i32, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, vp]),
     'factk_loss_combine': (i32, [vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, i32, f32, f32, i32, vp, vp, i32, vp]),
     'factk_fuse_eval': (i32, [vp, vp, i32, i32, vp, vp, i32, f32, vp, i32, i32, vp, i32, i32, i32, vp]),

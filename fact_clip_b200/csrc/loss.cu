@@ -102,17 +102,22 @@ __global__ void __launch_bounds__(256) smooth_kernel(const float* __restrict__ X
 }
 
 // lse over rows r < nrows[b] (rows with a negative mapped target are skipped when rmask0 is given) for every column.
+// With a workspace the rows are split into LC_ROWS-row chunks across CTAs (a long video at batch 1 would otherwise be ten CTAs
+// walking 16384 rows) and the (max, sum) partials are combined in chunk order by col_lse_combine_kernel.
+constexpr int LC_ROWS = 512;
 __global__ void __launch_bounds__(256) col_lse_kernel(const float* __restrict__ X, int ldx, int xslot, int ncol,
                                                       const int32_t* __restrict__ nrows, const int32_t* __restrict__ rmask0,
                                                       const int32_t* __restrict__ rmap, int rmap_bstride,
-                                                      float* __restrict__ out, int ldo) {
+                                                      float* __restrict__ out, int ldo, float* __restrict__ ws, int nchunk) {
     __shared__ float smx[8][33], sms[8][33];
     const int b = blockIdx.y, cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     const int R = nrows[b];
+    const int r0 = ws ? blockIdx.z * LC_ROWS : 0, r1 = ws ? min(R, r0 + LC_ROWS) : R;
+    if (ws && r0 >= R) return;
     float mx = -INFINITY, s = 0.f;
     if (c < ncol) {
-        for (int r = ry; r < R; r += 8) {
+        for (int r = r0 + ry; r < r1; r += 8) {
             if (rmask0) {
                 int k = rmask0[(size_t)b * xslot + r];
                 if (rmap && k >= 0) k = rmap[(size_t)b * rmap_bstride + k];
@@ -131,8 +136,28 @@ __global__ void __launch_bounds__(256) col_lse_kernel(const float* __restrict__ 
         for (int i = 0; i < 8; ++i) M = fmaxf(M, smx[i][cx]);
         float S = 0.f;
         for (int i = 0; i < 8; ++i) S += (smx[i][cx] == -INFINITY) ? 0.f : sms[i][cx] * expf(smx[i][cx] - M);
-        out[(size_t)b * ldo + c] = M + logf(S);
+        if (ws) {
+            float* o = ws + ((size_t)(b * nchunk + blockIdx.z) * ncol + c) * 2;
+            o[0] = M; o[1] = S;
+        } else {
+            out[(size_t)b * ldo + c] = M + logf(S);
+        }
     }
+}
+
+__global__ void col_lse_combine_kernel(const float* __restrict__ ws, int ncol, const int32_t* __restrict__ nrows, int nchunk,
+                                       float* __restrict__ out, int ldo) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= ncol) return;
+    const int R = nrows[b];
+    float M = -INFINITY;
+    for (int k = 0; k < nchunk && k * LC_ROWS < R; ++k) M = fmaxf(M, ws[((size_t)(b * nchunk + k) * ncol + c) * 2]);
+    float S = 0.f;
+    for (int k = 0; k < nchunk && k * LC_ROWS < R; ++k) {
+        const float* p = ws + ((size_t)(b * nchunk + k) * ncol + c) * 2;
+        S += (p[0] == -INFINITY) ? 0.f : p[1] * expf(p[0] - M);
+    }
+    out[(size_t)b * ldo + c] = M + logf(S);
 }
 
 __global__ void __launch_bounds__(256) label_prep_kernel(const int32_t* __restrict__ label, const int32_t* __restrict__ seg_start,
@@ -342,11 +367,22 @@ extern "C" int factk_loss_smooth(const float* X, int ldx, int ncol, float* part,
     return check_launch("factk_loss_smooth");
 }
 
+extern "C" size_t factk_col_lse_ws_floats(int B, int xslot, int ncol) {
+    return xslot > 2 * factk::LC_ROWS ? (size_t)B * ((xslot + factk::LC_ROWS - 1) / factk::LC_ROWS) * ncol * 2 : 0;
+}
+
 extern "C" int factk_col_lse(const float* X, int ldx, int xslot, int ncol, const int32_t* nrows, const int32_t* rmask0,
-                             const int32_t* rmap, int rmap_bstride, float* out, int ldo, int B, void* stream) {
+                             const int32_t* rmap, int rmap_bstride, float* out, int ldo, int B, float* ws, void* stream) {
     FACTK_REQUIRE(X && nrows && out && B > 0 && ncol > 0 && ldo >= ncol, "factk_col_lse: bad args");
-    col_lse_kernel<<<dim3((ncol + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(X, ldx, xslot, ncol, nrows, rmask0, rmap,
-                                                                                rmap_bstride, out, ldo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ws != nullptr && xslot > 2 * LC_ROWS) {          // long rows tensors: chunks of rows across CTAs, fixed-order combine
+        const int nchunk = (xslot + LC_ROWS - 1) / LC_ROWS;
+        col_lse_kernel<<<dim3((ncol + 31) / 32, B, nchunk), 256, 0, st>>>(X, ldx, xslot, ncol, nrows, rmask0, rmap, rmap_bstride, out, ldo, ws,
+                                                                         nchunk);
+        col_lse_combine_kernel<<<dim3((ncol + 63) / 64, B), 64, 0, st>>>(ws, ncol, nrows, nchunk, out, ldo);
+    } else {
+        col_lse_kernel<<<dim3((ncol + 31) / 32, B), 256, 0, st>>>(X, ldx, xslot, ncol, nrows, rmask0, rmap, rmap_bstride, out, ldo, nullptr, 1);
+    }
     return check_launch("factk_col_lse");
 }
 

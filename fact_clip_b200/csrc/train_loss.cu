@@ -146,12 +146,31 @@ __global__ void xattn_grad_kernel(int mode, const float* __restrict__ X, int ldx
         for (int m = lane; m < M; m += 32) if (mu[m] > 0.f) zs += mu[m] * expf(row[m] - mx);
         zs = warp_sum(zs);
     }
+    // the usual row lies inside one ground-truth segment or straddles two: their (column, weight) pairs are fetched once, not per column
+    const bool few = g1 - g0 <= 1;
+    int c0 = -2, c1 = -2;
+    float q0 = 0.f, q1 = 0.f;
+    if (few) {
+        c0 = cm[g0];
+        const int a0 = gstart[(size_t)b * slot + g0], a1 = a0 + glen[(size_t)b * slot + g0];
+        q0 = (float)(min(fe, a1) - max(fs, a0)) * wm[g0];
+        if (g1 > g0) {
+            c1 = cm[g1];
+            const int b0 = gstart[(size_t)b * slot + g1], b1 = b0 + glen[(size_t)b * slot + g1];
+            q1 = (float)(min(fe, b1) - max(fs, b0)) * wm[g1];
+        }
+    }
+#pragma unroll 2
     for (int m = lane; m < M; m += 32) {
         float q = 0.f;
-        for (int gs = g0; gs <= g1; ++gs) {
-            if (cm[gs] != m) continue;
-            const int s0 = gstart[(size_t)b * slot + gs], s1 = s0 + glen[(size_t)b * slot + gs];
-            q += (float)(min(fe, s1) - max(fs, s0)) * wm[gs];
+        if (few) {
+            q = (m == c0 ? q0 : 0.f) + (m == c1 ? q1 : 0.f);
+        } else {
+            for (int gs = g0; gs <= g1; ++gs) {
+                if (cm[gs] != m) continue;
+                const int s0 = gstart[(size_t)b * slot + gs], s1 = s0 + glen[(size_t)b * slot + gs];
+                q += (float)(min(fe, s1) - max(fs, s0)) * wm[gs];
+            }
         }
         q *= k;
         float g;
@@ -167,25 +186,31 @@ __global__ void xattn_grad_kernel(int mode, const float* __restrict__ X, int ldx
 }
 
 // colmass[b][m] = coef/Z * sum over ground-truth segments gs with col[gs] == m of w[gs] * sum_{t in gs} 1/rlen(t)
-__global__ void xattn_colmass_kernel(float* __restrict__ colmass, int M, const int32_t* __restrict__ gstart, const int32_t* __restrict__ glen,
-                                     const int32_t* __restrict__ gn, const int32_t* __restrict__ colmap, const float* __restrict__ wmap,
-                                     int smax, const int32_t* __restrict__ seg_label, const int32_t* __restrict__ seg_len,
-                                     const int32_t* __restrict__ nrows, const float* __restrict__ coef, int slot) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (m >= M) return;
+// One CTA per (column, video): the frames of a matching segment are spread over the threads (a column that owns most of a long
+// video would otherwise be one thread walking 16384 frames); fixed thread -> frame assignment and block_sum: deterministic.
+__global__ void __launch_bounds__(128) xattn_colmass_kernel(float* __restrict__ colmass, int M, const int32_t* __restrict__ gstart,
+                                                            const int32_t* __restrict__ glen, const int32_t* __restrict__ gn,
+                                                            const int32_t* __restrict__ colmap, const float* __restrict__ wmap, int smax,
+                                                            const int32_t* __restrict__ seg_label, const int32_t* __restrict__ seg_len,
+                                                            const int32_t* __restrict__ nrows, const float* __restrict__ coef, int slot) {
+    __shared__ float sm[32];
+    const int m = blockIdx.x, b = blockIdx.y;
     const float k = coef[b] / (float)min(nrows[b], slot);
     float s = 0.f;
-    for (int gs = 0; gs < gn[b]; ++gs) {
+    const int n_gs = gn[b];
+    for (int gs = 0; gs < n_gs; ++gs) {
         if (colmap[(size_t)b * smax + gs] != m) continue;
         const int s0 = gstart[(size_t)b * slot + gs], n = glen[(size_t)b * slot + gs];
-        float mass = 0.f;
-        if (seg_label)
-            for (int t = s0; t < s0 + n; ++t) mass += 1.f / (float)seg_len[(size_t)b * slot + seg_label[(size_t)b * slot + t]];
-        else
-            mass = (float)n;
-        s += wmap[(size_t)b * smax + gs] * mass;
+        const float w = wmap[(size_t)b * smax + gs];
+        if (seg_label) {
+            for (int t = s0 + threadIdx.x; t < s0 + n; t += blockDim.x)
+                s += w / (float)seg_len[(size_t)b * slot + seg_label[(size_t)b * slot + t]];
+        } else if (threadIdx.x == 0) {
+            s += w * (float)n;
+        }
     }
-    colmass[(size_t)b * M + m] = s * k;
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) colmass[(size_t)b * M + m] = s * k;
 }
 
 // infonce_contrastive_loss (loss.py:280-341) on sim = emb . text^T / temp, restricted to the seen classes (cmap[c] >= 0) and
@@ -267,7 +292,7 @@ extern "C" int factk_loss_grad_xattn(int mode, const float* X, int ldx, int M, f
     FACTK_REQUIRE(mode == 0 ? mult != nullptr : (colmass && col_lse), "factk_loss_grad_xattn: mode %d operands missing", mode);
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 1)
-        xattn_colmass_kernel<<<dim3((M + 63) / 64, B), 64, 0, st>>>(colmass, M, gstart, glen, gn, colmap, wmap, smax, seg_label, seg_len,
+        xattn_colmass_kernel<<<dim3(M, B), 128, 0, st>>>(colmass, M, gstart, glen, gn, colmap, wmap, smax, seg_label, seg_len,
                                                                    nrows, coef, slot);
     xattn_grad_kernel<<<dim3((slot + 7) / 8, B), 256, 0, st>>>(mode, X, ldx, M, dX, lddx, gseg, gstart, glen, colmap, wmap, smax, mult,
                                                              colmass, col_lse, ld_lse, seg_start, seg_len, nrows, coef, slot);

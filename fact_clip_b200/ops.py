@@ -390,9 +390,11 @@ def loss_smooth(X, ncol, part, len, is_logp=False):
 
 def col_lse(X, ncol, nrows, out, rmask0=None, rmap=None):
     B = X.shape[0]
-    COUNTERS['launches'] += 1
+    n = L.load().factk_col_lse_ws_floats(B, X.shape[1], ncol)
+    ws = _ws(X.device, n) if n else None
+    COUNTERS['launches'] += 2 if n else 1
     _call('factk_col_lse', None, X.data_ptr(), _row_ld(X), X.shape[1], ncol, nrows.data_ptr(), L.ptr(rmask0), L.ptr(rmap),
-          0 if rmap is None or rmap.dim() == 1 else rmap.stride(0), out.data_ptr(), out.stride(0), B, L.stream())
+          0 if rmap is None or rmap.dim() == 1 else rmap.stride(0), out.data_ptr(), out.stride(0), B, L.ptr(ws), L.stream())
 
 
 def token_loss(aclogit, aind, sind, nmatch, transcript, cweight, out, logp_mean=False):

@@ -309,8 +309,11 @@ int factk_loss_smooth(const float* X, int ldx, int ncol, float* part, int B, int
                       int is_logp, void* stream);
 
 /* out[b][c] = log-sum-exp over rows r < nrows[b] of X[b][r][c]; rows whose (mapped) rmask0 entry is negative are skipped. */
+/* ws: factk_col_lse_ws_floats(B, xslot, ncol) floats (0: not needed; NULL is always accepted -- one CTA column per 32 columns
+ * then walks all rows); with it long rows tensors are reduced in 512-row chunks across CTAs, combined in chunk order. */
+size_t factk_col_lse_ws_floats(int B, int xslot, int ncol);
 int factk_col_lse(const float* X, int ldx, int xslot, int ncol, const int32_t* nrows, const int32_t* rmask0,
-                  const int32_t* rmap, int rmap_bstride, float* out, int ldo, int B, void* stream);
+                  const int32_t* rmap, int rmap_bstride, float* out, int ldo, int B, float* ws, void* stream);
 
 /* action_token_loss (loss.py:196-209): out[b*out_stride] = class-weighted cross entropy of the tokens, unmatched tokens
  * labelled with the null class C1-1.  logp_mean != 0: the verb/noun model's form (blocks_SepVerbNoun.py:254-266): rows
