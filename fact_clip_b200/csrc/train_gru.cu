@@ -116,9 +116,13 @@ __global__ void __launch_bounds__(GB_THREADS) gru_bwd_kernel(const float* __rest
 // Hh = 256 (every shipped configuration): W_hh^T in REGISTERS.  The shared-memory version above streams its 192 KB weight slice
 // through the LSU every step (>= 1536 cycles of shared-memory bandwidth, measured 4.2 us per step with the cluster barrier);
 // here thread (unit u, slice q) of 512 keeps the 96 weights W_hh[96 q .. 96 q + 95][unit] in registers for the whole kernel,
-// the received dgh vector is read as broadcast 128-bit loads, and the exchange is st.async (16 bytes per store) completing a
-// transaction mbarrier of the destination CTA -- no cluster barrier in the loop (same protocol as the forward kernel, tdu.cu).
+// the received dgh vector is read as broadcast 128-bit loads, and the exchange is plain 16-byte distributed-shared-memory
+// stores with the arrival flag IN the data (the protocol of the tensor-core forward kernel, gru_mma.cu): a word that has not
+// arrived holds a NaN pattern no arithmetic produces; the 64 threads of a K slice poll two words each, meet at a named
+// barrier, read the slice, and re-mark their words after the CTA barrier that ends the step.  (st.async completing a
+// transaction mbarrier cost ~1000 cycles per step here, the flagged stores cost one remote-store latency: 1.9 -> ~1 us.)
 constexpr int GB2_THREADS = 512, GB2_Q = 8, GB2_KS = 96;      // 768 = 8 x 96
+constexpr uint32_t GB2_EMPTY = 0xFFFFFFFFu;                     // "not arrived yet" marker of an exchanged word
 
 __device__ __forceinline__ void gb_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
@@ -144,7 +148,6 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
     __shared__ __align__(16) float mine[3 * U];
     __shared__ float part[GB2_Q][U];
     __shared__ float carry[U];
-    __shared__ __align__(8) uint64_t ready[2];
     const float* W = dir ? w_hh_b : w_hh_f;
     const int tid = threadIdx.x, lane = tid & 31;
     const int u = tid & (U - 1), q = tid >> 6;
@@ -152,17 +155,7 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
 #pragma unroll
     for (int i = 0; i < GB2_KS; ++i) w[i] = W[(size_t)(q * GB2_KS + i) * Hh + rank * U + u];
     if (tid < U) carry[tid] = 0.f;
-    if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&ready[i]);
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(1) : "memory");
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < 2; ++i) {       // arm both phases: every step delivers the 768 dgh values from the four CTAs
-            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&ready[i]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(G * 4) : "memory");
-        }
-    }
+    for (int i = tid; i < 2 * G; i += GB2_THREADS) reinterpret_cast<uint32_t*>(&dfull[0][0])[i] = GB2_EMPTY;
     const int n = min(nseg[b], slot);
     const bool unit = tid < U;
     const int j = rank * U + u;
@@ -183,7 +176,9 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
     };
     if (n > 0) fetch(dir ? 0 : n - 1);
     const uint32_t dfull_u32 = (uint32_t)__cvta_generic_to_shared(&dfull[0][0]);
-    const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(&ready[0]);
+    // polling role: thread p < 48 of slice q owns words 2p, 2p + 1 of the slice's 96
+    const int pl = tid & 63;
+    const uint32_t poll_u32 = dfull_u32 + (uint32_t)(q * GB2_KS + 2 * pl) * 4u;
     __syncthreads();
     cluster.sync();
 
@@ -209,16 +204,24 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
             const int dest = tid / 48, c = tid % 48, g = c >> 4, u4 = (c & 15) * 4;
             const float4 v = *reinterpret_cast<const float4*>(&mine[g * U + u4]);
             const uint32_t o = dfull_u32 + (uint32_t)(buf * G + g * Hh + rank * U + u4) * 4u;
-            uint32_t ra, rb;
+            uint32_t ra;
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(o), "r"(dest));
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(bar_u32 + (uint32_t)buf * 8u), "r"(dest));
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                         ::"r"(ra), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
-                           "r"(__float_as_uint(v.w)), "r"(rb) : "memory");
+            uint32_t x[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = (x[i] == GB2_EMPTY) ? 0x7FC00000u : x[i];      // a NaN stays a NaN, never "not arrived"
+            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
         }
         if (s + 1 < n) fetch(dir ? s + 1 : n - 2 - s);       // next step's operands: in flight across the exchange
-        if (lane == 0) gb_wait(&ready[buf], (s >> 1) & 1);
-        __syncwarp();
+        if (pl < GB2_KS / 2) {              // wait for this slice's words (two per polling thread)
+            uint32_t a0, a1, spins = 0;
+            const uint32_t pa = poll_u32 + (uint32_t)(buf * G) * 4u;
+            while (true) {
+                asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(pa) : "memory");
+                if (a0 != GB2_EMPTY && a1 != GB2_EMPTY) break;
+                if (++spins > (1u << 24)) __trap();     // protocol bug: fail loudly instead of hanging the GPU
+            }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");           // the two warps of slice q
         {
             const float* dv = &dfull[buf][q * GB2_KS];
             float a4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -231,9 +234,9 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
             part[q][u] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
         }
         __syncthreads();
-        if (tid == 0) {                     // everyone of this CTA has read dfull[buf]: re-arm it for step s + 2
-            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&ready[buf]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(G * 4) : "memory");
+        if (pl < GB2_KS / 2) {              // everyone of this CTA has read dfull[buf]: mark it "not arrived" for step s + 2
+            const uint32_t pa = poll_u32 + (uint32_t)(buf * G) * 4u;
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pa), "r"(GB2_EMPTY), "r"(GB2_EMPTY) : "memory");
         }
         if (unit) {
             float a = dh_dir;

@@ -199,6 +199,52 @@ def test_row_kernels_backward():
     assert rel(dl[..., :M] * mask.to(DEV), lgg.grad[..., :M]) < 1e-5
 
 
+@pytest.mark.parametrize('dt,M,slot,lens', [(torch.bfloat16, 2432, 640, [640, 333]), (torch.float32, 300, 1500, [1500]), (torch.bfloat16, 75, 256, [9, 256])])
+def test_col_softmax_dtypes_and_vector_path(dt, M, slot, lens):
+    """Column softmax (softmax over the frames) forward / backward with bf16 tensors (the tcgen05 cross-attention path keeps its
+    probability tensors in bf16) and the 4-columns-per-thread vector path, against float64 torch."""
+    B = len(lens)
+    g = torch.Generator().manual_seed(M + slot)
+    lg = (torch.randn(B, slot, M, generator=g) * 2).to(dt)
+    gp = torch.randn(B, slot, M, generator=g).to(dt)
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    P = torch.zeros(B, slot, M, dtype=dt, device=DEV)
+    ops.col_softmax(lg.to(DEV), P, M, scale=0.5, len=ln)
+    dl = torch.zeros(B, slot, M, dtype=dt, device=DEV)
+    ops.col_softmax_bwd(P, gp.to(DEV), dl, M, scale=0.5, len=ln)
+    tol = 1e-5 if dt == torch.float32 else 6e-3
+    for b_, T in enumerate(lens):
+        x = lg[b_, :T].double().requires_grad_(True)
+        ref = torch.softmax(0.5 * x, 0)
+        assert rel(P[b_, :T], ref.detach()) < tol
+        (P[b_, :T].double().cpu() * gp[b_, :T].double()).sum()             # the kernel differentiates through ITS rounded P
+        (ref * gp[b_, :T].double()).sum().backward()
+        assert rel(dl[b_, :T], x.grad) < 4 * tol
+        assert float(P[b_, T:].float().abs().sum()) == 0.0 and float(dl[b_, T:].float().abs().sum()) == 0.0
+
+
+def test_col_lse_chunked_rows():
+    """factk_col_lse on a long rows tensor (512-row chunks across CTAs + fixed-order combine) equals torch.logsumexp, with the row mask."""
+    B, slot, M = 2, 5000, 300
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(B, slot, M, generator=g) * 3).to(DEV)
+    nrows = torch.tensor([5000, 1777], dtype=torch.int32, device=DEV)
+    out = torch.zeros(B, M, device=DEV)
+    ops.col_lse(x, M, nrows, out)
+    for b_ in range(B):
+        assert rel(out[b_], torch.logsumexp(x[b_, :int(nrows[b_])].double(), 0)) < 1e-6
+    lab = torch.randint(0, 7, (B, slot), generator=g).to(torch.int32).to(DEV)
+    cmap = torch.tensor([0, -1, 1, 2, -1, 3, 4], dtype=torch.int32, device=DEV)
+    out2 = torch.zeros(B, M, device=DEV)
+    ops.col_lse(x, M, nrows, out2, rmask0=lab, rmap=cmap)
+    for b_ in range(B):
+        keep = (cmap[lab[b_, :int(nrows[b_])].long()] >= 0)
+        assert rel(out2[b_], torch.logsumexp(x[b_, :int(nrows[b_])][keep].double(), 0)) < 1e-6
+    again = torch.zeros(B, M, device=DEV)
+    ops.col_lse(x, M, nrows, again, rmask0=lab, rmap=cmap)
+    assert torch.equal(out2, again)
+
+
 @pytest.mark.parametrize('Hh,lens', [(32, [40, 7, 1]), (256, [300, 120])])
 def test_gru_backward(Hh, lens):
     """BPTT kernel + the generic kernels around it against autograd through torch's nn.GRU."""
