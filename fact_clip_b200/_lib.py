@@ -53,6 +53,7 @@ _SIGS = {
     'factk_token_layer_supported': (i32, [i32, i32, i32, i32]),
     'factk_token_layer': (i32, [C.POINTER(TokenLayer), vp]),
     'factk_token_layer_debug': (i32, [vp]),
+    'factk_gru_bwd_debug': (i32, [vp]),
     'factk_gemm_tc': (i32, [C.POINTER(Gemm), vp]),
     'factk_gemm_tc_supported': (i32, [C.POINTER(Gemm)]),
     'factk_gemm_pair_supported': (i32, [i32, i32]),

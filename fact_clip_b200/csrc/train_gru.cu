@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(GB_THREADS) gru_bwd_kernel(const float* __rest
 // barrier, read the slice, and re-mark their words after the CTA barrier that ends the step.  (st.async completing a
 // transaction mbarrier cost ~1000 cycles per step here, the flagged stores cost one remote-store latency: 1.9 -> ~1 us.)
 constexpr int GB2_THREADS = 512, GB2_Q = 8, GB2_KS = 96;      // 768 = 8 x 96
+__device__ long long* gb2_dbg = nullptr;     // factk_gru_bwd_debug: clock64 of (cluster 0, rank 0, thread 0) at six points of the first 64 steps
+#define GB2_MARK(i) do { if (dbgp != nullptr && s < 64) dbgp[s * 8 + (i)] = clock64(); } while (0)
 constexpr uint32_t GB2_EMPTY = 0xFFFFFFFFu;                     // "not arrived yet" marker of an exchanged word
 
 __device__ __forceinline__ void gb_wait(uint64_t* bar, uint32_t parity) {
@@ -148,6 +150,7 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
     __shared__ __align__(16) float mine[3 * U];
     __shared__ float part[GB2_Q][U];
     __shared__ float carry[U];
+    long long* const dbgp = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) ? gb2_dbg : nullptr;
     const float* W = dir ? w_hh_b : w_hh_f;
     const int tid = threadIdx.x, lane = tid & 31;
     const int u = tid & (U - 1), q = tid >> 6;
@@ -186,6 +189,7 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
         const int t = dir ? s : n - 1 - s;
         const int buf = s & 1;
         float dh_dir = 0.f;
+        GB2_MARK(0);
         if (unit) {
             const float r = sigmoidf_(c_gi[0] + c_gh[0]), z = sigmoidf_(c_gi[1] + c_gh[1]);
             const float nn = tanhf(c_gi[2] + r * c_gh[2]);
@@ -200,6 +204,7 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
             mine[u] = drp; mine[U + u] = dzp; mine[2 * U + u] = dnp * r;
         }
         __syncthreads();
+        GB2_MARK(1);
         if (tid < 192) {                    // 48 x 16 bytes to each of the four CTAs (this one included)
             const int dest = tid / 48, c = tid % 48, g = c >> 4, u4 = (c & 15) * 4;
             const float4 v = *reinterpret_cast<const float4*>(&mine[g * U + u4]);
@@ -211,7 +216,9 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
             for (int i = 0; i < 4; ++i) x[i] = (x[i] == GB2_EMPTY) ? 0x7FC00000u : x[i];      // a NaN stays a NaN, never "not arrived"
             asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
         }
+        GB2_MARK(2);
         if (s + 1 < n) fetch(dir ? s + 1 : n - 2 - s);       // next step's operands: in flight across the exchange
+        GB2_MARK(3);
         if (pl < GB2_KS / 2) {              // wait for this slice's words (two per polling thread)
             uint32_t a0, a1, spins = 0;
             const uint32_t pa = poll_u32 + (uint32_t)(buf * G) * 4u;
@@ -222,6 +229,7 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
             }
         }
         asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");           // the two warps of slice q
+        GB2_MARK(4);
         {
             const float* dv = &dfull[buf][q * GB2_KS];
             float a4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -233,7 +241,9 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
             }
             part[q][u] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
         }
+        GB2_MARK(5);
         __syncthreads();
+        GB2_MARK(6);
         if (pl < GB2_KS / 2) {              // everyone of this CTA has read dfull[buf]: mark it "not arrived" for step s + 2
             const uint32_t pa = poll_u32 + (uint32_t)(buf * G) * 4u;
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pa), "r"(GB2_EMPTY), "r"(GB2_EMPTY) : "memory");
@@ -251,6 +261,13 @@ gru_bwd256_kernel(const float* __restrict__ gi, const float* __restrict__ gh, co
 }  // namespace factk
 
 using namespace factk;
+
+/* Debug aid: clock64 at seven points of the first 64 steps of the Hh = 256 kernel (cluster 0, rank 0) into buf[64][8] (int64, device); NULL: off. */
+extern "C" int factk_gru_bwd_debug(void* buf) {
+    long long* p = reinterpret_cast<long long*>(buf);
+    cudaMemcpyToSymbol(factk::gb2_dbg, &p, sizeof(p));
+    return factk::check_launch("factk_gru_bwd_debug");
+}
 
 /* BPTT of factk_gru_bidir (one layer).  gi, gh fp32 [B][slot][6*Hh] (gh = h_{t-1} W_hh^T + b_hh for every step, both directions);
  * hout [B][slot][ldh] = the layer's output BEFORE any ReLU (cat[fwd, bwd]); dout its gradient; -> dgi, dgh fp32 [B][slot][6*Hh]

@@ -506,6 +506,8 @@ int factk_segment_expand(const void* seg, int s_dtype, int lds, const int32_t* s
 int factk_gru_bwd(const float* gi, const float* gh, const void* hout, int h_dtype, int ldh, const void* dout, int do_dtype,
                   int lddo, const float* w_hh_f, const float* w_hh_b, int Hh, float* dgi, float* dgh, int B, int slot,
                   const int32_t* nseg, void* stream);
+/* Debug aid: clock64 at seven points of the first 64 steps of the Hh = 256 BPTT kernel into buf[64][8] (int64, device); NULL: off. */
+int factk_gru_bwd_debug(void* buf);
 
 /* Gradients of the training loss w.r.t. the logit tensors it reads (csrc/train_loss.cu; reference: autograd through
  * models/loss.py:8-19,196-341 and the compute_loss methods of models/blocks.py:313-320,369-382,487-497,677-786).  Each call
