@@ -452,6 +452,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-split', type=int, default=4, help='sub-batches per step on the end-to-end (pipelined) path')
     ap.add_argument('--no-graph', action='store_true', help='eager kernel launches instead of one CUDA graph per batch')
+    ap.add_argument('--lanes', type=int, default=2, help='resident measurement: steps alternate between this many streams / activation arenas')
     ap.add_argument('--no-prefetch', action='store_true', help='(--train) copy each step\'s video to the device at the start of the step instead of during the previous step')
     ap.add_argument('--timeline', action='store_true', help='(--train) torch.profiler device timeline of one step: busy / idle / top kernels, to stderr')
     ap.add_argument('--profile', action='store_true', help='print a CUDA-event breakdown per kernel family to stderr')
@@ -496,8 +497,26 @@ def main():
     seq_host = [host[b] for b in range(B)]
     labels = [torch.zeros(T, dtype=torch.long) for _ in range(B)]
 
+    lanes = [torch.cuda.Stream() for _ in range(args.lanes)] if args.lanes > 1 else None
+    lane_no = [0]
+
     def step_resident():
-        return eng.run_packed_graphed(x, ln, lengths)
+        if lanes is None or ops.TIMER is not None:
+            return eng.run_packed_graphed(x, ln, lengths)
+        # `--lanes N`: consecutive steps (independent batches) alternate between N streams, each with its own activation arena and
+        # CUDA graph, so one step's latency-bound stretches (the GRU chain) overlap the next step's tensor-core work
+        k = lane_no[0] = (lane_no[0] + 1) % len(lanes)
+        eng.lane = k
+        lanes[k].wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(lanes[k]):
+            out = eng.run_packed_graphed(x, ln, lengths)
+        eng.lane = 0
+        return out
+
+    def drain_lanes():
+        if lanes is not None:
+            for s_ in lanes:
+                torch.cuda.current_stream().wait_stream(s_)
 
     pending = []
     e2e_split = [args.e2e_split]
@@ -545,7 +564,8 @@ def main():
     sampler = ClockSampler(local)
     ops.COUNTERS['launches'] = 0
     sampler.start()
-    ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    ms = timed(step_resident, args.steps, max(args.warmup, 3), drain=drain_lanes)
+    ms_single = timed(lambda: eng.run_packed_graphed(x, ln, lengths), args.steps, max(args.warmup, 3)) if lanes is not None else ms
     clocks = sampler.summary()
     launches = eng.last_launches if eng.use_graph else ops.COUNTERS['launches'] // (args.steps + max(args.warmup, 3))
     # kernel-level pass: the same steps with eager launches and CUDA events around every launch of the dominant kernel
@@ -606,9 +626,14 @@ def main():
                                f'{B} videos/GPU/step, random-init weights, segment-structured synthetic features',
                    'videos_per_gpu': B, 'frames_per_step': frames_step,
                    'launch': 'cuda-graph' if eng.use_graph else 'eager',
+                   'resident_lanes': args.lanes,
+                   'resident_lanes_note': 'consecutive steps (independent batches) alternate between this many streams, each with its own '
+                                          'activation arena and CUDA graph: one step\'s latency-bound GRU chain overlaps the next step\'s '
+                                          'tensor-core kernels; single_stream below is the same loop on one stream',
                    'l2_policy': f'inputs larger than L2 ({B * T * IN_DIM * 4 / 2**20:.0f} MiB of fp32 features per step)',
                    'segments_per_U_block_rank0': [[min(s), max(s)] for s in nseg], 'numa_rank0': numa},
         'clocks': clocks, 'gpu_launches': launches,
+        'single_stream': {'value': frames_step * args.steps / (ms_single * 1e-3), 'unit': UNIT, 'ms_per_step': ms_single / args.steps},
         'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': B * T * IN_DIM * 4 * world,
                 'd2h_bytes_per_step': B * T * 8 * world, 'ms_per_step': ms_e2e / args.steps,
                 'features': 'fp32 on the host (the reference format)', 'sub_batches_per_step': args.e2e_split,

@@ -45,6 +45,9 @@ class FactEngine:
         # Measured: 1.46 instead of 1.41 ms per step for the 73 token GEMMs -- fewer, fuller tiles stream more per CTA and the
         # launches are one wave either way -- so it stays off.
         self.flat_tokens = os.environ.get('FACTK_FLAT_TOKENS', '0') == '1'
+        # activation arenas (and the graphs captured over them) are per (batch shape, lane): two batches in flight on two streams
+        # -- one filling the SMs that the other's latency-bound GRU chain leaves idle -- use lanes 0 and 1
+        self.lane = 0
         # one launch per token-side decoder (half-)layer (csrc/token_layer.cu) instead of 8-11 dependent ones; bf16 mode only
         self.use_fused_tokens = os.environ.get('FACTK_FUSED_TOKENS', '1') != '0'
         self.use_graph = True        # replay the whole batched forward as ONE CUDA graph (no per-kernel host launch cost)
@@ -860,7 +863,7 @@ class FactEngine:
         if not self.use_graph or ops.TIMER is not None:
             return self.run_packed(x, ln, lengths, pred_out=pred_out)
         self._refresh_weights()
-        self._set_arena((x.shape[0], x.shape[1], self.ntok))
+        self._set_arena((x.shape[0], x.shape[1], self.ntok, self.lane))
         # the captured launches depend on B, slot and the buffer pointers only: the lengths reach the kernels through the
         # device tensor ``ln``, so batches of the same shape with other lengths replay the same graph
         key = (x.data_ptr(), tuple(x.shape), x.dtype, ln.data_ptr(), None if pred_out is None else pred_out.data_ptr())
@@ -899,7 +902,7 @@ class FactEngine:
     def run_packed(self, x, ln, lengths, forced_preds=None, keep=False, pred_out=None):
         self._refresh_weights()
         hp = self.hp
-        self._set_arena((x.shape[0], x.shape[1], self.ntok))
+        self._set_arena((x.shape[0], x.shape[1], self.ntok, self.lane))
         self.B, self.slot, self.len, self.keep = x.shape[0], x.shape[1], ln, keep
         if self._len_sig != tuple(lengths):
             for t in self._zbufs.values():
