@@ -452,6 +452,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-split', type=int, default=4, help='sub-batches per step on the end-to-end (pipelined) path')
     ap.add_argument('--no-graph', action='store_true', help='eager kernel launches instead of one CUDA graph per batch')
+    ap.add_argument('--resident-only', action='store_true', help='stop after the resident loop (profiling aid)')
     ap.add_argument('--lanes', type=int, default=2, help='resident measurement: steps alternate between this many streams / activation arenas')
     ap.add_argument('--no-prefetch', action='store_true', help='(--train) copy each step\'s video to the device at the start of the step instead of during the previous step')
     ap.add_argument('--timeline', action='store_true', help='(--train) torch.profiler device timeline of one step: busy / idle / top kernels, to stderr')
@@ -566,6 +567,11 @@ def main():
     sampler.start()
     ms = timed(step_resident, args.steps, max(args.warmup, 3), drain=drain_lanes)
     ms_single = timed(lambda: eng.run_packed_graphed(x, ln, lengths), args.steps, max(args.warmup, 3)) if lanes is not None else ms
+    if args.resident_only:            # profiling aid (ncu launch lists): nothing but the resident loop
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': B * T * world * args.steps / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / args.steps,
+                              'gpu_launches': eng.last_launches if eng.use_graph else None, 'note': '--resident-only'}))
+        return
     clocks = sampler.summary()
     launches = eng.last_launches if eng.use_graph else ops.COUNTERS['launches'] // (args.steps + max(args.warmup, 3))
     # kernel-level pass: the same steps with eager launches and CUDA events around every launch of the dominant kernel
@@ -669,12 +675,6 @@ def main():
     res['hbm_kernels'] = {'in_proj': {'bytes_per_frame': 4 * IN_DIM + 2 * F, 'frac_of_hbm': hbm_of('in_proj', 4 * IN_DIM + 2 * F)},
                           'conv_out': {'bytes_per_frame': 2 * F + 2 * 512, 'frac_of_hbm': hbm_of('conv_out', 2 * F + 2 * 512)},
                           'hbm_peak_gbs': pk['hbm'], 'ncu': 'profiles/r2_frame_gemms_ncu.md (dram bytes per launch)'}
-    if world == 1 and args.calibrate_steps > 0:
-        try:
-            res['calibrated_regime'] = calibrated_regime(net, cfg, dev, x, ln, lengths, B, T, args)
-        except Exception as e:          # the second regime never takes the headline line down
-            import traceback
-            res['calibrated_regime'] = {'error': f'{type(e).__name__}: {str(e)[:200]}', 'where': traceback.format_exc()[-1500:]}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)       # the CPU baseline may use every host core
@@ -691,6 +691,14 @@ def main():
                                    'sample': f'{n_cpu} videos x T={T} of the same workload, '
                                              + ('stock reference FACT_CLIP from baseline/_ref' if kind == 'reference' else 'oracle port')
                                              + f' (torch CPU fp32, eval, no_grad), {dt:.1f} s'}
+    # the calibrated regime trains the net in place: it runs LAST (the parity check above compares against the reference's random init)
+    if world == 1 and args.calibrate_steps > 0:
+        try:
+            res['calibrated_regime'] = calibrated_regime(net, cfg, dev, x, ln, lengths, B, T, args)
+        except Exception as e:          # the second regime never takes the headline line down
+            import traceback
+            res['calibrated_regime'] = {'error': f'{type(e).__name__}: {str(e)[:200]}', 'where': traceback.format_exc()[-1500:]}
+    if rank == 0:
         print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()

@@ -7,7 +7,7 @@
 // computes half of the output columns of every GEMM (its half of the heads in the attention), writing them into its own and,
 // through distributed shared memory, its peer's copy; a cluster barrier separates the stages.  The weights stream from L2
 // once per CTA pair, pre-packed on the host side in mma.m16n8k16 B-fragment order (one coalesced 16-byte load per lane and
-// k-step, prefetched three k-steps ahead; no shared-memory staging of weights).  bf16 operands, fp32 accumulate, fp32
+// k-step, prefetched seven k-steps ahead; no shared-memory staging of weights).  bf16 operands, fp32 accumulate, fp32
 // residual, LayerNorm and softmax.  The token side is latency-bound (75 rows per video, measured: the legacy tensor pipe
 // retires one m16n8k16 per ~4.4 cycles per SM, which is what bounds a stage): the point of this kernel is the launch count,
 // the L2 round trips between dependent launches, and spreading 64 videos over 128 SMs.
@@ -69,9 +69,9 @@ __device__ __forceinline__ uint32_t tl_pack(float lo, float hi) {
 // position table, residual) -- all of a task's addends are fetched before its k loop, so their (global memory) latencies hide
 // under the MMAs instead of serialising behind possibly-aliasing stores -- and put(row, col, v0, v1) stores.
 // K % 64 == 0, col0 % 16 == 0, ncols % 16 == 0.
-template <typename Add, typename Put>
-__device__ __forceinline__ void tl_gemm(const __nv_bfloat16* Ab, int lda, int MT, int K, const uint4* __restrict__ Wp, int nsec, int sec_stride,
-                                        int col0, int ncols, Add add, Put put) {
+template <int RING, typename Add, typename Put>
+__device__ __forceinline__ void tl_gemm_r(const __nv_bfloat16* Ab, int lda, int MT, int K, const uint4* __restrict__ Wp, int nsec, int sec_stride,
+                                          int col0, int ncols, Add add, Put put) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KS = K >> 4, tps = ncols >> 4, ntask = nsec * tps;
     const __nv_bfloat16* arow = Ab + (size_t)(lane & 15) * lda + (lane >> 4) * 8;
@@ -83,9 +83,9 @@ __device__ __forceinline__ void tl_gemm(const __nv_bfloat16* Ab, int lda, int MT
 #pragma unroll
             for (int t = 0; t < 2; ++t) acc[mt][t][0] = acc[mt][t][1] = acc[mt][t][2] = acc[mt][t][3] = 0.f;
         const uint4* wp = Wp + ((size_t)(cbase >> 5) * KS * 32 + lane) * 2 + ((cbase >> 4) & 1);          // + 64 uint4 per k-step
-        uint4 q[4];
+        uint4 q[RING];               // weight fragments RING - 1 k-steps ahead (L2 latency ~ 800 cycles, a k-step ~ 100-200)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) q[s] = __ldg(wp + s * 64);
+        for (int s = 0; s < RING - 1; ++s) q[s] = __ldg(wp + s * 64);
         // the epilogue's addends (bias, tables, residual) are fetched now: their latency hides under the k loop
         const int g = lane >> 2, c2 = (lane & 3) * 2;
         float2 ad[TL_MAXMT][2][2];
@@ -99,11 +99,11 @@ __device__ __forceinline__ void tl_gemm(const __nv_bfloat16* Ab, int lda, int MT
                 }
             }
         }
-        for (int ks0 = 0; ks0 < KS; ks0 += 4) {
+        for (int ks0 = 0; ks0 < KS; ks0 += RING) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
+            for (int s = 0; s < RING; ++s) {
                 const int ks = ks0 + s;
-                if (ks + 3 < KS) q[(s + 3) & 3] = __ldg(wp + (ks + 3) * 64);
+                if (ks + RING - 1 < KS) q[(s + RING - 1) & (RING - 1)] = __ldg(wp + (ks + RING - 1) * 64);
                 const uint32_t bf[4] = {q[s].x, q[s].y, q[s].z, q[s].w};
                 uint32_t a[TL_MAXMT][4];          // every A fragment of the k-step first: the ldmatrix latencies overlap
 #pragma unroll
@@ -129,6 +129,13 @@ __device__ __forceinline__ void tl_gemm(const __nv_bfloat16* Ab, int lda, int MT
             }
         }
     }
+}
+
+template <typename Add, typename Put>
+__device__ __forceinline__ void tl_gemm(const __nv_bfloat16* Ab, int lda, int MT, int K, const uint4* __restrict__ Wp, int nsec, int sec_stride,
+                                        int col0, int ncols, Add add, Put put) {
+    if ((K & 127) == 0) tl_gemm_r<8>(Ab, lda, MT, K, Wp, nsec, sec_stride, col0, ncols, add, put);      // K / 16 % 8 == 0
+    else tl_gemm_r<4>(Ab, lda, MT, K, Wp, nsec, sec_stride, col0, ncols, add, put);
 }
 
 // Per-head softmax(q k^T / sqrt(dh)) v for the heads h0 .. h0 + nh - 1, q | k | v the column bands of the bf16 rows in shared
