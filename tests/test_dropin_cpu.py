@@ -144,3 +144,16 @@ def test_input_validation_messages():
     assert net([], []) == []                                   # no videos: the reference's loop does not run either
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         net([torch.zeros(5, 24)], None)
+
+
+def test_token_weight_packing_layout():
+    """ops.pack_token_weight (pure torch, no launch): the documented mma.m16n8k16 B-fragment order of include/factk.h --
+    W[N][K] as [N/32][K/16][lane = 4 (n % 8) + (k % 8) / 2][(n / 8) % 4][(k / 8) % 2][k % 2] -- checked element by element."""
+    from fact_clip_b200 import ops
+    N, K = 64, 32
+    W = torch.arange(N * K, dtype=torch.float32).view(N, K) % 251          # exactly representable in bf16
+    p = ops.pack_token_weight(W).view(N // 32, K // 16, 32, 4, 2, 2).float()
+    for n in range(N):
+        for k in range(K):
+            lane = 4 * (n % 8) + (k % 8) // 2
+            assert p[n // 32, k // 16, lane, (n // 8) % 4, (k // 8) % 2, k % 2] == W[n, k], (n, k)
