@@ -74,6 +74,10 @@ _SIGS = {
     'factk_a2f_fused_supported': (i32, [i32, i32, i32, i32]),
     'factk_a2f_fused': (i32, [vp, i32, vp, i32, C.c_longlong, vp, C.c_longlong, vp, i32, vp, i32, C.c_longlong, vp, vp, i32, vp, vp, i32, i32, i32,
                               vp, i32, i32, i32, vp]),
+    'factk_f2a_fused_supported': (i32, [i32, i32, i32]),
+    'factk_f2a_fused_ws_floats': (C.c_size_t, [i32, i32, i32, i32]),
+    'factk_f2a_debug': (i32, [vp]),
+    'factk_f2a_fused': (i32, [vp, i32, vp, i32, C.c_longlong, vp, i32, i32, i32, vp, i32, i32, vp, vp]),
     'factk_tdu_segment': (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     'factk_segment_mean_ws_floats': (C.c_size_t, [i32, i32, i32]),
     'factk_segment_mean': (i32, [vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp]),

@@ -514,25 +514,37 @@ class FactEngine:
         qt = self.buf('x2y_qt16' if tc else 'x2y_qt', (B, M, H), torch.bfloat16 if tc else torch.float32)   # alpha * Wk^T yq
         cb = self.buf('x2y_c', (B, M, 1))                                   # alpha * yq . bk
         fold = self.mode == 'bf16' and self.use_tc
+        fused = (tc and fold and not want_attn and self.frame_pos is None and self.use_fused_x2y and rows.is_contiguous()
+                 and ops.f2a_fused_ok(M, H, slot))
         if fold:
             # yq = Y_Q(action + pos) only feeds linear maps: fold Y_Q into them (one GEMM instead of two, no yq buffer)
             Wf, bf_, u, c0 = self._x2y_fold(pfx, 'Y_Q', 'X_K', alpha)
             self.lin(action, Wf, H, qt, pos=qpos, bias=bf_)
-            self.lin(action, u, 1, cb, pos=qpos, bias=c0)
+            if not fused:       # (the per-token logit bias is constant along the rows: the fused softmax never needs it)
+                self.lin(action, u, 1, cb, pos=qpos, bias=c0)
         else:
             yq = self.buf('x2y_tokH', (B, M, H))
             self.lin(action, self.p(pfx + 'Y_Q.weight'), H, yq, pos=qpos, bias=self.p(pfx + 'Y_Q.bias'))
             self.lin(yq, self.tr(pfx + 'X_K.weight'), H, qt, alpha=alpha)
             self.lin(yq, self.p(pfx + 'X_K.bias')[None, :], 1, cb, alpha=alpha)
-        logit = self.buf('f2a_logit_' + tag, (B, slot, Mp))
-        if tc:
-            ops.gemm([S(self.with_pos(rows, rlen, pos_idx, 'x2y_rows_pos'), qt)], M, logit, len=rlen, bias=cb[:, :, 0], tc=True, tag='x2y_rows')
-        else:
-            ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tag='x2y_rows')
-        attn = self.buf('f2a_attn_' + tag, (B, slot, Mp)) if want_attn else None
         xbar = self.buf('x2y_xbar', (B, M, H))
-        ws = self.buf('col_ws', (ops.col_softmax_ws(B, slot, M, H),))
-        ops.col_softmax_apply(logit, rows, xbar, M, ws, attn=attn, len=rlen, E=H)
+        if fused:
+            # ONE tcgen05 kernel (f2a_fused.cu): S = qt rows^T in TMEM, softmax over the rows on TMEM lanes, xbar += P rows with the
+            # same TMA tile as the second operand -- the rows are read once and the fp32 logits never exist (their per-token
+            # bias cb is constant along the rows and cancels).  The logits / attention only leave the SM on the unfused path
+            # below, which serves the loss and keep_attn (self.keep).
+            logit = attn = None
+            ws = self.buf('f2a_ws', (ops.f2a_fused_ws(B, slot, M, H),))
+            ops.f2a_fused(rows, qt, xbar, M, ws, len=rlen)
+        else:
+            logit = self.buf('f2a_logit_' + tag, (B, slot, Mp))
+            if tc:
+                ops.gemm([S(self.with_pos(rows, rlen, pos_idx, 'x2y_rows_pos'), qt)], M, logit, len=rlen, bias=cb[:, :, 0], tc=True, tag='x2y_rows')
+            else:
+                ops.gemm([S(rows, qt, pos=self.frame_pos, pos_idx=pos_idx)], M, logit, len=rlen, bias=cb[:, :, 0], tag='x2y_rows')
+            attn = self.buf('f2a_attn_' + tag, (B, slot, Mp)) if want_attn else None
+            ws = self.buf('col_ws', (ops.col_softmax_ws(B, slot, M, H),))
+            ops.col_softmax_apply(logit, rows, xbar, M, ws, attn=attn, len=rlen, E=H)
         W = self.p(pfx + 'Y_W.weight')
         out = self.buf('tok_x', (B, M, A))
         if fold:     # Y_W(cat[action, X_V(xbar)]) = action W1^T + xbar (W2 Wv)^T + (b + W2 bv)

@@ -226,6 +226,25 @@ def a2f_fused(rows, kt, cb, wy, vt, bias, out, M, logit=None, attn=None, len=Non
           L.ptr(logit), L.ptr(attn), _row_ld(ref) if ref is not None else 0, B, slot, L.ptr(len), M, H, F, L.stream())
 
 
+def f2a_fused_ok(M, H, slot):
+    return bool(L.load().factk_f2a_fused_supported(int(M), int(H), int(slot)))
+
+
+def f2a_fused_ws(B, slot, M, H):
+    return int(L.load().factk_f2a_fused_ws_floats(B, slot, M, H))
+
+
+def f2a_fused(rows, qt, out, M, ws, len=None):
+    """Fused X2Y_map (f2a direction): rows [B, slot, H] bf16, qt [B, M, H] bf16 -> out [B, M, H] fp32 (softmax over the rows of each
+    video, weighted row sum); one tcgen05 launch + the split combine."""
+    B, slot, H = rows.shape
+    assert rows.dtype == qt.dtype == torch.bfloat16 and out.dtype == ws.dtype == torch.float32
+    assert rows.stride(0) == slot * _row_ld(rows)
+    COUNTERS['launches'] += 2
+    _call('factk_f2a_fused', 'f2a_fused', rows.data_ptr(), _row_ld(rows), qt.data_ptr(), _row_ld(qt), qt.stride(0), out.data_ptr(), _row_ld(out),
+          B, slot, L.ptr(len), M, H, ws.data_ptr(), L.stream())
+
+
 def token_layer_ok(M, A, nhead, ff):
     return bool(L.load().factk_token_layer_supported(M, A, nhead, ff))
 

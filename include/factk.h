@@ -185,6 +185,18 @@ int factk_a2f_fused(const void* X, int ldx, const void* Kt, int ldkt, long long 
                     const void* Wy, int ldwy, const void* Vt, int ldvt, long long vt_bstride, const float* bias, void* out, int ldo,
                     float* logit, float* attn, int ldl, int B, int slot, const int32_t* len, int M, int H, int F, void* stream);
 
+/* X2Y_map, f2a direction (models/basic.py:349-389 with X = frame / segment rows, Y = tokens; blocks.py:346,458) as ONE
+ * tcgen05 / TMEM kernel + a fixed-order combine: out[b][m][:] = sum_t softmax_t(qt[b][m] . X[b][t]) X[b][t][:], t < len[b].
+ * The rows are read once; the [B][slot][M] logits never reach HBM (the per-token logit bias is constant along t and cancels).
+ * rows X bf16 [B][slot][ldx] (H channels), qt bf16 [B][M][ldq] (the token-side fold alpha Wk^T Y_Q(tokens)), out fp32 [B][M][ldo],
+ * ws >= factk_f2a_fused_ws_floats(B, slot, M, H) floats.  H == 256, M <= 128, slot % 64 == 0.  Rows in [len, slot) may hold anything. */
+int factk_f2a_fused_supported(int M, int H, int slot);
+size_t factk_f2a_fused_ws_floats(int B, int slot, int M, int H);
+int factk_f2a_fused(const void* X, int ldx, const void* Qt, int ldq, long long qt_bstride, float* out, int ldo, int B, int slot,
+                    const int32_t* len, int M, int H, float* ws, void* stream);
+/* development aid: clock64 timeline of one CTA of the next factk_f2a_fused launches (tools/bench_f2a.py); NULL = off */
+int factk_f2a_debug(long long* dbg);
+
 /* Run-length segmentation on device (utils/utils.py:25-48, basic.py:597-607, blocks.py:454):
  * pred int32 [B][slot] -> seg_label[B][slot], seg_start[B][slot], seg_len[B][slot],
  * seg_center[B][slot] (= (start+end)/2 floor), nseg[B]. */

@@ -464,6 +464,44 @@ def test_a2f_fused(M, slot, lens, with_outputs):
         assert float(out[b, T:].float().abs().sum()) == 0.0          # rows past the end are never written
 
 
+@pytest.mark.parametrize('M,slot,lens,qscale,ramp', [(75, 512, [512, 300], 0.1, 0.0), (128, 1024, [1024, 513, 1], 0.1, 0.0),
+                                                     (12, 384, [64, 384, 130], 0.3, 0.0), (75, 4096, [4096, 4000, 577], 0.05, 0.0),
+                                                     (75, 2048, [2048, 1500], 0.1, 40.0), (33, 640, [640, 65], 0.1, -25.0)])
+def test_f2a_fused(M, slot, lens, qscale, ramp):
+    """Fused X2Y_map, f2a direction (f2a_fused.cu): S = qt rows^T -> softmax over the rows (online, split over 512-row CTAs) ->
+    weighted row sum in one tcgen05 kernel + the split combine, against fp32 torch on the same bf16 operands.  ``ramp`` adds a
+    trend along the rows so that the running maximum keeps growing (positive: the accumulator rescale path) or the first tile
+    dominates (negative); rows past len[b] hold NaN (they must not reach the accumulator)."""
+    B, H = len(lens), 256
+    bf = torch.bfloat16
+    assert ops.f2a_fused_ok(M, H, slot)
+    rows = rnd(B, slot, H, seed=41)
+    qt = rnd(B, M, H, seed=42) * qscale
+    if ramp:
+        # one channel carries t / slot; the queries read it with weight ``ramp``: logit += ramp * t / slot
+        rows[:, :, 0] = torch.arange(slot, dtype=torch.float32)[None, :] / slot
+        qt[:, :, 0] = ramp
+    rows, qt = rows.to(bf), qt.to(bf)
+    rows_dev = rows.clone()
+    for b, T in enumerate(lens):
+        rows_dev[b, T:] = float('nan')
+    out = torch.full((B, M, H), float('nan'), device=DEV)
+    ws = torch.empty(ops.f2a_fused_ws(B, slot, M, H), device=DEV)
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    ops.f2a_fused(rows_dev.to(DEV), qt.to(DEV), out, M, ws, len=ln)
+    torch.cuda.synchronize()
+    for b, T in enumerate(lens):
+        x = rows[b, :T].double()
+        p = torch.softmax(x @ qt[b].double().t(), 0)                # [T, M], softmax over the rows
+        ref = (p.t() @ x).float()
+        err = rel_l2(out[b], ref)
+        assert err < 6e-3, (b, T, err)
+    # bit-reproducible and batch invariant: video 0 alone gives the same bits
+    out1 = torch.empty(1, M, H, device=DEV)
+    ops.f2a_fused(rows_dev[:1].contiguous().to(DEV), qt[:1].contiguous().to(DEV), out1, M, ws, len=ln[:1].contiguous())
+    assert torch.equal(out1[0], out[0])
+
+
 def _ref_token_layer(x, nhead, Wo, bo, ln1, Win=None, bin_=None, pos=None, o_in=None, Wq=None, bq=None, ffn=None):
     """fp32 torch restatement of SALayer / the two halves of SCALayer (models/basic.py:429-452, 494-523), eval mode."""
     import torch.nn.functional as Fn
