@@ -567,7 +567,20 @@ def main():
     sampler.start()
     ms = timed(step_resident, args.steps, max(args.warmup, 3), drain=drain_lanes)
     ms_single = timed(lambda: eng.run_packed_graphed(x, ln, lengths), args.steps, max(args.warmup, 3)) if lanes is not None else ms
+    def profile_pass():
+        ops.TIMER = ops.KernelTimer(None)
+        for _ in range(3):
+            step_resident()
+        prof = ops.TIMER.collect(skip_steps=1, steps=2)
+        ops.TIMER = None
+        tot = sum(v['ms'] for v in prof.values())
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+            sys.stderr.write(f"  {k:28s} n/step={v['n'] // 2:4d} {v['ms'] / 2:8.3f} ms/step {100 * v['ms'] / tot:5.1f}%\n")
+        sys.stderr.write(f"  total {tot / 2:.3f} ms/step (sum of kernel times)\n")
+
     if args.resident_only:            # profiling aid (ncu launch lists): nothing but the resident loop
+        if args.profile:
+            profile_pass()
         if rank == 0:
             print(json.dumps({'metric': METRIC, 'value': B * T * world * args.steps / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / args.steps,
                               'gpu_launches': eng.last_launches if eng.use_graph else None, 'note': '--resident-only'}))
@@ -580,15 +593,7 @@ def main():
     ktimes = ops.TIMER.collect(skip_steps=1, steps=args.steps)
     ops.TIMER = None
     if args.profile:
-        ops.TIMER = ops.KernelTimer(None)
-        for _ in range(3):
-            step_resident()
-        prof = ops.TIMER.collect(skip_steps=1, steps=2)
-        ops.TIMER = None
-        tot = sum(v['ms'] for v in prof.values())
-        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
-            sys.stderr.write(f"  {k:28s} n/step={v['n'] // 2:4d} {v['ms'] / 2:8.3f} ms/step {100 * v['ms'] / tot:5.1f}%\n")
-        sys.stderr.write(f"  total {tot / 2:.3f} ms/step (sum of kernel times)\n")
+        profile_pass()
     # the ceiling of the host-fed number: all ranks copy their pinned feature buffer to the device at the same time, nothing else
     xin = torch.empty_like(x)
     def step_h2d():

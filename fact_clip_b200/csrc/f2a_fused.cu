@@ -12,24 +12,28 @@
 //                                               tile of the rows is the K-major B operand of S and the MN-major B operand of O
 //
 // The rows are read ONCE (512 B per row); the fp32 logits [B, slot, M] that the unfused chain (tcgen05 logit GEMM -> column
-// statistics -> mma.sync apply) wrote and read twice never exist.  One CTA = one 512-row split of one video: warp 0 = TMA
-// producer (3-stage ring of [64 rows x 256 channels]), warp 1 issues S = Q X^T, warp 2 issues O += P X, warps 4-7 = softmax /
-// epilogue (TMEM lane quarter = warp % 4).  Every split writes (max, sum) and the unnormalised O per token;
+// statistics -> mma.sync apply) wrote and read twice never exist.  One CTA = one 2048-row split of one video: warp 0 = TMA
+// producer (4-stage ring of [64 rows x 256 channels]), warp 1 issues S = Q X^T, warp 2 issues O += P X, warps 4-11 = softmax /
+// epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the 64 columns of a tile).  Every split writes (max, sum) and the unnormalised O per token;
 // f2a_combine_kernel merges the splits in a fixed order (bit-reproducible, batch invariant).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace factk {
 
-constexpr int FF_SPLIT = 512;                        // rows per CTA (== SPLIT_ROWS of attn.cu: the workspace layout is shared)
+constexpr int FF_SPLIT = 2048;                       // rows per CTA: 64 videos x 4096 rows = 128 CTAs, one round on 148 SMs.  A constant
+                                                     // (not a function of B), so results do not depend on the batch a video is in
 constexpr int FF_TILE = 64;                          // rows per pipeline stage
 constexpr int FF_H = 256;
 constexpr int FF_QBYTES = 4 * 128 * 128;             // 4 boxes [128 tokens x 64 channels] bf16
 constexpr int FF_XBYTES = 4 * FF_TILE * 128;         // 4 boxes [64 rows x 64 channels] bf16
-constexpr int FF_NSTAGE = 3;
+constexpr int FF_NSTAGE = 4;                         // with 3 stages the S issuer waited ~1100 cycles for rows every third tile
 constexpr int FF_PBYTES = 128 * 128;                 // [128 tokens x 64 rows] bf16
-constexpr int FF_SMEM = FF_QBYTES + FF_NSTAGE * FF_XBYTES + FF_PBYTES + 256 + 1024;
-constexpr int FF_THREADS = 256;
+constexpr int FF_MXBYTES = 3 * 2 * 128 * 4;          // row maxima exchanged between the two column halves: [tile parity][half][token]; [2] = final sums
+constexpr int FF_SMEM = FF_QBYTES + FF_NSTAGE * FF_XBYTES + FF_PBYTES + FF_MXBYTES + 256 + 1024;
+constexpr int FF_THREADS = 128 + 256;                // TMA, S issuer, P X issuer, (idle), 8 softmax warps
 constexpr float FF_RESCALE = 8.f;                    // log2 units: rescale O only when the maximum grew by more than this
 static_assert(FF_SMEM <= 232448, "dynamic shared memory limit");
 
@@ -79,7 +83,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) f2a_fused_kernel(const __grid_c
     uint8_t* qs = smem;
     uint8_t* xs = qs + FF_QBYTES;
     uint8_t* ps = xs + FF_NSTAGE * FF_XBYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ps + FF_PBYTES);
+    float* mxs = reinterpret_cast<float*>(ps + FF_PBYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ps + FF_PBYTES + FF_MXBYTES);
     uint64_t *x_full = bars, *x_empty = bars + FF_NSTAGE, *s_full = bars + 2 * FF_NSTAGE, *s_empty = s_full + 2, *p_full = s_full + 4,
              *p_empty = s_full + 5, *q_full = s_full + 6, *o_full = s_full + 7;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
@@ -102,23 +107,26 @@ __global__ void __launch_bounds__(FF_THREADS, 1) f2a_fused_kernel(const __grid_c
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s_full[i], 1);
-            tc::mbar_init(&s_empty[i], 4);
+            tc::mbar_init(&s_empty[i], 8);
         }
-        tc::mbar_init(p_full, 4);
+        tc::mbar_init(p_full, 8);
         tc::mbar_init(p_empty, 1);
         tc::mbar_init(q_full, 1);
         tc::mbar_init(o_full, 1);
         tc::fence_barrier_init();
     }
-    __syncthreads();
-    if (warp == 1) {
-        tc::tmem_alloc(tmem_slot, 512);
-        tc::tmem_relinquish();
+    __syncthreads();                                     // barriers initialised; the TMA warp runs ahead from here
+    uint32_t tmem_base = 0;
+    if (warp >= 1) {
+        if (warp == 1) {
+            tc::tmem_alloc(tmem_slot, 512);
+            tc::tmem_relinquish();
+        }
+        tc::tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(FF_THREADS - 32) : "memory");
+        tc::tc_fence_after();
+        tmem_base = *tmem_slot;
     }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + 2 * FF_TILE;     // S buffers: columns [0, 128); O: [128, 384)
 
     if (warp == 0) {
@@ -175,44 +183,52 @@ __global__ void __launch_bounds__(FF_THREADS, 1) f2a_fused_kernel(const __grid_c
             tc::umma_commit(o_full);
         }
     } else if (warp >= 4) {
-        const int q = warp & 3;
+        // Two warps per TMEM lane quarter: warp 4 + q reads columns [0, 32) of a tile of S, warp 8 + q columns [32, 64) of the
+        // SAME 32 token rows; the pair exchanges its row maxima through shared memory (named barrier 2 + q, 64 threads), so
+        // both halves use one reference and every thread does half of the exp2 work.  Two warps per scheduler also hide each
+        // other's latencies (one warp per scheduler ran at 1530 cycles per tile, of which ~450 were barrier round trips).
+        const int q = warp & 3, half = (warp - 4) >> 2;
         const int row = q * 32 + lane;                     // token
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const uint32_t prow = tc::smem_u32(ps) + (uint32_t)row * 128u;
         constexpr float LOG2E = 1.4426950408889634f;
-        float mx = -INFINITY, ls = 0.f;                    // reference maximum (log2 units), running sum
+        constexpr int HT = FF_TILE / 2;                    // columns of S per thread
+        float mx = -INFINITY, ls = 0.f;                    // reference maximum (log2 units), running sum of this half's columns
         const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && warp == 4 && lane == 0;
         if (dbg_on) { p.dbg[0] = t_entry; p.dbg[1] = clock64(); }
         for (int t = 0; t < ntile; ++t) {
             const int sb = t & 1;
-            const int valid = min(FF_TILE, nrows - t * FF_TILE);
-            if (dbg_on) p.dbg[8 + t * 4 + 0] = clock64();
+            const int valid = min(FF_TILE, nrows - t * FF_TILE) - half * HT;      // columns of this half below len[b] (may be <= 0)
+            if (dbg_on && t < 12) p.dbg[8 + t * 4 + 0] = clock64();
             tc::mbar_wait(&s_full[sb], (t >> 1) & 1);
             tc::tc_fence_after();
-            if (dbg_on) p.dbg[8 + t * 4 + 1] = clock64();
-            float s[FF_TILE];
-            tc::tmem_ld32(tmem_base + sb * FF_TILE + lane_off, s);
-            tc::tmem_ld32(tmem_base + sb * FF_TILE + 32 + lane_off, s + 32);
+            if (dbg_on && t < 12) p.dbg[8 + t * 4 + 1] = clock64();
+            float s[HT];
+            tc::tmem_ld32(tmem_base + sb * FF_TILE + half * HT + lane_off, s);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s_empty[sb]);
-            if (valid < FF_TILE) {                         // warp-uniform: only the last tile of a video is ragged
+            if (valid < HT) {                              // warp-uniform: only the last tile of a video is ragged
 #pragma unroll
-                for (int j = 0; j < FF_TILE; ++j)
+                for (int j = 0; j < HT; ++j)
                     if (j >= valid) s[j] = -INFINITY;
             }
             float r4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int j = 0; j < FF_TILE; j += 4) {
+            for (int j = 0; j < HT; j += 4) {
                 r4[0] = fmaxf(r4[0], s[j]); r4[1] = fmaxf(r4[1], s[j + 1]); r4[2] = fmaxf(r4[2], s[j + 2]); r4[3] = fmaxf(r4[3], s[j + 3]);
             }
-            const float tmax = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3])) * LOG2E;
-            const bool grow = tmax > mx + FF_RESCALE;      // (always true on the first tile: mx = -inf)
+            const float hmax = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3]));
+            float* mxt = mxs + (t & 1) * 256;              // parity-double-buffered: the partner reads the slot of tile t while
+            mxt[half * 128 + row] = hmax;                  // this thread may already write the one of tile t + 1
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+            const float tmax = fmaxf(hmax, mxt[(half ^ 1) * 128 + row]) * LOG2E;
+            const bool grow = tmax > mx + FF_RESCALE;      // (always true on the first tile: mx = -inf); identical in both halves
             const float mnew = grow ? tmax : mx;
             float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < FF_TILE; j += 4) {
+            for (int j = 0; j < HT; j += 4) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float e = ff_ex2(fmaf(s[j + u], LOG2E, -mnew));
@@ -222,14 +238,14 @@ __global__ void __launch_bounds__(FF_THREADS, 1) f2a_fused_kernel(const __grid_c
             }
             const float rsum = (a4[0] + a4[1]) + (a4[2] + a4[3]);
             // the previous O += P X (and every earlier MMA) has completed once the P buffer is free again
-            if (dbg_on) p.dbg[8 + t * 4 + 2] = clock64();
+            if (dbg_on && t < 12) p.dbg[8 + t * 4 + 2] = clock64();
             tc::mbar_wait(p_empty, (t & 1) ^ 1);
             tc::tc_fence_after();
-            if (dbg_on) p.dbg[8 + t * 4 + 3] = clock64();
+            if (dbg_on && t < 12) p.dbg[8 + t * 4 + 3] = clock64();
             const float sc = ff_ex2(mx - mnew);            // 1 when the reference did not move, 0 on the first tile
-            if (t > 0 && __any_sync(0xffffffffu, grow)) {
+            if (t > 0 && __any_sync(0xffffffffu, grow)) {  // this half rescales its 128 columns of O
 #pragma unroll 1
-                for (int c = 0; c < FF_H; c += 32) {
+                for (int c = half * (FF_H / 2); c < (half + 1) * (FF_H / 2); c += 32) {
                     float o[32];
                     tc::tmem_ld32(tmem_o + c + lane_off, o);
                     tc::tmem_ld_wait();
@@ -241,20 +257,21 @@ __global__ void __launch_bounds__(FF_THREADS, 1) f2a_fused_kernel(const __grid_c
             }
             ls = ls * sc + rsum;
             mx = mnew;
-            // P row -> bf16, 8 chunks of 16 bytes, K-major 128B swizzle (chunk ^ (row % 8))
+            // P row -> bf16, this half's 4 chunks of 16 bytes, K-major 128B swizzle (chunk ^ (row % 8))
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                tc::sts_v4(prow + (uint32_t)((c ^ (row & 7)) << 4), tc::pack_bf16x2(s[c * 8], s[c * 8 + 1]),
+            for (int c = 0; c < 4; ++c)
+                tc::sts_v4(prow + (uint32_t)(((half * 4 + c) ^ (row & 7)) << 4), tc::pack_bf16x2(s[c * 8], s[c * 8 + 1]),
                            tc::pack_bf16x2(s[c * 8 + 2], s[c * 8 + 3]), tc::pack_bf16x2(s[c * 8 + 4], s[c * 8 + 5]),
                            tc::pack_bf16x2(s[c * 8 + 6], s[c * 8 + 7]));
-            if (valid < FF_TILE) {
+            const int valid_t = min(FF_TILE, nrows - t * FF_TILE);
+            if (valid_t < FF_TILE) {
                 // rows in [len, slot) of the tile may hold anything (0 x NaN would poison O): zero them in shared memory.  S of
                 // this tile has completed, so the stage is idle until the P X issuer sees p_full.  A row is 128 bytes in each
                 // of the 4 channel boxes; the swizzle only permutes 16-byte chunks inside a row.
                 const uint32_t xst = tc::smem_u32(xs) + (uint32_t)((t % FF_NSTAGE) * FF_XBYTES);
-                const int nz = (FF_TILE - valid) * 32;      // 16-byte chunks to clear: rows x 4 boxes x 8 chunks
-                for (int i = (warp - 4) * 32 + lane; i < nz; i += 128) {
-                    const int r = valid + (i >> 5), j = (i >> 3) & 3, c = i & 7;
+                const int nz = (FF_TILE - valid_t) * 32;    // 16-byte chunks to clear: rows x 4 boxes x 8 chunks
+                for (int i = (warp - 4) * 32 + lane; i < nz; i += 256) {
+                    const int r = valid_t + (i >> 5), j = (i >> 3) & 3, c = i & 7;
                     tc::sts_v4(xst + (uint32_t)(j * FF_TILE * 128 + r * 128 + c * 16), 0u, 0u, 0u, 0u);
                 }
             }
@@ -265,22 +282,29 @@ __global__ void __launch_bounds__(FF_THREADS, 1) f2a_fused_kernel(const __grid_c
         }
         // epilogue: (max, sum) and the unnormalised O of every token of this split
         if (dbg_on) p.dbg[2] = clock64();
+        mxs[512 + half * 128 + row] = ls;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        const float lsum = ls + mxs[512 + (half ^ 1) * 128 + row];
         tc::mbar_wait(o_full, 0);
         tc::tc_fence_after();
         if (dbg_on) p.dbg[3] = clock64();
-        const bool live = row < p.M;
-        const size_t prt = ((size_t)b * p.nsplit + split) * p.M + row;
-        if (live) *reinterpret_cast<float2*>(p.stats + prt * 2) = make_float2(mx, ls);
+        const size_t prt0 = ((size_t)b * p.nsplit + split) * p.M;          // first token row of this split's partials
+        if (half == 0 && row < p.M) *reinterpret_cast<float2*>(p.stats + (prt0 + row) * 2) = make_float2(mx, lsum);
+        // every MMA and TMA load has completed: the row stages serve as per-warp [32][33] transposition buffers, so that the 32
+        // floats a warp stores at a time are consecutive channels of ONE token (128-byte lines instead of 32 scattered 16-byte pieces)
+        float* stg = reinterpret_cast<float*>(xs) + (warp - 4) * (32 * 33);
+        const int nval = max(0, min(32, p.M - q * 32));
 #pragma unroll 1
-        for (int c = 0; c < FF_H; c += 32) {
+        for (int c = half * (FF_H / 2); c < (half + 1) * (FF_H / 2); c += 32) {
             float o[32];
             tc::tmem_ld32(tmem_o + c + lane_off, o);
             tc::tmem_ld_wait();
-            if (live) {
-                float* dst = p.part + prt * FF_H + c;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            }
+            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = o[j];
+            __syncwarp();
+            float* dst = p.part + (prt0 + q * 32) * FF_H + c + lane;
+            for (int r = 0; r < nval; ++r) dst[(size_t)r * FF_H] = stg[r * 33 + lane];
+            __syncwarp();
         }
     }
     if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128) p.dbg[4] = clock64();
@@ -297,13 +321,13 @@ long long* g_f2a_dbg = nullptr;
 // out[b][m][e] = sum_s w_s O_s[m][e] / sum_s w_s l_s,  w_s = 2^(max_s - max over the splits); fixed split order.
 __global__ void __launch_bounds__(256) f2a_combine_kernel(const float* __restrict__ stats, const float* __restrict__ part,
                                                           float* __restrict__ out, int ldo, int slot, const int32_t* __restrict__ len,
-                                                          int M, int nsplit) {
+                                                          int M, int H, int nsplit) {
     const int b = blockIdx.y;
     const int len_b = len ? min(len[b], slot) : slot;
     const int ns = (len_b + FF_SPLIT - 1) / FF_SPLIT;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * FF_H) return;
-    const int m = i / FF_H, e = i % FF_H;
+    if (i >= M * H) return;
+    const int m = i / H, e = i % H;
     float gm = -INFINITY;
     for (int s = 0; s < ns; ++s) gm = fmaxf(gm, stats[(((size_t)b * nsplit + s) * M + m) * 2]);
     float l = 0.f, a = 0.f;
@@ -311,7 +335,7 @@ __global__ void __launch_bounds__(256) f2a_combine_kernel(const float* __restric
         const size_t r = ((size_t)b * nsplit + s) * M + m;
         const float w = exp2f(stats[r * 2] - gm);
         l = fmaf(stats[r * 2 + 1], w, l);
-        a = fmaf(part[r * FF_H + e], w, a);
+        a = fmaf(part[r * H + e], w, a);
     }
     out[((size_t)b * M + m) * ldo + e] = ns > 0 ? a / l : 0.f;
 }
@@ -320,8 +344,25 @@ __global__ void __launch_bounds__(256) f2a_combine_kernel(const float* __restric
 
 using namespace factk;
 
-/* 1 when factk_f2a_fused serves the shapes: H == 256, M <= 128, slot a multiple of 64. */
-extern "C" int factk_f2a_fused_supported(int M, int H, int slot) { return H == FF_H && M >= 1 && M <= 128 && (slot % FF_TILE) == 0; }
+namespace factk {
+// f2a_fused_t.cu: the transposed kernel (rows on the M side of both products): H = 512 and H = 256
+bool f2a_fused_t_ok(int M, int H, int slot);
+int f2a_fused_t_launch(const void* X, int ldx, const void* Qt, int ldq, long long qt_bstride, int B, int slot, const int32_t* len, int M, int H,
+                       float* stats, float* part, cudaStream_t st);
+}  // namespace factk
+
+// FACTK_F2A_KERNEL=token forces the token-major kernel of this file where both serve the shape (H == 256), =rows the transposed one
+static bool f2a_use_rows_kernel(int M, int H, int slot) {
+    static const int mode = [] { const char* e = getenv("FACTK_F2A_KERNEL"); return !e ? 0 : (e[0] == 't' ? 1 : 2); }();
+    const bool t_ok = f2a_fused_t_ok(M, H, slot), v_ok = H == FF_H && M <= 128 && (slot % FF_TILE) == 0;
+    if (t_ok && v_ok) return mode == 2 || (mode == 0 && M <= 80);      // (more than 80 token columns spill registers in the rows kernel)
+    return t_ok;
+}
+
+/* 1 when factk_f2a_fused serves the shapes: H == 256 with M <= 128, or H == 512 with M <= 80; slot a multiple of 128. */
+extern "C" int factk_f2a_fused_supported(int M, int H, int slot) {
+    return M >= 1 && (slot % 128) == 0 && ((H == FF_H && M <= 128) || f2a_fused_t_ok(M, H, slot));
+}
 
 extern "C" size_t factk_f2a_fused_ws_floats(int B, int slot, int M, int H) {
     const size_t ns = (size_t)(slot + FF_SPLIT - 1) / FF_SPLIT;
@@ -334,18 +375,25 @@ extern "C" int factk_f2a_fused(const void* X, int ldx, const void* Qt, int ldq, 
     FACTK_REQUIRE(factk_f2a_fused_supported(M, H, slot), "factk_f2a_fused: unsupported shape M=%d H=%d slot=%d", M, H, slot);
     FACTK_REQUIRE(ldx % 8 == 0 && ldq % 8 == 0 && qt_bstride % 8 == 0 && aligned16(X) && aligned16(Qt) && aligned16(ws),
                   "factk_f2a_fused: operands must be 16-byte aligned");
-    FfParams p;
     const int ns = (slot + FF_SPLIT - 1) / FF_SPLIT;
-    if (!tc_get_map(&p.qmap, Qt, 2, (uint64_t)H, (uint64_t)M, (uint64_t)B, (uint64_t)ldq, (uint64_t)qt_bstride, 128)) return FACTK_ERR_CUDA;
-    if (!tc_get_map(&p.xmap, X, 2, (uint64_t)H, (uint64_t)slot, (uint64_t)B, (uint64_t)ldx, (uint64_t)slot * ldx, FF_TILE)) return FACTK_ERR_CUDA;
-    p.M = M; p.slot = slot; p.nsplit = ns; p.len = len; p.dbg = g_f2a_dbg;
-    p.stats = ws;
-    p.part = ws + (((size_t)B * ns * M * 2 + 3) & ~(size_t)3);
-    static unsigned long long devs = 0;
-    if (first_use_on_device(devs)) cudaFuncSetAttribute(f2a_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
+    float* stats = ws;
+    float* part = ws + (((size_t)B * ns * M * 2 + 3) & ~(size_t)3);
     cudaStream_t st = (cudaStream_t)stream;
-    f2a_fused_kernel<<<dim3(ns, B), FF_THREADS, FF_SMEM, st>>>(p);
-    f2a_combine_kernel<<<dim3((M * FF_H + 255) / 256, B), 256, 0, st>>>(p.stats, p.part, out, ldo, slot, len, M, ns);
+    if (f2a_use_rows_kernel(M, H, slot)) {
+        const int rc = f2a_fused_t_launch(X, ldx, Qt, ldq, qt_bstride, B, slot, len, M, H, stats, part, st);
+        if (rc) return rc;
+    } else {
+        FfParams p;
+        if (!tc_get_map(&p.qmap, Qt, 2, (uint64_t)H, (uint64_t)M, (uint64_t)B, (uint64_t)ldq, (uint64_t)qt_bstride, 128)) return FACTK_ERR_CUDA;
+        if (!tc_get_map(&p.xmap, X, 2, (uint64_t)H, (uint64_t)slot, (uint64_t)B, (uint64_t)ldx, (uint64_t)slot * ldx, FF_TILE)) return FACTK_ERR_CUDA;
+        p.M = M; p.slot = slot; p.nsplit = ns; p.len = len; p.dbg = g_f2a_dbg;
+        p.stats = stats;
+        p.part = part;
+        static unsigned long long devs = 0;
+        if (first_use_on_device(devs)) cudaFuncSetAttribute(f2a_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
+        f2a_fused_kernel<<<dim3(ns, B), FF_THREADS, FF_SMEM, st>>>(p);
+    }
+    f2a_combine_kernel<<<dim3((M * H + 255) / 256, B), 256, 0, st>>>(stats, part, out, ldo, slot, len, M, H, ns);
     return check_launch("factk_f2a_fused");
 }
 

@@ -86,7 +86,11 @@ class FactEngine:
         key = (name, tuple(shape), dtype)
         t = self._bufs.get(key)
         if t is None:
-            t = torch.empty(shape, dtype=dtype, device=self.dev)
+            # zero-initialised ONCE: rows in [len, slot) are never written, and the tensor-core attention kernels multiply them by
+            # exact-zero probabilities -- stale finite values are harmless there, uninitialised NaN bit patterns would not be
+            t = torch.zeros(shape, dtype=dtype, device=self.dev)
+            if not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream().synchronize()  # (the fill must not race a copy-stream write into the new buffer)
             self._bufs[key] = t
         return t
 
@@ -752,7 +756,7 @@ class FactEngine:
         if self.hp['trans']:
             assert transcript is not None and len(seqs) == 1, 'FACT.trans: one video per call, with its transcript'
             self.ntok = int(transcript.numel())
-        self._set_arena((B, slot, self.ntok))
+        self._set_arena((B, slot, self.ntok, self.lane))
         if self.hp['trans']:
             N, A = int(transcript.numel()), self.hp['blocks'][0]['a_dim']
             self.ntok, self.transcript = N, transcript.to(torch.int32).contiguous()
@@ -793,7 +797,7 @@ class FactEngine:
         old = self._slot_pending[k]
         if old is not None:                 # the batch that last used this slot: take its predictions out of the pinned buffer
             old.detach_result()
-        self._set_arena((B, slot, self.ntok))
+        self._set_arena((B, slot, self.ntok, self.lane))
         main = torch.cuda.current_stream()
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.dev)

@@ -361,7 +361,8 @@ class _FactBase(nn.Module):
                     blk.a2f_attn_logit = st['a2f_attn_logit'][b, :S, :M].unsqueeze(0)
                 if st.get('a2f_attn_seg') is not None:
                     blk.a2f_attn = st['a2f_attn_seg'][b, :S, :M][lab].unsqueeze(0)
-                blk.f2a_attn_logit = st['f2a_attn_logit'][b, :S, :M].t().unsqueeze(0)
+                if st.get('f2a_attn_logit') is not None:      # (the fused f2a kernel never forms the logits unless keep_attn / the loss asks)
+                    blk.f2a_attn_logit = st['f2a_attn_logit'][b, :S, :M].t().unsqueeze(0)
                 if st.get('f2a_attn_seg') is not None:
                     blk.f2a_attn = st['f2a_attn_seg'][b, :S, :M][lab].t().unsqueeze(0)
             elif 'a2f_attn' in st:
@@ -369,7 +370,8 @@ class _FactBase(nn.Module):
                     blk.a2f_attn_logit = st['a2f_attn_logit'][b, :T, :M].unsqueeze(0)
                 if st.get('a2f_attn') is not None:
                     blk.a2f_attn = st['a2f_attn'][b, :T, :M].unsqueeze(0)
-                blk.f2a_attn_logit = st['f2a_attn_logit'][b, :T, :M].t().unsqueeze(0)
+                if st.get('f2a_attn_logit') is not None:      # (the fused f2a kernel never forms the logits unless keep_attn / the loss asks)
+                    blk.f2a_attn_logit = st['f2a_attn_logit'][b, :T, :M].t().unsqueeze(0)
                 if st.get('f2a_attn') is not None:
                     blk.f2a_attn = st['f2a_attn'][b, :T, :M].t().unsqueeze(0)
         if 'projected_frame_embeddings' in out:

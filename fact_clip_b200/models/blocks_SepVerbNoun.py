@@ -125,6 +125,7 @@ class FACT(_FactBase):
             if 'a2f_attn_logit' in st:
                 blk.a2f_attn_logit = st['a2f_attn_logit'][b, :S, :M].unsqueeze(0)
                 blk.a2f_attn = st['a2f_attn_seg'][b, :S, :M][lab].unsqueeze(0)
-                blk.f2a_attn_logit = st['f2a_attn_logit'][b, :S, :M].t().unsqueeze(0)
+                if st.get('f2a_attn_logit') is not None:      # (the fused f2a kernel never forms the logits unless keep_attn / the loss asks)
+                    blk.f2a_attn_logit = st['f2a_attn_logit'][b, :S, :M].t().unsqueeze(0)
                 if st.get('f2a_attn_seg') is not None:
                     blk.f2a_attn = st['f2a_attn_seg'][b, :S, :M][lab].t().unsqueeze(0)

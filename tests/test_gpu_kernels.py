@@ -464,19 +464,22 @@ def test_a2f_fused(M, slot, lens, with_outputs):
         assert float(out[b, T:].float().abs().sum()) == 0.0          # rows past the end are never written
 
 
-@pytest.mark.parametrize('M,slot,lens,qscale,ramp', [(75, 512, [512, 300], 0.1, 0.0), (128, 1024, [1024, 513, 1], 0.1, 0.0),
-                                                     (12, 384, [64, 384, 130], 0.3, 0.0), (75, 4096, [4096, 4000, 577], 0.05, 0.0),
-                                                     (75, 2048, [2048, 1500], 0.1, 40.0), (33, 640, [640, 65], 0.1, -25.0)])
-def test_f2a_fused(M, slot, lens, qscale, ramp):
-    """Fused X2Y_map, f2a direction (f2a_fused.cu): S = qt rows^T -> softmax over the rows (online, split over 512-row CTAs) ->
-    weighted row sum in one tcgen05 kernel + the split combine, against fp32 torch on the same bf16 operands.  ``ramp`` adds a
-    trend along the rows so that the running maximum keeps growing (positive: the accumulator rescale path) or the first tile
-    dominates (negative); rows past len[b] hold NaN (they must not reach the accumulator)."""
-    B, H = len(lens), 256
+@pytest.mark.parametrize('M,H,slot,lens,qscale,ramp', [
+    (75, 512, 4096, [4096, 4000, 577], 0.05, 0.0), (75, 512, 512, [512, 300], 0.1, 0.0), (80, 512, 256, [256, 1, 129], 0.1, 0.0),
+    (12, 512, 384, [64, 384, 130], 0.3, 0.0), (33, 512, 640, [640, 65], 0.1, -25.0), (75, 512, 2304, [2304, 1500], 0.1, 40.0),
+    (75, 256, 512, [512, 300], 0.1, 0.0), (128, 256, 1024, [1024, 513, 1], 0.1, 0.0), (96, 256, 2048, [2048, 1500], 0.1, 40.0),
+    (12, 256, 384, [64, 384, 130], 0.3, 0.0), (33, 256, 640, [640, 65], 0.1, -25.0)])
+def test_f2a_fused(M, H, slot, lens, qscale, ramp):
+    """Fused X2Y_map, f2a direction (f2a_fused_t.cu: rows on the M side, hid_dim 512 / 256; f2a_fused.cu: tokens on the M side,
+    hid_dim 256 with more than 80 tokens): S = qt rows^T -> softmax over the rows (online, 2048-row CTAs) -> weighted row sum in
+    one tcgen05 kernel + the split combine, against fp64 torch on the same bf16 operands.  ``ramp`` adds a trend along the rows
+    so that the running maximum keeps growing (positive: the accumulator rescale path) or the first tile dominates (negative);
+    rows past len[b] hold large finite garbage (they get exact-zero probabilities)."""
+    B = len(lens)
     bf = torch.bfloat16
     assert ops.f2a_fused_ok(M, H, slot)
     rows = rnd(B, slot, H, seed=41)
-    qt = rnd(B, M, H, seed=42) * qscale
+    qt = rnd(B, M, H, seed=42) * qscale * (256 / H) ** 0.5
     if ramp:
         # one channel carries t / slot; the queries read it with weight ``ramp``: logit += ramp * t / slot
         rows[:, :, 0] = torch.arange(slot, dtype=torch.float32)[None, :] / slot
@@ -484,7 +487,7 @@ def test_f2a_fused(M, slot, lens, qscale, ramp):
     rows, qt = rows.to(bf), qt.to(bf)
     rows_dev = rows.clone()
     for b, T in enumerate(lens):
-        rows_dev[b, T:] = float('nan')
+        rows_dev[b, T:] = 1.0e4
     out = torch.full((B, M, H), float('nan'), device=DEV)
     ws = torch.empty(ops.f2a_fused_ws(B, slot, M, H), device=DEV)
     ln = torch.tensor(lens, dtype=torch.int32, device=DEV)

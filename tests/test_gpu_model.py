@@ -324,7 +324,7 @@ def test_graph_reused_across_lengths_and_arenas_bounded():
     for h, ref in zip(handles, refs):
         for a, b in zip(h.result(), ref):
             assert np.array_equal(a['pred'], b['pred'])
-    arena = eng._arenas[(2, 128, eng.ntok)]
+    arena = eng._arenas[(2, 128, eng.ntok, eng.lane)]
     assert len(arena['graphs']) == 2, 'one graph per input slot, not one per lengths tuple'
     for n in (130, 260, 390, 520, 650, 780):                                # six more slot sizes
         got = net.submit(batch((n, n // 2)), None).result()
