@@ -254,7 +254,7 @@ def calibrated_regime(net, cfg, dev, x, ln, lengths, B, T, args):
     return {'label': 'CALIBRATED weights (not the headline): same forward workload after a short training run with this repo\'s own training step',
             'training': {'steps': args.calibrate_steps, 'videos_per_step': nb, 'frames_per_video': Tt, 'loss_first': first, 'loss_last': last,
                          'seconds': train_s, 'optimizer': 'Adam lr 3e-4, clip_grad_norm 10'},
-            'value': B * T / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+            'value': B * T / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'launch': 'one CUDA graph per step on ONE stream (compare with single_stream, not with the multi-lane headline)',
             'segments_per_U_block': [[min(s_), max(s_)] for s_ in nseg]}
 
 
@@ -453,7 +453,7 @@ def main():
     ap.add_argument('--e2e-split', type=int, default=4, help='sub-batches per step on the end-to-end (pipelined) path')
     ap.add_argument('--no-graph', action='store_true', help='eager kernel launches instead of one CUDA graph per batch')
     ap.add_argument('--resident-only', action='store_true', help='stop after the resident loop (profiling aid)')
-    ap.add_argument('--lanes', type=int, default=2, help='resident measurement: steps alternate between this many streams / activation arenas')
+    ap.add_argument('--lanes', type=int, default=3, help='resident measurement: steps alternate between this many streams / activation arenas')
     ap.add_argument('--no-prefetch', action='store_true', help='(--train) copy each step\'s video to the device at the start of the step instead of during the previous step')
     ap.add_argument('--timeline', action='store_true', help='(--train) torch.profiler device timeline of one step: busy / idle / top kernels, to stderr')
     ap.add_argument('--profile', action='store_true', help='print a CUDA-event breakdown per kernel family to stderr')

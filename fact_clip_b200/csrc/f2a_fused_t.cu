@@ -41,6 +41,7 @@ struct FtParams {
     const int32_t* len;
     float* stats;                    // [B][nsplit][M][2] = (reference in log2 units, sum)
     float* part;                     // [B][nsplit][M][H] unnormalised weighted row sums
+    long long* dbg;                  // optional clock64 timeline of CTA (0,0), softmax warp 4 lane 0 (development aid)
 };
 
 constexpr uint32_t FT_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);       // SBO 1024 | version 1 | SWIZZLE_128B
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_entry = clock64();
     const int split = blockIdx.x, b = blockIdx.y;
     const int len_b = p.len ? min(p.len[b], p.slot) : p.slot;
     const int r0 = split * FT_SPLIT;
@@ -231,11 +233,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
         float l[NH];                                       // running sums of this thread's rows, per token of its half
 #pragma unroll
         for (int c = 0; c < NH; ++c) l[c] = 0.f;
+        const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && warp == 4 && lane == 0;
+        if (dbg_on) { p.dbg[0] = t_entry; p.dbg[1] = clock64(); }
         for (int t = 0; t < ntile; ++t) {
             const int sb = t & 1;
             const bool live = t * FT_TILE + f < nrows;
+            if (dbg_on && t < 12) p.dbg[8 + t * 4 + 0] = clock64();
             tc::mbar_wait(&s_full[sb], (t >> 1) & 1);
             tc::tc_fence_after();
+            if (dbg_on && t < 12) p.dbg[8 + t * 4 + 1] = clock64();
             float x[NH];
 #pragma unroll
             for (int g = 0; g < NH / 8; ++g) ft_tmem_ld8(tmem_base + sb * N + c0 + g * 8 + lane_off, x + g * 8);
@@ -283,8 +289,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
                 l[c] += x[c]; l[c + 1] += x[c + 1]; l[c + 2] += x[c + 2]; l[c + 3] += x[c + 3];
             }
             // the previous O^T += X^T P^T (and every earlier MMA) has completed once the P^T buffer is free again
+            if (dbg_on && t < 12) p.dbg[8 + t * 4 + 2] = clock64();
             tc::mbar_wait(p_empty, (t & 1) ^ 1);
             tc::tc_fence_after();
+            if (dbg_on && t < 12) p.dbg[8 + t * 4 + 3] = clock64();
             if (slow && t > 0) {                           // rescale this thread's share of O^T: lane quarter q, its token columns
                 for (int j = 0; j < MT; ++j) {
 #pragma unroll
@@ -312,6 +320,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(p_full);
         }
+        if (dbg_on) p.dbg[2] = clock64();
         // normaliser: sum over the rows = over lanes, quarters (fixed order)
 #pragma unroll
         for (int c = 0; c < NH; ++c) {
@@ -325,6 +334,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
         // O^T: thread = channel, columns = tokens: the 32 lanes of a warp write 32 consecutive channels of one token
         tc::mbar_wait(o_full, 0);
         tc::tc_fence_after();
+        if (dbg_on) p.dbg[3] = clock64();
         for (int j = 0; j < MT; ++j) {
             float o[NH];
 #pragma unroll
@@ -336,6 +346,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
                 if (c0 + c < p.M) dst[(size_t)(c0 + c) * p.H] = o[c];
         }
     }
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128) p.dbg[4] = clock64();
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -343,6 +354,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
         tc::tmem_dealloc(tmem_base, 512);
     }
 }
+
+extern long long* g_f2a_dbg;     // f2a_fused.cu (factk_f2a_debug)
 
 static int ft_cols(int M) {
     const int opts[] = {32, 64, 80, 96, 128};
@@ -372,7 +385,7 @@ int f2a_fused_t_launch(const void* X, int ldx, const void* Qt, int ldq, long lon
     const int ns = (slot + FT_SPLIT - 1) / FT_SPLIT;
     if (!tc_get_map(&p.qmap, Qt, 2, (uint64_t)H, (uint64_t)M, (uint64_t)B, (uint64_t)ldq, (uint64_t)qt_bstride, (uint32_t)N)) return FACTK_ERR_CUDA;
     if (!tc_get_map(&p.xmap, X, 2, (uint64_t)H, (uint64_t)slot, (uint64_t)B, (uint64_t)ldx, (uint64_t)slot * ldx, FT_TILE)) return FACTK_ERR_CUDA;
-    p.M = M; p.H = H; p.slot = slot; p.nsplit = ns; p.len = len; p.stats = stats; p.part = part;
+    p.M = M; p.H = H; p.slot = slot; p.nsplit = ns; p.len = len; p.stats = stats; p.part = part; p.dbg = g_f2a_dbg;
     switch (N) {
         case 32: ft_launch<32>(p, B, st); break;
         case 64: ft_launch<64>(p, B, st); break;

@@ -108,6 +108,83 @@ __global__ void __launch_bounds__(256) splice_small_kernel(T* __restrict__ X, in
     }
 }
 
+// splice_small_kernel with RW consecutive rows per warp: all the loads of the RW rows are issued before the first reduction, so a
+// warp keeps RW * NV loads in flight instead of NV (the frame-level launches of the one-row kernel ran at a third of the HBM rate:
+// 64 warps x 3 short loads per SM do not cover the memory latency).  Same arithmetic, same results.
+template <typename T, int NV, int RW>
+__global__ void __launch_bounds__(256) splice_multi_kernel(T* __restrict__ X, int B, int slot, const int32_t* __restrict__ len,
+                                                           int ld, int H, int C, float* __restrict__ clogit,
+                                                           int32_t* __restrict__ pred) {
+    const long row0 = ((long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5)) * RW;
+    if (row0 >= (long)B * slot) return;
+    const int b = (int)(row0 / slot), t0 = (int)(row0 % slot);          // slot % RW == 0: a group never straddles two videos
+    const int nvalid = min(RW, (len ? min(len[b], slot) : slot) - t0);
+    if (nvalid <= 0) return;
+    const int lane = threadIdx.x & 31;
+    T* x0 = X + (size_t)row0 * (size_t)ld + (H - C);
+    float v[RW][NV];
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            v[r][i] = (r < nvalid && c < C) ? to_f<T>(x0[(size_t)r * ld + c]) : -INFINITY;
+        }
+    float mx[RW], inv[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+        mx[r] = v[r][0];
+#pragma unroll
+        for (int i = 1; i < NV; ++i) mx[r] = fmaxf(mx[r], v[r][i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < RW; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+    float e[RW][NV];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+        inv[r] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            e[r][i] = __expf(v[r][i] - mx[r]);          // exp(-inf) = 0 for the padding lanes
+            inv[r] += e[r][i];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < RW; ++r) inv[r] += __shfl_xor_sync(0xffffffffu, inv[r], o);
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+        if (r >= nvalid) break;
+        const float iv = 1.f / inv[r];
+        const size_t row = (size_t)row0 + r;
+        float* cl = clogit + row * (size_t)C;
+        float best = -1.f;
+        int besti = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) {
+                const float p = e[r][i] * iv;
+                cl[c] = v[r][i];
+                x0[(size_t)r * ld + c] = from_f<T>(p);
+                if (p > best) { best = p; besti = c; }   // strict > keeps the first index within a lane
+            }
+        }
+        if (pred) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            if (lane == 0) pred[row] = besti;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* X, int x_dtype, int ldx, const void* R, int r_dtype,
                                                         int ldr, const float* w, const float* bb, float eps, int relu,
                                                         void* Y, int y_dtype, int ldy, int B, int slot,
@@ -300,6 +377,12 @@ extern "C" int factk_softmax_splice(void* X, int dtype, int B, int slot, const i
                          : splice_small_kernel<float, NV_><<<row_grid(B, slot), 256, 0, st>>>(reinterpret_cast<float*>(X), B,    \
                                                                                                 slot, len, ld, H, C, clogit_out, \
                                                                                                 pred_out))
+    // frame-level launches of the shipped class counts: four rows per warp (splice_multi_kernel)
+    if (dtype == FACTK_BF16 && nv == 3 && (slot % 4) == 0 && (long)B * slot >= 32768) {
+        const unsigned grid4 = (unsigned)(((long)B * slot / 4 + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+        splice_multi_kernel<__nv_bfloat16, 3, 4><<<grid4, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(X), B, slot, len, ld, H, C, clogit_out, pred_out);
+        return check_launch("factk_softmax_splice");
+    }
     if (nv == 1) SPLICE(1);
     else if (nv == 2) SPLICE(2);
     else if (nv == 3) SPLICE(3);

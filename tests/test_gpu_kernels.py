@@ -115,6 +115,24 @@ def test_softmax_splice(dtype):
         close(xd[b, T:], x[b, T:], rtol=0, atol=0)
 
 
+def test_softmax_splice_frame_level_four_rows_per_warp():
+    """The frame-level launches (bf16, 65..96 classes, >= 32768 rows) take splice_multi_kernel (four rows per warp): same results as
+    the oracle's process_feature, ragged lengths that end inside a four-row group, rows past the end untouched."""
+    B, slot, H, C, lens = 3, 16384, 512, 75, [16384, 16381, 5]
+    x = rnd(B, slot, H, seed=61, scale=2.0).to(torch.bfloat16)
+    xd = x.to(DEV).clone()
+    clogit = torch.zeros(B, slot, C, device=DEV)
+    pred = torch.full((B, slot), -1, dtype=torch.int32, device=DEV)
+    ops.softmax_splice(xd, C, clogit, pred, len=torch.tensor(lens, dtype=torch.int32, device=DEV))
+    for b, T in enumerate(lens):
+        feat, cl = O.process_feature(x[b, :T].float(), C)
+        close(clogit[b, :T], cl, rtol=0, atol=0)
+        close(xd[b, :T], feat, rtol=1e-2, atol=1e-2)
+        assert torch.equal(pred[b, :T].cpu().long(), cl.argmax(-1))
+        close(xd[b, T:], x[b, T:], rtol=0, atol=0)
+        assert bool((pred[b, T:] == -1).all())
+
+
 def test_layernorm_l2norm_rowsoftmax_gather():
     B, slot, E = 2, 40, 96
     x, r = rnd(B, slot, E, seed=17), rnd(B, slot, E, seed=18)

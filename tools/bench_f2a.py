@@ -50,6 +50,20 @@ def main():
             ts.append(e0.elapsed_time(e1) * 1e3)
         ts.sort()
         res[name] = ts[len(ts) // 2]
+    # stage timeline of CTA (0, 0): softmax warp 4, lane 0 (clock64)
+    from fact_clip_b200 import _lib
+    dbg = torch.zeros(64, dtype=torch.int64, device=dev)
+    _lib.load().factk_f2a_debug(dbg.data_ptr())
+    fused()
+    torch.cuda.synchronize()
+    _lib.load().factk_f2a_debug(None)
+    d = dbg.tolist()
+    t0 = d[0]
+    print(f'timeline (cycles from CTA entry): setup done {d[1] - t0}, tiles done {d[2] - t0}, o_full {d[3] - t0}, exit {d[4] - t0}')
+    for t in range(12):
+        a = d[8 + 4 * t: 12 + 4 * t]
+        if a[0]:
+            print(f'  tile {t}: wait S {a[1] - a[0]:6d}  softmax {a[2] - a[1]:6d}  wait P free {a[3] - a[2]:6d}   (start {a[0] - t0})')
     err = float((out_a - out_b).norm() / out_a.norm())
     bytes_rows = B * slot * H * 2
     print(f'B={B} slot={slot} M={M}: chain {res["chain"]:.1f} us, fused {res["fused"]:.1f} us '
