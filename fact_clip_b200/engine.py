@@ -39,6 +39,7 @@ class FactEngine:
         self.use_fused_tcn = True
         self.use_pair_gemm = True
         self.use_fused_x2y = os.environ.get('FACTK_FUSED_X2Y', '1') != '0'
+        self.use_merged_kv = os.environ.get('FACTK_MERGED_KV', '1') != '0'
         self._submits, self._copy_stream, self._slot_free, self._slot_pending = 0, None, [None, None], [None, None]
         self._wcache, self._wsig = {}, None
         # FACTK_FLAT_TOKENS=1 tiles the token rows of all videos as ONE dense matrix (38 instead of 64 tiles at 64 x 75 tokens).
@@ -388,21 +389,35 @@ class FactEngine:
         else:
             tgt.copy_(self.action_init)
         t = self.buf('tok_t', (B, M, A))
-        # zero-initialised: rows >= len are never written and the tensor-core attention multiplies them by exact zeros
-        kv = self.zbuf('sca_kv', (B, slot, 2 * A), self.act)
         ws = self.buf('attn_ws', (max(ops.attn_rows_ws(B, slot, M, nh, A // nh), 1),))
         fpos = self.frame_pos
         ff = self.p(f'{pfx}layers.0.linear1.weight').shape[0]
         fused = self._tok_fused(tgt, nh, ff)
-        for i in range(bc['a_layers']):
-            q = f'{pfx}layers.{i}.'
-            c = q + 'multihead_attn.'
-            cb = self.p(c + 'in_proj_bias')
+
+        def xattn_w(i):
+            c = f'{pfx}layers.{i}.multihead_attn.'
             if (c + 'in_proj_weight') in self._p:
                 W = self.p(c + 'in_proj_weight')
-                wq, wk, wv = W[:A], W[A:2 * A], W[2 * A:]
-            else:
-                wq, wk, wv = self.p(c + 'q_proj_weight'), self.p(c + 'k_proj_weight'), self.p(c + 'v_proj_weight')
+                return W[:A], W[A:2 * A], W[2 * A:], self.p(c + 'in_proj_bias')
+            return self.p(c + 'q_proj_weight'), self.p(c + 'k_proj_weight'), self.p(c + 'v_proj_weight'), self.p(c + 'in_proj_bias')
+
+        nl = bc['a_layers']
+        kv_all = None
+        if fpos is None and self.mode == 'bf16' and self.use_tc and frame.dtype == torch.bfloat16 and nl > 1 and self.use_merged_kv:
+            # every layer projects the SAME memory rows: one GEMM with the key / value weights of all layers stacked (N = 2 A layers)
+            # reads the rows once instead of once per layer; layer i attends columns [2 A i, 2 A (i + 1)) of the result
+            wkv_all = self.derived(('wkv_all', pfx), lambda: torch.cat([torch.cat(xattn_w(i)[1:3], 0) for i in range(nl)], 0))
+            bkv_all = self.derived(('bkv_all', pfx), lambda: torch.cat([xattn_w(i)[3][A:] for i in range(nl)], 0))
+            kv_all = self.zbuf('sca_kv_all', (B, slot, 2 * A * nl), self.act)
+            self.mm([S(frame, wkv_all)], 2 * A * nl, kv_all, len=rlen, bias=bkv_all, tag='sca_kv')
+        # zero-initialised: rows >= len are never written and the tensor-core attention multiplies them by exact zeros
+        kv = self.zbuf('sca_kv', (B, slot, 2 * A), self.act) if kv_all is None else None
+        for i in range(nl):
+            q = f'{pfx}layers.{i}.'
+            c = q + 'multihead_attn.'
+            wq, wk, wv, cb = xattn_w(i)
+            if kv_all is not None:
+                kv = kv_all[:, :, 2 * A * i:2 * A * (i + 1)]
             cq = self.buf('tok_cq', (B, M, A))
             if fused:
                 # self attention + out_proj + norm1 + the cross attention's query projection: one launch
@@ -417,7 +432,9 @@ class FactEngine:
                 ops.layernorm(t, self.p(q + 'norm1.weight'), self.p(q + 'norm1.bias'), tgt)
                 # cross attention: q from tokens, k from frames (+pos), v from frames
                 self.lin(tgt, wq, A, cq, pos=qpos, bias=cb[:A])
-            if fpos is None:
+            if kv_all is not None:
+                pass
+            elif fpos is None:
                 wkv = self.derived(('wkv', c), lambda: torch.cat([wk, wv], 0))
                 self.mm([S(frame, wkv)], 2 * A, kv, len=rlen, bias=cb[A:], tag='sca_kv')
             elif self.mode == 'bf16' and self.use_tc and frame.dtype == torch.bfloat16:
