@@ -251,10 +251,38 @@ def calibrated_regime(net, cfg, dev, x, ln, lengths, B, T, args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     nseg = [st['nseg'].tolist() for st in stash['blocks'] if 'nseg' in st]
+    # the same loop with consecutive steps on args.lanes streams / arenas / graphs (how the headline `value` is measured)
+    ms_lanes = None
+    if args.lanes > 1:
+        streams = [torch.cuda.Stream() for _ in range(args.lanes)]
+
+        def lane_step(i):
+            k = i % len(streams)
+            eng.lane = k
+            streams[k].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[k]):
+                eng.run_packed_graphed(x, ln, lengths)
+            eng.lane = 0
+
+        for i in range(2 * len(streams)):
+            lane_step(i)
+        for s_ in streams:
+            torch.cuda.current_stream().wait_stream(s_)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            lane_step(i)
+        for s_ in streams:
+            torch.cuda.current_stream().wait_stream(s_)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_lanes = e0.elapsed_time(e1) / args.steps
     return {'label': 'CALIBRATED weights (not the headline): same forward workload after a short training run with this repo\'s own training step',
             'training': {'steps': args.calibrate_steps, 'videos_per_step': nb, 'frames_per_video': Tt, 'loss_first': first, 'loss_last': last,
                          'seconds': train_s, 'optimizer': 'Adam lr 3e-4, clip_grad_norm 10'},
-            'value': B * T / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'launch': 'one CUDA graph per step on ONE stream (compare with single_stream, not with the multi-lane headline)',
+            'value': B * T / ((ms_lanes or ms) * 1e-3), 'unit': UNIT, 'ms_per_step': ms_lanes or ms,
+            'launch': f'one CUDA graph per step, consecutive steps on {args.lanes} streams (like the headline value)' if ms_lanes else 'one CUDA graph per step on one stream',
+            'single_stream': {'value': B * T / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms},
             'segments_per_U_block': [[min(s_), max(s_)] for s_ in nseg]}
 
 
@@ -458,7 +486,7 @@ def main():
     ap.add_argument('--timeline', action='store_true', help='(--train) torch.profiler device timeline of one step: busy / idle / top kernels, to stderr')
     ap.add_argument('--profile', action='store_true', help='print a CUDA-event breakdown per kernel family to stderr')
     ap.add_argument('--train', action='store_true', help='BASELINE config 5: data-parallel training step (Epic-Kitchens shape, T=16384)')
-    ap.add_argument('--calibrate-steps', type=int, default=120, help='training steps for the second (calibrated-weights) regime; 0 skips it')
+    ap.add_argument('--calibrate-steps', type=int, default=600, help='training steps for the second (calibrated-weights) regime; 0 skips it')
     ap.add_argument('--train-frames', type=int, default=16384)
     ap.add_argument('--train-nseg', type=int, default=52, help='ground-truth segments per synthetic training video (epic o2m average)')
     args = ap.parse_args()
