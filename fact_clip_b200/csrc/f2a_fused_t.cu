@@ -16,8 +16,8 @@
 // H = 512) does not stay resident: it streams through a 3-stage ring of [128 rows x 128 channels] twice per tile, once for
 // S^T (from HBM) and once for O^T (from L2).  The normaliser is a per-thread running sum per token, reduced once at the end.
 // Warp 0 = TMA producer, warp 1 = MMA issuer (order S(0) S(1) | O(0) S(2) | O(1) S(3) ...), warps 4-11 = softmax / epilogue: the
-// two warps of a TMEM lane quarter split the token columns.  Rows in [len[b], slot) must hold FINITE values (the engine
-// zero-initialises its buffers): their probabilities are exactly zero, but 0 x NaN would poison the accumulator.
+// two warps of a TMEM lane quarter split the token columns.  Rows in [len[b], slot) may hold anything: their logits are masked,
+// and before the O^T pass of a ragged last tile the softmax warps zero them in the shared-memory stages (0 x NaN would poison O^T).
 // Output: the same per-split partials as f2a_fused.cu (max in log2 units, sum, unnormalised O), merged by f2a_combine_kernel.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
     float* wq = scs + 128;                                           // [4 lane quarters][128]: tile maxima, final sums
     uint64_t* bars = reinterpret_cast<uint64_t*>(pt + FT_PBYTES + FT_SMALL);
     uint64_t *full = bars, *empty = bars + FT_NSTAGE, *s_full = bars + 2 * FT_NSTAGE, *s_empty = s_full + 2, *p_full = s_full + 4,
-             *p_empty = s_full + 5, *q_full = s_full + 6, *o_full = s_full + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+             *p_empty = s_full + 5, *q_full = s_full + 6, *o_full = s_full + 7, *clean = s_full + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 12);      // (clean[0..3]: one single-use barrier per stage of the pass)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t_entry = clock64();
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
     if (r0 >= len_b) return;                             // uniform per CTA: nothing allocated yet
     const int nrows = min(r0 + FT_SPLIT, len_b) - r0;
     const int ntile = (nrows + FT_TILE - 1) / FT_TILE;
+    const int last_valid = nrows - (ntile - 1) * FT_TILE;      // rows of the last tile below len[b]; < 128: the tile is ragged
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&p.qmap);
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
         tc::mbar_init(p_empty, 1);
         tc::mbar_init(q_full, 1);
         tc::mbar_init(o_full, 1);
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&clean[i], 8);
         tc::fence_barrier_init();
     }
     if (threadIdx.x >= 128 && threadIdx.x < 256) ref[threadIdx.x - 128] = -INFINITY;
@@ -201,8 +203,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
             auto o_tile = [&](int t) {                   // O^T_j += X_t[:, 128 j ..]^T P^T: 8 k-steps of 16 rows per channel tile
                 tc::mbar_wait(p_full, t & 1);
                 tc::tc_fence_after();
+                const bool ragged = t == ntile - 1 && last_valid < FT_TILE;
                 for (int j = 0; j < MT; ++j) {
                     tc::mbar_wait(&full[stage], phase);
+                    if (ragged) tc::mbar_wait(&clean[j], 0);           // rows past len[b] of this stage zeroed by the softmax warps
                     tc::tc_fence_after();
                     const uint32_t xa = xm_lo + (uint32_t)((stage * FT_STAGE) >> 4);
 #pragma unroll
@@ -321,6 +325,25 @@ __global__ void __launch_bounds__(FT_THREADS, 1) f2a_fused_t_kernel(const __grid
             if (lane == 0) tc::mbar_arrive(p_full);
         }
         if (dbg_on) p.dbg[2] = clock64();
+        if (last_valid < FT_TILE) {
+            // Ragged last tile: its rows in [len[b], slot) have exact-zero probabilities, but they may hold anything (0 x NaN would
+            // poison O^T), so the stages of the LAST O^T pass are cleaned in shared memory between the TMA arrival and the MMAs.
+            // That pass is ring pass number 2 ntile - 1 (all S^T passes and the other O^T passes come before it).
+            const int first = (2 * ntile - 1) * MT;
+            for (int j = 0; j < MT; ++j) {
+                const int g = first + j, stage = g % FT_NSTAGE;
+                tc::mbar_wait(&full[stage], (uint32_t)(g / FT_NSTAGE) & 1u);
+                const uint32_t st = tc::smem_u32(ring) + (uint32_t)(stage * FT_STAGE);
+                const int nz = (FT_TILE - last_valid) * 16;             // 16-byte chunks: rows x 2 boxes x 8 (a row is a 128-byte line)
+                for (int i = tsm; i < nz; i += 256) {
+                    const int r = last_valid + (i >> 4), bx = (i >> 3) & 1, c = i & 7;
+                    tc::sts_v4(st + (uint32_t)(bx * FT_BOX + r * 128 + c * 16), 0u, 0u, 0u, 0u);
+                }
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&clean[j]);      // (one barrier per stage: a phase-counted one could run two phases ahead of the issuer)
+            }
+        }
         // normaliser: sum over the rows = over lanes, quarters (fixed order)
 #pragma unroll
         for (int c = 0; c < NH; ++c) {

@@ -190,7 +190,7 @@ int factk_a2f_fused(const void* X, int ldx, const void* Kt, int ldkt, long long 
  * The rows are read once; the [B][slot][M] logits never reach HBM (the per-token logit bias is constant along t and cancels).
  * rows X bf16 [B][slot][ldx] (H channels), qt bf16 [B][M][ldq] (the token-side fold alpha Wk^T Y_Q(tokens)), out fp32 [B][M][ldo],
  * ws >= factk_f2a_fused_ws_floats(B, slot, M, H) floats.  H == 512 with M <= 80 or H == 256 with M <= 128; slot % 128 == 0.
- * Rows in [len[b], slot) must hold FINITE values (their probabilities are exactly zero; 0 x NaN would poison the accumulator).
+ * Rows in [len[b], slot) may hold anything (masked; zeroed in shared memory before the value product of a ragged tile).
  * Kernels: f2a_fused_t.cu (rows on the M side of both MMAs; H = 512, and H = 256 up to 80 tokens), f2a_fused.cu (tokens on the
  * M side; H = 256).  Results are bit-reproducible and do not depend on the batch a video is in. */
 int factk_f2a_fused_supported(int M, int H, int slot);

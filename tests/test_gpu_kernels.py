@@ -492,7 +492,7 @@ def test_f2a_fused(M, H, slot, lens, qscale, ramp):
     hid_dim 256 with more than 80 tokens): S = qt rows^T -> softmax over the rows (online, 2048-row CTAs) -> weighted row sum in
     one tcgen05 kernel + the split combine, against fp64 torch on the same bf16 operands.  ``ramp`` adds a trend along the rows
     so that the running maximum keeps growing (positive: the accumulator rescale path) or the first tile dominates (negative);
-    rows past len[b] hold large finite garbage (they get exact-zero probabilities)."""
+    rows past len[b] hold NaN (they must not reach the accumulator)."""
     B = len(lens)
     bf = torch.bfloat16
     assert ops.f2a_fused_ok(M, H, slot)
@@ -505,7 +505,7 @@ def test_f2a_fused(M, H, slot, lens, qscale, ramp):
     rows, qt = rows.to(bf), qt.to(bf)
     rows_dev = rows.clone()
     for b, T in enumerate(lens):
-        rows_dev[b, T:] = 1.0e4
+        rows_dev[b, T:] = float('nan')
     out = torch.full((B, M, H), float('nan'), device=DEV)
     ws = torch.empty(ops.f2a_fused_ws(B, slot, M, H), device=DEV)
     ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
