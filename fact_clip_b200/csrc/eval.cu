@@ -6,7 +6,7 @@
 
 namespace factk {
 
-constexpr int EV_WARPS = 8, EV_FRAMES = 64, EV_MAXM = 512;
+constexpr int EV_WARPS = 8, EV_FRAMES = 256, EV_MAXM = 512;   // 256 frames per CTA: the per-CTA token statistics (M rows) are amortised over 4x more frames than with 64
 
 __global__ void __launch_bounds__(EV_WARPS * 32) fuse_eval_kernel(const float* __restrict__ aclogit,
                                                                   const float* __restrict__ attn, int lda, int attn_slot,
