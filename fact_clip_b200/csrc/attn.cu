@@ -273,6 +273,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int DH, bool QSPLIT>
 __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restrict__ Q, int ldq,
                                                             const __nv_bfloat16* __restrict__ Kx,
@@ -293,7 +299,8 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
     const int r1 = min(r0 + SPLIT_ROWS, len_b);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
     const int m_lo = qb * 128 + warp * 16 + g, m_hi = m_lo + 8;   // up to 8 warps x 16 queries per CTA
-    const float scale = rsqrtf((float)DH);
+    // logits in log2 units (log2(e) folded into the query scale): one ex2.approx per probability, no multiply
+    const float scale = rsqrtf((float)DH) * 1.4426950408889634f;
 
     // Q fragments (A operand, row-major 16 x DH), scaled, bf16
     // (queries are fp32: split q = hi + lo into two bf16 fragments so the logits only carry the keys' rounding)
@@ -365,13 +372,18 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
                 if constexpr (QSPLIT) mma_bf16_16816(sacc[j], qb_lo[ks], b0, b1);
             }
         }
-        // mask frames beyond the split, online softmax (rows g and g+8 of this warp's tile)
+        // mask frames beyond the split (only its last tile can be ragged), online softmax (rows g and g+8 of this warp's tile)
+        if (t0 + TR > r1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int t = t0 + j * 8 + tig * 2;
+                if (t >= r1) { sacc[j][0] = -INFINITY; sacc[j][2] = -INFINITY; }
+                if (t + 1 >= r1) { sacc[j][1] = -INFINITY; sacc[j][3] = -INFINITY; }
+            }
+        }
         float nm_lo = mx_lo, nm_hi = mx_hi;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int t = t0 + j * 8 + tig * 2;
-            if (t >= r1) { sacc[j][0] = -INFINITY; sacc[j][2] = -INFINITY; }
-            if (t + 1 >= r1) { sacc[j][1] = -INFINITY; sacc[j][3] = -INFINITY; }
             nm_lo = fmaxf(nm_lo, fmaxf(sacc[j][0], sacc[j][1]));
             nm_hi = fmaxf(nm_hi, fmaxf(sacc[j][2], sacc[j][3]));
         }
@@ -379,20 +391,22 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
         nm_lo = fmaxf(nm_lo, __shfl_xor_sync(0xffffffffu, nm_lo, 2));
         nm_hi = fmaxf(nm_hi, __shfl_xor_sync(0xffffffffu, nm_hi, 1));
         nm_hi = fmaxf(nm_hi, __shfl_xor_sync(0xffffffffu, nm_hi, 2));
-        const float c_lo = __expf(mx_lo - nm_lo), c_hi = __expf(mx_hi - nm_hi);   // exp(-inf) = 0 on the first tile
-        l_lo *= c_lo; l_hi *= c_hi;
+        if (__any_sync(0xffffffffu, nm_lo != mx_lo || nm_hi != mx_hi)) {           // a running maximum moved: rescale (rare after the
+            const float c_lo = ex2_approx(mx_lo - nm_lo), c_hi = ex2_approx(mx_hi - nm_hi);   // first tiles); 2^(-inf) = 0 on the first tile
+            l_lo *= c_lo; l_hi *= c_hi;
 #pragma unroll
-        for (int i = 0; i < NT; ++i) { o[i][0] *= c_lo; o[i][1] *= c_lo; o[i][2] *= c_hi; o[i][3] *= c_hi; }
-        mx_lo = nm_lo; mx_hi = nm_hi;
+            for (int i = 0; i < NT; ++i) { o[i][0] *= c_lo; o[i][1] *= c_lo; o[i][2] *= c_hi; o[i][3] *= c_hi; }
+            mx_lo = nm_lo; mx_hi = nm_hi;
+        }
         // P = exp(S - max) packed straight into A fragments; O += P V
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             uint32_t pa[4];
             {
-                const float p00 = __expf(sacc[2 * kk][0] - nm_lo), p01 = __expf(sacc[2 * kk][1] - nm_lo);
-                const float p10 = __expf(sacc[2 * kk][2] - nm_hi), p11 = __expf(sacc[2 * kk][3] - nm_hi);
-                const float q00 = __expf(sacc[2 * kk + 1][0] - nm_lo), q01 = __expf(sacc[2 * kk + 1][1] - nm_lo);
-                const float q10 = __expf(sacc[2 * kk + 1][2] - nm_hi), q11 = __expf(sacc[2 * kk + 1][3] - nm_hi);
+                const float p00 = ex2_approx(sacc[2 * kk][0] - nm_lo), p01 = ex2_approx(sacc[2 * kk][1] - nm_lo);
+                const float p10 = ex2_approx(sacc[2 * kk][2] - nm_hi), p11 = ex2_approx(sacc[2 * kk][3] - nm_hi);
+                const float q00 = ex2_approx(sacc[2 * kk + 1][0] - nm_lo), q01 = ex2_approx(sacc[2 * kk + 1][1] - nm_lo);
+                const float q10 = ex2_approx(sacc[2 * kk + 1][2] - nm_hi), q11 = ex2_approx(sacc[2 * kk + 1][3] - nm_hi);
                 l_lo += p00 + p01 + q00 + q01;
                 l_hi += p10 + p11 + q10 + q11;
                 pa[0] = pack_bf16(p00, p01); pa[1] = pack_bf16(p10, p11);
@@ -416,13 +430,13 @@ __global__ void __launch_bounds__(256) attn_rows_mma_kernel(const float* __restr
     float* base = part + (((size_t)b * nhead + h) * nsplit + sp) * M * (DH + 2);
     if (m_lo < M) {
         float* p = base + (size_t)m_lo * (DH + 2);
-        if (tig == 0) { p[0] = mx_lo; p[1] = l_lo; }
+        if (tig == 0) { p[0] = mx_lo * 0.6931471805599453f; p[1] = l_lo; }      // back to natural-log units for the combine kernel
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { p[2 + nt * 8 + tig * 2] = o[nt][0]; p[2 + nt * 8 + tig * 2 + 1] = o[nt][1]; }
     }
     if (m_hi < M) {
         float* p = base + (size_t)m_hi * (DH + 2);
-        if (tig == 0) { p[0] = mx_hi; p[1] = l_hi; }
+        if (tig == 0) { p[0] = mx_hi * 0.6931471805599453f; p[1] = l_hi; }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { p[2 + nt * 8 + tig * 2] = o[nt][2]; p[2 + nt * 8 + tig * 2 + 1] = o[nt][3]; }
     }
