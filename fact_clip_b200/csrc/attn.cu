@@ -452,8 +452,10 @@ __global__ void attn_rows_combine_kernel(const float* __restrict__ part, float* 
         const int m = i / DH, d = i % DH;
         const float* p0 = part + (((size_t)b * nhead + h) * nsplit * M + m) * (DH + 2);
         float gm = -INFINITY;
-        for (int s = 0; s < ns; ++s) gm = fmaxf(gm, p0[(size_t)s * M * (DH + 2)]);
+#pragma unroll 8
+        for (int s = 0; s < ns; ++s) gm = fmaxf(gm, p0[(size_t)s * M * (DH + 2)]);      // (unrolled: the loads of the splits are independent)
         float l = 0.f, a = 0.f;
+#pragma unroll 8
         for (int s = 0; s < ns; ++s) {
             const float* p = p0 + (size_t)s * M * (DH + 2);
             const float w = __expf(p[0] - gm);
