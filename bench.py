@@ -312,7 +312,10 @@ def run_train(args):
     net = net.to(dev).train()
     net.mcriterion = MatchCriterion(cfg, ncls, [0])
     net.train_graphs = not args.no_graph
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=0.0)          # epic-kitchens.yaml:74-80
+    # torch's own Adam (scripts/train.py builds torch.optim.Adam, epic-kitchens.yaml:74-80); fused=True is its single multi-tensor
+    # kernel instead of the foreach chain -- same update rule (clip + step 2.0 -> 1.4 ms); FACTK_FUSED_ADAM=0 selects torch's default
+    adam_kw = dict(fused=True) if os.environ.get('FACTK_FUSED_ADAM', '1') != '0' else {}
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=0.0, **adam_kw)
     red = GradAllReducer()
     net.grad_ready_hook = red.on_bucket
     nparam = sum(p.numel() for p in net.parameters())
