@@ -395,6 +395,53 @@ def test_full_size_batch_invariance_and_determinism(lens):
         assert alone[0]['pred'].shape == (lens[i],)
 
 
+def test_batches_in_flight_on_three_lanes_match_one_stream():
+    """The resident loop of bench.py: consecutive independent batches on several streams, each with its own activation arena and
+    CUDA graph (engine.lane).  Three different batches launched back to back on three lanes give bit-identical predictions and
+    logits to the same batches run one after the other on one stream, on the first (capture) pass and on the replays."""
+    cfg = C.PRESETS['havid_view0_lh_pt_holdout']()
+    torch.manual_seed(0)
+    net = FACT_CLIP(cfg, 2048, 75, make_text_embeddings(75)).eval()
+    net.compute_mode = 'bf16'
+    net = net.to(DEV)
+    eng = net.engine()
+    lens = [640, 512, 300]
+    batches = []
+    for k in range(3):
+        xs, _ = make_batch(lens, 2048, 75, base_seed=300 + 10 * k, nseg=8)
+        x = torch.zeros(len(lens), 640, 2048, dtype=torch.bfloat16, device=DEV)
+        for b, v in enumerate(xs):
+            x[b, :lens[b]] = v.to(DEV)
+        batches.append(x)
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+
+    def snapshot(out):
+        return out['pred'].clone(), out['blocks'][-1]['frame_clogit'].clone()
+
+    eng.lane = 0
+    ref = []
+    for x in batches:
+        ref.append(snapshot(eng.run_packed_graphed(x, ln, lens)))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    for rep in range(3):                                   # capture pass, then replays
+        outs = []
+        for k, x in enumerate(batches):
+            eng.lane = k
+            streams[k].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[k]):
+                outs.append(eng.run_packed_graphed(x, ln, lens))
+        eng.lane = 0
+        for s_ in streams:
+            torch.cuda.current_stream().wait_stream(s_)
+        torch.cuda.synchronize()
+        for k, out in enumerate(outs):
+            pred, logit = snapshot(out)
+            for b, T in enumerate(lens):
+                assert torch.equal(pred[b, :T], ref[k][0][b, :T]), (rep, k, b)
+                assert torch.equal(logit[b, :T], ref[k][1][b, :T]), (rep, k, b)
+
+
 def test_sweep_shard_forward_gather_metrics():
     """tools/sweep.py at world size 1: length-balanced shard -> pipelined forward -> prediction gather -> metrics dict."""
     sys.path.insert(0, os.path.join(ROOT, 'tools'))
