@@ -16,6 +16,8 @@
 // producer (4-stage ring of [64 rows x 256 channels]), warp 1 issues S = Q X^T, warp 2 issues O += P X, warps 4-11 = softmax /
 // epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the 64 columns of a tile).  Every split writes (max, sum) and the unnormalised O per token;
 // f2a_combine_kernel merges the splits in a fixed order (bit-reproducible, batch invariant).
+// This token-major kernel serves hid_dim 256 (with more than 80 tokens by default); hid_dim 512 -- every shipped configuration --
+// runs the transposed kernel of f2a_fused_t.cu (rows on the M side), whose header explains why.  factk_f2a_fused dispatches.
 #include <cstdlib>
 
 #include "common.cuh"
