@@ -72,6 +72,22 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(lib.factk_last_error(), bytes)
 
 
+def test_fused_cross_attention_shape_support_is_host_logic():
+    """The shape predicates of the fused X2Y kernels run on the host (no GPU): f2a serves hid_dim 512 up to 80 tokens (the 512 TMEM
+    columns hold H / 128 output tiles + two logit buffers of N token columns) and hid_dim 256 up to 128 tokens; the workspace holds
+    (max, sum) and an H-wide partial per token and 2048-row split."""
+    lib = _lib.load()
+    ok = lambda M, H, slot: bool(lib.factk_f2a_fused_supported(M, H, slot))
+    assert ok(75, 512, 4096) and ok(80, 512, 128) and ok(1, 512, 256)
+    assert not ok(81, 512, 4096)            # 96 token columns x (4 + 2) tiles > 512 TMEM columns
+    assert ok(128, 256, 1024) and ok(96, 256, 128) and not ok(129, 256, 1024)
+    assert not ok(75, 384, 4096) and not ok(75, 512, 4100) and not ok(0, 512, 4096)
+    B, slot, M, H = 3, 4096, 75, 512
+    ns = (slot + 2047) // 2048
+    assert lib.factk_f2a_fused_ws_floats(B, slot, M, H) >= B * ns * M * (H + 2)
+    assert bool(lib.factk_a2f_fused_supported(75, 512, 256, 4096)) and not bool(lib.factk_a2f_fused_supported(75, 512, 200, 4096))
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip('CUDA present')
